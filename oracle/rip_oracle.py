@@ -1,0 +1,561 @@
+"""CPU ORACLE for the L1->L2 calibration hot path and the forward ramp model.  TEST INFRASTRUCTURE ONLY.
+
+This file is a NumPy restatement of the reference algorithm.  It exists only so that the CUDA path can be
+checked; nothing under ``romanimpreprocess_b200/`` may import it (only ``tests/``, ``__graft_entry__.smoke()``
+and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` do).
+
+Every function cites the reference lines it follows (paths relative to the reference checkout).  The op order
+and dtypes follow SURVEY.md Appendix A so that, run under the same NumPy, results are bit-identical to the
+reference's own functions; this is *pinned*: ``tests/golden/make_golden.py`` imports the unmodified reference
+modules (with ``asdf`` / ``roman_datamodels`` stubbed) and stores their outputs, ``tests/test_oracle_golden.py``
+compares.  Calibration data are passed as arrays / in-memory trees instead of ASDF file names.
+
+PARITY UNPINNED for the third-party steps whose source is not in the reference tree (romancal ``do_dqinit``,
+``flag_saturation`` -> stcal ``flag_saturated_pixels``, ``subtract_dark_current``, ``_create_image_model``,
+romanisim ``apportion_counts_to_resultants`` / ``add_read_noise_to_resultants``): functions ``dq_init``,
+``flag_saturation``, ``subtract_dark_current``, ``apportion_counts`` and ``add_read_noise`` below restate the
+behaviour recorded in SURVEY.md Appendix D (from the reference's call sites and docs); the reference holds no
+golden vector for them.
+"""
+
+import numpy as np
+
+DO_NOT_USE = np.uint32(1)
+SATURATED = np.uint32(2)
+JUMP_DET = np.uint32(4)
+AD_FLOOR = np.uint32(64)
+NO_FLAT_FIELD = np.uint32(2**18)
+NO_GAIN_VALUE = np.uint32(2**19)
+NO_LIN_CORR = np.uint32(2**20)
+NO_SAT_CHECK = np.uint32(2**21)
+REFERENCE_PIXEL = np.uint32(2**31)
+
+NSIDE = 4096
+CHANNELWIDTH = 128
+
+# ---------------------------------------------------------------------------------------------------------
+# IPC   (reference src/romanimpreprocess/utils/ipc_linearity.py:37-186)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def ipc_fwd(image, kernel, gain=None):
+    """9-tap source-indexed IPC convolution; accumulation order of ipc_linearity.py:69-99."""
+    im = image if gain is None else gain * image
+    out = im * kernel[1, 1]
+    out[1:, :] += im[:-1, :] * kernel[2, 1, :-1, :]
+    out[:-1, :] += im[1:, :] * kernel[0, 1, 1:, :]
+    out[:, 1:] += im[:, :-1] * kernel[1, 2, :, :-1]
+    out[:, :-1] += im[:, 1:] * kernel[1, 0, :, 1:]
+    out[1:, 1:] += im[:-1, :-1] * kernel[2, 2, :-1, :-1]
+    out[1:, :-1] += im[:-1, 1:] * kernel[2, 0, :-1, 1:]
+    out[:-1, 1:] += im[1:, :-1] * kernel[0, 2, 1:, :-1]
+    out[:-1, :-1] += im[1:, 1:] * kernel[0, 0, 1:, 1:]
+    if gain is not None:
+        out /= gain
+    return out
+
+
+def ipc_rev(image, kernel, order=2, gain=None):
+    """Iterative deconvolution out <- out + image - K*out (ipc_linearity.py:134-142)."""
+    im2 = image if gain is None else gain * image
+    out = np.copy(im2)
+    for _ in range(order):
+        out = out + im2 - ipc_fwd(out, kernel)
+    if gain is not None:
+        out /= gain
+    return out
+
+
+def correct_cube(data, kernel, gain_full=None):
+    """In-place IPC correction of the active region of every group (ipc_linearity.py:176-186)."""
+    ngrp, ny, nx = data.shape
+    nb = (8192 + (nx - kernel.shape[-1]) // 2) % 16
+    g = 1.0 if gain_full is None else np.copy(gain_full[nb : ny - nb, nb : nx - nb])
+    for i in range(ngrp):
+        data[i, nb : ny - nb, nb : nx - nb] = ipc_rev(data[i, nb : ny - nb, nb : nx - nb] * g, kernel) / g
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Legendre linearity (ipc_linearity.py:192-392)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def lin_eval(z, coefs, linextrap=True):
+    """phi = sum_L c_L P_L(z), linear extrapolation for |z|>1 (ipc_linearity.py:215-231)."""
+    ex = np.abs(z) > 1
+    phi = np.copy(coefs[0])
+    prev = np.ones_like(phi)
+    cur = np.copy(z)
+    for L in range(1, coefs.shape[0]):
+        if linextrap:
+            phi += coefs[L] * np.where(ex, np.sign(z) ** L * (1 + L * (L + 1) / 2.0 * (np.abs(z) - 1)), cur)
+        else:
+            phi += coefs[L] * cur
+        nxt = (2 * L + 1) / (L + 1) * z * cur - L / (L + 1) * prev
+        prev = cur
+        cur = nxt
+    return phi, ex
+
+
+def linearity(S, lin, origin=(0, 0)):
+    """Single-frame linearity (ipc_linearity.py:261-273); ``lin`` is the ``roman`` branch of the lin file."""
+    dy, dx = S.shape
+    y0, x0 = origin[1], origin[0]
+    Smin = lin["Smin"][y0 : y0 + dy, x0 : x0 + dx]
+    Smax = lin["Smax"][y0 : y0 + dy, x0 : x0 + dx]
+    phi, ex = lin_eval(-1 + 2 * (S - Smin) / (Smax - Smin), lin["data"][:, y0 : y0 + dy, x0 : x0 + dx])
+    dq = np.copy(lin["dq"][y0 : y0 + dy, x0 : x0 + dx])
+    dq |= np.where(ex, NO_LIN_CORR, 0).astype(np.uint32)
+    return phi, dq
+
+
+def multilin(S, lin, origin=(0, 0), do_not_flag_first=True, attempt_corr=None):
+    """Multi-group linearity with DQ (ipc_linearity.py:313-344)."""
+    ngrp, dy, dx = S.shape
+    y0, x0 = origin[1], origin[0]
+    if attempt_corr is None:
+        attempt_corr = np.ones((ngrp, dy, dx), dtype=bool)
+    phi = np.zeros(S.shape, dtype=np.float32)
+    Smin = lin["Smin"][y0 : y0 + dy, x0 : x0 + dx]
+    Smax = lin["Smax"][y0 : y0 + dy, x0 : x0 + dx]
+    Sref = lin["Sref"][y0 : y0 + dy, x0 : x0 + dx]
+    coefs = lin["data"][:, y0 : y0 + dy, x0 : x0 + dx]
+    dq = np.copy(lin["dq"][y0 : y0 + dy, x0 : x0 + dx])
+    for j in range(ngrp):
+        z = -1 + 2 * (S[j] - Smin) / (Smax - Smin)
+        if j == 0 and do_not_flag_first:
+            z = np.clip(z, -1, 1)
+        p, ex = lin_eval(z, coefs)
+        phi[j] = p
+        phi[j] = np.where(dq & (NO_LIN_CORR | REFERENCE_PIXEL) == 0, phi[j], S[j] - Sref)
+        if not (j == 0 and do_not_flag_first):
+            dq |= np.where(np.logical_and(ex, attempt_corr[j]), NO_LIN_CORR, 0).astype(np.uint32)
+    return phi, dq
+
+
+def invlinearity(Slin, lin, origin=(0, 0)):
+    """24-step bisection inverse of the Legendre map (ipc_linearity.py:374-392)."""
+    dy, dx = Slin.shape
+    y0, x0 = origin[1], origin[0]
+    coefs = lin["data"][:, y0 : y0 + dy, x0 : x0 + dx]
+    z = np.zeros_like(Slin)
+    for j in range(1, 25):
+        phi, ex = lin_eval(z, coefs, linextrap=False)
+        z += np.where(phi < Slin, 1 / 2**j, -1 / 2**j)
+    Smin = lin["Smin"][y0 : y0 + dy, x0 : x0 + dx]
+    Smax = lin["Smax"][y0 : y0 + dy, x0 : x0 + dx]
+    return Smin + (Smax - Smin) / 2.0 * (1 + z), ex
+
+
+def il_apply(counts, lin, gain_full, ipc_kernel, start_e=0.0, electrons=True, electrons_out=False):
+    """IL.apply: IPC -> /gain -> inverse linearity (ipc_linearity.py:461-513)."""
+    conv = ipc_fwd(counts + start_e, ipc_kernel) if ipc_kernel is not None else counts + start_e
+    nyc, nxc = counts.shape
+    g_in = 1.0
+    g_out = 1.0
+    if electrons or electrons_out:
+        g = gain_full
+        if g.shape[0] > nyc:
+            b = (g.shape[0] - nyc) // 2
+            g = g[b:-b, b:-b]
+        if electrons:
+            g_in = g
+        if electrons_out:
+            g_out = g
+    nb = (8192 - nyc // 2) % 16
+    S, _ = invlinearity(conv / g_in, lin, origin=(nb, nb))
+    if not electrons_out:
+        return S
+    return g_out * (S - lin["Sref"][nb : nb + nyc, nb : nb + nxc])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Reference-pixel correction (utils/reference_subtraction.py:16-125, L1_to_L2/gen_cal_image.py:531-556)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def ref_subtraction_row(image, use_ref_channel=False, slope=None):
+    """Row correction from per-row reference medians (reference_subtraction.py:104-125).  In place."""
+    ny = image.shape[0]
+    if use_ref_channel:
+        ref_med = np.median(image[:, NSIDE : NSIDE + CHANNELWIDTH], axis=1)
+    else:
+        ref_med = np.median(np.hstack((image[:, 0:4], image[:, NSIDE - 4 : NSIDE])), axis=1)
+    ref_med = np.asarray(ref_med)
+    if slope is None:
+        sci_med = np.median(image[:, 4 : NSIDE - 4], axis=1)
+        m_med, _ = np.polyfit(ref_med, sci_med, 1)
+    else:
+        m_med = slope
+    ctr = np.median(ref_med)
+    image[:, :] = image - (m_med * (ref_med - ctr))[:, None]
+    assert ny == NSIDE
+    return image
+
+
+def ref_subtraction_channel(image, use_ref_channel=False):
+    """Per-128-column-channel line through bottom/top reference medians (reference_subtraction.py:45-74)."""
+    nch = 33 if use_ref_channel else 32
+    rows = np.arange(NSIDE)
+    for c in range(nch):
+        ch = image[:, 128 * c : 128 * (c + 1)]
+        bottom = np.median(ch[0:4, :])
+        top = np.median(ch[4092:4096, :])
+        A = np.vstack([(1.5, 4093.5), np.ones(2)]).T
+        m_cor, c_cor = np.linalg.lstsq(A, (bottom, top), rcond=None)[0]
+        ch[:, :] = ch - (m_cor * rows + c_cor)[:, None]
+    return image
+
+
+def optimal_refout_slope(read):
+    """The once-per-exposure reference-output coefficient (gen_cal_image.py:542-553); np.float64."""
+    a = read["amp33"]
+    cvar = read["anc"]["C_PINK"] ** 2
+    return a["M_PINK"] * cvar / (a["M_PINK"] ** 2 * cvar + a["RU_PINK"] ** 2 + np.median(a["std"]) ** 2 / 128 / np.log(4096))
+
+
+def refpix_loop(data, amp33, dark_cube, read):
+    """The per-group reference-pixel loop of calibrateimage (gen_cal_image.py:530-556).  data f32 in place."""
+    ngrp = data.shape[0]
+    slope = optimal_refout_slope(read)
+    for j in range(ngrp):
+        image = np.zeros((NSIDE, NSIDE + CHANNELWIDTH), dtype=np.float32)
+        image[:, :NSIDE] = data[j] - dark_cube[j]
+        image[:, -CHANNELWIDTH:] = amp33[j] - read["amp33"]["med"]
+        image[:, -CHANNELWIDTH:] -= np.median(image[:, -CHANNELWIDTH:])
+        image = ref_subtraction_row(image, use_ref_channel=True, slope=slope)
+        image = ref_subtraction_channel(image, use_ref_channel=True)
+        data[j] = image[:, :NSIDE] + dark_cube[j]
+    return data
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Ramp fitting (utils/fitting.py:20-355)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def construct_weights(u, meta, exclude_first=True):
+    """Fixed optimal weights (fitting.py:63-86)."""
+    K = np.zeros(meta["ngrp"])
+    start = 1 if exclude_first else 0
+    ngrp = meta["ngrp"] - start
+    tbar = meta["tbar"][start:].astype(np.float64)
+    tau = meta["tau"][start:].astype(np.float64)
+    C = np.zeros((ngrp, ngrp))
+    for i in range(ngrp):
+        C[i, i] = 1.0 / meta["N"][start + i] + u * tau[i]
+        for j in range(i):
+            C[i, j] = C[j, i] = u * tbar[j]
+    W = np.linalg.inv(C)
+    Ws = np.sum(W, axis=0)
+    Wt = W @ tbar
+    F0 = np.sum(W)
+    F1 = np.sum(Wt)
+    F2 = np.dot(tbar, Wt)
+    D = F0 * F2 - F1**2
+    K[start:] = (F0 * Wt - F1 * Ws) / D
+    return K.astype(np.float32)
+
+
+def jump_detect(data, rdq, pdq, meta, gain, read, exclude_first=True, truncate_ramp=None):
+    """Slope, errors and Sharma-Casertano jump flags (fitting.py:157-255).  rdq updated in place."""
+    ngrp = meta["ngrp"]
+    ny, nx = pdq.shape
+    start = 1 if exclude_first else 0
+    K = meta["K"]
+    if truncate_ramp is not None:
+        ngrp = truncate_ramp
+        K = np.zeros(ngrp, dtype=np.float32)
+        K[-1] = 1.0 / (meta["tbar"][ngrp - 1] - meta["tbar"][start])
+        K[start] = -K[-1]
+    SthreshA, SthreshB, IthreshA, IthreshB = 5.5, 4.5, 1.0, 1000.0
+    jp = meta.get("jump_detect_pars", {})
+    SthreshA = float(jp.get("SthreshA", SthreshA))
+    SthreshB = float(jp.get("SthreshB", SthreshB))
+    IthreshA = float(jp.get("IthreshA", IthreshA))
+    IthreshB = float(jp.get("IthreshB", IthreshB))
+
+    slope = np.einsum("t,tij->ij", K, data[:ngrp] - data[1][None]).astype(np.float32)
+    smap = np.zeros((2 * (ngrp - start) - 3, ny, nx), dtype=np.float32)
+    coef = 0.0
+    for i in range(start, ngrp):
+        coef += K[i] ** 2 * meta["tau"][i]
+        for j in range(start, i):
+            coef += 2.0 * K[i] * K[j] * meta["tbar"][j]
+    dvardt = np.clip(slope / np.clip(gain, 1e-4, 1e4), 0.0, None)
+    err_p = np.sqrt(np.clip(coef * dvardt, 0, None)).astype(np.float32)
+    sig2read = read**2
+    err_r = (read * np.sqrt(np.sum(K**2 / np.array(meta["N"][:ngrp])))).astype(np.float32)
+
+    x = np.clip(slope, IthreshA, IthreshB)
+    x = np.log(x / IthreshA) / np.log(IthreshB / IthreshA)
+    sthresh = SthreshA + (SthreshB - SthreshA) * x
+    nb = meta["nborder"]
+    sl = 0
+    for i in range(start, ngrp - 1):
+        dimax = 1 if (i == ngrp - 2 or ngrp - 1 - start == 2) else 2
+        for di in range(1, 1 + dimax):
+            dt = meta["tbar"][i + di] - meta["tbar"][i]
+            dslope = (data[i + di] - data[i]) / dt - slope
+            w = np.zeros(ngrp)
+            w[i + di] = 1.0 / dt
+            w[i] = -1.0 / dt
+            w -= K
+            var = np.zeros((ny, nx))
+            for a in range(ngrp):
+                var += w[a] ** 2 * (dvardt * meta["tau"][a] + sig2read / np.array(meta["N"][a]))
+                for b in range(a):
+                    var += 2 * w[a] * w[b] * dvardt * meta["tbar"][b]
+            smap[sl] = dslope / np.sqrt(var).astype(np.float32)
+            rdq[i, nb : ny - nb, nb : nx - nb] |= np.where(
+                smap[sl, nb : ny - nb, nb : nx - nb] > sthresh[nb : ny - nb, nb : nx - nb], JUMP_DET, 0
+            ).astype(np.uint32)
+            sl += 1
+    return slope, err_r, err_p, smap
+
+
+def ramp_fit(data, rdq, pdq, meta, gain, read, exclude_first=True):
+    """Full fit + saturation-truncated refits + DQ propagation (fitting.py:310-355).  rdq, pdq in place."""
+    loc = np.zeros_like(rdq)
+    slope, err_r, err_p, _ = jump_detect(data, loc, pdq, meta, gain, read, exclude_first, None)
+    unsat = ~rdq[-1] & SATURATED != 0
+    rdq |= np.where(unsat[None], loc, 0)
+    start = 1 if exclude_first else 0
+    for iend in range(meta["ngrp"] - 1, 2 + start, -1):
+        layer = rdq[iend] & ~rdq[iend - 1] & SATURATED != 0
+        loc[:, :, :] = 0
+        s_, r_, p_, _ = jump_detect(data, loc, pdq, meta, gain, read, exclude_first, iend)
+        slope = np.where(layer, s_, slope)
+        err_r = np.where(layer, r_, err_r)
+        err_p = np.where(layer, p_, err_p)
+        rdq |= np.where(layer[None], loc, 0)
+    pdq2 = np.zeros_like(pdq)
+    dnu = np.uint32(DO_NOT_USE)
+    pdq2 |= np.bitwise_or.reduce(np.where(~rdq & SATURATED, rdq, 0), axis=0) & ~dnu
+    pdq2 |= np.where(np.bitwise_and.reduce(rdq & DO_NOT_USE != 0, axis=0), dnu, 0).astype(np.uint32)
+    pdq2 |= np.where(rdq[1 + start] & SATURATED != 0, DO_NOT_USE, 0).astype(np.uint32)
+    pdq2 |= np.bitwise_or.reduce(rdq & SATURATED, axis=0)
+    pdq |= np.where(~pdq & REFERENCE_PIXEL, pdq2, 0)
+    return slope, err_r, err_p
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Flat (utils/flatutils.py:44-76)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def get_flat(flat_full, gain_full, ipc_kernel, nborder, pdq, ipc_deconvolve=True):
+    """Padded, clipped, flagged, IPC-deconvolved flat in DN units (flatutils.py:44-76).  pdq in place."""
+    ny, nx = flat_full.shape
+    nb = nborder
+    f = np.ones((ny, nx), dtype=np.float32)
+    f[nb : ny - nb, nb : nx - nb] = flat_full[nb : ny - nb, nb : nx - nb]
+    if pdq is not None:
+        pdq |= np.where(np.logical_or(f < 0.1, f > 10), NO_FLAT_FIELD, 0).astype(np.uint32)
+    f = np.clip(f, 0.1, 10)
+    if ipc_deconvolve:
+        g = gain_full[nb : ny - nb, nb : nx - nb]
+        if pdq is not None:
+            pdq[nb : ny - nb, nb : nx - nb] |= np.where(g <= 0.1, NO_GAIN_VALUE, 0).astype(np.uint32)
+            g = np.clip(g, 0.1, None)
+        f[nb : ny - nb, nb : nx - nb] = ipc_rev(f[nb : ny - nb, nb : nx - nb], ipc_kernel, gain=g)
+    return f
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Third-party steps -- RESTATEMENTS, parity unpinned
+# ---------------------------------------------------------------------------------------------------------
+
+
+def dq_init(data_u16, mask_dq, exclude_first=True):
+    """romancal do_dqinit as used at gen_cal_image.py:117-143: f32 data, pixeldq = mask dq, groupdq u8."""
+    data = data_u16.astype(np.float32)
+    pdq = np.zeros(data.shape[1:], dtype=np.uint32) if mask_dq is None else mask_dq.astype(np.uint32).copy()
+    rdq = np.zeros(data.shape, dtype=np.uint8)
+    if exclude_first:
+        rdq[0] |= np.uint8(DO_NOT_USE)
+    return data, rdq, pdq
+
+
+def _grow3(flag):
+    """3x3 box dilation of a boolean map (n_pix_grow_sat=1)."""
+    out = flag.copy()
+    out[1:, :] |= flag[:-1, :]
+    out[:-1, :] |= flag[1:, :]
+    h = out.copy()
+    out[:, 1:] |= h[:, :-1]
+    out[:, :-1] |= h[:, 1:]
+    return out
+
+
+def flag_saturation(data, rdq, pdq, sat_thresh, sat_dq, backup=1, skip_firstn=1):
+    """saturation_check -> romancal flag_saturation(n_pix_grow_sat=1, backup) (gen_cal_image.py:148-185).
+
+    Restated (docs/L1_to_L2_README.rst:87): on the raw groups ``skip_firstn..G-1``: thresholds
+    with NO_SAT_CHECK or NaN are never exceeded (pixeldq |= NO_SAT_CHECK); ``data >= thresh`` sets SATURATED in
+    that and all later groups, grown by one pixel (3x3); ``data <= 0`` sets AD_FLOOR|DO_NOT_USE in that group
+    only; then SATURATED is also set in the ``backup`` groups preceding a saturated group (never in the skipped
+    leading groups).  The group-averaging look-back passes of stcal only add DO_NOT_USE to single groups, which
+    the reference's fitter ignores unless every group has it; they are not restated.
+    """
+    G = data.shape[0]
+    thr = sat_thresh.astype(np.float32).copy()
+    nocheck = (sat_dq & NO_SAT_CHECK) != 0
+    nocheck |= np.isnan(thr)
+    thr[nocheck] = np.inf
+    pdq |= np.where((sat_dq & NO_SAT_CHECK) != 0, NO_SAT_CHECK, 0).astype(np.uint32)
+    cum = np.zeros(data.shape[1:], dtype=bool)
+    sat = np.zeros(data.shape, dtype=bool)
+    for g in range(skip_firstn, G):
+        cum |= data[g] >= thr
+        sat[g] = _grow3(cum)
+        rdq[g] |= np.where(data[g] <= 0, np.uint8(AD_FLOOR | DO_NOT_USE), np.uint8(0))
+    if backup > 0:
+        s2 = sat.copy()
+        for g in range(skip_firstn, G):
+            for b in range(1, backup + 1):
+                if g + b < G:
+                    s2[g] |= sat[g + b]
+        sat = s2
+    rdq |= np.where(sat, np.uint8(SATURATED), np.uint8(0))
+    return rdq, pdq
+
+
+def subtract_dark_current(slope_full, dq_full, dark_slope_ipc, dark_dq, nb=4):
+    """romancal subtract_dark_current on the active region (gen_cal_image.py:223-229): data -= dark; dq |= dark dq."""
+    slope_full[nb:-nb, nb:-nb] -= dark_slope_ipc[nb:-nb, nb:-nb]
+    dq_full[nb:-nb, nb:-nb] |= dark_dq[nb:-nb, nb:-nb]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The whole L1 -> L2 numerics chain (gen_cal_image.py:480-629, 697-709)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def make_meta(read_pattern, frame_time):
+    """N, tbar, tau (gen_cal_image.py:123-140)."""
+    ngrp = len(read_pattern)
+    meta = {"frame_time": frame_time, "read_pattern": read_pattern, "ngrp": ngrp, "nborder": 4}
+    meta["tbar"] = np.zeros(ngrp, dtype=np.float32)
+    meta["tau"] = np.zeros(ngrp, dtype=np.float32)
+    meta["N"] = np.zeros(ngrp, dtype=np.int16)
+    for i in range(ngrp):
+        meta["N"][i] = len(read_pattern[i])
+        t0 = read_pattern[i][0]
+        meta["tbar"][i] = (t0 + (meta["N"][i] - 1) / 2.0) * frame_time
+        meta["tau"][i] = (t0 + (meta["N"][i] - 1) * (2 * meta["N"][i] - 1) / (6.0 * meta["N"][i])) * frame_time
+    return meta
+
+
+def l1_to_l2(data_u16, amp33_u16, cal, read_pattern, frame_time, area_factor, config=None, do_refpix=True,
+             return_intermediates=False):  # fmt: skip
+    """calibrateimage numerics from L1 arrays to L2 arrays (gen_cal_image.py:503-629,697-709).
+
+    ``cal`` maps CALDIR keys to the ``roman`` branches.  Returns a dict with slope, err_read, err_poisson, pdq
+    (all full frame [n,n]), rdq [G,n,n] u8, endslice i8 [n-8,n-8], K, and optionally the intermediate cubes.
+    ``do_refpix=False`` skips the 4096-only reference-pixel loop (small-frame tests).
+    """
+    config = config or {}
+    nb = 4
+    exclude_first = config.get("EXCLUDE_FIRST", True)
+    backup = config.get("SATURATION_BACKUP", 1)
+    meta = make_meta(read_pattern, frame_time)
+    mask_dq = cal["mask"]["dq"] if "mask" in cal else None
+    data, rdq, pdq = dq_init(data_u16, mask_dq, exclude_first)
+    flag_saturation(data, rdq, pdq, cal["saturation"]["data"], cal["saturation"]["dq"], backup=backup)
+    ngrp = data.shape[0]
+    inter = {}
+    if do_refpix:
+        refpix_loop(data, amp33_u16, cal["dark"]["data"], cal["read"])
+    if return_intermediates:
+        inter["refcorr"] = data.copy()
+    if "biascorr" in cal:
+        bc = cal["biascorr"]["data"]
+        de = bc.shape[0] - ngrp
+        data[:, nb:-nb, nb:-nb] -= bc[de:]
+    data, dq_lin = multilin(
+        data,
+        cal["linearitylegendre"],
+        do_not_flag_first=(list(read_pattern[0]) == [0]),
+        attempt_corr=~rdq & SATURATED,
+    )
+    pdq |= dq_lin
+    if return_intermediates:
+        inter["lin"] = data.copy()
+    if "ipc4d" in cal:
+        correct_cube(data, cal["ipc4d"]["data"], cal["gain"]["data"])
+    if return_intermediates:
+        inter["ipc"] = data.copy()
+    uopt = config.get("RAMP_OPT_PARS", {"slope": 0.4, "gain": 1.8, "sigma_read": 6.5})
+    u_ = float(uopt["slope"]) / float(uopt["gain"]) / float(uopt["sigma_read"]) ** 2
+    meta["K"] = construct_weights(u_, meta, exclude_first=exclude_first)
+    if "JUMP_DETECT_PARS" in config:
+        meta["jump_detect_pars"] = config["JUMP_DETECT_PARS"]
+    slope, err_r, err_p = ramp_fit(data, rdq, pdq, meta, cal["gain"]["data"], cal["read"]["data"], exclude_first)
+    # do_ramp_fit packaging (gen_cal_image.py:458-475): err, var_poisson, border zeroed
+    err = np.hypot(err_r, err_p)
+    varp = err_p**2
+
+    def embed(a):
+        full = np.zeros(a.shape, dtype=np.float32)
+        full[nb:-nb, nb:-nb] = a[nb:-nb, nb:-nb]
+        return full
+
+    slope = embed(slope)
+    varp = embed(varp)
+    err = embed(err)
+    # dark current (gen_cal_image.py:212-229)
+    dslope = np.array(cal["dark"]["dark_slope"], dtype=np.float32)[None]
+    if "ipc4d" in cal:
+        correct_cube(dslope, cal["ipc4d"]["data"], cal["gain"]["data"])
+    subtract_dark_current(slope, pdq, dslope[0], cal["dark"]["dq"], nb)
+    # unpack + error split (gen_cal_image.py:607-613)
+    err_p = np.sqrt(varp)
+    err_r = np.sqrt(np.clip(err**2 - err_p**2, 0.0, None))
+    # flat + area (gen_cal_image.py:616-629)
+    flat = get_flat(cal["flat"]["data"], cal["gain"]["data"], cal["ipc4d"]["data"], nb, pdq)
+    flat = (flat / area_factor).astype(np.float32)
+    slope /= flat
+    err_r /= flat
+    err_p /= flat
+    # endslice (gen_cal_image.py:697-709)
+    n = slope.shape[0]
+    endslice = np.zeros((n - 2 * nb, n - 2 * nb), dtype=np.int8) - 1
+    for iend in range(1, ngrp):
+        endslice = np.where(
+            rdq[iend, nb:-nb, nb:-nb] & ~rdq[iend - 1, nb:-nb, nb:-nb] & SATURATED != 0, iend - 1, endslice
+        )
+    out = {"slope": slope, "err_read": err_r, "err_poisson": err_p, "pdq": pdq, "rdq": rdq,
+           "endslice": endslice.astype(np.int8), "K": meta["K"], "flat": flat, "meta": meta}  # fmt: skip
+    out.update(inter)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Forward model (from_sim/sim_to_isim.py:163-262 + romanisim restatements, parity unpinned)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def read_pattern_to_tij(read_pattern, read_time=3.04):
+    """romanisim.l1.read_pattern_to_tij as used at sim_to_isim.py:204: time of each read = read_time*index."""
+    return [[read_time * r for r in grp] for grp in read_pattern]
+
+
+def forward_deterministic(mean_counts_per_read, cal, read_pattern, start_e):
+    """Noise-free forward ramp: per read IL.apply(cumulative electrons), group mean, + biascorr, round.
+
+    ``mean_counts_per_read`` [n_reads_total, na, na] cumulative electrons at each read (already apportioned).
+    Restates the deterministic part of make_l1_fullcal (sim_to_isim.py:222-260): used to check the CUDA
+    kernel's IL/bisection/group-average arithmetic exactly, with the RNG draws supplied from outside.
+    """
+    lin = cal["linearitylegendre"]
+    res = []
+    k = 0
+    for grp in read_pattern:
+        acc = None
+        for _ in grp:
+            s = il_apply(mean_counts_per_read[k], lin, cal["gain"]["data"], cal["ipc4d"]["data"], start_e=start_e)
+            acc = s if acc is None else acc + s
+            k += 1
+        res.append((acc / len(grp)).astype(np.float32))
+    return np.stack(res)

@@ -1,0 +1,47 @@
+"""pytest configuration: markers and shared fixtures."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as f:
+        return {k: f[k] for k in f.files}
+
+
+SMALL_CASES = {
+    # tag: (n, read pattern name, p_order, gain dtype, ipc dtype, seed)   -- must match tests/golden/make_golden.py
+    "small_p4_f32": (40, "TEST_READ_PATTERN", 3, np.float32, np.float32, 11),
+    "small_p11_f32": (40, "README_PATTERN", 10, np.float32, np.float32, 12),
+    "small_p4_g64": (40, "TEST_READ_PATTERN", 3, np.float64, np.float32, 13),
+    "small_p11_k64": (40, "README_PATTERN", 10, np.float32, np.float64, 14),
+}
+
+
+def build_small_case(tag):
+    """Regenerate the seeded inputs of one golden case (digest-checked against the golden file)."""
+    from romanimpreprocess_b200 import synth
+
+    n, rpname, p_order, gdt, kdt, seed = SMALL_CASES[tag]
+    rp = getattr(synth, rpname)
+    cal = synth.make_caldir(n=n, seed=seed, read_pattern=rp, p_order=p_order, gain_dtype=gdt, ipc_dtype=kdt,
+                            sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
+    data_u16, amp33_u16, meta = synth.make_l1(cal, rp, seed=seed + 1, n_sources=9, cr_frac=0.01)
+    return cal, data_u16, amp33_u16, meta, rp
+
+
+@pytest.fixture(scope="session")
+def kats():
+    return load_golden("kats")
