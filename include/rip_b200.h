@@ -1,0 +1,263 @@
+/* rip_b200.h -- C ABI of the B200 (sm_100a) implementation of romanimpreprocess's per-pixel hot path.
+ *
+ * The reference (Roman-HLIS-Cosmology-PIT/romanimpreprocess) has no FFI: the path sits behind plain Python
+ * functions on NumPy arrays.  Each entry point below replaces one of those functions and cites it
+ * (paths relative to the reference checkout).  The Python modules of `romanimpreprocess_b200/` bind these with
+ * ctypes and keep the reference's names, argument meaning, in-place semantics and exceptions; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; rip_last_error() gives the message (thread local)
+ *   - no exceptions cross the boundary, the caller owns every buffer passed in
+ *   - "host" entry points take host pointers and are synchronous (copies inside);
+ *     "_dev" entry points take device pointers + a cudaStream_t (as void*) and are asynchronous
+ *   - frames are row-major [ny][nx]; cubes [ngroup][ny][nx]; ipc4d kernels [3][3][nya][nxa]
+ *   - dtype tags: the precision of the reference's arithmetic depends on the dtype of each calibration plane
+ *     (SURVEY App. A0), so gain / ipc4d / area planes carry a tag
+ */
+#ifndef RIP_B200_H
+#define RIP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RIP_ABI_VERSION 1
+#define RIP_GMAX 16      /* max resultants (groups) per ramp on the fused path            */
+#define RIP_MAXVAR 16    /* full fit + truncated-fit variants in a ramp plan              */
+#define RIP_MAXSLICE 256 /* total single/double differences over all variants             */
+#define RIP_PMAX 16      /* max Legendre coefficients (order+1)                           */
+
+enum rip_dtype { RIP_F32 = 0, RIP_F64 = 1, RIP_I32 = 2, RIP_U16 = 3 };
+
+/* ---- ramp plan: every scalar of utils/fitting.py:jump_detect that does not depend on the pixel ------------
+ * Built by the host with the reference's own NumPy expressions (romanimpreprocess_b200/utils/fitting.py
+ * build_plan) so each value carries the reference's rounding.  Variant 0 = full ramp; variant v>=1 = ramp
+ * truncated at iend = G - v with two-point weights (reference utils/fitting.py:165-169, 326). */
+typedef struct rip_ramp_slice {
+    int32_t i, di;  /* difference data[i+di]-data[i]                    (fitting.py:225-231) */
+    float dt;       /* tbar[i+di]-tbar[i] as float32                                          */
+    float inv_dt;   /* fast path only                                                         */
+    float A, B;     /* fast path: var(delta slope) ~= dvardt*A + read^2*B     */
+} rip_ramp_slice;
+
+typedef struct rip_ramp_plan {
+    int32_t G, start, nvar, reserved;
+    float tbar[RIP_GMAX], tau[RIP_GMAX], nreads[RIP_GMAX];
+    int32_t var_ngrp[RIP_MAXVAR];
+    float var_K[RIP_MAXVAR][RIP_GMAX]; /* weights per variant (fitting.py:162-169)                    */
+    float var_coef[RIP_MAXVAR];        /* Poisson variance coefficient, f32 accumulation (:196-200)   */
+    float var_rfac[RIP_MAXVAR];        /* sqrt(sum K^2/N) as float32 (:209)                           */
+    int32_t var_slice_off[RIP_MAXVAR + 1];
+    rip_ramp_slice slices[RIP_MAXSLICE];
+    float IthreshA_f, IthreshB_f;
+    double SthreshA, SthreshB, logIratio; /* (:172-184, 215-217)                                      */
+    float band;                           /* relative half-width of the exact-recheck band            */
+    float pad_;
+} rip_ramp_plan;
+
+/* ---- one SCA's calibration reference data (CALDIR), host pointers ---------------------------*/
+typedef struct rip_caldir_desc {
+    int32_t n;          /* frame side incl. reference pixels (4096)                         */
+    int32_t nb;         /* reference-pixel border (4)                                       */
+    int32_t P;          /* Legendre coefficients = order+1                                  */
+    int32_t n_dark;     /* groups in the dark cube                                          */
+    int32_t n_bias;     /* groups in the biascorr cube, 0 = no biascorr                     */
+    int32_t gain_dtype; /* RIP_F32 | RIP_F64                                                */
+    int32_t ipc_dtype;  /* RIP_F32 | RIP_F64                                                */
+    int32_t has_amp33;  /* read file carries amp33 statistics                               */
+    const float* lin_coefs; /* [P,n,n]   linearitylegendre.data                             */
+    const float* Smin;      /* [n,n]                                                        */
+    const float* Smax;
+    const float* Sref;
+    const uint32_t* lin_dq;     /* [n,n]                                                    */
+    const uint32_t* mask_dq;    /* [n,n] or NULL                                            */
+    const float* sat_thresh;    /* [n,n]   saturation.data                                  */
+    const uint32_t* sat_dq;     /* [n,n]                                                    */
+    const void* gain;           /* [n,n]   gain.data (f32|f64)                              */
+    const void* ipc;            /* [3,3,n-2nb,n-2nb] ipc4d.data (f32|f64) or NULL           */
+    const float* read;          /* [n,n]   read.data                                        */
+    const float* resetnoise;    /* [n,n]   read.resetnoise (forward model) or NULL          */
+    const float* dark_cube;     /* [n_dark,n,n] dark.data                                   */
+    const float* dark_slope;    /* [n,n]   dark.dark_slope                                  */
+    const uint32_t* dark_dq;    /* [n,n]                                                    */
+    const float* biascorr;      /* [n_bias,n-2nb,n-2nb] or NULL                             */
+    const float* flat;          /* [n,n]   flat (pflat).data                                */
+    const float* amp33_med;     /* [n,128] or NULL                                          */
+    const float* amp33_std;     /* [n,128] or NULL                                          */
+    double biascorr_t0, m_pink, ru_pink, c_pink, u_pink;
+    double refout_slope; /* optimal reference-output coefficient (gen_cal_image.py:542-553), computed by the
+                            host with the reference's expression; NaN = derive it inside the library          */
+} rip_caldir_desc;
+
+typedef struct rip_caldir rip_caldir; /* opaque: device-resident planes + static products of one SCA */
+
+/* ---- parameters / outputs of the fused L1->L2 call ---------------------------------------------------------*/
+typedef struct rip_l1l2_params {
+    int32_t G;                  /* resultants in the L1 cube                                          */
+    int32_t exclude_first;      /* EXCLUDE_FIRST (gen_cal_image.py:142,434)                           */
+    int32_t sat_backup;         /* SATURATION_BACKUP (gen_cal_image.py:504)                           */
+    int32_t do_not_flag_first;  /* read_pattern[0]==[0] (gen_cal_image.py:583)                        */
+    int32_t do_refpix;          /* run the reference-pixel loop (needs amp33; gen_cal_image.py:531)   */
+    int32_t area_dtype;         /* RIP_F32 | RIP_F64 for the AreaFactor plane (may be NULL -> 1)      */
+    int32_t threads;            /* 0 = default tile width                                             */
+    int32_t band_rows;          /* 0 = default rows per tile                                          */
+} rip_l1l2_params;
+
+typedef struct rip_l2_out {
+    float* slope;        /* [n,n] DN/s, flat-fielded (gen_cal_image.py:627)         */
+    float* err_read;     /* [n,n]                     (:613,628)                    */
+    float* err_poisson;  /* [n,n]                     (:612,629)                    */
+    uint32_t* pdq;       /* [n,n]                                                   */
+    int8_t* endslice;    /* [n-2nb,n-2nb] or NULL     (:697-709)                    */
+    uint8_t* rdq;        /* [G,n,n] or NULL  group dq after ramp_fit                */
+    float* lin_cube;     /* [G,n,n] or NULL  data after multilin + correct_cube     */
+} rip_l2_out;
+
+/* ---- library ------------------------------------------------------------------------------------------------*/
+const char* rip_last_error(void);
+int rip_abi_version(void);
+int rip_device_count(int* count);
+int rip_device_sync(int device);
+int rip_host_alloc(void** p, size_t bytes); /* pinned host memory for full-speed async copies */
+int rip_host_free(void* p);
+int rip_dev_alloc(int device, void** p, size_t bytes);
+int rip_dev_free(int device, void* p);
+int rip_copy_h2d(int device, void* dst_dev, const void* src_host, size_t bytes, void* stream);
+int rip_copy_d2h(int device, void* dst_host, const void* src_dev, size_t bytes, void* stream);
+int rip_stream_sync(int device, void* stream);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long rip_launch_count(void);
+/* sizeof() of the ABI structs as compiled (binding self-check): 0 rip_ramp_slice, 1 rip_ramp_plan, 2 rip_caldir_desc,
+ * 3 rip_l1l2_params, 4 rip_l2_out, 5 rip_fwd_params; -1 otherwise */
+long rip_struct_size(int which);
+
+/* ---- stage entry points: one per reference function, HOST pointers, synchronous ----------------------------*/
+
+/* _lin (utils/ipc_linearity.py:192): phi = sum_L c_L P_L(z) (+ linear extrapolation), exflag = |z|>1.
+ * z f32|f64 [npix]; coefs f32 [P,npix]; phi f32 [npix]. */
+int rip_lin_eval(int device, const void* z, int z_dtype, const float* coefs, int P, long npix, int linextrap,
+                 float* phi, uint8_t* exflag);
+
+/* multilin (utils/ipc_linearity.py:276) and, with single_frame=1, linearity (:234).
+ * S f32 [G,npix]; attempt u8 [G,npix] or NULL (=all true); phi f32 [G,npix]; dq_out u32 [npix]. */
+int rip_multilin(int device, const float* S, int G, long npix, const float* coefs, int P, const float* Smin,
+                 const float* Smax, const float* Sref, const uint32_t* lin_dq, const uint8_t* attempt,
+                 int do_not_flag_first, int single_frame, float* phi, uint32_t* dq_out);
+
+/* invlinearity (utils/ipc_linearity.py:347): 24-step bisection.  Slin, S_out f32|f64 [npix]. */
+int rip_invlinearity(int device, const void* Slin, int dtype, long npix, const float* coefs, int P,
+                     const float* Smin, const float* Smax, void* S_out, uint8_t* exflag);
+
+/* ipc_fwd (utils/ipc_linearity.py:37) / ipc_rev (:102).  image [ny,nx] img_dtype; kernel [3,3,ny,nx] k_dtype;
+ * gain [ny,nx] g_dtype or NULL.  out has NumPy's promoted dtype (f64 if any input plane is f64), reported in
+ * *out_dtype; out must hold ny*nx doubles in the worst case. */
+int rip_ipc_fwd(int device, const void* image, int img_dtype, int ny, int nx, const void* kernel, int k_dtype,
+                const void* gain, int g_dtype, void* out, int* out_dtype);
+int rip_ipc_rev(int device, const void* image, int img_dtype, int ny, int nx, const void* kernel, int k_dtype,
+                int order, const void* gain, int g_dtype, void* out, int* out_dtype);
+
+/* correct_cube (utils/ipc_linearity.py:145): in-place on the active region of data f32 [G,ny,nx];
+ * kernel [3,3,ny-2nb,nx-2nb]; gain_full [ny,nx] or NULL. */
+int rip_correct_cube(int device, float* data, int G, int ny, int nx, const void* kernel, int k_dtype, int nya,
+                     int nxa, const void* gain_full, int g_dtype);
+
+/* jump_detect (utils/fitting.py:89) for plan variant `variant` (0 = truncate_ramp None).
+ * data f32 [G,ny,nx]; rdq u8 [G,ny,nx] in/out; smap f32 [nslices,ny,nx] or NULL. */
+int rip_jump_detect(int device, const float* data, uint8_t* rdq, int ny, int nx, int nb, const rip_ramp_plan* plan,
+                    const double* w_exact, int variant, const void* gain, int g_dtype, const float* read,
+                    float* slope, float* err_read, float* err_poisson, float* smap);
+
+/* ramp_fit (utils/fitting.py:258).  rdq u8 [G,ny,nx] and pdq u32 [ny,nx] in/out.  fast=1 uses the factorised
+ * variance with exact re-evaluation of borderline slices (same flags), fast=0 the exact op order throughout. */
+int rip_ramp_fit(int device, const float* data, uint8_t* rdq, uint32_t* pdq, int ny, int nx, int nb,
+                 const rip_ramp_plan* plan, const double* w_exact, const void* gain, int g_dtype,
+                 const float* read, int fast, float* slope, float* err_read, float* err_poisson);
+
+/* ref_subtraction_row (utils/reference_subtraction.py:77) in two calls (np.polyfit stays on the host):
+ * medians: image f32 [n, ncols]; ref_med[n] = per-row median of the reference output (use_ref_channel) or of the
+ * 8 side reference pixels; sci_med[n] (optional) = per-row median of columns 4..n-5. */
+int rip_row_medians(int device, const float* image, int n, int ncols, int use_ref_channel, float* ref_med,
+                    float* sci_med);
+/* apply: image[i,:] = f32(f64(image[i,:]) - m_med*(ref_med[i]-ctr)), ctr = median(ref_med) (:115-123) */
+int rip_refsub_row_apply(int device, float* image, int n, int ncols, double m_med, const float* ref_med);
+
+/* ref_subtraction_channel (utils/reference_subtraction.py:16): nchan channels of 128 columns. */
+int rip_refsub_channel(int device, float* image, int n, int ncols, int nchan);
+
+/* get_flat (utils/flatutils.py:20).  pdq u32 [n,n] in/out or NULL; out f32 [n,n]. */
+int rip_get_flat(int device, const float* flat, int n, int nb, const void* gain, int g_dtype, const void* kernel,
+                 int k_dtype, uint32_t* pdq, int ipc_deconvolve, float* out);
+
+/* saturation_check -> romancal flag_saturation (L1_to_L2/gen_cal_image.py:148-185; restated).
+ * raw u16 [G,n,n]; rdq u8 [G,n,n] in/out; pdq u32 [n,n] in/out. */
+int rip_flag_saturation(int device, const uint16_t* raw, int G, int n, const float* sat_thresh,
+                        const uint32_t* sat_dq, int backup, int skip_firstn, uint8_t* rdq, uint32_t* pdq);
+
+/* ---- CALDIR handle + fused path ------------------------------------------------------------------------------*/
+int rip_caldir_create(int device, const rip_caldir_desc* desc, rip_caldir** out);
+void rip_caldir_destroy(rip_caldir* h);
+/* static products: IPC-corrected dark slope (gen_cal_image.py:217-221), get_flat output and its
+ * flags, merged static dq; copied to host buffers (any may be NULL) for inspection/tests. */
+int rip_caldir_get_static(rip_caldir* h, float* dark_slope_ipc, float* flat_ipc, uint32_t* static_dq, double* refout_slope);
+
+/* calibrateimage numerics, L1 arrays -> L2 arrays (L1_to_L2/gen_cal_image.py:503-629, 697-709).
+ * raw u16 [G,n,n]; amp33 u16 [G,n,128] (NULL iff !do_refpix); area [n,n] or NULL. */
+int rip_l1_to_l2_host(rip_caldir* h, const uint16_t* raw, const uint16_t* amp33, const void* area,
+                      const rip_l1l2_params* prm, const rip_ramp_plan* plan, const double* w_exact,
+                      const rip_l2_out* out);
+int rip_l1_to_l2_dev(rip_caldir* h, const uint16_t* d_raw, const uint16_t* d_amp33, const void* d_area,
+                     const rip_l1l2_params* prm, const rip_ramp_plan* plan, const double* w_exact,
+                     const rip_l2_out* d_out, void* stream);
+/* Per-launch device timing of the fused kernel (bench.py's roofline): while enabled, every rip_l1_to_l2_* call on
+ * this handle brackets the fused kernel with CUDA events on its launch stream; rip_profile_fetch waits for them,
+ * returns the summed kernel time [ms] and the number of launches, and resets the counter. */
+int rip_profile_enable(rip_caldir* h, int on);
+int rip_profile_fetch(rip_caldir* h, double* fused_ms_sum, int* launches);
+/* the K0 statistics alone (tests): rowcorr f64 [G,n], chan_m/chan_c f64 [G,32] to host */
+int rip_refpix_stats_host(rip_caldir* h, const uint16_t* raw, const uint16_t* amp33, int G, double* rowcorr,
+                          double* chan_m, double* chan_c, float* gmed);
+
+/* ---- forward model (from_sim/sim_to_isim.py) ------------------------------------------------------------------*/
+
+/* IL.apply (utils/ipc_linearity.py:461-513) on explicit planes of a window [ny,nx] (HOST pointers): counts
+ * (i32|f32|f64) + start_e (f32|f64 plane, or NULL -> start_scalar) -> ipc_fwd (kernel [3,3,ny,nx] or NULL) ->
+ * /gain (if electrons) -> 24-step bisection; with electrons_out: gain*(S-Sref).  Arithmetic follows NumPy's dtype
+ * promotion (int32+f32 -> f64: SURVEY App. A10); out receives f64 values, *out_dtype the NumPy result dtype. */
+int rip_il_apply_planes(int device, const void* counts, int c_dtype, int ny, int nx, const void* start_e, int s_dtype,
+                        double start_scalar, const void* kernel, int k_dtype, const void* gain, int g_dtype,
+                        const float* coefs, int P, const float* Smin, const float* Smax, const float* Sref,
+                        int electrons, int electrons_out, double* out, int* out_dtype);
+
+/* the same on the resident planes of a CALDIR handle: counts [na,na], start_e f32 [na,na] or NULL; out f64. */
+int rip_il_apply(rip_caldir* h, const void* counts, int c_dtype, const float* start_e, int electrons,
+                 int electrons_out, double* out);
+
+typedef struct rip_fwd_params {
+    int32_t G;
+    int32_t n_reads;                   /* total reads listed in the pattern                              */
+    int32_t reads_per_group[RIP_GMAX];
+    int32_t read_index[64];            /* flattened read indices (time = read_time*index)                */
+    double read_time;
+    uint64_t seed;
+    int32_t add_read_noise, add_reset_noise, add_biascorr, quantize;
+} rip_fwd_params;
+
+/* make_l1_fullcal (from_sim/sim_to_isim.py:163-262) with romanisim's apportioning / read noise restated
+ * (SURVEY App. D): counts i32 [na,na] total electrons of the exposure -> resultants f32 [G,na,na] (DN).
+ * Reset noise, binomial apportioning of the counts to the reads, IL.apply per read (float64), group mean,
+ * read noise, + biascorr, round.  Counter-based Philox RNG (seed, pixel, purpose).
+ * cum_counts i32 [n_reads,na,na] (host entry only, tests): externally apportioned cumulative counts, replaces
+ * the binomial draws so the deterministic arithmetic can be checked exactly. */
+int rip_make_l1_host(rip_caldir* h, const int32_t* counts, const int32_t* cum_counts, const rip_fwd_params* prm,
+                     float* resultants);
+int rip_make_l1_dev(rip_caldir* h, const int32_t* d_counts, const rip_fwd_params* prm, float* d_resultants,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIP_B200_H */

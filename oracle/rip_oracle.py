@@ -175,33 +175,37 @@ def il_apply(counts, lin, gain_full, ipc_kernel, start_e=0.0, electrons=True, el
 
 
 def ref_subtraction_row(image, use_ref_channel=False, slope=None):
-    """Row correction from per-row reference medians (reference_subtraction.py:104-125).  In place."""
-    ny = image.shape[0]
+    """Row correction from per-row reference medians (reference_subtraction.py:104-125).  In place.
+
+    The reference hard-codes the 4096-pixel geometry (pars.nside); here the frame side is ``image.shape[0]`` so
+    that small frames can be used in tests -- identical at 4096 (pinned by tests/golden/refsub_4096.npz).
+    """
+    ns = image.shape[0]
     if use_ref_channel:
-        ref_med = np.median(image[:, NSIDE : NSIDE + CHANNELWIDTH], axis=1)
+        ref_med = np.median(image[:, ns : ns + CHANNELWIDTH], axis=1)
     else:
-        ref_med = np.median(np.hstack((image[:, 0:4], image[:, NSIDE - 4 : NSIDE])), axis=1)
+        ref_med = np.median(np.hstack((image[:, 0:4], image[:, ns - 4 : ns])), axis=1)
     ref_med = np.asarray(ref_med)
     if slope is None:
-        sci_med = np.median(image[:, 4 : NSIDE - 4], axis=1)
+        sci_med = np.median(image[:, 4 : ns - 4], axis=1)
         m_med, _ = np.polyfit(ref_med, sci_med, 1)
     else:
         m_med = slope
     ctr = np.median(ref_med)
     image[:, :] = image - (m_med * (ref_med - ctr))[:, None]
-    assert ny == NSIDE
     return image
 
 
 def ref_subtraction_channel(image, use_ref_channel=False):
     """Per-128-column-channel line through bottom/top reference medians (reference_subtraction.py:45-74)."""
-    nch = 33 if use_ref_channel else 32
-    rows = np.arange(NSIDE)
+    ns = image.shape[0]
+    nch = ns // CHANNELWIDTH + (1 if use_ref_channel else 0)
+    rows = np.arange(ns)
     for c in range(nch):
         ch = image[:, 128 * c : 128 * (c + 1)]
         bottom = np.median(ch[0:4, :])
-        top = np.median(ch[4092:4096, :])
-        A = np.vstack([(1.5, 4093.5), np.ones(2)]).T
+        top = np.median(ch[ns - 4 : ns, :])
+        A = np.vstack([(1.5, ns - 2.5), np.ones(2)]).T
         m_cor, c_cor = np.linalg.lstsq(A, (bottom, top), rcond=None)[0]
         ch[:, :] = ch - (m_cor * rows + c_cor)[:, None]
     return image
@@ -219,13 +223,14 @@ def refpix_loop(data, amp33, dark_cube, read):
     ngrp = data.shape[0]
     slope = optimal_refout_slope(read)
     for j in range(ngrp):
-        image = np.zeros((NSIDE, NSIDE + CHANNELWIDTH), dtype=np.float32)
-        image[:, :NSIDE] = data[j] - dark_cube[j]
+        ns = data.shape[1]
+        image = np.zeros((ns, ns + CHANNELWIDTH), dtype=np.float32)
+        image[:, :ns] = data[j] - dark_cube[j]
         image[:, -CHANNELWIDTH:] = amp33[j] - read["amp33"]["med"]
         image[:, -CHANNELWIDTH:] -= np.median(image[:, -CHANNELWIDTH:])
         image = ref_subtraction_row(image, use_ref_channel=True, slope=slope)
         image = ref_subtraction_channel(image, use_ref_channel=True)
-        data[j] = image[:, :NSIDE] + dark_cube[j]
+        data[j] = image[:, :ns] + dark_cube[j]
     return data
 
 

@@ -1,0 +1,375 @@
+"""L1 -> L2 calibration on the GPU: drop-in for the numerics of ``romanimpreprocess.L1_to_L2.gen_cal_image``.
+
+The reference driver ``calibrateimage`` (reference L1_to_L2/gen_cal_image.py:480-739) runs, per exposure,
+dq-init -> saturation flagging -> reference-pixel loop -> bias correction -> ``multilin`` -> ``correct_cube`` ->
+``do_ramp_fit`` -> ``subtract_dark_current`` -> error split -> ``get_flat``/area division -> (sky, packaging,
+I/O) -> endslice.  Everything from the raw ``uint16`` cube to the flat-fielded slope / error / DQ / endslice
+arrays (reference lines 503-629 and 697-709) is one call into ``librip_b200.so`` here
+(``rip_l1_to_l2_host`` / ``rip_l1_to_l2_dev``): a reference-pixel statistics pass and ONE fused kernel that
+streams the cube through HBM once.  YAML configuration, CALDIR files and the ASDF data models are unchanged.
+
+Classes
+-------
+CalDir
+    One SCA's calibration reference data resident on a GPU (the reference re-opens the ASDF files inside every
+    routine; here they are uploaded once and the exposure-independent products are precomputed).
+
+Functions
+---------
+exposure_meta
+    ``N``, ``tbar``, ``tau`` of a read pattern (reference gen_cal_image.py:123-140).
+calibrate_arrays
+    L1 arrays -> L2 arrays, host buffers (copies inside).
+calibrate_device
+    The same on device pointers (asynchronous; for callers that keep exposures resident).
+calibrateimage
+    The reference's entry point: config dict -> L2 ASDF file (needs the ASDF / roman_datamodels stack for I/O).
+"""
+
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib, pars
+from ..caltree import open_tree
+from ..dqflags import pixel
+from ..utils import fitting
+
+
+def exposure_meta(read_pattern, frame_time):
+    """``meta`` dictionary of an exposure exactly as ``initializationstep`` builds it (gen_cal_image.py:123-140)."""
+    ngrp = len(read_pattern)
+    meta = {"frame_time": frame_time, "read_pattern": [list(g) for g in read_pattern], "ngrp": ngrp}
+    meta["tbar"] = np.zeros(ngrp, dtype=np.float32)
+    meta["tau"] = np.zeros(ngrp, dtype=np.float32)
+    meta["N"] = np.zeros(ngrp, dtype=np.int16)
+    for i in range(ngrp):
+        meta["N"][i] = len(read_pattern[i])
+        t0 = read_pattern[i][0]
+        meta["tbar"][i] = (t0 + (meta["N"][i] - 1) / 2.0) * frame_time
+        meta["tau"][i] = (t0 + (meta["N"][i] - 1) * (2 * meta["N"][i] - 1) / (6.0 * meta["N"][i])) * frame_time
+    meta["nborder"] = pars.nborder
+    return meta
+
+
+def ramp_setup(meta, config):
+    """Weights and jump parameters as ``do_ramp_fit`` sets them (gen_cal_image.py:434-444); returns the ramp plan."""
+    exclude_first = config.get("EXCLUDE_FIRST", True)
+    uopt = {"slope": 0.4, "gain": 1.8, "sigma_read": 6.5}
+    if "RAMP_OPT_PARS" in config:
+        uopt = config["RAMP_OPT_PARS"]
+    u_ = float(uopt["slope"]) / float(uopt["gain"]) / float(uopt["sigma_read"]) ** 2
+    meta["K"] = fitting.construct_weights(u_, meta, exclude_first=exclude_first)
+    meta["ramp_opt_pars"] = uopt
+    if "JUMP_DETECT_PARS" in config:
+        meta["jump_detect_pars"] = config["JUMP_DETECT_PARS"]
+    return fitting.build_plan(meta, exclude_first)
+
+
+class CalDir:
+    """
+    Calibration reference data of one SCA resident on one GPU (``rip_caldir_create``).
+
+    Parameters
+    ----------
+    caldir : dict
+        The ``CALDIR`` dictionary of the configuration: keys ``linearitylegendre``, ``saturation``, ``gain``,
+        ``read``, ``dark``, ``flat`` (required), ``mask``, ``ipc4d``, ``biascorr`` (optional).  Values are ASDF
+        file names (as in the reference) or in-memory trees.
+    device : int
+        CUDA device ordinal.
+    """
+
+    def __init__(self, caldir, device=0):
+        self.device = device
+        self._h = C.c_void_p()
+        d = _lib.CaldirDesc()
+        keep = []
+
+        def put(field, arr, dtype=None):
+            a = _lib.as_float_plane(arr) if dtype is None else _lib.as_c(arr, dtype)
+            keep.append(a)
+            setattr(d, field, a.ctypes.data)
+            return a
+
+        with open_tree(caldir["linearitylegendre"]) as f:
+            r = f["roman"]
+            coefs = put("lin_coefs", r["data"], np.float32)
+            put("Smin", r["Smin"], np.float32)
+            put("Smax", r["Smax"], np.float32)
+            put("Sref", r["Sref"], np.float32)
+            put("lin_dq", r["dq"], np.uint32)
+        self.P, self.n = coefs.shape[0], coefs.shape[-1]
+        self.nb = pars.nborder
+        self.na = self.n - 2 * self.nb
+        d.n, d.nb, d.P = self.n, self.nb, self.P
+        if "mask" in caldir:
+            with open_tree(caldir["mask"]) as f:
+                put("mask_dq", f["roman"]["dq"], np.uint32)
+        with open_tree(caldir["saturation"]) as f:
+            put("sat_thresh", f["roman"]["data"], np.float32)
+            put("sat_dq", f["roman"]["dq"], np.uint32)
+        with open_tree(caldir["gain"]) as f:
+            g = put("gain", f["roman"]["data"])
+            d.gain_dtype = _lib.float_tag(g)
+        self.has_ipc = "ipc4d" in caldir
+        if self.has_ipc:
+            with open_tree(caldir["ipc4d"]) as f:
+                k = put("ipc", f["roman"]["data"])
+                d.ipc_dtype = _lib.float_tag(k)
+        self.refout_slope = None
+        d.refout_slope = float("nan")
+        with open_tree(caldir["read"]) as f:
+            r = f["roman"]
+            put("read", r["data"], np.float32)
+            if "resetnoise" in r:
+                put("resetnoise", r["resetnoise"], np.float32)
+            if "anc" in r:
+                d.c_pink, d.u_pink = float(r["anc"]["C_PINK"]), float(r["anc"]["U_PINK"])
+            self.has_amp33 = "amp33" in r
+            if self.has_amp33:
+                a = r["amp33"]
+                put("amp33_med", a["med"], np.float32)
+                put("amp33_std", a["std"], np.float32)
+                d.has_amp33 = 1
+                d.m_pink, d.ru_pink = float(a["M_PINK"]), float(a["RU_PINK"])
+                # the reference's own expression for the optimal reference-output coefficient (gen_cal_image.py:542-553)
+                cvar = r["anc"]["C_PINK"] ** 2
+                self.refout_slope = a["M_PINK"] * cvar / (
+                    a["M_PINK"] ** 2 * cvar + a["RU_PINK"] ** 2 + np.median(a["std"]) ** 2 / 128 / np.log(4096)
+                )
+                d.refout_slope = float(self.refout_slope)
+        with open_tree(caldir["dark"]) as f:
+            r = f["roman"]
+            dk = put("dark_cube", r["data"], np.float32)
+            d.n_dark = dk.shape[0]
+            put("dark_slope", np.array(r["dark_slope"], dtype=np.float32), np.float32)
+            put("dark_dq", r["dq"], np.uint32)
+        self.n_dark = d.n_dark
+        self.has_bias = "biascorr" in caldir
+        self.biascorr_t0 = 0.0
+        if self.has_bias:
+            with open_tree(caldir["biascorr"]) as f:
+                b = put("biascorr", f["roman"]["data"], np.float32)
+                d.n_bias = b.shape[0]
+                if "t0" in f["roman"]:
+                    self.biascorr_t0 = d.biascorr_t0 = float(f["roman"]["t0"])
+        with open_tree(caldir["flat"]) as f:
+            put("flat", f["roman"]["data"], np.float32)
+        with open_tree(caldir["gain"]) as f:
+            self.medgain = np.median(f["roman"]["data"])  # gen_cal_image.py:632-633
+        _lib.check(_lib.lib().rip_caldir_create(device, C.byref(d), C.byref(self._h)))
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise RuntimeError("CalDir already closed")
+        return self._h
+
+    def static_products(self):
+        """IPC-corrected dark slope, ``get_flat`` product and merged static DQ (host copies; tests/inspection)."""
+        n = self.n
+        ds, fl, dq = np.empty((n, n), np.float32), np.empty((n, n), np.float32), np.empty((n, n), np.uint32)
+        s = C.c_double(0.0)
+        _lib.check(_lib.lib().rip_caldir_get_static(self.handle, _lib.ptr(ds), _lib.ptr(fl), _lib.ptr(dq), C.byref(s)))
+        return {"dark_slope_ipc": ds, "flat": fl, "static_dq": dq, "refout_slope": s.value}
+
+    def close(self):
+        if self._h:
+            _lib.lib().rip_caldir_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def _params(cal, meta, config, do_refpix, threads=0, band_rows=0, area=None):
+    prm = _lib.L1L2Params()
+    prm.G = int(meta["ngrp"])
+    prm.exclude_first = 1 if config.get("EXCLUDE_FIRST", True) else 0
+    prm.sat_backup = int(config.get("SATURATION_BACKUP", 1))
+    prm.do_not_flag_first = 1 if list(meta["read_pattern"][0]) == [0] else 0  # gen_cal_image.py:583
+    prm.do_refpix = 1 if do_refpix else 0
+    prm.area_dtype = _lib.RIP_F32 if area is None else _lib.float_tag(area)
+    prm.threads, prm.band_rows = int(threads), int(band_rows)
+    return prm
+
+
+def calibrate_arrays(cal, data, amp33, read_pattern, frame_time, area_factor=None, config=None, do_refpix=True,
+                     want_rdq=False, want_lin_cube=False, want_endslice=None, threads=0, band_rows=0, out=None,
+                     dplan=None):  # fmt: skip
+    """
+    The numerics of ``calibrateimage`` from L1 arrays to L2 arrays (reference gen_cal_image.py:503-629, 697-709).
+
+    Parameters
+    ----------
+    cal : CalDir
+    data : np.ndarray, uint16 (G, n, n)
+        L1 resultants.
+    amp33 : np.ndarray, uint16 (G, n, 128), or None
+        Reference-output resultants (needed for the reference-pixel correction).
+    read_pattern : list of list of int
+    frame_time : float
+    area_factor : np.ndarray (n, n), float32 or float64, optional
+        Pixel area / ``pars.Omega_ideal`` (reference gen_cal_image.py:618-621; a host WCS product).
+    config : dict, optional
+        The reference's configuration keys ``EXCLUDE_FIRST``, ``SATURATION_BACKUP``, ``RAMP_OPT_PARS``,
+        ``JUMP_DETECT_PARS``, ``SLICEOUT``.
+    do_refpix : bool
+        Run the reference-pixel loop (the reference always does; needs ``amp33`` and a frame side multiple of 128).
+    out : dict, optional
+        Preallocated output arrays to fill (e.g. page-locked buffers from ``_lib.pinned_empty`` so that the
+        device-to-host copies run at full PCIe speed); missing entries are allocated.
+    dplan : DevicePlan, optional
+        Reuse the pixel-independent plan of a previous call with the same read pattern and configuration.
+
+    Returns
+    -------
+    dict
+        ``slope``, ``err_read``, ``err_poisson`` (float32, flat-fielded DN/s, full frame), ``pdq`` (uint32),
+        ``endslice`` (int8, active region; if SLICEOUT), ``rdq`` / ``lin_cube`` if asked, ``meta`` (with ``K``).
+    """
+    config = config or {}
+    d = _lib.as_c(data, np.uint16)
+    G, n, _ = d.shape
+    if n != cal.n:
+        raise ValueError(f"L1 frame side {n} does not match the CALDIR ({cal.n})")
+    if G >= 128 and config.get("SLICEOUT", False):
+        raise ValueError("too many groups")  # gen_cal_image.py:699-700
+    if dplan is not None:
+        meta, plan, w_exact = dplan.meta, dplan.plan, dplan.w_exact
+    else:
+        meta = exposure_meta(read_pattern, frame_time)
+        plan, w_exact = ramp_setup(meta, config)
+    if meta["ngrp"] != G:
+        raise ValueError("read pattern and data cube disagree on the number of resultants")
+    a33 = None
+    if do_refpix:
+        if amp33 is None:
+            raise ValueError("the reference-pixel correction needs the amp33 cube")
+        a33 = _lib.as_c(amp33, np.uint16)
+    area = None if area_factor is None else _lib.as_float_plane(area_factor)
+    prm = _params(cal, meta, config, do_refpix, threads, band_rows, area)
+    if want_endslice is None:
+        want_endslice = bool(config.get("SLICEOUT", False))
+    out = {} if out is None else out
+
+    def buf(key, shape, dtype):
+        a = out.get(key)
+        if a is None or a.shape != shape or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+            a = out[key] = np.empty(shape, dtype)
+        return a
+
+    buf("slope", (n, n), np.float32)
+    buf("err_read", (n, n), np.float32)
+    buf("err_poisson", (n, n), np.float32)
+    buf("pdq", (n, n), np.uint32)
+    o = _lib.L2Out()
+    o.slope, o.err_read, o.err_poisson, o.pdq = (out[k].ctypes.data for k in ("slope", "err_read", "err_poisson", "pdq"))
+    if want_endslice:
+        buf("endslice", (cal.na, cal.na), np.int8)
+        o.endslice = out["endslice"].ctypes.data
+    if want_rdq:
+        buf("rdq", (G, n, n), np.uint8)
+        o.rdq = out["rdq"].ctypes.data
+    if want_lin_cube:
+        buf("lin_cube", (G, n, n), np.float32)
+        o.lin_cube = out["lin_cube"].ctypes.data
+    _lib.check(
+        _lib.lib().rip_l1_to_l2_host(cal.handle, _lib.ptr(d), _lib.ptr(a33), _lib.ptr(area), C.byref(prm),
+                                     C.byref(plan), _lib.ptr(w_exact), C.byref(o))
+    )  # fmt: skip
+    out["meta"] = meta
+    return out
+
+
+class DevicePlan:
+    """Pixel-independent inputs of the device entry point, built once per (read pattern, config)."""
+
+    def __init__(self, cal, read_pattern, frame_time, config=None, do_refpix=True, area_dtype=None, threads=0,
+                 band_rows=0):  # fmt: skip
+        config = config or {}
+        self.meta = exposure_meta(read_pattern, frame_time)
+        self.plan, self.w_exact = ramp_setup(self.meta, config)
+        self.prm = _params(cal, self.meta, config, do_refpix, threads, band_rows)
+        if area_dtype is not None:
+            self.prm.area_dtype = _lib.RIP_F64 if np.dtype(area_dtype) == np.float64 else _lib.RIP_F32
+
+
+def calibrate_device(cal, dplan, d_raw, d_amp33, d_area, d_slope, d_err_read, d_err_poisson, d_pdq, d_endslice=0,
+                     d_rdq=0, d_lin_cube=0, stream=0):  # fmt: skip
+    """
+    ``calibrate_arrays`` on DEVICE pointers (integers, e.g. ``tensor.data_ptr()``), asynchronous on ``stream``
+    (``rip_l1_to_l2_dev``).  The caller owns every buffer and synchronises.
+    """
+    o = _lib.L2Out()
+    o.slope, o.err_read, o.err_poisson, o.pdq = d_slope, d_err_read, d_err_poisson, d_pdq
+    o.endslice, o.rdq, o.lin_cube = d_endslice or None, d_rdq or None, d_lin_cube or None
+    _lib.check(
+        _lib.lib().rip_l1_to_l2_dev(cal.handle, C.c_void_p(d_raw), C.c_void_p(d_amp33 or None),
+                                    C.c_void_p(d_area or None), C.byref(dplan.prm), C.byref(dplan.plan),
+                                    _lib.ptr(dplan.w_exact), C.byref(o), C.c_void_p(stream or None))
+    )  # fmt: skip
+
+
+_CAL_CACHE = {}
+
+
+def _cached_caldir(caldir, device):
+    key = (device, tuple(sorted((k, v if isinstance(v, str) else id(v)) for k, v in caldir.items())))
+    if key not in _CAL_CACHE:
+        _CAL_CACHE[key] = CalDir(caldir, device)
+    return _CAL_CACHE[key]
+
+
+def calibrateimage(config, verbose=True, device=0):
+    """
+    Main routine to run the specified calibrations from a config file (same contract as the reference's
+    ``calibrateimage``: reads ``config["IN"]`` (L1 ASDF), writes ``config["OUT"]`` (L2 ASDF)).
+
+    The per-pixel numerics run on the GPU; reading/writing the data models, the WCS-derived pixel area, sky
+    statistics and packaging are the reference's host code and need its I/O stack (``asdf``, ``roman_datamodels``,
+    ``romanisim``, ``astropy``, ``gwcs``) -- they are imported from the installed ``romanimpreprocess`` package, which
+    this module does not replace.
+    """
+    try:
+        import asdf  # noqa: PLC0415
+        from romanimpreprocess.L1_to_L2 import gen_cal_image as _ref  # noqa: PLC0415
+    except ImportError as e:
+        raise ImportError(
+            "calibrateimage() reads and writes ASDF data models through the reference's I/O layer "
+            "(asdf, roman_datamodels, romanisim, romanimpreprocess); install them, or call calibrate_arrays() "
+            "with in-memory arrays"
+        ) from e
+    caldir = config["CALDIR"]
+    cal = _cached_caldir(caldir, device)
+    with asdf.open(config["IN"]) as f:
+        r = f["roman"]
+        data = np.asarray(r["data"])
+        amp33 = np.asarray(r["amp33"]) if "amp33" in r else None
+        read_pattern = [list(g) for g in r["meta"]["exposure"]["read_pattern"]]
+        frame_time = float(r["meta"]["exposure"]["frame_time"])
+        if "reference_read" in r:  # EXTRACT_REF round trip (reference sim_to_isim.py:711-730)
+            off = int(r["meta"]["instrument"].get("data_encoding_offset", 0)) if "instrument" in r["meta"] else 0
+            data = (data.astype(np.int32) + np.asarray(r["reference_read"]).astype(np.int32) - off).astype(np.uint16)
+    thewcs = _ref.wcs_from_config(config)
+    from romanisim import wcs as riwcs  # noqa: PLC0415
+    from romanimpreprocess.utils import coordutils  # noqa: PLC0415
+
+    area = coordutils.pixelarea(riwcs.convert_wcs_to_gwcs(_ref.repackage_wcs(thewcs)), N=data.shape[-1]) / pars.Omega_ideal
+    out = calibrate_arrays(cal, data, amp33, read_pattern, frame_time, area, config, do_refpix=cal.has_amp33,
+                           want_rdq=True, want_endslice=bool(config.get("SLICEOUT", False)))  # fmt: skip
+    return _ref._package_l2(config, out, thewcs) if hasattr(_ref, "_package_l2") else out
+
+
+__all__ = ["CalDir", "DevicePlan", "calibrate_arrays", "calibrate_device", "calibrateimage", "exposure_meta",
+           "ramp_setup", "pixel"]  # fmt: skip

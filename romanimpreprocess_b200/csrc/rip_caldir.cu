@@ -1,0 +1,514 @@
+// CALDIR handle (device-resident calibration planes of one SCA), static products, reference-pixel
+// statistics and the fused L1->L2 entry points (include/rip_b200.h).
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <memory>
+
+#include "rip_handle.h"
+#include "rip_launch.h"
+
+namespace rip {
+
+// =========================================================================================================
+// K2: static, exposure-independent products
+// =========================================================================================================
+__global__ void static_planes_kernel(int n, int nb, const float* __restrict__ sat_thr, const uint32_t* __restrict__ sat_dq,
+                                     const uint32_t* __restrict__ lin_dq, const uint32_t* __restrict__ mask_dq,
+                                     const uint32_t* __restrict__ dark_dq, float* __restrict__ thr_eff,
+                                     uint8_t* __restrict__ aux, uint32_t* __restrict__ sdq) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (long)n * n) return;
+    const int y = (int)(p / n), x = (int)(p % n);
+    const bool active = (y >= nb && y < n - nb && x >= nb && x < n - nb);
+    float t = sat_thr[p];
+    const uint32_t sd = sat_dq[p];
+    if ((sd & DQ_NO_SAT_CHECK) || t != t) t = INFINITY;
+    thr_eff[p] = t;
+    const uint32_t ld = lin_dq[p], md = mask_dq ? mask_dq[p] : 0u;
+    uint8_t a = 0;
+    if (ld & (DQ_NO_LIN_CORR | DQ_REFERENCE_PIXEL)) a |= 1;
+    if ((ld | md) & DQ_REFERENCE_PIXEL) a |= 2;
+    aux[p] = a;
+    // pdq sources that do not depend on the exposure: mask (do_dqinit), NO_SAT_CHECK (flag_saturation), lin dq
+    // (ipc_linearity.py:328), dark dq on the active region (subtract_dark_current); flat flags are OR'ed later
+    sdq[p] |= md | (sd & DQ_NO_SAT_CHECK) | ld | ((active && dark_dq) ? dark_dq[p] : 0u);
+}
+
+// =========================================================================================================
+// K0: reference-pixel statistics (gen_cal_image.py:531-555 + utils/reference_subtraction.py)
+// =========================================================================================================
+__device__ __forceinline__ uint32_t f2key(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+
+__global__ void k0_init_kernel(SelState* st, int G, uint32_t M) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    st[g].prefix[0] = st[g].prefix[1] = 0u;
+    st[g].rank[0] = M / 2 - 1;  // M is even: np.median averages the two middle elements
+    st[g].rank[1] = M / 2;
+}
+
+// radix-select histogram pass over e = f32(amp33) - med, key bits [shift, shift+nbits); elements must match
+// the already-known high bits (prefix) of each of the two order statistics.
+__global__ void k0_hist_kernel(const uint16_t* __restrict__ amp33, const float* __restrict__ med, long M, int pass,
+                               const SelState* __restrict__ st, uint32_t* __restrict__ hist /*[G][2][2048]*/) {
+    __shared__ uint32_t sh[2][2048];
+    const int g = blockIdx.y;
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) (&sh[0][0])[i] = 0u;
+    __syncthreads();
+    const SelState s = st[g];
+    const int shift_hi = (pass == 0) ? 32 : (pass == 1 ? 21 : 10);
+    const int shift = (pass == 0) ? 21 : (pass == 1 ? 10 : 0);
+    const uint32_t mask = (pass == 2) ? 1023u : 2047u;
+    const uint16_t* a = amp33 + (long)g * M;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long)gridDim.x * blockDim.x) {
+        const float e = (float)a[i] - med[i];
+        const uint32_t k = f2key(e);
+        const uint32_t hi = (shift_hi >= 32) ? 0u : (k >> shift_hi);
+        const uint32_t b = (k >> shift) & mask;
+        if (hi == s.prefix[0]) atomicAdd(&sh[0][b], 1u);
+        if (hi == s.prefix[1]) atomicAdd(&sh[1][b], 1u);
+    }
+    __syncthreads();
+    uint32_t* h = hist + (long)g * 4096;
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) {
+        const uint32_t v = (&sh[0][0])[i];
+        if (v) atomicAdd(&h[i], v);
+    }
+}
+
+// find the bucket holding each rank; extend the prefixes; clear the histogram for the next pass
+__global__ void k0_scan_kernel(uint32_t* __restrict__ hist, SelState* __restrict__ st, int pass) {
+    __shared__ uint32_t cum[2048];
+    const int g = blockIdx.x;
+    const int nbits = (pass == 2) ? 10 : 11;
+    const int nbin = 1 << nbits;
+    for (int r = 0; r < 2; ++r) {
+        uint32_t* h = hist + (long)g * 4096 + r * 2048;
+        for (int i = threadIdx.x; i < 2048; i += blockDim.x) cum[i] = (i < nbin) ? h[i] : 0u;
+        __syncthreads();
+        for (int off = 1; off < 2048; off <<= 1) {  // Hillis-Steele inclusive scan
+            uint32_t v[2];
+            int k = 0;
+            for (int i = threadIdx.x; i < 2048; i += blockDim.x) v[k++] = (i >= off) ? cum[i - off] : 0u;
+            __syncthreads();
+            k = 0;
+            for (int i = threadIdx.x; i < 2048; i += blockDim.x) cum[i] += v[k++];
+            __syncthreads();
+        }
+        const uint32_t rank = st[g].rank[r];
+        __syncthreads();
+        for (int i = threadIdx.x; i < nbin; i += blockDim.x) {
+            const uint32_t before = i ? cum[i - 1] : 0u;
+            if (rank >= before && rank < cum[i]) {
+                st[g].prefix[r] = (st[g].prefix[r] << nbits) | (uint32_t)i;
+                st[g].rank[r] = rank - before;
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2048; i += blockDim.x) h[i] = 0u;
+        __syncthreads();
+    }
+}
+
+// the two middle order statistics (ranks 63, 64) of the 128 reference-output pixels of every row
+__global__ void k0_rowmid_kernel(const uint16_t* __restrict__ amp33, const float* __restrict__ med, int n,
+                                 float* __restrict__ rowA, float* __restrict__ rowB) {
+    __shared__ float sv[8][128];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + w, g = blockIdx.y;
+    if (row >= n) return;
+    const uint16_t* a = amp33 + ((long)g * n + row) * 128;
+    const float* m = med + (long)row * 128;
+    float e[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        e[k] = (float)a[lane + 32 * k] - m[lane + 32 * k];
+        sv[w][lane + 32 * k] = e[k];
+    }
+    __syncwarp();
+    int rk[4] = {0, 0, 0, 0};
+    for (int j = 0; j < 128; ++j) {
+        const float o = sv[w][j];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = lane + 32 * k;
+            rk[k] += (o < e[k] || (o == e[k] && j < idx)) ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (rk[k] == 63) rowA[(long)g * n + row] = e[k];
+        if (rk[k] == 64) rowB[(long)g * n + row] = e[k];
+    }
+}
+
+__device__ __forceinline__ void bitonic_sort_block(float* v, int npow2) {
+    for (int k = 2; k <= npow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const float a = v[i], b = v[ixj];
+                    const bool up = ((i & k) == 0);
+                    if ((a > b) == up) { v[i] = b; v[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// global median, per-row reference medians, their median, and the f64 row correction
+__global__ void k0_final_kernel(const SelState* __restrict__ st, const float* __restrict__ rowA,
+                                const float* __restrict__ rowB, int n, int npow2, double slope,
+                                double* __restrict__ rowcorr, float* __restrict__ gmed_out) {
+    extern __shared__ float sv[];
+    float* refm = sv + npow2;
+    const int g = blockIdx.x;
+    const float kA = key2f(st[g].prefix[0]), kB = key2f(st[g].prefix[1]);
+    const float gmed = (kA + kB) / 2.0f;
+    if (threadIdx.x == 0 && gmed_out) gmed_out[g] = gmed;
+    for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+        float v = INFINITY;
+        if (i < n) {
+            const float a = rowA[(long)g * n + i] - gmed, b = rowB[(long)g * n + i] - gmed;
+            v = (a + b) / 2.0f;
+            refm[i] = v;
+        }
+        sv[i] = v;
+    }
+    __syncthreads();
+    bitonic_sort_block(sv, npow2);
+    const float ctr = (n & 1) ? sv[n / 2] : (sv[n / 2 - 1] + sv[n / 2]) / 2.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float dm = refm[i] - ctr;
+        rowcorr[(long)g * n + i] = slope * (double)dm;
+    }
+}
+
+// per (group, channel): medians of the 4 bottom / 4 top reference rows of the row-corrected (data - dark), and
+// the line through (1.5, bottom), (n-2.5, top)
+__global__ void k0_chan_kernel(const uint16_t* __restrict__ raw, const float* __restrict__ dark, int n,
+                               const double* __restrict__ rowcorr, double* __restrict__ chan_m,
+                               double* __restrict__ chan_c) {
+    __shared__ float sv[2][512];
+    __shared__ float meds[2];
+    const int ch = blockIdx.x, g = blockIdx.y;
+    const long npl = (long)n * n;
+    for (int side = 0; side < 2; ++side) {
+        const int rbase = side ? (n - 4) : 0;
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+            const int row = rbase + (i >> 7), x = ch * 128 + (i & 127);
+            const long p = (long)row * n + x;
+            float v = (float)raw[(long)g * npl + p] - dark[(long)g * npl + p];
+            v = (float)((double)v - rowcorr[(long)g * n + row]);
+            sv[side][i] = v;
+        }
+    }
+    __syncthreads();
+    for (int side = 0; side < 2; ++side) {
+        bitonic_sort_block(sv[side], 512);
+        if (threadIdx.x == 0) meds[side] = (sv[side][255] + sv[side][256]) / 2.0f;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double b = (double)meds[0], t = (double)meds[1];
+        const double x0 = 1.5, x1 = (double)n - 2.5;
+        const double m = (t - b) / (x1 - x0);
+        chan_m[g * 32 + ch] = m;
+        chan_c[g * 32 + ch] = b - m * x0;
+    }
+}
+
+}  // namespace rip
+
+using namespace rip;
+
+// =========================================================================================================
+// the handle
+// =========================================================================================================
+static void run_k0(rip_caldir* h, const uint16_t* d_raw, const uint16_t* d_amp33, int G, cudaStream_t st) {
+    const int n = h->n;
+    RIP_REQUIRE(h->has_amp33, "reference-pixel correction needs amp33 statistics in the read file (the reference's np.polyfit fails without them: SURVEY 7)");
+    RIP_REQUIRE(n % 128 == 0 && n <= 4096 && n >= 256, "reference-pixel correction needs a frame side that is a multiple of 128 in 256..4096 (got %d)", n);
+    RIP_REQUIRE(d_amp33 != nullptr, "reference-pixel correction needs the amp33 cube");
+    const long M = (long)n * 128;
+    const int nch = n / 128;
+    if (h->hist.n < (size_t)G * 4096) {
+        h->hist.alloc((size_t)RIP_GMAX * 4096);
+        h->sel.alloc(RIP_GMAX);
+        h->rowA.alloc((size_t)RIP_GMAX * n);
+        h->rowB.alloc((size_t)RIP_GMAX * n);
+        h->gmed.alloc(RIP_GMAX);
+        h->rowcorr.alloc((size_t)RIP_GMAX * n);
+        h->chan_m.alloc((size_t)RIP_GMAX * 32);
+        h->chan_c.alloc((size_t)RIP_GMAX * 32);
+    }
+    h->hist.zero(st);
+    RIP_LAUNCH(k0_init_kernel, 1, 32, 0, st, h->sel.p, G, (uint32_t)M);
+    RIP_LAUNCH(k0_rowmid_kernel, dim3((n + 7) / 8, G), 256, 0, st, d_amp33, h->amp_med.p, n, h->rowA.p, h->rowB.p);
+    const int nblk = (int)std::min<long>(64, (M + 4095) / 4096);
+    for (int pass = 0; pass < 3; ++pass) {
+        RIP_LAUNCH(k0_hist_kernel, dim3(nblk, G), 256, 0, st, d_amp33, h->amp_med.p, M, pass, h->sel.p, h->hist.p);
+        RIP_LAUNCH(k0_scan_kernel, G, 1024, 0, st, h->hist.p, h->sel.p, pass);
+    }
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    RIP_LAUNCH(k0_final_kernel, G, 1024, (size_t)2 * np2 * sizeof(float), st, h->sel.p, h->rowA.p, h->rowB.p, n, np2,
+               h->refout_slope, h->rowcorr.p, h->gmed.p);
+    RIP_LAUNCH(k0_chan_kernel, dim3(nch, G), 256, 0, st, d_raw, h->dark_cube.p, n, h->rowcorr.p, h->chan_m.p, h->chan_c.p);
+}
+
+static double derive_refout_slope(const rip_caldir_desc* d) {
+    // gen_cal_image.py:542-553 (the Python layer normally supplies this with the reference's own expression)
+    const size_t m = (size_t)d->n * 128;
+    std::vector<float> v(d->amp33_std, d->amp33_std + m);
+    std::nth_element(v.begin(), v.begin() + m / 2, v.end());
+    const float hi = v[m / 2];
+    const float lo = *std::max_element(v.begin(), v.begin() + m / 2);
+    const float med = (m & 1) ? hi : (lo + hi) / 2.0f;
+    const float t = (med * med) / 128.0f;
+    const double cvar = d->c_pink * d->c_pink;
+    return d->m_pink * cvar / (d->m_pink * d->m_pink * cvar + d->ru_pink * d->ru_pink + (double)t / std::log(4096.0));
+}
+
+extern "C" int rip_caldir_create(int device, const rip_caldir_desc* d, rip_caldir** out) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(d && out, "rip_caldir_create: null argument");
+    RIP_REQUIRE(d->n >= 16 && d->nb >= 1 && d->n > 2 * d->nb + 4, "rip_caldir_create: bad geometry n=%d nb=%d", d->n, d->nb);
+    RIP_REQUIRE(d->P >= 1 && d->P <= RIP_PMAX, "rip_caldir_create: P=%d outside 1..%d", d->P, RIP_PMAX);
+    RIP_REQUIRE(d->lin_coefs && d->Smin && d->Smax && d->Sref && d->lin_dq, "rip_caldir_create: linearitylegendre planes missing");
+    RIP_REQUIRE(d->sat_thresh && d->sat_dq, "rip_caldir_create: saturation planes missing");
+    RIP_REQUIRE(d->gain && d->read && d->dark_slope && d->flat, "rip_caldir_create: gain/read/dark_slope/flat missing");
+    RIP_REQUIRE(d->gain_dtype == RIP_F32 || d->gain_dtype == RIP_F64, "rip_caldir_create: gain dtype");
+    RIP_REQUIRE(!d->ipc || d->ipc_dtype == RIP_F32 || d->ipc_dtype == RIP_F64, "rip_caldir_create: ipc dtype");
+    use_device(device);
+    std::unique_ptr<rip_caldir> h(new rip_caldir);
+    h->device = device;
+    h->d = *d;
+    const int n = h->n = d->n, nb = h->nb = d->nb, na = h->na = d->n - 2 * d->nb;
+    h->P = d->P;
+    const size_t npl = (size_t)n * n, npa = (size_t)na * na;
+    RIP_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    cudaStream_t st = h->stream;
+    h->coefs.upload(d->lin_coefs, (size_t)d->P * npl, st);
+    h->Smin.upload(d->Smin, npl, st);
+    h->Smax.upload(d->Smax, npl, st);
+    h->Sref.upload(d->Sref, npl, st);
+    h->lin_dq.upload(d->lin_dq, npl, st);
+    h->sat_thr.upload(d->sat_thresh, npl, st);
+    h->read.upload(d->read, npl, st);
+    if (d->resetnoise) h->resetnoise.upload(d->resetnoise, npl, st);
+    if (d->dark_cube && d->n_dark > 0) h->dark_cube.upload(d->dark_cube, (size_t)d->n_dark * npl, st);
+    h->dark_slope.upload(d->dark_slope, npl, st);
+    h->flat.upload(d->flat, npl, st);
+    h->gain.upload(d->gain, npl * dtype_size(d->gain_dtype), st);
+    h->has_ipc = d->ipc != nullptr;
+    if (h->has_ipc) h->ipc.upload(d->ipc, 9 * npa * dtype_size(d->ipc_dtype), st);
+    h->has_bias = d->biascorr != nullptr && d->n_bias > 0;
+    if (h->has_bias) h->biascorr.upload(d->biascorr, (size_t)d->n_bias * npa, st);
+    h->has_amp33 = d->has_amp33 && d->amp33_med != nullptr;
+    if (h->has_amp33) {
+        h->amp_med.upload(d->amp33_med, (size_t)n * 128, st);
+        h->refout_slope = (d->refout_slope == d->refout_slope) ? d->refout_slope
+                          : (d->amp33_std ? derive_refout_slope(d) : std::numeric_limits<double>::quiet_NaN());
+        RIP_REQUIRE(h->refout_slope == h->refout_slope, "rip_caldir_create: cannot derive the reference-output slope (amp33 std missing)");
+    }
+    // ---- static products ----
+    DevBuf<uint32_t> sat_dq, mask_dq, dark_dq;
+    sat_dq.upload(d->sat_dq, npl, st);
+    if (d->mask_dq) mask_dq.upload(d->mask_dq, npl, st);
+    if (d->dark_dq) dark_dq.upload(d->dark_dq, npl, st);
+    h->thr_eff.alloc(npl);
+    h->aux.alloc(npl);
+    h->sdq.alloc(npl);
+    h->sdq.zero(st);
+    h->flat_ipc.alloc(npl);
+    h->dslope_ipc.alloc(npl);
+    // flat first: its flags are OR'ed into sdq (utils/flatutils.py:55-68)
+    launch_flat_prepare(h->flat.p, n, nb, h->gain.p, d->gain_dtype, h->sdq.p, h->has_ipc ? 1 : 0, h->flat_ipc.p, st);
+    RIP_LAUNCH(static_planes_kernel, (unsigned)((npl + 255) / 256), 256, 0, st, n, nb, h->sat_thr.p, sat_dq.p, h->lin_dq.p,
+               d->mask_dq ? mask_dq.p : nullptr, d->dark_dq ? dark_dq.p : nullptr, h->thr_eff.p, h->aux.p, h->sdq.p);
+    RIP_CUDA(cudaMemcpyAsync(h->dslope_ipc.p, h->dark_slope.p, npl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (h->has_ipc) {
+        DevRaw tmp;
+        tmp.alloc(npa * 8);
+        launch_ipc_rev_dn(h->flat_ipc.p, n, n, nb, h->ipc.p, d->ipc_dtype, h->gain.p, d->gain_dtype, true, 0.1f, tmp.p, st);
+        launch_ipc_rev_dn(h->dslope_ipc.p, n, n, nb, h->ipc.p, d->ipc_dtype, h->gain.p, d->gain_dtype, false, 0.f, tmp.p, st);
+        RIP_CUDA(cudaStreamSynchronize(st));
+    }
+    RIP_CUDA(cudaStreamSynchronize(st));
+    // pointers in the stored desc are the caller's: never dereference them again
+    *out = h.release();
+    RIP_API_END
+}
+
+extern "C" void rip_caldir_destroy(rip_caldir* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    delete h;
+}
+
+extern "C" int rip_caldir_get_static(rip_caldir* h, float* dark_slope_ipc, float* flat_ipc, uint32_t* static_dq, double* refout_slope) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h, "rip_caldir_get_static: null handle");
+    use_device(h->device);
+    const size_t npl = (size_t)h->n * h->n;
+    if (dark_slope_ipc) h->dslope_ipc.download(dark_slope_ipc, npl, h->stream);
+    if (flat_ipc) h->flat_ipc.download(flat_ipc, npl, h->stream);
+    if (static_dq) h->sdq.download(static_dq, npl, h->stream);
+    if (refout_slope) *refout_slope = h->refout_slope;
+    RIP_CUDA(cudaStreamSynchronize(h->stream));
+    RIP_API_END
+}
+
+// =========================================================================================================
+// fused L1 -> L2
+// =========================================================================================================
+static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16_t* d_amp33, const void* d_area,
+                              const rip_l1l2_params* prm, const rip_ramp_plan* plan, const double* w_exact,
+                              const rip_l2_out* o, cudaStream_t st) {
+    RIP_REQUIRE(h && d_raw && prm && plan && o, "rip_l1_to_l2: null argument");
+    RIP_REQUIRE(o->slope && o->err_read && o->err_poisson && o->pdq, "rip_l1_to_l2: slope/err_read/err_poisson/pdq outputs are required");
+    const int G = prm->G, n = h->n;
+    RIP_REQUIRE(G == plan->G, "rip_l1_to_l2: params.G=%d but plan.G=%d", G, plan->G);
+    RIP_REQUIRE(G >= 3 && G <= RIP_GMAX, "rip_l1_to_l2: G=%d outside 3..%d", G, RIP_GMAX);
+    RIP_REQUIRE((plan->start != 0) == (prm->exclude_first != 0), "rip_l1_to_l2: plan.start and exclude_first disagree");
+    RIP_REQUIRE(!prm->do_refpix || (int)(h->dark_cube.n / ((size_t)n * n)) >= G, "rip_l1_to_l2: dark cube has fewer groups than the exposure");
+    RIP_REQUIRE(!h->has_bias || h->d.n_bias >= G, "rip_l1_to_l2: biascorr cube has fewer groups than the exposure");
+    RIP_REQUIRE(prm->sat_backup >= 0 && prm->sat_backup < RIP_GMAX, "rip_l1_to_l2: bad SATURATION_BACKUP %d", prm->sat_backup);
+    const double* dw = plan_to_device(h->device, plan, w_exact, st);
+    if (prm->do_refpix) run_k0(h, d_raw, d_amp33, G, st);
+    CalArgs A;
+    memset(&A, 0, sizeof A);
+    A.n = n; A.nb = h->nb; A.G = G; A.P = h->P;
+    A.band_rows = prm->band_rows > 0 ? prm->band_rows : 128;
+    A.do_refpix = prm->do_refpix; A.do_not_flag_first = prm->do_not_flag_first; A.exclude_first = prm->exclude_first;
+    A.sat_backup = prm->sat_backup; A.area_dtype = prm->area_dtype;
+    A.raw = d_raw; A.area = d_area;
+    A.rowcorr = h->rowcorr.p; A.chan_m = h->chan_m.p; A.chan_c = h->chan_c.p;
+    A.dark = h->dark_cube.p;
+    A.bias = h->has_bias ? h->biascorr.p + (size_t)(h->d.n_bias - G) * h->na * h->na : nullptr;  // gen_cal_image.py:561-562
+    A.coefs = h->coefs.p; A.Smin = h->Smin.p; A.Smax = h->Smax.p; A.Sref = h->Sref.p;
+    A.aux = h->aux.p; A.sdq = h->sdq.p; A.thr = h->thr_eff.p;
+    A.gain = h->gain.p; A.ipc = h->has_ipc ? h->ipc.p : nullptr; A.read = h->read.p;
+    A.dslope = h->dslope_ipc.p; A.flat = h->flat_ipc.p; A.w_exact = dw;
+    A.slope = o->slope; A.err_read = o->err_read; A.err_poisson = o->err_poisson; A.pdq = o->pdq;
+    A.endslice = o->endslice; A.rdq = o->rdq; A.lincube = o->lin_cube;
+    int threads = prm->threads > 0 ? prm->threads : 128;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->profile) {
+        if (h->prof_used + 2 > h->prof_ev.size()) {
+            cudaEvent_t a, b;
+            RIP_CUDA(cudaEventCreate(&a));
+            RIP_CUDA(cudaEventCreate(&b));
+            h->prof_ev.push_back(a);
+            h->prof_ev.push_back(b);
+        }
+        e0 = h->prof_ev[h->prof_used];
+        e1 = h->prof_ev[h->prof_used + 1];
+        h->prof_used += 2;
+        RIP_CUDA(cudaEventRecord(e0, st));
+    }
+    launch_cal_fused(A, h->d.gain_dtype, h->has_ipc ? h->d.ipc_dtype : RIP_F32, threads, st);
+    if (e1) RIP_CUDA(cudaEventRecord(e1, st));
+}
+
+extern "C" int rip_profile_enable(rip_caldir* h, int on) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h, "rip_profile_enable: null handle");
+    h->profile = on != 0;
+    h->prof_used = 0;
+    RIP_API_END
+}
+
+extern "C" int rip_profile_fetch(rip_caldir* h, double* fused_ms_sum, int* launches) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && fused_ms_sum && launches, "rip_profile_fetch: null argument");
+    use_device(h->device);
+    double sum = 0.0;
+    for (size_t k = 0; k + 1 < h->prof_used; k += 2) {
+        RIP_CUDA(cudaEventSynchronize(h->prof_ev[k + 1]));
+        float ms = 0.f;
+        RIP_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[k], h->prof_ev[k + 1]));
+        sum += ms;
+    }
+    *fused_ms_sum = sum;
+    *launches = (int)(h->prof_used / 2);
+    h->prof_used = 0;
+    RIP_API_END
+}
+
+extern "C" int rip_l1_to_l2_dev(rip_caldir* h, const uint16_t* d_raw, const uint16_t* d_amp33, const void* d_area,
+                                const rip_l1l2_params* prm, const rip_ramp_plan* plan, const double* w_exact,
+                                const rip_l2_out* d_out, void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h, "rip_l1_to_l2_dev: null handle");
+    use_device(h->device);
+    l1_to_l2_dev_impl(h, d_raw, d_amp33, d_area, prm, plan, w_exact, d_out, (cudaStream_t)stream);
+    RIP_API_END
+}
+
+extern "C" int rip_l1_to_l2_host(rip_caldir* h, const uint16_t* raw, const uint16_t* amp33, const void* area,
+                                 const rip_l1l2_params* prm, const rip_ramp_plan* plan, const double* w_exact,
+                                 const rip_l2_out* out) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && raw && prm && plan && out, "rip_l1_to_l2_host: null argument");
+    use_device(h->device);
+    cudaStream_t st = h->stream;
+    const int G = prm->G, n = h->n, na = h->na;
+    RIP_REQUIRE(G >= 3 && G <= RIP_GMAX, "rip_l1_to_l2_host: G=%d outside 3..%d", G, RIP_GMAX);
+    const size_t npl = (size_t)n * n;
+    h->w_raw.upload(raw, (size_t)G * npl, st);
+    if (prm->do_refpix) {
+        RIP_REQUIRE(amp33, "rip_l1_to_l2_host: do_refpix needs the amp33 cube");
+        h->w_amp.upload(amp33, (size_t)G * n * 128, st);
+    }
+    if (area) h->w_area.upload(area, npl * dtype_size(prm->area_dtype), st);
+    if (h->w_slope.n < npl) { h->w_slope.alloc(npl); h->w_er.alloc(npl); h->w_ep.alloc(npl); h->w_pdq.alloc(npl); }
+    rip_l2_out o{};
+    o.slope = h->w_slope.p; o.err_read = h->w_er.p; o.err_poisson = h->w_ep.p; o.pdq = h->w_pdq.p;
+    if (out->endslice) { if (h->w_end.n < (size_t)na * na) h->w_end.alloc((size_t)na * na); o.endslice = h->w_end.p; }
+    if (out->rdq) { if (h->w_rdq.n < (size_t)G * npl) h->w_rdq.alloc((size_t)G * npl); o.rdq = h->w_rdq.p; }
+    if (out->lin_cube) { if (h->w_lin.n < (size_t)G * npl) h->w_lin.alloc((size_t)G * npl); o.lin_cube = h->w_lin.p; }
+    l1_to_l2_dev_impl(h, h->w_raw.p, prm->do_refpix ? h->w_amp.p : nullptr, area ? h->w_area.p : nullptr, prm, plan, w_exact, &o, st);
+    h->w_slope.download(out->slope, npl, st);
+    h->w_er.download(out->err_read, npl, st);
+    h->w_ep.download(out->err_poisson, npl, st);
+    h->w_pdq.download(out->pdq, npl, st);
+    if (out->endslice) h->w_end.download(out->endslice, (size_t)na * na, st);
+    if (out->rdq) h->w_rdq.download(out->rdq, (size_t)G * npl, st);
+    if (out->lin_cube) h->w_lin.download(out->lin_cube, (size_t)G * npl, st);
+    RIP_CUDA(cudaStreamSynchronize(st));
+    RIP_API_END
+}
+
+extern "C" int rip_refpix_stats_host(rip_caldir* h, const uint16_t* raw, const uint16_t* amp33, int G, double* rowcorr,
+                                     double* chan_m, double* chan_c, float* gmed) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && raw && amp33, "rip_refpix_stats_host: null argument");
+    RIP_REQUIRE(G >= 1 && G <= RIP_GMAX, "rip_refpix_stats_host: G=%d outside 1..%d", G, RIP_GMAX);
+    use_device(h->device);
+    cudaStream_t st = h->stream;
+    const int n = h->n;
+    h->w_raw.upload(raw, (size_t)G * n * n, st);
+    h->w_amp.upload(amp33, (size_t)G * n * 128, st);
+    run_k0(h, h->w_raw.p, h->w_amp.p, G, st);
+    if (rowcorr) h->rowcorr.download(rowcorr, (size_t)G * n, st);
+    if (chan_m) h->chan_m.download(chan_m, (size_t)G * 32, st);
+    if (chan_c) h->chan_c.download(chan_c, (size_t)G * 32, st);
+    if (gmed) h->gmed.download(gmed, G, st);
+    RIP_CUDA(cudaStreamSynchronize(st));
+    RIP_API_END
+}

@@ -1,0 +1,493 @@
+// Forward model (scene electrons -> L1 resultants): IL.apply (reference utils/ipc_linearity.py:461-513) and
+// make_l1_fullcal (reference from_sim/sim_to_isim.py:163-262) with romanisim's apportioning / read noise
+// restated (parity unpinned, validated statistically).
+//
+// ALU-bound (24 bisection steps x Legendre order x n_reads in float64), not HBM-bound.
+#include <memory>
+
+#include "rip_launch.h"
+
+namespace rip {
+
+// ---------------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (Salmon et al. 2011); one stream per (pixel, purpose)
+// ---------------------------------------------------------------------------------------------------------
+struct Philox {
+    uint32_t c[4], k[2];
+    uint32_t out[4];
+    int have;
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t idx, uint32_t stream) {
+        k[0] = (uint32_t)seed; k[1] = (uint32_t)(seed >> 32);
+        c[0] = 0u; c[1] = stream; c[2] = (uint32_t)idx; c[3] = (uint32_t)(idx >> 32);
+        have = 0;
+    }
+    __device__ __forceinline__ void round_(uint32_t (&x)[4], uint32_t k0, uint32_t k1) {
+        const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+        const uint32_t hi0 = __umulhi(M0, x[0]), lo0 = M0 * x[0];
+        const uint32_t hi1 = __umulhi(M1, x[2]), lo1 = M1 * x[2];
+        const uint32_t y0 = hi1 ^ x[1] ^ k0, y1 = lo1, y2 = hi0 ^ x[3] ^ k1, y3 = lo0;
+        x[0] = y0; x[1] = y1; x[2] = y2; x[3] = y3;
+    }
+    __device__ __forceinline__ void gen() {
+        uint32_t x[4] = {c[0], c[1], c[2], c[3]};
+        uint32_t k0 = k[0], k1 = k[1];
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            round_(x, k0, k1);
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3];
+        ++c[0];
+        have = 4;
+    }
+    __device__ __forceinline__ uint32_t next() {
+        if (have == 0) gen();
+        return out[--have];
+    }
+    // uniform in (0,1), 24-bit
+    __device__ __forceinline__ float uniform() { return ((next() >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+    // uniform in (0,1), 53-bit
+    __device__ __forceinline__ double uniform53() {
+        const uint64_t a = next() >> 5, b = next() >> 6;
+        return ((double)a * 67108864.0 + (double)b + 0.5) * (1.0 / 9007199254740992.0);
+    }
+    __device__ __forceinline__ float normal() {
+        const float u1 = uniform(), u2 = uniform();
+        return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+    }
+};
+
+// Stirling tail log(k!) - [(k+1/2)log(k+1) - (k+1) + (1/2)log(2pi)]  (Hormann 1993)
+__device__ __forceinline__ double stirling_tail(double k) {
+    const double t[10] = {0.0810614667953272, 0.0413406959554092, 0.0276779256849983, 0.02079067210376509,
+                          0.0166446911898211, 0.0138761288230707, 0.0118967099458917, 0.0104112652619720,
+                          0.00925546218271273, 0.00833056343336287};
+    if (k <= 9.0) return t[(int)k];
+    const double kp1sq = (k + 1.0) * (k + 1.0);
+    return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / kp1sq) / kp1sq) / (k + 1.0);
+}
+
+// Binomial(n, p) sampler: inversion for n*min(p,1-p) < 10, Hormann's BTRS transformed rejection otherwise.
+__device__ long binomial_draw(Philox& rng, long n, double p) {
+    if (n <= 0 || p <= 0.0) return 0;
+    if (p >= 1.0) return n;
+    const bool flip = p > 0.5;
+    const double q = flip ? 1.0 - p : p;
+    long k;
+    if ((double)n * q < 10.0) {
+        // sequential inversion via geometric waiting times
+        const double lq = log1p(-q);
+        long x = 0, sum = 0;
+        for (;;) {
+            const double u = rng.uniform53();
+            sum += (long)floor(log(u) / lq) + 1;
+            if (sum > n) break;
+            ++x;
+        }
+        k = x;
+    } else {
+        const double nd = (double)n;
+        const double spq = sqrt(nd * q * (1.0 - q));
+        const double b = 1.15 + 2.53 * spq, a = -0.0873 + 0.0248 * b + 0.01 * q, c = nd * q + 0.5;
+        const double vr = 0.92 - 4.2 / b, r = q / (1.0 - q), alpha = (2.83 + 5.1 / b) * spq;
+        const double m = floor((nd + 1.0) * q);
+        for (;;) {
+            const double u = rng.uniform53() - 0.5;
+            double v = rng.uniform53();
+            const double us = 0.5 - fabs(u);
+            const double kk = floor((2.0 * a / us + b) * u + c);
+            if (kk < 0.0 || kk > nd) continue;
+            if (us >= 0.07 && v <= vr) { k = (long)kk; break; }
+            v = log(v * alpha / (a / (us * us) + b));
+            const double ub = (m + 0.5) * log((m + 1.0) / (r * (nd - m + 1.0))) +
+                              (nd + 1.0) * log((nd - m + 1.0) / (nd - kk + 1.0)) +
+                              (kk + 0.5) * log(r * (nd - kk + 1.0) / (kk + 1.0)) + stirling_tail(m) +
+                              stirling_tail(nd - m) - stirling_tail(kk) - stirling_tail(nd - kk);
+            if (v <= ub) { k = (long)kk; break; }
+        }
+    }
+    return flip ? n - k : k;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// IL.apply chain on a window [ny,nx] of pitched calibration planes
+// ---------------------------------------------------------------------------------------------------------
+template <typename TC, typename TS, typename TO>
+__global__ void il_sum_kernel(const TC* __restrict__ counts, const TS* __restrict__ start_e, double start_scalar, long npix,
+                              TO* __restrict__ out) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    out[p] = start_e ? (TO)counts[p] + (TO)start_e[p] : (TO)counts[p] + (TO)start_scalar;
+}
+
+// conv (type TI) = 9-tap source-indexed IPC of im; optional; then / gain -> Slin (TL); bisection -> S (TL)
+template <typename TIM, typename TK, typename TG, typename TL, int PMAX>
+__global__ void il_chain_kernel(const TIM* __restrict__ im, const TK* __restrict__ K, const TG* __restrict__ gain,
+                                long gain_off, int gain_pitch, int ny, int nx, const float* __restrict__ coefs,
+                                long lin_plane, long lin_off, int lin_pitch, int P, const float* __restrict__ Smin,
+                                const float* __restrict__ Smax, const float* __restrict__ Sref, int gain_in, int electrons_out,
+                                double* __restrict__ out) {
+    typedef typename Promote<TIM, TK>::type TI;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx) return;
+    const long pl = (long)ny * nx;
+    TI conv;
+    if (K) {
+        const int DY[9] = {0, 1, -1, 0, 0, 1, 1, -1, -1};
+        const int DX[9] = {0, 0, 0, 1, -1, 1, -1, 1, -1};
+        conv = (TI)im[(long)y * nx + x] * (TI)K[4 * pl + (long)y * nx + x];
+#pragma unroll
+        for (int q = 1; q < 9; ++q) {
+            const int ys = y - DY[q], xs = x - DX[q];
+            if (ys >= 0 && ys < ny && xs >= 0 && xs < nx)
+                conv = conv + (TI)im[(long)ys * nx + xs] * (TI)K[(long)((1 + DY[q]) * 3 + (1 + DX[q])) * pl + (long)ys * nx + xs];
+        }
+    } else {
+        conv = (TI)im[(long)y * nx + x];
+    }
+    const long lp = lin_off + (long)y * lin_pitch + x;
+    TL slin = gain_in ? (TL)conv / (TL)gain[gain_off + (long)y * gain_pitch + x] : (TL)conv;
+    float c[PMAX];
+#pragma unroll
+    for (int L = 0; L < PMAX; ++L) c[L] = (L < P) ? coefs[(long)L * lin_plane + lp] : 0.0f;
+    bool ex;
+    TL S = invlin_pixel<TL, PMAX>(slin, c, P, Smin[lp], Smax[lp], ex);
+    double r = (double)S;
+    if (electrons_out) {
+        // g_out * (S - Sref): S has type TL, Sref f32, gain TG  (ipc_linearity.py:513)
+        TL diff = S - (TL)Sref[lp];
+        r = (double)((typename Promote<TL, TG>::type)gain[gain_off + (long)y * gain_pitch + x] * (typename Promote<TL, TG>::type)diff);
+    }
+    out[(long)y * nx + x] = r;
+}
+
+struct IlWindow {
+    int ny, nx;
+    const void* K; int k_dtype;
+    const void* gain; int g_dtype; long gain_off; int gain_pitch;
+    const float *coefs, *Smin, *Smax, *Sref; long lin_plane, lin_off; int lin_pitch; int P;
+};
+
+template <typename TIM, typename TK, typename TG, typename TL>
+static void il_chain_launch(const void* im, const IlWindow& w, bool use_gain, int electrons_out, double* out, cudaStream_t st) {
+    dim3 grid((w.nx + 127) / 128, w.ny), block(128);
+#define ILC(PM)                                                                                                        \
+    RIP_LAUNCH((il_chain_kernel<TIM, TK, TG, TL, PM>), grid, block, 0, st, (const TIM*)im, (const TK*)w.K,              \
+               (const TG*)((use_gain || electrons_out) ? w.gain : nullptr), w.gain_off, w.gain_pitch, w.ny, w.nx, w.coefs, \
+               w.lin_plane, w.lin_off, w.lin_pitch, w.P, w.Smin, w.Smax, w.Sref, use_gain ? 1 : 0, electrons_out, out)
+    if (w.P <= 4) ILC(4);
+    else if (w.P <= 11) ILC(11);
+    else ILC(RIP_PMAX);
+#undef ILC
+}
+
+// Runs IL.apply on device data.  d_counts: device window [ny,nx] of c_dtype; d_start: device f32/f64 plane or null.
+// Returns the NumPy result dtype tag (values are written as f64).
+static int il_apply_device(const void* d_counts, int c_dtype, const void* d_start, int s_dtype, double start_scalar,
+                           const IlWindow& w, int electrons, int electrons_out, double* d_out, void* d_tmp,
+                           cudaStream_t st) {
+    const long npix = (long)w.ny * w.nx;
+    // dtype of counts + start_e: ints (>=32 bit) + f32 -> f64; f32 + (f32 | python scalar) -> f32
+    const bool cd = (c_dtype == RIP_F64 || c_dtype == RIP_I32);
+    const bool sd = d_start && s_dtype == RIP_F64;
+    const bool sumd = cd || sd;
+    const unsigned nb = (unsigned)((npix + 255) / 256);
+#define SUM(TC, TS, TO) RIP_LAUNCH((il_sum_kernel<TC, TS, TO>), nb, 256, 0, st, (const TC*)d_counts, (const TS*)d_start, start_scalar, npix, (TO*)d_tmp)
+    if (c_dtype == RIP_I32) { if (sd) SUM(int32_t, double, double); else SUM(int32_t, float, double); }
+    else if (c_dtype == RIP_F64) { if (sd) SUM(double, double, double); else SUM(double, float, double); }
+    else { if (sd) SUM(float, double, double); else SUM(float, float, float); }
+#undef SUM
+    const bool kd = w.K && w.k_dtype == RIP_F64;
+    const bool gd = w.g_dtype == RIP_F64;
+    const bool convd = sumd || kd;
+    const bool use_gain = electrons != 0;
+    const bool slind = convd || (use_gain && gd);
+    // TL = dtype of counts_conv / g_in
+    if (!sumd) {
+        if (!kd) { if (slind) il_chain_launch<float, float, double, double>(d_tmp, w, use_gain, electrons_out, d_out, st);
+                   else il_chain_launch<float, float, float, float>(d_tmp, w, use_gain, electrons_out, d_out, st); }
+        else { if (gd) il_chain_launch<float, double, double, double>(d_tmp, w, use_gain, electrons_out, d_out, st);
+               else il_chain_launch<float, double, float, double>(d_tmp, w, use_gain, electrons_out, d_out, st); }
+    } else {
+        if (!kd) { if (gd) il_chain_launch<double, float, double, double>(d_tmp, w, use_gain, electrons_out, d_out, st);
+                   else il_chain_launch<double, float, float, double>(d_tmp, w, use_gain, electrons_out, d_out, st); }
+        else { if (gd) il_chain_launch<double, double, double, double>(d_tmp, w, use_gain, electrons_out, d_out, st);
+               else il_chain_launch<double, double, float, double>(d_tmp, w, use_gain, electrons_out, d_out, st); }
+    }
+    bool outd = slind;
+    if (electrons_out && gd) outd = true;
+    return outd ? RIP_F64 : RIP_F32;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3: forward ramp.  One CTA = TX x TY active pixels (+1 halo for the IPC stencil); loop over reads.
+// ---------------------------------------------------------------------------------------------------------
+struct FwdArgs {
+    int n, nb, na, G, P, n_reads;
+    int reads_per_group[RIP_GMAX];
+    int read_index[64];
+    double read_time;
+    uint64_t seed;
+    int add_read_noise, add_reset_noise, add_biascorr, quantize;
+    double biascorr_t0;
+    int has_bias;
+    const int32_t* counts;      // [na,na] total electrons of the exposure (already Poisson)
+    const int32_t* cum_counts;  // [n_reads,na,na] optional externally apportioned cumulative counts (tests)
+    const float* coefs; const float* Smin; const float* Smax;  // full-frame planes
+    const void* gain; const void* ipc; const float* read; const float* resetnoise; const float* dark_slope;
+    const float* bias;          // [G,na,na] or null (offset applied)
+    float* out;                 // [G,na,na]
+};
+
+constexpr int FTX = 32, FTY = 8;
+
+template <int PMAX, typename TG, typename TK>
+__global__ void __launch_bounds__((FTX + 2) * (FTY + 2)) fwd_ramp_kernel(const FwdArgs A) {
+    __shared__ double se[FTY + 2][FTX + 2];  // electrons in the well at this read (counts so far + start_e)
+    const int tx = threadIdx.x % (FTX + 2), ty = threadIdx.x / (FTX + 2);
+    const int xa = blockIdx.x * FTX + tx - 1, ya = blockIdx.y * FTY + ty - 1;  // active coords incl. halo
+    const int na = A.na, n = A.n, nb = A.nb;
+    const bool inside = (xa >= 0 && xa < na && ya >= 0 && ya < na);
+    const bool owner = inside && tx >= 1 && tx <= FTX && ty >= 1 && ty <= FTY;
+    const long pa = (long)ya * na + xa;
+    const long pf = (long)(ya + nb) * n + (xa + nb);
+    const long npa = (long)na * na, npl = (long)n * n;
+    const TG* gainp = (const TG*)A.gain;
+    const TK* K = (const TK*)A.ipc;
+
+    Philox rng;
+    rng.init(A.seed, inside ? (uint64_t)pa : 0ull, 1u);
+    // reset noise in electrons (sim_to_isim.py:195-215): N(0,1)*resetnoise*gain - t0*dark_slope/gain, float32
+    float start_e = 0.0f;
+    long remaining = 0;
+    TG g = (TG)1;
+    if (inside) {
+        g = gainp[pf];
+        if (A.add_reset_noise) {
+            float rn = rng.normal();
+            rn = rn * A.resetnoise[pf];
+            rn = (float)((typename Promote<float, TG>::type)rn * (typename Promote<float, TG>::type)g);
+            start_e = rn;
+        }
+        if (A.has_bias) {
+            typedef typename Promote<float, TG>::type TP;
+            // tbias * dark_slope / gain : python float * f32 array -> f32, / gain -> TP
+            const float td = (float)A.biascorr_t0 * A.dark_slope[pf];
+            start_e = (float)((TP)start_e - (TP)td / (TP)g);
+        }
+        if (A.counts) {
+            long c = A.counts[pa];
+            remaining = c < 0 ? 0 : (c > 2000000000L ? 2000000000L : c);
+        }
+    }
+    float c[PMAX];
+    float smin = 0.f, smax = 1.f;
+    if (owner) {
+#pragma unroll
+        for (int L = 0; L < PMAX; ++L) c[L] = (L < A.P) ? A.coefs[(long)L * npl + pf] : 0.0f;
+        smin = A.Smin[pf];
+        smax = A.Smax[pf];
+    }
+    // IPC taps for the owner pixel (source-indexed kernel)
+    double kt[9];
+    bool kok[9];
+    {
+        const int DY[9] = {0, 1, -1, 0, 0, 1, 1, -1, -1};
+        const int DX[9] = {0, 0, 0, 1, -1, 1, -1, 1, -1};
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            const int ys = ya - DY[q], xs = xa - DX[q];
+            kok[q] = owner && K && ys >= 0 && ys < na && xs >= 0 && xs < na;
+            kt[q] = kok[q] ? (double)K[(long)((1 + DY[q]) * 3 + (1 + DX[q])) * npa + (long)ys * na + xs] : 0.0;
+        }
+    }
+    const double t_last = A.read_time * (double)A.read_index[A.n_reads - 1];
+    double t_prev = 0.0;  // romanisim starts the clock at the reset
+    long cum = 0;
+    int k = 0;
+    for (int grp = 0; grp < A.G; ++grp) {
+        double acc = 0.0;
+        for (int r = 0; r < A.reads_per_group[grp]; ++r, ++k) {
+            const double t = A.read_time * (double)A.read_index[k];
+            if (inside) {
+                if (A.cum_counts) {
+                    cum = A.cum_counts[(long)k * npa + pa];
+                } else if (remaining > 0 && t > t_prev) {
+                    const double p = (t_last > t_prev) ? (t - t_prev) / (t_last - t_prev) : 1.0;
+                    const long d = binomial_draw(rng, remaining, p >= 1.0 ? 1.0 : p);
+                    cum += d;
+                    remaining -= d;
+                }
+            }
+            t_prev = t;
+            __syncthreads();
+            se[ty][tx] = inside ? (double)(int32_t)cum + (double)start_e : 0.0;
+            __syncthreads();
+            if (owner) {
+                double conv;
+                if (K) {
+                    conv = se[ty][tx] * kt[0];
+                    if (kok[1]) conv = conv + se[ty - 1][tx] * kt[1];
+                    if (kok[2]) conv = conv + se[ty + 1][tx] * kt[2];
+                    if (kok[3]) conv = conv + se[ty][tx - 1] * kt[3];
+                    if (kok[4]) conv = conv + se[ty][tx + 1] * kt[4];
+                    if (kok[5]) conv = conv + se[ty - 1][tx - 1] * kt[5];
+                    if (kok[6]) conv = conv + se[ty - 1][tx + 1] * kt[6];
+                    if (kok[7]) conv = conv + se[ty + 1][tx - 1] * kt[7];
+                    if (kok[8]) conv = conv + se[ty + 1][tx + 1] * kt[8];
+                } else {
+                    conv = se[ty][tx];
+                }
+                bool ex;
+                const double S = invlin_pixel<double, PMAX>(conv / (double)g, c, A.P, smin, smax, ex);
+                acc = acc + S;
+            }
+        }
+        if (owner) {
+            // romanisim: resultant = mean of the reads in the group, stored float32
+            float res = (float)(acc / (double)A.reads_per_group[grp]);
+            if (A.add_read_noise) {
+                Philox rn;
+                rn.init(A.seed, (uint64_t)pa, 16u + (uint32_t)grp);
+                res = res + rn.normal() * (A.read[pf] / sqrtf((float)A.reads_per_group[grp]));
+            }
+            if (A.add_biascorr && A.bias) res = res + A.bias[(long)grp * npa + pa];
+            if (A.quantize) res = rintf(res);
+            A.out[(long)grp * npa + pa] = res;
+        }
+    }
+}
+
+}  // namespace rip
+
+using namespace rip;
+
+extern "C" int rip_il_apply_planes(int device, const void* counts, int c_dtype, int ny, int nx, const void* start_e,
+                                   int s_dtype, double start_scalar, const void* kernel, int k_dtype, const void* gain,
+                                   int g_dtype, const float* coefs, int P, const float* Smin, const float* Smax,
+                                   const float* Sref, int electrons, int electrons_out, double* out, int* out_dtype) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(counts && coefs && Smin && Smax && out, "rip_il_apply_planes: null argument");
+    RIP_REQUIRE(P >= 1 && P <= RIP_PMAX, "rip_il_apply_planes: P=%d outside 1..%d", P, RIP_PMAX);
+    RIP_REQUIRE(c_dtype == RIP_F32 || c_dtype == RIP_F64 || c_dtype == RIP_I32, "rip_il_apply_planes: counts dtype");
+    RIP_REQUIRE(!(electrons || electrons_out) || gain, "rip_il_apply_planes: gain needed for electron units");
+    RIP_REQUIRE(!electrons_out || Sref, "rip_il_apply_planes: Sref needed for electrons_out");
+    use_device(device);
+    const long npix = (long)ny * nx;
+    DevRaw dc, ds, dk, dg, tmp;
+    DevBuf<float> dco, dmin, dmax, dref;
+    DevBuf<double> dout(npix);
+    dc.upload(counts, npix * dtype_size(c_dtype));
+    if (start_e) ds.upload(start_e, npix * dtype_size(s_dtype));
+    if (kernel) dk.upload(kernel, 9 * npix * dtype_size(k_dtype));
+    if (gain) dg.upload(gain, npix * dtype_size(g_dtype));
+    dco.upload(coefs, (size_t)P * npix);
+    dmin.upload(Smin, npix);
+    dmax.upload(Smax, npix);
+    if (Sref) dref.upload(Sref, npix);
+    tmp.alloc(npix * 8);
+    IlWindow w;
+    w.ny = ny; w.nx = nx; w.K = kernel ? dk.p : nullptr; w.k_dtype = k_dtype;
+    w.gain = gain ? dg.p : nullptr; w.g_dtype = gain ? g_dtype : RIP_F32; w.gain_off = 0; w.gain_pitch = nx;
+    w.coefs = dco.p; w.Smin = dmin.p; w.Smax = dmax.p; w.Sref = dref.p; w.lin_plane = npix; w.lin_off = 0; w.lin_pitch = nx; w.P = P;
+    const int tag = il_apply_device(dc.p, c_dtype, start_e ? ds.p : nullptr, s_dtype, start_scalar, w, electrons, electrons_out, dout.p, tmp.p, 0);
+    dout.download(out, npix);
+    if (out_dtype) *out_dtype = tag;
+    RIP_CUDA(cudaDeviceSynchronize());
+    RIP_API_END
+}
+
+// ---- handle-based entry points ----------------------------------------------------------------------------
+#include "rip_handle.h"
+
+extern "C" int rip_il_apply(rip_caldir* h, const void* counts, int c_dtype, const float* start_e, int electrons,
+                            int electrons_out, double* out) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && counts && out, "rip_il_apply: null argument");
+    RIP_REQUIRE(c_dtype == RIP_F32 || c_dtype == RIP_F64 || c_dtype == RIP_I32, "rip_il_apply: counts dtype");
+    use_device(h->device);
+    cudaStream_t st = h->stream;
+    const int na = h->na, n = h->n, nb = h->nb;
+    const long npa = (long)na * na;
+    DevRaw dc, ds, tmp;
+    DevBuf<double> dout(npa);
+    dc.upload(counts, npa * dtype_size(c_dtype), st);
+    if (start_e) ds.upload(start_e, npa * 4, st);
+    tmp.alloc(npa * 8);
+    IlWindow w;
+    w.ny = na; w.nx = na; w.K = h->has_ipc ? h->ipc.p : nullptr; w.k_dtype = h->d.ipc_dtype;
+    w.gain = h->gain.p; w.g_dtype = h->d.gain_dtype; w.gain_off = (long)nb * n + nb; w.gain_pitch = n;
+    w.coefs = h->coefs.p; w.Smin = h->Smin.p; w.Smax = h->Smax.p; w.Sref = h->Sref.p;
+    w.lin_plane = (long)n * n; w.lin_off = (long)nb * n + nb; w.lin_pitch = n; w.P = h->P;
+    il_apply_device(dc.p, c_dtype, start_e ? ds.p : nullptr, RIP_F32, 0.0, w, electrons, electrons_out, dout.p, tmp.p, st);
+    dout.download(out, npa, st);
+    RIP_CUDA(cudaStreamSynchronize(st));
+    RIP_API_END
+}
+
+static void make_l1_impl(rip_caldir* h, const int32_t* d_counts, const int32_t* d_cum, const rip_fwd_params* prm,
+                         float* d_out, cudaStream_t st) {
+    RIP_REQUIRE(prm->G >= 1 && prm->G <= RIP_GMAX, "rip_make_l1: G=%d outside 1..%d", prm->G, RIP_GMAX);
+    RIP_REQUIRE(prm->n_reads >= 1 && prm->n_reads <= 64, "rip_make_l1: n_reads=%d outside 1..64", prm->n_reads);
+    int tot = 0;
+    for (int g = 0; g < prm->G; ++g) { RIP_REQUIRE(prm->reads_per_group[g] >= 1, "rip_make_l1: empty group"); tot += prm->reads_per_group[g]; }
+    RIP_REQUIRE(tot == prm->n_reads, "rip_make_l1: reads_per_group sums to %d, n_reads=%d", tot, prm->n_reads);
+    RIP_REQUIRE(!prm->add_reset_noise || h->resetnoise.p, "rip_make_l1: read file has no resetnoise plane");
+    RIP_REQUIRE(!(prm->add_biascorr && h->has_bias) || h->d.n_bias >= prm->G, "rip_make_l1: biascorr has fewer groups than the read pattern");
+    FwdArgs A;
+    memset(&A, 0, sizeof A);
+    A.n = h->n; A.nb = h->nb; A.na = h->na; A.G = prm->G; A.P = h->P; A.n_reads = prm->n_reads;
+    for (int g = 0; g < RIP_GMAX; ++g) A.reads_per_group[g] = prm->reads_per_group[g];
+    for (int k = 0; k < 64; ++k) A.read_index[k] = prm->read_index[k];
+    A.read_time = prm->read_time; A.seed = prm->seed;
+    A.add_read_noise = prm->add_read_noise; A.add_reset_noise = prm->add_reset_noise;
+    A.add_biascorr = prm->add_biascorr; A.quantize = prm->quantize;
+    A.biascorr_t0 = h->d.biascorr_t0; A.has_bias = h->has_bias ? 1 : 0;
+    A.counts = d_counts; A.cum_counts = d_cum;
+    A.coefs = h->coefs.p; A.Smin = h->Smin.p; A.Smax = h->Smax.p;
+    A.gain = h->gain.p; A.ipc = h->has_ipc ? h->ipc.p : nullptr; A.read = h->read.p; A.resetnoise = h->resetnoise.p;
+    A.dark_slope = h->dark_slope.p;
+    // sim_to_isim.py:256-258 adds the whole biascorr cube (same number of groups as the pattern)
+    A.bias = h->has_bias ? h->biascorr.p + (size_t)(h->d.n_bias - prm->G) * h->na * h->na : nullptr;
+    A.out = d_out;
+    dim3 grid((h->na + FTX - 1) / FTX, (h->na + FTY - 1) / FTY);
+    const int threads = (FTX + 2) * (FTY + 2);
+    const bool gd = h->d.gain_dtype == RIP_F64, kd = h->has_ipc && h->d.ipc_dtype == RIP_F64;
+#define FW(PM)                                                                                   \
+    do {                                                                                         \
+        if (!gd && !kd) RIP_LAUNCH((fwd_ramp_kernel<PM, float, float>), grid, threads, 0, st, A);  \
+        else if (gd && !kd) RIP_LAUNCH((fwd_ramp_kernel<PM, double, float>), grid, threads, 0, st, A); \
+        else if (!gd && kd) RIP_LAUNCH((fwd_ramp_kernel<PM, float, double>), grid, threads, 0, st, A); \
+        else RIP_LAUNCH((fwd_ramp_kernel<PM, double, double>), grid, threads, 0, st, A);           \
+    } while (0)
+    if (h->P <= 4) FW(4);
+    else if (h->P <= 11) FW(11);
+    else FW(RIP_PMAX);
+#undef FW
+}
+
+extern "C" int rip_make_l1_dev(rip_caldir* h, const int32_t* d_counts, const rip_fwd_params* prm, float* d_resultants,
+                               void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && d_counts && prm && d_resultants, "rip_make_l1_dev: null argument");
+    use_device(h->device);
+    make_l1_impl(h, d_counts, nullptr, prm, d_resultants, (cudaStream_t)stream);
+    RIP_API_END
+}
+
+extern "C" int rip_make_l1_host(rip_caldir* h, const int32_t* counts, const int32_t* cum_counts,
+                                const rip_fwd_params* prm, float* resultants) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && (counts || cum_counts) && prm && resultants, "rip_make_l1_host: null argument");
+    use_device(h->device);
+    cudaStream_t st = h->stream;
+    const size_t npa = (size_t)h->na * h->na;
+    DevBuf<int32_t> dc, dcum;
+    if (counts) dc.upload(counts, npa, st);
+    if (cum_counts) dcum.upload(cum_counts, npa * prm->n_reads, st);
+    DevBuf<float> dout(npa * prm->G);
+    make_l1_impl(h, counts ? dc.p : nullptr, cum_counts ? dcum.p : nullptr, prm, dout.p, st);
+    dout.download(resultants, npa * prm->G, st);
+    RIP_CUDA(cudaStreamSynchronize(st));
+    RIP_API_END
+}

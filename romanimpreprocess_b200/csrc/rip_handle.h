@@ -1,0 +1,44 @@
+// The CALDIR handle (opaque in the public ABI), shared by rip_caldir.cu and rip_fwd.cu.
+#pragma once
+#include "rip_rt.h"
+
+namespace rip {
+struct SelState { uint32_t prefix[2]; uint32_t rank[2]; };
+}
+using rip::DevBuf;
+using rip::DevRaw;
+using rip::SelState;
+
+struct rip_caldir {
+    int device = 0;
+    rip_caldir_desc d{};  // scalar fields only are meaningful after creation
+    int n = 0, nb = 0, na = 0, P = 0;
+    bool has_ipc = false, has_bias = false, has_amp33 = false;
+    double refout_slope = 0.0;
+    // CALDIR planes
+    DevBuf<float> coefs, Smin, Smax, Sref, sat_thr, read, resetnoise, dark_cube, dark_slope, biascorr, flat, amp_med;
+    DevBuf<uint32_t> lin_dq;
+    DevRaw gain, ipc;
+    // static products
+    DevBuf<float> thr_eff, dslope_ipc, flat_ipc;
+    DevBuf<uint8_t> aux;
+    DevBuf<uint32_t> sdq;
+    // K0 workspace
+    DevBuf<uint32_t> hist;
+    DevBuf<SelState> sel;
+    DevBuf<float> rowA, rowB, gmed;
+    DevBuf<double> rowcorr, chan_m, chan_c;
+    // host-entry workspace
+    DevBuf<uint16_t> w_raw, w_amp;
+    DevRaw w_area;
+    DevBuf<float> w_slope, w_er, w_ep, w_lin;
+    DevBuf<uint32_t> w_pdq;
+    DevBuf<int8_t> w_end;
+    DevBuf<uint8_t> w_rdq;
+    cudaStream_t stream = nullptr;
+    // optional per-launch timing of the fused kernel (rip_profile_enable): event pairs recorded on the launch stream
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev;  // [2*k] start, [2*k+1] stop
+    size_t prof_used = 0;
+};
+

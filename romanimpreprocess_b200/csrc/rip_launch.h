@@ -1,0 +1,25 @@
+// Internal device-pointer launchers shared between translation units (not part of the public ABI).
+#pragma once
+#include "rip_cal_core.cuh"
+#include "rip_rt.h"
+
+namespace rip {
+
+// rip_stage.cu ---------------------------------------------------------------------------------------------
+// In-place "DN-space" IPC deconvolution of the active region of one f32 plane [ny,nx] (border nb):
+//   plane_act <- f32( ipc_rev(plane_act * g, K, order=2) / g ),  g = gain_act (optionally clipped below at g_lo)
+// == one group of correct_cube (utils/ipc_linearity.py:185-186) == the IPC part of get_flat (flatutils.py:72-74).
+// tmp must hold nya*nxa elements of double.  gain may be null (g = 1).
+void launch_ipc_rev_dn(float* plane, int ny, int nx, int nb, const void* K, int k_dtype, const void* gain_full,
+                       int g_dtype, bool clip_gain, float g_lo, void* tmp, cudaStream_t st);
+
+// flat pad/flag/clip (utils/flatutils.py:44-69); pdq may be null
+void launch_flat_prepare(const float* flat, int n, int nb, const void* gain, int g_dtype, uint32_t* pdq,
+                         int ipc_deconvolve, float* out, cudaStream_t st);
+
+// rip_fit.cu -----------------------------------------------------------------------------------------------
+// The fused K1 kernel.  gain/ipc dtypes select the instantiation.  Plan must already be on the device.
+void launch_cal_fused(const CalArgs& A, int g_dtype, int k_dtype, int threads, cudaStream_t st);
+size_t cal_fused_smem_bytes(int G, int g_dtype, int k_dtype, int threads);
+
+}  // namespace rip

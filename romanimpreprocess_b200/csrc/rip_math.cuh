@@ -1,0 +1,275 @@
+// Per-pixel arithmetic of the L1->L2 path, written once for device and host.
+//
+// Everything here is __host__ __device__ so that tests/hostcheck can run the *same* source on the CPU (this
+// container has no GPU); the product never calls the host instantiation.  All translation units are compiled
+// with -fmad=false (nvcc) / -ffp-contract=off (g++): NumPy never fuses multiply-add and the parity contract
+//  is "same roundings as the reference", so every * and + below is a separate IEEE operation.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "rip_b200.h"
+
+#ifdef __CUDACC__
+#define RIP_HD __host__ __device__ __forceinline__
+#else
+#define RIP_HD inline
+#endif
+
+namespace rip {
+
+// DQ bits (roman_datamodels.dqflags.pixel)
+constexpr uint32_t DQ_DO_NOT_USE = 1u;
+constexpr uint32_t DQ_SATURATED = 2u;
+constexpr uint32_t DQ_JUMP_DET = 4u;
+constexpr uint32_t DQ_AD_FLOOR = 64u;
+constexpr uint32_t DQ_NO_FLAT_FIELD = 1u << 18;
+constexpr uint32_t DQ_NO_GAIN_VALUE = 1u << 19;
+constexpr uint32_t DQ_NO_LIN_CORR = 1u << 20;
+constexpr uint32_t DQ_NO_SAT_CHECK = 1u << 21;
+constexpr uint32_t DQ_REFERENCE_PIXEL = 1u << 31;
+
+
+RIP_HD float rip_sqrt(float x) { return sqrtf(x); }
+RIP_HD double rip_sqrt(double x) { return sqrt(x); }
+
+// ---- NumPy-flavoured min/max/clip: NaN propagates (np.clip / np.maximum semantics) ----
+template <typename T> RIP_HD T np_max(T a, T b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+template <typename T> RIP_HD T np_min(T a, T b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
+template <typename T> RIP_HD T np_clip(T x, T lo, T hi) { return np_min(np_max(x, lo), hi); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Legendre evaluation  (reference utils/ipc_linearity.py:215-231)
+//   phi = c0 + sum_{L>=1} c_L * (|z|>1 ? sign(z)^L (1 + L(L+1)/2 (|z|-1)) : P_L(z)),
+//   P_{L+1} = ((2L+1)/(L+1) z) P_L - (L/(L+1)) P_{L-1}, rational constants rounded to T first.
+// ---------------------------------------------------------------------------------------------------------
+//   NB (observed in the reference, pinned by the golden vectors): the accumulator `phi` is created as a copy of
+//   coefs[0], i.e. it has the dtype of the coefficient planes (float32) even when z is float64; each
+//   `phi += c_L * term` is evaluated in the promoted type TZ and rounded back to float32.
+template <typename TZ, int PMAX, bool LINEXTRAP>
+RIP_HD float legendre_eval(TZ z, const float (&c)[PMAX], int P, bool& ex) {
+    TZ az = z < 0 ? -z : z;  // fabs; NaN stays NaN
+    ex = az > (TZ)1;
+    float phi = c[0];
+    TZ prev = (TZ)1;
+    TZ cur = z;
+#pragma unroll
+    for (int L = 1; L < PMAX; ++L) {
+        if (L < P) {
+            TZ term = cur;
+            if (LINEXTRAP && ex) {
+                TZ s = (z > 0) ? (TZ)1 : ((L & 1) ? (TZ)-1 : (TZ)1);  // sign(z)^L, z != 0 here
+                TZ e = (TZ)(L * (L + 1) / 2.0);
+                term = s * ((TZ)1 + e * (az - (TZ)1));
+            }
+            phi = (float)((TZ)phi + (TZ)c[L] * term);
+            TZ a = (TZ)((2 * L + 1) / (double)(L + 1));
+            TZ b = (TZ)(L / (double)(L + 1));
+            TZ nxt = (a * z) * cur - b * prev;
+            prev = cur;
+            cur = nxt;
+        }
+    }
+    return phi;
+}
+
+// z = -1 + 2 (S - Smin) / (Smax - Smin)   (ipc_linearity.py:330)
+template <typename T> RIP_HD T lin_z(T S, T Smin, T Smax) { return (T)-1 + ((T)2 * (S - Smin)) / (Smax - Smin); }
+
+// One pixel through multilin (ipc_linearity.py:329-342): G groups in, G linearised groups out, dq updated.
+//   attempt_mask bit g = "try to flag group g" (the reference passes ~rdq & SATURATED, gen_cal_image.py:585)
+template <int GMAX, int PMAX>
+RIP_HD void multilin_pixel(const float (&S)[GMAX], int G, const float (&c)[PMAX], int P, float Smin, float Smax,
+                           float Sref, uint32_t& dq, uint32_t attempt_mask, bool do_not_flag_first,
+                           float (&phi)[GMAX]) {
+#pragma unroll
+    for (int j = 0; j < GMAX; ++j) {
+        if (j < G) {
+            float z = lin_z<float>(S[j], Smin, Smax);
+            const bool first = (j == 0) && do_not_flag_first;
+            if (first) z = np_clip<float>(z, -1.0f, 1.0f);
+            bool ex;
+            float p = legendre_eval<float, PMAX, true>(z, c, P, ex);
+            phi[j] = ((dq & (DQ_NO_LIN_CORR | DQ_REFERENCE_PIXEL)) == 0) ? p : (S[j] - Sref);
+            if (!first && ex && ((attempt_mask >> j) & 1u)) dq |= DQ_NO_LIN_CORR;
+        }
+    }
+}
+
+// 24-step bisection inverse (ipc_linearity.py:381-390) with z in type TZ (the reference runs it in float64
+// inside IL.apply because counts are int32: SURVEY App. A10).  (Smax-Smin)/2 is an f32 expression in the
+// reference (both planes are f32) and is promoted afterwards.
+template <typename TZ, int PMAX>
+RIP_HD TZ invlin_pixel(TZ Slin, const float (&c)[PMAX], int P, float Smin, float Smax, bool& ex) {
+    TZ z = (TZ)0;
+    TZ step = (TZ)1;
+    ex = false;
+    for (int j = 1; j < 25; ++j) {
+        step = step * (TZ)0.5;  // exact powers of two
+        float phi = legendre_eval<TZ, PMAX, false>(z, c, P, ex);
+        z = z + (((TZ)phi < Slin) ? step : -step);
+    }
+    float half = (Smax - Smin) / 2.0f;
+    return (TZ)Smin + (TZ)half * ((TZ)1 + z);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Ramp-fit plan (built on the host with NumPy so that every scalar has the reference's rounding; see
+// romanimpreprocess_b200/utils/fitting.py:build_plan).  Variant 0 is the full ramp, variant v>=1 is the ramp
+// truncated at iend = G - v (reference utils/fitting.py:165-169,326).
+// ---------------------------------------------------------------------------------------------------------
+using RampSlice = rip_ramp_slice;
+using RampPlanDev = rip_ramp_plan;
+
+// Exact variance of one slice's slope difference in the reference's op order (fitting.py:233-241; App. A7).
+//   TD = float when the gain plane is f32 (dvardt f32, inner term rounded to f32), double when it is f64.
+//   Takes only scalars (no register-array indexing) so the cold path never forces the ramp into local memory.
+template <typename TD>
+RIP_HD float smap_exact(float delta, int ngrp, TD dvardt, float sig2read, const RampPlanDev& pl, const double* w) {
+    double var = 0.0;
+    for (int a = 0; a < ngrp; ++a) {
+        TD inner = dvardt * (TD)pl.tau[a] + (TD)(sig2read / pl.nreads[a]);
+        var = var + (w[a] * w[a]) * (double)inner;
+        for (int b = 0; b < a; ++b) var = var + (((double)2 * w[a]) * w[b] * (double)dvardt) * (double)pl.tbar[b];
+    }
+    return delta / (float)sqrt(var);
+}
+
+// sthresh (f64) for a slope (fitting.py:215-217).  logf: CUDA/glibc logf vs NumPy's SIMD logf may differ in the
+// last ulp (SURVEY 7 "Bit-exact DQ vs float thresholds"); evaluated via double log and rounded to f32.
+RIP_HD double jump_threshold(float slope, const RampPlanDev& pl) {
+    float x = np_clip<float>(slope, pl.IthreshA_f, pl.IthreshB_f);
+    float t = (float)log((double)(x / pl.IthreshA_f));
+    double xx = (double)t / pl.logIratio;
+    return pl.SthreshA + (pl.SthreshB - pl.SthreshA) * xx;
+}
+
+struct FitResult {
+    float slope, err_read, err_poisson;
+    uint32_t jump_mask;  // bit i = JUMP_DET on group i
+};
+
+// jump_detect for one pixel and one plan variant (fitting.py:157-255).
+//   FAST=false: every slice in the reference's exact op order (used by the stage entry point; writes smap).
+//   FAST=true : factorised f32 variance; slices whose significance is within `band` of the threshold are
+//               re-evaluated exactly, so the flags are those of the exact path.
+// The (i, di) loops are the reference's (fitting.py:225-229) and fully unrolled so d[] is indexed statically.
+template <int GMAX, typename TD, bool FAST>
+RIP_HD FitResult jump_detect_pixel(const float (&d)[GMAX], int v, TD gain, float read, bool active,
+                                   const RampPlanDev& pl, const double* w_all, float* smap_out, long smap_stride) {
+    FitResult r;
+    const int ngrp = pl.var_ngrp[v];
+    const int start = pl.start;
+    float acc = 0.0f;
+#pragma unroll
+    for (int t = 0; t < GMAX; ++t)
+        if (t < ngrp) acc = acc + pl.var_K[v][t] * (d[t] - d[1]);
+    r.slope = acc;
+    TD gc = np_clip<TD>(gain, (TD)1e-4, (TD)1e4);
+    TD dvardt = np_max<TD>((TD)r.slope / gc, (TD)0);
+    r.err_poisson = (float)rip_sqrt(np_max<TD>((TD)pl.var_coef[v] * dvardt, (TD)0));
+    r.err_read = read * pl.var_rfac[v];
+    r.jump_mask = 0u;
+    if (FAST && !active) return r;
+    const float sig2read = read * read;
+    int s = pl.var_slice_off[v];
+    const int s0 = s;
+    double thr_exact = 0.0;
+    bool have_thr = false;
+    float hi = 0.0f, lo = 0.0f;
+    const float dv = (float)dvardt;
+    if (FAST) {
+        // approximate threshold: logf is within ~1e-6 relative of the reference's; the band absorbs it
+        float x = np_clip<float>(r.slope, pl.IthreshA_f, pl.IthreshB_f);
+        float thr = (float)pl.SthreshA + (float)(pl.SthreshB - pl.SthreshA) * (logf(x / pl.IthreshA_f) / (float)pl.logIratio);
+        hi = thr * (1.0f + pl.band);
+        lo = thr * (1.0f - pl.band);
+        if (hi < lo) { float tt = hi; hi = lo; lo = tt; }
+    } else {
+        thr_exact = jump_threshold(r.slope, pl);
+        have_thr = true;
+    }
+#pragma unroll
+    for (int i = 0; i < GMAX - 1; ++i) {
+        if (i >= start && i < ngrp - 1) {
+            const int dimax = (i == ngrp - 2 || ngrp - 1 - start == 2) ? 1 : 2;
+#pragma unroll
+            for (int di = 1; di <= 2; ++di) {
+                if (di <= dimax) {
+                    const RampSlice& sl = pl.slices[s];
+                    const float diff = d[(i + di < GMAX) ? (i + di) : (GMAX - 1)] - d[i];
+                    if (!FAST) {
+                        float sm = smap_exact<TD>(diff / sl.dt - r.slope, ngrp, dvardt, sig2read, pl, w_all + (long)s * RIP_GMAX);
+                        if (smap_out) smap_out[(long)(s - s0) * smap_stride] = sm;
+                        if (active && ((double)sm > thr_exact)) r.jump_mask |= 1u << i;
+                    } else {
+                        float var = dv * sl.A + sig2read * sl.B;
+                        float sm = (diff * sl.inv_dt - r.slope) / sqrtf(var);
+                        if (sm > hi) {
+                            r.jump_mask |= 1u << i;
+                        } else if (!(sm < lo)) {  // borderline, NaN or degenerate variance -> exact evaluation
+                            if (!have_thr) { thr_exact = jump_threshold(r.slope, pl); have_thr = true; }
+                            float sme = smap_exact<TD>(diff / sl.dt - r.slope, ngrp, dvardt, sig2read, pl, w_all + (long)s * RIP_GMAX);
+                            if ((double)sme > thr_exact) r.jump_mask |= 1u << i;
+                        }
+                    }
+                    ++s;
+                }
+            }
+        }
+    }
+    return r;
+}
+
+// Per-pixel group flags as bit masks over groups (bit g <-> group g).
+struct GroupFlags {
+    uint32_t dnu, sat, jump, adf;
+    uint32_t other_unsat;  // OR over unsaturated groups of any other rdq bits (stage entry point only)
+};
+
+// ramp_fit for one pixel (fitting.py:310-355).  Updates gf.jump and pdq.
+template <int GMAX, typename TD, bool FAST>
+RIP_HD FitResult ramp_fit_pixel(const float (&d)[GMAX], GroupFlags& gf, uint32_t& pdq, TD gain, float read,
+                                bool active, const RampPlanDev& pl, const double* w_all) {
+    const int G = pl.G;
+    FitResult r = jump_detect_pixel<GMAX, TD, FAST>(d, 0, gain, read, active, pl, w_all, nullptr, 0);
+    const bool unsat = ((gf.sat >> (G - 1)) & 1u) == 0u;
+    if (unsat) gf.jump |= r.jump_mask;
+    for (int iend = G - 1; iend > 2 + pl.start; --iend) {
+        const bool layer = ((gf.sat >> iend) & 1u) && !((gf.sat >> (iend - 1)) & 1u);
+        if (layer) {
+            FitResult t = jump_detect_pixel<GMAX, TD, FAST>(d, G - iend, gain, read, active, pl, w_all, nullptr, 0);
+            r.slope = t.slope;
+            r.err_read = t.err_read;
+            r.err_poisson = t.err_poisson;
+            gf.jump |= t.jump_mask;
+        }
+    }
+    const uint32_t allg = (G >= 32) ? 0xffffffffu : ((1u << G) - 1u);
+    const uint32_t unsat_g = ~gf.sat & allg;
+    uint32_t pdq2 = gf.other_unsat & ~DQ_DO_NOT_USE;
+    if (gf.jump & unsat_g) pdq2 |= DQ_JUMP_DET;
+    if (gf.adf & unsat_g) pdq2 |= DQ_AD_FLOOR;
+    if ((gf.dnu & allg) == allg) pdq2 |= DQ_DO_NOT_USE;
+    if ((gf.sat >> (1 + pl.start)) & 1u) pdq2 |= DQ_DO_NOT_USE;
+    if (gf.sat & allg) pdq2 |= DQ_SATURATED;
+    if ((pdq & DQ_REFERENCE_PIXEL) == 0u) pdq |= pdq2;
+    return r;
+}
+
+// do_ramp_fit packaging + dark + error split + flat (gen_cal_image.py:458-475,223-229,607-629).
+//   flat_area = f32(flat_ipc / AreaFactor) is computed by the caller (f64 or f32 area plane).
+RIP_HD void l2_epilogue(FitResult& r, bool active, float dark_slope_ipc, float flat_area) {
+    float err = (float)sqrt((double)r.err_read * (double)r.err_read + (double)r.err_poisson * (double)r.err_poisson);
+    float varp = r.err_poisson * r.err_poisson;
+    float slope = r.slope;
+    if (!active) { slope = 0.0f; varp = 0.0f; err = 0.0f; }
+    if (active) slope = slope - dark_slope_ipc;
+    float ep = sqrtf(varp);
+    float er = sqrtf(np_max<float>(err * err - ep * ep, 0.0f));
+    r.slope = slope / flat_area;
+    r.err_read = er / flat_area;
+    r.err_poisson = ep / flat_area;
+}
+
+}  // namespace rip

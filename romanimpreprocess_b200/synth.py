@@ -213,7 +213,7 @@ def meta_from_pattern(read_pattern, frame_time=FRAME_TIME):
     return meta
 
 
-def make_l1(cal, read_pattern, seed=200, n_sources=25, cr_frac=1e-3, sky=0.6, frame_time=FRAME_TIME):
+def make_l1(cal, read_pattern, seed=200, n_sources=25, cr_frac=1e-3, sky=0.6, frame_time=FRAME_TIME, bright=1.0):
     """A synthetic (not forward-modelled) L1 cube ``u16[G,n,n]`` + ``amp33 u16[G,n,128]`` for parity/throughput.
 
     raw = Sref + (sky + dark + sources)*tbar (mildly compressed near full well) + read noise + CR steps, with
@@ -232,7 +232,7 @@ def make_l1(cal, read_pattern, seed=200, n_sources=25, cr_frac=1e-3, sky=0.6, fr
     for j in range(n_sources):
         cx = 10 + (n - 20) * j / float(n_sources)
         cy = 10 + (n - 20) * ((13 * j) % n_sources) / float(n_sources)
-        amp = 4000.0 * j / texp  # DN/s at the peak; the brightest reach full well in the first groups
+        amp = bright * 4000.0 * j / texp  # DN/s at the peak; ``bright`` > 1 makes sources saturate in early groups
         rate += (amp * np.exp(-0.5 * ((xx - cx) ** 2 + (yy - cy) ** 2) / 2.0**2)).astype(np.float32)
     read = cal["read"]["roman"]["data"]
     cube = np.empty((G, n, n), dtype=np.float32)

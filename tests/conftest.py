@@ -27,6 +27,8 @@ SMALL_CASES = {
     "small_p11_f32": (40, "README_PATTERN", 10, np.float32, np.float32, 12),
     "small_p4_g64": (40, "TEST_READ_PATTERN", 3, np.float64, np.float32, 13),
     "small_p11_k64": (40, "README_PATTERN", 10, np.float32, np.float64, 14),
+    "small_sat_f32": (56, "README_PATTERN", 10, np.float32, np.float32, 15, 12.0),
+    "small_sat_g64k64": (56, "TEST_READ_PATTERN", 3, np.float64, np.float64, 16, 12.0),
 }
 
 
@@ -34,11 +36,12 @@ def build_small_case(tag):
     """Regenerate the seeded inputs of one golden case (digest-checked against the golden file)."""
     from romanimpreprocess_b200 import synth
 
-    n, rpname, p_order, gdt, kdt, seed = SMALL_CASES[tag]
+    n, rpname, p_order, gdt, kdt, seed = SMALL_CASES[tag][:6]
+    bright = SMALL_CASES[tag][6] if len(SMALL_CASES[tag]) > 6 else 1.0
     rp = getattr(synth, rpname)
     cal = synth.make_caldir(n=n, seed=seed, read_pattern=rp, p_order=p_order, gain_dtype=gdt, ipc_dtype=kdt,
                             sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
-    data_u16, amp33_u16, meta = synth.make_l1(cal, rp, seed=seed + 1, n_sources=9, cr_frac=0.01)
+    data_u16, amp33_u16, meta = synth.make_l1(cal, rp, seed=seed + 1, n_sources=9, cr_frac=0.01, bright=bright)
     return cal, data_u16, amp33_u16, meta, rp
 
 

@@ -75,7 +75,7 @@ def register(cal, tag):
     return names
 
 
-def small_case(tag, n, read_pattern, p_order, gain_dtype, ipc_dtype, seed):
+def small_case(tag, n, read_pattern, p_order, gain_dtype, ipc_dtype, seed, bright=1.0):
     """Run every size-agnostic reference function on one small synthetic case."""
     from romanimpreprocess.utils import fitting, flatutils, ipc_linearity
     from romanimpreprocess_b200 import synth
@@ -83,7 +83,7 @@ def small_case(tag, n, read_pattern, p_order, gain_dtype, ipc_dtype, seed):
 
     cal = synth.make_caldir(n=n, seed=seed, read_pattern=read_pattern, p_order=p_order, gain_dtype=gain_dtype,
                             ipc_dtype=ipc_dtype, sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
-    data_u16, amp33_u16, meta = synth.make_l1(cal, read_pattern, seed=seed + 1, n_sources=9, cr_frac=0.01)
+    data_u16, amp33_u16, meta = synth.make_l1(cal, read_pattern, seed=seed + 1, n_sources=9, cr_frac=0.01, bright=bright)
     names = register(cal, tag)
     out = {}
     out["input_digest"] = np.array(
@@ -256,4 +256,7 @@ if __name__ == "__main__":
     small_case("small_p11_f32", 40, synth.README_PATTERN, 10, np.float32, np.float32, 12)
     small_case("small_p4_g64", 40, synth.TEST_READ_PATTERN, 3, np.float64, np.float32, 13)
     small_case("small_p11_k64", 40, synth.README_PATTERN, 10, np.float32, np.float64, 14)
+    # bright sources: pixels saturate in every group, so each truncated refit of ramp_fit (fitting.py:326-337) fires
+    small_case("small_sat_f32", 56, synth.README_PATTERN, 10, np.float32, np.float32, 15, bright=12.0)
+    small_case("small_sat_g64k64", 56, synth.TEST_READ_PATTERN, 3, np.float64, np.float64, 16, bright=12.0)
     refsub_case()

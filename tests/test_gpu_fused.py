@@ -1,0 +1,152 @@
+"""GPU: the fused L1->L2 path (rip_l1_to_l2_host/_dev through ``calibrate_arrays``) against the oracle's restatement
+of ``calibrateimage`` (reference L1_to_L2/gen_cal_image.py:503-629,697-709) on the same seeded inputs.
+
+DQ (pdq, rdq), endslice: bit-exact.  slope / err_read / err_poisson / linearised+IPC-corrected cube: RTOL=1e-5
+(tests/parity.py).  At full size (4096^2) the oracle takes minutes, so parity there is checked through the K0
+statistics (cheap to restate), a row band of the frame, and tiling invariance.
+"""
+
+import numpy as np
+import pytest
+from conftest import SMALL_CASES, build_small_case
+from parity import assert_bits_equal, assert_float_close, band_check, compare_l2
+
+from oracle import rip_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CFG7 = {"RAMP_OPT_PARS": {"slope": 0.4, "gain": 1.8, "sigma_read": 7.0}, "SLICEOUT": True}
+
+
+def _run(cal, data, amp33, rp, area, cfg, do_refpix, **kw):
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+
+    with gci.CalDir(cal) as cd:
+        return gci.calibrate_arrays(cd, data, amp33, rp, 3.04, area, cfg, do_refpix=do_refpix, want_rdq=True,
+                                    want_lin_cube=True, want_endslice=True, **kw)  # fmt: skip
+
+
+@pytest.mark.parametrize("tag", list(SMALL_CASES))
+def test_small_cases(tag):
+    from romanimpreprocess_b200 import synth
+
+    cal, data_u16, amp33_u16, meta, rp = build_small_case(tag)
+    n = data_u16.shape[1]
+    area = synth.make_area_factor(n)
+    c = {k: v["roman"] for k, v in cal.items()}
+    ref = orc.l1_to_l2(data_u16, amp33_u16, c, rp, 3.04, area, CFG7, do_refpix=False, return_intermediates=True)
+    for threads, band in ((0, 0), (32, 16), (64, 7)):
+        out = _run(cal, data_u16, amp33_u16, rp, area, CFG7, False, threads=threads, band_rows=band)
+        stats = compare_l2(out, ref)
+        assert np.array_equal(out["meta"]["K"], ref["K"])
+        print(tag, threads, band, "values not bit-identical:", stats)
+
+
+MEDIUM = [
+    (256, "README_PATTERN", 10, np.float32, np.float32, 21, {}, 1.0, np.float64),
+    (256, "LONG16_PATTERN", 10, np.float32, np.float32, 22, {"EXCLUDE_FIRST": False, "SATURATION_BACKUP": 2}, 4.0, np.float32),
+    (384, "TEST_READ_PATTERN", 3, np.float64, np.float64, 23,
+     {"JUMP_DETECT_PARS": {"SthreshA": 4.0, "SthreshB": 3.5, "IthreshA": 0.6, "IthreshB": 600.0}}, 2.0, np.float64),
+    (256, "README_PATTERN", 10, np.float32, np.float64, 24, {"SATURATION_BACKUP": 0}, 8.0, None),
+    (512, "README_PATTERN", 15, np.float64, np.float32, 25, {}, 3.0, np.float64),
+]  # fmt: skip
+
+
+@pytest.mark.parametrize("case", MEDIUM, ids=[f"n{c[0]}_{c[1]}_s{c[5]}" for c in MEDIUM])
+def test_medium_cases_with_refpix(case):
+    from romanimpreprocess_b200 import synth
+
+    n, rpname, po, gdt, kdt, seed, cfg, bright, adt = case
+    rp = getattr(synth, rpname)
+    cal = synth.make_caldir(n=n, seed=seed, read_pattern=rp, p_order=po, gain_dtype=gdt, ipc_dtype=kdt,
+                            sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
+    data_u16, amp33_u16, _ = synth.make_l1(cal, rp, seed=seed + 1, n_sources=25, cr_frac=0.01, bright=bright)
+    area = None if adt is None else synth.make_area_factor(n, adt)
+    c = {k: v["roman"] for k, v in cal.items()}
+    ref = orc.l1_to_l2(data_u16, amp33_u16, c, rp, 3.04, 1.0 if area is None else area, cfg, do_refpix=True,
+                       return_intermediates=True)  # fmt: skip
+    out = _run(cal, data_u16, amp33_u16, rp, area, cfg, True)
+    stats = compare_l2(out, ref)
+    print(case[:2], "values not bit-identical:", stats)
+    assert np.count_nonzero(ref["pdq"] & orc.SATURATED) > 50
+    assert np.count_nonzero(ref["pdq"] & orc.JUMP_DET) > 50
+    assert len(np.unique(ref["endslice"])) >= 4
+
+
+def test_static_products_against_oracle():
+    """K2: IPC-corrected dark slope (gen_cal_image.py:217-221), get_flat product + flags (flatutils.py:44-76)."""
+    from hostcheck import harness
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+
+    cal, *_ = build_small_case("small_sat_g64k64")
+    c = {k: v["roman"] for k, v in cal.items()}
+    thr, aux, sdq, dslope, flat = harness.static_products(c)
+    with gci.CalDir(cal) as cd:
+        sp = cd.static_products()
+        assert sp["refout_slope"] == float(orc.optimal_refout_slope(c["read"]))
+    assert_float_close(sp["dark_slope_ipc"], dslope, "dark_slope_ipc")
+    assert_float_close(sp["flat"], flat, "flat")
+    assert_bits_equal(sp["static_dq"], sdq, "static_dq")
+
+
+@pytest.fixture(scope="module")
+def full_case():
+    from romanimpreprocess_b200 import synth
+
+    rp = synth.README_PATTERN
+    cal = synth.make_caldir(n=4096, seed=1000, read_pattern=rp, p_order=10, gain_dtype=np.float32,
+                            ipc_dtype=np.float32, sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
+    data_u16, amp33_u16, _ = synth.make_l1(cal, rp, seed=200, n_sources=25, cr_frac=1e-3, bright=3.0)
+    area = synth.make_area_factor(4096, np.float64)
+    return cal, data_u16, amp33_u16, rp, area
+
+
+def test_full_size_refpix_stats(full_case):
+    """K0 at 4096^2 x 8: per-row / global / per-channel medians and the f64 corrections vs a NumPy restatement of
+    gen_cal_image.py:531-555 + reference_subtraction.py (medians only -- seconds on the CPU)."""
+    import ctypes as C
+
+    from hostcheck import harness
+    from romanimpreprocess_b200 import _lib
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+
+    cal, data_u16, amp33_u16, rp, area = full_case
+    c = {k: v["roman"] for k, v in cal.items()}
+    G, n, _ = data_u16.shape
+    rc_ref, cm_ref, cc_ref = harness.refpix_stats(data_u16, amp33_u16, c)
+    rc, cm, cc, gm = np.empty((G, n)), np.empty((G, 32)), np.empty((G, 32)), np.empty(G, np.float32)
+    with gci.CalDir(cal) as cd:
+        _lib.check(_lib.lib().rip_refpix_stats_host(cd.handle, _lib.ptr(data_u16), _lib.ptr(amp33_u16), G, _lib.ptr(rc),
+                                                    _lib.ptr(cm), _lib.ptr(cc), _lib.ptr(gm)))  # fmt: skip
+    assert np.array_equal(rc, rc_ref), np.abs(rc - rc_ref).max()
+    assert np.array_equal(cm, cm_ref) and np.array_equal(cc, cc_ref)
+    for j in range(G):
+        ro = amp33_u16[j].astype(np.float32) - c["read"]["amp33"]["med"]
+        assert gm[j] == np.median(ro)
+
+
+def test_full_size_band_and_tiling_invariance(full_case):
+    """4096^2 x 8, P=11 (BASELINE configs[1]/[0] shape): (1) a 64-row band + halo is cut out and run through the
+    oracle with the full-frame K0 statistics -> must match the band of the full-frame CUDA result;
+    (2) results are invariant under the tile geometry (threads, band_rows)."""
+    from hostcheck import harness
+
+    cal, data_u16, amp33_u16, rp, area = full_case
+    cfg = dict(CFG7)
+    out = _run(cal, data_u16, amp33_u16, rp, area, cfg, True)
+    out2 = _run(cal, data_u16, amp33_u16, rp, area, cfg, True, threads=256, band_rows=512)
+    for k in ("slope", "err_read", "err_poisson", "lin_cube"):
+        assert np.array_equal(out[k], out2[k], equal_nan=True), k
+    for k in ("pdq", "rdq", "endslice"):
+        assert np.array_equal(out[k], out2[k]), k
+    # border semantics (gen_cal_image.py:470-475): science border zero, reference-pixel flag kept
+    assert np.all(out["slope"][:4] == 0) and np.all(out["slope"][:, -4:] == 0)
+    assert np.all(out["pdq"][:4] & orc.REFERENCE_PIXEL) and np.all(out["pdq"][4:-4, 4:-4] & orc.REFERENCE_PIXEL == 0)
+    assert np.count_nonzero(out["pdq"] & orc.SATURATED) > 1000 and np.count_nonzero(out["pdq"] & orc.JUMP_DET) > 5000
+
+    # band check against the oracle
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+
+    with gci.CalDir(cal) as cd:
+        sp = cd.static_products()
+    band_check(out, cal, data_u16, amp33_u16, rp, area, sp["flat"], sp["dark_slope_ipc"])

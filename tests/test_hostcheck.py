@@ -1,0 +1,80 @@
+"""CPU: the fused kernel's per-pixel source (csrc/rip_cal_core.cuh, csrc/rip_math.cuh), compiled for the host and
+walked through the kernel's tile / march schedule (tests/hostcheck), against the oracle.
+
+This is a logic check of the shared __host__ __device__ source in the GPU-less container (ring depths, halos, tile
+seams, DQ propagation, every truncation branch); the product parity gate is tests/test_gpu_fused.py.
+"""
+
+import numpy as np
+import pytest
+from conftest import SMALL_CASES, build_small_case
+from hostcheck import harness
+from parity import compare_l2
+
+from oracle import rip_oracle as orc
+from romanimpreprocess_b200 import synth
+
+CFG7 = {"RAMP_OPT_PARS": {"slope": 0.4, "gain": 1.8, "sigma_read": 7.0}}
+
+
+@pytest.mark.parametrize("tag", list(SMALL_CASES))
+def test_small_cases(tag):
+    cal, data_u16, amp33_u16, meta, rp = build_small_case(tag)
+    n = data_u16.shape[1]
+    area = synth.make_area_factor(n)
+    c = {k: v["roman"] for k, v in cal.items()}
+    ref = orc.l1_to_l2(data_u16, amp33_u16, c, rp, 3.04, area, CFG7, do_refpix=False, return_intermediates=True)
+    for threads, band in ((32, 16), (64, 7), (128, 40)):
+        out = harness.run_fused(cal, data_u16, amp33_u16, rp, 3.04, area, CFG7, do_refpix=False, threads=threads,
+                                band_rows=band)  # fmt: skip
+        stats = compare_l2(out, ref, lin_key="ipc")
+        assert all(v == 0 for v in stats.values()), stats  # in fact bit-identical
+
+
+MEDIUM = [
+    # n, pattern, order, gain dtype, ipc dtype, seed, config, threads, band, bright
+    (256, "README_PATTERN", 10, np.float32, np.float32, 21, {}, 64, 32, 1.0),
+    (256, "LONG16_PATTERN", 10, np.float32, np.float32, 22, {"EXCLUDE_FIRST": False, "SATURATION_BACKUP": 2}, 128, 100, 4.0),
+    (384, "TEST_READ_PATTERN", 3, np.float64, np.float64, 23,
+     {"JUMP_DETECT_PARS": {"SthreshA": 4.0, "SthreshB": 3.5, "IthreshA": 0.6, "IthreshB": 600.0}}, 96, 7, 2.0),
+    (256, "README_PATTERN", 10, np.float32, np.float64, 24, {"SATURATION_BACKUP": 0}, 256, 256, 8.0),
+]  # fmt: skip
+
+
+@pytest.mark.parametrize("case", MEDIUM, ids=[f"n{c[0]}_{c[1]}_s{c[5]}" for c in MEDIUM])
+def test_medium_cases_with_refpix(case):
+    n, rpname, po, gdt, kdt, seed, cfg, threads, band, bright = case
+    rp = getattr(synth, rpname)
+    cal = synth.make_caldir(n=n, seed=seed, read_pattern=rp, p_order=po, gain_dtype=gdt, ipc_dtype=kdt,
+                            sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
+    data_u16, amp33_u16, _ = synth.make_l1(cal, rp, seed=seed + 1, n_sources=25, cr_frac=0.01, bright=bright)
+    area = synth.make_area_factor(n)
+    c = {k: v["roman"] for k, v in cal.items()}
+    ref = orc.l1_to_l2(data_u16, amp33_u16, c, rp, 3.04, area, cfg, do_refpix=True, return_intermediates=True)
+    out = harness.run_fused(cal, data_u16, amp33_u16, rp, 3.04, area, cfg, do_refpix=True, threads=threads,
+                            band_rows=band)  # fmt: skip
+    stats = compare_l2(out, ref, lin_key="ipc")
+    assert all(v == 0 for v in stats.values()), stats
+    # the case must exercise what it claims to
+    assert np.count_nonzero(ref["pdq"] & orc.SATURATED) > 50
+    assert np.count_nonzero(ref["pdq"] & orc.JUMP_DET) > 50
+    assert np.count_nonzero(ref["pdq"] & orc.NO_LIN_CORR) > 0
+    assert len(np.unique(ref["endslice"])) >= 4
+
+
+def test_band_check_helper_on_host():
+    """The row-band comparison used for the 4096^2 GPU case (tests/parity.py:band_check), exercised here at n=512."""
+    from parity import band_check
+
+    rp = synth.README_PATTERN
+    n = 512
+    cal = synth.make_caldir(n=n, seed=31, read_pattern=rp, p_order=10, gain_dtype=np.float32, ipc_dtype=np.float32,
+                            sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
+    data_u16, amp33_u16, _ = synth.make_l1(cal, rp, seed=32, n_sources=25, cr_frac=1e-2, bright=3.0)
+    area = synth.make_area_factor(n, np.float64)
+    out = harness.run_fused(cal, data_u16, amp33_u16, rp, 3.04, area, CFG7, do_refpix=True, threads=128, band_rows=128)
+    out["lin_cube"] = out["ipc"]
+    c = {k: v["roman"] for k, v in cal.items()}
+    _, _, _, dslope, flat = harness.static_products(c)
+    y0, y1 = band_check(out, cal, data_u16, amp33_u16, rp, area, flat, dslope)
+    assert y1 - y0 == 64
