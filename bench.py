@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the L1->L2 calibration hot path: calibrated SCA frames/s (4096^2 x 8 resultants).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference algorithm on the host cores (oracle port)
+
+A "step" is one pass of the hot path over one SCA exposure per GPU: u16 L1 cube [8,4096,4096] + amp33 -> slope,
+err_read, err_poisson, pdq, endslice (reference L1_to_L2/gen_cal_image.py:503-629,697-709), order-10 Legendre
+linearity (P=11), f32 calibration planes, reference-pixel correction, IPC deconvolution and jump/saturation flagging
+on.  Inputs are synthetic (romanimpreprocess_b200/synth.py: the reference's gencal fixture recipe + a synthetic L1).
+
+Reported on ONE JSON line: ``value`` = SCA/s with the exposure already resident in HBM (device-pointer C ABI,
+CUDA-event timed, max over ranks); ``e2e`` = SCA/s through the host-buffer API (``calibrate_arrays`` ->
+``rip_l1_to_l2_host``) with the H2D/D2H copies from/to pinned memory inside the timed region; ``roofline`` for the
+fused kernel (algorithmic bytes B(G,P)*n^2 / its CUDA-event duration vs the measured HBM copy bandwidth);
+``cpu_baseline`` = the oracle (NumPy port of the reference) on a bounded sub-frame on the host.
+Multi-GPU: one process per GPU (torchrun), SCAs are independent -> no collective on the data path (weak scaling).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "calibrated SCA frames/sec (4096^2 x 8 resultants)"
+UNIT = "SCA/s"
+N_SIDE = 4096
+P_ORDER = 10
+
+
+def bytes_per_pixel(G, P):
+    """Algorithmic HBM bytes per pixel of the fused L1->L2 pass: B(G,P) = 10.0625 G + 4 P + 105."""
+    return 10.0625 * G + 4.0 * P + 105.0
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")  # fmt: skip
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                clk, mx = float(f[0]), float(f[1])
+            except ValueError:
+                continue
+            smax = mx
+            if t0 - 0.05 <= t <= t1 + 0.05:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: use everything
+            for _, line in self.rows:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}  # fmt: skip
+
+
+def make_inputs(n, read_pattern, n_exposures, seed=1000):
+    from romanimpreprocess_b200 import synth
+
+    cal = synth.make_caldir(n=n, seed=seed, read_pattern=read_pattern, p_order=P_ORDER, gain_dtype=np.float32,
+                            ipc_dtype=np.float32, sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
+    data, amp33, _ = synth.make_l1(cal, read_pattern, seed=200, n_sources=25, cr_frac=1e-3, bright=3.0)
+    rng = np.random.default_rng(seed + 1)
+    exposures = [(data, amp33)]
+    for _ in range(1, n_exposures):  # further exposures: the same scene with fresh +-3 DN noise (cheap to draw)
+        d = (data.astype(np.int32) + rng.integers(-3, 4, size=data.shape, dtype=np.int8)).clip(0, 65535).astype(np.uint16)
+        a = (amp33.astype(np.int32) + rng.integers(-3, 4, size=amp33.shape, dtype=np.int8)).clip(0, 65535).astype(np.uint16)
+        exposures.append((d, a))
+    area = synth.make_area_factor(n, np.float32)
+    return cal, exposures, area
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference arm / cpu baseline: the oracle (NumPy port of the reference) on host cores
+# ---------------------------------------------------------------------------------------------------------------
+def _oracle_tile(args):
+    """One bounded sample: the full oracle L1->L2 chain on an m x m sub-frame (same G, P, flags)."""
+    m, seed = args
+    from oracle import rip_oracle as orc
+    from romanimpreprocess_b200 import synth
+
+    rp = synth.README_PATTERN
+    cal = synth.make_caldir(n=m, seed=seed, read_pattern=rp, p_order=P_ORDER, gain_dtype=np.float32,
+                            ipc_dtype=np.float32, sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
+    data, amp33, _ = synth.make_l1(cal, rp, seed=seed + 1, n_sources=25, cr_frac=1e-3, bright=3.0)
+    area = synth.make_area_factor(m, np.float32)
+    c = {k: v["roman"] for k, v in cal.items()}
+    t = time.perf_counter()
+    orc.l1_to_l2(data, amp33, c, rp, synth.FRAME_TIME, area, {"SLICEOUT": True}, do_refpix=True)
+    return time.perf_counter() - t
+
+
+def cpu_baseline_single(m=1024):
+    """Oracle on one core on an m^2 sub-frame; returns the cpu_baseline object."""
+    dt = _oracle_tile((m, 77))
+    frac = (m * m) / float(N_SIDE * N_SIDE)
+    return {"value": frac / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"oracle/rip_oracle.py l1_to_l2 (NumPy port of the reference chain) on one {m}x{m} sub-frame "
+                      f"(1/{int(round(1 / frac))} of an SCA, same G=8, P=11, refpix+IPC+jump flags), {dt:.1f} s, "
+                      "scaled by pixel count"}  # fmt: skip
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm (oracle port; the Python reference cannot travel to the GPU box and
+    needs asdf/romancal) on all host cores, one independent sub-frame per process per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    m = 512
+    frac = (m * m) / float(N_SIDE * N_SIDE)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        for w in range(args.warmup):
+            pool.map(_oracle_tile, [(128, 10 + i) for i in range(cores)])  # warm the workers (imports, BLAS)
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            pool.map(_oracle_tile, [(m, 100 + 17 * s + i) for i in range(cores)])
+        dt = time.perf_counter() - t0
+    value = args.steps * cores * frac / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "gen_cal_image L1->L2, one 4096^2 x 8-resultant SCA, P=11, CPU reference path "
+                               "(BASELINE configs[0])", "step": f"{cores} independent {m}x{m} sub-frames"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"per step: {cores} processes x one {m}x{m} sub-frame through oracle.l1_to_l2, "
+                                   "scaled by pixel count"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }  # fmt: skip
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from romanimpreprocess_b200 import _lib, synth
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+
+    rp = synth.README_PATTERN if args.groups == 8 else synth.LONG16_PATTERN
+    G, n = len(rp), args.n
+    n_exp = max(2, args.exposures)
+    cal, exposures, area = make_inputs(n, rp, n_exp, seed=1000 + rank)
+    cfg = {"SLICEOUT": True}
+    cd = gci.CalDir(cal, device=local)
+    dplan = gci.DevicePlan(cd, rp, synth.FRAME_TIME, cfg, do_refpix=True, area_dtype=np.float32,
+                           threads=args.threads, band_rows=args.band_rows)  # fmt: skip
+    na = n - 8
+
+    # ---- device-resident leg -------------------------------------------------------------------------------
+    d_raw = [torch.from_numpy(d.view(np.int16)).to(dev) for d, _ in exposures]
+    d_amp = [torch.from_numpy(a.view(np.int16)).to(dev) for _, a in exposures]
+    d_area = torch.from_numpy(area).to(dev)
+    o_slope = torch.empty((n, n), dtype=torch.float32, device=dev)
+    o_er = torch.empty_like(o_slope)
+    o_ep = torch.empty_like(o_slope)
+    o_pdq = torch.empty((n, n), dtype=torch.int32, device=dev)
+    o_end = torch.empty((na, na), dtype=torch.int8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(i):
+        k = i % n_exp
+        gci.calibrate_device(cd, dplan, d_raw[k].data_ptr(), d_amp[k].data_ptr(), d_area.data_ptr(), o_slope.data_ptr(),
+                             o_er.data_ptr(), o_ep.data_ptr(), o_pdq.data_ptr(), d_endslice=o_end.data_ptr(),
+                             stream=stream)  # fmt: skip
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    _lib.check(lib.rip_profile_enable(cd.handle, 1))
+    l0 = lib.rip_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record()
+    barrier()
+    t1 = time.perf_counter()
+    launches = lib.rip_launch_count() - l0
+    ms_total = ev0.elapsed_time(ev1)
+    import ctypes as C
+
+    fused_ms, fused_n = C.c_double(0), C.c_int(0)
+    _lib.check(lib.rip_profile_fetch(cd.handle, C.byref(fused_ms), C.byref(fused_n)))
+    _lib.check(lib.rip_profile_enable(cd.handle, 0))
+    clocks = sampler.stop(t0, t1) if sampler else None
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total_max = float(tmax.item())
+    value = world * args.steps / (ms_total_max * 1e-3)
+
+    # ---- end-to-end leg: host buffers in, host buffers out, through the public API --------------------------
+    h_in = []
+    for d, a in exposures:
+        pd, pa = _lib.pinned_empty(d.shape, np.uint16), _lib.pinned_empty(a.shape, np.uint16)
+        pd[...] = d
+        pa[...] = a
+        h_in.append((pd, pa))
+    h_area = _lib.pinned_empty(area.shape, np.float32)
+    h_area[...] = area
+    h_out = {"slope": _lib.pinned_empty((n, n), np.float32), "err_read": _lib.pinned_empty((n, n), np.float32),
+             "err_poisson": _lib.pinned_empty((n, n), np.float32), "pdq": _lib.pinned_empty((n, n), np.uint32),
+             "endslice": _lib.pinned_empty((na, na), np.int8)}  # fmt: skip
+
+    def e2e_step(i):
+        d, a = h_in[i % n_exp]
+        gci.calibrate_arrays(cd, d, a, rp, synth.FRAME_TIME, h_area, cfg, do_refpix=True, want_endslice=True,
+                             threads=args.threads, band_rows=args.band_rows, out=h_out, dplan=dplan)  # fmt: skip
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    te0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(2 + i)
+    torch.cuda.synchronize()
+    te = time.perf_counter() - te0
+    temax = torch.tensor([te], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(temax, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps / float(temax.item())
+    h2d = int(exposures[0][0].nbytes + exposures[0][1].nbytes + area.nbytes)
+    d2h = int(sum(v.nbytes for v in h_out.values()))
+    checksum = int(h_out["pdq"].astype(np.uint64).sum() % (1 << 32))
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        algo_bytes = bytes_per_pixel(G, P_ORDER + 1) * n * n
+        fused_avg_ms = fused_ms.value / max(fused_n.value, 1)
+        achieved = algo_bytes / (fused_avg_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "fused_traffic.json")  # dram bytes per launch from the ncu --set full capture
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as f:
+                    traffic = json.load(f).get(f"G{G}_P{P_ORDER + 1}_n{n}")
+            except Exception:  # noqa: BLE001
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"fused L1->L2 (gen_cal_image chain), one {n}^2 x {G}-resultant SCA per GPU per step, "
+                            f"Legendre order {P_ORDER} (P={P_ORDER + 1}), f32 CALDIR planes, refpix + IPC + ramp fit + "
+                            "jump/saturation flags + dark + flat/area + endslice (BASELINE metric config)",
+                "l2_policy": f"inputs larger than L2: each step streams {algo_bytes / 1e9:.2f} GB (126 MB L2) and "
+                             f"{n_exp} distinct exposures are rotated",
+                "threads": args.threads or 128, "band_rows": args.band_rows or 128, "parallelism": f"sca-sharded x{world}",
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "cal_fused_kernel",
+                         "kernel_ms": fused_avg_ms, "algorithmic_bytes": algo_bytes,
+                         "step_share": fused_ms.value / ms_total},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "gen_cal_image.calibrate_arrays -> rip_l1_to_l2_host (pinned host buffers)",
+                    "pdq_checksum": checksum},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }  # fmt: skip
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_single(args.cpu_tile)
+        print(json.dumps(line), flush=True)
+    cd.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=N_SIDE, help="frame side (default 4096; smaller only for debugging)")
+    ap.add_argument("--groups", type=int, default=8, choices=[8, 16])
+    ap.add_argument("--exposures", type=int, default=3, help="distinct resident exposures rotated through the steps")
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--band-rows", type=int, default=0)
+    ap.add_argument("--cpu-tile", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

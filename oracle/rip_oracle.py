@@ -13,7 +13,7 @@ compares.  Calibration data are passed as arrays / in-memory trees instead of AS
 PARITY UNPINNED for the third-party steps whose source is not in the reference tree (romancal ``do_dqinit``,
 ``flag_saturation`` -> stcal ``flag_saturated_pixels``, ``subtract_dark_current``, ``_create_image_model``,
 romanisim ``apportion_counts_to_resultants`` / ``add_read_noise_to_resultants``): functions ``dq_init``,
-``flag_saturation``, ``subtract_dark_current``, ``apportion_counts`` and ``add_read_noise`` below restate the
+``flag_saturation``, ``subtract_dark_current`` and ``make_l1_fullcal`` (apportioning + read noise) below restate the
 behaviour recorded in SURVEY.md Appendix D (from the reference's call sites and docs); the reference holds no
 golden vector for them.
 """
@@ -564,3 +564,63 @@ def forward_deterministic(mean_counts_per_read, cal, read_pattern, start_e):
             k += 1
         res.append((acc / len(grp)).astype(np.float32))
     return np.stack(res)
+
+
+def make_l1_fullcal(counts, cal, read_pattern, rng, read_time=3.04, add_reset_noise=True, add_read_noise=True,
+                    quantize=True, cum_counts_out=None):  # fmt: skip
+    """make_l1_fullcal (from_sim/sim_to_isim.py:195-260) with romanisim's apportioning and read noise RESTATED
+    (parity unpinned): NumPy ``rng`` (a ``np.random.Generator``) instead of GalSim deviates.
+
+    counts int32 [na,na] total electrons of the exposure.  Reset noise N(0,1)*resetnoise*gain - t0*dark_slope/gain
+    (:195-215); per read, electrons so far ~ sequential Binomial(remaining, dt/(t_last - t_prev)); IL.apply per read
+    (float64); resultant = mean over the group's reads (float32); + N(0,1)*read/sqrt(N) (:246-253); + biascorr
+    (:256-258); round (:260).  Returns float32 [G,na,na].
+    """
+    nb = 4
+    lin = cal["linearitylegendre"]
+    gain = cal["gain"]["data"]
+    g_act = gain[nb:-nb, nb:-nb]
+    na = counts.shape[0]
+    start_e = np.zeros((na, na), dtype=np.float32)
+    if add_reset_noise:
+        start_e = rng.standard_normal((na, na), dtype=np.float32)
+        start_e *= cal["read"]["resetnoise"][nb:-nb, nb:-nb]
+        start_e = (start_e * g_act).astype(np.float32)
+    if "biascorr" in cal:
+        tbias = float(cal["biascorr"]["t0"])
+        start_e = (start_e - tbias * cal["dark"]["dark_slope"][nb:-nb, nb:-nb] / g_act).astype(np.float32)
+    tij = read_pattern_to_tij(read_pattern, read_time)
+    t_last = tij[-1][-1]
+    remaining = np.clip(counts, 0, 2000000000).astype(np.int64)
+    cum = np.zeros((na, na), dtype=np.int64)
+    t_prev = 0.0
+    res = []
+    k = 0
+    for grp in tij:
+        acc = None
+        for t in grp:
+            if t > t_prev:
+                p = (t - t_prev) / (t_last - t_prev) if t_last > t_prev else 1.0
+                d = rng.binomial(remaining, min(p, 1.0))
+                cum += d
+                remaining -= d
+            t_prev = t
+            if cum_counts_out is not None:
+                cum_counts_out[k] = cum
+            k += 1
+            s = il_apply(cum.astype(np.int32), lin, gain, cal["ipc4d"]["data"] if "ipc4d" in cal else None,
+                         start_e=start_e)  # fmt: skip
+            acc = s if acc is None else acc + s
+        res.append((acc / len(grp)).astype(np.float32))
+    res = np.stack(res)
+    if add_read_noise:
+        for g, grp in enumerate(tij):
+            res[g] += rng.standard_normal((na, na), dtype=np.float32) * (
+                cal["read"]["data"][nb:-nb, nb:-nb] / np.float32(np.sqrt(np.float32(len(grp))))
+            )
+    if "biascorr" in cal:
+        bc = cal["biascorr"]["data"]
+        res += bc[bc.shape[0] - len(tij) :]
+    if quantize:
+        res = np.round(res)
+    return res.astype(np.float32)

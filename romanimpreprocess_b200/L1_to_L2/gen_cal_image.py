@@ -98,11 +98,12 @@ class CalDir:
             put("Smin", r["Smin"], np.float32)
             put("Smax", r["Smax"], np.float32)
             put("Sref", r["Sref"], np.float32)
-            put("lin_dq", r["dq"], np.uint32)
+            ldq = put("lin_dq", r["dq"], np.uint32)
         self.P, self.n = coefs.shape[0], coefs.shape[-1]
         self.nb = pars.nborder
         self.na = self.n - 2 * self.nb
         d.n, d.nb, d.P = self.n, self.nb, self.P
+        self.lin_dq_active = ldq[self.nb : self.n - self.nb, self.nb : self.n - self.nb].copy()  # IL.set_dq
         if "mask" in caldir:
             with open_tree(caldir["mask"]) as f:
                 put("mask_dq", f["roman"]["dq"], np.uint32)
