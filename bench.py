@@ -106,6 +106,30 @@ class ClockSampler:
 
 
 def make_inputs(n, read_pattern, n_exposures, seed=1000):
+    """Synthetic CALDIR + exposures; cached under the temp dir so that repeated invocations on one box (plain run, ncu
+    launch list, ncu full capture) do not regenerate them (~1 min of NumPy RNG at 4096^2)."""
+    import pickle
+
+    from romanimpreprocess_b200 import synth
+
+    cache = os.path.join(tempfile.gettempdir(), f"rip_bench_inputs_n{n}_G{len(read_pattern)}_e{n_exposures}_s{seed}.pkl")
+    if os.path.exists(cache):
+        try:
+            with open(cache, "rb") as f:
+                return pickle.load(f)
+        except Exception:  # noqa: BLE001
+            pass
+    res = _make_inputs(n, read_pattern, n_exposures, seed)
+    try:
+        with open(cache + ".tmp", "wb") as f:
+            pickle.dump(res, f, protocol=4)
+        os.replace(cache + ".tmp", cache)
+    except Exception:  # noqa: BLE001
+        pass
+    return res
+
+
+def _make_inputs(n, read_pattern, n_exposures, seed):
     from romanimpreprocess_b200 import synth
 
     cal = synth.make_caldir(n=n, seed=seed, read_pattern=read_pattern, p_order=P_ORDER, gain_dtype=np.float32,
@@ -269,6 +293,15 @@ def run_ours(args):
     value = world * args.steps / (ms_total_max * 1e-3)
 
     # ---- end-to-end leg: host buffers in, host buffers out, through the public API --------------------------
+    if args.no_e2e:  # profiling runs only (ncu): the printed line is not a bench value
+        if rank == 0:
+            print(json.dumps({"profiling_run": True, "value": value, "ms_per_step": ms_total_max / args.steps,
+                              "fused_ms": fused_ms.value / max(fused_n.value, 1), "gpu_launches": int(launches)}), flush=True)
+        cd.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     h_in = []
     for d, a in exposures:
         pd, pa = _lib.pinned_empty(d.shape, np.uint16), _lib.pinned_empty(a.shape, np.uint16)
@@ -300,7 +333,7 @@ def run_ours(args):
         dist.all_reduce(temax, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_steps / float(temax.item())
     h2d = int(exposures[0][0].nbytes + exposures[0][1].nbytes + area.nbytes)
-    d2h = int(sum(v.nbytes for v in h_out.values()))
+    d2h = int(sum(v.nbytes for v in h_out.values() if isinstance(v, np.ndarray)))
     checksum = int(h_out["pdq"].astype(np.uint64).sum() % (1 << 32))
 
     if rank == 0:
@@ -360,6 +393,7 @@ def main():
     ap.add_argument("--band-rows", type=int, default=0)
     ap.add_argument("--cpu-tile", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (for ncu captures)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
