@@ -7,6 +7,7 @@
 
 #include "rip_handle.h"
 #include "rip_launch.h"
+#include "rip_v2_core.cuh"
 
 namespace rip {
 
@@ -390,23 +391,10 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
     RIP_REQUIRE(prm->sat_backup >= 0 && prm->sat_backup < RIP_GMAX, "rip_l1_to_l2: bad SATURATION_BACKUP %d", prm->sat_backup);
     const double* dw = plan_to_device(h->device, plan, w_exact, st);
     if (prm->do_refpix) run_k0(h, d_raw, d_amp33, G, st);
-    CalArgs A;
-    memset(&A, 0, sizeof A);
-    A.n = n; A.nb = h->nb; A.G = G; A.P = h->P;
-    A.band_rows = prm->band_rows > 0 ? prm->band_rows : 128;
-    A.do_refpix = prm->do_refpix; A.do_not_flag_first = prm->do_not_flag_first; A.exclude_first = prm->exclude_first;
-    A.sat_backup = prm->sat_backup; A.area_dtype = prm->area_dtype;
-    A.raw = d_raw; A.area = d_area;
-    A.rowcorr = h->rowcorr.p; A.chan_m = h->chan_m.p; A.chan_c = h->chan_c.p;
-    A.dark = h->dark_cube.p;
-    A.bias = h->has_bias ? h->biascorr.p + (size_t)(h->d.n_bias - G) * h->na * h->na : nullptr;  // gen_cal_image.py:561-562
-    A.coefs = h->coefs.p; A.Smin = h->Smin.p; A.Smax = h->Smax.p; A.Sref = h->Sref.p;
-    A.aux = h->aux.p; A.sdq = h->sdq.p; A.thr = h->thr_eff.p;
-    A.gain = h->gain.p; A.ipc = h->has_ipc ? h->ipc.p : nullptr; A.read = h->read.p;
-    A.dslope = h->dslope_ipc.p; A.flat = h->flat_ipc.p; A.w_exact = dw;
-    A.slope = o->slope; A.err_read = o->err_read; A.err_poisson = o->err_poisson; A.pdq = o->pdq;
-    A.endslice = o->endslice; A.rdq = o->rdq; A.lincube = o->lin_cube;
-    int threads = prm->threads > 0 ? prm->threads : 128;
+    // v2 (rip_v2_core.cuh) for the common all-f32 configuration; params.threads > 0 selects the generic v1 tile kernel
+    const bool use_v2 = prm->threads == 0 && h->has_ipc && h->d.gain_dtype == RIP_F32 && h->d.ipc_dtype == RIP_F32 &&
+                        h->nb == 4 && n % 8 == 0 && n >= 16 && v2_supported(G, h->P) &&
+                        (prm->area_dtype == RIP_F32 || prm->area_dtype == RIP_F64);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {
         if (h->prof_used + 2 > h->prof_ev.size()) {
@@ -419,8 +407,45 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
         e0 = h->prof_ev[h->prof_used];
         e1 = h->prof_ev[h->prof_used + 1];
         h->prof_used += 2;
-        RIP_CUDA(cudaEventRecord(e0, st));
     }
+    const float* bias_p = h->has_bias ? h->biascorr.p + (size_t)(h->d.n_bias - G) * h->na * h->na : nullptr;  // gen_cal_image.py:561-562
+    if (use_v2) {
+        v2_pack(h, G, st);
+        v2::Args V;
+        memset(&V, 0, sizeof V);
+        V.n = n; V.ntile = v2::ntiles(n);
+        V.band_rows = prm->band_rows > 0 ? prm->band_rows : 128;
+        V.do_refpix = prm->do_refpix; V.do_not_flag_first = prm->do_not_flag_first; V.exclude_first = prm->exclude_first;
+        V.sat_backup = prm->sat_backup; V.area_dtype = prm->area_dtype;
+        V.raw = d_raw; V.area = d_area;
+        V.rowcorr = h->rowcorr.p; V.chan_m = h->chan_m.p; V.chan_c = h->chan_c.p;
+        V.rec1 = (const v2::f4*)h->v2_rec1.p; V.recK = (const v2::f4*)h->v2_recK.p; V.thr = h->thr_eff.p;
+        V.w_exact = dw;
+        V.slope = o->slope; V.err_read = o->err_read; V.err_poisson = o->err_poisson; V.pdq = o->pdq;
+        V.endslice = o->endslice; V.rdq = o->rdq; V.lincube = o->lin_cube;
+        if (e0) RIP_CUDA(cudaEventRecord(e0, st));
+        launch_cal_fused_v2(V, G, h->P, st);
+        if (e1) RIP_CUDA(cudaEventRecord(e1, st));
+        return;
+    }
+    CalArgs A;
+    memset(&A, 0, sizeof A);
+    A.n = n; A.nb = h->nb; A.G = G; A.P = h->P;
+    A.band_rows = prm->band_rows > 0 ? prm->band_rows : 128;
+    A.do_refpix = prm->do_refpix; A.do_not_flag_first = prm->do_not_flag_first; A.exclude_first = prm->exclude_first;
+    A.sat_backup = prm->sat_backup; A.area_dtype = prm->area_dtype;
+    A.raw = d_raw; A.area = d_area;
+    A.rowcorr = h->rowcorr.p; A.chan_m = h->chan_m.p; A.chan_c = h->chan_c.p;
+    A.dark = h->dark_cube.p;
+    A.bias = bias_p;
+    A.coefs = h->coefs.p; A.Smin = h->Smin.p; A.Smax = h->Smax.p; A.Sref = h->Sref.p;
+    A.aux = h->aux.p; A.sdq = h->sdq.p; A.thr = h->thr_eff.p;
+    A.gain = h->gain.p; A.ipc = h->has_ipc ? h->ipc.p : nullptr; A.read = h->read.p;
+    A.dslope = h->dslope_ipc.p; A.flat = h->flat_ipc.p; A.w_exact = dw;
+    A.slope = o->slope; A.err_read = o->err_read; A.err_poisson = o->err_poisson; A.pdq = o->pdq;
+    A.endslice = o->endslice; A.rdq = o->rdq; A.lincube = o->lin_cube;
+    int threads = prm->threads > 0 ? prm->threads : 128;
+    if (e0) RIP_CUDA(cudaEventRecord(e0, st));
     launch_cal_fused(A, h->d.gain_dtype, h->has_ipc ? h->d.ipc_dtype : RIP_F32, threads, st);
     if (e1) RIP_CUDA(cudaEventRecord(e1, st));
 }

@@ -47,6 +47,7 @@ const double* plan_to_device(int device, const rip_ramp_plan* plan, const double
         }
         if (nw) RIP_CUDA(cudaMemcpyAsync(s.d_w, s.w.data(), nw * sizeof(double), cudaMemcpyHostToDevice, st));
         RIP_CUDA(cudaMemcpyToSymbolAsync(c_plan, &s.host, sizeof(rip_ramp_plan), 0, cudaMemcpyHostToDevice, st));
+        v2_plan_to_device(&s.host, st);
         RIP_CUDA(cudaStreamSynchronize(st));
         s.valid = true;
     }

@@ -23,6 +23,9 @@ struct rip_caldir {
     DevBuf<float> thr_eff, dslope_ipc, flat_ipc;
     DevBuf<uint8_t> aux;
     DevBuf<uint32_t> sdq;
+    // cal_fused v2: packed per-(row, tile) records (rip_v2_core.cuh), built lazily per group count
+    DevBuf<float> v2_rec1, v2_recK;
+    int v2_G = 0;
     // K0 workspace
     DevBuf<uint32_t> hist;
     DevBuf<SelState> sel;

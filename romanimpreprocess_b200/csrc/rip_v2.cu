@@ -1,0 +1,107 @@
+// cal_fused v2 (see rip_v2_core.cuh): record packing, kernel, launcher.
+#include "rip_handle.h"
+#include "rip_launch.h"
+#include "rip_v2_core.cuh"
+
+namespace rip {
+
+__constant__ RampPlanDev c_plan_v2;
+
+namespace v2 {
+
+__global__ void pack_rec1_kernel(const PackSrc S, int ntile, int nq, f4* __restrict__ out) {
+    const int c = threadIdx.x, tile = blockIdx.x, row = blockIdx.y;
+    const int x = tile * TS + c;
+    f4* o = out + ((long)row * ntile + tile) * ((long)nq * TW) + c;
+    for (int q = 0; q < nq; ++q) {
+        f4 v;
+        v.x = rec1_word(S, row, x, 4 * q);
+        v.y = rec1_word(S, row, x, 4 * q + 1);
+        v.z = rec1_word(S, row, x, 4 * q + 2);
+        v.w = rec1_word(S, row, x, 4 * q + 3);
+        o[q * TW] = v;
+    }
+}
+
+__global__ void pack_recK_kernel(const PackSrc S, int ntile, f4* __restrict__ out) {
+    const int c = threadIdx.x, tile = blockIdx.x, row = blockIdx.y;
+    const int x = tile * TS + c;
+    f4* o = out + ((long)row * ntile + tile) * ((long)KQ * TW) + c;
+    for (int q = 0; q < KQ; ++q) {
+        f4 v;
+        v.x = recK_word(S, row, x, 4 * q);
+        v.y = recK_word(S, row, x, 4 * q + 1);
+        v.z = recK_word(S, row, x, 4 * q + 2);
+        v.w = recK_word(S, row, x, 4 * q + 3);
+        o[q * TW] = v;
+    }
+}
+
+template <int G, int P>
+__global__ void __launch_bounds__(TW, 3) cal_fused_v2_kernel(const Args A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<G> sm;
+    sm.carve(smem_raw);
+    Regs<G, P> R;
+    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int r0 = blockIdx.y * A.band_rows;
+    const int r1 = min(r0 + A.band_rows, A.n);
+    prologue<G, P>(A, sm, R, tid, tile, r0, r1);
+    __syncthreads();
+    for (int s = r0 - 3; s <= r1 + 5; ++s) {
+        step<G, P>(A, c_plan_v2, sm, R, tid, tile, r0, r1, s);
+        __syncthreads();
+    }
+}
+
+template <int G, int P>
+static void launch_t(const Args& A, cudaStream_t st) {
+    const size_t smem = Smem<G>::bytes();
+    auto kern = cal_fused_v2_kernel<G, P>;
+    static thread_local bool configured = false;
+    if (!configured) {
+        RIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
+    RIP_LAUNCH(kern, grid, TW, smem, st, A);
+}
+
+}  // namespace v2
+
+bool v2_supported(int G, int P) {
+    return (G == 8 && P == 4) || (G == 8 && P == 11) || (G == 16 && P == 11) || (G == 16 && P == 4);
+}
+
+void launch_cal_fused_v2(const v2::Args& A, int G, int P, cudaStream_t st) {
+    if (G == 16 && P == 4) v2::launch_t<16, 4>(A, st);
+    else if (G == 8 && P == 4) v2::launch_t<8, 4>(A, st);
+    else if (G == 8 && P == 11) v2::launch_t<8, 11>(A, st);
+    else if (G == 16 && P == 11) v2::launch_t<16, 11>(A, st);
+    else throw Error("cal_fused v2: unsupported (G, P)");
+}
+
+void v2_plan_to_device(const rip_ramp_plan* plan, cudaStream_t st) {
+    RIP_CUDA(cudaMemcpyToSymbolAsync(c_plan_v2, plan, sizeof(rip_ramp_plan), 0, cudaMemcpyHostToDevice, st));
+}
+
+// (re)build the packed records of a handle for G groups
+void v2_pack(rip_caldir* h, int G, cudaStream_t st) {
+    if (h->v2_G == G) return;
+    const int n = h->n, ntile = v2::ntiles(n), nq = v2::nq1(G, h->P);
+    h->v2_rec1.alloc((size_t)n * ntile * nq * v2::TW * 4);
+    h->v2_recK.alloc((size_t)n * ntile * v2::KQ * v2::TW * 4);
+    v2::PackSrc S;
+    S.n = n; S.nb = h->nb; S.G = G; S.P = h->P;
+    S.dark = h->dark_cube.p;
+    S.bias = h->has_bias ? h->biascorr.p + (size_t)(h->d.n_bias - G) * h->na * h->na : nullptr;
+    S.coefs = h->coefs.p; S.Smin = h->Smin.p; S.Smax = h->Smax.p; S.Sref = h->Sref.p;
+    S.gain = (const float*)h->gain.p; S.aux = h->aux.p; S.ipc = (const float*)h->ipc.p;
+    S.read = h->read.p; S.dslope = h->dslope_ipc.p; S.flat = h->flat_ipc.p; S.sdq = h->sdq.p;
+    dim3 grid(ntile, n);
+    RIP_LAUNCH(v2::pack_rec1_kernel, grid, v2::TW, 0, st, S, ntile, nq, (v2::f4*)h->v2_rec1.p);
+    RIP_LAUNCH(v2::pack_recK_kernel, grid, v2::TW, 0, st, S, ntile, (v2::f4*)h->v2_recK.p);
+    h->v2_G = G;
+}
+
+}  // namespace rip

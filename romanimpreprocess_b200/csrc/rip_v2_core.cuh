@@ -1,0 +1,740 @@
+// cal_fused v2: the throughput form of the fused L1->L2 tile kernel for the common configuration
+// (all-f32 calibration planes, ipc4d present, nb = 4, even G in 4..16, frame side a multiple of 8).
+// Everything else runs the generic v1 kernel (rip_cal_core.cuh).  Same arithmetic, same roundings, same flags as
+// v1 -- only the organisation differs (profiles/r01: v1 was instruction-issue bound, 40 % of its instructions were
+// address arithmetic and 10 % branches):
+//
+//   * exact (G, P) template parameters: no per-group / per-order predicates;
+//   * calibration data repacked once per CALDIR into per-(row, column-tile) records of float4 words
+//     (rec1: dark[G] bias[G] Smin Smax Sref gain aux coefs[P];  recK: 9 gathered IPC taps, gain, read, dark slope,
+//     flat, static dq) -> every input arrives as a fully coalesced 128-bit load with immediate offsets;
+//   * the loads of stage X for the next march step are issued right after stage X of this step has consumed its
+//     registers (one full step of latency budget, no double buffering);
+//   * shared-memory rings hold float4 (4 groups of one pixel) -> conflict-free LDS.128 / STS.128;
+//   * group pairs are processed with the packed FP32 instructions of sm_100 (FMUL2 / FADD2 / FFMA2: two IEEE
+//     single-precision results per issue slot; each lane is rounded exactly like the scalar op, so results are
+//     bit-identical to v1);
+//   * the 8 divisions by the same denominator (z = .../(Smax-Smin), d = o2/gain) share one refined reciprocal and
+//     use the FMA-residual correction that yields the correctly rounded quotient (== IEEE division);
+//   * gathered IPC taps are zero where the source pixel is outside the active area and D is stored as 0 for
+//     non-active pixels, so the 3x3 stencils are branch-free;
+//   * jump significance is tested as delta^2 > thr^2 var (no sqrt / division); anything within the relative band of
+//     the threshold is re-evaluated exactly in the reference's op order (same fallback as v1).
+//
+// Written __host__ __device__ like v1 so that tests/hostcheck can walk the identical source on the CPU.
+#pragma once
+#include "rip_math.cuh"
+
+namespace rip {
+namespace v2 {
+
+constexpr int TW = 128;   // columns per tile (= compute threads per CTA)
+constexpr int TS = 120;   // tile stride: outputs are tile columns 4..123 (tile 0 also 0..3)
+constexpr int RW = TW + 4;  // ring width: 2 pad columns on each side
+constexpr int KQ = 4;     // float4 words per pixel in recK
+constexpr int D_DEPTH = 8, O_DEPTH = 4, S_DEPTH = 4, F_DEPTH = 5;  // D also parks the converted raw rows (s..s-6 live)
+
+RIP_HD constexpr int nq1(int G, int P) { return (2 * G + 5 + P + 3) / 4; }
+inline int ntiles(int n) { return (n - 4 + TS - 1) / TS; }
+
+struct alignas(8) f2 {
+    float x, y;
+};
+struct alignas(16) f4 {
+    float x, y, z, w;
+};
+
+// ---- packed arithmetic: two independent IEEE-rounded single-precision operations -------------------------
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return f2{r.x, r.y}; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return f2{r.x, r.y}; }
+// a - b == fma(b, -1, a) exactly (the product is exact)
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { float2 r = __ffma2_rn(make_float2(b.x, b.y), make_float2(-1.0f, -1.0f), make_float2(a.x, a.y)); return f2{r.x, r.y}; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y)); return f2{r.x, r.y}; }
+__device__ __forceinline__ float fma1(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float rcp_approx(float d) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d)); return r; }
+#else
+inline f2 mul2(f2 a, f2 b) { return f2{a.x * b.x, a.y * b.y}; }
+inline f2 add2(f2 a, f2 b) { return f2{a.x + b.x, a.y + b.y}; }
+inline f2 sub2(f2 a, f2 b) { return f2{a.x - b.x, a.y - b.y}; }
+inline f2 fma2(f2 a, f2 b, f2 c) { return f2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+inline float fma1(float a, float b, float c) { return fmaf(a, b, c); }
+inline float rcp_approx(float d) { return 1.0f / d; }
+#endif
+RIP_HD f2 bc(float a) { return f2{a, a}; }
+
+// Correctly rounded x/d for several numerators sharing one denominator (Newton-refined reciprocal + two
+// FMA-residual corrections: the classic IEEE division sequence).  `ok` = denominator in the range where no
+// intermediate can over/underflow for |x| < 2^40; otherwise the caller uses true division.
+struct SharedDiv {
+    float d, r;
+    bool ok;
+    RIP_HD void init(float den) {
+        d = den;
+        const float ad = den < 0 ? -den : den;
+        ok = (ad > 1.0e-18f) && (ad < 1.0e18f);
+        float r0 = rcp_approx(den);
+        float e = fma1(-den, r0, 1.0f);
+        r = fma1(r0, e, r0);
+    }
+    RIP_HD f2 div2(f2 x) const {
+        const f2 nd = bc(-d), rr = bc(r);
+        f2 q = mul2(x, rr);
+        f2 rem = fma2(nd, q, x);
+        q = fma2(rem, rr, q);
+        rem = fma2(nd, q, x);
+        q = fma2(rem, rr, q);
+        return q;
+    }
+};
+
+// u16 -> f32 exactly, on the full-rate pipes: (0x4B000000 | v) is 2^23 + v
+RIP_HD float u16_to_f32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(0x4B000000u | v) - 8388608.0f;
+#else
+    return (float)v;
+#endif
+}
+
+struct Args {
+    int n, ntile, band_rows;
+    int do_refpix, do_not_flag_first, exclude_first, sat_backup, area_dtype;
+    const uint16_t* raw;     // [G,n,n]
+    const void* area;        // [n,n] f32|f64 or null
+    const double* rowcorr;   // [G,n]
+    const double* chan_m;    // [G,32]
+    const double* chan_c;
+    const f4* rec1;          // [n][ntile][NQ1][TW]
+    const f4* recK;          // [n][ntile][KQ][TW]
+    const float* thr;        // [n,n]
+    const double* w_exact;
+    float* slope;
+    float* err_read;
+    float* err_poisson;
+    uint32_t* pdq;
+    int8_t* endslice;
+    uint8_t* rdq;
+    float* lincube;
+};
+
+template <int G>
+struct Smem {
+    f4* D;            // [D_DEPTH][G/4][RW]
+    f4* O1;           // [O_DEPTH][G/4][RW]
+    uint32_t* sat;    // [S_DEPTH][RW]
+    uint32_t* flg;    // [F_DEPTH][TW][2]   (satm | adf<<16, nlc)   thread-private delay line a1 -> c
+    double* rc;       // [2][G]             row correction of the row a1 handles next / now
+    double* ln;       // [2][2][G]          channel line for the two channels the tile touches
+    static constexpr int H = G / 4;
+    RIP_HD static size_t bytes() {
+        return sizeof(f4) * (size_t)(D_DEPTH + O_DEPTH) * H * RW + 4 * (size_t)S_DEPTH * RW + 8 * (size_t)F_DEPTH * TW +
+               8 * (size_t)(2 * G + 4 * G) + 64;
+    }
+    RIP_HD void carve(unsigned char* base) {
+        size_t off = 0;
+        D = (f4*)(base + off); off += sizeof(f4) * (size_t)D_DEPTH * H * RW;
+        O1 = (f4*)(base + off); off += sizeof(f4) * (size_t)O_DEPTH * H * RW;
+        rc = (double*)(base + off); off += 8 * (size_t)2 * G;
+        ln = (double*)(base + off); off += 8 * (size_t)4 * G;
+        sat = (uint32_t*)(base + off); off += 4 * (size_t)S_DEPTH * RW;
+        flg = (uint32_t*)(base + off);
+    }
+};
+
+// registers a thread carries from one march step to the next: inputs prefetched for each stage
+template <int G, int P>
+struct Regs {
+    static constexpr int NQ1 = nq1(G, P);
+    uint32_t raw[G];   // stage a0, row s
+    float thr;
+    f4 r1[NQ1];        // stage a1, row s-2
+    f4 kb[3];          // stage b,  row s-4 (taps 0..8)
+    f4 kc[KQ];         // stage c,  row s-6
+    float area32;
+    double area64;
+};
+
+RIP_HD int mod_pos(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
+
+// ---- loads -------------------------------------------------------------------------------------------------
+template <int G, int P>
+RIP_HD void load_a0(const Args& A, Regs<G, P>& R, int row, int x, bool xin, int lo, int hi) {
+    if (row >= 0 && row < A.n && row >= lo && row < hi && xin) {
+        const long npl = (long)A.n * A.n;
+        const uint16_t* p = A.raw + (long)row * A.n + x;
+#pragma unroll
+        for (int g = 0; g < G; ++g) R.raw[g] = p[(long)g * npl];
+        R.thr = A.thr[(long)row * A.n + x];
+    }
+}
+template <int G, int P>
+RIP_HD void load_a1(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int lo, int hi) {
+    if (row >= 0 && row < A.n && row >= lo && row < hi) {
+        const f4* p = A.rec1 + ((long)row * A.ntile + tile) * (Regs<G, P>::NQ1 * TW) + tid;
+#pragma unroll
+        for (int q = 0; q < Regs<G, P>::NQ1; ++q) R.r1[q] = p[q * TW];
+    }
+}
+template <int G, int P>
+RIP_HD void load_b(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int lo, int hi) {
+    if (row >= 0 && row < A.n && row >= lo && row < hi) {
+        const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW) + tid;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) R.kb[q] = p[q * TW];
+    }
+}
+template <int G, int P>
+RIP_HD void load_c(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int x, bool xin, int lo, int hi) {
+    if (row >= 0 && row < A.n && row >= lo && row < hi) {
+        const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW) + tid;
+#pragma unroll
+        for (int q = 0; q < KQ; ++q) R.kc[q] = p[q * TW];
+        if (A.area && xin) {
+            if (A.area_dtype == RIP_F64) R.area64 = ((const double*)A.area)[(long)row * A.n + x];
+            else R.area32 = ((const float*)A.area)[(long)row * A.n + x];
+        }
+    }
+}
+
+RIP_HD float f4_get(const f4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+RIP_HD uint32_t f_as_u(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+
+// word w of the rec1 record held in registers (w is a compile-time constant after unrolling)
+template <int NQ>
+RIP_HD float r1w(const f4 (&r)[NQ], int w) { return f4_get(r[w >> 2], w & 3); }
+
+// 9-tap stencil over a float4 ring for one half (4 groups) -> two packed pairs.  Tap order = the reference's
+// accumulation order (utils/ipc_linearity.py:69-94): c, (1,0), (-1,0), (0,1), (0,-1), (1,1), (1,-1), (-1,1), (-1,-1);
+// tap (dy,dx) reads the image at (row-dy, col-dx).
+RIP_HD void stencil9(const f4* ring_m, const f4* ring_0, const f4* ring_p, int col, const float (&k)[9], f2& lo, f2& hi) {
+    // ring_m = row-1 (dy=+1), ring_0 = row, ring_p = row+1 (dy=-1); col already includes the pad offset
+    const f4 c = ring_0[col];
+    lo = mul2(f2{c.x, c.y}, bc(k[0]));
+    hi = mul2(f2{c.z, c.w}, bc(k[0]));
+#define RIP_TAP(V, Q)                                     \
+    {                                                     \
+        const f4 t = (V);                                 \
+        lo = add2(lo, mul2(f2{t.x, t.y}, bc(k[Q])));      \
+        hi = add2(hi, mul2(f2{t.z, t.w}, bc(k[Q])));      \
+    }
+    RIP_TAP(ring_m[col], 1)
+    RIP_TAP(ring_p[col], 2)
+    RIP_TAP(ring_0[col - 1], 3)
+    RIP_TAP(ring_0[col + 1], 4)
+    RIP_TAP(ring_m[col - 1], 5)
+    RIP_TAP(ring_m[col + 1], 6)
+    RIP_TAP(ring_p[col - 1], 7)
+    RIP_TAP(ring_p[col + 1], 8)
+#undef RIP_TAP
+}
+
+// jump_detect for one pixel, fast form (plan variant v, compile-time G).  Same decisions as
+// rip::jump_detect_pixel<.., FAST=true>; the sure-flag / sure-clear tests are done on squares.
+template <int G>
+RIP_HD FitResult jump_fast(const float (&d)[G], int v, float gain, float read, bool active, const RampPlanDev& pl,
+                           const double* w_all) {
+    FitResult r;
+    const int ngrp = pl.var_ngrp[v];
+    const int start = pl.start;
+    float acc = 0.0f;
+#pragma unroll
+    for (int t = 0; t < G; ++t)
+        if (t < ngrp) acc = acc + pl.var_K[v][t] * (d[t] - d[1]);
+    r.slope = acc;
+    const float gc = np_clip<float>(gain, 1e-4f, 1e4f);
+    const float dvardt = np_max<float>(r.slope / gc, 0.0f);
+    r.err_poisson = sqrtf(np_max<float>(pl.var_coef[v] * dvardt, 0.0f));
+    r.err_read = read * pl.var_rfac[v];
+    r.jump_mask = 0u;
+    if (!active) return r;
+    const float sig2read = read * read;
+    int s = pl.var_slice_off[v];
+    const float x = np_clip<float>(r.slope, pl.IthreshA_f, pl.IthreshB_f);
+    const float thr = (float)pl.SthreshA + (float)(pl.SthreshB - pl.SthreshA) * (logf(x / pl.IthreshA_f) / (float)pl.logIratio);
+    // sure-flag: delta > 0 and delta^2 > thr_hi^2 var; sure-clear: delta <= 0 (thr > 0) or delta^2 < thr_lo^2 var
+    const bool thr_pos = thr > 0.0f;
+    float hi = thr * (1.0f + pl.band), lo = thr * (1.0f - pl.band);
+    const float hi2 = hi * hi * (1.0f + 4.0e-7f), lo2 = lo * lo * (1.0f - 4.0e-7f);
+    double thr_exact = 0.0;
+    bool have_thr = false;
+#pragma unroll
+    for (int i = 0; i < G - 1; ++i) {
+        if (i >= start && i < ngrp - 1) {
+            const int dimax = (i == ngrp - 2 || ngrp - 1 - start == 2) ? 1 : 2;
+#pragma unroll
+            for (int di = 1; di <= 2; ++di) {
+                if (di <= dimax) {
+                    const RampSlice& sl = pl.slices[s];
+                    const float diff = d[(i + di < G) ? (i + di) : (G - 1)] - d[i];
+                    const float var = dvardt * sl.A + sig2read * sl.B;
+                    const float delta = diff * sl.inv_dt - r.slope;
+                    const float l2 = delta * delta;
+                    const bool vpos = thr_pos && (var > 0.0f);
+                    const bool sure_set = vpos && (delta > 0.0f) && (l2 > hi2 * var);
+                    const bool sure_clr = vpos && ((delta <= 0.0f) || (l2 < lo2 * var));
+                    if (sure_set) {
+                        r.jump_mask |= 1u << i;
+                    } else if (!sure_clr) {  // borderline, NaN, degenerate variance or exotic thresholds -> exact
+                        if (!have_thr) { thr_exact = jump_threshold(r.slope, pl); have_thr = true; }
+                        const float sme = smap_exact<float>(diff / sl.dt - r.slope, ngrp, dvardt, sig2read, pl, w_all + (long)s * RIP_GMAX);
+                        if ((double)sme > thr_exact) r.jump_mask |= 1u << i;
+                    }
+                    ++s;
+                }
+            }
+        }
+    }
+    return r;
+}
+
+template <int G>
+RIP_HD FitResult ramp_fit_fast(const float (&d)[G], GroupFlags& gf, uint32_t& pdq, float gain, float read, bool active,
+                               const RampPlanDev& pl, const double* w_all) {
+    FitResult r = jump_fast<G>(d, 0, gain, read, active, pl, w_all);
+    const bool unsat = ((gf.sat >> (G - 1)) & 1u) == 0u;
+    if (unsat) gf.jump |= r.jump_mask;
+    if (gf.sat) {  // truncated refits only where some group is saturated
+        for (int iend = G - 1; iend > 2 + pl.start; --iend) {
+            const bool layer = ((gf.sat >> iend) & 1u) && !((gf.sat >> (iend - 1)) & 1u);
+            if (layer) {
+                FitResult t = jump_fast<G>(d, G - iend, gain, read, active, pl, w_all);
+                r.slope = t.slope;
+                r.err_read = t.err_read;
+                r.err_poisson = t.err_poisson;
+                gf.jump |= t.jump_mask;
+            }
+        }
+    }
+    const uint32_t allg = (1u << G) - 1u;
+    const uint32_t unsat_g = ~gf.sat & allg;
+    uint32_t pdq2 = 0u;
+    if (gf.jump & unsat_g) pdq2 |= DQ_JUMP_DET;
+    if (gf.adf & unsat_g) pdq2 |= DQ_AD_FLOOR;
+    if ((gf.dnu & allg) == allg) pdq2 |= DQ_DO_NOT_USE;
+    if ((gf.sat >> (1 + pl.start)) & 1u) pdq2 |= DQ_DO_NOT_USE;
+    if (gf.sat & allg) pdq2 |= DQ_SATURATED;
+    if ((pdq & DQ_REFERENCE_PIXEL) == 0u) pdq |= pdq2;
+    return r;
+}
+
+// ---- one march step --------------------------------------------------------------------------------------------
+// Stage rows as in v1: a0 row s, a1 row s-2, b row s-4, c row s-6.  After each stage the registers it consumed
+// are refilled with the inputs of the same stage for the next step.
+template <int G, int P>
+RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& R, const int tid, const int tile,
+                 const int r0, const int r1, const int s) {
+    constexpr int H = G / 4;
+    constexpr int NQ1 = Regs<G, P>::NQ1;
+    const int n = A.n, nb = 4, na = n - 8;
+    const long npl = (long)n * n;
+    const int x = tile * TS + tid;
+    const bool xin = x < n;
+    const int col = tid + 2;
+    const uint32_t allg = (1u << G) - 1u;
+    const bool xact = (x >= nb && x < n - nb);
+
+    // ================= stage c : row s-6 =================
+    {
+        const int row = s - 6;
+        const bool out_col = (tid >= 4 || tile == 0) && tid < TW - 4 && xin;
+        if (row >= r0 && row < r1 && out_col) {
+            const long p = (long)row * n + x;
+            const bool active = xact && (row >= nb && row < n - nb);
+            const uint32_t fl = sm.flg[(mod_pos(row, F_DEPTH) * TW + tid) * 2];
+            const uint32_t nlc = sm.flg[(mod_pos(row, F_DEPTH) * TW + tid) * 2 + 1];
+            const float gval = R.kc[2].y, readv = R.kc[2].z, dsl = R.kc[2].w, flat = R.kc[3].x;
+            const uint32_t sdq = f_as_u(R.kc[3].y);
+            float d[G];
+            if (active) {
+                const float k[9] = {R.kc[0].x, R.kc[0].y, R.kc[0].z, R.kc[0].w, R.kc[1].x, R.kc[1].y, R.kc[1].z, R.kc[1].w, R.kc[2].x};
+                SharedDiv sd;
+                sd.init(gval);
+                const f4* om = sm.O1 + (size_t)((row - 1) & (O_DEPTH - 1)) * H * RW;
+                const f4* o0 = sm.O1 + (size_t)(row & (O_DEPTH - 1)) * H * RW;
+                const f4* op = sm.O1 + (size_t)((row + 1) & (O_DEPTH - 1)) * H * RW;
+                const f4* dd = sm.D + (size_t)(row & (D_DEPTH - 1)) * H * RW;
+                f2 t[G / 2], q[G / 2];
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    f2 lo, hi;
+                    stencil9(om + h * RW, o0 + h * RW, op + h * RW, col, k, lo, hi);
+                    const f4 oc = o0[h * RW + col], dc = dd[h * RW + col];
+                    t[2 * h] = sub2(add2(f2{oc.x, oc.y}, f2{dc.x, dc.y}), lo);  // (output + image2) - ipc_fwd(output)
+                    t[2 * h + 1] = sub2(add2(f2{oc.z, oc.w}, f2{dc.z, dc.w}), hi);
+                }
+                bool slow = !sd.ok;
+                if (!slow) {
+                    f2 chk = f2{0.f, 0.f};
+#pragma unroll
+                    for (int j = 0; j < G / 2; ++j) { q[j] = sd.div2(t[j]); chk = add2(chk, q[j]); }
+                    const float tt = chk.x + chk.y;
+                    slow = !(tt == tt);  // a NaN from the correction steps (infinite numerator) -> true division
+                }
+                if (slow) {
+#pragma unroll
+                    for (int j = 0; j < G / 2; ++j) q[j] = f2{t[j].x / gval, t[j].y / gval};
+                }
+#pragma unroll
+                for (int j = 0; j < G / 2; ++j) { d[2 * j] = q[j].x; d[2 * j + 1] = q[j].y; }
+                if (A.lincube) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) A.lincube[(long)g * npl + p] = d[g];
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < G; ++g) d[g] = 0.0f;  // unused: every output of a non-active pixel is flag-only
+            }
+            GroupFlags gf;
+            gf.sat = fl & 0xffffu;
+            gf.adf = fl >> 16;
+            gf.dnu = gf.adf | (A.exclude_first ? 1u : 0u);
+            gf.jump = 0u;
+            gf.other_unsat = 0u;
+            uint32_t pd = (nlc & 4u) ? DQ_REFERENCE_PIXEL : 0u;
+            FitResult r;
+            if (active) {
+                r = ramp_fit_fast<G>(d, gf, pd, gval, readv, true, pl, A.w_exact);
+            } else {
+                // reference pixels / phantom border: the fit result is zeroed by the packaging step
+                // (gen_cal_image.py:470-472); only the flag propagation of ramp_fit matters (fitting.py:340-353)
+                r.slope = 0.0f; r.err_read = 0.0f; r.err_poisson = 0.0f; r.jump_mask = 0u;
+                const uint32_t unsat_g = ~gf.sat & allg;
+                uint32_t pdq2 = 0u;
+                if (gf.adf & unsat_g) pdq2 |= DQ_AD_FLOOR;
+                if ((gf.dnu & allg) == allg) pdq2 |= DQ_DO_NOT_USE;
+                if ((gf.sat >> (1 + pl.start)) & 1u) pdq2 |= DQ_DO_NOT_USE;
+                if (gf.sat & allg) pdq2 |= DQ_SATURATED;
+                if ((pd & DQ_REFERENCE_PIXEL) == 0u) pd |= pdq2;
+            }
+            const uint32_t pdq = sdq | ((nlc & 1u) ? DQ_NO_LIN_CORR : 0u) | (pd & ~DQ_REFERENCE_PIXEL);
+            float fa = flat;
+            if (A.area) {
+                if (A.area_dtype == RIP_F64) fa = (float)((double)fa / R.area64);
+                else fa = fa / R.area32;
+            }
+            l2_epilogue(r, active, dsl, fa);
+            A.slope[p] = r.slope;
+            A.err_read[p] = r.err_read;
+            A.err_poisson[p] = r.err_poisson;
+            A.pdq[p] = pdq;
+            if (A.endslice && active) {
+                int es = -1;
+#pragma unroll
+                for (int iend = 1; iend < G; ++iend)
+                    if (((gf.sat >> iend) & 1u) && !((gf.sat >> (iend - 1)) & 1u)) es = iend - 1;
+                A.endslice[(long)(row - nb) * na + (x - nb)] = (int8_t)es;
+            }
+            if (A.rdq) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    uint32_t b = 0u;
+                    if ((gf.dnu >> g) & 1u) b |= DQ_DO_NOT_USE;
+                    if ((gf.sat >> g) & 1u) b |= DQ_SATURATED;
+                    if ((gf.jump >> g) & 1u) b |= DQ_JUMP_DET;
+                    if ((gf.adf >> g) & 1u) b |= DQ_AD_FLOOR;
+                    A.rdq[(long)g * npl + p] = (uint8_t)b;
+                }
+            }
+        }
+        load_c<G, P>(A, R, row + 1, tile, tid, x, xin, r0, r1);
+    }
+
+    // ================= stage b : row s-4 (IPC pass 1) =================
+    {
+        const int row = s - 4;
+        const bool rowok = row >= nb && row < n - nb && row >= r0 - 1 && row < r1 + 1;
+        f4* o = sm.O1 + (size_t)(row & (O_DEPTH - 1)) * H * RW;
+        if (rowok && tid >= 2 && tid <= TW - 3 && xact) {
+            const float k[9] = {R.kb[0].x, R.kb[0].y, R.kb[0].z, R.kb[0].w, R.kb[1].x, R.kb[1].y, R.kb[1].z, R.kb[1].w, R.kb[2].x};
+            const f4* dm = sm.D + (size_t)((row - 1) & (D_DEPTH - 1)) * H * RW;
+            const f4* d0 = sm.D + (size_t)(row & (D_DEPTH - 1)) * H * RW;
+            const f4* dp = sm.D + (size_t)((row + 1) & (D_DEPTH - 1)) * H * RW;
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                f2 lo, hi;
+                stencil9(dm + h * RW, d0 + h * RW, dp + h * RW, col, k, lo, hi);
+                const f4 dc = d0[h * RW + col];
+                const f2 clo{dc.x, dc.y}, chi{dc.z, dc.w};
+                const f2 rlo = sub2(add2(clo, clo), lo), rhi = sub2(add2(chi, chi), hi);  // output + image2 - ipc_fwd(output)
+                o[h * RW + col] = f4{rlo.x, rlo.y, rhi.x, rhi.y};
+            }
+        } else if (row >= r0 - 1 && row < r1 + 1) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) o[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
+        }
+        load_b<G, P>(A, R, row + 1, tile, tid, r0 - 1, r1 + 1);
+    }
+
+    // ================= stage a1 : row s-2 (flags, refpix, bias, multilin, D) =================
+    {
+        const int row = s - 2;
+        const bool rowin = row >= 0 && row < n && row >= r0 - 2 && row < r1 + 2;
+        f4* dst = sm.D + (size_t)(row & (D_DEPTH - 1)) * H * RW;
+        uint32_t* fdst = sm.flg + (mod_pos(row, F_DEPTH) * TW + tid) * 2;
+        if (rowin && (tid >= 1 || tile == 0) && tid <= TW - 2 && xin) {
+            uint32_t grown = 0u;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const uint32_t* sr = sm.sat + (size_t)((row + dy) & (S_DEPTH - 1)) * RW + col;
+                grown |= sr[-1] | sr[0] | sr[1];
+            }
+            const uint32_t own = sm.sat[(size_t)(row & (S_DEPTH - 1)) * RW + col];
+            grown &= 0xffffu;
+            uint32_t satm = grown;
+            for (int b = 1; b <= A.sat_backup; ++b) satm |= grown >> b;
+            satm &= allg & ~1u;
+            const uint32_t adf = own >> 16;
+            const bool active = xact && (row >= nb && row < n - nb);
+            // raw values of this row were converted by stage a0 two steps ago and parked in the D ring slot of
+            // this row (overwritten below)
+            float S[G];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const f4 v = dst[h * RW + col];
+                S[4 * h] = v.x; S[4 * h + 1] = v.y; S[4 * h + 2] = v.z; S[4 * h + 3] = v.w;
+            }
+            if (A.do_refpix) {  // gen_cal_image.py:535-556: f64 subtractions, f32 stores
+                const int chsel = ((x >> 7) != ((tile * TS) >> 7)) ? 1 : 0;
+                const double* rc = sm.rc + (size_t)(row & 1) * G;
+                const double* ln = sm.ln + (size_t)((row & 1) * 2 + chsel) * G;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float dk = r1w<NQ1>(R.r1, g);
+                    float v = S[g] - dk;
+                    v = (float)((double)v - rc[g]);
+                    v = (float)((double)v - ln[g]);
+                    S[g] = v + dk;
+                }
+            }
+            // biascorr (embedded with zeros outside the active region: v - 0 == v)
+            f2 S2[G / 2];
+#pragma unroll
+            for (int j = 0; j < G / 2; ++j)
+                S2[j] = sub2(f2{S[2 * j], S[2 * j + 1]}, f2{r1w<NQ1>(R.r1, G + 2 * j), r1w<NQ1>(R.r1, G + 2 * j + 1)});
+            const float Smin = r1w<NQ1>(R.r1, 2 * G), Smax = r1w<NQ1>(R.r1, 2 * G + 1), Sref = r1w<NQ1>(R.r1, 2 * G + 2);
+            const float gain = r1w<NQ1>(R.r1, 2 * G + 3);
+            const uint32_t aux = f_as_u(r1w<NQ1>(R.r1, 2 * G + 4));
+            float c[P];
+#pragma unroll
+            for (int L = 0; L < P; ++L) c[L] = r1w<NQ1>(R.r1, 2 * G + 5 + L);
+            // z = -1 + (2 (S - Smin)) / (Smax - Smin)      (ipc_linearity.py:330)
+            SharedDiv sd;
+            const float den = Smax - Smin;
+            sd.init(den);
+            const bool div_ok = sd.ok && (Smin > -1.0e18f) && (Smin < 1.0e18f);
+            f2 z2[G / 2];
+#pragma unroll
+            for (int j = 0; j < G / 2; ++j) {
+                const f2 num = mul2(bc(2.0f), sub2(S2[j], bc(Smin)));
+                f2 q;
+                if (div_ok) q = sd.div2(num);
+                else q = f2{num.x / den, num.y / den};
+                z2[j] = add2(bc(-1.0f), q);
+            }
+            if (A.do_not_flag_first) z2[0].x = np_clip<float>(z2[0].x, -1.0f, 1.0f);
+            // |z| > 1 anywhere (or NaN) -> the extrapolating scalar evaluation of v1 for this pixel (rare)
+            bool anyex = false;
+#pragma unroll
+            for (int j = 0; j < G / 2; ++j) {
+                const float ax = z2[j].x < 0 ? -z2[j].x : z2[j].x, ay = z2[j].y < 0 ? -z2[j].y : z2[j].y;
+                anyex = anyex || !(ax <= 1.0f) || !(ay <= 1.0f);
+            }
+            uint32_t dq = (aux & 1u) ? DQ_REFERENCE_PIXEL : 0u;
+            f2 phi2[G / 2];
+            if (!anyex) {
+                f2 prev[G / 2], cur[G / 2];
+#pragma unroll
+                for (int j = 0; j < G / 2; ++j) { phi2[j] = bc(c[0]); prev[j] = bc(1.0f); cur[j] = z2[j]; }
+#pragma unroll
+                for (int L = 1; L < P; ++L) {
+                    const float a = (float)((2 * L + 1) / (double)(L + 1)), b = (float)(L / (double)(L + 1));
+#pragma unroll
+                    for (int j = 0; j < G / 2; ++j) {
+                        phi2[j] = add2(phi2[j], mul2(bc(c[L]), cur[j]));
+                        const f2 nxt = sub2(mul2(mul2(bc(a), z2[j]), cur[j]), mul2(bc(b), prev[j]));
+                        prev[j] = cur[j];
+                        cur[j] = nxt;
+                    }
+                }
+            } else {
+                float cc[P];
+#pragma unroll
+                for (int L = 0; L < P; ++L) cc[L] = c[L];
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float z = (g & 1) ? z2[g >> 1].y : z2[g >> 1].x;
+                    bool ex;
+                    const float ph = legendre_eval<float, P, true>(z, cc, P, ex);
+                    if (g & 1) phi2[g >> 1].y = ph; else phi2[g >> 1].x = ph;
+                    const bool first = (g == 0) && A.do_not_flag_first;
+                    if (!first && ex && !((satm >> g) & 1u)) dq |= DQ_NO_LIN_CORR;
+                }
+            }
+            if (aux & 1u) {  // lin dq has NO_LIN_CORR | REFERENCE_PIXEL: S - Sref instead (ipc_linearity.py:334-336)
+#pragma unroll
+                for (int j = 0; j < G / 2; ++j) phi2[j] = sub2(S2[j], bc(Sref));
+            }
+            if (active) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const f2 a = mul2(phi2[2 * h], bc(gain)), b = mul2(phi2[2 * h + 1], bc(gain));
+                    dst[h * RW + col] = f4{a.x, a.y, b.x, b.y};
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
+                if (A.lincube && row >= r0 && row < r1 && (tid >= 4 || tile == 0) && tid < TW - 4) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g)
+                        A.lincube[(long)g * npl + (long)row * n + x] = (g & 1) ? phi2[g >> 1].y : phi2[g >> 1].x;
+                }
+            }
+            fdst[0] = satm | (adf << 16);
+            fdst[1] = ((dq & DQ_NO_LIN_CORR) ? 1u : 0u) | ((aux & 2u) ? 4u : 0u);
+        } else if (row >= r0 - 2 && row < r1 + 2) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
+            fdst[0] = 0u;
+            fdst[1] = 0u;
+        }
+        load_a1<G, P>(A, R, row + 1, tile, tid, r0 - 2, r1 + 2);
+    }
+
+    // ================= stage a0 : row s (raw -> saturation bits; converted raw parked in the D slot) ===========
+    {
+        const int row = s;
+        uint32_t bits = 0u;
+        const bool rowin = row >= 0 && row < n && row >= r0 - 3 && row < r1 + 3;
+        if (rowin && xin) {
+            f4* dst = sm.D + (size_t)(row & (D_DEPTH - 1)) * H * RW;
+            const float thr = R.thr;
+            bool cum = false;
+            float fv[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                fv[g] = u16_to_f32(R.raw[g]);
+                if (g >= 1) {  // saturation_check skips the first resultant (gen_cal_image.py:174-180)
+                    cum = cum || (fv[g] >= thr);
+                    if (cum) bits |= 1u << g;
+                    if (fv[g] <= 0.0f) bits |= 1u << (16 + g);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{fv[4 * h], fv[4 * h + 1], fv[4 * h + 2], fv[4 * h + 3]};
+        }
+        sm.sat[(size_t)(row & (S_DEPTH - 1)) * RW + col] = bits;
+        // row / channel corrections of the row stage a1 handles in the NEXT step (row s-1): parity (s-1)&1
+        if (A.do_refpix && tid < 3 * G) {
+            const int rown = s - 1;
+            if (rown >= 0 && rown < n) {
+                const int g = tid % G, which = tid / G;
+                if (which == 0) {
+                    sm.rc[(size_t)(rown & 1) * G + g] = A.rowcorr[(long)g * n + rown];
+                } else {
+                    int ch = ((tile * TS) >> 7) + (which - 1);
+                    if (ch > 31) ch = 31;
+                    sm.ln[(size_t)((rown & 1) * 2 + (which - 1)) * G + g] = A.chan_m[g * 32 + ch] * (double)rown + A.chan_c[g * 32 + ch];
+                }
+            }
+        }
+        load_a0<G, P>(A, R, row + 1, x, xin, r0 - 3, r1 + 3);
+    }
+}
+
+// prologue: inputs of the first step s0 (rows s0, s0-2, s0-4, s0-6 -- only the first can be inside the frame, the
+// others are loaded for uniformity: rows < 0 are skipped by the loaders)
+template <int G, int P>
+RIP_HD void prologue(const Args& A, Smem<G>& sm, Regs<G, P>& R, int tid, int tile, int r0, int r1) {
+    const int x = tile * TS + tid;
+    const bool xin = x < A.n;
+    const int s0 = r0 - 3;
+    load_c<G, P>(A, R, s0 - 6, tile, tid, x, xin, r0, r1);
+    load_b<G, P>(A, R, s0 - 4, tile, tid, r0 - 1, r1 + 1);
+    load_a1<G, P>(A, R, s0 - 2, tile, tid, r0 - 2, r1 + 2);
+    load_a0<G, P>(A, R, s0, x, xin, r0 - 3, r1 + 3);
+    // ring pads and the slots stage a1 / b read before anything was written there
+    for (int i = tid; i < S_DEPTH * RW; i += TW) sm.sat[i] = 0u;
+    for (int i = tid; i < (D_DEPTH + O_DEPTH) * Smem<G>::H * RW; i += TW) sm.D[i] = f4{0.f, 0.f, 0.f, 0.f};
+}
+
+// ---- packed calibration records (built once per CALDIR and group count) -------------------------------------
+struct PackSrc {
+    int n, nb, G, P;
+    const float* dark;     // [>=G,n,n]
+    const float* bias;     // [G,na,na] (group offset applied) or null
+    const float* coefs;    // [P,n,n]
+    const float* Smin;
+    const float* Smax;
+    const float* Sref;
+    const float* gain;     // [n,n] f32
+    const uint8_t* aux;    // [n,n]
+    const float* ipc;      // [9,na,na] f32
+    const float* read;
+    const float* dslope;   // IPC-corrected dark slope
+    const float* flat;     // get_flat product
+    const uint32_t* sdq;   // merged static dq
+};
+
+RIP_HD float u_as_f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+// word w of rec1 at detector pixel (row, x); x >= n -> 0
+RIP_HD float rec1_word(const PackSrc& S, int row, int x, int w) {
+    if (x >= S.n) return 0.0f;
+    const long npl = (long)S.n * S.n, p = (long)row * S.n + x;
+    const int G = S.G, na = S.n - 2 * S.nb;
+    if (w < G) return S.dark[(long)w * npl + p];
+    if (w < 2 * G) {
+        const int ya = row - S.nb, xa = x - S.nb;
+        if (!S.bias || ya < 0 || ya >= na || xa < 0 || xa >= na) return 0.0f;
+        return S.bias[((long)(w - G) * na + ya) * na + xa];
+    }
+    w -= 2 * G;
+    if (w == 0) return S.Smin[p];
+    if (w == 1) return S.Smax[p];
+    if (w == 2) return S.Sref[p];
+    if (w == 3) return S.gain[p];
+    if (w == 4) return u_as_f((uint32_t)S.aux[p]);
+    w -= 5;
+    if (w < S.P) return S.coefs[(long)w * npl + p];
+    return 0.0f;
+}
+
+// word w of recK: 0..8 gathered IPC taps K[1+dy][1+dx][y-dy][x-dx] in the reference's accumulation order (zero when
+// the source pixel is outside the active area or (row, x) is not active), 9 gain, 10 read, 11 dark slope (IPC
+// corrected), 12 flat, 13 static dq bits, 14..15 zero.
+RIP_HD float recK_word(const PackSrc& S, int row, int x, int w) {
+    if (x >= S.n) return 0.0f;
+    const long p = (long)row * S.n + x;
+    const int na = S.n - 2 * S.nb;
+    if (w < 9) {
+        const int DY[9] = {0, 1, -1, 0, 0, 1, 1, -1, -1};
+        const int DX[9] = {0, 0, 0, 1, -1, 1, -1, 1, -1};
+        const int ya = row - S.nb, xa = x - S.nb;
+        if (ya < 0 || ya >= na || xa < 0 || xa >= na) return 0.0f;
+        const int ys = ya - DY[w], xs = xa - DX[w];
+        if (ys < 0 || ys >= na || xs < 0 || xs >= na) return 0.0f;
+        return S.ipc[((long)((1 + DY[w]) * 3 + (1 + DX[w])) * na + ys) * na + xs];
+    }
+    if (w == 9) return S.gain[p];
+    if (w == 10) return S.read[p];
+    if (w == 11) return S.dslope[p];
+    if (w == 12) return S.flat[p];
+    if (w == 13) return u_as_f(S.sdq[p]);
+    return 0.0f;
+}
+
+}  // namespace v2
+}  // namespace rip

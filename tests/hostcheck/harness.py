@@ -31,8 +31,21 @@ class CalArgs(C.Structure):
                                           "lincube")]  # fmt: skip
 
 
+class V2Args(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("n", "ntile", "band_rows", "do_refpix", "do_not_flag_first", "exclude_first",
+                                       "sat_backup", "area_dtype")] + \
+               [(k, C.c_void_p) for k in ("raw", "area", "rowcorr", "chan_m", "chan_c", "rec1", "recK", "thr", "w_exact",
+                                          "slope", "err_read", "err_poisson", "pdq", "endslice", "rdq", "lincube")]  # fmt: skip
+
+
+class PackSrc(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("n", "nb", "G", "P")] + \
+               [(k, C.c_void_p) for k in ("dark", "bias", "coefs", "Smin", "Smax", "Sref", "gain", "aux", "ipc", "read",
+                                          "dslope", "flat", "sdq")]  # fmt: skip
+
+
 def build():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("rip_cal_core.cuh", "rip_math.cuh")] + [
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("rip_cal_core.cuh", "rip_math.cuh", "rip_v2_core.cuh")] + [
         os.path.join(ROOT, "include", "rip_b200.h")
     ]
     if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
@@ -53,6 +66,12 @@ def lib():
         _h.hostcheck_cal_fused.restype = C.c_int
         _h.hostcheck_cal_fused.argtypes = [C.POINTER(CalArgs), C.POINTER(_lib.RampPlan), C.c_int, C.c_int, C.c_int]
         assert _h.hostcheck_sizeof_calargs() == C.sizeof(CalArgs)
+        _h.hostcheck_cal_fused_v2.restype = C.c_int
+        _h.hostcheck_cal_fused_v2.argtypes = [C.POINTER(V2Args), C.POINTER(PackSrc), C.POINTER(_lib.RampPlan)]
+        assert _h.hostcheck_sizeof_v2args() == C.sizeof(V2Args)
+        assert _h.hostcheck_sizeof_packsrc() == C.sizeof(PackSrc)
+        _h.hostcheck_shared_div.restype = C.c_long
+        _h.hostcheck_shared_div.argtypes = [C.c_long, C.c_uint, C.c_float, C.c_float, C.c_float]
     return _h
 
 
@@ -108,8 +127,9 @@ def refpix_stats(data_u16, amp33_u16, c):
 
 
 def run_fused(cal, data_u16, amp33_u16, read_pattern, frame_time, area, config=None, do_refpix=False, threads=64,
-              band_rows=16, want_rdq=True, want_lin=True):  # fmt: skip
-    """Host emulation of rip_l1_to_l2 (same argument meaning as the oracle's l1_to_l2)."""
+              band_rows=16, want_rdq=True, want_lin=True, v2=False):  # fmt: skip
+    """Host emulation of rip_l1_to_l2 (same argument meaning as the oracle's l1_to_l2); ``v2`` selects the v2 kernel
+    source (rip_v2_core.cuh: all-f32 planes, G in {8,16}, P in {4,11})."""
     config = config or {}
     c = {k: v["roman"] for k, v in cal.items()}
     nb = 4
@@ -133,6 +153,9 @@ def run_fused(cal, data_u16, amp33_u16, read_pattern, frame_time, area, config=N
         keep.append(a)
         return a.ctypes.data_as(C.c_void_p)
 
+    if v2:
+        return _run_v2(c, data_u16, amp33_u16, read_pattern, area, config, do_refpix, band_rows, want_rdq, want_lin,
+                       plan, w_exact, (thr, aux, sdq, dslope, flat), meta, p)
     A = CalArgs()
     A.n, A.nb, A.G, A.P = n, nb, G, c["linearitylegendre"]["data"].shape[0]
     A.band_rows = band_rows
@@ -182,5 +205,63 @@ def run_fused(cal, data_u16, amp33_u16, read_pattern, frame_time, area, config=N
     rc = lib().hostcheck_cal_fused(C.byref(A), C.byref(plan), _lib.float_tag(gain),
                                    _lib.RIP_F32 if ipc is None else _lib.float_tag(ipc), threads)  # fmt: skip
     assert rc == 0
+    out["K"] = meta["K"]
+    return out
+
+
+def _run_v2(c, data_u16, amp33_u16, read_pattern, area, config, do_refpix, band_rows, want_rdq, want_lin, plan, w_exact,
+            static, meta, p):  # fmt: skip
+    thr, aux, sdq, dslope, flat = static
+    G, n, _ = data_u16.shape
+    na = n - 8
+    P = c["linearitylegendre"]["data"].shape[0]
+    assert c["gain"]["data"].dtype == np.float32 and c["ipc4d"]["data"].dtype == np.float32
+    S = PackSrc()
+    S.n, S.nb, S.G, S.P = n, 4, G, P
+    S.dark = p(c["dark"]["data"], np.float32)
+    if "biascorr" in c:
+        bc = c["biascorr"]["data"]
+        S.bias = p(bc[bc.shape[0] - G :], np.float32)
+    S.coefs = p(c["linearitylegendre"]["data"], np.float32)
+    S.Smin = p(c["linearitylegendre"]["Smin"], np.float32)
+    S.Smax = p(c["linearitylegendre"]["Smax"], np.float32)
+    S.Sref = p(c["linearitylegendre"]["Sref"], np.float32)
+    S.gain = p(c["gain"]["data"], np.float32)
+    S.aux, S.sdq = p(aux), p(sdq)
+    S.ipc = p(c["ipc4d"]["data"], np.float32)
+    S.read = p(c["read"]["data"], np.float32)
+    S.dslope, S.flat = p(dslope, np.float32), p(flat, np.float32)
+    A = V2Args()
+    A.n, A.band_rows = n, band_rows
+    A.do_refpix = 1 if do_refpix else 0
+    A.do_not_flag_first = 1 if list(read_pattern[0]) == [0] else 0
+    A.exclude_first = 1 if config.get("EXCLUDE_FIRST", True) else 0
+    A.sat_backup = config.get("SATURATION_BACKUP", 1)
+    A.area_dtype = _lib.RIP_F32
+    if area is not None:
+        area = _lib.as_float_plane(area)
+        A.area_dtype = _lib.float_tag(area)
+    A.raw, A.area = p(data_u16, np.uint16), p(area)
+    if do_refpix:
+        rc, cm, cc = refpix_stats(data_u16, amp33_u16, c)
+        A.rowcorr, A.chan_m, A.chan_c = p(rc), p(cm), p(cc)
+    A.thr, A.w_exact = p(thr), p(w_exact)
+    out = {
+        "slope": np.full((n, n), np.nan, np.float32),
+        "err_read": np.full((n, n), np.nan, np.float32),
+        "err_poisson": np.full((n, n), np.nan, np.float32),
+        "pdq": np.full((n, n), 0xDEADBEEF, np.uint32),
+        "endslice": np.full((na, na), 99, np.int8),
+    }
+    A.slope, A.err_read, A.err_poisson = p(out["slope"]), p(out["err_read"]), p(out["err_poisson"])
+    A.pdq, A.endslice = p(out["pdq"]), p(out["endslice"])
+    if want_rdq:
+        out["rdq"] = np.full((G, n, n), 0xEE, np.uint8)
+        A.rdq = p(out["rdq"])
+    if want_lin:
+        out["ipc"] = np.full((G, n, n), np.nan, np.float32)
+        A.lincube = p(out["ipc"])
+    rc = lib().hostcheck_cal_fused_v2(C.byref(A), C.byref(S), C.byref(plan))
+    assert rc == 0, "v2 host check: unsupported (G, P)"
     out["K"] = meta["K"]
     return out

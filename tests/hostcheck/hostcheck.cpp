@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "rip_cal_core.cuh"
+#include "rip_v2_core.cuh"
 
 using namespace rip;
 
@@ -59,3 +60,78 @@ extern "C" int hostcheck_cal_fused(const CalArgs* A, const rip_ramp_plan* plan, 
 }
 
 extern "C" int hostcheck_sizeof_calargs(void) { return (int)sizeof(CalArgs); }
+
+
+// ---- v2 (rip_v2_core.cuh): host pack with the shared rec*_word functions + the kernel's march schedule ---------
+template <int G, int P>
+static void run_v2_t(rip::v2::Args A, const rip::v2::PackSrc& S, const rip_ramp_plan& pl) {
+    using namespace rip::v2;
+    const int n = A.n, ntile = ntiles(n), nq = nq1(G, P);
+    std::vector<f4> rec1((size_t)n * ntile * nq * TW), recK((size_t)n * ntile * KQ * TW);
+    for (int row = 0; row < n; ++row)
+        for (int tile = 0; tile < ntile; ++tile)
+            for (int c = 0; c < TW; ++c) {
+                const int x = tile * TS + c;
+                for (int q = 0; q < nq; ++q)
+                    rec1[((size_t)(row * ntile + tile) * nq + q) * TW + c] =
+                        f4{rec1_word(S, row, x, 4 * q), rec1_word(S, row, x, 4 * q + 1), rec1_word(S, row, x, 4 * q + 2), rec1_word(S, row, x, 4 * q + 3)};
+                for (int q = 0; q < KQ; ++q)
+                    recK[((size_t)(row * ntile + tile) * KQ + q) * TW + c] =
+                        f4{recK_word(S, row, x, 4 * q), recK_word(S, row, x, 4 * q + 1), recK_word(S, row, x, 4 * q + 2), recK_word(S, row, x, 4 * q + 3)};
+            }
+    A.ntile = ntile;
+    A.rec1 = rec1.data();
+    A.recK = recK.data();
+    const size_t smem = Smem<G>::bytes();
+    std::vector<unsigned char> buf(smem + 64);
+    std::vector<Regs<G, P>> regs(TW);
+    const int gy = (n + A.band_rows - 1) / A.band_rows;
+    for (int by = 0; by < gy; ++by)
+        for (int tile = 0; tile < ntile; ++tile) {
+            memset(buf.data(), 0xA5, buf.size());
+            memset((void*)regs.data(), 0xA5, sizeof(Regs<G, P>) * TW);
+            unsigned char* base = buf.data();
+            base += (16 - ((size_t)base & 15)) & 15;
+            Smem<G> sm;
+            sm.carve(base);
+            const int r0 = by * A.band_rows, r1 = (r0 + A.band_rows < n) ? r0 + A.band_rows : n;
+            for (int tid = 0; tid < TW; ++tid) prologue<G, P>(A, sm, regs[tid], tid, tile, r0, r1);
+            for (int s = r0 - 3; s <= r1 + 5; ++s)
+                for (int tid = 0; tid < TW; ++tid) step<G, P>(A, pl, sm, regs[tid], tid, tile, r0, r1, s);
+        }
+}
+
+extern "C" int hostcheck_cal_fused_v2(const rip::v2::Args* A, const rip::v2::PackSrc* S, const rip_ramp_plan* plan) {
+    const int G = S->G, P = S->P;
+    if (G == 8 && P == 4) run_v2_t<8, 4>(*A, *S, *plan);
+    else if (G == 8 && P == 11) run_v2_t<8, 11>(*A, *S, *plan);
+    else if (G == 16 && P == 11) run_v2_t<16, 11>(*A, *S, *plan);
+    else if (G == 16 && P == 4) run_v2_t<16, 4>(*A, *S, *plan);
+    else return 1;
+    return 0;
+}
+extern "C" int hostcheck_sizeof_v2args(void) { return (int)sizeof(rip::v2::Args); }
+extern "C" int hostcheck_sizeof_packsrc(void) { return (int)sizeof(rip::v2::PackSrc); }
+
+// Shared-reciprocal division (rip::v2::SharedDiv) against true IEEE division, with the hardware reciprocal emulated
+// as a 1-ulp-perturbed 1/d.  Returns the number of mismatches over `count` pseudo-random (x, d) pairs.
+extern "C" long hostcheck_shared_div(long count, unsigned seed, float dlo, float dhi, float xmax) {
+    unsigned long long st = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+    auto rnd = [&]() { st = st * 6364136223846793005ULL + 1442695040888963407ULL; return (double)(st >> 11) / 9007199254740992.0; };
+    long bad = 0;
+    for (long i = 0; i < count; ++i) {
+        const float d = (float)(dlo * pow((double)dhi / dlo, rnd())) * (rnd() < 0.5 ? 1.f : -1.f);
+        const float x = (float)((2.0 * rnd() - 1.0) * xmax * pow(2.0, -20.0 * rnd()));
+        rip::v2::SharedDiv sd;
+        sd.d = d;
+        sd.ok = true;
+        float r0 = 1.0f / d;
+        const int pert = (int)(rnd() * 3.0) - 1;  // -1, 0, +1 ulp: MUFU.RCP is not correctly rounded
+        r0 = nextafterf(r0, pert > 0 ? INFINITY : (pert < 0 ? -INFINITY : r0));
+        const float e = fmaf(-d, r0, 1.0f);
+        sd.r = fmaf(r0, e, r0);
+        const rip::v2::f2 q = sd.div2(rip::v2::f2{x, -x});
+        if (q.x != x / d || q.y != (-x) / d) ++bad;
+    }
+    return bad;
+}

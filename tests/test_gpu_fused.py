@@ -35,7 +35,9 @@ def test_small_cases(tag):
     area = synth.make_area_factor(n)
     c = {k: v["roman"] for k, v in cal.items()}
     ref = orc.l1_to_l2(data_u16, amp33_u16, c, rp, 3.04, area, CFG7, do_refpix=False, return_intermediates=True)
-    for threads, band in ((0, 0), (32, 16), (64, 7)):
+    # threads = 0: automatic kernel choice (the v2 throughput kernel where eligible: all-f32 planes, G in {8,16},
+    # P in {4,11}); threads > 0: the generic v1 tile kernel with that tile width
+    for threads, band in ((0, 0), (0, 5), (32, 16), (64, 7)):
         out = _run(cal, data_u16, amp33_u16, rp, area, CFG7, False, threads=threads, band_rows=band)
         stats = compare_l2(out, ref)
         assert np.array_equal(out["meta"]["K"], ref["K"])
@@ -49,6 +51,9 @@ MEDIUM = [
      {"JUMP_DETECT_PARS": {"SthreshA": 4.0, "SthreshB": 3.5, "IthreshA": 0.6, "IthreshB": 600.0}}, 2.0, np.float64),
     (256, "README_PATTERN", 10, np.float32, np.float64, 24, {"SATURATION_BACKUP": 0}, 8.0, None),
     (512, "README_PATTERN", 15, np.float64, np.float32, 25, {}, 3.0, np.float64),
+    (384, "README_PATTERN", 3, np.float32, np.float32, 26,
+     {"SATURATION_BACKUP": 0, "JUMP_DETECT_PARS": {"SthreshA": 4.0, "SthreshB": 3.5}}, 8.0, np.float32),
+    (128, "LONG16_PATTERN", 3, np.float32, np.float32, 27, {}, 6.0, np.float64),
 ]  # fmt: skip
 
 
@@ -65,9 +70,10 @@ def test_medium_cases_with_refpix(case):
     c = {k: v["roman"] for k, v in cal.items()}
     ref = orc.l1_to_l2(data_u16, amp33_u16, c, rp, 3.04, 1.0 if area is None else area, cfg, do_refpix=True,
                        return_intermediates=True)  # fmt: skip
-    out = _run(cal, data_u16, amp33_u16, rp, area, cfg, True)
-    stats = compare_l2(out, ref)
-    print(case[:2], "values not bit-identical:", stats)
+    for threads in (0, 128):  # v2 where eligible, and v1
+        out = _run(cal, data_u16, amp33_u16, rp, area, cfg, True, threads=threads)
+        stats = compare_l2(out, ref)
+        print(case[:2], threads, "values not bit-identical:", stats)
     assert np.count_nonzero(ref["pdq"] & orc.SATURATED) > 50
     assert np.count_nonzero(ref["pdq"] & orc.JUMP_DET) > 50
     assert len(np.unique(ref["endslice"])) >= 4
@@ -134,7 +140,12 @@ def test_full_size_band_and_tiling_invariance(full_case):
     cal, data_u16, amp33_u16, rp, area = full_case
     cfg = dict(CFG7)
     out = _run(cal, data_u16, amp33_u16, rp, area, cfg, True)
-    out2 = _run(cal, data_u16, amp33_u16, rp, area, cfg, True, threads=256, band_rows=512)
+    out2 = _run(cal, data_u16, amp33_u16, rp, area, cfg, True, threads=256, band_rows=512)  # v1 kernel, other tiling
+    out3 = _run(cal, data_u16, amp33_u16, rp, area, cfg, True, band_rows=96)  # v2 kernel, other band height
+    for k in ("slope", "err_read", "err_poisson", "lin_cube"):
+        assert np.array_equal(out[k], out3[k], equal_nan=True), k
+    for k in ("pdq", "rdq", "endslice"):
+        assert np.array_equal(out[k], out3[k]), k
     for k in ("slope", "err_read", "err_poisson", "lin_cube"):
         assert np.array_equal(out[k], out2[k], equal_nan=True), k
     for k in ("pdq", "rdq", "endslice"):
