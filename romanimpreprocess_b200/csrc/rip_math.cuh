@@ -12,8 +12,10 @@
 
 #ifdef __CUDACC__
 #define RIP_HD __host__ __device__ __forceinline__
+#define RIP_HD_COLD inline __host__ __device__ __noinline__   // rarely executed paths: keep them out of the hot instruction stream
 #else
 #define RIP_HD inline
+#define RIP_HD_COLD inline
 #endif
 
 namespace rip {
@@ -125,7 +127,7 @@ using RampPlanDev = rip_ramp_plan;
 //   TD = float when the gain plane is f32 (dvardt f32, inner term rounded to f32), double when it is f64.
 //   Takes only scalars (no register-array indexing) so the cold path never forces the ramp into local memory.
 template <typename TD>
-RIP_HD float smap_exact(float delta, int ngrp, TD dvardt, float sig2read, const RampPlanDev& pl, const double* w) {
+RIP_HD_COLD float smap_exact(float delta, int ngrp, TD dvardt, float sig2read, const RampPlanDev& pl, const double* w) {
     double var = 0.0;
     for (int a = 0; a < ngrp; ++a) {
         TD inner = dvardt * (TD)pl.tau[a] + (TD)(sig2read / pl.nreads[a]);
@@ -137,7 +139,7 @@ RIP_HD float smap_exact(float delta, int ngrp, TD dvardt, float sig2read, const 
 
 // sthresh (f64) for a slope (fitting.py:215-217).  logf: CUDA/glibc logf vs NumPy's SIMD logf may differ in the
 // last ulp (SURVEY 7 "Bit-exact DQ vs float thresholds"); evaluated via double log and rounded to f32.
-RIP_HD double jump_threshold(float slope, const RampPlanDev& pl) {
+RIP_HD_COLD double jump_threshold(float slope, const RampPlanDev& pl) {
     float x = np_clip<float>(slope, pl.IthreshA_f, pl.IthreshB_f);
     float t = (float)log((double)(x / pl.IthreshA_f));
     double xx = (double)t / pl.logIratio;

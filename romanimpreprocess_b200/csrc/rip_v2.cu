@@ -37,8 +37,8 @@ __global__ void pack_recK_kernel(const PackSrc S, int ntile, f4* __restrict__ ou
     }
 }
 
-template <int G, int P>
-__global__ void __launch_bounds__(TW, 3) cal_fused_v2_kernel(const Args A) {
+template <int G, int P, int MINB>
+__global__ void __launch_bounds__(TW, MINB) cal_fused_v2_kernel(const Args A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<G> sm;
     sm.carve(smem_raw);
@@ -54,17 +54,31 @@ __global__ void __launch_bounds__(TW, 3) cal_fused_v2_kernel(const Args A) {
     }
 }
 
-template <int G, int P>
-static void launch_t(const Args& A, cudaStream_t st) {
+template <int G, int P, int MINB>
+static void launch_tb(const Args& A, cudaStream_t st) {
     const size_t smem = Smem<G>::bytes();
-    auto kern = cal_fused_v2_kernel<G, P>;
+    auto kern = cal_fused_v2_kernel<G, P, MINB>;
     static thread_local bool configured = false;
     if (!configured) {
         RIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
     dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
     RIP_LAUNCH(kern, grid, TW, smem, st, A);
+}
+
+// resident CTAs per SM the kernel is compiled for: 4 (128 registers/thread) for G <= 8, 3 for G = 16 (larger rings);
+// RIP_V2_MINB=3|4 overrides for experiments
+template <int G, int P>
+static void launch_t(const Args& A, cudaStream_t st) {
+    static const int minb = [] {
+        const char* e = getenv("RIP_V2_MINB");
+        const int v = e ? atoi(e) : 0;
+        return (v == 3 || v == 4) ? v : ((G <= 8) ? 4 : 3);
+    }();
+    if (minb == 4 && G <= 8) launch_tb<G, P, 4>(A, st);
+    else launch_tb<G, P, 3>(A, st);
 }
 
 }  // namespace v2

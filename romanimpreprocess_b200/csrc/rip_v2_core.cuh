@@ -30,7 +30,7 @@ namespace v2 {
 
 constexpr int TW = 128;   // columns per tile (= compute threads per CTA)
 constexpr int TS = 120;   // tile stride: outputs are tile columns 4..123 (tile 0 also 0..3)
-constexpr int RW = TW + 4;  // ring width: 2 pad columns on each side
+constexpr int RW = TW + 2;  // ring width: 1 pad column on each side
 constexpr int KQ = 4;     // float4 words per pixel in recK
 constexpr int D_DEPTH = 8, O_DEPTH = 4, S_DEPTH = 4, F_DEPTH = 5;  // D also parks the converted raw rows (s..s-6 live)
 
@@ -45,21 +45,31 @@ struct alignas(16) f4 {
 };
 
 // ---- packed arithmetic: two independent IEEE-rounded single-precision operations -------------------------
+// NB (measured, CUDA 12.9 ptxas for sm_100a): ptxas contracts `mul.rn.f32x2` feeding `add.rn.f32x2` into one FFMA2
+// even with --fmad=false, which would change the rounding.  It does NOT contract a packed multiply feeding SCALAR
+// `add.rn.f32` / `sub.rn.f32`.  Hence: multiplies are packed (mul2); additions/subtractions that may consume a
+// product are scalar pairs (add2 / sub2); packed add/sub (add2p / sub2p) only where no operand is a product.
+// `make check-sass` (csrc/Makefile) verifies that the FFMA2 count in SASS equals the fma.rn.f32x2 count in PTX.
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return f2{r.x, r.y}; }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return f2{r.x, r.y}; }
-// a - b == fma(b, -1, a) exactly (the product is exact)
-__device__ __forceinline__ f2 sub2(f2 a, f2 b) { float2 r = __ffma2_rn(make_float2(b.x, b.y), make_float2(-1.0f, -1.0f), make_float2(a.x, a.y)); return f2{r.x, r.y}; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return f2{__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)}; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return f2{__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)}; }
+__device__ __forceinline__ f2 add2p(f2 a, f2 b) { float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return f2{r.x, r.y}; }
+__device__ __forceinline__ f2 sub2p(f2 a, f2 b) { float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(-b.x, -b.y)); return f2{r.x, r.y}; }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y)); return f2{r.x, r.y}; }
 __device__ __forceinline__ float fma1(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ float rcp_approx(float d) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d)); return r; }
+#define RIP_COLD __noinline__
 #else
 inline f2 mul2(f2 a, f2 b) { return f2{a.x * b.x, a.y * b.y}; }
 inline f2 add2(f2 a, f2 b) { return f2{a.x + b.x, a.y + b.y}; }
 inline f2 sub2(f2 a, f2 b) { return f2{a.x - b.x, a.y - b.y}; }
+inline f2 add2p(f2 a, f2 b) { return add2(a, b); }
+inline f2 sub2p(f2 a, f2 b) { return sub2(a, b); }
 inline f2 fma2(f2 a, f2 b, f2 c) { return f2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
 inline float fma1(float a, float b, float c) { return fmaf(a, b, c); }
 inline float rcp_approx(float d) { return 1.0f / d; }
+#define RIP_COLD
 #endif
 RIP_HD f2 bc(float a) { return f2{a, a}; }
 
@@ -123,12 +133,13 @@ struct Smem {
     f4* D;            // [D_DEPTH][G/4][RW]
     f4* O1;           // [O_DEPTH][G/4][RW]
     uint32_t* sat;    // [S_DEPTH][RW]
-    uint32_t* flg;    // [F_DEPTH][TW][2]   (satm | adf<<16, nlc)   thread-private delay line a1 -> c
+    uint32_t* flg;    // [F_DEPTH][TW]      satm | adf<<16                 thread-private delay line a1 -> c
+    uint8_t* nlc;     // [F_DEPTH][TW]      bit0 dynamic NO_LIN_CORR, bit2 reference pixel
     double* rc;       // [2][G]             row correction of the row a1 handles next / now
     double* ln;       // [2][2][G]          channel line for the two channels the tile touches
     static constexpr int H = G / 4;
     RIP_HD static size_t bytes() {
-        return sizeof(f4) * (size_t)(D_DEPTH + O_DEPTH) * H * RW + 4 * (size_t)S_DEPTH * RW + 8 * (size_t)F_DEPTH * TW +
+        return sizeof(f4) * (size_t)(D_DEPTH + O_DEPTH) * H * RW + 4 * (size_t)S_DEPTH * RW + 5 * (size_t)F_DEPTH * TW +
                8 * (size_t)(2 * G + 4 * G) + 64;
     }
     RIP_HD void carve(unsigned char* base) {
@@ -138,7 +149,8 @@ struct Smem {
         rc = (double*)(base + off); off += 8 * (size_t)2 * G;
         ln = (double*)(base + off); off += 8 * (size_t)4 * G;
         sat = (uint32_t*)(base + off); off += 4 * (size_t)S_DEPTH * RW;
-        flg = (uint32_t*)(base + off);
+        flg = (uint32_t*)(base + off); off += 4 * (size_t)F_DEPTH * TW;
+        nlc = (uint8_t*)(base + off);
     }
 };
 
@@ -235,6 +247,32 @@ RIP_HD void stencil9(const f4* ring_m, const f4* ring_0, const f4* ring_p, int c
 #undef RIP_TAP
 }
 
+// all slices of variant v in the reference's exact op order (fitting.py:225-251); cold
+template <int G>
+RIP_HD_COLD uint32_t jump_exact(const float (&d)[G], int v, float slope, float dvardt, float sig2read, const RampPlanDev& pl,
+                                const double* w_all) {
+    const int ngrp = pl.var_ngrp[v], start = pl.start;
+    const double thr_exact = jump_threshold(slope, pl);
+    int s = pl.var_slice_off[v];
+    uint32_t mask = 0u;
+    for (int i = start; i < ngrp - 1; ++i) {
+        const int dimax = (i == ngrp - 2 || ngrp - 1 - start == 2) ? 1 : 2;
+        for (int di = 1; di <= dimax; ++di) {
+            const RampSlice& sl = pl.slices[s];
+            float dhi = d[0], dlo = d[0];
+#pragma unroll
+            for (int t = 0; t < G; ++t) {  // register-array selects instead of dynamic indexing
+                if (t == i + di) dhi = d[t];
+                if (t == i) dlo = d[t];
+            }
+            const float sme = smap_exact<float>((dhi - dlo) / sl.dt - slope, ngrp, dvardt, sig2read, pl, w_all + (long)s * RIP_GMAX);
+            if ((double)sme > thr_exact) mask |= 1u << i;
+            ++s;
+        }
+    }
+    return mask;
+}
+
 // jump_detect for one pixel, fast form (plan variant v, compile-time G).  Same decisions as
 // rip::jump_detect_pixel<.., FAST=true>; the sure-flag / sure-clear tests are done on squares.
 template <int G>
@@ -262,8 +300,9 @@ RIP_HD FitResult jump_fast(const float (&d)[G], int v, float gain, float read, b
     const bool thr_pos = thr > 0.0f;
     float hi = thr * (1.0f + pl.band), lo = thr * (1.0f - pl.band);
     const float hi2 = hi * hi * (1.0f + 4.0e-7f), lo2 = lo * lo * (1.0f - 4.0e-7f);
-    double thr_exact = 0.0;
-    bool have_thr = false;
+    // every slice is classified without branching; pixels with any unsure slice redo all slices exactly (rare)
+    bool unsure = false;
+    uint32_t mask = 0u;
 #pragma unroll
     for (int i = 0; i < G - 1; ++i) {
         if (i >= start && i < ngrp - 1) {
@@ -279,18 +318,15 @@ RIP_HD FitResult jump_fast(const float (&d)[G], int v, float gain, float read, b
                     const bool vpos = thr_pos && (var > 0.0f);
                     const bool sure_set = vpos && (delta > 0.0f) && (l2 > hi2 * var);
                     const bool sure_clr = vpos && ((delta <= 0.0f) || (l2 < lo2 * var));
-                    if (sure_set) {
-                        r.jump_mask |= 1u << i;
-                    } else if (!sure_clr) {  // borderline, NaN, degenerate variance or exotic thresholds -> exact
-                        if (!have_thr) { thr_exact = jump_threshold(r.slope, pl); have_thr = true; }
-                        const float sme = smap_exact<float>(diff / sl.dt - r.slope, ngrp, dvardt, sig2read, pl, w_all + (long)s * RIP_GMAX);
-                        if ((double)sme > thr_exact) r.jump_mask |= 1u << i;
-                    }
+                    mask |= sure_set ? (1u << i) : 0u;
+                    unsure = unsure || !(sure_set || sure_clr);  // borderline, NaN, degenerate variance, exotic thresholds
                     ++s;
                 }
             }
         }
     }
+    if (unsure) mask = jump_exact<G>(d, v, r.slope, dvardt, sig2read, pl, w_all);
+    r.jump_mask = mask;
     return r;
 }
 
@@ -336,7 +372,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
     const long npl = (long)n * n;
     const int x = tile * TS + tid;
     const bool xin = x < n;
-    const int col = tid + 2;
+    const int col = tid + 1;
     const uint32_t allg = (1u << G) - 1u;
     const bool xact = (x >= nb && x < n - nb);
 
@@ -347,8 +383,8 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
         if (row >= r0 && row < r1 && out_col) {
             const long p = (long)row * n + x;
             const bool active = xact && (row >= nb && row < n - nb);
-            const uint32_t fl = sm.flg[(mod_pos(row, F_DEPTH) * TW + tid) * 2];
-            const uint32_t nlc = sm.flg[(mod_pos(row, F_DEPTH) * TW + tid) * 2 + 1];
+            const uint32_t fl = sm.flg[mod_pos(row, F_DEPTH) * TW + tid];
+            const uint32_t nlc = sm.nlc[mod_pos(row, F_DEPTH) * TW + tid];
             const float gval = R.kc[2].y, readv = R.kc[2].z, dsl = R.kc[2].w, flat = R.kc[3].x;
             const uint32_t sdq = f_as_u(R.kc[3].y);
             float d[G];
@@ -366,14 +402,14 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
                     f2 lo, hi;
                     stencil9(om + h * RW, o0 + h * RW, op + h * RW, col, k, lo, hi);
                     const f4 oc = o0[h * RW + col], dc = dd[h * RW + col];
-                    t[2 * h] = sub2(add2(f2{oc.x, oc.y}, f2{dc.x, dc.y}), lo);  // (output + image2) - ipc_fwd(output)
-                    t[2 * h + 1] = sub2(add2(f2{oc.z, oc.w}, f2{dc.z, dc.w}), hi);
+                    t[2 * h] = sub2p(add2p(f2{oc.x, oc.y}, f2{dc.x, dc.y}), lo);  // (output + image2) - ipc_fwd(output)
+                    t[2 * h + 1] = sub2p(add2p(f2{oc.z, oc.w}, f2{dc.z, dc.w}), hi);
                 }
                 bool slow = !sd.ok;
                 if (!slow) {
                     f2 chk = f2{0.f, 0.f};
 #pragma unroll
-                    for (int j = 0; j < G / 2; ++j) { q[j] = sd.div2(t[j]); chk = add2(chk, q[j]); }
+                    for (int j = 0; j < G / 2; ++j) { q[j] = sd.div2(t[j]); chk = add2p(chk, q[j]); }
                     const float tt = chk.x + chk.y;
                     slow = !(tt == tt);  // a NaN from the correction steps (infinite numerator) -> true division
                 }
@@ -462,7 +498,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
                 stencil9(dm + h * RW, d0 + h * RW, dp + h * RW, col, k, lo, hi);
                 const f4 dc = d0[h * RW + col];
                 const f2 clo{dc.x, dc.y}, chi{dc.z, dc.w};
-                const f2 rlo = sub2(add2(clo, clo), lo), rhi = sub2(add2(chi, chi), hi);  // output + image2 - ipc_fwd(output)
+                const f2 rlo = sub2p(add2p(clo, clo), lo), rhi = sub2p(add2p(chi, chi), hi);  // output + image2 - ipc_fwd(output)
                 o[h * RW + col] = f4{rlo.x, rlo.y, rhi.x, rhi.y};
             }
         } else if (row >= r0 - 1 && row < r1 + 1) {
@@ -477,7 +513,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
         const int row = s - 2;
         const bool rowin = row >= 0 && row < n && row >= r0 - 2 && row < r1 + 2;
         f4* dst = sm.D + (size_t)(row & (D_DEPTH - 1)) * H * RW;
-        uint32_t* fdst = sm.flg + (mod_pos(row, F_DEPTH) * TW + tid) * 2;
+        const int fslot = mod_pos(row, F_DEPTH) * TW + tid;
         if (rowin && (tid >= 1 || tile == 0) && tid <= TW - 2 && xin) {
             uint32_t grown = 0u;
 #pragma unroll
@@ -517,7 +553,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
             f2 S2[G / 2];
 #pragma unroll
             for (int j = 0; j < G / 2; ++j)
-                S2[j] = sub2(f2{S[2 * j], S[2 * j + 1]}, f2{r1w<NQ1>(R.r1, G + 2 * j), r1w<NQ1>(R.r1, G + 2 * j + 1)});
+                S2[j] = sub2p(f2{S[2 * j], S[2 * j + 1]}, f2{r1w<NQ1>(R.r1, G + 2 * j), r1w<NQ1>(R.r1, G + 2 * j + 1)});
             const float Smin = r1w<NQ1>(R.r1, 2 * G), Smax = r1w<NQ1>(R.r1, 2 * G + 1), Sref = r1w<NQ1>(R.r1, 2 * G + 2);
             const float gain = r1w<NQ1>(R.r1, 2 * G + 3);
             const uint32_t aux = f_as_u(r1w<NQ1>(R.r1, 2 * G + 4));
@@ -532,11 +568,11 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
             f2 z2[G / 2];
 #pragma unroll
             for (int j = 0; j < G / 2; ++j) {
-                const f2 num = mul2(bc(2.0f), sub2(S2[j], bc(Smin)));
+                const f2 num = mul2(bc(2.0f), sub2p(S2[j], bc(Smin)));
                 f2 q;
                 if (div_ok) q = sd.div2(num);
                 else q = f2{num.x / den, num.y / den};
-                z2[j] = add2(bc(-1.0f), q);
+                z2[j] = add2p(bc(-1.0f), q);
             }
             if (A.do_not_flag_first) z2[0].x = np_clip<float>(z2[0].x, -1.0f, 1.0f);
             // |z| > 1 anywhere (or NaN) -> the extrapolating scalar evaluation of v1 for this pixel (rare)
@@ -579,7 +615,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
             }
             if (aux & 1u) {  // lin dq has NO_LIN_CORR | REFERENCE_PIXEL: S - Sref instead (ipc_linearity.py:334-336)
 #pragma unroll
-                for (int j = 0; j < G / 2; ++j) phi2[j] = sub2(S2[j], bc(Sref));
+                for (int j = 0; j < G / 2; ++j) phi2[j] = sub2p(S2[j], bc(Sref));
             }
             if (active) {
 #pragma unroll
@@ -596,13 +632,13 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
                         A.lincube[(long)g * npl + (long)row * n + x] = (g & 1) ? phi2[g >> 1].y : phi2[g >> 1].x;
                 }
             }
-            fdst[0] = satm | (adf << 16);
-            fdst[1] = ((dq & DQ_NO_LIN_CORR) ? 1u : 0u) | ((aux & 2u) ? 4u : 0u);
+            sm.flg[fslot] = satm | (adf << 16);
+            sm.nlc[fslot] = (uint8_t)(((dq & DQ_NO_LIN_CORR) ? 1u : 0u) | ((aux & 2u) ? 4u : 0u));
         } else if (row >= r0 - 2 && row < r1 + 2) {
 #pragma unroll
             for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
-            fdst[0] = 0u;
-            fdst[1] = 0u;
+            sm.flg[fslot] = 0u;
+            sm.nlc[fslot] = 0;
         }
         load_a1<G, P>(A, R, row + 1, tile, tid, r0 - 2, r1 + 2);
     }
