@@ -56,7 +56,8 @@ typedef struct rip_ramp_plan {
     float IthreshA_f, IthreshB_f;
     double SthreshA, SthreshB, logIratio; /* (:172-184, 215-217)                                      */
     float band;                           /* relative half-width of the exact-recheck band            */
-    float pad_;
+    /* fast path only: thr ~= thrA_f + thrK_f * log(clip(slope) * invIA_f),  thrK = (SthreshB-SthreshA)/log(IB/IA) */
+    float thrA_f, thrK_f, invIA_f;
 } rip_ramp_plan;
 
 /* ---- one SCA's calibration reference data (CALDIR), host pointers ---------------------------*/
@@ -212,6 +213,19 @@ int rip_l1_to_l2_host(rip_caldir* h, const uint16_t* raw, const uint16_t* amp33,
 int rip_l1_to_l2_dev(rip_caldir* h, const uint16_t* d_raw, const uint16_t* d_amp33, const void* d_area,
                      const rip_l1l2_params* prm, const rip_ramp_plan* plan, const double* w_exact,
                      const rip_l2_out* d_out, void* stream);
+/* Pipelined host entry for a stream of exposures of one SCA: `depth` exposures in flight on three CUDA streams
+ * (H2D | reference-pixel statistics + fused kernel | D2H), so PCIe copies overlap the kernels.  submit() returns
+ * immediately (it blocks only when all slots are busy) and hands back a ticket; the host output buffers named in
+ * `out` are valid after wait(ticket).  Host buffers should be page-locked (rip_host_alloc) for real overlap; the
+ * input buffers must stay untouched until wait() returns.  Same arithmetic as rip_l1_to_l2_host. */
+typedef struct rip_pipeline rip_pipeline;
+int rip_pipeline_create(rip_caldir* h, int G, int depth, int want_endslice, int want_rdq, rip_pipeline** out);
+void rip_pipeline_destroy(rip_pipeline* p);
+int rip_pipeline_submit(rip_pipeline* p, const uint16_t* raw, const uint16_t* amp33, const void* area,
+                        const rip_l1l2_params* prm, const rip_ramp_plan* plan, const double* w_exact,
+                        const rip_l2_out* out, long* ticket);
+int rip_pipeline_wait(rip_pipeline* p, long ticket);
+
 /* Per-launch device timing of the fused kernel (bench.py's roofline): while enabled, every rip_l1_to_l2_* call on
  * this handle brackets the fused kernel with CUDA events on its launch stream; rip_profile_fetch waits for them,
  * returns the summed kernel time [ms] and the number of launches, and resets the counter. */

@@ -35,7 +35,7 @@ class RampPlan(C.Structure):
         ("slices", RampSlice * RIP_MAXSLICE),
         ("IthreshA_f", C.c_float), ("IthreshB_f", C.c_float),
         ("SthreshA", C.c_double), ("SthreshB", C.c_double), ("logIratio", C.c_double),
-        ("band", C.c_float), ("pad_", C.c_float),
+        ("band", C.c_float), ("thrA_f", C.c_float), ("thrK_f", C.c_float), ("invIA_f", C.c_float),
     ]  # fmt: skip
 
 
@@ -117,6 +117,11 @@ _SIGS = {
                                     C.POINTER(RampPlan), C.c_void_p, C.POINTER(L2Out)]),
     "rip_l1_to_l2_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(L1L2Params),
                                    C.POINTER(RampPlan), C.c_void_p, C.POINTER(L2Out), C.c_void_p]),
+    "rip_pipeline_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "rip_pipeline_destroy": (None, [C.c_void_p]),
+    "rip_pipeline_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(L1L2Params),
+                                      C.POINTER(RampPlan), C.c_void_p, C.POINTER(L2Out), C.POINTER(C.c_long)]),
+    "rip_pipeline_wait": (C.c_int, [C.c_void_p, C.c_long]),
     "rip_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "rip_profile_fetch": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "rip_refpix_stats_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,

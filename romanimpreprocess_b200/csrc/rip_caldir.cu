@@ -240,7 +240,7 @@ using namespace rip;
 static void run_k0(rip_caldir* h, const uint16_t* d_raw, const uint16_t* d_amp33, int G, cudaStream_t st) {
     const int n = h->n;
     RIP_REQUIRE(h->has_amp33, "reference-pixel correction needs amp33 statistics in the read file (the reference's np.polyfit fails without them: SURVEY 7)");
-    RIP_REQUIRE(n % 128 == 0 && n <= 4096 && n >= 256, "reference-pixel correction needs a frame side that is a multiple of 128 in 256..4096 (got %d)", n);
+    RIP_REQUIRE(n % 128 == 0 && n <= 4096 && n >= 128, "reference-pixel correction needs a frame side that is a multiple of 128 in 128..4096 (got %d)", n);
     RIP_REQUIRE(d_amp33 != nullptr, "reference-pixel correction needs the amp33 cube");
     const long M = (long)n * 128;
     const int nch = n / 128;
@@ -535,5 +535,135 @@ extern "C" int rip_refpix_stats_host(rip_caldir* h, const uint16_t* raw, const u
     if (chan_c) h->chan_c.download(chan_c, (size_t)G * 32, st);
     if (gmed) h->gmed.download(gmed, G, st);
     RIP_CUDA(cudaStreamSynchronize(st));
+    RIP_API_END
+}
+
+
+// =========================================================================================================
+// Pipelined host entry: exposures in flight on three streams (H2D | K0 + fused kernel | D2H), `depth` slots of
+// device buffers.  For callers that process a stream of exposures of one SCA from (pinned) host memory: the
+// PCIe copies of neighbouring exposures overlap the kernels, so the end-to-end rate is bounded by the slower PCIe
+// direction instead of the sum of copies and compute.
+// =========================================================================================================
+struct rip_pipeline {
+    rip_caldir* h = nullptr;
+    int G = 0, depth = 0;
+    bool want_end = false, want_rdq = false;
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    struct Slot {
+        DevBuf<uint16_t> raw, amp;
+        DevRaw area;
+        DevBuf<float> slope, er, ep;
+        DevBuf<uint32_t> pdq;
+        DevBuf<int8_t> end;
+        DevBuf<uint8_t> rdq;
+        cudaEvent_t in_done = nullptr, run_done = nullptr, out_done = nullptr;
+        long ticket = -1;
+    };
+    std::unique_ptr<Slot[]> slots;
+    long next_ticket = 0;
+};
+
+extern "C" int rip_pipeline_create(rip_caldir* h, int G, int depth, int want_endslice, int want_rdq, rip_pipeline** out) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && out, "rip_pipeline_create: null argument");
+    RIP_REQUIRE(G >= 3 && G <= RIP_GMAX, "rip_pipeline_create: G=%d outside 3..%d", G, RIP_GMAX);
+    RIP_REQUIRE(depth >= 1 && depth <= 8, "rip_pipeline_create: depth=%d outside 1..8", depth);
+    use_device(h->device);
+    std::unique_ptr<rip_pipeline> p(new rip_pipeline);
+    p->h = h; p->G = G; p->depth = depth; p->want_end = want_endslice != 0; p->want_rdq = want_rdq != 0;
+    RIP_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+    RIP_CUDA(cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking));
+    RIP_CUDA(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+    const size_t npl = (size_t)h->n * h->n, npa = (size_t)h->na * h->na;
+    p->slots.reset(new rip_pipeline::Slot[depth]);
+    for (int i = 0; i < depth; ++i) {
+        auto& s = p->slots[i];
+        s.raw.alloc((size_t)G * npl);
+        s.amp.alloc((size_t)G * h->n * 128);
+        s.area.alloc(npl * 8);
+        s.slope.alloc(npl); s.er.alloc(npl); s.ep.alloc(npl); s.pdq.alloc(npl);
+        if (p->want_end) s.end.alloc(npa);
+        if (p->want_rdq) s.rdq.alloc((size_t)G * npl);
+        RIP_CUDA(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
+        RIP_CUDA(cudaEventCreateWithFlags(&s.run_done, cudaEventDisableTiming));
+        RIP_CUDA(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
+    }
+    *out = p.release();
+    RIP_API_END
+}
+
+extern "C" void rip_pipeline_destroy(rip_pipeline* p) {
+    if (!p) return;
+    cudaSetDevice(p->h->device);
+    cudaStreamSynchronize(p->s_in);
+    cudaStreamSynchronize(p->s_run);
+    cudaStreamSynchronize(p->s_out);
+    for (int i = 0; i < p->depth; ++i) {
+        auto& s = p->slots[i];
+        if (s.in_done) cudaEventDestroy(s.in_done);
+        if (s.run_done) cudaEventDestroy(s.run_done);
+        if (s.out_done) cudaEventDestroy(s.out_done);
+    }
+    cudaStreamDestroy(p->s_in);
+    cudaStreamDestroy(p->s_run);
+    cudaStreamDestroy(p->s_out);
+    delete p;
+}
+
+extern "C" int rip_pipeline_submit(rip_pipeline* p, const uint16_t* raw, const uint16_t* amp33, const void* area,
+                                   const rip_l1l2_params* prm, const rip_ramp_plan* plan, const double* w_exact,
+                                   const rip_l2_out* out, long* ticket) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(p && raw && prm && plan && out && ticket, "rip_pipeline_submit: null argument");
+    RIP_REQUIRE(prm->G == p->G, "rip_pipeline_submit: params.G=%d but the pipeline was created for G=%d", prm->G, p->G);
+    RIP_REQUIRE(out->slope && out->err_read && out->err_poisson && out->pdq, "rip_pipeline_submit: slope/err_read/err_poisson/pdq outputs are required");
+    RIP_REQUIRE(!out->endslice || p->want_end, "rip_pipeline_submit: pipeline was created without endslice buffers");
+    RIP_REQUIRE(!out->rdq || p->want_rdq, "rip_pipeline_submit: pipeline was created without rdq buffers");
+    RIP_REQUIRE(!out->lin_cube, "rip_pipeline_submit: lin_cube is not available on the pipelined path");
+    rip_caldir* h = p->h;
+    use_device(h->device);
+    const size_t npl = (size_t)h->n * h->n, npa = (size_t)h->na * h->na;
+    const int G = p->G;
+    auto& s = p->slots[p->next_ticket % p->depth];
+    if (s.ticket >= 0) RIP_CUDA(cudaEventSynchronize(s.out_done));  // slot still draining to the host: wait for it
+    // H2D
+    RIP_CUDA(cudaMemcpyAsync(s.raw.p, raw, (size_t)G * npl * 2, cudaMemcpyHostToDevice, p->s_in));
+    if (prm->do_refpix) {
+        RIP_REQUIRE(amp33, "rip_pipeline_submit: do_refpix needs the amp33 cube");
+        RIP_CUDA(cudaMemcpyAsync(s.amp.p, amp33, (size_t)G * h->n * 128 * 2, cudaMemcpyHostToDevice, p->s_in));
+    }
+    if (area) RIP_CUDA(cudaMemcpyAsync(s.area.p, area, npl * dtype_size(prm->area_dtype), cudaMemcpyHostToDevice, p->s_in));
+    RIP_CUDA(cudaEventRecord(s.in_done, p->s_in));
+    // compute (one stream: the K0 workspace of the handle is shared by all slots)
+    RIP_CUDA(cudaStreamWaitEvent(p->s_run, s.in_done, 0));
+    rip_l2_out o{};
+    o.slope = s.slope.p; o.err_read = s.er.p; o.err_poisson = s.ep.p; o.pdq = s.pdq.p;
+    if (out->endslice) o.endslice = s.end.p;
+    if (out->rdq) o.rdq = s.rdq.p;
+    l1_to_l2_dev_impl(h, s.raw.p, prm->do_refpix ? s.amp.p : nullptr, area ? s.area.p : nullptr, prm, plan, w_exact, &o, p->s_run);
+    RIP_CUDA(cudaEventRecord(s.run_done, p->s_run));
+    // D2H
+    RIP_CUDA(cudaStreamWaitEvent(p->s_out, s.run_done, 0));
+    RIP_CUDA(cudaMemcpyAsync(out->slope, s.slope.p, npl * 4, cudaMemcpyDeviceToHost, p->s_out));
+    RIP_CUDA(cudaMemcpyAsync(out->err_read, s.er.p, npl * 4, cudaMemcpyDeviceToHost, p->s_out));
+    RIP_CUDA(cudaMemcpyAsync(out->err_poisson, s.ep.p, npl * 4, cudaMemcpyDeviceToHost, p->s_out));
+    RIP_CUDA(cudaMemcpyAsync(out->pdq, s.pdq.p, npl * 4, cudaMemcpyDeviceToHost, p->s_out));
+    if (out->endslice) RIP_CUDA(cudaMemcpyAsync(out->endslice, s.end.p, npa, cudaMemcpyDeviceToHost, p->s_out));
+    if (out->rdq) RIP_CUDA(cudaMemcpyAsync(out->rdq, s.rdq.p, (size_t)G * npl, cudaMemcpyDeviceToHost, p->s_out));
+    RIP_CUDA(cudaEventRecord(s.out_done, p->s_out));
+    s.ticket = p->next_ticket;
+    *ticket = p->next_ticket++;
+    RIP_API_END
+}
+
+extern "C" int rip_pipeline_wait(rip_pipeline* p, long ticket) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(p, "rip_pipeline_wait: null pipeline");
+    RIP_REQUIRE(ticket >= 0 && ticket < p->next_ticket, "rip_pipeline_wait: unknown ticket %ld", ticket);
+    use_device(p->h->device);
+    auto& s = p->slots[ticket % p->depth];
+    // a newer exposure in the same slot implies this ticket completed (submit waited for it)
+    if (s.ticket == ticket) RIP_CUDA(cudaEventSynchronize(s.out_done));
     RIP_API_END
 }

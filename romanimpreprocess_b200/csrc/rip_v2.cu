@@ -48,8 +48,10 @@ __global__ void __launch_bounds__(TW, MINB) cal_fused_v2_kernel(const Args A) {
     const int r1 = min(r0 + A.band_rows, A.n);
     prologue<G, P>(A, sm, R, tid, tile, r0, r1);
     __syncthreads();
+    int f5 = mod_pos(r0 - 3, F_DEPTH);
     for (int s = r0 - 3; s <= r1 + 5; ++s) {
-        step<G, P>(A, c_plan_v2, sm, R, tid, tile, r0, r1, s);
+        step<G, P>(A, c_plan_v2, sm, R, tid, tile, r0, r1, s, f5);
+        f5 = (f5 == F_DEPTH - 1) ? 0 : f5 + 1;
         __syncthreads();
     }
 }

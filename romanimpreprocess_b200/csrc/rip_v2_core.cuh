@@ -32,7 +32,7 @@ constexpr int TW = 128;   // columns per tile (= compute threads per CTA)
 constexpr int TS = 120;   // tile stride: outputs are tile columns 4..123 (tile 0 also 0..3)
 constexpr int RW = TW + 2;  // ring width: 1 pad column on each side
 constexpr int KQ = 4;     // float4 words per pixel in recK
-constexpr int D_DEPTH = 8, O_DEPTH = 4, S_DEPTH = 4, F_DEPTH = 5;  // D also parks the converted raw rows (s..s-6 live)
+constexpr int D_DEPTH = 5, O_DEPTH = 4, S_DEPTH = 4, F_DEPTH = 5, R_DEPTH = 5;  // the depth-5 rings share one modulo index
 
 RIP_HD constexpr int nq1(int G, int P) { return (2 * G + 5 + P + 3) / 4; }
 inline int ntiles(int n) { return (n - 4 + TS - 1) / TS; }
@@ -135,17 +135,19 @@ struct Smem {
     uint32_t* sat;    // [S_DEPTH][RW]
     uint32_t* flg;    // [F_DEPTH][TW]      satm | adf<<16                 thread-private delay line a1 -> c
     uint8_t* nlc;     // [F_DEPTH][TW]      bit0 dynamic NO_LIN_CORR, bit2 reference pixel
+    uint16_t* rawq;   // [R_DEPTH][G][TW]   raw resultants, filled by cp.async two steps ahead (rows s-2 .. s+2 live)
     double* rc;       // [2][G]             row correction of the row a1 handles next / now
     double* ln;       // [2][2][G]          channel line for the two channels the tile touches
     static constexpr int H = G / 4;
     RIP_HD static size_t bytes() {
         return sizeof(f4) * (size_t)(D_DEPTH + O_DEPTH) * H * RW + 4 * (size_t)S_DEPTH * RW + 5 * (size_t)F_DEPTH * TW +
-               8 * (size_t)(2 * G + 4 * G) + 64;
+               8 * (size_t)(2 * G + 4 * G) + 2 * (size_t)R_DEPTH * G * TW + 64;
     }
     RIP_HD void carve(unsigned char* base) {
         size_t off = 0;
         D = (f4*)(base + off); off += sizeof(f4) * (size_t)D_DEPTH * H * RW;
         O1 = (f4*)(base + off); off += sizeof(f4) * (size_t)O_DEPTH * H * RW;
+        rawq = (uint16_t*)(base + off); off += 2 * (size_t)R_DEPTH * G * TW;
         rc = (double*)(base + off); off += 8 * (size_t)2 * G;
         ln = (double*)(base + off); off += 8 * (size_t)4 * G;
         sat = (uint32_t*)(base + off); off += 4 * (size_t)S_DEPTH * RW;
@@ -158,27 +160,62 @@ struct Smem {
 template <int G, int P>
 struct Regs {
     static constexpr int NQ1 = nq1(G, P);
-    uint32_t raw[G];   // stage a0, row s
-    float thr;
+    float thr;         // stage a0, row s (the raw resultants arrive in shared memory by cp.async)
     f4 r1[NQ1];        // stage a1, row s-2
-    f4 kb[3];          // stage b,  row s-4 (taps 0..8)
+    f4 kb[2];          // stage b,  row s-4 (taps 0..7)
+    float kb8;         //                   (tap 8)
     f4 kc[KQ];         // stage c,  row s-6
     float area32;
     double area64;
 };
 
 RIP_HD int mod_pos(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
+RIP_HD int wrap5(int a) { return a >= F_DEPTH ? a - F_DEPTH : a; }  // a in [0, 2*F_DEPTH)
+// slot of row s+DK in a depth-5 ring, given f5 = s mod 5 (DK is a compile-time constant)
+#define RIP_SLOT5(DK) wrap5(f5 + ((((DK) % 5) + 5) % 5))
 
 // ---- loads -------------------------------------------------------------------------------------------------
 template <int G, int P>
 RIP_HD void load_a0(const Args& A, Regs<G, P>& R, int row, int x, bool xin, int lo, int hi) {
-    if (row >= 0 && row < A.n && row >= lo && row < hi && xin) {
+    if (row >= 0 && row < A.n && row >= lo && row < hi && xin) R.thr = A.thr[(long)row * A.n + x];
+}
+
+// 16-byte asynchronous global -> shared copy (LDGSTS); the host build copies at once
+RIP_HD void cp_async16(void* smem_dst, const void* gmem_src) {
+#if defined(__CUDA_ARCH__)
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#else
+    memcpy(smem_dst, gmem_src, 16);
+#endif
+}
+RIP_HD void cp_async_commit() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+RIP_HD void cp_async_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+// raw resultants of one row of the tile -> ring slot: G x 128 columns x u16 = G x 16 chunks of 16 bytes, one (G = 8) or
+// two (G = 16) per thread.  Every thread commits a group each step (possibly empty) so that wait_group counts steps.
+template <int G>
+RIP_HD void raw_row_async(const Args& A, Smem<G>& sm, int row, int slot, int tile, int tid, int lo, int hi) {
+    if (row >= 0 && row < A.n && row >= lo && row < hi) {
         const long npl = (long)A.n * A.n;
-        const uint16_t* p = A.raw + (long)row * A.n + x;
+        const int x0 = tile * TS;
 #pragma unroll
-        for (int g = 0; g < G; ++g) R.raw[g] = p[(long)g * npl];
-        R.thr = A.thr[(long)row * A.n + x];
+        for (int k = 0; k < (G * 16 + TW - 1) / TW; ++k) {
+            const int idx = tid + k * TW, g = idx >> 4, c = idx & 15;
+            if (g < G && x0 + 8 * c + 8 <= A.n)
+                cp_async16(sm.rawq + ((size_t)slot * G + g) * TW + 8 * c, A.raw + (long)g * npl + (long)row * A.n + x0 + 8 * c);
+        }
     }
+    cp_async_commit();
 }
 template <int G, int P>
 RIP_HD void load_a1(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int lo, int hi) {
@@ -192,8 +229,9 @@ template <int G, int P>
 RIP_HD void load_b(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int lo, int hi) {
     if (row >= 0 && row < A.n && row >= lo && row < hi) {
         const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW) + tid;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) R.kb[q] = p[q * TW];
+        R.kb[0] = p[0];
+        R.kb[1] = p[TW];
+        R.kb8 = ((const float*)(p + 2 * TW))[0];  // .x of the third word
     }
 }
 template <int G, int P>
@@ -249,8 +287,13 @@ RIP_HD void stencil9(const f4* ring_m, const f4* ring_0, const f4* ring_p, int c
 
 // all slices of variant v in the reference's exact op order (fitting.py:225-251); cold
 template <int G>
-RIP_HD_COLD uint32_t jump_exact(const float (&d)[G], int v, float slope, float dvardt, float sig2read, const RampPlanDev& pl,
+struct Ramp {
+    float v[G];
+};
+template <int G>
+RIP_HD_COLD uint32_t jump_exact(const Ramp<G> rd, int v, float slope, float dvardt, float sig2read, const RampPlanDev& pl,
                                 const double* w_all) {
+    const float (&d)[G] = rd.v;
     const int ngrp = pl.var_ngrp[v], start = pl.start;
     const double thr_exact = jump_threshold(slope, pl);
     int s = pl.var_slice_off[v];
@@ -273,14 +316,18 @@ RIP_HD_COLD uint32_t jump_exact(const float (&d)[G], int v, float slope, float d
     return mask;
 }
 
-// jump_detect for one pixel, fast form (plan variant v, compile-time G).  Same decisions as
-// rip::jump_detect_pixel<.., FAST=true>; the sure-flag / sure-clear tests are done on squares.
-template <int G>
-RIP_HD FitResult jump_fast(const float (&d)[G], int v, float gain, float read, bool active, const RampPlanDev& pl,
+// jump_detect for one pixel, fast form (compile-time G).  FULL = plan variant 0 (the whole ramp: slice and weight
+// constants become immediate constant-bank operands); otherwise variant v (saturation-truncated refits, rare).
+// Same decisions as rip::jump_detect_pixel<.., FAST=true>; the sure-flag / sure-clear tests are done on squares.
+template <int G, int START>  // START = 0 / 1: full ramp with that first group (compile-time slice table); -1: variant v_in
+RIP_HD FitResult jump_fast(const float (&d)[G], int v_in, float gain, float read, bool active, const RampPlanDev& pl,
                            const double* w_all) {
+    static_assert(G >= 6, "slice indexing of the full-ramp specialisation assumes at least 6 groups");
+    constexpr bool FULL = START >= 0;
     FitResult r;
-    const int ngrp = pl.var_ngrp[v];
-    const int start = pl.start;
+    const int v = FULL ? 0 : v_in;
+    const int ngrp = FULL ? G : pl.var_ngrp[v];
+    const int start = FULL ? START : pl.start;
     float acc = 0.0f;
 #pragma unroll
     for (int t = 0; t < G; ++t)
@@ -293,16 +340,21 @@ RIP_HD FitResult jump_fast(const float (&d)[G], int v, float gain, float read, b
     r.jump_mask = 0u;
     if (!active) return r;
     const float sig2read = read * read;
-    int s = pl.var_slice_off[v];
     const float x = np_clip<float>(r.slope, pl.IthreshA_f, pl.IthreshB_f);
-    const float thr = (float)pl.SthreshA + (float)(pl.SthreshB - pl.SthreshA) * (logf(x / pl.IthreshA_f) / (float)pl.logIratio);
-    // sure-flag: delta > 0 and delta^2 > thr_hi^2 var; sure-clear: delta <= 0 (thr > 0) or delta^2 < thr_lo^2 var
-    const bool thr_pos = thr > 0.0f;
-    float hi = thr * (1.0f + pl.band), lo = thr * (1.0f - pl.band);
+#if defined(__CUDA_ARCH__)
+    const float thr = pl.thrA_f + pl.thrK_f * __logf(x * pl.invIA_f);  // approximate: the band absorbs ~1e-6
+#else
+    const float thr = pl.thrA_f + pl.thrK_f * logf(x * pl.invIA_f);
+#endif
+    // sure-flag: delta > 0 and delta^2 > thr_hi^2 var; sure-clear: delta <= 0 (thr > 0) or delta^2 < thr_lo^2 var.
+    // var = dvardt*A + read^2*B >= 0 (A, B >= 0 checked by build_plan); NaNs make every comparison false -> unsure.
+    const bool thr_ok = (thr > 0.0f) && (pl.band < 0.5f);
+    const float hi = thr * (1.0f + pl.band), lo = thr * (1.0f - pl.band);
     const float hi2 = hi * hi * (1.0f + 4.0e-7f), lo2 = lo * lo * (1.0f - 4.0e-7f);
     // every slice is classified without branching; pixels with any unsure slice redo all slices exactly (rare)
-    bool unsure = false;
+    bool unsure = !thr_ok;
     uint32_t mask = 0u;
+    int s = FULL ? 0 : pl.var_slice_off[v];
 #pragma unroll
     for (int i = 0; i < G - 1; ++i) {
         if (i >= start && i < ngrp - 1) {
@@ -310,22 +362,29 @@ RIP_HD FitResult jump_fast(const float (&d)[G], int v, float gain, float read, b
 #pragma unroll
             for (int di = 1; di <= 2; ++di) {
                 if (di <= dimax) {
-                    const RampSlice& sl = pl.slices[s];
+                    // FULL: slices are enumerated (i, di) with two per i except the last -> index (i-start)*2 + di-1
+                    const int si = FULL ? ((i - start) * 2 + (di - 1)) : s;
+                    const RampSlice& sl = pl.slices[si];
                     const float diff = d[(i + di < G) ? (i + di) : (G - 1)] - d[i];
                     const float var = dvardt * sl.A + sig2read * sl.B;
                     const float delta = diff * sl.inv_dt - r.slope;
                     const float l2 = delta * delta;
-                    const bool vpos = thr_pos && (var > 0.0f);
-                    const bool sure_set = vpos && (delta > 0.0f) && (l2 > hi2 * var);
-                    const bool sure_clr = vpos && ((delta <= 0.0f) || (l2 < lo2 * var));
+                    const bool pos = delta > 0.0f;
+                    const bool sure_set = pos && (l2 > hi2 * var);
+                    const bool sure_clr = (delta <= 0.0f) || (l2 < lo2 * var);
                     mask |= sure_set ? (1u << i) : 0u;
-                    unsure = unsure || !(sure_set || sure_clr);  // borderline, NaN, degenerate variance, exotic thresholds
+                    unsure = unsure || !(sure_set || sure_clr);  // borderline or NaN
                     ++s;
                 }
             }
         }
     }
-    if (unsure) mask = jump_exact<G>(d, v, r.slope, dvardt, sig2read, pl, w_all);
+    if (unsure) {
+        Ramp<G> rd;
+#pragma unroll
+        for (int t = 0; t < G; ++t) rd.v[t] = d[t];
+        mask = jump_exact<G>(rd, v, r.slope, dvardt, sig2read, pl, w_all);
+    }
     r.jump_mask = mask;
     return r;
 }
@@ -333,14 +392,15 @@ RIP_HD FitResult jump_fast(const float (&d)[G], int v, float gain, float read, b
 template <int G>
 RIP_HD FitResult ramp_fit_fast(const float (&d)[G], GroupFlags& gf, uint32_t& pdq, float gain, float read, bool active,
                                const RampPlanDev& pl, const double* w_all) {
-    FitResult r = jump_fast<G>(d, 0, gain, read, active, pl, w_all);
+    FitResult r = pl.start ? jump_fast<G, 1>(d, 0, gain, read, active, pl, w_all)
+                           : jump_fast<G, 0>(d, 0, gain, read, active, pl, w_all);
     const bool unsat = ((gf.sat >> (G - 1)) & 1u) == 0u;
     if (unsat) gf.jump |= r.jump_mask;
     if (gf.sat) {  // truncated refits only where some group is saturated
         for (int iend = G - 1; iend > 2 + pl.start; --iend) {
             const bool layer = ((gf.sat >> iend) & 1u) && !((gf.sat >> (iend - 1)) & 1u);
             if (layer) {
-                FitResult t = jump_fast<G>(d, G - iend, gain, read, active, pl, w_all);
+                FitResult t = jump_fast<G, -1>(d, G - iend, gain, read, active, pl, w_all);
                 r.slope = t.slope;
                 r.err_read = t.err_read;
                 r.err_poisson = t.err_poisson;
@@ -360,12 +420,39 @@ RIP_HD FitResult ramp_fit_fast(const float (&d)[G], GroupFlags& gf, uint32_t& pd
     return r;
 }
 
+// the extrapolating evaluation (some |z| > 1 or NaN): scalar, group by group, exactly as multilin_pixel of v1.  Cold:
+// arguments and results travel by value so that the caller's arrays stay in registers.
+template <int G, int P>
+struct ExtrapIn {
+    float z[G];
+    float c[P];
+};
+template <int G>
+struct ExtrapOut {
+    float phi[G];
+    uint32_t dq;
+};
+template <int G, int P>
+RIP_HD_COLD ExtrapOut<G> phi_extrap(const ExtrapIn<G, P> in, uint32_t satm, bool do_not_flag_first) {
+    ExtrapOut<G> o;
+    o.dq = 0u;
+    for (int g = 0; g < G; ++g) {
+        bool ex;
+        o.phi[g] = legendre_eval<float, P, true>(in.z[g], in.c, P, ex);
+        const bool first = (g == 0) && do_not_flag_first;
+        if (!first && ex && !((satm >> g) & 1u)) o.dq |= DQ_NO_LIN_CORR;
+    }
+    return o;
+}
+
 // ---- one march step --------------------------------------------------------------------------------------------
-// Stage rows as in v1: a0 row s, a1 row s-2, b row s-4, c row s-6.  After each stage the registers it consumed
-// are refilled with the inputs of the same stage for the next step.
+// Stage rows as in v1: a0 row s, a1 row s-2, b row s-4, c row s-6.  Input registers are filled a fraction of a step
+// ahead of their use and never all at once (register budget: 128 / thread for 4 resident CTAs per SM):
+//     [L1, Lb issued]  c-compute  [Lc for the next step]  b-compute  [L0]  a1-compute  a0-compute  barrier
+// f5 = s mod F_DEPTH, carried by the caller.
 template <int G, int P>
 RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& R, const int tid, const int tile,
-                 const int r0, const int r1, const int s) {
+                 const int r0, const int r1, const int s, const int f5) {
     constexpr int H = G / 4;
     constexpr int NQ1 = Regs<G, P>::NQ1;
     const int n = A.n, nb = 4, na = n - 8;
@@ -376,6 +463,10 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
     const uint32_t allg = (1u << G) - 1u;
     const bool xact = (x >= nb && x < n - nb);
 
+    raw_row_async<G>(A, sm, s + 2, RIP_SLOT5(2), tile, tid, r0 - 3, r1 + 3);
+    load_a1<G, P>(A, R, s - 2, tile, tid, r0 - 2, r1 + 2);
+    load_b<G, P>(A, R, s - 4, tile, tid, r0 - 1, r1 + 1);
+
     // ================= stage c : row s-6 =================
     {
         const int row = s - 6;
@@ -383,8 +474,9 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
         if (row >= r0 && row < r1 && out_col) {
             const long p = (long)row * n + x;
             const bool active = xact && (row >= nb && row < n - nb);
-            const uint32_t fl = sm.flg[mod_pos(row, F_DEPTH) * TW + tid];
-            const uint32_t nlc = sm.nlc[mod_pos(row, F_DEPTH) * TW + tid];
+            const int fslot = RIP_SLOT5(-6) * TW + tid;
+            const uint32_t fl = sm.flg[fslot];
+            const uint32_t nlc = sm.nlc[fslot];
             const float gval = R.kc[2].y, readv = R.kc[2].z, dsl = R.kc[2].w, flat = R.kc[3].x;
             const uint32_t sdq = f_as_u(R.kc[3].y);
             float d[G];
@@ -395,7 +487,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
                 const f4* om = sm.O1 + (size_t)((row - 1) & (O_DEPTH - 1)) * H * RW;
                 const f4* o0 = sm.O1 + (size_t)(row & (O_DEPTH - 1)) * H * RW;
                 const f4* op = sm.O1 + (size_t)((row + 1) & (O_DEPTH - 1)) * H * RW;
-                const f4* dd = sm.D + (size_t)(row & (D_DEPTH - 1)) * H * RW;
+                const f4* dd = sm.D + (size_t)RIP_SLOT5(-6) * H * RW;
                 f2 t[G / 2], q[G / 2];
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
@@ -461,10 +553,18 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
             A.err_poisson[p] = r.err_poisson;
             A.pdq[p] = pdq;
             if (A.endslice && active) {
+                // group where SATURATED first appears, minus one (gen_cal_image.py:703-708: the last 0->1 transition wins)
+                const uint32_t tr = gf.sat & ~(gf.sat << 1) & ~1u & allg;
                 int es = -1;
-#pragma unroll
-                for (int iend = 1; iend < G; ++iend)
-                    if (((gf.sat >> iend) & 1u) && !((gf.sat >> (iend - 1)) & 1u)) es = iend - 1;
+                if (tr) {
+#if defined(__CUDA_ARCH__)
+                    es = 30 - __clz((int)tr);
+#else
+                    int hb = 0;
+                    for (int g = 0; g < G; ++g) if ((tr >> g) & 1u) hb = g;
+                    es = hb - 1;
+#endif
+                }
                 A.endslice[(long)(row - nb) * na + (x - nb)] = (int8_t)es;
             }
             if (A.rdq) {
@@ -488,10 +588,10 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
         const bool rowok = row >= nb && row < n - nb && row >= r0 - 1 && row < r1 + 1;
         f4* o = sm.O1 + (size_t)(row & (O_DEPTH - 1)) * H * RW;
         if (rowok && tid >= 2 && tid <= TW - 3 && xact) {
-            const float k[9] = {R.kb[0].x, R.kb[0].y, R.kb[0].z, R.kb[0].w, R.kb[1].x, R.kb[1].y, R.kb[1].z, R.kb[1].w, R.kb[2].x};
-            const f4* dm = sm.D + (size_t)((row - 1) & (D_DEPTH - 1)) * H * RW;
-            const f4* d0 = sm.D + (size_t)(row & (D_DEPTH - 1)) * H * RW;
-            const f4* dp = sm.D + (size_t)((row + 1) & (D_DEPTH - 1)) * H * RW;
+            const float k[9] = {R.kb[0].x, R.kb[0].y, R.kb[0].z, R.kb[0].w, R.kb[1].x, R.kb[1].y, R.kb[1].z, R.kb[1].w, R.kb8};
+            const f4* dm = sm.D + (size_t)RIP_SLOT5(-5) * H * RW;
+            const f4* d0 = sm.D + (size_t)RIP_SLOT5(-4) * H * RW;
+            const f4* dp = sm.D + (size_t)RIP_SLOT5(-3) * H * RW;
 #pragma unroll
             for (int h = 0; h < H; ++h) {
                 f2 lo, hi;
@@ -505,15 +605,30 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
 #pragma unroll
             for (int h = 0; h < H; ++h) o[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
         }
-        load_b<G, P>(A, R, row + 1, tile, tid, r0 - 1, r1 + 1);
+    }
+
+    load_a0<G, P>(A, R, s, x, xin, r0 - 3, r1 + 3);
+    // row / channel corrections of the row stage a1 handles in the NEXT step (row s-1): fetched here, parked in
+    // shared memory at the end of the step (parity (s-1)&1)
+    double corr_next = 0.0;
+    const bool corr_thread = A.do_refpix && tid < 3 * G && (s - 1) >= 0 && (s - 1) < n;
+    if (corr_thread) {
+        const int rown = s - 1, g = tid % G, which = tid / G;
+        if (which == 0) {
+            corr_next = A.rowcorr[(long)g * n + rown];
+        } else {
+            int ch = ((tile * TS) >> 7) + (which - 1);
+            if (ch > 31) ch = 31;
+            corr_next = A.chan_m[g * 32 + ch] * (double)rown + A.chan_c[g * 32 + ch];
+        }
     }
 
     // ================= stage a1 : row s-2 (flags, refpix, bias, multilin, D) =================
     {
         const int row = s - 2;
         const bool rowin = row >= 0 && row < n && row >= r0 - 2 && row < r1 + 2;
-        f4* dst = sm.D + (size_t)(row & (D_DEPTH - 1)) * H * RW;
-        const int fslot = mod_pos(row, F_DEPTH) * TW + tid;
+        f4* dst = sm.D + (size_t)RIP_SLOT5(-2) * H * RW;
+        const int fslot = RIP_SLOT5(-2) * TW + tid;
         if (rowin && (tid >= 1 || tile == 0) && tid <= TW - 2 && xin) {
             uint32_t grown = 0u;
 #pragma unroll
@@ -524,17 +639,17 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
             const uint32_t own = sm.sat[(size_t)(row & (S_DEPTH - 1)) * RW + col];
             grown &= 0xffffu;
             uint32_t satm = grown;
-            for (int b = 1; b <= A.sat_backup; ++b) satm |= grown >> b;
+            if (grown) {
+                for (int b = 1; b <= A.sat_backup; ++b) satm |= grown >> b;
+            }
             satm &= allg & ~1u;
             const uint32_t adf = own >> 16;
             const bool active = xact && (row >= nb && row < n - nb);
-            // raw values of this row were converted by stage a0 two steps ago and parked in the D ring slot of
-            // this row (overwritten below)
             float S[G];
+            {
+                const uint16_t* rq = sm.rawq + (size_t)RIP_SLOT5(-2) * G * TW + tid;
 #pragma unroll
-            for (int h = 0; h < H; ++h) {
-                const f4 v = dst[h * RW + col];
-                S[4 * h] = v.x; S[4 * h + 1] = v.y; S[4 * h + 2] = v.z; S[4 * h + 3] = v.w;
+                for (int g = 0; g < G; ++g) S[g] = u16_to_f32(rq[g * TW]);
             }
             if (A.do_refpix) {  // gen_cal_image.py:535-556: f64 subtractions, f32 stores
                 const int chsel = ((x >> 7) != ((tile * TS) >> 7)) ? 1 : 0;
@@ -594,24 +709,23 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
 #pragma unroll
                     for (int j = 0; j < G / 2; ++j) {
                         phi2[j] = add2(phi2[j], mul2(bc(c[L]), cur[j]));
-                        const f2 nxt = sub2(mul2(mul2(bc(a), z2[j]), cur[j]), mul2(bc(b), prev[j]));
-                        prev[j] = cur[j];
-                        cur[j] = nxt;
+                        if (L + 1 < P) {  // the recursion value of the last order is never used
+                            const f2 nxt = sub2(mul2(mul2(bc(a), z2[j]), cur[j]), mul2(bc(b), prev[j]));
+                            prev[j] = cur[j];
+                            cur[j] = nxt;
+                        }
                     }
                 }
             } else {
-                float cc[P];
+                ExtrapIn<G, P> ein;
 #pragma unroll
-                for (int L = 0; L < P; ++L) cc[L] = c[L];
+                for (int j = 0; j < G / 2; ++j) { ein.z[2 * j] = z2[j].x; ein.z[2 * j + 1] = z2[j].y; }
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const float z = (g & 1) ? z2[g >> 1].y : z2[g >> 1].x;
-                    bool ex;
-                    const float ph = legendre_eval<float, P, true>(z, cc, P, ex);
-                    if (g & 1) phi2[g >> 1].y = ph; else phi2[g >> 1].x = ph;
-                    const bool first = (g == 0) && A.do_not_flag_first;
-                    if (!first && ex && !((satm >> g) & 1u)) dq |= DQ_NO_LIN_CORR;
-                }
+                for (int L = 0; L < P; ++L) ein.c[L] = c[L];
+                const ExtrapOut<G> eo = phi_extrap<G, P>(ein, satm, A.do_not_flag_first != 0);
+#pragma unroll
+                for (int j = 0; j < G / 2; ++j) phi2[j] = f2{eo.phi[2 * j], eo.phi[2 * j + 1]};
+                dq |= eo.dq;
             }
             if (aux & 1u) {  // lin dq has NO_LIN_CORR | REFERENCE_PIXEL: S - Sref instead (ipc_linearity.py:334-336)
 #pragma unroll
@@ -640,64 +754,59 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
             sm.flg[fslot] = 0u;
             sm.nlc[fslot] = 0;
         }
-        load_a1<G, P>(A, R, row + 1, tile, tid, r0 - 2, r1 + 2);
     }
 
-    // ================= stage a0 : row s (raw -> saturation bits; converted raw parked in the D slot) ===========
+    // ================= stage a0 : row s (raw -> cumulative saturation / A-D floor bits) ===========
     {
         const int row = s;
         uint32_t bits = 0u;
         const bool rowin = row >= 0 && row < n && row >= r0 - 3 && row < r1 + 3;
         if (rowin && xin) {
-            f4* dst = sm.D + (size_t)(row & (D_DEPTH - 1)) * H * RW;
+            const uint16_t* rq = sm.rawq + (size_t)RIP_SLOT5(0) * G * TW + tid;
             const float thr = R.thr;
-            bool cum = false;
-            float fv[G];
+            uint32_t rv[G];
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                fv[g] = u16_to_f32(R.raw[g]);
-                if (g >= 1) {  // saturation_check skips the first resultant (gen_cal_image.py:174-180)
-                    cum = cum || (fv[g] >= thr);
+            for (int g = 0; g < G; ++g) rv[g] = rq[g * TW];
+            // fast exit: no group (>= 1; saturation_check skips the first resultant, gen_cal_image.py:174-180) reaches
+            // the threshold or the A/D floor
+            uint32_t mx = rv[1], mn = rv[1];
+#pragma unroll
+            for (int g = 2; g < G; ++g) { mx = mx > rv[g] ? mx : rv[g]; mn = mn < rv[g] ? mn : rv[g]; }
+            if (!(u16_to_f32(mx) < thr) || mn == 0u) {  // (NaN thresholds were replaced by +inf when the CALDIR was loaded)
+                bool cum = false;
+#pragma unroll
+                for (int g = 1; g < G; ++g) {
+                    const float fv = u16_to_f32(rv[g]);
+                    cum = cum || (fv >= thr);
                     if (cum) bits |= 1u << g;
-                    if (fv[g] <= 0.0f) bits |= 1u << (16 + g);
+                    if (fv <= 0.0f) bits |= 1u << (16 + g);
                 }
             }
-#pragma unroll
-            for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{fv[4 * h], fv[4 * h + 1], fv[4 * h + 2], fv[4 * h + 3]};
         }
         sm.sat[(size_t)(row & (S_DEPTH - 1)) * RW + col] = bits;
-        // row / channel corrections of the row stage a1 handles in the NEXT step (row s-1): parity (s-1)&1
-        if (A.do_refpix && tid < 3 * G) {
-            const int rown = s - 1;
-            if (rown >= 0 && rown < n) {
-                const int g = tid % G, which = tid / G;
-                if (which == 0) {
-                    sm.rc[(size_t)(rown & 1) * G + g] = A.rowcorr[(long)g * n + rown];
-                } else {
-                    int ch = ((tile * TS) >> 7) + (which - 1);
-                    if (ch > 31) ch = 31;
-                    sm.ln[(size_t)((rown & 1) * 2 + (which - 1)) * G + g] = A.chan_m[g * 32 + ch] * (double)rown + A.chan_c[g * 32 + ch];
-                }
-            }
+        if (corr_thread) {
+            const int rown = s - 1, g = tid % G, which = tid / G;
+            if (which == 0) sm.rc[(size_t)(rown & 1) * G + g] = corr_next;
+            else sm.ln[(size_t)((rown & 1) * 2 + (which - 1)) * G + g] = corr_next;
         }
-        load_a0<G, P>(A, R, row + 1, x, xin, r0 - 3, r1 + 3);
     }
+    cp_async_wait<1>();  // the raw row issued in the previous step (row s+1) has landed; the caller's barrier publishes it
 }
 
-// prologue: inputs of the first step s0 (rows s0, s0-2, s0-4, s0-6 -- only the first can be inside the frame, the
-// others are loaded for uniformity: rows < 0 are skipped by the loaders)
+// prologue: raw rows of the first two steps, the registers stage c needs in the first step, and the ring pads
 template <int G, int P>
 RIP_HD void prologue(const Args& A, Smem<G>& sm, Regs<G, P>& R, int tid, int tile, int r0, int r1) {
     const int x = tile * TS + tid;
     const bool xin = x < A.n;
     const int s0 = r0 - 3;
+    const int f5 = mod_pos(s0, F_DEPTH);
+    raw_row_async<G>(A, sm, s0, RIP_SLOT5(0), tile, tid, r0 - 3, r1 + 3);
+    raw_row_async<G>(A, sm, s0 + 1, RIP_SLOT5(1), tile, tid, r0 - 3, r1 + 3);
     load_c<G, P>(A, R, s0 - 6, tile, tid, x, xin, r0, r1);
-    load_b<G, P>(A, R, s0 - 4, tile, tid, r0 - 1, r1 + 1);
-    load_a1<G, P>(A, R, s0 - 2, tile, tid, r0 - 2, r1 + 2);
-    load_a0<G, P>(A, R, s0, x, xin, r0 - 3, r1 + 3);
     // ring pads and the slots stage a1 / b read before anything was written there
     for (int i = tid; i < S_DEPTH * RW; i += TW) sm.sat[i] = 0u;
     for (int i = tid; i < (D_DEPTH + O_DEPTH) * Smem<G>::H * RW; i += TW) sm.D[i] = f4{0.f, 0.f, 0.f, 0.f};
+    cp_async_wait<0>();
 }
 
 // ---- packed calibration records (built once per CALDIR and group count) -------------------------------------

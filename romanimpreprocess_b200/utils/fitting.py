@@ -129,6 +129,9 @@ def build_plan(meta, exclude_first=True, band=DEFAULT_BAND):
     plan.SthreshA, plan.SthreshB = SthreshA, SthreshB
     plan.logIratio = float(np.log(IthreshB / IthreshA))
     plan.band = band
+    plan.thrA_f = SthreshA
+    plan.thrK_f = (SthreshB - SthreshA) / plan.logIratio
+    plan.invIA_f = 1.0 / IthreshA
     variants = [G] + list(range(G - 1, 2 + start, -1))  # full ramp, then iend = G-1 ... start+3
     if len(variants) > _lib.RIP_MAXVAR:
         raise ValueError("too many truncation variants")
@@ -147,6 +150,8 @@ def build_plan(meta, exclude_first=True, band=DEFAULT_BAND):
             if off >= _lib.RIP_MAXSLICE:
                 raise ValueError("too many jump-detection slices for the plan")
             s = plan.slices[off]
+            if not (A >= 0.0 and B >= 0.0):  # cannot happen for a valid read pattern; keeps the squared test sound
+                plan.band = float("inf")
             s.i, s.di, s.dt, s.inv_dt, s.A, s.B = i, di, dt, 1.0 / float(dt), A, B
             row = np.zeros(_lib.RIP_GMAX)
             row[:ngrp] = w

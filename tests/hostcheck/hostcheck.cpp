@@ -97,7 +97,7 @@ static void run_v2_t(rip::v2::Args A, const rip::v2::PackSrc& S, const rip_ramp_
             const int r0 = by * A.band_rows, r1 = (r0 + A.band_rows < n) ? r0 + A.band_rows : n;
             for (int tid = 0; tid < TW; ++tid) prologue<G, P>(A, sm, regs[tid], tid, tile, r0, r1);
             for (int s = r0 - 3; s <= r1 + 5; ++s)
-                for (int tid = 0; tid < TW; ++tid) step<G, P>(A, pl, sm, regs[tid], tid, tile, r0, r1, s);
+                for (int tid = 0; tid < TW; ++tid) step<G, P>(A, pl, sm, regs[tid], tid, tile, r0, r1, s, mod_pos(s, rip::v2::F_DEPTH));
         }
 }
 
