@@ -314,24 +314,40 @@ def run_ours(args):
              "err_poisson": _lib.pinned_empty((n, n), np.float32), "pdq": _lib.pinned_empty((n, n), np.uint32),
              "endslice": _lib.pinned_empty((na, na), np.int8)}  # fmt: skip
 
-    def e2e_step(i):
-        d, a = h_in[i % n_exp]
-        gci.calibrate_arrays(cd, d, a, rp, synth.FRAME_TIME, h_area, cfg, do_refpix=True, want_endslice=True,
-                             threads=args.threads, band_rows=args.band_rows, out=h_out, dplan=dplan)  # fmt: skip
+    # one set of pinned output buffers per slot in flight
+    depth = 3
+    h_outs = [h_out] + [{k: _lib.pinned_empty(v.shape, v.dtype) for k, v in h_out.items()} for _ in range(depth - 1)]
+    pipe = gci.Pipeline(cd, rp, synth.FRAME_TIME, cfg, do_refpix=True, depth=depth, want_endslice=True)
+    e2e_steps = max(6, min(args.steps, 20))
 
-    e2e_steps = max(3, min(args.steps, 10))
-    for i in range(2):
-        e2e_step(i)
+    def e2e_run(count, first):
+        tickets = []
+        for i in range(count):
+            if len(tickets) >= depth:
+                pipe.result(tickets.pop(0))  # the slot's host buffers are about to be reused
+            d, a = h_in[(first + i) % n_exp]
+            tickets.append(pipe.submit(d, a, h_area, out=h_outs[(first + i) % depth]))
+        for t in tickets:
+            pipe.result(t)
+
+    e2e_run(3, 0)
     barrier()
     te0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(2 + i)
+    e2e_run(e2e_steps, 3)
     torch.cuda.synchronize()
     te = time.perf_counter() - te0
     temax = torch.tensor([te], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(temax, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_steps / float(temax.item())
+    # the synchronous single-call API for comparison (not the headline)
+    ts0 = time.perf_counter()
+    for i in range(3):
+        d, a = h_in[i % n_exp]
+        gci.calibrate_arrays(cd, d, a, rp, synth.FRAME_TIME, h_area, cfg, do_refpix=True, want_endslice=True, out=h_out,
+                             dplan=dplan)  # fmt: skip
+    e2e_sync = world * 3 / (time.perf_counter() - ts0)
+    pipe.close()
     h2d = int(exposures[0][0].nbytes + exposures[0][1].nbytes + area.nbytes)
     d2h = int(sum(v.nbytes for v in h_out.values() if isinstance(v, np.ndarray)))
     checksum = int(h_out["pdq"].astype(np.uint64).sum() % (1 << 32))
@@ -366,7 +382,10 @@ def run_ours(args):
                          "kernel_ms": fused_avg_ms, "algorithmic_bytes": algo_bytes,
                          "step_share": fused_ms.value / ms_total},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "gen_cal_image.calibrate_arrays -> rip_l1_to_l2_host (pinned host buffers)",
+                    "steps": e2e_steps,
+                    "api": f"gen_cal_image.Pipeline.submit/result -> rip_pipeline_* (pinned host buffers, {depth} exposures in "
+                           "flight: H2D | kernels | D2H on three streams)",
+                    "sync_api_value": e2e_sync,
                     "pdq_checksum": checksum},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -322,6 +322,99 @@ def calibrate_device(cal, dplan, d_raw, d_amp33, d_area, d_slope, d_err_read, d_
     )  # fmt: skip
 
 
+class Pipeline:
+    """
+    A stream of exposures of one SCA through the GPU with the PCIe copies overlapped (``rip_pipeline_*``): ``depth``
+    exposures are in flight on three CUDA streams (host->device | reference-pixel statistics + fused kernel |
+    device->host).  Same arithmetic as ``calibrate_arrays``.
+
+    >>> pipe = Pipeline(cal, read_pattern, frame_time, config)            # doctest: +SKIP
+    >>> tickets = [pipe.submit(data, amp33, area) for data, amp33, area in exposures]
+    >>> results = [pipe.result(t) for t in tickets]
+
+    For real overlap the host arrays must be page-locked (``_lib.pinned_empty``); input arrays must not be modified
+    until ``result()`` of their ticket has returned.
+    """
+
+    def __init__(self, cal, read_pattern, frame_time, config=None, do_refpix=True, depth=3, want_rdq=False,
+                 want_endslice=None, area_dtype=np.float32):  # fmt: skip
+        config = config or {}
+        self.cal, self.config, self.do_refpix = cal, config, do_refpix
+        self.want_rdq = bool(want_rdq)
+        self.want_endslice = bool(config.get("SLICEOUT", False)) if want_endslice is None else bool(want_endslice)
+        self.dplan = DevicePlan(cal, read_pattern, frame_time, config, do_refpix, area_dtype)
+        self.G = int(self.dplan.meta["ngrp"])
+        if self.G >= 128 and config.get("SLICEOUT", False):
+            raise ValueError("too many groups")  # gen_cal_image.py:699-700
+        self._p = C.c_void_p()
+        _lib.check(_lib.lib().rip_pipeline_create(cal.handle, self.G, int(depth), int(self.want_endslice),
+                                                  int(self.want_rdq), C.byref(self._p)))  # fmt: skip
+        self._pending = {}
+
+    def submit(self, data, amp33, area_factor=None, out=None):
+        """Queue one exposure; returns a ticket.  ``out``: optional dict of preallocated (pinned) output arrays."""
+        cal, n, G = self.cal, self.cal.n, self.G
+        d = _lib.as_c(data, np.uint16)
+        if d.shape != (G, n, n):
+            raise ValueError(f"expected a ({G},{n},{n}) uint16 cube, got {d.shape}")
+        a33 = None
+        if self.do_refpix:
+            if amp33 is None:
+                raise ValueError("the reference-pixel correction needs the amp33 cube")
+            a33 = _lib.as_c(amp33, np.uint16)
+        area = None if area_factor is None else _lib.as_float_plane(area_factor)
+        prm = _lib.L1L2Params()
+        C.memmove(C.byref(prm), C.byref(self.dplan.prm), C.sizeof(prm))
+        prm.area_dtype = _lib.RIP_F32 if area is None else _lib.float_tag(area)
+        out = {} if out is None else out
+
+        def buf(key, shape, dtype):
+            a = out.get(key)
+            if a is None or a.shape != shape or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+                a = out[key] = np.empty(shape, dtype)
+            return a
+
+        o = _lib.L2Out()
+        o.slope = buf("slope", (n, n), np.float32).ctypes.data
+        o.err_read = buf("err_read", (n, n), np.float32).ctypes.data
+        o.err_poisson = buf("err_poisson", (n, n), np.float32).ctypes.data
+        o.pdq = buf("pdq", (n, n), np.uint32).ctypes.data
+        if self.want_endslice:
+            o.endslice = buf("endslice", (cal.na, cal.na), np.int8).ctypes.data
+        if self.want_rdq:
+            o.rdq = buf("rdq", (G, n, n), np.uint8).ctypes.data
+        t = C.c_long(-1)
+        _lib.check(_lib.lib().rip_pipeline_submit(self._p, _lib.ptr(d), _lib.ptr(a33), _lib.ptr(area), C.byref(prm),
+                                                  C.byref(self.dplan.plan), _lib.ptr(self.dplan.w_exact), C.byref(o),
+                                                  C.byref(t)))  # fmt: skip
+        out["meta"] = self.dplan.meta
+        self._pending[t.value] = (out, d, a33, area)  # keep the buffers alive until the copies are done
+        return t.value
+
+    def result(self, ticket):
+        """Block until the exposure of ``ticket`` is complete; returns its output dict."""
+        _lib.check(_lib.lib().rip_pipeline_wait(self._p, C.c_long(ticket)))
+        return self._pending.pop(ticket)[0]
+
+    def close(self):
+        if self._p:
+            _lib.lib().rip_pipeline_destroy(self._p)
+            self._p = C.c_void_p()
+            self._pending.clear()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 _CAL_CACHE = {}
 
 
@@ -372,5 +465,5 @@ def calibrateimage(config, verbose=True, device=0):
     return _ref._package_l2(config, out, thewcs) if hasattr(_ref, "_package_l2") else out
 
 
-__all__ = ["CalDir", "DevicePlan", "calibrate_arrays", "calibrate_device", "calibrateimage", "exposure_meta",
+__all__ = ["CalDir", "DevicePlan", "Pipeline", "calibrate_arrays", "calibrate_device", "calibrateimage", "exposure_meta",
            "ramp_setup", "pixel"]  # fmt: skip

@@ -167,17 +167,24 @@ struct Regs {
     f4 kc[KQ];         // stage c,  row s-6
     float area32;
     double area64;
+    // running per-thread pointers (advanced by one detector row per step): no per-load address arithmetic
+    const f4* p1;            // rec1 at row s-2
+    const f4* pk;            // recK at row s-6 (stage b reads two rows further down)
+    const float* pthr;       // thr  at (row s, x)
+    const uint16_t* praw;    // raw group (tid>>4) at (row s+2, x0 + 8 (tid&15))   [cp.async source]
+    const char* parea;       // area at (row s-6, x)
+    long pout;               // output pixel index of (row s-6, x)
 };
 
 RIP_HD int mod_pos(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 RIP_HD int wrap5(int a) { return a >= F_DEPTH ? a - F_DEPTH : a; }  // a in [0, 2*F_DEPTH)
 // slot of row s+DK in a depth-5 ring, given f5 = s mod 5 (DK is a compile-time constant)
-#define RIP_SLOT5(DK) wrap5(f5 + ((((DK) % 5) + 5) % 5))
+#define RIP_SLOT5(DK) sl5[(((DK) % 5) + 5) % 5]
 
 // ---- loads -------------------------------------------------------------------------------------------------
 template <int G, int P>
-RIP_HD void load_a0(const Args& A, Regs<G, P>& R, int row, int x, bool xin, int lo, int hi) {
-    if (row >= 0 && row < A.n && row >= lo && row < hi && xin) R.thr = A.thr[(long)row * A.n + x];
+RIP_HD void load_a0(const Args& A, Regs<G, P>& R, int row, bool xin, int lo, int hi) {
+    if (row >= 0 && row < A.n && row >= lo && row < hi && xin) R.thr = R.pthr[0];
 }
 
 // 16-byte asynchronous global -> shared copy (LDGSTS); the host build copies at once
@@ -203,48 +210,67 @@ RIP_HD void cp_async_wait() {
 
 // raw resultants of one row of the tile -> ring slot: G x 128 columns x u16 = G x 16 chunks of 16 bytes, one (G = 8) or
 // two (G = 16) per thread.  Every thread commits a group each step (possibly empty) so that wait_group counts steps.
-template <int G>
-RIP_HD void raw_row_async(const Args& A, Smem<G>& sm, int row, int slot, int tile, int tid, int lo, int hi) {
+template <int G, int P>
+RIP_HD void raw_row_async(const Args& A, Smem<G>& sm, const Regs<G, P>& R, int row, int row_off, int slot, int tile, int tid,
+                          int lo, int hi) {  // row_off: rows relative to R.praw (which points at row s+2)
     if (row >= 0 && row < A.n && row >= lo && row < hi) {
         const long npl = (long)A.n * A.n;
-        const int x0 = tile * TS;
+        const int c = tid & 15, g0 = tid >> 4;
+        if (tile * TS + 8 * c + 8 <= A.n) {
 #pragma unroll
-        for (int k = 0; k < (G * 16 + TW - 1) / TW; ++k) {
-            const int idx = tid + k * TW, g = idx >> 4, c = idx & 15;
-            if (g < G && x0 + 8 * c + 8 <= A.n)
-                cp_async16(sm.rawq + ((size_t)slot * G + g) * TW + 8 * c, A.raw + (long)g * npl + (long)row * A.n + x0 + 8 * c);
+            for (int k = 0; k < G / 8; ++k)
+                cp_async16(sm.rawq + ((size_t)slot * G + g0 + 8 * k) * TW + 8 * c, R.praw + (long)(8 * k) * npl + (long)row_off * A.n);
         }
     }
     cp_async_commit();
 }
 template <int G, int P>
-RIP_HD void load_a1(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int lo, int hi) {
+RIP_HD void load_a1(const Args& A, Regs<G, P>& R, int row, int lo, int hi) {
     if (row >= 0 && row < A.n && row >= lo && row < hi) {
-        const f4* p = A.rec1 + ((long)row * A.ntile + tile) * (Regs<G, P>::NQ1 * TW) + tid;
 #pragma unroll
-        for (int q = 0; q < Regs<G, P>::NQ1; ++q) R.r1[q] = p[q * TW];
+        for (int q = 0; q < Regs<G, P>::NQ1; ++q) R.r1[q] = R.p1[q * TW];
     }
 }
 template <int G, int P>
-RIP_HD void load_b(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int lo, int hi) {
+RIP_HD void load_b(const Args& A, Regs<G, P>& R, int row, int lo, int hi) {
     if (row >= 0 && row < A.n && row >= lo && row < hi) {
-        const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW) + tid;
+        const f4* p = R.pk + 2 * (long)A.ntile * (KQ * TW);  // two rows below stage c's row
         R.kb[0] = p[0];
         R.kb[1] = p[TW];
         R.kb8 = ((const float*)(p + 2 * TW))[0];  // .x of the third word
     }
 }
 template <int G, int P>
-RIP_HD void load_c(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int x, bool xin, int lo, int hi) {
+RIP_HD void load_c(const Args& A, Regs<G, P>& R, int row, int ahead, bool xin, int lo, int hi) {  // ahead: rows below R.pk's row
     if (row >= 0 && row < A.n && row >= lo && row < hi) {
-        const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW) + tid;
+        const f4* p = R.pk + ahead * (long)A.ntile * (KQ * TW);
 #pragma unroll
         for (int q = 0; q < KQ; ++q) R.kc[q] = p[q * TW];
         if (A.area && xin) {
-            if (A.area_dtype == RIP_F64) R.area64 = ((const double*)A.area)[(long)row * A.n + x];
-            else R.area32 = ((const float*)A.area)[(long)row * A.n + x];
+            if (A.area_dtype == RIP_F64) R.area64 = ((const double*)R.parea)[ahead * (long)A.n];
+            else R.area32 = ((const float*)R.parea)[ahead * (long)A.n];
         }
     }
+}
+// pointers for march step s (rows may be outside the frame: the pointers are then never dereferenced)
+template <int G, int P>
+RIP_HD void init_pointers(const Args& A, Regs<G, P>& R, int tid, int tile, int s) {
+    const int x = tile * TS + tid;
+    R.p1 = A.rec1 + ((long)(s - 2) * A.ntile + tile) * (Regs<G, P>::NQ1 * TW) + tid;
+    R.pk = A.recK + ((long)(s - 6) * A.ntile + tile) * (KQ * TW) + tid;
+    R.pthr = A.thr + (long)s * A.n + x;
+    R.praw = A.raw + (long)(tid >> 4) * ((long)A.n * A.n) + (long)(s + 2) * A.n + tile * TS + 8 * (tid & 15);
+    R.pout = (long)(s - 6) * A.n + x;
+    R.parea = (const char*)A.area + R.pout * (A.area_dtype == RIP_F64 ? 8 : 4);
+}
+template <int G, int P>
+RIP_HD void advance_pointers(const Args& A, Regs<G, P>& R) {
+    R.p1 += (long)A.ntile * (Regs<G, P>::NQ1 * TW);
+    R.pk += (long)A.ntile * (KQ * TW);
+    R.pthr += A.n;
+    R.praw += A.n;
+    R.pout += A.n;
+    R.parea += (long)A.n * (A.area_dtype == RIP_F64 ? 8 : 4);
 }
 
 RIP_HD float f4_get(const f4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
@@ -463,16 +489,17 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
     const uint32_t allg = (1u << G) - 1u;
     const bool xact = (x >= nb && x < n - nb);
 
-    raw_row_async<G>(A, sm, s + 2, RIP_SLOT5(2), tile, tid, r0 - 3, r1 + 3);
-    load_a1<G, P>(A, R, s - 2, tile, tid, r0 - 2, r1 + 2);
-    load_b<G, P>(A, R, s - 4, tile, tid, r0 - 1, r1 + 1);
+    // slots of rows s, s+1, .. s+4 (== s-5 .. s-1) in the depth-5 rings
+    const int sl5[5] = {f5, wrap5(f5 + 1), wrap5(f5 + 2), wrap5(f5 + 3), wrap5(f5 + 4)};
+    raw_row_async<G, P>(A, sm, R, s + 2, 0, RIP_SLOT5(2), tile, tid, r0 - 3, r1 + 3);
+    load_b<G, P>(A, R, s - 4, r0 - 1, r1 + 1);
 
     // ================= stage c : row s-6 =================
     {
         const int row = s - 6;
         const bool out_col = (tid >= 4 || tile == 0) && tid < TW - 4 && xin;
         if (row >= r0 && row < r1 && out_col) {
-            const long p = (long)row * n + x;
+            const long p = R.pout;
             const bool active = xact && (row >= nb && row < n - nb);
             const int fslot = RIP_SLOT5(-6) * TW + tid;
             const uint32_t fl = sm.flg[fslot];
@@ -579,7 +606,8 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
                 }
             }
         }
-        load_c<G, P>(A, R, row + 1, tile, tid, x, xin, r0, r1);
+        load_c<G, P>(A, R, row + 1, 1, xin, r0, r1);
+        load_a1<G, P>(A, R, s - 2, r0 - 2, r1 + 2);
     }
 
     // ================= stage b : row s-4 (IPC pass 1) =================
@@ -607,7 +635,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
         }
     }
 
-    load_a0<G, P>(A, R, s, x, xin, r0 - 3, r1 + 3);
+    load_a0<G, P>(A, R, s, xin, r0 - 3, r1 + 3);
     // row / channel corrections of the row stage a1 handles in the NEXT step (row s-1): fetched here, parked in
     // shared memory at the end of the step (parity (s-1)&1)
     double corr_next = 0.0;
@@ -790,19 +818,21 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
             else sm.ln[(size_t)((rown & 1) * 2 + (which - 1)) * G + g] = corr_next;
         }
     }
+    advance_pointers<G, P>(A, R);
     cp_async_wait<1>();  // the raw row issued in the previous step (row s+1) has landed; the caller's barrier publishes it
 }
 
-// prologue: raw rows of the first two steps, the registers stage c needs in the first step, and the ring pads
+// prologue: pointers, raw rows of the first two steps, the registers stage c needs in the first step, ring pads
 template <int G, int P>
 RIP_HD void prologue(const Args& A, Smem<G>& sm, Regs<G, P>& R, int tid, int tile, int r0, int r1) {
     const int x = tile * TS + tid;
     const bool xin = x < A.n;
     const int s0 = r0 - 3;
     const int f5 = mod_pos(s0, F_DEPTH);
-    raw_row_async<G>(A, sm, s0, RIP_SLOT5(0), tile, tid, r0 - 3, r1 + 3);
-    raw_row_async<G>(A, sm, s0 + 1, RIP_SLOT5(1), tile, tid, r0 - 3, r1 + 3);
-    load_c<G, P>(A, R, s0 - 6, tile, tid, x, xin, r0, r1);
+    init_pointers<G, P>(A, R, tid, tile, s0);
+    raw_row_async<G, P>(A, sm, R, s0, -2, f5, tile, tid, r0 - 3, r1 + 3);
+    raw_row_async<G, P>(A, sm, R, s0 + 1, -1, wrap5(f5 + 1), tile, tid, r0 - 3, r1 + 3);
+    load_c<G, P>(A, R, s0 - 6, 0, xin, r0, r1);
     // ring pads and the slots stage a1 / b read before anything was written there
     for (int i = tid; i < S_DEPTH * RW; i += TW) sm.sat[i] = 0u;
     for (int i = tid; i < (D_DEPTH + O_DEPTH) * Smem<G>::H * RW; i += TW) sm.D[i] = f4{0.f, 0.f, 0.f, 0.f};

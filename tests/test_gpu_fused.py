@@ -162,3 +162,36 @@ def test_full_size_band_and_tiling_invariance(full_case):
     with gci.CalDir(cal) as cd:
         sp = cd.static_products()
     band_check(out, cal, data_u16, amp33_u16, rp, area, sp["flat"], sp["dark_slope_ipc"])
+
+
+def test_pipeline_matches_synchronous_path():
+    """rip_pipeline_* (three streams, exposures in flight) gives the same arrays as rip_l1_to_l2_host, in order, also
+    when more exposures are queued than there are slots."""
+    from romanimpreprocess_b200 import _lib, synth
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+
+    n, rp = 256, synth.README_PATTERN
+    cal = synth.make_caldir(n=n, seed=51, read_pattern=rp, p_order=10, gain_dtype=np.float32, ipc_dtype=np.float32,
+                            sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
+    exposures = [synth.make_l1(cal, rp, seed=60 + k, n_sources=25, cr_frac=0.01, bright=3.0)[:2] for k in range(5)]
+    area = synth.make_area_factor(n, np.float32)
+    cfg = {"SLICEOUT": True}
+    with gci.CalDir(cal) as cd:
+        ref = [gci.calibrate_arrays(cd, d, a, rp, 3.04, area, cfg, want_rdq=True) for d, a in exposures]
+        with gci.Pipeline(cd, rp, 3.04, cfg, depth=2, want_rdq=True) as pipe:
+            pinned = []
+            for d, a in exposures:
+                pd, pa = _lib.pinned_empty(d.shape, np.uint16), _lib.pinned_empty(a.shape, np.uint16)
+                pd[...] = d
+                pa[...] = a
+                pinned.append((pd, pa))
+            tickets = [pipe.submit(pd, pa, area) for pd, pa in pinned]
+            outs = [pipe.result(t) for t in tickets]
+            with pytest.raises(_lib.RipError, match="unknown ticket"):
+                pipe.result(99)
+    for o, r in zip(outs, ref):
+        for k in ("slope", "err_read", "err_poisson"):
+            assert np.array_equal(o[k], r[k], equal_nan=True), k
+        for k in ("pdq", "rdq", "endslice"):
+            assert np.array_equal(o[k], r[k]), k
+    assert not np.array_equal(outs[0]["slope"], outs[1]["slope"])

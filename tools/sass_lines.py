@@ -64,3 +64,24 @@ for key, n in inst.most_common(60):
     st = " ".join(f"{k}:{v}" for k, v in stall[key].most_common(3))
     text = src.get(key[1], "") if annot and key[0] == annot.split("/")[-1] else ""
     print(f"{key[0]:>18}:{key[1]:<4} inst {100 * n / tot:5.1f}%  smp {100 * smp[key] / max(tots, 1):5.1f}%  [{st}]  {text.strip()[:90]}")
+
+# optional: aggregate by named line ranges of the annotated file:  RANGES="name:lo-hi,name:lo-hi"
+import os
+if os.environ.get("RANGES") and annot:
+    base_name = annot.split("/")[-1]
+    agg = collections.Counter()
+    for spec in os.environ["RANGES"].split(","):
+        name, r = spec.split(":")
+        lo, hi = map(int, r.split("-"))
+        for (f, l), n in inst.items():
+            if f == base_name and lo <= l <= hi:
+                agg[name] += n
+    other = collections.Counter()
+    for (f, l), n in inst.items():
+        if f != base_name:
+            other[f] += n
+    print("--- by range (thread-instructions per 4096^2 pixel) ---")
+    for name, n in agg.most_common():
+        print(f"{name:>14} {100 * n / tot:5.1f}%  {n * 32 / 4096**2:7.1f}")
+    for f, n in other.most_common(6):
+        print(f"{f:>14} {100 * n / tot:5.1f}%  {n * 32 / 4096**2:7.1f}")
