@@ -49,107 +49,143 @@ __device__ __forceinline__ float key2f(uint32_t k) {
 }
 
 
-__global__ void k0_init_kernel(SelState* st, int G, uint32_t M) {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= G) return;
-    st[g].prefix[0] = st[g].prefix[1] = 0u;
-    st[g].rank[0] = M / 2 - 1;  // M is even: np.median averages the two middle elements
-    st[g].rank[1] = M / 2;
+// ---- radix select of the two middle order statistics of e = f32(amp33) - med over the whole reference-output frame:
+// 3 histogram passes over order-preserving keys (11 + 11 + 10 bits).  The block that finishes a pass last (ticket
+// counter) also locates the buckets of the two ranks, extends their prefixes and clears the histogram, so a pass
+// is ONE launch; pass 0 is fused into the per-row sorting kernel below.
+
+// executed by all 256 threads of one block; hist = this group's [2][2048] counters
+__device__ void k0_scan_block(uint32_t* __restrict__ hist, SelState* __restrict__ st, int pass, uint32_t M, uint32_t* sh /*[256]*/) {
+    const int tid = threadIdx.x;
+    const int nbits = (pass == 2) ? 10 : 11, nbin = 1 << nbits;
+    for (int r = 0; r < 2; ++r) {
+        const uint32_t* h = hist + ((pass == 0) ? 0 : r * 2048);  // pass 0: both ranks share the (empty) prefix
+        uint32_t loc[8], sum = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int bin = tid * 8 + k;
+            loc[k] = (bin < nbin) ? __ldcg(h + bin) : 0u;
+            sum += loc[k];
+        }
+        sh[tid] = sum;
+        __syncthreads();
+        for (int off = 1; off < 256; off <<= 1) {  // Hillis-Steele inclusive scan
+            const uint32_t v = (tid >= off) ? sh[tid - off] : 0u;
+            __syncthreads();
+            sh[tid] += v;
+            __syncthreads();
+        }
+        uint32_t before = sh[tid] - sum;
+        const uint32_t rank = (pass == 0) ? (M / 2 - 1 + r) : st->rank[r];  // M even: np.median averages the two middle values
+        const uint32_t prefix = (pass == 0) ? 0u : st->prefix[r];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (rank >= before && rank < before + loc[k]) {
+                st->prefix[r] = (prefix << nbits) | (uint32_t)(tid * 8 + k);
+                st->rank[r] = rank - before;
+            }
+            before += loc[k];
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < 4096; i += 256) hist[i] = 0u;
 }
 
-// radix-select histogram pass over e = f32(amp33) - med, key bits [shift, shift+nbits); elements must match
-// the already-known high bits (prefix) of each of the two order statistics.
-__global__ void k0_hist_kernel(const uint16_t* __restrict__ amp33, const float* __restrict__ med, long M, int pass,
-                               const SelState* __restrict__ st, uint32_t* __restrict__ hist /*[G][2][2048]*/) {
+// flush a block's shared histogram to the group's global one; the last block of the group runs the scan
+__device__ void k0_flush_and_scan(uint32_t* sh_hist /*[2][2048]*/, int nhist, uint32_t* __restrict__ ghist, SelState* __restrict__ st,
+                                  uint32_t* __restrict__ ticket, int nblocks, int pass, uint32_t M) {
+    __shared__ uint32_t scan_sh[256];
+    __shared__ int is_last;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nhist * 2048; i += blockDim.x) {
+        const uint32_t v = sh_hist[i];
+        if (v) atomicAdd(&ghist[i], v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == (uint32_t)nblocks - 1u);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        k0_scan_block(ghist, st, pass, M, scan_sh);
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+
+// passes 1 and 2: elements must match the already-known high bits (prefix) of each of the two order statistics
+__global__ void __launch_bounds__(256) k0_hist_kernel(const uint16_t* __restrict__ amp33, const float* __restrict__ med, long M,
+                                                      int pass, SelState* __restrict__ st, uint32_t* __restrict__ hist /*[G][2][2048]*/,
+                                                      uint32_t* __restrict__ ticket /*[G]*/) {
     __shared__ uint32_t sh[2][2048];
     const int g = blockIdx.y;
     for (int i = threadIdx.x; i < 4096; i += blockDim.x) (&sh[0][0])[i] = 0u;
     __syncthreads();
     const SelState s = st[g];
-    const int shift_hi = (pass == 0) ? 32 : (pass == 1 ? 21 : 10);
-    const int shift = (pass == 0) ? 21 : (pass == 1 ? 10 : 0);
+    const int shift_hi = (pass == 1) ? 21 : 10;
+    const int shift = (pass == 1) ? 10 : 0;
     const uint32_t mask = (pass == 2) ? 1023u : 2047u;
     const uint16_t* a = amp33 + (long)g * M;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long)gridDim.x * blockDim.x) {
         const float e = (float)a[i] - med[i];
         const uint32_t k = f2key(e);
-        const uint32_t hi = (shift_hi >= 32) ? 0u : (k >> shift_hi);
+        const uint32_t hi = k >> shift_hi;
         const uint32_t b = (k >> shift) & mask;
         if (hi == s.prefix[0]) atomicAdd(&sh[0][b], 1u);
         if (hi == s.prefix[1]) atomicAdd(&sh[1][b], 1u);
     }
-    __syncthreads();
-    uint32_t* h = hist + (long)g * 4096;
-    for (int i = threadIdx.x; i < 4096; i += blockDim.x) {
-        const uint32_t v = (&sh[0][0])[i];
-        if (v) atomicAdd(&h[i], v);
-    }
+    k0_flush_and_scan(&sh[0][0], 2, hist + (long)g * 4096, st + g, ticket + g, gridDim.x, pass, (uint32_t)M);
 }
 
-// find the bucket holding each rank; extend the prefixes; clear the histogram for the next pass
-__global__ void k0_scan_kernel(uint32_t* __restrict__ hist, SelState* __restrict__ st, int pass) {
-    __shared__ uint32_t cum[2048];
-    const int g = blockIdx.x;
-    const int nbits = (pass == 2) ? 10 : 11;
-    const int nbin = 1 << nbits;
-    for (int r = 0; r < 2; ++r) {
-        uint32_t* h = hist + (long)g * 4096 + r * 2048;
-        for (int i = threadIdx.x; i < 2048; i += blockDim.x) cum[i] = (i < nbin) ? h[i] : 0u;
-        __syncthreads();
-        for (int off = 1; off < 2048; off <<= 1) {  // Hillis-Steele inclusive scan
-            uint32_t v[2];
-            int k = 0;
-            for (int i = threadIdx.x; i < 2048; i += blockDim.x) v[k++] = (i >= off) ? cum[i - off] : 0u;
-            __syncthreads();
-            k = 0;
-            for (int i = threadIdx.x; i < 2048; i += blockDim.x) cum[i] += v[k++];
-            __syncthreads();
-        }
-        const uint32_t rank = st[g].rank[r];
-        __syncthreads();
-        for (int i = threadIdx.x; i < nbin; i += blockDim.x) {
-            const uint32_t before = i ? cum[i - 1] : 0u;
-            if (rank >= before && rank < cum[i]) {
-                st[g].prefix[r] = (st[g].prefix[r] << nbits) | (uint32_t)i;
-                st[g].rank[r] = rank - before;
-            }
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < 2048; i += blockDim.x) h[i] = 0u;
-        __syncthreads();
-    }
-}
-
-// the two middle order statistics (ranks 63, 64) of the 128 reference-output pixels of every row
-__global__ void k0_rowmid_kernel(const uint16_t* __restrict__ amp33, const float* __restrict__ med, int n,
-                                 float* __restrict__ rowA, float* __restrict__ rowB) {
-    __shared__ float sv[8][128];
+// One warp per row of the reference output: bitonic sort of its 128 values e = f32(amp33) - med (4 per lane, element
+// index i = 32 k + lane) -> the two middle order statistics (ranks 63, 64); plus pass 0 of the global radix select.
+__global__ void __launch_bounds__(256) k0_rows_kernel(const uint16_t* __restrict__ amp33, const float* __restrict__ med, int n,
+                                                      float* __restrict__ rowA, float* __restrict__ rowB, SelState* __restrict__ st,
+                                                      uint32_t* __restrict__ hist, uint32_t* __restrict__ ticket) {
+    __shared__ uint32_t sh[2048];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + w, g = blockIdx.y;
-    if (row >= n) return;
-    const uint16_t* a = amp33 + ((long)g * n + row) * 128;
-    const float* m = med + (long)row * 128;
-    float e[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        e[k] = (float)a[lane + 32 * k] - m[lane + 32 * k];
-        sv[w][lane + 32 * k] = e[k];
-    }
-    __syncwarp();
-    int rk[4] = {0, 0, 0, 0};
-    for (int j = 0; j < 128; ++j) {
-        const float o = sv[w][j];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh[i] = 0u;
+    __syncthreads();
+    if (row < n) {
+        const uint16_t* a = amp33 + ((long)g * n + row) * 128;
+        const float* m = med + (long)row * 128;
+        float v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int idx = lane + 32 * k;
-            rk[k] += (o < e[k] || (o == e[k] && j < idx)) ? 1 : 0;
+            v[k] = (float)a[lane + 32 * k] - m[lane + 32 * k];
+            atomicAdd(&sh[f2key(v[k]) >> 21], 1u);
         }
-    }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (rk[k] == 63) rowA[(long)g * n + row] = e[k];
-        if (rk[k] == 64) rowB[(long)g * n + row] = e[k];
+        for (int k2 = 2; k2 <= 128; k2 <<= 1) {
+#pragma unroll
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                if (j >= 32) {  // partner in the same lane: registers k and k ^ (j / 32)
+                    const int dk = j >> 5;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if ((k & dk) == 0) {
+                            const bool up = (((k * 32) & k2) == 0);  // (i & k2) with i = 32 k + lane, k2 >= 64 here
+                            const float lo = fminf(v[k], v[k | dk]), hi = fmaxf(v[k], v[k | dk]);
+                            v[k] = up ? lo : hi;
+                            v[k | dk] = up ? hi : lo;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float o = __shfl_xor_sync(0xffffffffu, v[k], j);
+                        const bool lower = (lane & j) == 0;
+                        const bool up = (((k * 32 + lane) & k2) == 0);
+                        v[k] = (lower == up) ? fminf(v[k], o) : fmaxf(v[k], o);
+                    }
+                }
+            }
+        }
+        if (lane == 31) rowA[(long)g * n + row] = v[1];  // rank 63 = 32*1 + 31
+        if (lane == 0) rowB[(long)g * n + row] = v[2];   // rank 64 = 32*2 + 0
     }
+    k0_flush_and_scan(sh, 1, hist + (long)g * 4096, st + g, ticket + g, gridDim.x, 0, (uint32_t)n * 128u);
 }
 
 __device__ __forceinline__ void bitonic_sort_block(float* v, int npow2) {
@@ -247,6 +283,9 @@ static void run_k0(rip_caldir* h, const uint16_t* d_raw, const uint16_t* d_amp33
     if (h->hist.n < (size_t)G * 4096) {
         h->hist.alloc((size_t)RIP_GMAX * 4096);
         h->sel.alloc(RIP_GMAX);
+        h->k0_ticket.alloc(RIP_GMAX);
+        h->k0_ticket.zero(st);
+        h->hist.zero(st);  // (histograms and tickets are left zeroed by every pass)
         h->rowA.alloc((size_t)RIP_GMAX * n);
         h->rowB.alloc((size_t)RIP_GMAX * n);
         h->gmed.alloc(RIP_GMAX);
@@ -254,14 +293,11 @@ static void run_k0(rip_caldir* h, const uint16_t* d_raw, const uint16_t* d_amp33
         h->chan_m.alloc((size_t)RIP_GMAX * 32);
         h->chan_c.alloc((size_t)RIP_GMAX * 32);
     }
-    h->hist.zero(st);
-    RIP_LAUNCH(k0_init_kernel, 1, 32, 0, st, h->sel.p, G, (uint32_t)M);
-    RIP_LAUNCH(k0_rowmid_kernel, dim3((n + 7) / 8, G), 256, 0, st, d_amp33, h->amp_med.p, n, h->rowA.p, h->rowB.p);
+    RIP_LAUNCH(k0_rows_kernel, dim3((n + 7) / 8, G), 256, 0, st, d_amp33, h->amp_med.p, n, h->rowA.p, h->rowB.p, h->sel.p,
+               h->hist.p, h->k0_ticket.p);
     const int nblk = (int)std::min<long>(64, (M + 4095) / 4096);
-    for (int pass = 0; pass < 3; ++pass) {
-        RIP_LAUNCH(k0_hist_kernel, dim3(nblk, G), 256, 0, st, d_amp33, h->amp_med.p, M, pass, h->sel.p, h->hist.p);
-        RIP_LAUNCH(k0_scan_kernel, G, 1024, 0, st, h->hist.p, h->sel.p, pass);
-    }
+    for (int pass = 1; pass < 3; ++pass)
+        RIP_LAUNCH(k0_hist_kernel, dim3(nblk, G), 256, 0, st, d_amp33, h->amp_med.p, M, pass, h->sel.p, h->hist.p, h->k0_ticket.p);
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
     RIP_LAUNCH(k0_final_kernel, G, 1024, (size_t)2 * np2 * sizeof(float), st, h->sel.p, h->rowA.p, h->rowB.p, n, np2,

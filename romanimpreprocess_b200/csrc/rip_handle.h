@@ -27,7 +27,7 @@ struct rip_caldir {
     DevBuf<float> v2_rec1, v2_recK;
     int v2_G = 0;
     // K0 workspace
-    DevBuf<uint32_t> hist;
+    DevBuf<uint32_t> hist, k0_ticket;
     DevBuf<SelState> sel;
     DevBuf<float> rowA, rowB, gmed;
     DevBuf<double> rowcorr, chan_m, chan_c;

@@ -167,13 +167,11 @@ struct Regs {
     f4 kc[KQ];         // stage c,  row s-6
     float area32;
     double area64;
-    // running per-thread pointers (advanced by one detector row per step): no per-load address arithmetic
-    const f4* p1;            // rec1 at row s-2
-    const f4* pk;            // recK at row s-6 (stage b reads two rows further down)
-    const float* pthr;       // thr  at (row s, x)
-    const uint16_t* praw;    // raw group (tid>>4) at (row s+2, x0 + 8 (tid&15))   [cp.async source]
-    const char* parea;       // area at (row s-6, x)
-    long pout;               // output pixel index of (row s-6, x)
+    // running CTA-uniform element offsets (advanced by one detector row per step; they depend only on blockIdx and
+    // the step, so they live in uniform registers): the per-thread part of every address is just tid / x
+    long o1;     // rec1 record of (row s-2, tile), in f4 units
+    long ok;     // recK record of (row s-6, tile), in f4 units
+    long orow;   // s * n  (pixel offset of detector row s)
 };
 
 RIP_HD int mod_pos(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
@@ -183,8 +181,10 @@ RIP_HD int wrap5(int a) { return a >= F_DEPTH ? a - F_DEPTH : a; }  // a in [0, 
 
 // ---- loads -------------------------------------------------------------------------------------------------
 template <int G, int P>
-RIP_HD void load_a0(const Args& A, Regs<G, P>& R, int row, bool xin, int lo, int hi) {
-    if (row >= 0 && row < A.n && row >= lo && row < hi && xin) R.thr = R.pthr[0];
+RIP_HD void load_a0(const Args& A, Regs<G, P>& R, int row, int x, bool xin, int lo, int hi) {
+    // (every loader assigns in both branches: otherwise the old register contents stay live around the whole loop)
+    if (row >= 0 && row < A.n && row >= lo && row < hi && xin) R.thr = (A.thr + R.orow)[x];
+    else R.thr = 0.0f;
 }
 
 // 16-byte asynchronous global -> shared copy (LDGSTS); the host build copies at once
@@ -212,65 +212,79 @@ RIP_HD void cp_async_wait() {
 // two (G = 16) per thread.  Every thread commits a group each step (possibly empty) so that wait_group counts steps.
 template <int G, int P>
 RIP_HD void raw_row_async(const Args& A, Smem<G>& sm, const Regs<G, P>& R, int row, int row_off, int slot, int tile, int tid,
-                          int lo, int hi) {  // row_off: rows relative to R.praw (which points at row s+2)
+                          int lo, int hi) {  // row_off: rows relative to row s (R.orow)
     if (row >= 0 && row < A.n && row >= lo && row < hi) {
         const long npl = (long)A.n * A.n;
         const int c = tid & 15, g0 = tid >> 4;
         if (tile * TS + 8 * c + 8 <= A.n) {
+            const uint16_t* src = A.raw + (R.orow + (long)row_off * A.n + tile * TS);  // uniform
+            const int toff = g0 * (int)npl + 8 * c;                                     // per thread (< 2^31 for n <= 4096, G <= 16)
 #pragma unroll
             for (int k = 0; k < G / 8; ++k)
-                cp_async16(sm.rawq + ((size_t)slot * G + g0 + 8 * k) * TW + 8 * c, R.praw + (long)(8 * k) * npl + (long)row_off * A.n);
+                cp_async16(sm.rawq + ((size_t)slot * G + g0 + 8 * k) * TW + 8 * c, src + (long)(8 * k) * npl + toff);
         }
     }
     cp_async_commit();
 }
 template <int G, int P>
-RIP_HD void load_a1(const Args& A, Regs<G, P>& R, int row, int lo, int hi) {
+RIP_HD void load_a1(const Args& A, Regs<G, P>& R, int row, int tid, int lo, int hi, int part) {
+    // part 0: dark + bias words (first G/2 float4), part 1: the rest (Smin .. coefficients)
     if (row >= 0 && row < A.n && row >= lo && row < hi) {
+        const f4* p = A.rec1 + R.o1;
 #pragma unroll
-        for (int q = 0; q < Regs<G, P>::NQ1; ++q) R.r1[q] = R.p1[q * TW];
+        for (int q = 0; q < Regs<G, P>::NQ1; ++q)
+            if ((q < G / 2) == (part == 0)) R.r1[q] = p[q * TW + tid];
+    } else {
+#pragma unroll
+        for (int q = 0; q < Regs<G, P>::NQ1; ++q)
+            if ((q < G / 2) == (part == 0)) R.r1[q] = f4{0.f, 0.f, 0.f, 0.f};
     }
 }
 template <int G, int P>
-RIP_HD void load_b(const Args& A, Regs<G, P>& R, int row, int lo, int hi) {
+RIP_HD void load_b(const Args& A, Regs<G, P>& R, int row, int tid, int lo, int hi) {
     if (row >= 0 && row < A.n && row >= lo && row < hi) {
-        const f4* p = R.pk + 2 * (long)A.ntile * (KQ * TW);  // two rows below stage c's row
-        R.kb[0] = p[0];
-        R.kb[1] = p[TW];
-        R.kb8 = ((const float*)(p + 2 * TW))[0];  // .x of the third word
+        const f4* p = A.recK + (R.ok + 2 * (long)A.ntile * (KQ * TW));  // two rows below stage c's row
+        R.kb[0] = p[tid];
+        R.kb[1] = p[TW + tid];
+        R.kb8 = ((const float*)(p + 2 * TW))[4 * tid];  // .x of the third word
+    } else {
+        R.kb[0] = R.kb[1] = f4{0.f, 0.f, 0.f, 0.f};
+        R.kb8 = 0.0f;
     }
 }
 template <int G, int P>
-RIP_HD void load_c(const Args& A, Regs<G, P>& R, int row, int ahead, bool xin, int lo, int hi) {  // ahead: rows below R.pk's row
+RIP_HD void load_c(const Args& A, Regs<G, P>& R, int row, int ahead, int tid, int x, bool xin, int lo, int hi) {  // ahead: rows below R.ok's row
     if (row >= 0 && row < A.n && row >= lo && row < hi) {
-        const f4* p = R.pk + ahead * (long)A.ntile * (KQ * TW);
+        const f4* p = A.recK + (R.ok + ahead * (long)A.ntile * (KQ * TW));
 #pragma unroll
-        for (int q = 0; q < KQ; ++q) R.kc[q] = p[q * TW];
+        for (int q = 0; q < KQ; ++q) R.kc[q] = p[q * TW + tid];
         if (A.area && xin) {
-            if (A.area_dtype == RIP_F64) R.area64 = ((const double*)R.parea)[ahead * (long)A.n];
-            else R.area32 = ((const float*)R.parea)[ahead * (long)A.n];
+            const long o = R.orow + (long)(ahead - 6) * A.n;  // row s-6+ahead
+            if (A.area_dtype == RIP_F64) R.area64 = ((const double*)A.area + o)[x];
+            else R.area32 = ((const float*)A.area + o)[x];
+        } else {
+            R.area64 = 1.0;
+            R.area32 = 1.0f;
         }
+    } else {
+#pragma unroll
+        for (int q = 0; q < KQ; ++q) R.kc[q] = f4{0.f, 0.f, 0.f, 0.f};
+        R.area64 = 1.0;
+        R.area32 = 1.0f;
     }
 }
-// pointers for march step s (rows may be outside the frame: the pointers are then never dereferenced)
+// offsets for march step s (rows may be outside the frame: the addresses are then never dereferenced)
 template <int G, int P>
-RIP_HD void init_pointers(const Args& A, Regs<G, P>& R, int tid, int tile, int s) {
-    const int x = tile * TS + tid;
-    R.p1 = A.rec1 + ((long)(s - 2) * A.ntile + tile) * (Regs<G, P>::NQ1 * TW) + tid;
-    R.pk = A.recK + ((long)(s - 6) * A.ntile + tile) * (KQ * TW) + tid;
-    R.pthr = A.thr + (long)s * A.n + x;
-    R.praw = A.raw + (long)(tid >> 4) * ((long)A.n * A.n) + (long)(s + 2) * A.n + tile * TS + 8 * (tid & 15);
-    R.pout = (long)(s - 6) * A.n + x;
-    R.parea = (const char*)A.area + R.pout * (A.area_dtype == RIP_F64 ? 8 : 4);
+RIP_HD void init_pointers(const Args& A, Regs<G, P>& R, int tile, int s) {
+    R.o1 = ((long)(s - 2) * A.ntile + tile) * (Regs<G, P>::NQ1 * TW);
+    R.ok = ((long)(s - 6) * A.ntile + tile) * (KQ * TW);
+    R.orow = (long)s * A.n;
 }
 template <int G, int P>
 RIP_HD void advance_pointers(const Args& A, Regs<G, P>& R) {
-    R.p1 += (long)A.ntile * (Regs<G, P>::NQ1 * TW);
-    R.pk += (long)A.ntile * (KQ * TW);
-    R.pthr += A.n;
-    R.praw += A.n;
-    R.pout += A.n;
-    R.parea += (long)A.n * (A.area_dtype == RIP_F64 ? 8 : 4);
+    R.o1 += (long)A.ntile * (Regs<G, P>::NQ1 * TW);
+    R.ok += (long)A.ntile * (KQ * TW);
+    R.orow += A.n;
 }
 
 RIP_HD float f4_get(const f4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
@@ -491,15 +505,16 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
 
     // slots of rows s, s+1, .. s+4 (== s-5 .. s-1) in the depth-5 rings
     const int sl5[5] = {f5, wrap5(f5 + 1), wrap5(f5 + 2), wrap5(f5 + 3), wrap5(f5 + 4)};
-    raw_row_async<G, P>(A, sm, R, s + 2, 0, RIP_SLOT5(2), tile, tid, r0 - 3, r1 + 3);
-    load_b<G, P>(A, R, s - 4, r0 - 1, r1 + 1);
+    raw_row_async<G, P>(A, sm, R, s + 2, 2, RIP_SLOT5(2), tile, tid, r0 - 3, r1 + 3);
+    load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 0);
+    load_b<G, P>(A, R, s - 4, tid, r0 - 1, r1 + 1);
 
     // ================= stage c : row s-6 =================
     {
         const int row = s - 6;
         const bool out_col = (tid >= 4 || tile == 0) && tid < TW - 4 && xin;
         if (row >= r0 && row < r1 && out_col) {
-            const long p = R.pout;
+            const long p = R.orow - 6 * (long)n + x;
             const bool active = xact && (row >= nb && row < n - nb);
             const int fslot = RIP_SLOT5(-6) * TW + tid;
             const uint32_t fl = sm.flg[fslot];
@@ -606,8 +621,8 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
                 }
             }
         }
-        load_c<G, P>(A, R, row + 1, 1, xin, r0, r1);
-        load_a1<G, P>(A, R, s - 2, r0 - 2, r1 + 2);
+        load_c<G, P>(A, R, row + 1, 1, tid, x, xin, r0, r1);
+        load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 1);
     }
 
     // ================= stage b : row s-4 (IPC pass 1) =================
@@ -635,7 +650,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
         }
     }
 
-    load_a0<G, P>(A, R, s, xin, r0 - 3, r1 + 3);
+    load_a0<G, P>(A, R, s, x, xin, r0 - 3, r1 + 3);
     // row / channel corrections of the row stage a1 handles in the NEXT step (row s-1): fetched here, parked in
     // shared memory at the end of the step (parity (s-1)&1)
     double corr_next = 0.0;
@@ -829,10 +844,10 @@ RIP_HD void prologue(const Args& A, Smem<G>& sm, Regs<G, P>& R, int tid, int til
     const bool xin = x < A.n;
     const int s0 = r0 - 3;
     const int f5 = mod_pos(s0, F_DEPTH);
-    init_pointers<G, P>(A, R, tid, tile, s0);
-    raw_row_async<G, P>(A, sm, R, s0, -2, f5, tile, tid, r0 - 3, r1 + 3);
-    raw_row_async<G, P>(A, sm, R, s0 + 1, -1, wrap5(f5 + 1), tile, tid, r0 - 3, r1 + 3);
-    load_c<G, P>(A, R, s0 - 6, 0, xin, r0, r1);
+    init_pointers<G, P>(A, R, tile, s0);
+    raw_row_async<G, P>(A, sm, R, s0, 0, f5, tile, tid, r0 - 3, r1 + 3);
+    raw_row_async<G, P>(A, sm, R, s0 + 1, 1, wrap5(f5 + 1), tile, tid, r0 - 3, r1 + 3);
+    load_c<G, P>(A, R, s0 - 6, 0, tid, x, xin, r0, r1);
     // ring pads and the slots stage a1 / b read before anything was written there
     for (int i = tid; i < S_DEPTH * RW; i += TW) sm.sat[i] = 0u;
     for (int i = tid; i < (D_DEPTH + O_DEPTH) * Smem<G>::H * RW; i += TW) sm.D[i] = f4{0.f, 0.f, 0.f, 0.f};
