@@ -513,7 +513,9 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
     {
         const int row = s - 6;
         const bool out_col = (tid >= 4 || tile == 0) && tid < TW - 4 && xin;
-        if (row >= r0 && row < r1 && out_col) {
+        const bool c_on = row >= r0 && row < r1 && out_col;
+        if (!c_on) load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 1);  // (otherwise issued below, before the ramp fit)
+        if (c_on) {
             const long p = R.orow - 6 * (long)n + x;
             const bool active = xact && (row >= nb && row < n - nb);
             const int fslot = RIP_SLOT5(-6) * TW + tid;
@@ -561,6 +563,8 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
 #pragma unroll
                 for (int g = 0; g < G; ++g) d[g] = 0.0f;  // unused: every output of a non-active pixel is flag-only
             }
+            // second half of stage a1's record: the IPC taps of this stage are dead now, the ramp fit hides the latency
+            load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 1);
             GroupFlags gf;
             gf.sat = fl & 0xffffu;
             gf.adf = fl >> 16;
@@ -622,7 +626,6 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
             }
         }
         load_c<G, P>(A, R, row + 1, 1, tid, x, xin, r0, r1);
-        load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 1);
     }
 
     // ================= stage b : row s-4 (IPC pass 1) =================
