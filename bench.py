@@ -52,57 +52,90 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region: an NVML polling thread (every
+    ~2 ms; the timed region of a default run is tens of ms, too short for `nvidia-smi -lms`), nvidia-smi as fallback."""
 
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")  # fmt: skip
 
-    def __init__(self, index):
-        self.rows = []
+    def __init__(self, index, uuid=None):
+        self.samples = []  # (t, sm_mhz, reason bits)
+        self.smax = None
+        self.stop_flag = False
+        self.mode = None
         self.proc = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:  # noqa: BLE001
-            self.proc = None
+            import pynvml
 
-    def _read(self):
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                for cand in (uuid, "GPU-" + uuid):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand if isinstance(cand, bytes) else cand.encode())
+                        break
+                    except Exception:  # noqa: BLE001
+                        h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+                pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                             int(get_reasons(h))))  # fmt: skip
+                    except Exception:  # noqa: BLE001
+                        pass
+                    time.sleep(0.002)
+
+            self.t = threading.Thread(target=poll, daemon=True)
+            self.t.start()
+            self.mode = "nvml"
+        except Exception:  # noqa: BLE001
+            try:
+                self.proc = subprocess.Popen(
+                    ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)],
+                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
+                self.t = threading.Thread(target=self._read_smi, daemon=True)
+                self.t.start()
+                self.mode = "nvidia-smi"
+            except Exception:  # noqa: BLE001
+                self.mode = None
+
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
+            f = [x.strip() for x in line.split(",")]
+            try:
+                clk, self.smax = float(f[0]), float(f[1])
+            except (ValueError, IndexError):
+                continue
+            bits = 0
+            for bit, v in zip((0x8, 0x40, 0x20, 0x4), f[3:7]):
+                if v.lower().startswith("active"):
+                    bits |= bit
+            self.samples.append((time.perf_counter(), clk, bits))
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        for t, line in self.rows:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                clk, mx = float(f[0]), float(f[1])
-            except ValueError:
-                continue
-            smax = mx
-            if t0 - 0.05 <= t <= t1 + 0.05:
-                sm.append(clk)
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        if not sm:  # region shorter than the sampling period: use everything
-            for _, line in self.rows:
-                f = [x.strip() for x in line.split(",")]
-                try:
-                    sm.append(float(f[0]))
-                except (ValueError, IndexError):
-                    pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}  # fmt: skip
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        time.sleep(0.03)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        inside = [(c, b) for t, c, b in self.samples if t0 <= t <= t1]
+        if not inside:  # region shorter than one sampling period: nearest samples around it
+            inside = [(c, b) for t, c, b in self.samples if t0 - 0.05 <= t <= t1 + 0.05]
+        bits = 0
+        for _, b in inside:
+            bits |= b
+        reasons = sorted(name for bit, name in self.REASONS.items() if bits & bit)
+        return {"sm_mhz": float(np.median([c for c, _ in inside])) if inside else None, "sm_max_mhz": self.smax,
+                "reasons": reasons, "samples": len(inside), "source": self.mode}  # fmt: skip
 
 
 def make_inputs(n, read_pattern, n_exposures, seed=1000):
@@ -267,7 +300,11 @@ def run_ours(args):
     for i in range(args.warmup):
         step(i)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:  # noqa: BLE001
+        uuid = None
+    sampler = ClockSampler(local, uuid) if rank == 0 else None
     _lib.check(lib.rip_profile_enable(cd.handle, 1))
     l0 = lib.rip_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -51,10 +51,12 @@ __global__ void __launch_bounds__(TW, MINB) cal_fused_v2_kernel(const Args A, in
     const int tid = threadIdx.x;
     const int nband = (A.n + A.band_rows - 1) / A.band_rows;
     const int total = nband * A.ntile;
-    for (;;) {
-        if (tid == 0) s_item = atomicAdd(counter, 1);
-        __syncthreads();
-        const int item = s_item;
+    for (int it = 0;; ++it) {
+        if (counter) {
+            if (tid == 0) s_item = atomicAdd(counter, 1);
+            __syncthreads();
+        }
+        const int item = counter ? s_item : (it == 0 ? (int)blockIdx.x : total);  // no counter: one item per CTA
         if (item >= total) break;
         const int tile = item % A.ntile;  // neighbouring items = neighbouring column tiles of one band (halo reuse in L2)
         const int r0 = (item / A.ntile) * A.band_rows;
@@ -87,9 +89,13 @@ static void launch_tb(const Args& A, int* counter, cudaStream_t st) {
         RIP_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     const int total = A.ntile * ((A.n + A.band_rows - 1) / A.band_rows);
-    const int grid = std::min(total, sm_count * MINB);
-    RIP_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
-    RIP_LAUNCH(kern, grid, TW, smem, st, A, counter);
+    static const bool persist = [] { const char* e = getenv("RIP_V2_PERSIST"); return !(e && atoi(e) == 0); }();
+    if (persist) {
+        RIP_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+        RIP_LAUNCH(kern, std::min(total, sm_count * MINB), TW, smem, st, A, counter);
+    } else {
+        RIP_LAUNCH(kern, total, TW, smem, st, A, (int*)nullptr);
+    }
 }
 
 // resident CTAs per SM the kernel is compiled for: 4 (128 registers/thread) for G <= 8, 3 for G = 16 (larger rings);

@@ -25,6 +25,13 @@
 #pragma once
 #include "rip_math.cuh"
 
+#ifndef RIP_V2_SCHED
+#define RIP_V2_SCHED 0  // stage order within a march step: 0 = c, b, a1, a0;  1 = c, a1, b, a0
+#endif
+#ifndef RIP_V2_EARLY_L1
+#define RIP_V2_EARLY_L1 0  // 1: issue the second half of stage a1's record before the ramp fit instead of after stage c
+#endif
+
 namespace rip {
 namespace v2 {
 
@@ -506,15 +513,20 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
     // slots of rows s, s+1, .. s+4 (== s-5 .. s-1) in the depth-5 rings
     const int sl5[5] = {f5, wrap5(f5 + 1), wrap5(f5 + 2), wrap5(f5 + 3), wrap5(f5 + 4)};
     raw_row_async<G, P>(A, sm, R, s + 2, 2, RIP_SLOT5(2), tile, tid, r0 - 3, r1 + 3);
+#if RIP_V2_SCHED == 0
     load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 0);
     load_b<G, P>(A, R, s - 4, tid, r0 - 1, r1 + 1);
+#else  // stage order c, a1, b, a0: the whole a1 record is in flight during stage c, the taps of stage b during stage a1
+    load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 0);
+    load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 1);
+#endif
 
     // ================= stage c : row s-6 =================
     {
         const int row = s - 6;
         const bool out_col = (tid >= 4 || tile == 0) && tid < TW - 4 && xin;
         const bool c_on = row >= r0 && row < r1 && out_col;
-        if (!c_on) load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 1);  // (otherwise issued below, before the ramp fit)
+        if (RIP_V2_EARLY_L1 && !c_on) load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 1);  // (otherwise issued below, before the ramp fit)
         if (c_on) {
             const long p = R.orow - 6 * (long)n + x;
             const bool active = xact && (row >= nb && row < n - nb);
@@ -564,7 +576,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
                 for (int g = 0; g < G; ++g) d[g] = 0.0f;  // unused: every output of a non-active pixel is flag-only
             }
             // second half of stage a1's record: the IPC taps of this stage are dead now, the ramp fit hides the latency
-            load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 1);
+            if (RIP_V2_EARLY_L1) load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 1);
             GroupFlags gf;
             gf.sat = fl & 0xffffu;
             gf.adf = fl >> 16;
@@ -626,8 +638,14 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
             }
         }
         load_c<G, P>(A, R, row + 1, 1, tid, x, xin, r0, r1);
+#if RIP_V2_SCHED == 0
+        if (!RIP_V2_EARLY_L1) load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 1);
+#else
+        load_b<G, P>(A, R, s - 4, tid, r0 - 1, r1 + 1);
+#endif
     }
 
+#if RIP_V2_SCHED == 0
     // ================= stage b : row s-4 (IPC pass 1) =================
     {
         const int row = s - 4;
@@ -802,6 +820,182 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
         }
     }
 
+#else
+    load_a0<G, P>(A, R, s, x, xin, r0 - 3, r1 + 3);
+    // row / channel corrections of the row stage a1 handles in the NEXT step (row s-1): fetched here, parked in
+    // shared memory at the end of the step (parity (s-1)&1)
+    double corr_next = 0.0;
+    const bool corr_thread = A.do_refpix && tid < 3 * G && (s - 1) >= 0 && (s - 1) < n;
+    if (corr_thread) {
+        const int rown = s - 1, g = tid % G, which = tid / G;
+        if (which == 0) {
+            corr_next = A.rowcorr[(long)g * n + rown];
+        } else {
+            int ch = ((tile * TS) >> 7) + (which - 1);
+            if (ch > 31) ch = 31;
+            corr_next = A.chan_m[g * 32 + ch] * (double)rown + A.chan_c[g * 32 + ch];
+        }
+    }
+
+    // ================= stage a1 : row s-2 (flags, refpix, bias, multilin, D) =================
+    {
+        const int row = s - 2;
+        const bool rowin = row >= 0 && row < n && row >= r0 - 2 && row < r1 + 2;
+        f4* dst = sm.D + (size_t)RIP_SLOT5(-2) * H * RW;
+        const int fslot = RIP_SLOT5(-2) * TW + tid;
+        if (rowin && (tid >= 1 || tile == 0) && tid <= TW - 2 && xin) {
+            uint32_t grown = 0u;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const uint32_t* sr = sm.sat + (size_t)((row + dy) & (S_DEPTH - 1)) * RW + col;
+                grown |= sr[-1] | sr[0] | sr[1];
+            }
+            const uint32_t own = sm.sat[(size_t)(row & (S_DEPTH - 1)) * RW + col];
+            grown &= 0xffffu;
+            uint32_t satm = grown;
+            if (grown) {
+                for (int b = 1; b <= A.sat_backup; ++b) satm |= grown >> b;
+            }
+            satm &= allg & ~1u;
+            const uint32_t adf = own >> 16;
+            const bool active = xact && (row >= nb && row < n - nb);
+            float S[G];
+            {
+                const uint16_t* rq = sm.rawq + (size_t)RIP_SLOT5(-2) * G * TW + tid;
+#pragma unroll
+                for (int g = 0; g < G; ++g) S[g] = u16_to_f32(rq[g * TW]);
+            }
+            if (A.do_refpix) {  // gen_cal_image.py:535-556: f64 subtractions, f32 stores
+                const int chsel = ((x >> 7) != ((tile * TS) >> 7)) ? 1 : 0;
+                const double* rc = sm.rc + (size_t)(row & 1) * G;
+                const double* ln = sm.ln + (size_t)((row & 1) * 2 + chsel) * G;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float dk = r1w<NQ1>(R.r1, g);
+                    float v = S[g] - dk;
+                    v = (float)((double)v - rc[g]);
+                    v = (float)((double)v - ln[g]);
+                    S[g] = v + dk;
+                }
+            }
+            // biascorr (embedded with zeros outside the active region: v - 0 == v)
+            f2 S2[G / 2];
+#pragma unroll
+            for (int j = 0; j < G / 2; ++j)
+                S2[j] = sub2p(f2{S[2 * j], S[2 * j + 1]}, f2{r1w<NQ1>(R.r1, G + 2 * j), r1w<NQ1>(R.r1, G + 2 * j + 1)});
+            const float Smin = r1w<NQ1>(R.r1, 2 * G), Smax = r1w<NQ1>(R.r1, 2 * G + 1), Sref = r1w<NQ1>(R.r1, 2 * G + 2);
+            const float gain = r1w<NQ1>(R.r1, 2 * G + 3);
+            const uint32_t aux = f_as_u(r1w<NQ1>(R.r1, 2 * G + 4));
+            float c[P];
+#pragma unroll
+            for (int L = 0; L < P; ++L) c[L] = r1w<NQ1>(R.r1, 2 * G + 5 + L);
+            // z = -1 + (2 (S - Smin)) / (Smax - Smin)      (ipc_linearity.py:330)
+            SharedDiv sd;
+            const float den = Smax - Smin;
+            sd.init(den);
+            const bool div_ok = sd.ok && (Smin > -1.0e18f) && (Smin < 1.0e18f);
+            f2 z2[G / 2];
+#pragma unroll
+            for (int j = 0; j < G / 2; ++j) {
+                const f2 num = mul2(bc(2.0f), sub2p(S2[j], bc(Smin)));
+                f2 q;
+                if (div_ok) q = sd.div2(num);
+                else q = f2{num.x / den, num.y / den};
+                z2[j] = add2p(bc(-1.0f), q);
+            }
+            if (A.do_not_flag_first) z2[0].x = np_clip<float>(z2[0].x, -1.0f, 1.0f);
+            // |z| > 1 anywhere (or NaN) -> the extrapolating scalar evaluation of v1 for this pixel (rare)
+            bool anyex = false;
+#pragma unroll
+            for (int j = 0; j < G / 2; ++j) {
+                const float ax = z2[j].x < 0 ? -z2[j].x : z2[j].x, ay = z2[j].y < 0 ? -z2[j].y : z2[j].y;
+                anyex = anyex || !(ax <= 1.0f) || !(ay <= 1.0f);
+            }
+            uint32_t dq = (aux & 1u) ? DQ_REFERENCE_PIXEL : 0u;
+            f2 phi2[G / 2];
+            if (!anyex) {
+                f2 prev[G / 2], cur[G / 2];
+#pragma unroll
+                for (int j = 0; j < G / 2; ++j) { phi2[j] = bc(c[0]); prev[j] = bc(1.0f); cur[j] = z2[j]; }
+#pragma unroll
+                for (int L = 1; L < P; ++L) {
+                    const float a = (float)((2 * L + 1) / (double)(L + 1)), b = (float)(L / (double)(L + 1));
+#pragma unroll
+                    for (int j = 0; j < G / 2; ++j) {
+                        phi2[j] = add2(phi2[j], mul2(bc(c[L]), cur[j]));
+                        if (L + 1 < P) {  // the recursion value of the last order is never used
+                            const f2 nxt = sub2(mul2(mul2(bc(a), z2[j]), cur[j]), mul2(bc(b), prev[j]));
+                            prev[j] = cur[j];
+                            cur[j] = nxt;
+                        }
+                    }
+                }
+            } else {
+                ExtrapIn<G, P> ein;
+#pragma unroll
+                for (int j = 0; j < G / 2; ++j) { ein.z[2 * j] = z2[j].x; ein.z[2 * j + 1] = z2[j].y; }
+#pragma unroll
+                for (int L = 0; L < P; ++L) ein.c[L] = c[L];
+                const ExtrapOut<G> eo = phi_extrap<G, P>(ein, satm, A.do_not_flag_first != 0);
+#pragma unroll
+                for (int j = 0; j < G / 2; ++j) phi2[j] = f2{eo.phi[2 * j], eo.phi[2 * j + 1]};
+                dq |= eo.dq;
+            }
+            if (aux & 1u) {  // lin dq has NO_LIN_CORR | REFERENCE_PIXEL: S - Sref instead (ipc_linearity.py:334-336)
+#pragma unroll
+                for (int j = 0; j < G / 2; ++j) phi2[j] = sub2p(S2[j], bc(Sref));
+            }
+            if (active) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const f2 a = mul2(phi2[2 * h], bc(gain)), b = mul2(phi2[2 * h + 1], bc(gain));
+                    dst[h * RW + col] = f4{a.x, a.y, b.x, b.y};
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
+                if (A.lincube && row >= r0 && row < r1 && (tid >= 4 || tile == 0) && tid < TW - 4) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g)
+                        A.lincube[(long)g * npl + (long)row * n + x] = (g & 1) ? phi2[g >> 1].y : phi2[g >> 1].x;
+                }
+            }
+            sm.flg[fslot] = satm | (adf << 16);
+            sm.nlc[fslot] = (uint8_t)(((dq & DQ_NO_LIN_CORR) ? 1u : 0u) | ((aux & 2u) ? 4u : 0u));
+        } else if (row >= r0 - 2 && row < r1 + 2) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
+            sm.flg[fslot] = 0u;
+            sm.nlc[fslot] = 0;
+        }
+    }
+
+    // ================= stage b : row s-4 (IPC pass 1) =================
+    {
+        const int row = s - 4;
+        const bool rowok = row >= nb && row < n - nb && row >= r0 - 1 && row < r1 + 1;
+        f4* o = sm.O1 + (size_t)(row & (O_DEPTH - 1)) * H * RW;
+        if (rowok && tid >= 2 && tid <= TW - 3 && xact) {
+            const float k[9] = {R.kb[0].x, R.kb[0].y, R.kb[0].z, R.kb[0].w, R.kb[1].x, R.kb[1].y, R.kb[1].z, R.kb[1].w, R.kb8};
+            const f4* dm = sm.D + (size_t)RIP_SLOT5(-5) * H * RW;
+            const f4* d0 = sm.D + (size_t)RIP_SLOT5(-4) * H * RW;
+            const f4* dp = sm.D + (size_t)RIP_SLOT5(-3) * H * RW;
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                f2 lo, hi;
+                stencil9(dm + h * RW, d0 + h * RW, dp + h * RW, col, k, lo, hi);
+                const f4 dc = d0[h * RW + col];
+                const f2 clo{dc.x, dc.y}, chi{dc.z, dc.w};
+                const f2 rlo = sub2p(add2p(clo, clo), lo), rhi = sub2p(add2p(chi, chi), hi);  // output + image2 - ipc_fwd(output)
+                o[h * RW + col] = f4{rlo.x, rlo.y, rhi.x, rhi.y};
+            }
+        } else if (row >= r0 - 1 && row < r1 + 1) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) o[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
+        }
+    }
+
+#endif
     // ================= stage a0 : row s (raw -> cumulative saturation / A-D floor bits) ===========
     {
         const int row = s;
