@@ -460,8 +460,7 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
         V.slope = o->slope; V.err_read = o->err_read; V.err_poisson = o->err_poisson; V.pdq = o->pdq;
         V.endslice = o->endslice; V.rdq = o->rdq; V.lincube = o->lin_cube;
         if (e0) RIP_CUDA(cudaEventRecord(e0, st));
-        if (!h->v2_counter.p) h->v2_counter.alloc(1);
-        launch_cal_fused_v2(V, G, h->P, h->v2_counter.p, st);
+        launch_cal_fused_v2(V, G, h->P, st);
         if (e1) RIP_CUDA(cudaEventRecord(e1, st));
         return;
     }

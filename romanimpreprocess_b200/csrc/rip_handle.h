@@ -25,7 +25,6 @@ struct rip_caldir {
     DevBuf<uint32_t> sdq;
     // cal_fused v2: packed per-(row, tile) records (rip_v2_core.cuh), built lazily per group count
     DevBuf<float> v2_rec1, v2_recK;
-    DevBuf<int> v2_counter;  // work-item counter of the persistent kernel
     int v2_G = 0;
     // K0 workspace
     DevBuf<uint32_t> hist, k0_ticket;

@@ -26,7 +26,7 @@ size_t cal_fused_smem_bytes(int G, int g_dtype, int k_dtype, int threads);
 namespace v2 { struct Args; }
 bool v2_supported(int G, int P);
 void v2_plan_to_device(const rip_ramp_plan* plan, cudaStream_t st);
-void launch_cal_fused_v2(const v2::Args& A, int G, int P, int* counter, cudaStream_t st);
+void launch_cal_fused_v2(const v2::Args& A, int G, int P, cudaStream_t st);
 void v2_pack(rip_caldir* h, int G, cudaStream_t st);
 
 }  // namespace rip

@@ -39,41 +39,30 @@ __global__ void pack_recK_kernel(const PackSrc S, int ntile, f4* __restrict__ ou
     }
 }
 
-// Persistent CTAs: MINB per SM, each pulling (band, column-tile) work items from an atomic counter until none are
-// left, so the tail of the launch is one tile long instead of one wave long.
+// One CTA per (column tile, row band).  (A persistent-CTA variant pulling work items from an atomic counter was
+// measured on B200: no gain -- 1120 items on 592 resident slots already overlap well -- and its outer loop cost
+// registers, i.e. spills at the 128-register budget; dropped.)
 template <int G, int P, int MINB>
-__global__ void __launch_bounds__(TW, MINB) cal_fused_v2_kernel(const Args A, int* __restrict__ counter) {
+__global__ void __launch_bounds__(TW, MINB) cal_fused_v2_kernel(const Args A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_item;
     Smem<G> sm;
     sm.carve(smem_raw);
     Regs<G, P> R;
-    const int tid = threadIdx.x;
-    const int nband = (A.n + A.band_rows - 1) / A.band_rows;
-    const int total = nband * A.ntile;
-    for (int it = 0;; ++it) {
-        if (counter) {
-            if (tid == 0) s_item = atomicAdd(counter, 1);
-            __syncthreads();
-        }
-        const int item = counter ? s_item : (it == 0 ? (int)blockIdx.x : total);  // no counter: one item per CTA
-        if (item >= total) break;
-        const int tile = item % A.ntile;  // neighbouring items = neighbouring column tiles of one band (halo reuse in L2)
-        const int r0 = (item / A.ntile) * A.band_rows;
-        const int r1 = min(r0 + A.band_rows, A.n);
-        prologue<G, P>(A, sm, R, tid, tile, r0, r1);
+    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int r0 = blockIdx.y * A.band_rows;
+    const int r1 = min(r0 + A.band_rows, A.n);
+    prologue<G, P>(A, sm, R, tid, tile, r0, r1);
+    __syncthreads();
+    int f5 = mod_pos(r0 - 3, F_DEPTH);
+    for (int s = r0 - 3; s <= r1 + 5; ++s) {
+        step<G, P>(A, c_plan_v2, sm, R, tid, tile, r0, r1, s, f5);
+        f5 = (f5 == F_DEPTH - 1) ? 0 : f5 + 1;
         __syncthreads();
-        int f5 = mod_pos(r0 - 3, F_DEPTH);
-        for (int s = r0 - 3; s <= r1 + 5; ++s) {
-            step<G, P>(A, c_plan_v2, sm, R, tid, tile, r0, r1, s, f5);
-            f5 = (f5 == F_DEPTH - 1) ? 0 : f5 + 1;
-            __syncthreads();
-        }
     }
 }
 
 template <int G, int P, int MINB>
-static void launch_tb(const Args& A, int* counter, cudaStream_t st) {
+static void launch_tb(const Args& A, cudaStream_t st) {
     const size_t smem = Smem<G>::bytes();
     auto kern = cal_fused_v2_kernel<G, P, MINB>;
     static thread_local bool configured = false;
@@ -82,33 +71,21 @@ static void launch_tb(const Args& A, int* counter, cudaStream_t st) {
         RIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
-    static thread_local int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        RIP_CUDA(cudaGetDevice(&dev));
-        RIP_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
-    const int total = A.ntile * ((A.n + A.band_rows - 1) / A.band_rows);
-    static const bool persist = [] { const char* e = getenv("RIP_V2_PERSIST"); return !(e && atoi(e) == 0); }();
-    if (persist) {
-        RIP_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
-        RIP_LAUNCH(kern, std::min(total, sm_count * MINB), TW, smem, st, A, counter);
-    } else {
-        RIP_LAUNCH(kern, total, TW, smem, st, A, (int*)nullptr);
-    }
+    dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
+    RIP_LAUNCH(kern, grid, TW, smem, st, A);
 }
 
 // resident CTAs per SM the kernel is compiled for: 4 (128 registers/thread) for G <= 8, 3 for G = 16 (larger rings);
 // RIP_V2_MINB=3|4 overrides for experiments
 template <int G, int P>
-static void launch_t(const Args& A, int* counter, cudaStream_t st) {
+static void launch_t(const Args& A, cudaStream_t st) {
     static const int minb = [] {
         const char* e = getenv("RIP_V2_MINB");
         const int v = e ? atoi(e) : 0;
         return (v == 3 || v == 4) ? v : ((G <= 8) ? 4 : 3);
     }();
-    if (minb == 4 && G <= 8) launch_tb<G, P, 4>(A, counter, st);
-    else launch_tb<G, P, 3>(A, counter, st);
+    if (minb == 4 && G <= 8) launch_tb<G, P, 4>(A, st);
+    else launch_tb<G, P, 3>(A, st);
 }
 
 }  // namespace v2
@@ -117,11 +94,11 @@ bool v2_supported(int G, int P) {
     return (G == 8 && P == 4) || (G == 8 && P == 11) || (G == 16 && P == 11) || (G == 16 && P == 4);
 }
 
-void launch_cal_fused_v2(const v2::Args& A, int G, int P, int* counter, cudaStream_t st) {
-    if (G == 16 && P == 4) v2::launch_t<16, 4>(A, counter, st);
-    else if (G == 8 && P == 4) v2::launch_t<8, 4>(A, counter, st);
-    else if (G == 8 && P == 11) v2::launch_t<8, 11>(A, counter, st);
-    else if (G == 16 && P == 11) v2::launch_t<16, 11>(A, counter, st);
+void launch_cal_fused_v2(const v2::Args& A, int G, int P, cudaStream_t st) {
+    if (G == 16 && P == 4) v2::launch_t<16, 4>(A, st);
+    else if (G == 8 && P == 4) v2::launch_t<8, 4>(A, st);
+    else if (G == 8 && P == 11) v2::launch_t<8, 11>(A, st);
+    else if (G == 16 && P == 11) v2::launch_t<16, 11>(A, st);
     else throw Error("cal_fused v2: unsupported (G, P)");
 }
 

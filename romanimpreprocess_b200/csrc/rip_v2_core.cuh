@@ -176,8 +176,6 @@ struct Regs {
     double area64;
     // running CTA-uniform element offsets (advanced by one detector row per step; they depend only on blockIdx and
     // the step, so they live in uniform registers): the per-thread part of every address is just tid / x
-    long o1;     // rec1 record of (row s-2, tile), in f4 units
-    long ok;     // recK record of (row s-6, tile), in f4 units
     long orow;   // s * n  (pixel offset of detector row s)
 };
 
@@ -187,11 +185,15 @@ RIP_HD int wrap5(int a) { return a >= F_DEPTH ? a - F_DEPTH : a; }  // a in [0, 
 #define RIP_SLOT5(DK) sl5[(((DK) % 5) + 5) % 5]
 
 // ---- loads -------------------------------------------------------------------------------------------------
+// The loaders are unconditional (rows outside the frame are clamped, rows outside the stage's band range are loaded
+// but never used: a few per cent of extra L2 traffic at the band edges): a conditional load would keep the old register
+// contents live around the whole loop, and zero-filling costs predicated moves in every step.
+RIP_HD int clamp_row(int row, int n) { return row < 0 ? 0 : (row >= n ? n - 1 : row); }
+
 template <int G, int P>
-RIP_HD void load_a0(const Args& A, Regs<G, P>& R, int row, int x, bool xin, int lo, int hi) {
-    // (every loader assigns in both branches: otherwise the old register contents stay live around the whole loop)
-    if (row >= 0 && row < A.n && row >= lo && row < hi && xin) R.thr = (A.thr + R.orow)[x];
-    else R.thr = 0.0f;
+RIP_HD void load_a0(const Args& A, Regs<G, P>& R, int row, int x, bool xin) {
+    const int xx = xin ? x : 0;
+    R.thr = A.thr[(long)clamp_row(row, A.n) * A.n + xx];
 }
 
 // 16-byte asynchronous global -> shared copy (LDGSTS); the host build copies at once
@@ -234,63 +236,39 @@ RIP_HD void raw_row_async(const Args& A, Smem<G>& sm, const Regs<G, P>& R, int r
     cp_async_commit();
 }
 template <int G, int P>
-RIP_HD void load_a1(const Args& A, Regs<G, P>& R, int row, int tid, int lo, int hi, int part) {
+RIP_HD void load_a1(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int part) {
     // part 0: dark + bias words (first G/2 float4), part 1: the rest (Smin .. coefficients)
-    if (row >= 0 && row < A.n && row >= lo && row < hi) {
-        const f4* p = A.rec1 + R.o1;
+    const f4* p = A.rec1 + ((long)clamp_row(row, A.n) * A.ntile + tile) * (Regs<G, P>::NQ1 * TW);
 #pragma unroll
-        for (int q = 0; q < Regs<G, P>::NQ1; ++q)
-            if ((q < G / 2) == (part == 0)) R.r1[q] = p[q * TW + tid];
-    } else {
-#pragma unroll
-        for (int q = 0; q < Regs<G, P>::NQ1; ++q)
-            if ((q < G / 2) == (part == 0)) R.r1[q] = f4{0.f, 0.f, 0.f, 0.f};
-    }
+    for (int q = 0; q < Regs<G, P>::NQ1; ++q)
+        if ((q < G / 2) == (part == 0)) R.r1[q] = p[q * TW + tid];
 }
 template <int G, int P>
-RIP_HD void load_b(const Args& A, Regs<G, P>& R, int row, int tid, int lo, int hi) {
-    if (row >= 0 && row < A.n && row >= lo && row < hi) {
-        const f4* p = A.recK + (R.ok + 2 * (long)A.ntile * (KQ * TW));  // two rows below stage c's row
-        R.kb[0] = p[tid];
-        R.kb[1] = p[TW + tid];
-        R.kb8 = ((const float*)(p + 2 * TW))[4 * tid];  // .x of the third word
-    } else {
-        R.kb[0] = R.kb[1] = f4{0.f, 0.f, 0.f, 0.f};
-        R.kb8 = 0.0f;
-    }
+RIP_HD void load_b(const Args& A, Regs<G, P>& R, int row, int tile, int tid) {
+    const f4* p = A.recK + ((long)clamp_row(row, A.n) * A.ntile + tile) * (KQ * TW);
+    R.kb[0] = p[tid];
+    R.kb[1] = p[TW + tid];
+    R.kb8 = ((const float*)(p + 2 * TW))[4 * tid];  // .x of the third word
 }
 template <int G, int P>
-RIP_HD void load_c(const Args& A, Regs<G, P>& R, int row, int ahead, int tid, int x, bool xin, int lo, int hi) {  // ahead: rows below R.ok's row
-    if (row >= 0 && row < A.n && row >= lo && row < hi) {
-        const f4* p = A.recK + (R.ok + ahead * (long)A.ntile * (KQ * TW));
+RIP_HD void load_c(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int x, bool xin) {
+    const int rr = clamp_row(row, A.n);
+    const f4* p = A.recK + ((long)rr * A.ntile + tile) * (KQ * TW);
 #pragma unroll
-        for (int q = 0; q < KQ; ++q) R.kc[q] = p[q * TW + tid];
-        if (A.area && xin) {
-            const long o = R.orow + (long)(ahead - 6) * A.n;  // row s-6+ahead
-            if (A.area_dtype == RIP_F64) R.area64 = ((const double*)A.area + o)[x];
-            else R.area32 = ((const float*)A.area + o)[x];
-        } else {
-            R.area64 = 1.0;
-            R.area32 = 1.0f;
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < KQ; ++q) R.kc[q] = f4{0.f, 0.f, 0.f, 0.f};
-        R.area64 = 1.0;
-        R.area32 = 1.0f;
+    for (int q = 0; q < KQ; ++q) R.kc[q] = p[q * TW + tid];
+    if (A.area) {
+        const long o = (long)rr * A.n + (xin ? x : 0);
+        if (A.area_dtype == RIP_F64) R.area64 = ((const double*)A.area)[o];
+        else R.area32 = ((const float*)A.area)[o];
     }
 }
 // offsets for march step s (rows may be outside the frame: the addresses are then never dereferenced)
 template <int G, int P>
 RIP_HD void init_pointers(const Args& A, Regs<G, P>& R, int tile, int s) {
-    R.o1 = ((long)(s - 2) * A.ntile + tile) * (Regs<G, P>::NQ1 * TW);
-    R.ok = ((long)(s - 6) * A.ntile + tile) * (KQ * TW);
     R.orow = (long)s * A.n;
 }
 template <int G, int P>
 RIP_HD void advance_pointers(const Args& A, Regs<G, P>& R) {
-    R.o1 += (long)A.ntile * (Regs<G, P>::NQ1 * TW);
-    R.ok += (long)A.ntile * (KQ * TW);
     R.orow += A.n;
 }
 
@@ -514,11 +492,11 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
     const int sl5[5] = {f5, wrap5(f5 + 1), wrap5(f5 + 2), wrap5(f5 + 3), wrap5(f5 + 4)};
     raw_row_async<G, P>(A, sm, R, s + 2, 2, RIP_SLOT5(2), tile, tid, r0 - 3, r1 + 3);
 #if RIP_V2_SCHED == 0
-    load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 0);
-    load_b<G, P>(A, R, s - 4, tid, r0 - 1, r1 + 1);
+    load_a1<G, P>(A, R, s - 2, tile, tid, 0);
+    load_b<G, P>(A, R, s - 4, tile, tid);
 #else  // stage order c, a1, b, a0: the whole a1 record is in flight during stage c, the taps of stage b during stage a1
-    load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 0);
-    load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 1);
+    load_a1<G, P>(A, R, s - 2, tile, tid, 0);
+    load_a1<G, P>(A, R, s - 2, tile, tid, 1);
 #endif
 
     // ================= stage c : row s-6 =================
@@ -526,7 +504,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
         const int row = s - 6;
         const bool out_col = (tid >= 4 || tile == 0) && tid < TW - 4 && xin;
         const bool c_on = row >= r0 && row < r1 && out_col;
-        if (RIP_V2_EARLY_L1 && !c_on) load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 1);  // (otherwise issued below, before the ramp fit)
+        if (RIP_V2_EARLY_L1 && !c_on) load_a1<G, P>(A, R, s - 2, tile, tid, 1);  // (otherwise issued below, before the ramp fit)
         if (c_on) {
             const long p = R.orow - 6 * (long)n + x;
             const bool active = xact && (row >= nb && row < n - nb);
@@ -576,7 +554,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
                 for (int g = 0; g < G; ++g) d[g] = 0.0f;  // unused: every output of a non-active pixel is flag-only
             }
             // second half of stage a1's record: the IPC taps of this stage are dead now, the ramp fit hides the latency
-            if (RIP_V2_EARLY_L1) load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 1);
+            if (RIP_V2_EARLY_L1) load_a1<G, P>(A, R, s - 2, tile, tid, 1);
             GroupFlags gf;
             gf.sat = fl & 0xffffu;
             gf.adf = fl >> 16;
@@ -637,11 +615,11 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
                 }
             }
         }
-        load_c<G, P>(A, R, row + 1, 1, tid, x, xin, r0, r1);
+        load_c<G, P>(A, R, row + 1, tile, tid, x, xin);
 #if RIP_V2_SCHED == 0
-        if (!RIP_V2_EARLY_L1) load_a1<G, P>(A, R, s - 2, tid, r0 - 2, r1 + 2, 1);
+        if (!RIP_V2_EARLY_L1) load_a1<G, P>(A, R, s - 2, tile, tid, 1);
 #else
-        load_b<G, P>(A, R, s - 4, tid, r0 - 1, r1 + 1);
+        load_b<G, P>(A, R, s - 4, tile, tid);
 #endif
     }
 
@@ -671,7 +649,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
         }
     }
 
-    load_a0<G, P>(A, R, s, x, xin, r0 - 3, r1 + 3);
+    load_a0<G, P>(A, R, s, x, xin);
     // row / channel corrections of the row stage a1 handles in the NEXT step (row s-1): fetched here, parked in
     // shared memory at the end of the step (parity (s-1)&1)
     double corr_next = 0.0;
@@ -821,7 +799,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
     }
 
 #else
-    load_a0<G, P>(A, R, s, x, xin, r0 - 3, r1 + 3);
+    load_a0<G, P>(A, R, s, x, xin);
     // row / channel corrections of the row stage a1 handles in the NEXT step (row s-1): fetched here, parked in
     // shared memory at the end of the step (parity (s-1)&1)
     double corr_next = 0.0;
@@ -1044,7 +1022,7 @@ RIP_HD void prologue(const Args& A, Smem<G>& sm, Regs<G, P>& R, int tid, int til
     init_pointers<G, P>(A, R, tile, s0);
     raw_row_async<G, P>(A, sm, R, s0, 0, f5, tile, tid, r0 - 3, r1 + 3);
     raw_row_async<G, P>(A, sm, R, s0 + 1, 1, wrap5(f5 + 1), tile, tid, r0 - 3, r1 + 3);
-    load_c<G, P>(A, R, s0 - 6, 0, tid, x, xin, r0, r1);
+    load_c<G, P>(A, R, s0 - 6, tile, tid, x, xin);
     // ring pads and the slots stage a1 / b read before anything was written there
     for (int i = tid; i < S_DEPTH * RW; i += TW) sm.sat[i] = 0u;
     for (int i = tid; i < (D_DEPTH + O_DEPTH) * Smem<G>::H * RW; i += TW) sm.D[i] = f4{0.f, 0.f, 0.f, 0.f};
