@@ -16,7 +16,7 @@ RIP_PMAX = 16
 RIP_F32, RIP_F64, RIP_I32, RIP_U16 = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librip_b200.so")
+LIB_PATH = os.environ.get("RIP_B200_LIB") or os.path.join(_HERE, "librip_b200.so")  # (override: development A/B builds)
 
 
 class RampSlice(C.Structure):

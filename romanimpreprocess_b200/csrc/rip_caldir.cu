@@ -453,6 +453,7 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
         V.band_rows = prm->band_rows > 0 ? prm->band_rows : 128;
         V.do_refpix = prm->do_refpix; V.do_not_flag_first = prm->do_not_flag_first; V.exclude_first = prm->exclude_first;
         V.sat_backup = prm->sat_backup; V.area_dtype = prm->area_dtype;
+        V.negzero = -0.0f;
         V.raw = d_raw; V.area = d_area;
         V.rowcorr = h->rowcorr.p; V.chan_m = h->chan_m.p; V.chan_c = h->chan_c.p;
         V.rec1 = (const v2::f4*)h->v2_rec1.p; V.recK = (const v2::f4*)h->v2_recK.p; V.thr = h->thr_eff.p;

@@ -56,6 +56,10 @@ struct alignas(16) f4 {
 // even with --fmad=false, which would change the rounding.  It does NOT contract a packed multiply feeding SCALAR
 // `add.rn.f32` / `sub.rn.f32`.  Hence: multiplies are packed (mul2); additions/subtractions that may consume a
 // product are scalar pairs (add2 / sub2); packed add/sub (add2p / sub2p) only where no operand is a product.
+// A product that must feed a packed add is computed as fma(a, b, nz) with nz = -0.0f passed at RUN TIME (Args::negzero;
+// x + (-0) == x for every x, so this is the IEEE product, and ptxas can neither fold the unknown addend nor contract
+// an FMA into the following add): mul2x.  With that, products and sums of the long multiply-add chains (Legendre
+// recursion, 3x3 stencils) are all packed.
 // `make check-sass` (csrc/Makefile) verifies that the FFMA2 count in SASS equals the fma.rn.f32x2 count in PTX.
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return f2{r.x, r.y}; }
@@ -63,6 +67,7 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) { return f2{__fadd_rn(a.x, b.x), 
 __device__ __forceinline__ f2 sub2(f2 a, f2 b) { return f2{__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)}; }
 __device__ __forceinline__ f2 add2p(f2 a, f2 b) { float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return f2{r.x, r.y}; }
 __device__ __forceinline__ f2 sub2p(f2 a, f2 b) { float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(-b.x, -b.y)); return f2{r.x, r.y}; }
+__device__ __forceinline__ f2 mul2x(f2 a, f2 b, float nz) { float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(nz, nz)); return f2{r.x, r.y}; }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y)); return f2{r.x, r.y}; }
 __device__ __forceinline__ float fma1(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ float rcp_approx(float d) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d)); return r; }
@@ -73,6 +78,7 @@ inline f2 add2(f2 a, f2 b) { return f2{a.x + b.x, a.y + b.y}; }
 inline f2 sub2(f2 a, f2 b) { return f2{a.x - b.x, a.y - b.y}; }
 inline f2 add2p(f2 a, f2 b) { return add2(a, b); }
 inline f2 sub2p(f2 a, f2 b) { return sub2(a, b); }
+inline f2 mul2x(f2 a, f2 b, float) { return f2{a.x * b.x, a.y * b.y}; }
 inline f2 fma2(f2 a, f2 b, f2 c) { return f2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
 inline float fma1(float a, float b, float c) { return fmaf(a, b, c); }
 inline float rcp_approx(float d) { return 1.0f / d; }
@@ -117,6 +123,8 @@ RIP_HD float u16_to_f32(uint32_t v) {
 struct Args {
     int n, ntile, band_rows;
     int do_refpix, do_not_flag_first, exclude_first, sat_backup, area_dtype;
+    float negzero;           // -0.0f, deliberately a run-time value (see mul2x)
+    int pad_;
     const uint16_t* raw;     // [G,n,n]
     const void* area;        // [n,n] f32|f64 or null
     const double* rowcorr;   // [G,n]
@@ -288,16 +296,16 @@ RIP_HD float r1w(const f4 (&r)[NQ], int w) { return f4_get(r[w >> 2], w & 3); }
 // 9-tap stencil over a float4 ring for one half (4 groups) -> two packed pairs.  Tap order = the reference's
 // accumulation order (utils/ipc_linearity.py:69-94): c, (1,0), (-1,0), (0,1), (0,-1), (1,1), (1,-1), (-1,1), (-1,-1);
 // tap (dy,dx) reads the image at (row-dy, col-dx).
-RIP_HD void stencil9(const f4* ring_m, const f4* ring_0, const f4* ring_p, int col, const float (&k)[9], f2& lo, f2& hi) {
+RIP_HD void stencil9(const f4* ring_m, const f4* ring_0, const f4* ring_p, int col, const float (&k)[9], float nz, f2& lo, f2& hi) {
     // ring_m = row-1 (dy=+1), ring_0 = row, ring_p = row+1 (dy=-1); col already includes the pad offset
     const f4 c = ring_0[col];
-    lo = mul2(f2{c.x, c.y}, bc(k[0]));
-    hi = mul2(f2{c.z, c.w}, bc(k[0]));
+    lo = mul2x(f2{c.x, c.y}, bc(k[0]), nz);
+    hi = mul2x(f2{c.z, c.w}, bc(k[0]), nz);
 #define RIP_TAP(V, Q)                                     \
     {                                                     \
         const f4 t = (V);                                 \
-        lo = add2(lo, mul2(f2{t.x, t.y}, bc(k[Q])));      \
-        hi = add2(hi, mul2(f2{t.z, t.w}, bc(k[Q])));      \
+        lo = add2p(lo, mul2x(f2{t.x, t.y}, bc(k[Q]), nz)); \
+        hi = add2p(hi, mul2x(f2{t.z, t.w}, bc(k[Q]), nz)); \
     }
     RIP_TAP(ring_m[col], 1)
     RIP_TAP(ring_p[col], 2)
@@ -491,7 +499,8 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
     // slots of rows s, s+1, .. s+4 (== s-5 .. s-1) in the depth-5 rings
     const int sl5[5] = {f5, wrap5(f5 + 1), wrap5(f5 + 2), wrap5(f5 + 3), wrap5(f5 + 4)};
     raw_row_async<G, P>(A, sm, R, s + 2, 2, RIP_SLOT5(2), tile, tid, r0 - 3, r1 + 3);
-#if RIP_V2_SCHED == 0
+#if RIP_V2_SCHED == 2  // FIFO: every stage refills its registers for the NEXT step right after it ran (below)
+#elif RIP_V2_SCHED == 0
     load_a1<G, P>(A, R, s - 2, tile, tid, 0);
     load_b<G, P>(A, R, s - 4, tile, tid);
 #else  // stage order c, a1, b, a0: the whole a1 record is in flight during stage c, the taps of stage b during stage a1
@@ -526,7 +535,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
                     f2 lo, hi;
-                    stencil9(om + h * RW, o0 + h * RW, op + h * RW, col, k, lo, hi);
+                    stencil9(om + h * RW, o0 + h * RW, op + h * RW, col, k, A.negzero, lo, hi);
                     const f4 oc = o0[h * RW + col], dc = dd[h * RW + col];
                     t[2 * h] = sub2p(add2p(f2{oc.x, oc.y}, f2{dc.x, dc.y}), lo);  // (output + image2) - ipc_fwd(output)
                     t[2 * h + 1] = sub2p(add2p(f2{oc.z, oc.w}, f2{dc.z, dc.w}), hi);
@@ -616,14 +625,15 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
             }
         }
         load_c<G, P>(A, R, row + 1, tile, tid, x, xin);
-#if RIP_V2_SCHED == 0
+#if RIP_V2_SCHED == 2
+#elif RIP_V2_SCHED == 0
         if (!RIP_V2_EARLY_L1) load_a1<G, P>(A, R, s - 2, tile, tid, 1);
 #else
         load_b<G, P>(A, R, s - 4, tile, tid);
 #endif
     }
 
-#if RIP_V2_SCHED == 0
+#if RIP_V2_SCHED != 1
     // ================= stage b : row s-4 (IPC pass 1) =================
     {
         const int row = s - 4;
@@ -637,7 +647,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
 #pragma unroll
             for (int h = 0; h < H; ++h) {
                 f2 lo, hi;
-                stencil9(dm + h * RW, d0 + h * RW, dp + h * RW, col, k, lo, hi);
+                stencil9(dm + h * RW, d0 + h * RW, dp + h * RW, col, k, A.negzero, lo, hi);
                 const f4 dc = d0[h * RW + col];
                 const f2 clo{dc.x, dc.y}, chi{dc.z, dc.w};
                 const f2 rlo = sub2p(add2p(clo, clo), lo), rhi = sub2p(add2p(chi, chi), hi);  // output + image2 - ipc_fwd(output)
@@ -649,7 +659,15 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
         }
     }
 
+#if RIP_V2_SCHED == 2
+    load_b<G, P>(A, R, s - 3, tile, tid);
+#if RIP_V2_SCHED == 2
+    load_a1<G, P>(A, R, s - 1, tile, tid, 0);
+    load_a1<G, P>(A, R, s - 1, tile, tid, 1);
+#endif
+#else
     load_a0<G, P>(A, R, s, x, xin);
+#endif
     // row / channel corrections of the row stage a1 handles in the NEXT step (row s-1): fetched here, parked in
     // shared memory at the end of the step (parity (s-1)&1)
     double corr_next = 0.0;
@@ -750,9 +768,11 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
                     const float a = (float)((2 * L + 1) / (double)(L + 1)), b = (float)(L / (double)(L + 1));
 #pragma unroll
                     for (int j = 0; j < G / 2; ++j) {
-                        phi2[j] = add2(phi2[j], mul2(bc(c[L]), cur[j]));
+                        phi2[j] = add2p(phi2[j], mul2x(bc(c[L]), cur[j], A.negzero));
                         if (L + 1 < P) {  // the recursion value of the last order is never used
-                            const f2 nxt = sub2(mul2(mul2(bc(a), z2[j]), cur[j]), mul2(bc(b), prev[j]));
+                            // (L = 1: prev is exactly 1, b * 1 == b)
+                            const f2 bp = (L == 1) ? bc(b) : mul2x(bc(b), prev[j], A.negzero);
+                            const f2 nxt = sub2p(mul2x(mul2(bc(a), z2[j]), cur[j], A.negzero), bp);
                             prev[j] = cur[j];
                             cur[j] = nxt;
                         }
@@ -900,9 +920,11 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
                     const float a = (float)((2 * L + 1) / (double)(L + 1)), b = (float)(L / (double)(L + 1));
 #pragma unroll
                     for (int j = 0; j < G / 2; ++j) {
-                        phi2[j] = add2(phi2[j], mul2(bc(c[L]), cur[j]));
+                        phi2[j] = add2p(phi2[j], mul2x(bc(c[L]), cur[j], A.negzero));
                         if (L + 1 < P) {  // the recursion value of the last order is never used
-                            const f2 nxt = sub2(mul2(mul2(bc(a), z2[j]), cur[j]), mul2(bc(b), prev[j]));
+                            // (L = 1: prev is exactly 1, b * 1 == b)
+                            const f2 bp = (L == 1) ? bc(b) : mul2x(bc(b), prev[j], A.negzero);
+                            const f2 nxt = sub2p(mul2x(mul2(bc(a), z2[j]), cur[j], A.negzero), bp);
                             prev[j] = cur[j];
                             cur[j] = nxt;
                         }
@@ -961,7 +983,7 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
 #pragma unroll
             for (int h = 0; h < H; ++h) {
                 f2 lo, hi;
-                stencil9(dm + h * RW, d0 + h * RW, dp + h * RW, col, k, lo, hi);
+                stencil9(dm + h * RW, d0 + h * RW, dp + h * RW, col, k, A.negzero, lo, hi);
                 const f4 dc = d0[h * RW + col];
                 const f2 clo{dc.x, dc.y}, chi{dc.z, dc.w};
                 const f2 rlo = sub2p(add2p(clo, clo), lo), rhi = sub2p(add2p(chi, chi), hi);  // output + image2 - ipc_fwd(output)
@@ -1008,6 +1030,9 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& 
             else sm.ln[(size_t)((rown & 1) * 2 + (which - 1)) * G + g] = corr_next;
         }
     }
+#if RIP_V2_SCHED == 2
+    load_a0<G, P>(A, R, s + 1, x, xin);
+#endif
     advance_pointers<G, P>(A, R);
     cp_async_wait<1>();  // the raw row issued in the previous step (row s+1) has landed; the caller's barrier publishes it
 }
@@ -1023,6 +1048,12 @@ RIP_HD void prologue(const Args& A, Smem<G>& sm, Regs<G, P>& R, int tid, int til
     raw_row_async<G, P>(A, sm, R, s0, 0, f5, tile, tid, r0 - 3, r1 + 3);
     raw_row_async<G, P>(A, sm, R, s0 + 1, 1, wrap5(f5 + 1), tile, tid, r0 - 3, r1 + 3);
     load_c<G, P>(A, R, s0 - 6, tile, tid, x, xin);
+#if RIP_V2_SCHED == 2
+    load_b<G, P>(A, R, s0 - 4, tile, tid);
+    load_a1<G, P>(A, R, s0 - 2, tile, tid, 0);
+    load_a1<G, P>(A, R, s0 - 2, tile, tid, 1);
+    load_a0<G, P>(A, R, s0, x, xin);
+#endif
     // ring pads and the slots stage a1 / b read before anything was written there
     for (int i = tid; i < S_DEPTH * RW; i += TW) sm.sat[i] = 0u;
     for (int i = tid; i < (D_DEPTH + O_DEPTH) * Smem<G>::H * RW; i += TW) sm.D[i] = f4{0.f, 0.f, 0.f, 0.f};

@@ -33,7 +33,7 @@ class CalArgs(C.Structure):
 
 class V2Args(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("n", "ntile", "band_rows", "do_refpix", "do_not_flag_first", "exclude_first",
-                                       "sat_backup", "area_dtype")] + \
+                                       "sat_backup", "area_dtype")] + [("negzero", C.c_float), ("pad_", C.c_int)] + \
                [(k, C.c_void_p) for k in ("raw", "area", "rowcorr", "chan_m", "chan_c", "rec1", "recK", "thr", "w_exact",
                                           "slope", "err_read", "err_poisson", "pdq", "endslice", "rdq", "lincube")]  # fmt: skip
 
@@ -237,6 +237,7 @@ def _run_v2(c, data_u16, amp33_u16, read_pattern, area, config, do_refpix, band_
     A.do_not_flag_first = 1 if list(read_pattern[0]) == [0] else 0
     A.exclude_first = 1 if config.get("EXCLUDE_FIRST", True) else 0
     A.sat_backup = config.get("SATURATION_BACKUP", 1)
+    A.negzero = -0.0
     A.area_dtype = _lib.RIP_F32
     if area is not None:
         area = _lib.as_float_plane(area)
