@@ -414,7 +414,7 @@ def run_ours(args):
                             "jump/saturation flags + dark + flat/area + endslice (BASELINE metric config)",
                 "l2_policy": f"inputs larger than L2: each step streams {algo_bytes / 1e9:.2f} GB (126 MB L2) and "
                              f"{n_exp} distinct exposures are rotated",
-                "threads": args.threads or 128, "band_rows": args.band_rows or 128, "parallelism": f"sca-sharded x{world}",
+                "threads": args.threads or 128, "band_rows": args.band_rows or 64, "parallelism": f"sca-sharded x{world}",
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "cal_fused_kernel",
@@ -438,6 +438,59 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_forward(args):
+    """Secondary workload (BASELINE configs[1], not the headline line): sim_to_isim forward ramp generation for one
+    4096^2 SCA (README table: 8 resultants / 35 reads): reset noise, binomial apportioning per read, IPC + gain +
+    24-step float64 bisection of the order-10 Legendre map per read, group means, read noise, biascorr, rounding."""
+    import ctypes as C
+
+    import torch
+
+    from romanimpreprocess_b200 import _lib, synth
+    from romanimpreprocess_b200.from_sim import sim_to_isim as s2i
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+
+    torch.cuda.set_device(0)
+    rp = synth.README_PATTERN
+    n = args.n
+    cal, _, _ = make_inputs(n, rp, 2, seed=1000)
+    cd = gci.CalDir(cal, device=0)
+    na = n - 8
+    rng = np.random.default_rng(7)
+    yy, xx = np.mgrid[0:na, 0:na].astype(np.float32)
+    mean = 300.0 + 0.02 * xx + 4.0e4 * np.exp(-0.5 * (((xx % 512) - 256) ** 2 + ((yy % 512) - 256) ** 2) / 9.0)
+    counts = rng.poisson(mean).astype(np.int32)
+    d_counts = torch.from_numpy(counts).cuda()
+    d_out = torch.empty((len(rp), na, na), dtype=torch.float32, device="cuda")
+    lib = _lib.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(i):
+        prm = s2i.fwd_params(rp, 1000 + i)
+        _lib.check(lib.rip_make_l1_dev(cd.handle, C.c_void_p(d_counts.data_ptr()), C.byref(prm),
+                                       C.c_void_p(d_out.data_ptr()), C.c_void_p(stream)))  # fmt: skip
+
+    for i in range(max(args.warmup, 1)):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(100 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    nreads = sum(len(g) for g in rp)
+    flops = float(na) * na * nreads * (24 * (P_ORDER) * 6 + 18)  # SURVEY 8d estimate (bisection-faithful)
+    print(json.dumps({"metric": "forward-model SCA/s (sim_to_isim make_l1_fullcal, 4096^2, 35 reads -> 8 resultants)",
+                      "value": 1e3 / ms, "unit": "SCA/s", "ms_per_step": ms, "n_gpus": 1, "steps": args.steps,
+                      "dtype": "f64", "data": "synthetic", "secondary_workload": True,
+                      "roofline": {"bound": "fp64 ALU (not a measured peak: nominal B200 FP64 ~40 TFLOP/s)",
+                                   "achieved": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s"},
+                      "mean_DN_last_group": float(d_out[-1].mean().item())}), flush=True)  # fmt: skip
+    cd.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -452,10 +505,14 @@ def main():
     ap.add_argument("--cpu-tile", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (for ncu captures)")
+    ap.add_argument("--workload", default="l1l2", choices=["l1l2", "forward"],
+                    help="l1l2 = the headline metric; forward = secondary line for the forward ramp generator")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "forward":
+        run_forward(args)
     else:
         run_ours(args)
 
