@@ -236,9 +236,10 @@ __global__ void k0_final_kernel(const SelState* __restrict__ st, const float* __
 // the line through (1.5, bottom), (n-2.5, top)
 __global__ void k0_chan_kernel(const uint16_t* __restrict__ raw, const float* __restrict__ dark, int n,
                                const double* __restrict__ rowcorr, double* __restrict__ chan_m,
-                               double* __restrict__ chan_c) {
+                               double* __restrict__ chan_c, double* __restrict__ chan_line /*[G,32,n]*/) {
     __shared__ float sv[2][512];
     __shared__ float meds[2];
+    __shared__ double line_mc[2];
     const int ch = blockIdx.x, g = blockIdx.y;
     const long npl = (long)n * n;
     for (int side = 0; side < 2; ++side) {
@@ -263,7 +264,13 @@ __global__ void k0_chan_kernel(const uint16_t* __restrict__ raw, const float* __
         const double m = (t - b) / (x1 - x0);
         chan_m[g * 32 + ch] = m;
         chan_c[g * 32 + ch] = b - m * x0;
+        line_mc[0] = m;
+        line_mc[1] = b - m * x0;
     }
+    __syncthreads();
+    // the line itself, tabulated for the fused v2 kernel (same unfused f64 expression as v1: m * row + c)
+    const double m = line_mc[0], c = line_mc[1];
+    for (int row = threadIdx.x; row < n; row += blockDim.x) chan_line[((long)g * 32 + ch) * n + row] = m * (double)row + c;
 }
 
 }  // namespace rip
@@ -292,6 +299,7 @@ static void run_k0(rip_caldir* h, const uint16_t* d_raw, const uint16_t* d_amp33
         h->rowcorr.alloc((size_t)RIP_GMAX * n);
         h->chan_m.alloc((size_t)RIP_GMAX * 32);
         h->chan_c.alloc((size_t)RIP_GMAX * 32);
+        h->chan_line.alloc((size_t)RIP_GMAX * 32 * n);
     }
     RIP_LAUNCH(k0_rows_kernel, dim3((n + 7) / 8, G), 256, 0, st, d_amp33, h->amp_med.p, n, h->rowA.p, h->rowB.p, h->sel.p,
                h->hist.p, h->k0_ticket.p);
@@ -302,7 +310,7 @@ static void run_k0(rip_caldir* h, const uint16_t* d_raw, const uint16_t* d_amp33
     while (np2 < n) np2 <<= 1;
     RIP_LAUNCH(k0_final_kernel, G, 1024, (size_t)2 * np2 * sizeof(float), st, h->sel.p, h->rowA.p, h->rowB.p, n, np2,
                h->refout_slope, h->rowcorr.p, h->gmed.p);
-    RIP_LAUNCH(k0_chan_kernel, dim3(nch, G), 256, 0, st, d_raw, h->dark_cube.p, n, h->rowcorr.p, h->chan_m.p, h->chan_c.p);
+    RIP_LAUNCH(k0_chan_kernel, dim3(nch, G), 256, 0, st, d_raw, h->dark_cube.p, n, h->rowcorr.p, h->chan_m.p, h->chan_c.p, h->chan_line.p);
 }
 
 static double derive_refout_slope(const rip_caldir_desc* d) {
@@ -456,7 +464,8 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
         V.negzero = -0.0f;
         V.raw = d_raw; V.area = d_area;
         V.rowcorr = h->rowcorr.p; V.chan_m = h->chan_m.p; V.chan_c = h->chan_c.p;
-        V.rec1 = (const v2::f4*)h->v2_rec1.p; V.recK = (const v2::f4*)h->v2_recK.p; V.thr = h->thr_eff.p;
+        V.rec1 = v2_rec1_row0(h, G); V.recK = v2_recK_row0(h); V.thr = h->thr_eff.p;
+        V.chan_line = h->chan_line.p;
         V.w_exact = dw;
         V.slope = o->slope; V.err_read = o->err_read; V.err_poisson = o->err_poisson; V.pdq = o->pdq;
         V.endslice = o->endslice; V.rdq = o->rdq; V.lincube = o->lin_cube;

@@ -30,7 +30,7 @@ struct rip_caldir {
     DevBuf<uint32_t> hist, k0_ticket;
     DevBuf<SelState> sel;
     DevBuf<float> rowA, rowB, gmed;
-    DevBuf<double> rowcorr, chan_m, chan_c;
+    DevBuf<double> rowcorr, chan_m, chan_c, chan_line;
     // host-entry workspace
     DevBuf<uint16_t> w_raw, w_amp;
     DevRaw w_area;

@@ -23,10 +23,12 @@ void launch_cal_fused(const CalArgs& A, int g_dtype, int k_dtype, int threads, c
 size_t cal_fused_smem_bytes(int G, int g_dtype, int k_dtype, int threads);
 
 // rip_v2.cu ------------------------------------------------------------------------------------------------
-namespace v2 { struct Args; }
+namespace v2 { struct Args; struct f4; }
 bool v2_supported(int G, int P);
 void v2_plan_to_device(const rip_ramp_plan* plan, cudaStream_t st);
 void launch_cal_fused_v2(const v2::Args& A, int G, int P, cudaStream_t st);
 void v2_pack(rip_caldir* h, int G, cudaStream_t st);
+v2::f4* v2_rec1_row0(rip_caldir* h, int G);  // record of detector row 0 inside the padded allocations
+v2::f4* v2_recK_row0(rip_caldir* h);
 
 }  // namespace rip

@@ -8,11 +8,12 @@
 namespace rip {
 
 __constant__ RampPlanDev c_plan_v2;
+__constant__ v2::FastTab c_fast_v2;
 
 namespace v2 {
 
 __global__ void pack_rec1_kernel(const PackSrc S, int ntile, int nq, f4* __restrict__ out) {
-    const int c = threadIdx.x, tile = blockIdx.x, row = blockIdx.y;
+    const int c = threadIdx.x, tile = blockIdx.x, row = (int)blockIdx.y - PADR;  // out points at row 0
     const int x = tile * TS + c;
     f4* o = out + ((long)row * ntile + tile) * ((long)nq * TW) + c;
     for (int q = 0; q < nq; ++q) {
@@ -26,7 +27,7 @@ __global__ void pack_rec1_kernel(const PackSrc S, int ntile, int nq, f4* __restr
 }
 
 __global__ void pack_recK_kernel(const PackSrc S, int ntile, f4* __restrict__ out) {
-    const int c = threadIdx.x, tile = blockIdx.x, row = blockIdx.y;
+    const int c = threadIdx.x, tile = blockIdx.x, row = (int)blockIdx.y - PADR;
     const int x = tile * TS + c;
     f4* o = out + ((long)row * ntile + tile) * ((long)KQ * TW) + c;
     for (int q = 0; q < KQ; ++q) {
@@ -53,10 +54,10 @@ __global__ void __launch_bounds__(TW, MINB) cal_fused_v2_kernel(const Args A) {
     const int r1 = min(r0 + A.band_rows, A.n);
     prologue<G, P>(A, sm, R, tid, tile, r0, r1);
     __syncthreads();
-    int f5 = mod_pos(r0 - 3, F_DEPTH);
+    int f5 = mod_pos(r0 - 3, RING);
     for (int s = r0 - 3; s <= r1 + 5; ++s) {
-        step<G, P>(A, c_plan_v2, sm, R, tid, tile, r0, r1, s, f5);
-        f5 = (f5 == F_DEPTH - 1) ? 0 : f5 + 1;
+        step<G, P>(A, c_plan_v2, c_fast_v2, sm, R, tid, tile, r0, r1, s, f5);
+        f5 = (f5 == RING - 1) ? 0 : f5 + 1;
         __syncthreads();
     }
 }
@@ -104,14 +105,24 @@ void launch_cal_fused_v2(const v2::Args& A, int G, int P, cudaStream_t st) {
 
 void v2_plan_to_device(const rip_ramp_plan* plan, cudaStream_t st) {
     RIP_CUDA(cudaMemcpyToSymbolAsync(c_plan_v2, plan, sizeof(rip_ramp_plan), 0, cudaMemcpyHostToDevice, st));
+    // (the copy is taken from pageable memory at enqueue time, so the temporary may die here)
+    const v2::FastTab ft = v2::make_fast_tab(*plan);
+    RIP_CUDA(cudaMemcpyToSymbolAsync(c_fast_v2, &ft, sizeof ft, 0, cudaMemcpyHostToDevice, st));
 }
+
+// record of detector row 0 inside the padded allocations
+v2::f4* v2_rec1_row0(rip_caldir* h, int G) {
+    return (v2::f4*)h->v2_rec1.p + (size_t)v2::PADR * v2::ntiles(h->n) * v2::nq1(G, h->P) * v2::TW;
+}
+v2::f4* v2_recK_row0(rip_caldir* h) { return (v2::f4*)h->v2_recK.p + (size_t)v2::PADR * v2::ntiles(h->n) * v2::KQ * v2::TW; }
 
 // (re)build the packed records of a handle for G groups
 void v2_pack(rip_caldir* h, int G, cudaStream_t st) {
     if (h->v2_G == G) return;
     const int n = h->n, ntile = v2::ntiles(n), nq = v2::nq1(G, h->P);
-    h->v2_rec1.alloc((size_t)n * ntile * nq * v2::TW * 4);
-    h->v2_recK.alloc((size_t)n * ntile * v2::KQ * v2::TW * 4);
+    const int nrow = n + 2 * v2::PADR;  // zero rows on both sides: the kernel's loaders never clamp
+    h->v2_rec1.alloc((size_t)nrow * ntile * nq * v2::TW * 4);
+    h->v2_recK.alloc((size_t)nrow * ntile * v2::KQ * v2::TW * 4);
     v2::PackSrc S;
     S.n = n; S.nb = h->nb; S.G = G; S.P = h->P;
     S.dark = h->dark_cube.p;
@@ -119,9 +130,9 @@ void v2_pack(rip_caldir* h, int G, cudaStream_t st) {
     S.coefs = h->coefs.p; S.Smin = h->Smin.p; S.Smax = h->Smax.p; S.Sref = h->Sref.p;
     S.gain = (const float*)h->gain.p; S.aux = h->aux.p; S.ipc = (const float*)h->ipc.p;
     S.read = h->read.p; S.dslope = h->dslope_ipc.p; S.flat = h->flat_ipc.p; S.sdq = h->sdq.p;
-    dim3 grid(ntile, n);
-    RIP_LAUNCH(v2::pack_rec1_kernel, grid, v2::TW, 0, st, S, ntile, nq, (v2::f4*)h->v2_rec1.p);
-    RIP_LAUNCH(v2::pack_recK_kernel, grid, v2::TW, 0, st, S, ntile, (v2::f4*)h->v2_recK.p);
+    dim3 grid(ntile, nrow);
+    RIP_LAUNCH(v2::pack_rec1_kernel, grid, v2::TW, 0, st, S, ntile, nq, v2_rec1_row0(h, G));
+    RIP_LAUNCH(v2::pack_recK_kernel, grid, v2::TW, 0, st, S, ntile, v2_recK_row0(h));
     h->v2_G = G;
 }
 

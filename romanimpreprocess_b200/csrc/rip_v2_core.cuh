@@ -8,8 +8,9 @@
 //   * calibration data repacked once per CALDIR into per-(row, column-tile) records of float4 words
 //     (rec1: dark[G] bias[G] Smin Smax Sref gain aux coefs[P];  recK: 9 gathered IPC taps, gain, read, dark slope,
 //     flat, static dq) -> every input arrives as a fully coalesced 128-bit load with immediate offsets;
-//   * the loads of stage X for the next march step are issued right after stage X of this step has consumed its
-//     registers (one full step of latency budget, no double buffering);
+//   * the records of the next march step are loaded into registers behind a SINGLE scoreboard wait per step (ptxas
+//     gives all global loads of the loop one scoreboard, so any first use waits for every load in flight: see Regs);
+//     thresholds and reference-pixel corrections ride the cp.async group of the raw row instead of registers;
 //   * shared-memory rings hold float4 (4 groups of one pixel) -> conflict-free LDS.128 / STS.128;
 //   * group pairs are processed with the packed FP32 instructions of sm_100 (FMUL2 / FADD2 / FFMA2: two IEEE
 //     single-precision results per issue slot; each lane is rounded exactly like the scalar op, so results are
@@ -18,19 +19,15 @@
 //     use the FMA-residual correction that yields the correctly rounded quotient (== IEEE division);
 //   * gathered IPC taps are zero where the source pixel is outside the active area and D is stored as 0 for
 //     non-active pixels, so the 3x3 stencils are branch-free;
-//   * jump significance is tested as delta^2 > thr^2 var (no sqrt / division); anything within the relative band of
-//     the threshold is re-evaluated exactly in the reference's op order (same fallback as v1).
+//   * jump significance is tested as delta |delta| > thr^2 var on packed slice pairs (no sqrt / division; FMAs are
+//     fine there because it only classifies); anything within the relative band of the threshold is re-evaluated
+//     exactly in the reference's op order (same fallback as v1).
 //
 // Written __host__ __device__ like v1 so that tests/hostcheck can walk the identical source on the CPU.
 #pragma once
 #include "rip_math.cuh"
 
-#ifndef RIP_V2_SCHED
-#define RIP_V2_SCHED 0  // stage order within a march step: 0 = c, b, a1, a0;  1 = c, a1, b, a0
-#endif
-#ifndef RIP_V2_EARLY_L1
-#define RIP_V2_EARLY_L1 0  // 1: issue the second half of stage a1's record before the ramp fit instead of after stage c
-#endif
+#include <string.h>
 
 namespace rip {
 namespace v2 {
@@ -39,7 +36,9 @@ constexpr int TW = 128;   // columns per tile (= compute threads per CTA)
 constexpr int TS = 120;   // tile stride: outputs are tile columns 4..123 (tile 0 also 0..3)
 constexpr int RW = TW + 2;  // ring width: 1 pad column on each side
 constexpr int KQ = 4;     // float4 words per pixel in recK
-constexpr int D_DEPTH = 5, O_DEPTH = 4, S_DEPTH = 4, F_DEPTH = 5, R_DEPTH = 5;  // the depth-5 rings share one modulo index
+constexpr int RING = 5;   // depth of the rings addressed with the shared modulo-5 slot (D, raw, thresholds, flags, corrections)
+constexpr int O_DEPTH = 4, S_DEPTH = 4;
+constexpr int PADR = 10;  // zero rows above and below the packed records: the loaders never clamp (rows -9 .. n+4 are touched)
 
 RIP_HD constexpr int nq1(int G, int P) { return (2 * G + 5 + P + 3) / 4; }
 inline int ntiles(int n) { return (n - 4 + TS - 1) / TS; }
@@ -128,10 +127,10 @@ struct Args {
     const uint16_t* raw;     // [G,n,n]
     const void* area;        // [n,n] f32|f64 or null
     const double* rowcorr;   // [G,n]
-    const double* chan_m;    // [G,32]
+    const double* chan_m;    // [G,32]  (K0 products; the kernel reads the tabulated lines below)
     const double* chan_c;
-    const f4* rec1;          // [n][ntile][NQ1][TW]
-    const f4* recK;          // [n][ntile][KQ][TW]
+    const f4* rec1;          // [n + 2 PADR][ntile][NQ1][TW], pointing at row 0
+    const f4* recK;          // [n + 2 PADR][ntile][KQ][TW],  pointing at row 0
     const float* thr;        // [n,n]
     const double* w_exact;
     float* slope;
@@ -141,76 +140,72 @@ struct Args {
     int8_t* endslice;
     uint8_t* rdq;
     float* lincube;
+    const double* chan_line; // [G,32,n]  chan_m * row + chan_c (f64, unfused), tabulated by K0
 };
 
 template <int G>
 struct Smem {
-    f4* D;            // [D_DEPTH][G/4][RW]
+    f4* D;            // [RING][G/4][RW]
     f4* O1;           // [O_DEPTH][G/4][RW]
+    uint16_t* rawq;   // [RING][G][TW]      raw resultants, filled by cp.async two steps ahead (rows s-2 .. s+2 live)
+    float* thrq;      // [RING][TW]         saturation thresholds, same cp.async group as the raw row
+    double* rc;       // [RING][G]          row correction of the row,            〃
+    double* ln;       // [RING][2][G]       channel line for the two channels the tile touches, 〃
     uint32_t* sat;    // [S_DEPTH][RW]
-    uint32_t* flg;    // [F_DEPTH][TW]      satm | adf<<16                 thread-private delay line a1 -> c
-    uint8_t* nlc;     // [F_DEPTH][TW]      bit0 dynamic NO_LIN_CORR, bit2 reference pixel
-    uint16_t* rawq;   // [R_DEPTH][G][TW]   raw resultants, filled by cp.async two steps ahead (rows s-2 .. s+2 live)
-    double* rc;       // [2][G]             row correction of the row a1 handles next / now
-    double* ln;       // [2][2][G]          channel line for the two channels the tile touches
+    uint32_t* flg;    // [RING][TW]         satm | adf<<16                 thread-private delay line a1 -> c
+    uint8_t* nlc;     // [RING][TW]         bit0 dynamic NO_LIN_CORR, bit2 reference pixel
     static constexpr int H = G / 4;
     RIP_HD static size_t bytes() {
-        return sizeof(f4) * (size_t)(D_DEPTH + O_DEPTH) * H * RW + 4 * (size_t)S_DEPTH * RW + 5 * (size_t)F_DEPTH * TW +
-               8 * (size_t)(2 * G + 4 * G) + 2 * (size_t)R_DEPTH * G * TW + 64;
+        return sizeof(f4) * (size_t)(RING + O_DEPTH) * H * RW + 2 * (size_t)RING * G * TW + 4 * (size_t)RING * TW +
+               8 * (size_t)RING * 3 * G + 4 * (size_t)S_DEPTH * RW + 5 * (size_t)RING * TW + 64;
     }
     RIP_HD void carve(unsigned char* base) {
         size_t off = 0;
-        D = (f4*)(base + off); off += sizeof(f4) * (size_t)D_DEPTH * H * RW;
+        D = (f4*)(base + off); off += sizeof(f4) * (size_t)RING * H * RW;
         O1 = (f4*)(base + off); off += sizeof(f4) * (size_t)O_DEPTH * H * RW;
-        rawq = (uint16_t*)(base + off); off += 2 * (size_t)R_DEPTH * G * TW;
-        rc = (double*)(base + off); off += 8 * (size_t)2 * G;
-        ln = (double*)(base + off); off += 8 * (size_t)4 * G;
+        rawq = (uint16_t*)(base + off); off += 2 * (size_t)RING * G * TW;
+        thrq = (float*)(base + off); off += 4 * (size_t)RING * TW;
+        rc = (double*)(base + off); off += 8 * (size_t)RING * G;
+        ln = (double*)(base + off); off += 8 * (size_t)RING * 2 * G;
         sat = (uint32_t*)(base + off); off += 4 * (size_t)S_DEPTH * RW;
-        flg = (uint32_t*)(base + off); off += 4 * (size_t)F_DEPTH * TW;
+        flg = (uint32_t*)(base + off); off += 4 * (size_t)RING * TW;
         nlc = (uint8_t*)(base + off);
     }
 };
 
-// registers a thread carries from one march step to the next: inputs prefetched for each stage
+// Registers a thread carries from one march step to the next: the calibration records of each stage, loaded one step
+// ahead.  ptxas tracks every global load of the loop with ONE scoreboard (measured: profiles/r02), so the first use of
+// any of them waits for ALL loads in flight; the schedule therefore consumes everything at the top of the step (the
+// `kb = kbn` copy), when the youngest load is two stages old, and issues nothing before that point.
 template <int G, int P>
 struct Regs {
     static constexpr int NQ1 = nq1(G, P);
-    float thr;         // stage a0, row s (the raw resultants arrive in shared memory by cp.async)
     f4 r1[NQ1];        // stage a1, row s-2
-    f4 kb[2];          // stage b,  row s-4 (taps 0..7)
+    f4 kb[2];          // stage b,  row s-4 (taps 0..7), valid from the top of the step
     float kb8;         //                   (tap 8)
+    f4 kbn[2];         // the same for the NEXT step, in flight during this one
+    float kbn8;
     f4 kc[KQ];         // stage c,  row s-6
     float area32;
     double area64;
-    // running CTA-uniform element offsets (advanced by one detector row per step; they depend only on blockIdx and
-    // the step, so they live in uniform registers): the per-thread part of every address is just tid / x
-    long orow;   // s * n  (pixel offset of detector row s)
+    unsigned orow;     // s * n (pixel offset of detector row s): CTA-uniform, advanced by n per step
 };
 
 RIP_HD int mod_pos(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
-RIP_HD int wrap5(int a) { return a >= F_DEPTH ? a - F_DEPTH : a; }  // a in [0, 2*F_DEPTH)
+RIP_HD int wrap5(int a) { return a >= RING ? a - RING : a; }  // a in [0, 2*RING)
 // slot of row s+DK in a depth-5 ring, given f5 = s mod 5 (DK is a compile-time constant)
 #define RIP_SLOT5(DK) sl5[(((DK) % 5) + 5) % 5]
 
-// ---- loads -------------------------------------------------------------------------------------------------
-// The loaders are unconditional (rows outside the frame are clamped, rows outside the stage's band range are loaded
-// but never used: a few per cent of extra L2 traffic at the band edges): a conditional load would keep the old register
-// contents live around the whole loop, and zero-filling costs predicated moves in every step.
-RIP_HD int clamp_row(int row, int n) { return row < 0 ? 0 : (row >= n ? n - 1 : row); }
-
-template <int G, int P>
-RIP_HD void load_a0(const Args& A, Regs<G, P>& R, int row, int x, bool xin) {
-    const int xx = xin ? x : 0;
-    R.thr = A.thr[(long)clamp_row(row, A.n) * A.n + xx];
-}
-
-// 16-byte asynchronous global -> shared copy (LDGSTS); the host build copies at once
-RIP_HD void cp_async16(void* smem_dst, const void* gmem_src) {
+// ---- asynchronous global -> shared copies (LDGSTS); the host build copies at once ---------------------------
+template <int BYTES>
+RIP_HD void cp_async(void* smem_dst, const void* gmem_src) {
 #if defined(__CUDA_ARCH__)
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
 #else
-    memcpy(smem_dst, gmem_src, 16);
+    memcpy(smem_dst, gmem_src, BYTES);
 #endif
 }
 RIP_HD void cp_async_commit() {
@@ -225,59 +220,67 @@ RIP_HD void cp_async_wait() {
 #endif
 }
 
-// raw resultants of one row of the tile -> ring slot: G x 128 columns x u16 = G x 16 chunks of 16 bytes, one (G = 8) or
-// two (G = 16) per thread.  Every thread commits a group each step (possibly empty) so that wait_group counts steps.
+// Everything stage a0 / a1 need of detector row `row` that is not a packed record -> ring slot `slot`:
+//   raw resultants  G x 128 columns x u16 = G x 16 chunks of 16 bytes, one (G = 8) or two (G = 16) per thread;
+//   the saturation threshold of the thread's own column (4 bytes);
+//   row correction [G] and the two channel lines [2][G] of the row (threads 0 .. 3G-1, 8 bytes each).
+// Every thread commits one group per step (possibly empty) so that wait_group counts steps.
 template <int G, int P>
-RIP_HD void raw_row_async(const Args& A, Smem<G>& sm, const Regs<G, P>& R, int row, int row_off, int slot, int tile, int tid,
-                          int lo, int hi) {  // row_off: rows relative to row s (R.orow)
+RIP_HD void row_async(const Args& A, Smem<G>& sm, const Regs<G, P>& R, int row, int row_off, int slot, int tile, int tid,
+                      int lo, int hi) {  // row_off: rows relative to row s (R.orow)
     if (row >= 0 && row < A.n && row >= lo && row < hi) {
-        const long npl = (long)A.n * A.n;
+        const unsigned npl = (unsigned)A.n * (unsigned)A.n;
+        const unsigned obase = R.orow + (unsigned)(row_off * A.n) + (unsigned)(tile * TS);  // uniform
         const int c = tid & 15, g0 = tid >> 4;
         if (tile * TS + 8 * c + 8 <= A.n) {
-            const uint16_t* src = A.raw + (R.orow + (long)row_off * A.n + tile * TS);  // uniform
-            const int toff = g0 * (int)npl + 8 * c;                                     // per thread (< 2^31 for n <= 4096, G <= 16)
 #pragma unroll
             for (int k = 0; k < G / 8; ++k)
-                cp_async16(sm.rawq + ((size_t)slot * G + g0 + 8 * k) * TW + 8 * c, src + (long)(8 * k) * npl + toff);
+                cp_async<16>(sm.rawq + ((size_t)slot * G + g0 + 8 * k) * TW + 8 * c,
+                             A.raw + (obase + (unsigned)(g0 + 8 * k) * npl + (unsigned)(8 * c)));
+        }
+        const int x = tile * TS + tid;
+        cp_async<4>(sm.thrq + slot * TW + tid, A.thr + (obase + (unsigned)(x < A.n ? tid : -tile * TS)));
+        if (A.do_refpix && tid < 3 * G) {
+            const int g = tid % G, which = tid / G;
+            if (which == 0) {
+                cp_async<8>(sm.rc + slot * G + g, A.rowcorr + ((unsigned)(g * A.n) + (unsigned)row));
+            } else {
+                int ch = ((tile * TS) >> 7) + (which - 1);
+                if (ch > 31) ch = 31;
+                cp_async<8>(sm.ln + (slot * 2 + (which - 1)) * G + g, A.chan_line + ((unsigned)((g * 32 + ch) * A.n) + (unsigned)row));
+            }
         }
     }
     cp_async_commit();
 }
+
+// ---- record loads (registers).  Unconditional: the records are padded with PADR zero rows on both sides, so rows
+// outside the frame are loaded but never used (a conditional load would keep the old register contents live
+// around the whole loop).
 template <int G, int P>
-RIP_HD void load_a1(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int part) {
-    // part 0: dark + bias words (first G/2 float4), part 1: the rest (Smin .. coefficients)
-    const f4* p = A.rec1 + ((long)clamp_row(row, A.n) * A.ntile + tile) * (Regs<G, P>::NQ1 * TW);
+RIP_HD void load_a1(const Args& A, Regs<G, P>& R, int row, int tile, int tid) {
+    const f4* p = A.rec1 + ((long)row * A.ntile + tile) * (Regs<G, P>::NQ1 * TW);
 #pragma unroll
-    for (int q = 0; q < Regs<G, P>::NQ1; ++q)
-        if ((q < G / 2) == (part == 0)) R.r1[q] = p[q * TW + tid];
+    for (int q = 0; q < Regs<G, P>::NQ1; ++q) R.r1[q] = p[q * TW + tid];
 }
 template <int G, int P>
-RIP_HD void load_b(const Args& A, Regs<G, P>& R, int row, int tile, int tid) {
-    const f4* p = A.recK + ((long)clamp_row(row, A.n) * A.ntile + tile) * (KQ * TW);
-    R.kb[0] = p[tid];
-    R.kb[1] = p[TW + tid];
-    R.kb8 = ((const float*)(p + 2 * TW))[4 * tid];  // .x of the third word
+RIP_HD void load_bn(const Args& A, Regs<G, P>& R, int row, int tile, int tid) {
+    const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW);
+    R.kbn[0] = p[tid];
+    R.kbn[1] = p[TW + tid];
+    R.kbn8 = ((const float*)(p + 2 * TW))[4 * tid];  // .x of the third word
 }
 template <int G, int P>
 RIP_HD void load_c(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int x, bool xin) {
-    const int rr = clamp_row(row, A.n);
-    const f4* p = A.recK + ((long)rr * A.ntile + tile) * (KQ * TW);
+    const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW);
 #pragma unroll
     for (int q = 0; q < KQ; ++q) R.kc[q] = p[q * TW + tid];
     if (A.area) {
-        const long o = (long)rr * A.n + (xin ? x : 0);
+        const int rr = row < 0 ? 0 : (row >= A.n ? A.n - 1 : row);
+        const unsigned o = (unsigned)rr * (unsigned)A.n + (unsigned)(xin ? x : 0);
         if (A.area_dtype == RIP_F64) R.area64 = ((const double*)A.area)[o];
         else R.area32 = ((const float*)A.area)[o];
     }
-}
-// offsets for march step s (rows may be outside the frame: the addresses are then never dereferenced)
-template <int G, int P>
-RIP_HD void init_pointers(const Args& A, Regs<G, P>& R, int tile, int s) {
-    R.orow = (long)s * A.n;
-}
-template <int G, int P>
-RIP_HD void advance_pointers(const Args& A, Regs<G, P>& R) {
-    R.orow += A.n;
 }
 
 RIP_HD float f4_get(const f4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
@@ -286,6 +289,13 @@ RIP_HD uint32_t f_as_u(float f) {
     return __float_as_uint(f);
 #else
     uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+RIP_HD float abs_f(float f) {
+#if defined(__CUDA_ARCH__)
+    return fabsf(f);
+#else
+    return f < 0 ? -f : (f == 0 ? 0.0f : f);
 #endif
 }
 
@@ -349,18 +359,33 @@ RIP_HD_COLD uint32_t jump_exact(const Ramp<G> rd, int v, float slope, float dvar
     return mask;
 }
 
-// jump_detect for one pixel, fast form (compile-time G).  FULL = plan variant 0 (the whole ramp: slice and weight
-// constants become immediate constant-bank operands); otherwise variant v (saturation-truncated refits, rare).
+// approximate jump threshold^2 bounds for a slope (fast classification; the band absorbs the ~1e-6 of __logf)
+struct ThrBand {
+    float hi2, lo2;
+    bool ok;
+};
+RIP_HD ThrBand thr_band(float slope, const RampPlanDev& pl) {
+    const float x = np_clip<float>(slope, pl.IthreshA_f, pl.IthreshB_f);
+#if defined(__CUDA_ARCH__)
+    const float thr = pl.thrA_f + pl.thrK_f * __logf(x * pl.invIA_f);
+#else
+    const float thr = pl.thrA_f + pl.thrK_f * logf(x * pl.invIA_f);
+#endif
+    ThrBand t;
+    t.ok = (thr > 0.0f) && (pl.band < 0.5f);
+    const float hi = thr * (1.0f + pl.band), lo = thr * (1.0f - pl.band);
+    t.hi2 = hi * hi * (1.0f + 4.0e-7f);
+    t.lo2 = lo * lo * (1.0f - 4.0e-7f);
+    return t;
+}
+
+// jump_detect for one pixel and plan variant v >= 1 (saturation-truncated refits: rare), scalar.
 // Same decisions as rip::jump_detect_pixel<.., FAST=true>; the sure-flag / sure-clear tests are done on squares.
-template <int G, int START>  // START = 0 / 1: full ramp with that first group (compile-time slice table); -1: variant v_in
-RIP_HD FitResult jump_fast(const float (&d)[G], int v_in, float gain, float read, bool active, const RampPlanDev& pl,
-                           const double* w_all) {
-    static_assert(G >= 6, "slice indexing of the full-ramp specialisation assumes at least 6 groups");
-    constexpr bool FULL = START >= 0;
+template <int G>
+RIP_HD FitResult jump_fast_var(const float (&d)[G], int v, float gain, float read, const RampPlanDev& pl, const double* w_all) {
     FitResult r;
-    const int v = FULL ? 0 : v_in;
-    const int ngrp = FULL ? G : pl.var_ngrp[v];
-    const int start = FULL ? START : pl.start;
+    const int ngrp = pl.var_ngrp[v];
+    const int start = pl.start;
     float acc = 0.0f;
 #pragma unroll
     for (int t = 0; t < G; ++t)
@@ -370,24 +395,13 @@ RIP_HD FitResult jump_fast(const float (&d)[G], int v_in, float gain, float read
     const float dvardt = np_max<float>(r.slope / gc, 0.0f);
     r.err_poisson = sqrtf(np_max<float>(pl.var_coef[v] * dvardt, 0.0f));
     r.err_read = read * pl.var_rfac[v];
-    r.jump_mask = 0u;
-    if (!active) return r;
     const float sig2read = read * read;
-    const float x = np_clip<float>(r.slope, pl.IthreshA_f, pl.IthreshB_f);
-#if defined(__CUDA_ARCH__)
-    const float thr = pl.thrA_f + pl.thrK_f * __logf(x * pl.invIA_f);  // approximate: the band absorbs ~1e-6
-#else
-    const float thr = pl.thrA_f + pl.thrK_f * logf(x * pl.invIA_f);
-#endif
+    const ThrBand tb = thr_band(r.slope, pl);
     // sure-flag: delta > 0 and delta^2 > thr_hi^2 var; sure-clear: delta <= 0 (thr > 0) or delta^2 < thr_lo^2 var.
     // var = dvardt*A + read^2*B >= 0 (A, B >= 0 checked by build_plan); NaNs make every comparison false -> unsure.
-    const bool thr_ok = (thr > 0.0f) && (pl.band < 0.5f);
-    const float hi = thr * (1.0f + pl.band), lo = thr * (1.0f - pl.band);
-    const float hi2 = hi * hi * (1.0f + 4.0e-7f), lo2 = lo * lo * (1.0f - 4.0e-7f);
-    // every slice is classified without branching; pixels with any unsure slice redo all slices exactly (rare)
-    bool unsure = !thr_ok;
+    bool unsure = !tb.ok;
     uint32_t mask = 0u;
-    int s = FULL ? 0 : pl.var_slice_off[v];
+    int s = pl.var_slice_off[v];
 #pragma unroll
     for (int i = 0; i < G - 1; ++i) {
         if (i >= start && i < ngrp - 1) {
@@ -395,16 +409,14 @@ RIP_HD FitResult jump_fast(const float (&d)[G], int v_in, float gain, float read
 #pragma unroll
             for (int di = 1; di <= 2; ++di) {
                 if (di <= dimax) {
-                    // FULL: slices are enumerated (i, di) with two per i except the last -> index (i-start)*2 + di-1
-                    const int si = FULL ? ((i - start) * 2 + (di - 1)) : s;
-                    const RampSlice& sl = pl.slices[si];
+                    const RampSlice& sl = pl.slices[s];
                     const float diff = d[(i + di < G) ? (i + di) : (G - 1)] - d[i];
                     const float var = dvardt * sl.A + sig2read * sl.B;
                     const float delta = diff * sl.inv_dt - r.slope;
                     const float l2 = delta * delta;
                     const bool pos = delta > 0.0f;
-                    const bool sure_set = pos && (l2 > hi2 * var);
-                    const bool sure_clr = (delta <= 0.0f) || (l2 < lo2 * var);
+                    const bool sure_set = pos && (l2 > tb.hi2 * var);
+                    const bool sure_clr = (delta <= 0.0f) || (l2 < tb.lo2 * var);
                     mask |= sure_set ? (1u << i) : 0u;
                     unsure = unsure || !(sure_set || sure_clr);  // borderline or NaN
                     ++s;
@@ -422,18 +434,137 @@ RIP_HD FitResult jump_fast(const float (&d)[G], int v_in, float gain, float read
     return r;
 }
 
+// Pair constants of the full-ramp jump test, derived from the plan (host: make_fast_tab; device: __constant__).
+// Lane x / y of entry [di-1][k] belong to the slices (i, di) with i = 2k / 2k+1; lanes without a slice hold zeros.
+struct FastTab {
+    f2 inv_dt[2][RIP_GMAX / 2], A[2][RIP_GMAX / 2], B[2][RIP_GMAX / 2];
+    f2 K[RIP_GMAX / 2];  // full-ramp weights (plan variant 0)
+    float ratio;         // lower/upper bound of the squared significance band, rounded down
+    float pad_;
+};
+RIP_HD bool full_slice_valid(int G, int start, int i, int di) {
+    if (i < start || i + di > G - 1) return false;
+    if (di == 2 && (G - 1 - start == 2)) return false;
+    return true;
+}
+inline FastTab make_fast_tab(const RampPlanDev& pl) {
+    FastTab ft;
+    memset(&ft, 0, sizeof ft);
+    const int G = pl.G, start = pl.start;
+    for (int di = 1; di <= 2; ++di)
+        for (int i = 0; i < G && i < RIP_GMAX; ++i) {
+            if (!full_slice_valid(G, start, i, di)) continue;
+            const RampSlice& sl = pl.slices[(i - start) * 2 + (di - 1)];
+            float* f;
+            f = &ft.inv_dt[di - 1][i >> 1].x; f[i & 1] = sl.inv_dt;
+            f = &ft.A[di - 1][i >> 1].x; f[i & 1] = sl.A;
+            f = &ft.B[di - 1][i >> 1].x; f[i & 1] = sl.B;
+        }
+    for (int t = 0; t < G && t < RIP_GMAX; ++t) (&ft.K[t >> 1].x)[t & 1] = pl.var_K[0][t];
+    const double b = (double)pl.band;
+    double r = (b < 0.5) ? ((1.0 - b) / (1.0 + b)) * ((1.0 - b) / (1.0 + b)) * (1.0 - 4.0e-7) / (1.0 + 4.0e-7) : 0.0;
+    ft.ratio = (float)(r * (1.0 - 1.0e-6));
+    return ft;
+}
+
+// one pair of slices: lanes (i0, di), (i0+1, di); V0 / V1 = the lane has a slice (compile time)
+template <bool V0, bool V1>
+RIP_HD void jump_pair(const f2 diff, const f2 inv_dt, const f2 Ac, const f2 Bc, const float nslope, const f2 hd, const f2 hr,
+                      const float ratio, const int i0, uint32_t& mask, bool& unsure) {
+    // (classification only: rounding is irrelevant here, anything inside the band is re-evaluated exactly)
+    const f2 delta = fma2(diff, inv_dt, bc(nslope));
+    const f2 hv = fma2(Ac, hd, mul2(Bc, hr));
+    const f2 lv = mul2(hv, bc(ratio));
+    if (V0) {
+        const float l2s = delta.x * abs_f(delta.x);  // signed square: <= 0 is a sure clear (threshold > 0)
+        const bool set = l2s > hv.x, clr = l2s < lv.x;
+        mask |= set ? (1u << i0) : 0u;
+        unsure = unsure || !(set || clr);
+    }
+    if (V1) {
+        const float l2s = delta.y * abs_f(delta.y);
+        const bool set = l2s > hv.y, clr = l2s < lv.y;
+        mask |= set ? (2u << i0) : 0u;
+        unsure = unsure || !(set || clr);
+    }
+}
+
+// jump_detect of the whole ramp (plan variant 0) for one active pixel; q[j] = groups (2j, 2j+1).
+// slope / errors: the reference's op order (fitting.py:187-212).  Flags: every slice is classified without branching
+// on packed pairs; pixels with any slice inside the relative band of the threshold (or NaN) redo all slices in the
+// reference's exact f64 op order (cold) => the flags are those of the exact path.
+template <int G, int START>
+RIP_HD FitResult jump_full(const f2 (&q)[G / 2], float gain, float read, const RampPlanDev& pl, const FastTab& ft,
+                           const double* w_all) {
+    static_assert(G >= 6 && (G & 1) == 0, "pair indexing of the full-ramp specialisation");
+    FitResult r;
+    const float d1 = q[0].y;
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < G / 2; ++j) {
+        const f2 pr = mul2(ft.K[j], sub2p(q[j], bc(d1)));  // K_t * (d_t - d_1); the sum stays sequential
+        acc = acc + pr.x;
+        acc = acc + pr.y;
+    }
+    r.slope = acc;
+    const float gc = np_clip<float>(gain, 1e-4f, 1e4f);
+    const float dvardt = np_max<float>(r.slope / gc, 0.0f);
+    r.err_poisson = sqrtf(np_max<float>(pl.var_coef[0] * dvardt, 0.0f));
+    r.err_read = read * pl.var_rfac[0];
+    const float sig2read = read * read;
+    const ThrBand tb = thr_band(r.slope, pl);
+    bool unsure = !tb.ok;
+    uint32_t mask = 0u;
+    const f2 hd = bc(tb.hi2 * dvardt), hr = bc(tb.hi2 * sig2read);
+    const float ns = -r.slope;
+#pragma unroll
+    for (int k = 0; k < G / 2; ++k) {
+        // di = 1: (d[2k+1] - d[2k], d[2k+2] - d[2k+1])
+        {
+            const bool v0 = full_slice_valid(G, START, 2 * k, 1), v1 = full_slice_valid(G, START, 2 * k + 1, 1);
+            if (v0 || v1) {
+                const f2 up = f2{q[k].y, q[(k + 1 < G / 2) ? k + 1 : k].x};  // (the last lane pair has no second slice)
+                const f2 diff = sub2p(up, q[k]);
+                if (v0 && v1) jump_pair<true, true>(diff, ft.inv_dt[0][k], ft.A[0][k], ft.B[0][k], ns, hd, hr, ft.ratio, 2 * k, mask, unsure);
+                else if (v0) jump_pair<true, false>(diff, ft.inv_dt[0][k], ft.A[0][k], ft.B[0][k], ns, hd, hr, ft.ratio, 2 * k, mask, unsure);
+                else jump_pair<false, true>(diff, ft.inv_dt[0][k], ft.A[0][k], ft.B[0][k], ns, hd, hr, ft.ratio, 2 * k, mask, unsure);
+            }
+        }
+        // di = 2: (d[2k+2] - d[2k], d[2k+3] - d[2k+1])
+        if (k + 1 < G / 2) {
+            const bool v0 = full_slice_valid(G, START, 2 * k, 2), v1 = full_slice_valid(G, START, 2 * k + 1, 2);
+            if (v0 || v1) {
+                const f2 diff = sub2p(q[(k + 1 < G / 2) ? k + 1 : k], q[k]);
+                if (v0 && v1) jump_pair<true, true>(diff, ft.inv_dt[1][k], ft.A[1][k], ft.B[1][k], ns, hd, hr, ft.ratio, 2 * k, mask, unsure);
+                else if (v0) jump_pair<true, false>(diff, ft.inv_dt[1][k], ft.A[1][k], ft.B[1][k], ns, hd, hr, ft.ratio, 2 * k, mask, unsure);
+                else jump_pair<false, true>(diff, ft.inv_dt[1][k], ft.A[1][k], ft.B[1][k], ns, hd, hr, ft.ratio, 2 * k, mask, unsure);
+            }
+        }
+    }
+    if (unsure) {
+        Ramp<G> rd;
+#pragma unroll
+        for (int j = 0; j < G / 2; ++j) { rd.v[2 * j] = q[j].x; rd.v[2 * j + 1] = q[j].y; }
+        mask = jump_exact<G>(rd, 0, r.slope, dvardt, sig2read, pl, w_all);
+    }
+    r.jump_mask = mask;
+    return r;
+}
+
 template <int G>
-RIP_HD FitResult ramp_fit_fast(const float (&d)[G], GroupFlags& gf, uint32_t& pdq, float gain, float read, bool active,
-                               const RampPlanDev& pl, const double* w_all) {
-    FitResult r = pl.start ? jump_fast<G, 1>(d, 0, gain, read, active, pl, w_all)
-                           : jump_fast<G, 0>(d, 0, gain, read, active, pl, w_all);
+RIP_HD FitResult ramp_fit_fast(const f2 (&q)[G / 2], GroupFlags& gf, uint32_t& pdq, float gain, float read,
+                               const RampPlanDev& pl, const FastTab& ft, const double* w_all) {
+    FitResult r = pl.start ? jump_full<G, 1>(q, gain, read, pl, ft, w_all) : jump_full<G, 0>(q, gain, read, pl, ft, w_all);
     const bool unsat = ((gf.sat >> (G - 1)) & 1u) == 0u;
     if (unsat) gf.jump |= r.jump_mask;
     if (gf.sat) {  // truncated refits only where some group is saturated
+        float d[G];
+#pragma unroll
+        for (int j = 0; j < G / 2; ++j) { d[2 * j] = q[j].x; d[2 * j + 1] = q[j].y; }
         for (int iend = G - 1; iend > 2 + pl.start; --iend) {
             const bool layer = ((gf.sat >> iend) & 1u) && !((gf.sat >> (iend - 1)) & 1u);
             if (layer) {
-                FitResult t = jump_fast<G, -1>(d, G - iend, gain, read, active, pl, w_all);
+                FitResult t = jump_fast_var<G>(d, G - iend, gain, read, pl, w_all);
                 r.slope = t.slope;
                 r.err_read = t.err_read;
                 r.err_poisson = t.err_poisson;
@@ -478,585 +609,385 @@ RIP_HD_COLD ExtrapOut<G> phi_extrap(const ExtrapIn<G, P> in, uint32_t satm, bool
     return o;
 }
 
-// ---- one march step --------------------------------------------------------------------------------------------
-// Stage rows as in v1: a0 row s, a1 row s-2, b row s-4, c row s-6.  Input registers are filled a fraction of a step
-// ahead of their use and never all at once (register budget: 128 / thread for 4 resident CTAs per SM):
-//     [L1, Lb issued]  c-compute  [Lc for the next step]  b-compute  [L0]  a1-compute  a0-compute  barrier
-// f5 = s mod F_DEPTH, carried by the caller.
+// ---- the four stages of a march step ----------------------------------------------------------------------------
+struct StepCtx {  // what every stage derives from (tile, tid, band, step); all cheap / CTA-uniform
+    int n, tid, tile, x, col, r0, r1, s;
+    bool xin, xact;
+    int sl5[5];  // slots of rows s, s+1, .. s+4 (== s-5 .. s-1) in the depth-5 rings
+};
+
+// stage a1 : row s-2 (saturation growth, refpix, bias, multilin, D = lin * gain)
 template <int G, int P>
-RIP_HD void step(const Args& A, const RampPlanDev& pl, Smem<G>& sm, Regs<G, P>& R, const int tid, const int tile,
-                 const int r0, const int r1, const int s, const int f5) {
-    constexpr int H = G / 4;
-    constexpr int NQ1 = Regs<G, P>::NQ1;
-    const int n = A.n, nb = 4, na = n - 8;
-    const long npl = (long)n * n;
-    const int x = tile * TS + tid;
-    const bool xin = x < n;
-    const int col = tid + 1;
+RIP_HD void stage_a1(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const StepCtx& C) {
+    constexpr int H = G / 4, NQ1 = Regs<G, P>::NQ1;
+    const int n = C.n, nb = 4, tid = C.tid, col = C.col, x = C.x, r0 = C.r0, r1 = C.r1;
+    const int (&sl5)[5] = C.sl5;
     const uint32_t allg = (1u << G) - 1u;
-    const bool xact = (x >= nb && x < n - nb);
-
-    // slots of rows s, s+1, .. s+4 (== s-5 .. s-1) in the depth-5 rings
-    const int sl5[5] = {f5, wrap5(f5 + 1), wrap5(f5 + 2), wrap5(f5 + 3), wrap5(f5 + 4)};
-    raw_row_async<G, P>(A, sm, R, s + 2, 2, RIP_SLOT5(2), tile, tid, r0 - 3, r1 + 3);
-#if RIP_V2_SCHED == 2  // FIFO: every stage refills its registers for the NEXT step right after it ran (below)
-#elif RIP_V2_SCHED == 0
-    load_a1<G, P>(A, R, s - 2, tile, tid, 0);
-    load_b<G, P>(A, R, s - 4, tile, tid);
-#else  // stage order c, a1, b, a0: the whole a1 record is in flight during stage c, the taps of stage b during stage a1
-    load_a1<G, P>(A, R, s - 2, tile, tid, 0);
-    load_a1<G, P>(A, R, s - 2, tile, tid, 1);
-#endif
-
-    // ================= stage c : row s-6 =================
-    {
-        const int row = s - 6;
-        const bool out_col = (tid >= 4 || tile == 0) && tid < TW - 4 && xin;
-        const bool c_on = row >= r0 && row < r1 && out_col;
-        if (RIP_V2_EARLY_L1 && !c_on) load_a1<G, P>(A, R, s - 2, tile, tid, 1);  // (otherwise issued below, before the ramp fit)
-        if (c_on) {
-            const long p = R.orow - 6 * (long)n + x;
-            const bool active = xact && (row >= nb && row < n - nb);
-            const int fslot = RIP_SLOT5(-6) * TW + tid;
-            const uint32_t fl = sm.flg[fslot];
-            const uint32_t nlc = sm.nlc[fslot];
-            const float gval = R.kc[2].y, readv = R.kc[2].z, dsl = R.kc[2].w, flat = R.kc[3].x;
-            const uint32_t sdq = f_as_u(R.kc[3].y);
-            float d[G];
-            if (active) {
-                const float k[9] = {R.kc[0].x, R.kc[0].y, R.kc[0].z, R.kc[0].w, R.kc[1].x, R.kc[1].y, R.kc[1].z, R.kc[1].w, R.kc[2].x};
-                SharedDiv sd;
-                sd.init(gval);
-                const f4* om = sm.O1 + (size_t)((row - 1) & (O_DEPTH - 1)) * H * RW;
-                const f4* o0 = sm.O1 + (size_t)(row & (O_DEPTH - 1)) * H * RW;
-                const f4* op = sm.O1 + (size_t)((row + 1) & (O_DEPTH - 1)) * H * RW;
-                const f4* dd = sm.D + (size_t)RIP_SLOT5(-6) * H * RW;
-                f2 t[G / 2], q[G / 2];
+    const int row = C.s - 2;
+    const bool rowin = row >= 0 && row < n && row >= r0 - 2 && row < r1 + 2;
+    f4* dst = sm.D + (size_t)RIP_SLOT5(-2) * H * RW;
+    const int fslot = RIP_SLOT5(-2) * TW + tid;
+    if (rowin && (tid >= 1 || C.tile == 0) && tid <= TW - 2 && C.xin) {
+        uint32_t grown = 0u;
 #pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    f2 lo, hi;
-                    stencil9(om + h * RW, o0 + h * RW, op + h * RW, col, k, A.negzero, lo, hi);
-                    const f4 oc = o0[h * RW + col], dc = dd[h * RW + col];
-                    t[2 * h] = sub2p(add2p(f2{oc.x, oc.y}, f2{dc.x, dc.y}), lo);  // (output + image2) - ipc_fwd(output)
-                    t[2 * h + 1] = sub2p(add2p(f2{oc.z, oc.w}, f2{dc.z, dc.w}), hi);
-                }
-                bool slow = !sd.ok;
-                if (!slow) {
-                    f2 chk = f2{0.f, 0.f};
+        for (int dy = -1; dy <= 1; ++dy) {
+            const uint32_t* sr = sm.sat + (size_t)((row + dy) & (S_DEPTH - 1)) * RW + col;
+            grown |= sr[-1] | sr[0] | sr[1];
+        }
+        const uint32_t own = sm.sat[(size_t)(row & (S_DEPTH - 1)) * RW + col];
+        grown &= 0xffffu;
+        uint32_t satm = grown;
+        if (grown) {
+            for (int b = 1; b <= A.sat_backup; ++b) satm |= grown >> b;
+        }
+        satm &= allg & ~1u;
+        const uint32_t adf = own >> 16;
+        const bool active = C.xact && (row >= nb && row < n - nb);
+        float S[G];
+        {
+            const uint16_t* rq = sm.rawq + (size_t)RIP_SLOT5(-2) * G * TW + tid;
 #pragma unroll
-                    for (int j = 0; j < G / 2; ++j) { q[j] = sd.div2(t[j]); chk = add2p(chk, q[j]); }
-                    const float tt = chk.x + chk.y;
-                    slow = !(tt == tt);  // a NaN from the correction steps (infinite numerator) -> true division
-                }
-                if (slow) {
+            for (int g = 0; g < G; ++g) S[g] = u16_to_f32(rq[g * TW]);
+        }
+        if (A.do_refpix) {  // gen_cal_image.py:535-556: f64 subtractions, f32 stores
+            const int chsel = ((x >> 7) != ((C.tile * TS) >> 7)) ? 1 : 0;
+            const double* rc = sm.rc + (size_t)RIP_SLOT5(-2) * G;
+            const double* ln = sm.ln + (size_t)(RIP_SLOT5(-2) * 2 + chsel) * G;
 #pragma unroll
-                    for (int j = 0; j < G / 2; ++j) q[j] = f2{t[j].x / gval, t[j].y / gval};
-                }
-#pragma unroll
-                for (int j = 0; j < G / 2; ++j) { d[2 * j] = q[j].x; d[2 * j + 1] = q[j].y; }
-                if (A.lincube) {
-#pragma unroll
-                    for (int g = 0; g < G; ++g) A.lincube[(long)g * npl + p] = d[g];
-                }
-            } else {
-#pragma unroll
-                for (int g = 0; g < G; ++g) d[g] = 0.0f;  // unused: every output of a non-active pixel is flag-only
-            }
-            // second half of stage a1's record: the IPC taps of this stage are dead now, the ramp fit hides the latency
-            if (RIP_V2_EARLY_L1) load_a1<G, P>(A, R, s - 2, tile, tid, 1);
-            GroupFlags gf;
-            gf.sat = fl & 0xffffu;
-            gf.adf = fl >> 16;
-            gf.dnu = gf.adf | (A.exclude_first ? 1u : 0u);
-            gf.jump = 0u;
-            gf.other_unsat = 0u;
-            uint32_t pd = (nlc & 4u) ? DQ_REFERENCE_PIXEL : 0u;
-            FitResult r;
-            if (active) {
-                r = ramp_fit_fast<G>(d, gf, pd, gval, readv, true, pl, A.w_exact);
-            } else {
-                // reference pixels / phantom border: the fit result is zeroed by the packaging step
-                // (gen_cal_image.py:470-472); only the flag propagation of ramp_fit matters (fitting.py:340-353)
-                r.slope = 0.0f; r.err_read = 0.0f; r.err_poisson = 0.0f; r.jump_mask = 0u;
-                const uint32_t unsat_g = ~gf.sat & allg;
-                uint32_t pdq2 = 0u;
-                if (gf.adf & unsat_g) pdq2 |= DQ_AD_FLOOR;
-                if ((gf.dnu & allg) == allg) pdq2 |= DQ_DO_NOT_USE;
-                if ((gf.sat >> (1 + pl.start)) & 1u) pdq2 |= DQ_DO_NOT_USE;
-                if (gf.sat & allg) pdq2 |= DQ_SATURATED;
-                if ((pd & DQ_REFERENCE_PIXEL) == 0u) pd |= pdq2;
-            }
-            const uint32_t pdq = sdq | ((nlc & 1u) ? DQ_NO_LIN_CORR : 0u) | (pd & ~DQ_REFERENCE_PIXEL);
-            float fa = flat;
-            if (A.area) {
-                if (A.area_dtype == RIP_F64) fa = (float)((double)fa / R.area64);
-                else fa = fa / R.area32;
-            }
-            l2_epilogue(r, active, dsl, fa);
-            A.slope[p] = r.slope;
-            A.err_read[p] = r.err_read;
-            A.err_poisson[p] = r.err_poisson;
-            A.pdq[p] = pdq;
-            if (A.endslice && active) {
-                // group where SATURATED first appears, minus one (gen_cal_image.py:703-708: the last 0->1 transition wins)
-                const uint32_t tr = gf.sat & ~(gf.sat << 1) & ~1u & allg;
-                int es = -1;
-                if (tr) {
-#if defined(__CUDA_ARCH__)
-                    es = 30 - __clz((int)tr);
-#else
-                    int hb = 0;
-                    for (int g = 0; g < G; ++g) if ((tr >> g) & 1u) hb = g;
-                    es = hb - 1;
-#endif
-                }
-                A.endslice[(long)(row - nb) * na + (x - nb)] = (int8_t)es;
-            }
-            if (A.rdq) {
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    uint32_t b = 0u;
-                    if ((gf.dnu >> g) & 1u) b |= DQ_DO_NOT_USE;
-                    if ((gf.sat >> g) & 1u) b |= DQ_SATURATED;
-                    if ((gf.jump >> g) & 1u) b |= DQ_JUMP_DET;
-                    if ((gf.adf >> g) & 1u) b |= DQ_AD_FLOOR;
-                    A.rdq[(long)g * npl + p] = (uint8_t)b;
-                }
+            for (int g = 0; g < G; ++g) {
+                const float dk = r1w<NQ1>(R.r1, g);
+                float v = S[g] - dk;
+                v = (float)((double)v - rc[g]);
+                v = (float)((double)v - ln[g]);
+                S[g] = v + dk;
             }
         }
-        load_c<G, P>(A, R, row + 1, tile, tid, x, xin);
-#if RIP_V2_SCHED == 2
-#elif RIP_V2_SCHED == 0
-        if (!RIP_V2_EARLY_L1) load_a1<G, P>(A, R, s - 2, tile, tid, 1);
-#else
-        load_b<G, P>(A, R, s - 4, tile, tid);
-#endif
-    }
-
-#if RIP_V2_SCHED != 1
-    // ================= stage b : row s-4 (IPC pass 1) =================
-    {
-        const int row = s - 4;
-        const bool rowok = row >= nb && row < n - nb && row >= r0 - 1 && row < r1 + 1;
-        f4* o = sm.O1 + (size_t)(row & (O_DEPTH - 1)) * H * RW;
-        if (rowok && tid >= 2 && tid <= TW - 3 && xact) {
-            const float k[9] = {R.kb[0].x, R.kb[0].y, R.kb[0].z, R.kb[0].w, R.kb[1].x, R.kb[1].y, R.kb[1].z, R.kb[1].w, R.kb8};
-            const f4* dm = sm.D + (size_t)RIP_SLOT5(-5) * H * RW;
-            const f4* d0 = sm.D + (size_t)RIP_SLOT5(-4) * H * RW;
-            const f4* dp = sm.D + (size_t)RIP_SLOT5(-3) * H * RW;
+        // biascorr (embedded with zeros outside the active region: v - 0 == v)
+        f2 S2[G / 2];
 #pragma unroll
-            for (int h = 0; h < H; ++h) {
-                f2 lo, hi;
-                stencil9(dm + h * RW, d0 + h * RW, dp + h * RW, col, k, A.negzero, lo, hi);
-                const f4 dc = d0[h * RW + col];
-                const f2 clo{dc.x, dc.y}, chi{dc.z, dc.w};
-                const f2 rlo = sub2p(add2p(clo, clo), lo), rhi = sub2p(add2p(chi, chi), hi);  // output + image2 - ipc_fwd(output)
-                o[h * RW + col] = f4{rlo.x, rlo.y, rhi.x, rhi.y};
-            }
-        } else if (row >= r0 - 1 && row < r1 + 1) {
+        for (int j = 0; j < G / 2; ++j)
+            S2[j] = sub2p(f2{S[2 * j], S[2 * j + 1]}, f2{r1w<NQ1>(R.r1, G + 2 * j), r1w<NQ1>(R.r1, G + 2 * j + 1)});
+        const float Smin = r1w<NQ1>(R.r1, 2 * G), Smax = r1w<NQ1>(R.r1, 2 * G + 1), Sref = r1w<NQ1>(R.r1, 2 * G + 2);
+        const float gain = r1w<NQ1>(R.r1, 2 * G + 3);
+        const uint32_t aux = f_as_u(r1w<NQ1>(R.r1, 2 * G + 4));
+        float c[P];
 #pragma unroll
-            for (int h = 0; h < H; ++h) o[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
+        for (int L = 0; L < P; ++L) c[L] = r1w<NQ1>(R.r1, 2 * G + 5 + L);
+        // z = -1 + (2 (S - Smin)) / (Smax - Smin)      (ipc_linearity.py:330)
+        SharedDiv sd;
+        const float den = Smax - Smin;
+        sd.init(den);
+        const bool div_ok = sd.ok && (Smin > -1.0e18f) && (Smin < 1.0e18f);
+        f2 z2[G / 2];
+#pragma unroll
+        for (int j = 0; j < G / 2; ++j) {
+            const f2 num = mul2(bc(2.0f), sub2p(S2[j], bc(Smin)));
+            f2 q;
+            if (div_ok) q = sd.div2(num);
+            else q = f2{num.x / den, num.y / den};
+            z2[j] = add2p(bc(-1.0f), q);
         }
-    }
-
-#if RIP_V2_SCHED == 2
-    load_b<G, P>(A, R, s - 3, tile, tid);
-#if RIP_V2_SCHED == 2
-    load_a1<G, P>(A, R, s - 1, tile, tid, 0);
-    load_a1<G, P>(A, R, s - 1, tile, tid, 1);
-#endif
-#else
-    load_a0<G, P>(A, R, s, x, xin);
-#endif
-    // row / channel corrections of the row stage a1 handles in the NEXT step (row s-1): fetched here, parked in
-    // shared memory at the end of the step (parity (s-1)&1)
-    double corr_next = 0.0;
-    const bool corr_thread = A.do_refpix && tid < 3 * G && (s - 1) >= 0 && (s - 1) < n;
-    if (corr_thread) {
-        const int rown = s - 1, g = tid % G, which = tid / G;
-        if (which == 0) {
-            corr_next = A.rowcorr[(long)g * n + rown];
-        } else {
-            int ch = ((tile * TS) >> 7) + (which - 1);
-            if (ch > 31) ch = 31;
-            corr_next = A.chan_m[g * 32 + ch] * (double)rown + A.chan_c[g * 32 + ch];
+        if (A.do_not_flag_first) z2[0].x = np_clip<float>(z2[0].x, -1.0f, 1.0f);
+        // |z| > 1 anywhere (or NaN) -> the extrapolating scalar evaluation of v1 for this pixel (rare).  On the bit
+        // patterns: (bits & 0x7fffffff) > bits(1.0f) is true for |z| > 1, infinities and NaNs alike.
+        uint32_t zmax = 0u;
+#pragma unroll
+        for (int j = 0; j < G / 2; ++j) {
+            const uint32_t ax = f_as_u(z2[j].x) & 0x7fffffffu, ay = f_as_u(z2[j].y) & 0x7fffffffu;
+            zmax = zmax > ax ? zmax : ax;
+            zmax = zmax > ay ? zmax : ay;
         }
-    }
-
-    // ================= stage a1 : row s-2 (flags, refpix, bias, multilin, D) =================
-    {
-        const int row = s - 2;
-        const bool rowin = row >= 0 && row < n && row >= r0 - 2 && row < r1 + 2;
-        f4* dst = sm.D + (size_t)RIP_SLOT5(-2) * H * RW;
-        const int fslot = RIP_SLOT5(-2) * TW + tid;
-        if (rowin && (tid >= 1 || tile == 0) && tid <= TW - 2 && xin) {
-            uint32_t grown = 0u;
+        const bool anyex = zmax > 0x3f800000u;
+        uint32_t dq = (aux & 1u) ? DQ_REFERENCE_PIXEL : 0u;
+        f2 phi2[G / 2];
+        if (!anyex) {
+            f2 prev[G / 2], cur[G / 2];
 #pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
-                const uint32_t* sr = sm.sat + (size_t)((row + dy) & (S_DEPTH - 1)) * RW + col;
-                grown |= sr[-1] | sr[0] | sr[1];
-            }
-            const uint32_t own = sm.sat[(size_t)(row & (S_DEPTH - 1)) * RW + col];
-            grown &= 0xffffu;
-            uint32_t satm = grown;
-            if (grown) {
-                for (int b = 1; b <= A.sat_backup; ++b) satm |= grown >> b;
-            }
-            satm &= allg & ~1u;
-            const uint32_t adf = own >> 16;
-            const bool active = xact && (row >= nb && row < n - nb);
-            float S[G];
-            {
-                const uint16_t* rq = sm.rawq + (size_t)RIP_SLOT5(-2) * G * TW + tid;
+            for (int j = 0; j < G / 2; ++j) { phi2[j] = bc(c[0]); prev[j] = bc(1.0f); cur[j] = z2[j]; }
 #pragma unroll
-                for (int g = 0; g < G; ++g) S[g] = u16_to_f32(rq[g * TW]);
-            }
-            if (A.do_refpix) {  // gen_cal_image.py:535-556: f64 subtractions, f32 stores
-                const int chsel = ((x >> 7) != ((tile * TS) >> 7)) ? 1 : 0;
-                const double* rc = sm.rc + (size_t)(row & 1) * G;
-                const double* ln = sm.ln + (size_t)((row & 1) * 2 + chsel) * G;
+            for (int L = 1; L < P; ++L) {
+                const float a = (float)((2 * L + 1) / (double)(L + 1)), b = (float)(L / (double)(L + 1));
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const float dk = r1w<NQ1>(R.r1, g);
-                    float v = S[g] - dk;
-                    v = (float)((double)v - rc[g]);
-                    v = (float)((double)v - ln[g]);
-                    S[g] = v + dk;
-                }
-            }
-            // biascorr (embedded with zeros outside the active region: v - 0 == v)
-            f2 S2[G / 2];
-#pragma unroll
-            for (int j = 0; j < G / 2; ++j)
-                S2[j] = sub2p(f2{S[2 * j], S[2 * j + 1]}, f2{r1w<NQ1>(R.r1, G + 2 * j), r1w<NQ1>(R.r1, G + 2 * j + 1)});
-            const float Smin = r1w<NQ1>(R.r1, 2 * G), Smax = r1w<NQ1>(R.r1, 2 * G + 1), Sref = r1w<NQ1>(R.r1, 2 * G + 2);
-            const float gain = r1w<NQ1>(R.r1, 2 * G + 3);
-            const uint32_t aux = f_as_u(r1w<NQ1>(R.r1, 2 * G + 4));
-            float c[P];
-#pragma unroll
-            for (int L = 0; L < P; ++L) c[L] = r1w<NQ1>(R.r1, 2 * G + 5 + L);
-            // z = -1 + (2 (S - Smin)) / (Smax - Smin)      (ipc_linearity.py:330)
-            SharedDiv sd;
-            const float den = Smax - Smin;
-            sd.init(den);
-            const bool div_ok = sd.ok && (Smin > -1.0e18f) && (Smin < 1.0e18f);
-            f2 z2[G / 2];
-#pragma unroll
-            for (int j = 0; j < G / 2; ++j) {
-                const f2 num = mul2(bc(2.0f), sub2p(S2[j], bc(Smin)));
-                f2 q;
-                if (div_ok) q = sd.div2(num);
-                else q = f2{num.x / den, num.y / den};
-                z2[j] = add2p(bc(-1.0f), q);
-            }
-            if (A.do_not_flag_first) z2[0].x = np_clip<float>(z2[0].x, -1.0f, 1.0f);
-            // |z| > 1 anywhere (or NaN) -> the extrapolating scalar evaluation of v1 for this pixel (rare)
-            bool anyex = false;
-#pragma unroll
-            for (int j = 0; j < G / 2; ++j) {
-                const float ax = z2[j].x < 0 ? -z2[j].x : z2[j].x, ay = z2[j].y < 0 ? -z2[j].y : z2[j].y;
-                anyex = anyex || !(ax <= 1.0f) || !(ay <= 1.0f);
-            }
-            uint32_t dq = (aux & 1u) ? DQ_REFERENCE_PIXEL : 0u;
-            f2 phi2[G / 2];
-            if (!anyex) {
-                f2 prev[G / 2], cur[G / 2];
-#pragma unroll
-                for (int j = 0; j < G / 2; ++j) { phi2[j] = bc(c[0]); prev[j] = bc(1.0f); cur[j] = z2[j]; }
-#pragma unroll
-                for (int L = 1; L < P; ++L) {
-                    const float a = (float)((2 * L + 1) / (double)(L + 1)), b = (float)(L / (double)(L + 1));
-#pragma unroll
-                    for (int j = 0; j < G / 2; ++j) {
-                        phi2[j] = add2p(phi2[j], mul2x(bc(c[L]), cur[j], A.negzero));
-                        if (L + 1 < P) {  // the recursion value of the last order is never used
-                            // (L = 1: prev is exactly 1, b * 1 == b)
-                            const f2 bp = (L == 1) ? bc(b) : mul2x(bc(b), prev[j], A.negzero);
-                            const f2 nxt = sub2p(mul2x(mul2(bc(a), z2[j]), cur[j], A.negzero), bp);
-                            prev[j] = cur[j];
-                            cur[j] = nxt;
-                        }
+                for (int j = 0; j < G / 2; ++j) {
+                    phi2[j] = add2p(phi2[j], mul2x(bc(c[L]), cur[j], A.negzero));
+                    if (L + 1 < P) {  // the recursion value of the last order is never used
+                        // (L = 1: prev is exactly 1, b * 1 == b)
+                        const f2 bp = (L == 1) ? bc(b) : mul2x(bc(b), prev[j], A.negzero);
+                        const f2 nxt = sub2p(mul2x(mul2(bc(a), z2[j]), cur[j], A.negzero), bp);
+                        prev[j] = cur[j];
+                        cur[j] = nxt;
                     }
                 }
-            } else {
-                ExtrapIn<G, P> ein;
-#pragma unroll
-                for (int j = 0; j < G / 2; ++j) { ein.z[2 * j] = z2[j].x; ein.z[2 * j + 1] = z2[j].y; }
-#pragma unroll
-                for (int L = 0; L < P; ++L) ein.c[L] = c[L];
-                const ExtrapOut<G> eo = phi_extrap<G, P>(ein, satm, A.do_not_flag_first != 0);
-#pragma unroll
-                for (int j = 0; j < G / 2; ++j) phi2[j] = f2{eo.phi[2 * j], eo.phi[2 * j + 1]};
-                dq |= eo.dq;
             }
-            if (aux & 1u) {  // lin dq has NO_LIN_CORR | REFERENCE_PIXEL: S - Sref instead (ipc_linearity.py:334-336)
-#pragma unroll
-                for (int j = 0; j < G / 2; ++j) phi2[j] = sub2p(S2[j], bc(Sref));
-            }
-            if (active) {
-#pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    const f2 a = mul2(phi2[2 * h], bc(gain)), b = mul2(phi2[2 * h + 1], bc(gain));
-                    dst[h * RW + col] = f4{a.x, a.y, b.x, b.y};
-                }
-            } else {
-#pragma unroll
-                for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
-                if (A.lincube && row >= r0 && row < r1 && (tid >= 4 || tile == 0) && tid < TW - 4) {
-#pragma unroll
-                    for (int g = 0; g < G; ++g)
-                        A.lincube[(long)g * npl + (long)row * n + x] = (g & 1) ? phi2[g >> 1].y : phi2[g >> 1].x;
-                }
-            }
-            sm.flg[fslot] = satm | (adf << 16);
-            sm.nlc[fslot] = (uint8_t)(((dq & DQ_NO_LIN_CORR) ? 1u : 0u) | ((aux & 2u) ? 4u : 0u));
-        } else if (row >= r0 - 2 && row < r1 + 2) {
-#pragma unroll
-            for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
-            sm.flg[fslot] = 0u;
-            sm.nlc[fslot] = 0;
-        }
-    }
-
-#else
-    load_a0<G, P>(A, R, s, x, xin);
-    // row / channel corrections of the row stage a1 handles in the NEXT step (row s-1): fetched here, parked in
-    // shared memory at the end of the step (parity (s-1)&1)
-    double corr_next = 0.0;
-    const bool corr_thread = A.do_refpix && tid < 3 * G && (s - 1) >= 0 && (s - 1) < n;
-    if (corr_thread) {
-        const int rown = s - 1, g = tid % G, which = tid / G;
-        if (which == 0) {
-            corr_next = A.rowcorr[(long)g * n + rown];
         } else {
-            int ch = ((tile * TS) >> 7) + (which - 1);
-            if (ch > 31) ch = 31;
-            corr_next = A.chan_m[g * 32 + ch] * (double)rown + A.chan_c[g * 32 + ch];
+            ExtrapIn<G, P> ein;
+#pragma unroll
+            for (int j = 0; j < G / 2; ++j) { ein.z[2 * j] = z2[j].x; ein.z[2 * j + 1] = z2[j].y; }
+#pragma unroll
+            for (int L = 0; L < P; ++L) ein.c[L] = c[L];
+            const ExtrapOut<G> eo = phi_extrap<G, P>(ein, satm, A.do_not_flag_first != 0);
+#pragma unroll
+            for (int j = 0; j < G / 2; ++j) phi2[j] = f2{eo.phi[2 * j], eo.phi[2 * j + 1]};
+            dq |= eo.dq;
         }
-    }
-
-    // ================= stage a1 : row s-2 (flags, refpix, bias, multilin, D) =================
-    {
-        const int row = s - 2;
-        const bool rowin = row >= 0 && row < n && row >= r0 - 2 && row < r1 + 2;
-        f4* dst = sm.D + (size_t)RIP_SLOT5(-2) * H * RW;
-        const int fslot = RIP_SLOT5(-2) * TW + tid;
-        if (rowin && (tid >= 1 || tile == 0) && tid <= TW - 2 && xin) {
-            uint32_t grown = 0u;
+        if (aux & 1u) {  // lin dq has NO_LIN_CORR | REFERENCE_PIXEL: S - Sref instead (ipc_linearity.py:334-336)
 #pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
-                const uint32_t* sr = sm.sat + (size_t)((row + dy) & (S_DEPTH - 1)) * RW + col;
-                grown |= sr[-1] | sr[0] | sr[1];
-            }
-            const uint32_t own = sm.sat[(size_t)(row & (S_DEPTH - 1)) * RW + col];
-            grown &= 0xffffu;
-            uint32_t satm = grown;
-            if (grown) {
-                for (int b = 1; b <= A.sat_backup; ++b) satm |= grown >> b;
-            }
-            satm &= allg & ~1u;
-            const uint32_t adf = own >> 16;
-            const bool active = xact && (row >= nb && row < n - nb);
-            float S[G];
-            {
-                const uint16_t* rq = sm.rawq + (size_t)RIP_SLOT5(-2) * G * TW + tid;
-#pragma unroll
-                for (int g = 0; g < G; ++g) S[g] = u16_to_f32(rq[g * TW]);
-            }
-            if (A.do_refpix) {  // gen_cal_image.py:535-556: f64 subtractions, f32 stores
-                const int chsel = ((x >> 7) != ((tile * TS) >> 7)) ? 1 : 0;
-                const double* rc = sm.rc + (size_t)(row & 1) * G;
-                const double* ln = sm.ln + (size_t)((row & 1) * 2 + chsel) * G;
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const float dk = r1w<NQ1>(R.r1, g);
-                    float v = S[g] - dk;
-                    v = (float)((double)v - rc[g]);
-                    v = (float)((double)v - ln[g]);
-                    S[g] = v + dk;
-                }
-            }
-            // biascorr (embedded with zeros outside the active region: v - 0 == v)
-            f2 S2[G / 2];
-#pragma unroll
-            for (int j = 0; j < G / 2; ++j)
-                S2[j] = sub2p(f2{S[2 * j], S[2 * j + 1]}, f2{r1w<NQ1>(R.r1, G + 2 * j), r1w<NQ1>(R.r1, G + 2 * j + 1)});
-            const float Smin = r1w<NQ1>(R.r1, 2 * G), Smax = r1w<NQ1>(R.r1, 2 * G + 1), Sref = r1w<NQ1>(R.r1, 2 * G + 2);
-            const float gain = r1w<NQ1>(R.r1, 2 * G + 3);
-            const uint32_t aux = f_as_u(r1w<NQ1>(R.r1, 2 * G + 4));
-            float c[P];
-#pragma unroll
-            for (int L = 0; L < P; ++L) c[L] = r1w<NQ1>(R.r1, 2 * G + 5 + L);
-            // z = -1 + (2 (S - Smin)) / (Smax - Smin)      (ipc_linearity.py:330)
-            SharedDiv sd;
-            const float den = Smax - Smin;
-            sd.init(den);
-            const bool div_ok = sd.ok && (Smin > -1.0e18f) && (Smin < 1.0e18f);
-            f2 z2[G / 2];
-#pragma unroll
-            for (int j = 0; j < G / 2; ++j) {
-                const f2 num = mul2(bc(2.0f), sub2p(S2[j], bc(Smin)));
-                f2 q;
-                if (div_ok) q = sd.div2(num);
-                else q = f2{num.x / den, num.y / den};
-                z2[j] = add2p(bc(-1.0f), q);
-            }
-            if (A.do_not_flag_first) z2[0].x = np_clip<float>(z2[0].x, -1.0f, 1.0f);
-            // |z| > 1 anywhere (or NaN) -> the extrapolating scalar evaluation of v1 for this pixel (rare)
-            bool anyex = false;
-#pragma unroll
-            for (int j = 0; j < G / 2; ++j) {
-                const float ax = z2[j].x < 0 ? -z2[j].x : z2[j].x, ay = z2[j].y < 0 ? -z2[j].y : z2[j].y;
-                anyex = anyex || !(ax <= 1.0f) || !(ay <= 1.0f);
-            }
-            uint32_t dq = (aux & 1u) ? DQ_REFERENCE_PIXEL : 0u;
-            f2 phi2[G / 2];
-            if (!anyex) {
-                f2 prev[G / 2], cur[G / 2];
-#pragma unroll
-                for (int j = 0; j < G / 2; ++j) { phi2[j] = bc(c[0]); prev[j] = bc(1.0f); cur[j] = z2[j]; }
-#pragma unroll
-                for (int L = 1; L < P; ++L) {
-                    const float a = (float)((2 * L + 1) / (double)(L + 1)), b = (float)(L / (double)(L + 1));
-#pragma unroll
-                    for (int j = 0; j < G / 2; ++j) {
-                        phi2[j] = add2p(phi2[j], mul2x(bc(c[L]), cur[j], A.negzero));
-                        if (L + 1 < P) {  // the recursion value of the last order is never used
-                            // (L = 1: prev is exactly 1, b * 1 == b)
-                            const f2 bp = (L == 1) ? bc(b) : mul2x(bc(b), prev[j], A.negzero);
-                            const f2 nxt = sub2p(mul2x(mul2(bc(a), z2[j]), cur[j], A.negzero), bp);
-                            prev[j] = cur[j];
-                            cur[j] = nxt;
-                        }
-                    }
-                }
-            } else {
-                ExtrapIn<G, P> ein;
-#pragma unroll
-                for (int j = 0; j < G / 2; ++j) { ein.z[2 * j] = z2[j].x; ein.z[2 * j + 1] = z2[j].y; }
-#pragma unroll
-                for (int L = 0; L < P; ++L) ein.c[L] = c[L];
-                const ExtrapOut<G> eo = phi_extrap<G, P>(ein, satm, A.do_not_flag_first != 0);
-#pragma unroll
-                for (int j = 0; j < G / 2; ++j) phi2[j] = f2{eo.phi[2 * j], eo.phi[2 * j + 1]};
-                dq |= eo.dq;
-            }
-            if (aux & 1u) {  // lin dq has NO_LIN_CORR | REFERENCE_PIXEL: S - Sref instead (ipc_linearity.py:334-336)
-#pragma unroll
-                for (int j = 0; j < G / 2; ++j) phi2[j] = sub2p(S2[j], bc(Sref));
-            }
-            if (active) {
-#pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    const f2 a = mul2(phi2[2 * h], bc(gain)), b = mul2(phi2[2 * h + 1], bc(gain));
-                    dst[h * RW + col] = f4{a.x, a.y, b.x, b.y};
-                }
-            } else {
-#pragma unroll
-                for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
-                if (A.lincube && row >= r0 && row < r1 && (tid >= 4 || tile == 0) && tid < TW - 4) {
-#pragma unroll
-                    for (int g = 0; g < G; ++g)
-                        A.lincube[(long)g * npl + (long)row * n + x] = (g & 1) ? phi2[g >> 1].y : phi2[g >> 1].x;
-                }
-            }
-            sm.flg[fslot] = satm | (adf << 16);
-            sm.nlc[fslot] = (uint8_t)(((dq & DQ_NO_LIN_CORR) ? 1u : 0u) | ((aux & 2u) ? 4u : 0u));
-        } else if (row >= r0 - 2 && row < r1 + 2) {
-#pragma unroll
-            for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
-            sm.flg[fslot] = 0u;
-            sm.nlc[fslot] = 0;
+            for (int j = 0; j < G / 2; ++j) phi2[j] = sub2p(S2[j], bc(Sref));
         }
-    }
-
-    // ================= stage b : row s-4 (IPC pass 1) =================
-    {
-        const int row = s - 4;
-        const bool rowok = row >= nb && row < n - nb && row >= r0 - 1 && row < r1 + 1;
-        f4* o = sm.O1 + (size_t)(row & (O_DEPTH - 1)) * H * RW;
-        if (rowok && tid >= 2 && tid <= TW - 3 && xact) {
-            const float k[9] = {R.kb[0].x, R.kb[0].y, R.kb[0].z, R.kb[0].w, R.kb[1].x, R.kb[1].y, R.kb[1].z, R.kb[1].w, R.kb8};
-            const f4* dm = sm.D + (size_t)RIP_SLOT5(-5) * H * RW;
-            const f4* d0 = sm.D + (size_t)RIP_SLOT5(-4) * H * RW;
-            const f4* dp = sm.D + (size_t)RIP_SLOT5(-3) * H * RW;
+        if (active) {
 #pragma unroll
             for (int h = 0; h < H; ++h) {
-                f2 lo, hi;
-                stencil9(dm + h * RW, d0 + h * RW, dp + h * RW, col, k, A.negzero, lo, hi);
-                const f4 dc = d0[h * RW + col];
-                const f2 clo{dc.x, dc.y}, chi{dc.z, dc.w};
-                const f2 rlo = sub2p(add2p(clo, clo), lo), rhi = sub2p(add2p(chi, chi), hi);  // output + image2 - ipc_fwd(output)
-                o[h * RW + col] = f4{rlo.x, rlo.y, rhi.x, rhi.y};
+                const f2 a = mul2(phi2[2 * h], bc(gain)), b = mul2(phi2[2 * h + 1], bc(gain));
+                dst[h * RW + col] = f4{a.x, a.y, b.x, b.y};
             }
-        } else if (row >= r0 - 1 && row < r1 + 1) {
+        } else {
 #pragma unroll
-            for (int h = 0; h < H; ++h) o[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
-        }
-    }
-
-#endif
-    // ================= stage a0 : row s (raw -> cumulative saturation / A-D floor bits) ===========
-    {
-        const int row = s;
-        uint32_t bits = 0u;
-        const bool rowin = row >= 0 && row < n && row >= r0 - 3 && row < r1 + 3;
-        if (rowin && xin) {
-            const uint16_t* rq = sm.rawq + (size_t)RIP_SLOT5(0) * G * TW + tid;
-            const float thr = R.thr;
-            uint32_t rv[G];
+            for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
+            if (A.lincube && row >= r0 && row < r1 && (tid >= 4 || C.tile == 0) && tid < TW - 4) {
+                const unsigned npl = (unsigned)n * (unsigned)n;
 #pragma unroll
-            for (int g = 0; g < G; ++g) rv[g] = rq[g * TW];
-            // fast exit: no group (>= 1; saturation_check skips the first resultant, gen_cal_image.py:174-180) reaches
-            // the threshold or the A/D floor
-            uint32_t mx = rv[1], mn = rv[1];
-#pragma unroll
-            for (int g = 2; g < G; ++g) { mx = mx > rv[g] ? mx : rv[g]; mn = mn < rv[g] ? mn : rv[g]; }
-            if (!(u16_to_f32(mx) < thr) || mn == 0u) {  // (NaN thresholds were replaced by +inf when the CALDIR was loaded)
-                bool cum = false;
-#pragma unroll
-                for (int g = 1; g < G; ++g) {
-                    const float fv = u16_to_f32(rv[g]);
-                    cum = cum || (fv >= thr);
-                    if (cum) bits |= 1u << g;
-                    if (fv <= 0.0f) bits |= 1u << (16 + g);
-                }
+                for (int g = 0; g < G; ++g)
+                    A.lincube[(unsigned)g * npl + (unsigned)row * (unsigned)n + (unsigned)x] = (g & 1) ? phi2[g >> 1].y : phi2[g >> 1].x;
             }
         }
-        sm.sat[(size_t)(row & (S_DEPTH - 1)) * RW + col] = bits;
-        if (corr_thread) {
-            const int rown = s - 1, g = tid % G, which = tid / G;
-            if (which == 0) sm.rc[(size_t)(rown & 1) * G + g] = corr_next;
-            else sm.ln[(size_t)((rown & 1) * 2 + (which - 1)) * G + g] = corr_next;
-        }
+        sm.flg[fslot] = satm | (adf << 16);
+        sm.nlc[fslot] = (uint8_t)(((dq & DQ_NO_LIN_CORR) ? 1u : 0u) | ((aux & 2u) ? 4u : 0u));
+    } else if (row >= r0 - 2 && row < r1 + 2) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
+        sm.flg[fslot] = 0u;
+        sm.nlc[fslot] = 0;
     }
-#if RIP_V2_SCHED == 2
-    load_a0<G, P>(A, R, s + 1, x, xin);
-#endif
-    advance_pointers<G, P>(A, R);
-    cp_async_wait<1>();  // the raw row issued in the previous step (row s+1) has landed; the caller's barrier publishes it
 }
 
-// prologue: pointers, raw rows of the first two steps, the registers stage c needs in the first step, ring pads
+// stage b : row s-4 (IPC pass 1:  O1 = (D + D) - K (*) D)
+template <int G, int P>
+RIP_HD void stage_b(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const StepCtx& C) {
+    constexpr int H = G / 4;
+    const int n = C.n, nb = 4, tid = C.tid, col = C.col, r0 = C.r0, r1 = C.r1;
+    const int (&sl5)[5] = C.sl5;
+    const int row = C.s - 4;
+    const bool rowok = row >= nb && row < n - nb && row >= r0 - 1 && row < r1 + 1;
+    f4* o = sm.O1 + (size_t)(row & (O_DEPTH - 1)) * H * RW;
+    if (rowok && tid >= 2 && tid <= TW - 3 && C.xact) {
+        const float k[9] = {R.kb[0].x, R.kb[0].y, R.kb[0].z, R.kb[0].w, R.kb[1].x, R.kb[1].y, R.kb[1].z, R.kb[1].w, R.kb8};
+        const f4* dm = sm.D + (size_t)RIP_SLOT5(-5) * H * RW;
+        const f4* d0 = sm.D + (size_t)RIP_SLOT5(-4) * H * RW;
+        const f4* dp = sm.D + (size_t)RIP_SLOT5(-3) * H * RW;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            f2 lo, hi;
+            stencil9(dm + h * RW, d0 + h * RW, dp + h * RW, col, k, A.negzero, lo, hi);
+            const f4 dc = d0[h * RW + col];
+            const f2 clo{dc.x, dc.y}, chi{dc.z, dc.w};
+            const f2 rlo = sub2p(add2p(clo, clo), lo), rhi = sub2p(add2p(chi, chi), hi);  // output + image2 - ipc_fwd(output)
+            o[h * RW + col] = f4{rlo.x, rlo.y, rhi.x, rhi.y};
+        }
+    } else if (row >= r0 - 1 && row < r1 + 1) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) o[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
+    }
+}
+
+// stage c : row s-6 (IPC pass 2, /gain; ramp fit, jump flags, DQ propagation; dark, error split, flat/area; stores)
+template <int G, int P>
+RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G>& sm, const Regs<G, P>& R, const StepCtx& C) {
+    constexpr int H = G / 4;
+    const int n = C.n, nb = 4, na = n - 8, tid = C.tid, col = C.col, x = C.x, r0 = C.r0, r1 = C.r1;
+    const int (&sl5)[5] = C.sl5;
+    const uint32_t allg = (1u << G) - 1u;
+    const unsigned npl = (unsigned)n * (unsigned)n;
+    const int row = C.s - 6;
+    const bool out_col = (tid >= 4 || C.tile == 0) && tid < TW - 4 && C.xin;
+    const bool c_on = row >= r0 && row < r1 && out_col;
+    if (!c_on) return;
+    const unsigned p = R.orow - 6u * (unsigned)n + (unsigned)x;
+    const bool active = C.xact && (row >= nb && row < n - nb);
+    const int fslot = RIP_SLOT5(-6) * TW + tid;
+    const uint32_t fl = sm.flg[fslot];
+    const uint32_t nlc = sm.nlc[fslot];
+    const float gval = R.kc[2].y, readv = R.kc[2].z, dsl = R.kc[2].w, flat = R.kc[3].x;
+    const uint32_t sdq = f_as_u(R.kc[3].y);
+    f2 q[G / 2];
+    if (active) {
+        const float k[9] = {R.kc[0].x, R.kc[0].y, R.kc[0].z, R.kc[0].w, R.kc[1].x, R.kc[1].y, R.kc[1].z, R.kc[1].w, R.kc[2].x};
+        SharedDiv sd;
+        sd.init(gval);
+        const f4* om = sm.O1 + (size_t)((row - 1) & (O_DEPTH - 1)) * H * RW;
+        const f4* o0 = sm.O1 + (size_t)(row & (O_DEPTH - 1)) * H * RW;
+        const f4* op = sm.O1 + (size_t)((row + 1) & (O_DEPTH - 1)) * H * RW;
+        const f4* dd = sm.D + (size_t)RIP_SLOT5(-6) * H * RW;
+        f2 t[G / 2];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            f2 lo, hi;
+            stencil9(om + h * RW, o0 + h * RW, op + h * RW, col, k, A.negzero, lo, hi);
+            const f4 oc = o0[h * RW + col], dc = dd[h * RW + col];
+            t[2 * h] = sub2p(add2p(f2{oc.x, oc.y}, f2{dc.x, dc.y}), lo);  // (output + image2) - ipc_fwd(output)
+            t[2 * h + 1] = sub2p(add2p(f2{oc.z, oc.w}, f2{dc.z, dc.w}), hi);
+        }
+        bool slow = !sd.ok;
+        if (!slow) {
+            f2 chk = f2{0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < G / 2; ++j) { q[j] = sd.div2(t[j]); chk = add2p(chk, q[j]); }
+            const float tt = chk.x + chk.y;
+            slow = !(tt == tt);  // a NaN from the correction steps (infinite numerator) -> true division
+        }
+        if (slow) {
+#pragma unroll
+            for (int j = 0; j < G / 2; ++j) q[j] = f2{t[j].x / gval, t[j].y / gval};
+        }
+        if (A.lincube) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) A.lincube[(unsigned)g * npl + p] = (g & 1) ? q[g >> 1].y : q[g >> 1].x;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < G / 2; ++j) q[j] = f2{0.f, 0.f};  // unused: every output of a non-active pixel is flag-only
+    }
+    GroupFlags gf;
+    gf.sat = fl & 0xffffu;
+    gf.adf = fl >> 16;
+    gf.dnu = gf.adf | (A.exclude_first ? 1u : 0u);
+    gf.jump = 0u;
+    gf.other_unsat = 0u;
+    uint32_t pd = (nlc & 4u) ? DQ_REFERENCE_PIXEL : 0u;
+    FitResult r;
+    if (active) {
+        r = ramp_fit_fast<G>(q, gf, pd, gval, readv, pl, ft, A.w_exact);
+    } else {
+        // reference pixels / phantom border: the fit result is zeroed by the packaging step
+        // (gen_cal_image.py:470-472); only the flag propagation of ramp_fit matters (fitting.py:340-353)
+        r.slope = 0.0f; r.err_read = 0.0f; r.err_poisson = 0.0f; r.jump_mask = 0u;
+        const uint32_t unsat_g = ~gf.sat & allg;
+        uint32_t pdq2 = 0u;
+        if (gf.adf & unsat_g) pdq2 |= DQ_AD_FLOOR;
+        if ((gf.dnu & allg) == allg) pdq2 |= DQ_DO_NOT_USE;
+        if ((gf.sat >> (1 + pl.start)) & 1u) pdq2 |= DQ_DO_NOT_USE;
+        if (gf.sat & allg) pdq2 |= DQ_SATURATED;
+        if ((pd & DQ_REFERENCE_PIXEL) == 0u) pd |= pdq2;
+    }
+    const uint32_t pdq = sdq | ((nlc & 1u) ? DQ_NO_LIN_CORR : 0u) | (pd & ~DQ_REFERENCE_PIXEL);
+    float fa = flat;
+    if (A.area) {
+        if (A.area_dtype == RIP_F64) fa = (float)((double)fa / R.area64);
+        else fa = fa / R.area32;
+    }
+    l2_epilogue(r, active, dsl, fa);
+    A.slope[p] = r.slope;
+    A.err_read[p] = r.err_read;
+    A.err_poisson[p] = r.err_poisson;
+    A.pdq[p] = pdq;
+    if (A.endslice && active) {
+        // group where SATURATED first appears, minus one (gen_cal_image.py:703-708: the last 0->1 transition wins)
+        const uint32_t tr = gf.sat & ~(gf.sat << 1) & ~1u & allg;
+        int es = -1;
+        if (tr) {
+#if defined(__CUDA_ARCH__)
+            es = 30 - __clz((int)tr);
+#else
+            int hb = 0;
+            for (int g = 0; g < G; ++g) if ((tr >> g) & 1u) hb = g;
+            es = hb - 1;
+#endif
+        }
+        A.endslice[(unsigned)(row - nb) * (unsigned)na + (unsigned)(x - nb)] = (int8_t)es;
+    }
+    if (A.rdq) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            uint32_t b = 0u;
+            if ((gf.dnu >> g) & 1u) b |= DQ_DO_NOT_USE;
+            if ((gf.sat >> g) & 1u) b |= DQ_SATURATED;
+            if ((gf.jump >> g) & 1u) b |= DQ_JUMP_DET;
+            if ((gf.adf >> g) & 1u) b |= DQ_AD_FLOOR;
+            A.rdq[(unsigned)g * npl + p] = (uint8_t)b;
+        }
+    }
+}
+
+// stage a0 : row s (raw -> cumulative saturation / A-D floor bits)
+template <int G, int P>
+RIP_HD void stage_a0(const Args& A, Smem<G>& sm, const StepCtx& C) {
+    const int n = C.n, tid = C.tid, col = C.col, r0 = C.r0, r1 = C.r1;
+    const int (&sl5)[5] = C.sl5;
+    const int row = C.s;
+    uint32_t bits = 0u;
+    const bool rowin = row >= 0 && row < n && row >= r0 - 3 && row < r1 + 3;
+    if (rowin && C.xin) {
+        const uint16_t* rq = sm.rawq + (size_t)RIP_SLOT5(0) * G * TW + tid;
+        const float thr = sm.thrq[RIP_SLOT5(0) * TW + tid];
+        uint32_t rv[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) rv[g] = rq[g * TW];
+        // fast exit: no group (>= 1; saturation_check skips the first resultant, gen_cal_image.py:174-180) reaches
+        // the threshold or the A/D floor
+        uint32_t mx = rv[1], mn = rv[1];
+#pragma unroll
+        for (int g = 2; g < G; ++g) { mx = mx > rv[g] ? mx : rv[g]; mn = mn < rv[g] ? mn : rv[g]; }
+        if (!(u16_to_f32(mx) < thr) || mn == 0u) {  // (NaN thresholds were replaced by +inf when the CALDIR was loaded)
+            bool cum = false;
+#pragma unroll
+            for (int g = 1; g < G; ++g) {
+                const float fv = u16_to_f32(rv[g]);
+                cum = cum || (fv >= thr);
+                if (cum) bits |= 1u << g;
+                if (fv <= 0.0f) bits |= 1u << (16 + g);
+            }
+        }
+    }
+    sm.sat[(size_t)(row & (S_DEPTH - 1)) * RW + col] = bits;
+}
+
+// ---- one march step --------------------------------------------------------------------------------------------
+// Stage rows: a0 row s, a1 row s-2, b row s-4, c row s-6; every stage only reads ring slots written in earlier steps,
+// so one barrier per step suffices and the stages may run in any order.  Order and load placement (see Regs):
+//     [kb <- kbn: the one scoreboard wait]  [cp.async row s+2; Lb(next)]  a1  c  [Lc(next), L1(next)]  b  a0  barrier
+// f5 = s mod RING, carried by the caller.
+template <int G, int P>
+RIP_HD void step(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G>& sm, Regs<G, P>& R, const int tid,
+                 const int tile, const int r0, const int r1, const int s, const int f5) {
+    StepCtx C;
+    C.n = A.n; C.tid = tid; C.tile = tile; C.r0 = r0; C.r1 = r1; C.s = s;
+    C.x = tile * TS + tid;
+    C.col = tid + 1;
+    C.xin = C.x < A.n;
+    C.xact = (C.x >= 4 && C.x < A.n - 4);
+    C.sl5[0] = f5; C.sl5[1] = wrap5(f5 + 1); C.sl5[2] = wrap5(f5 + 2); C.sl5[3] = wrap5(f5 + 3); C.sl5[4] = wrap5(f5 + 4);
+    const int (&sl5)[5] = C.sl5;
+
+    R.kb[0] = R.kbn[0]; R.kb[1] = R.kbn[1]; R.kb8 = R.kbn8;
+    row_async<G, P>(A, sm, R, s + 2, 2, RIP_SLOT5(2), tile, tid, r0 - 3, r1 + 3);
+    load_bn<G, P>(A, R, s - 3, tile, tid);
+
+    stage_a1<G, P>(A, sm, R, C);
+    stage_c<G, P>(A, pl, ft, sm, R, C);
+    load_c<G, P>(A, R, s - 5, tile, tid, C.x, C.xin);
+    load_a1<G, P>(A, R, s - 1, tile, tid);
+    stage_b<G, P>(A, sm, R, C);
+    stage_a0<G, P>(A, sm, C);
+
+    R.orow += (unsigned)A.n;
+    cp_async_wait<1>();  // the rows issued in the previous step (row s+1) have landed; the caller's barrier publishes them
+}
+
+// prologue: offsets, the cp.async rows of the first two steps, the records the first step consumes, ring pads
 template <int G, int P>
 RIP_HD void prologue(const Args& A, Smem<G>& sm, Regs<G, P>& R, int tid, int tile, int r0, int r1) {
     const int x = tile * TS + tid;
     const bool xin = x < A.n;
     const int s0 = r0 - 3;
-    const int f5 = mod_pos(s0, F_DEPTH);
-    init_pointers<G, P>(A, R, tile, s0);
-    raw_row_async<G, P>(A, sm, R, s0, 0, f5, tile, tid, r0 - 3, r1 + 3);
-    raw_row_async<G, P>(A, sm, R, s0 + 1, 1, wrap5(f5 + 1), tile, tid, r0 - 3, r1 + 3);
+    const int f5 = mod_pos(s0, RING);
+    R.orow = (unsigned)(s0 * A.n);  // (mod 2^32 for s0 < 0: only ever used after adding back a non-negative row offset)
+    row_async<G, P>(A, sm, R, s0, 0, f5, tile, tid, r0 - 3, r1 + 3);
+    row_async<G, P>(A, sm, R, s0 + 1, 1, wrap5(f5 + 1), tile, tid, r0 - 3, r1 + 3);
     load_c<G, P>(A, R, s0 - 6, tile, tid, x, xin);
-#if RIP_V2_SCHED == 2
-    load_b<G, P>(A, R, s0 - 4, tile, tid);
-    load_a1<G, P>(A, R, s0 - 2, tile, tid, 0);
-    load_a1<G, P>(A, R, s0 - 2, tile, tid, 1);
-    load_a0<G, P>(A, R, s0, x, xin);
-#endif
+    load_a1<G, P>(A, R, s0 - 2, tile, tid);
+    load_bn<G, P>(A, R, s0 - 4, tile, tid);
     // ring pads and the slots stage a1 / b read before anything was written there
     for (int i = tid; i < S_DEPTH * RW; i += TW) sm.sat[i] = 0u;
-    for (int i = tid; i < (D_DEPTH + O_DEPTH) * Smem<G>::H * RW; i += TW) sm.D[i] = f4{0.f, 0.f, 0.f, 0.f};
+    for (int i = tid; i < (RING + O_DEPTH) * Smem<G>::H * RW; i += TW) sm.D[i] = f4{0.f, 0.f, 0.f, 0.f};
     cp_async_wait<0>();
 }
 
@@ -1086,9 +1017,9 @@ RIP_HD float u_as_f(uint32_t u) {
 #endif
 }
 
-// word w of rec1 at detector pixel (row, x); x >= n -> 0
+// word w of rec1 at detector pixel (row, x); x >= n or a padding row -> 0
 RIP_HD float rec1_word(const PackSrc& S, int row, int x, int w) {
-    if (x >= S.n) return 0.0f;
+    if (x >= S.n || row < 0 || row >= S.n) return 0.0f;
     const long npl = (long)S.n * S.n, p = (long)row * S.n + x;
     const int G = S.G, na = S.n - 2 * S.nb;
     if (w < G) return S.dark[(long)w * npl + p];
@@ -1112,7 +1043,7 @@ RIP_HD float rec1_word(const PackSrc& S, int row, int x, int w) {
 // the source pixel is outside the active area or (row, x) is not active), 9 gain, 10 read, 11 dark slope (IPC
 // corrected), 12 flat, 13 static dq bits, 14..15 zero.
 RIP_HD float recK_word(const PackSrc& S, int row, int x, int w) {
-    if (x >= S.n) return 0.0f;
+    if (x >= S.n || row < 0 || row >= S.n) return 0.0f;
     const long p = (long)row * S.n + x;
     const int na = S.n - 2 * S.nb;
     if (w < 9) {

@@ -35,7 +35,8 @@ class V2Args(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("n", "ntile", "band_rows", "do_refpix", "do_not_flag_first", "exclude_first",
                                        "sat_backup", "area_dtype")] + [("negzero", C.c_float), ("pad_", C.c_int)] + \
                [(k, C.c_void_p) for k in ("raw", "area", "rowcorr", "chan_m", "chan_c", "rec1", "recK", "thr", "w_exact",
-                                          "slope", "err_read", "err_poisson", "pdq", "endslice", "rdq", "lincube")]  # fmt: skip
+                                          "slope", "err_read", "err_poisson", "pdq", "endslice", "rdq", "lincube",
+                                          "chan_line")]  # fmt: skip
 
 
 class PackSrc(C.Structure):

@@ -67,21 +67,36 @@ template <int G, int P>
 static void run_v2_t(rip::v2::Args A, const rip::v2::PackSrc& S, const rip_ramp_plan& pl) {
     using namespace rip::v2;
     const int n = A.n, ntile = ntiles(n), nq = nq1(G, P);
-    std::vector<f4> rec1((size_t)n * ntile * nq * TW), recK((size_t)n * ntile * KQ * TW);
-    for (int row = 0; row < n; ++row)
+    // records with PADR zero rows on both sides, as v2_pack lays them out (rip_v2.cu)
+    const int nrow = n + 2 * PADR;
+    std::vector<f4> rec1((size_t)nrow * ntile * nq * TW), recK((size_t)nrow * ntile * KQ * TW);
+    for (int prow = 0; prow < nrow; ++prow)
         for (int tile = 0; tile < ntile; ++tile)
             for (int c = 0; c < TW; ++c) {
-                const int x = tile * TS + c;
+                const int x = tile * TS + c, row = prow - PADR;
                 for (int q = 0; q < nq; ++q)
-                    rec1[((size_t)(row * ntile + tile) * nq + q) * TW + c] =
+                    rec1[((size_t)(prow * ntile + tile) * nq + q) * TW + c] =
                         f4{rec1_word(S, row, x, 4 * q), rec1_word(S, row, x, 4 * q + 1), rec1_word(S, row, x, 4 * q + 2), rec1_word(S, row, x, 4 * q + 3)};
                 for (int q = 0; q < KQ; ++q)
-                    recK[((size_t)(row * ntile + tile) * KQ + q) * TW + c] =
+                    recK[((size_t)(prow * ntile + tile) * KQ + q) * TW + c] =
                         f4{recK_word(S, row, x, 4 * q), recK_word(S, row, x, 4 * q + 1), recK_word(S, row, x, 4 * q + 2), recK_word(S, row, x, 4 * q + 3)};
             }
     A.ntile = ntile;
-    A.rec1 = rec1.data();
-    A.recK = recK.data();
+    A.rec1 = rec1.data() + (size_t)PADR * ntile * nq * TW;
+    A.recK = recK.data() + (size_t)PADR * ntile * KQ * TW;
+    // the tabulated channel lines K0 (k0_chan_kernel) hands to the kernel: m * row + c in f64, unfused
+    std::vector<double> line;
+    if (A.do_refpix) {
+        line.resize((size_t)G * 32 * n);
+        for (int g = 0; g < G; ++g)
+            for (int ch = 0; ch < 32; ++ch)
+                for (int row = 0; row < n; ++row) {
+                    const double prod = A.chan_m[g * 32 + ch] * (double)row;
+                    line[((size_t)g * 32 + ch) * n + row] = prod + A.chan_c[g * 32 + ch];
+                }
+        A.chan_line = line.data();
+    }
+    const FastTab ft = make_fast_tab(pl);
     const size_t smem = Smem<G>::bytes();
     std::vector<unsigned char> buf(smem + 64);
     std::vector<Regs<G, P>> regs(TW);
@@ -97,7 +112,7 @@ static void run_v2_t(rip::v2::Args A, const rip::v2::PackSrc& S, const rip_ramp_
             const int r0 = by * A.band_rows, r1 = (r0 + A.band_rows < n) ? r0 + A.band_rows : n;
             for (int tid = 0; tid < TW; ++tid) prologue<G, P>(A, sm, regs[tid], tid, tile, r0, r1);
             for (int s = r0 - 3; s <= r1 + 5; ++s)
-                for (int tid = 0; tid < TW; ++tid) step<G, P>(A, pl, sm, regs[tid], tid, tile, r0, r1, s, mod_pos(s, rip::v2::F_DEPTH));
+                for (int tid = 0; tid < TW; ++tid) step<G, P>(A, pl, ft, sm, regs[tid], tid, tile, r0, r1, s, mod_pos(s, rip::v2::RING));
         }
 }
 
