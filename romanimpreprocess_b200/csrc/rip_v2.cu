@@ -54,11 +54,19 @@ __global__ void __launch_bounds__(TW, MINB) cal_fused_v2_kernel(const Args A) {
     const int r1 = min(r0 + A.band_rows, A.n);
     prologue<G, P>(A, sm, R, tid, tile, r0, r1);
     __syncthreads();
-    int f5 = mod_pos(r0 - 3, RING);
-    for (int s = r0 - 3; s <= r1 + 5; ++s) {
-        step<G, P>(A, c_plan_v2, c_fast_v2, sm, R, tid, tile, r0, r1, s, f5);
-        f5 = (f5 == RING - 1) ? 0 : f5 + 1;
-        __syncthreads();
+    unsigned o5s = first_o5<G>(r0);
+    if (interior(A.n, tile, r0, r1)) {
+        for (int s = r0 - 3; s <= r1 + 5; ++s) {
+            step<G, P, true>(A, c_plan_v2, c_fast_v2, sm, R, tid, tile, r0, r1, s, o5s);
+            o5s = next_o5<G>(o5s);
+            __syncthreads();
+        }
+    } else {
+        for (int s = r0 - 3; s <= r1 + 5; ++s) {
+            step<G, P, false>(A, c_plan_v2, c_fast_v2, sm, R, tid, tile, r0, r1, s, o5s);
+            o5s = next_o5<G>(o5s);
+            __syncthreads();
+        }
     }
 }
 
@@ -77,16 +85,9 @@ static void launch_tb(const Args& A, cudaStream_t st) {
 }
 
 // resident CTAs per SM the kernel is compiled for: 4 (128 registers/thread) for G <= 8, 3 for G = 16 (larger rings);
-// RIP_V2_MINB=3|4 overrides for experiments
 template <int G, int P>
 static void launch_t(const Args& A, cudaStream_t st) {
-    static const int minb = [] {
-        const char* e = getenv("RIP_V2_MINB");
-        const int v = e ? atoi(e) : 0;
-        return (v == 3 || v == 4) ? v : ((G <= 8) ? 4 : 3);
-    }();
-    if (minb == 4 && G <= 8) launch_tb<G, P, 4>(A, st);
-    else launch_tb<G, P, 3>(A, st);
+    launch_tb<G, P, (G <= 8) ? 4 : 3>(A, st);
 }
 
 }  // namespace v2

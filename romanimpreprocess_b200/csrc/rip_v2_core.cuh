@@ -85,6 +85,23 @@ inline float rcp_approx(float d) { return 1.0f / d; }
 #endif
 RIP_HD f2 bc(float a) { return f2{a, a}; }
 
+// np.maximum / np.minimum against a non-NaN, non-negative-zero bound (NaN in x propagates): one instruction on the device
+RIP_HD float max_nan(float x, float bound) {
+#if defined(__CUDA_ARCH__)
+    float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(bound)); return r;
+#else
+    return np_max<float>(x, bound);
+#endif
+}
+RIP_HD float min_nan(float x, float bound) {
+#if defined(__CUDA_ARCH__)
+    float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(bound)); return r;
+#else
+    return np_min<float>(x, bound);
+#endif
+}
+RIP_HD float clip_nan(float x, float lo, float hi) { return min_nan(max_nan(x, lo), hi); }
+
 // Correctly rounded x/d for several numerators sharing one denominator (Newton-refined reciprocal + two
 // FMA-residual corrections: the classic IEEE division sequence).  `ok` = denominator in the range where no
 // intermediate can over/underflow for |x| < 2^40; otherwise the caller uses true division.
@@ -143,34 +160,43 @@ struct Args {
     const double* chan_line; // [G,32,n]  chan_m * row + chan_c (f64, unfused), tabulated by K0
 };
 
+// Shared memory: two rings of per-row records, so that one byte offset per ring slot addresses everything of a row.
+//   ring5 (depth RING, slot = row mod 5): D f4[G/4][RW] | raw u16[G][TW] | thr f32[TW] | flg u32[TW] | rc f64[G] |
+//                                         ln f64[2][G] | nlc u8[TW]
+//   ring4 (depth 4, slot = row & 3):      O1 f4[G/4][RW] | sat u32[RW]
+// raw / thr / rc / ln are filled by cp.async two steps ahead (rows s-2 .. s+2 live); flg (satm | adf<<16) and nlc
+// (bit0 dynamic NO_LIN_CORR, bit2 reference pixel) are thread-private delay lines a1 -> c.
 template <int G>
 struct Smem {
-    f4* D;            // [RING][G/4][RW]
-    f4* O1;           // [O_DEPTH][G/4][RW]
-    uint16_t* rawq;   // [RING][G][TW]      raw resultants, filled by cp.async two steps ahead (rows s-2 .. s+2 live)
-    float* thrq;      // [RING][TW]         saturation thresholds, same cp.async group as the raw row
-    double* rc;       // [RING][G]          row correction of the row,            〃
-    double* ln;       // [RING][2][G]       channel line for the two channels the tile touches, 〃
-    uint32_t* sat;    // [S_DEPTH][RW]
-    uint32_t* flg;    // [RING][TW]         satm | adf<<16                 thread-private delay line a1 -> c
-    uint8_t* nlc;     // [RING][TW]         bit0 dynamic NO_LIN_CORR, bit2 reference pixel
     static constexpr int H = G / 4;
-    RIP_HD static size_t bytes() {
-        return sizeof(f4) * (size_t)(RING + O_DEPTH) * H * RW + 2 * (size_t)RING * G * TW + 4 * (size_t)RING * TW +
-               8 * (size_t)RING * 3 * G + 4 * (size_t)S_DEPTH * RW + 5 * (size_t)RING * TW + 64;
-    }
+    static constexpr int OFF_D = 0;
+    static constexpr int OFF_RAW = OFF_D + 16 * H * RW;
+    static constexpr int OFF_THR = OFF_RAW + 2 * G * TW;
+    static constexpr int OFF_FLG = OFF_THR + 4 * TW;
+    static constexpr int OFF_RC = OFF_FLG + 4 * TW;
+    static constexpr int OFF_LN = OFF_RC + 8 * G;
+    static constexpr int OFF_NLC = OFF_LN + 16 * G;
+    static constexpr int ROW5 = (OFF_NLC + TW + 15) / 16 * 16;
+    static constexpr int OFF_O1 = 0;
+    static constexpr int OFF_SAT = 16 * H * RW;
+    static constexpr int ROW4 = (OFF_SAT + 4 * RW + 15) / 16 * 16;
+    unsigned char* r5;
+    unsigned char* r4;
+    RIP_HD static size_t bytes() { return (size_t)RING * ROW5 + (size_t)O_DEPTH * ROW4 + 64; }
     RIP_HD void carve(unsigned char* base) {
-        size_t off = 0;
-        D = (f4*)(base + off); off += sizeof(f4) * (size_t)RING * H * RW;
-        O1 = (f4*)(base + off); off += sizeof(f4) * (size_t)O_DEPTH * H * RW;
-        rawq = (uint16_t*)(base + off); off += 2 * (size_t)RING * G * TW;
-        thrq = (float*)(base + off); off += 4 * (size_t)RING * TW;
-        rc = (double*)(base + off); off += 8 * (size_t)RING * G;
-        ln = (double*)(base + off); off += 8 * (size_t)RING * 2 * G;
-        sat = (uint32_t*)(base + off); off += 4 * (size_t)S_DEPTH * RW;
-        flg = (uint32_t*)(base + off); off += 4 * (size_t)RING * TW;
-        nlc = (uint8_t*)(base + off);
+        r5 = base;
+        r4 = base + (size_t)RING * ROW5;
     }
+    // o5 = byte offset of a ring5 slot, o4 = byte offset of a ring4 slot
+    RIP_HD f4* D(unsigned o5) const { return (f4*)(r5 + o5 + OFF_D); }
+    RIP_HD uint16_t* raw(unsigned o5) const { return (uint16_t*)(r5 + o5 + OFF_RAW); }
+    RIP_HD float* thr(unsigned o5) const { return (float*)(r5 + o5 + OFF_THR); }
+    RIP_HD uint32_t* flg(unsigned o5) const { return (uint32_t*)(r5 + o5 + OFF_FLG); }
+    RIP_HD double* rc(unsigned o5) const { return (double*)(r5 + o5 + OFF_RC); }
+    RIP_HD double* ln(unsigned o5) const { return (double*)(r5 + o5 + OFF_LN); }
+    RIP_HD uint8_t* nlc(unsigned o5) const { return (uint8_t*)(r5 + o5 + OFF_NLC); }
+    RIP_HD f4* O1(int row) const { return (f4*)(r4 + (unsigned)(row & (O_DEPTH - 1)) * ROW4 + OFF_O1); }
+    RIP_HD uint32_t* sat(int row) const { return (uint32_t*)(r4 + (unsigned)(row & (S_DEPTH - 1)) * ROW4 + OFF_SAT); }
 };
 
 // Registers a thread carries from one march step to the next: the calibration records of each stage, loaded one step
@@ -192,9 +218,10 @@ struct Regs {
 };
 
 RIP_HD int mod_pos(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
-RIP_HD int wrap5(int a) { return a >= RING ? a - RING : a; }  // a in [0, 2*RING)
-// slot of row s+DK in a depth-5 ring, given f5 = s mod 5 (DK is a compile-time constant)
-#define RIP_SLOT5(DK) sl5[(((DK) % 5) + 5) % 5]
+// byte offset of ring5 slot (f + k) mod 5 given o = f * ROW5: one add + one unsigned min (x - 5 ROW5 wraps above x when x < 5 ROW5)
+RIP_HD unsigned wrap5(unsigned x, unsigned ring_bytes) { const unsigned y = x - ring_bytes; return x < y ? x : y; }
+// byte offset of the ring5 slot of row s+DK, given o5[k] = offset of row s+k (DK is a compile-time constant)
+#define RIP_O5(DK) o5[(((DK) % 5) + 5) % 5]
 
 // ---- asynchronous global -> shared copies (LDGSTS); the host build copies at once ---------------------------
 template <int BYTES>
@@ -225,29 +252,29 @@ RIP_HD void cp_async_wait() {
 //   the saturation threshold of the thread's own column (4 bytes);
 //   row correction [G] and the two channel lines [2][G] of the row (threads 0 .. 3G-1, 8 bytes each).
 // Every thread commits one group per step (possibly empty) so that wait_group counts steps.
-template <int G, int P>
-RIP_HD void row_async(const Args& A, Smem<G>& sm, const Regs<G, P>& R, int row, int row_off, int slot, int tile, int tid,
+template <int G, int P, bool IN>
+RIP_HD void row_async(const Args& A, Smem<G>& sm, const Regs<G, P>& R, int row, int row_off, unsigned slot_o5, int tile, int tid,
                       int lo, int hi) {  // row_off: rows relative to row s (R.orow)
-    if (row >= 0 && row < A.n && row >= lo && row < hi) {
+    if ((IN || (row >= 0 && row < A.n)) && row >= lo && row < hi) {
         const unsigned npl = (unsigned)A.n * (unsigned)A.n;
         const unsigned obase = R.orow + (unsigned)(row_off * A.n) + (unsigned)(tile * TS);  // uniform
         const int c = tid & 15, g0 = tid >> 4;
-        if (tile * TS + 8 * c + 8 <= A.n) {
+        if (IN || tile * TS + 8 * c + 8 <= A.n) {
 #pragma unroll
             for (int k = 0; k < G / 8; ++k)
-                cp_async<16>(sm.rawq + ((size_t)slot * G + g0 + 8 * k) * TW + 8 * c,
+                cp_async<16>(sm.raw(slot_o5) + (g0 + 8 * k) * TW + 8 * c,
                              A.raw + (obase + (unsigned)(g0 + 8 * k) * npl + (unsigned)(8 * c)));
         }
         const int x = tile * TS + tid;
-        cp_async<4>(sm.thrq + slot * TW + tid, A.thr + (obase + (unsigned)(x < A.n ? tid : -tile * TS)));
+        cp_async<4>(sm.thr(slot_o5) + tid, A.thr + (obase + (unsigned)((IN || x < A.n) ? tid : -tile * TS)));
         if (A.do_refpix && tid < 3 * G) {
             const int g = tid % G, which = tid / G;
             if (which == 0) {
-                cp_async<8>(sm.rc + slot * G + g, A.rowcorr + ((unsigned)(g * A.n) + (unsigned)row));
+                cp_async<8>(sm.rc(slot_o5) + g, A.rowcorr + ((unsigned)(g * A.n) + (unsigned)row));
             } else {
                 int ch = ((tile * TS) >> 7) + (which - 1);
                 if (ch > 31) ch = 31;
-                cp_async<8>(sm.ln + (slot * 2 + (which - 1)) * G + g, A.chan_line + ((unsigned)((g * 32 + ch) * A.n) + (unsigned)row));
+                cp_async<8>(sm.ln(slot_o5) + (which - 1) * G + g, A.chan_line + ((unsigned)((g * 32 + ch) * A.n) + (unsigned)row));
             }
         }
     }
@@ -365,7 +392,7 @@ struct ThrBand {
     bool ok;
 };
 RIP_HD ThrBand thr_band(float slope, const RampPlanDev& pl) {
-    const float x = np_clip<float>(slope, pl.IthreshA_f, pl.IthreshB_f);
+    const float x = clip_nan(slope, pl.IthreshA_f, pl.IthreshB_f);
 #if defined(__CUDA_ARCH__)
     const float thr = pl.thrA_f + pl.thrK_f * __logf(x * pl.invIA_f);
 #else
@@ -507,9 +534,9 @@ RIP_HD FitResult jump_full(const f2 (&q)[G / 2], float gain, float read, const R
         acc = acc + pr.y;
     }
     r.slope = acc;
-    const float gc = np_clip<float>(gain, 1e-4f, 1e4f);
-    const float dvardt = np_max<float>(r.slope / gc, 0.0f);
-    r.err_poisson = sqrtf(np_max<float>(pl.var_coef[0] * dvardt, 0.0f));
+    const float gc = clip_nan(gain, 1e-4f, 1e4f);
+    const float dvardt = max_nan(r.slope / gc, 0.0f);
+    r.err_poisson = sqrtf(max_nan(pl.var_coef[0] * dvardt, 0.0f));
     r.err_read = read * pl.var_rfac[0];
     const float sig2read = read * read;
     const ThrBand tb = thr_band(r.slope, pl);
@@ -613,28 +640,27 @@ RIP_HD_COLD ExtrapOut<G> phi_extrap(const ExtrapIn<G, P> in, uint32_t satm, bool
 struct StepCtx {  // what every stage derives from (tile, tid, band, step); all cheap / CTA-uniform
     int n, tid, tile, x, col, r0, r1, s;
     bool xin, xact;
-    int sl5[5];  // slots of rows s, s+1, .. s+4 (== s-5 .. s-1) in the depth-5 rings
+    unsigned o5[5];  // byte offsets of the ring5 slots of rows s, s+1, .. s+4 (== s-5 .. s-1)
 };
 
 // stage a1 : row s-2 (saturation growth, refpix, bias, multilin, D = lin * gain)
-template <int G, int P>
+template <int G, int P, bool IN>
 RIP_HD void stage_a1(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const StepCtx& C) {
     constexpr int H = G / 4, NQ1 = Regs<G, P>::NQ1;
     const int n = C.n, nb = 4, tid = C.tid, col = C.col, x = C.x, r0 = C.r0, r1 = C.r1;
-    const int (&sl5)[5] = C.sl5;
+    const unsigned (&o5)[5] = C.o5;
     const uint32_t allg = (1u << G) - 1u;
     const int row = C.s - 2;
-    const bool rowin = row >= 0 && row < n && row >= r0 - 2 && row < r1 + 2;
-    f4* dst = sm.D + (size_t)RIP_SLOT5(-2) * H * RW;
-    const int fslot = RIP_SLOT5(-2) * TW + tid;
-    if (rowin && (tid >= 1 || C.tile == 0) && tid <= TW - 2 && C.xin) {
+    const bool rowin = (IN || (row >= 0 && row < n)) && row >= r0 - 2 && row < r1 + 2;
+    f4* dst = sm.D(RIP_O5(-2));
+    if (rowin && (tid >= 1 || (!IN && C.tile == 0)) && tid <= TW - 2 && C.xin) {
         uint32_t grown = 0u;
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
-            const uint32_t* sr = sm.sat + (size_t)((row + dy) & (S_DEPTH - 1)) * RW + col;
+            const uint32_t* sr = sm.sat(row + dy) + col;
             grown |= sr[-1] | sr[0] | sr[1];
         }
-        const uint32_t own = sm.sat[(size_t)(row & (S_DEPTH - 1)) * RW + col];
+        const uint32_t own = sm.sat(row)[col];
         grown &= 0xffffu;
         uint32_t satm = grown;
         if (grown) {
@@ -642,17 +668,17 @@ RIP_HD void stage_a1(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const Step
         }
         satm &= allg & ~1u;
         const uint32_t adf = own >> 16;
-        const bool active = C.xact && (row >= nb && row < n - nb);
+        const bool active = IN || (C.xact && (row >= nb && row < n - nb));
         float S[G];
         {
-            const uint16_t* rq = sm.rawq + (size_t)RIP_SLOT5(-2) * G * TW + tid;
+            const uint16_t* rq = sm.raw(RIP_O5(-2)) + tid;
 #pragma unroll
             for (int g = 0; g < G; ++g) S[g] = u16_to_f32(rq[g * TW]);
         }
         if (A.do_refpix) {  // gen_cal_image.py:535-556: f64 subtractions, f32 stores
             const int chsel = ((x >> 7) != ((C.tile * TS) >> 7)) ? 1 : 0;
-            const double* rc = sm.rc + (size_t)RIP_SLOT5(-2) * G;
-            const double* ln = sm.ln + (size_t)(RIP_SLOT5(-2) * 2 + chsel) * G;
+            const double* rc = sm.rc(RIP_O5(-2));
+            const double* ln = sm.ln(RIP_O5(-2)) + chsel * G;
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 const float dk = r1w<NQ1>(R.r1, g);
@@ -743,37 +769,37 @@ RIP_HD void stage_a1(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const Step
         } else {
 #pragma unroll
             for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
-            if (A.lincube && row >= r0 && row < r1 && (tid >= 4 || C.tile == 0) && tid < TW - 4) {
+            if (A.lincube && row >= r0 && row < r1 && (tid >= 4 || (!IN && C.tile == 0)) && tid < TW - 4) {
                 const unsigned npl = (unsigned)n * (unsigned)n;
 #pragma unroll
                 for (int g = 0; g < G; ++g)
                     A.lincube[(unsigned)g * npl + (unsigned)row * (unsigned)n + (unsigned)x] = (g & 1) ? phi2[g >> 1].y : phi2[g >> 1].x;
             }
         }
-        sm.flg[fslot] = satm | (adf << 16);
-        sm.nlc[fslot] = (uint8_t)(((dq & DQ_NO_LIN_CORR) ? 1u : 0u) | ((aux & 2u) ? 4u : 0u));
+        sm.flg(RIP_O5(-2))[tid] = satm | (adf << 16);
+        sm.nlc(RIP_O5(-2))[tid] = (uint8_t)(((dq & DQ_NO_LIN_CORR) ? 1u : 0u) | ((aux & 2u) ? 4u : 0u));
     } else if (row >= r0 - 2 && row < r1 + 2) {
 #pragma unroll
         for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
-        sm.flg[fslot] = 0u;
-        sm.nlc[fslot] = 0;
+        sm.flg(RIP_O5(-2))[tid] = 0u;
+        sm.nlc(RIP_O5(-2))[tid] = 0;
     }
 }
 
 // stage b : row s-4 (IPC pass 1:  O1 = (D + D) - K (*) D)
-template <int G, int P>
+template <int G, int P, bool IN>
 RIP_HD void stage_b(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const StepCtx& C) {
     constexpr int H = G / 4;
     const int n = C.n, nb = 4, tid = C.tid, col = C.col, r0 = C.r0, r1 = C.r1;
-    const int (&sl5)[5] = C.sl5;
+    const unsigned (&o5)[5] = C.o5;
     const int row = C.s - 4;
-    const bool rowok = row >= nb && row < n - nb && row >= r0 - 1 && row < r1 + 1;
-    f4* o = sm.O1 + (size_t)(row & (O_DEPTH - 1)) * H * RW;
+    const bool rowok = (IN || (row >= nb && row < n - nb)) && row >= r0 - 1 && row < r1 + 1;
+    f4* o = sm.O1(row);
     if (rowok && tid >= 2 && tid <= TW - 3 && C.xact) {
         const float k[9] = {R.kb[0].x, R.kb[0].y, R.kb[0].z, R.kb[0].w, R.kb[1].x, R.kb[1].y, R.kb[1].z, R.kb[1].w, R.kb8};
-        const f4* dm = sm.D + (size_t)RIP_SLOT5(-5) * H * RW;
-        const f4* d0 = sm.D + (size_t)RIP_SLOT5(-4) * H * RW;
-        const f4* dp = sm.D + (size_t)RIP_SLOT5(-3) * H * RW;
+        const f4* dm = sm.D(RIP_O5(-5));
+        const f4* d0 = sm.D(RIP_O5(-4));
+        const f4* dp = sm.D(RIP_O5(-3));
 #pragma unroll
         for (int h = 0; h < H; ++h) {
             f2 lo, hi;
@@ -790,22 +816,21 @@ RIP_HD void stage_b(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const StepC
 }
 
 // stage c : row s-6 (IPC pass 2, /gain; ramp fit, jump flags, DQ propagation; dark, error split, flat/area; stores)
-template <int G, int P>
+template <int G, int P, bool IN>
 RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G>& sm, const Regs<G, P>& R, const StepCtx& C) {
     constexpr int H = G / 4;
     const int n = C.n, nb = 4, na = n - 8, tid = C.tid, col = C.col, x = C.x, r0 = C.r0, r1 = C.r1;
-    const int (&sl5)[5] = C.sl5;
+    const unsigned (&o5)[5] = C.o5;
     const uint32_t allg = (1u << G) - 1u;
     const unsigned npl = (unsigned)n * (unsigned)n;
     const int row = C.s - 6;
-    const bool out_col = (tid >= 4 || C.tile == 0) && tid < TW - 4 && C.xin;
+    const bool out_col = (tid >= 4 || (!IN && C.tile == 0)) && tid < TW - 4 && C.xin;
     const bool c_on = row >= r0 && row < r1 && out_col;
     if (!c_on) return;
     const unsigned p = R.orow - 6u * (unsigned)n + (unsigned)x;
-    const bool active = C.xact && (row >= nb && row < n - nb);
-    const int fslot = RIP_SLOT5(-6) * TW + tid;
-    const uint32_t fl = sm.flg[fslot];
-    const uint32_t nlc = sm.nlc[fslot];
+    const bool active = IN || (C.xact && (row >= nb && row < n - nb));
+    const uint32_t fl = sm.flg(RIP_O5(-6))[tid];
+    const uint32_t nlc = sm.nlc(RIP_O5(-6))[tid];
     const float gval = R.kc[2].y, readv = R.kc[2].z, dsl = R.kc[2].w, flat = R.kc[3].x;
     const uint32_t sdq = f_as_u(R.kc[3].y);
     f2 q[G / 2];
@@ -813,10 +838,10 @@ RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, Sme
         const float k[9] = {R.kc[0].x, R.kc[0].y, R.kc[0].z, R.kc[0].w, R.kc[1].x, R.kc[1].y, R.kc[1].z, R.kc[1].w, R.kc[2].x};
         SharedDiv sd;
         sd.init(gval);
-        const f4* om = sm.O1 + (size_t)((row - 1) & (O_DEPTH - 1)) * H * RW;
-        const f4* o0 = sm.O1 + (size_t)(row & (O_DEPTH - 1)) * H * RW;
-        const f4* op = sm.O1 + (size_t)((row + 1) & (O_DEPTH - 1)) * H * RW;
-        const f4* dd = sm.D + (size_t)RIP_SLOT5(-6) * H * RW;
+        const f4* om = sm.O1(row - 1);
+        const f4* o0 = sm.O1(row);
+        const f4* op = sm.O1(row + 1);
+        const f4* dd = sm.D(RIP_O5(-6));
         f2 t[G / 2];
 #pragma unroll
         for (int h = 0; h < H; ++h) {
@@ -908,16 +933,16 @@ RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, Sme
 }
 
 // stage a0 : row s (raw -> cumulative saturation / A-D floor bits)
-template <int G, int P>
+template <int G, int P, bool IN>
 RIP_HD void stage_a0(const Args& A, Smem<G>& sm, const StepCtx& C) {
     const int n = C.n, tid = C.tid, col = C.col, r0 = C.r0, r1 = C.r1;
-    const int (&sl5)[5] = C.sl5;
+    const unsigned (&o5)[5] = C.o5;
     const int row = C.s;
     uint32_t bits = 0u;
-    const bool rowin = row >= 0 && row < n && row >= r0 - 3 && row < r1 + 3;
+    const bool rowin = (IN || (row >= 0 && row < n)) && row >= r0 - 3 && row < r1 + 3;
     if (rowin && C.xin) {
-        const uint16_t* rq = sm.rawq + (size_t)RIP_SLOT5(0) * G * TW + tid;
-        const float thr = sm.thrq[RIP_SLOT5(0) * TW + tid];
+        const uint16_t* rq = sm.raw(RIP_O5(0)) + tid;
+        const float thr = sm.thr(RIP_O5(0))[tid];
         uint32_t rv[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) rv[g] = rq[g * TW];
@@ -937,36 +962,43 @@ RIP_HD void stage_a0(const Args& A, Smem<G>& sm, const StepCtx& C) {
             }
         }
     }
-    sm.sat[(size_t)(row & (S_DEPTH - 1)) * RW + col] = bits;
+    sm.sat(row)[col] = bits;
 }
+
+// IN ("interior") = the CTA touches no frame edge: every pixel of the tile is an active pixel and every row it reads
+// exists, so the frame-edge predicates and the flag-only paths of reference pixels compile away (91 % of the CTAs of a
+// 4096^2 frame).  interior() is the (CTA-uniform) condition.
+RIP_HD bool interior(int n, int tile, int r0, int r1) { return tile >= 1 && tile * TS + TW <= n - 4 && r0 >= 6 && r1 <= n - 6; }
 
 // ---- one march step --------------------------------------------------------------------------------------------
 // Stage rows: a0 row s, a1 row s-2, b row s-4, c row s-6; every stage only reads ring slots written in earlier steps,
 // so one barrier per step suffices and the stages may run in any order.  Order and load placement (see Regs):
 //     [kb <- kbn: the one scoreboard wait]  [cp.async row s+2; Lb(next)]  a1  c  [Lc(next), L1(next)]  b  a0  barrier
-// f5 = s mod RING, carried by the caller.
-template <int G, int P>
+// o5s = (s mod RING) * ROW5, the byte offset of row s's ring5 slot, carried by the caller (next_o5).
+template <int G, int P, bool IN>
 RIP_HD void step(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G>& sm, Regs<G, P>& R, const int tid,
-                 const int tile, const int r0, const int r1, const int s, const int f5) {
+                 const int tile, const int r0, const int r1, const int s, const unsigned o5s) {
     StepCtx C;
     C.n = A.n; C.tid = tid; C.tile = tile; C.r0 = r0; C.r1 = r1; C.s = s;
     C.x = tile * TS + tid;
     C.col = tid + 1;
-    C.xin = C.x < A.n;
-    C.xact = (C.x >= 4 && C.x < A.n - 4);
-    C.sl5[0] = f5; C.sl5[1] = wrap5(f5 + 1); C.sl5[2] = wrap5(f5 + 2); C.sl5[3] = wrap5(f5 + 3); C.sl5[4] = wrap5(f5 + 4);
-    const int (&sl5)[5] = C.sl5;
+    C.xin = IN || C.x < A.n;
+    C.xact = IN || (C.x >= 4 && C.x < A.n - 4);
+    constexpr unsigned RB = Smem<G>::ROW5, RING_B = RING * Smem<G>::ROW5;
+    C.o5[0] = o5s; C.o5[1] = wrap5(o5s + RB, RING_B); C.o5[2] = wrap5(o5s + 2 * RB, RING_B);
+    C.o5[3] = wrap5(o5s + 3 * RB, RING_B); C.o5[4] = wrap5(o5s + 4 * RB, RING_B);
+    const unsigned (&o5)[5] = C.o5;
 
     R.kb[0] = R.kbn[0]; R.kb[1] = R.kbn[1]; R.kb8 = R.kbn8;
-    row_async<G, P>(A, sm, R, s + 2, 2, RIP_SLOT5(2), tile, tid, r0 - 3, r1 + 3);
+    row_async<G, P, IN>(A, sm, R, s + 2, 2, RIP_O5(2), tile, tid, r0 - 3, r1 + 3);
     load_bn<G, P>(A, R, s - 3, tile, tid);
 
-    stage_a1<G, P>(A, sm, R, C);
-    stage_c<G, P>(A, pl, ft, sm, R, C);
+    stage_a1<G, P, IN>(A, sm, R, C);
+    stage_c<G, P, IN>(A, pl, ft, sm, R, C);
     load_c<G, P>(A, R, s - 5, tile, tid, C.x, C.xin);
     load_a1<G, P>(A, R, s - 1, tile, tid);
-    stage_b<G, P>(A, sm, R, C);
-    stage_a0<G, P>(A, sm, C);
+    stage_b<G, P, IN>(A, sm, R, C);
+    stage_a0<G, P, IN>(A, sm, C);
 
     R.orow += (unsigned)A.n;
     cp_async_wait<1>();  // the rows issued in the previous step (row s+1) have landed; the caller's barrier publishes them
@@ -978,18 +1010,27 @@ RIP_HD void prologue(const Args& A, Smem<G>& sm, Regs<G, P>& R, int tid, int til
     const int x = tile * TS + tid;
     const bool xin = x < A.n;
     const int s0 = r0 - 3;
-    const int f5 = mod_pos(s0, RING);
+    constexpr unsigned RB = Smem<G>::ROW5, RING_B = RING * Smem<G>::ROW5;
+    const unsigned o5s = (unsigned)mod_pos(s0, RING) * RB;
     R.orow = (unsigned)(s0 * A.n);  // (mod 2^32 for s0 < 0: only ever used after adding back a non-negative row offset)
-    row_async<G, P>(A, sm, R, s0, 0, f5, tile, tid, r0 - 3, r1 + 3);
-    row_async<G, P>(A, sm, R, s0 + 1, 1, wrap5(f5 + 1), tile, tid, r0 - 3, r1 + 3);
+    row_async<G, P, false>(A, sm, R, s0, 0, o5s, tile, tid, r0 - 3, r1 + 3);
+    row_async<G, P, false>(A, sm, R, s0 + 1, 1, wrap5(o5s + RB, RING_B), tile, tid, r0 - 3, r1 + 3);
     load_c<G, P>(A, R, s0 - 6, tile, tid, x, xin);
     load_a1<G, P>(A, R, s0 - 2, tile, tid);
     load_bn<G, P>(A, R, s0 - 4, tile, tid);
     // ring pads and the slots stage a1 / b read before anything was written there
-    for (int i = tid; i < S_DEPTH * RW; i += TW) sm.sat[i] = 0u;
-    for (int i = tid; i < (RING + O_DEPTH) * Smem<G>::H * RW; i += TW) sm.D[i] = f4{0.f, 0.f, 0.f, 0.f};
+    // (D of every ring5 slot and the whole ring4; never the cp.async targets)
+    for (int k = 0; k < RING; ++k)
+        for (int i = tid; i < Smem<G>::H * RW; i += TW) sm.D((unsigned)k * RB)[i] = f4{0.f, 0.f, 0.f, 0.f};
+    for (int i = tid; i < O_DEPTH * Smem<G>::ROW4 / 16; i += TW) ((f4*)sm.r4)[i] = f4{0.f, 0.f, 0.f, 0.f};
     cp_async_wait<0>();
 }
+
+// ring5 offset of the next row (the march loop's carried variable)
+template <int G>
+RIP_HD unsigned next_o5(unsigned o5s) { return (o5s == (RING - 1) * Smem<G>::ROW5) ? 0u : o5s + Smem<G>::ROW5; }
+template <int G>
+RIP_HD unsigned first_o5(int r0) { return (unsigned)mod_pos(r0 - 3, RING) * Smem<G>::ROW5; }
 
 // ---- packed calibration records (built once per CALDIR and group count) -------------------------------------
 struct PackSrc {
