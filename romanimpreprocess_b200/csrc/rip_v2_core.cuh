@@ -140,7 +140,7 @@ struct Args {
     int n, ntile, band_rows;
     int do_refpix, do_not_flag_first, exclude_first, sat_backup, area_dtype;
     float negzero;           // -0.0f, deliberately a run-time value (see mul2x)
-    int pad_;
+    int pad_;                // 0, deliberately a run-time value (see step: load ordering)
     const uint16_t* raw;     // [G,n,n]
     const void* area;        // [n,n] f32|f64 or null
     const double* rowcorr;   // [G,n]
@@ -255,7 +255,7 @@ RIP_HD void cp_async_wait() {
 template <int G, int P, bool IN>
 RIP_HD void row_async(const Args& A, Smem<G>& sm, const Regs<G, P>& R, int row, int row_off, unsigned slot_o5, int tile, int tid,
                       int lo, int hi) {  // row_off: rows relative to row s (R.orow)
-    if ((IN || (row >= 0 && row < A.n)) && row >= lo && row < hi) {
+    if (IN || (row >= 0 && row < A.n && row >= lo && row < hi)) {
         const unsigned npl = (unsigned)A.n * (unsigned)A.n;
         const unsigned obase = R.orow + (unsigned)(row_off * A.n) + (unsigned)(tile * TS);  // uniform
         const int c = tid & 15, g0 = tid >> 4;
@@ -291,8 +291,10 @@ RIP_HD void load_a1(const Args& A, Regs<G, P>& R, int row, int tile, int tid) {
     for (int q = 0; q < Regs<G, P>::NQ1; ++q) R.r1[q] = p[q * TW + tid];
 }
 template <int G, int P>
-RIP_HD void load_bn(const Args& A, Regs<G, P>& R, int row, int tile, int tid) {
-    const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW);
+RIP_HD void load_bn(const Args& A, Regs<G, P>& R, int row, int tile, int tid, unsigned dep) {
+    // dep: a run-time zero derived from a register of the loads in flight (see step): the address depends on it, so
+    // these loads cannot be issued before the step's single scoreboard wait
+    const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW) + dep;
     R.kbn[0] = p[tid];
     R.kbn[1] = p[TW + tid];
     R.kbn8 = ((const float*)(p + 2 * TW))[4 * tid];  // .x of the third word
@@ -651,9 +653,9 @@ RIP_HD void stage_a1(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const Step
     const unsigned (&o5)[5] = C.o5;
     const uint32_t allg = (1u << G) - 1u;
     const int row = C.s - 2;
-    const bool rowin = (IN || (row >= 0 && row < n)) && row >= r0 - 2 && row < r1 + 2;
+    const bool rowin = IN || (row >= 0 && row < n && row >= r0 - 2 && row < r1 + 2);
     f4* dst = sm.D(RIP_O5(-2));
-    if (rowin && (tid >= 1 || (!IN && C.tile == 0)) && tid <= TW - 2 && C.xin) {
+    if (rowin && (IN || ((tid >= 1 || C.tile == 0) && tid <= TW - 2 && C.xin))) {  // (IN: the two edge columns compute unused values)
         uint32_t grown = 0u;
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
@@ -778,7 +780,7 @@ RIP_HD void stage_a1(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const Step
         }
         sm.flg(RIP_O5(-2))[tid] = satm | (adf << 16);
         sm.nlc(RIP_O5(-2))[tid] = (uint8_t)(((dq & DQ_NO_LIN_CORR) ? 1u : 0u) | ((aux & 2u) ? 4u : 0u));
-    } else if (row >= r0 - 2 && row < r1 + 2) {
+    } else if (!IN && row >= r0 - 2 && row < r1 + 2) {
 #pragma unroll
         for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
         sm.flg(RIP_O5(-2))[tid] = 0u;
@@ -793,9 +795,9 @@ RIP_HD void stage_b(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const StepC
     const int n = C.n, nb = 4, tid = C.tid, col = C.col, r0 = C.r0, r1 = C.r1;
     const unsigned (&o5)[5] = C.o5;
     const int row = C.s - 4;
-    const bool rowok = (IN || (row >= nb && row < n - nb)) && row >= r0 - 1 && row < r1 + 1;
+    const bool rowok = IN || (row >= nb && row < n - nb && row >= r0 - 1 && row < r1 + 1);
     f4* o = sm.O1(row);
-    if (rowok && tid >= 2 && tid <= TW - 3 && C.xact) {
+    if (rowok && (IN || (tid >= 2 && tid <= TW - 3 && C.xact))) {  // (IN: edge columns compute unused values)
         const float k[9] = {R.kb[0].x, R.kb[0].y, R.kb[0].z, R.kb[0].w, R.kb[1].x, R.kb[1].y, R.kb[1].z, R.kb[1].w, R.kb8};
         const f4* dm = sm.D(RIP_O5(-5));
         const f4* d0 = sm.D(RIP_O5(-4));
@@ -809,7 +811,7 @@ RIP_HD void stage_b(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const StepC
             const f2 rlo = sub2p(add2p(clo, clo), lo), rhi = sub2p(add2p(chi, chi), hi);  // output + image2 - ipc_fwd(output)
             o[h * RW + col] = f4{rlo.x, rlo.y, rhi.x, rhi.y};
         }
-    } else if (row >= r0 - 1 && row < r1 + 1) {
+    } else if (!IN && row >= r0 - 1 && row < r1 + 1) {
 #pragma unroll
         for (int h = 0; h < H; ++h) o[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
     }
@@ -825,7 +827,7 @@ RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, Sme
     const unsigned npl = (unsigned)n * (unsigned)n;
     const int row = C.s - 6;
     const bool out_col = (tid >= 4 || (!IN && C.tile == 0)) && tid < TW - 4 && C.xin;
-    const bool c_on = row >= r0 && row < r1 && out_col;
+    const bool c_on = (IN || (row >= r0 && row < r1)) && out_col;
     if (!c_on) return;
     const unsigned p = R.orow - 6u * (unsigned)n + (unsigned)x;
     const bool active = IN || (C.xact && (row >= nb && row < n - nb));
@@ -939,7 +941,7 @@ RIP_HD void stage_a0(const Args& A, Smem<G>& sm, const StepCtx& C) {
     const unsigned (&o5)[5] = C.o5;
     const int row = C.s;
     uint32_t bits = 0u;
-    const bool rowin = (IN || (row >= 0 && row < n)) && row >= r0 - 3 && row < r1 + 3;
+    const bool rowin = IN || (row >= 0 && row < n && row >= r0 - 3 && row < r1 + 3);
     if (rowin && C.xin) {
         const uint16_t* rq = sm.raw(RIP_O5(0)) + tid;
         const float thr = sm.thr(RIP_O5(0))[tid];
@@ -965,10 +967,13 @@ RIP_HD void stage_a0(const Args& A, Smem<G>& sm, const StepCtx& C) {
     sm.sat(row)[col] = bits;
 }
 
-// IN ("interior") = the CTA touches no frame edge: every pixel of the tile is an active pixel and every row it reads
-// exists, so the frame-edge predicates and the flag-only paths of reference pixels compile away (91 % of the CTAs of a
-// 4096^2 frame).  interior() is the (CTA-uniform) condition.
+// IN = "interior, steady state": the CTA touches no frame edge (every pixel of the tile is an active pixel, every row
+// it reads exists: interior()) AND the step is one where all four stages have a row of the band to work on
+// (steady()).  All row / frame predicates then compile away and the stages form one straight-line block, which ptxas
+// schedules across stage boundaries; the generic form (IN = false) runs the edge CTAs and the ramp-up / ramp-down
+// steps of every band.  91 % of the CTAs of a 4096^2 frame are interior and 59 of their 73 steps are steady.
 RIP_HD bool interior(int n, int tile, int r0, int r1) { return tile >= 1 && tile * TS + TW <= n - 4 && r0 >= 6 && r1 <= n - 6; }
+RIP_HD bool steady(int s, int r0, int r1) { return s >= r0 + 6 && s <= r1; }
 
 // ---- one march step --------------------------------------------------------------------------------------------
 // Stage rows: a0 row s, a1 row s-2, b row s-4, c row s-6; every stage only reads ring slots written in earlier steps,
@@ -989,9 +994,12 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G
     C.o5[3] = wrap5(o5s + 3 * RB, RING_B); C.o5[4] = wrap5(o5s + 4 * RB, RING_B);
     const unsigned (&o5)[5] = C.o5;
 
+    // The one scoreboard wait of the step: `dep` is zero at run time (Args::pad_), but ptxas cannot know, so the loads
+    // of load_bn -- and with them everything below -- are ordered after the arrival of all loads in flight.
+    const unsigned dep = f_as_u(R.kc[0].x) & (unsigned)A.pad_;
     R.kb[0] = R.kbn[0]; R.kb[1] = R.kbn[1]; R.kb8 = R.kbn8;
     row_async<G, P, IN>(A, sm, R, s + 2, 2, RIP_O5(2), tile, tid, r0 - 3, r1 + 3);
-    load_bn<G, P>(A, R, s - 3, tile, tid);
+    load_bn<G, P>(A, R, s - 3, tile, tid, dep);
 
     stage_a1<G, P, IN>(A, sm, R, C);
     stage_c<G, P, IN>(A, pl, ft, sm, R, C);
@@ -1017,7 +1025,7 @@ RIP_HD void prologue(const Args& A, Smem<G>& sm, Regs<G, P>& R, int tid, int til
     row_async<G, P, false>(A, sm, R, s0 + 1, 1, wrap5(o5s + RB, RING_B), tile, tid, r0 - 3, r1 + 3);
     load_c<G, P>(A, R, s0 - 6, tile, tid, x, xin);
     load_a1<G, P>(A, R, s0 - 2, tile, tid);
-    load_bn<G, P>(A, R, s0 - 4, tile, tid);
+    load_bn<G, P>(A, R, s0 - 4, tile, tid, 0u);
     // ring pads and the slots stage a1 / b read before anything was written there
     // (D of every ring5 slot and the whole ring4; never the cp.async targets)
     for (int k = 0; k < RING; ++k)
