@@ -55,10 +55,8 @@ __global__ void __launch_bounds__(TW, MINB) cal_fused_v2_kernel(const Args A) {
     prologue<G, P>(A, sm, R, tid, tile, r0, r1);
     __syncthreads();
     unsigned o5s = first_o5<G>(r0);
-    const bool in = interior(A.n, tile, r0, r1);
     for (int s = r0 - 3; s <= r1 + 5; ++s) {
-        if (in && steady(s, r0, r1)) step<G, P, true>(A, c_plan_v2, c_fast_v2, sm, R, tid, tile, r0, r1, s, o5s);
-        else step<G, P, false>(A, c_plan_v2, c_fast_v2, sm, R, tid, tile, r0, r1, s, o5s);
+        step<G, P>(A, c_plan_v2, c_fast_v2, sm, R, tid, tile, r0, r1, s, o5s);
         o5s = next_o5<G>(o5s);
         __syncthreads();
     }

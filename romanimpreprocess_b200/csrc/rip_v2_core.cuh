@@ -218,6 +218,10 @@ struct Regs {
 };
 
 RIP_HD int mod_pos(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
+// lo <= v < hi in two instructions (lo <= hi)
+RIP_HD bool in_range(int v, int lo, int hi) { return (unsigned)(v - lo) < (unsigned)(hi - lo); }
+RIP_HD int imax(int a, int b) { return a > b ? a : b; }
+RIP_HD int imin(int a, int b) { return a < b ? a : b; }
 // byte offset of ring5 slot (f + k) mod 5 given o = f * ROW5: one add + one unsigned min (x - 5 ROW5 wraps above x when x < 5 ROW5)
 RIP_HD unsigned wrap5(unsigned x, unsigned ring_bytes) { const unsigned y = x - ring_bytes; return x < y ? x : y; }
 // byte offset of the ring5 slot of row s+DK, given o5[k] = offset of row s+k (DK is a compile-time constant)
@@ -252,21 +256,21 @@ RIP_HD void cp_async_wait() {
 //   the saturation threshold of the thread's own column (4 bytes);
 //   row correction [G] and the two channel lines [2][G] of the row (threads 0 .. 3G-1, 8 bytes each).
 // Every thread commits one group per step (possibly empty) so that wait_group counts steps.
-template <int G, int P, bool IN>
+template <int G, int P>
 RIP_HD void row_async(const Args& A, Smem<G>& sm, const Regs<G, P>& R, int row, int row_off, unsigned slot_o5, int tile, int tid,
                       int lo, int hi) {  // row_off: rows relative to row s (R.orow)
-    if (IN || (row >= 0 && row < A.n && row >= lo && row < hi)) {
+    if (in_range(row, imax(lo, 0), imin(hi, A.n))) {
         const unsigned npl = (unsigned)A.n * (unsigned)A.n;
         const unsigned obase = R.orow + (unsigned)(row_off * A.n) + (unsigned)(tile * TS);  // uniform
         const int c = tid & 15, g0 = tid >> 4;
-        if (IN || tile * TS + 8 * c + 8 <= A.n) {
+        if (tile * TS + 8 * c + 8 <= A.n) {
 #pragma unroll
             for (int k = 0; k < G / 8; ++k)
                 cp_async<16>(sm.raw(slot_o5) + (g0 + 8 * k) * TW + 8 * c,
                              A.raw + (obase + (unsigned)(g0 + 8 * k) * npl + (unsigned)(8 * c)));
         }
         const int x = tile * TS + tid;
-        cp_async<4>(sm.thr(slot_o5) + tid, A.thr + (obase + (unsigned)((IN || x < A.n) ? tid : -tile * TS)));
+        cp_async<4>(sm.thr(slot_o5) + tid, A.thr + (obase + (unsigned)(x < A.n ? tid : -tile * TS)));
         if (A.do_refpix && tid < 3 * G) {
             const int g = tid % G, which = tid / G;
             if (which == 0) {
@@ -411,7 +415,8 @@ RIP_HD ThrBand thr_band(float slope, const RampPlanDev& pl) {
 // jump_detect for one pixel and plan variant v >= 1 (saturation-truncated refits: rare), scalar.
 // Same decisions as rip::jump_detect_pixel<.., FAST=true>; the sure-flag / sure-clear tests are done on squares.
 template <int G>
-RIP_HD FitResult jump_fast_var(const float (&d)[G], int v, float gain, float read, const RampPlanDev& pl, const double* w_all) {
+RIP_HD_COLD FitResult jump_fast_var(const Ramp<G> rdv, int v, float gain, float read, const RampPlanDev& pl, const double* w_all) {
+    const float (&d)[G] = rdv.v;
     FitResult r;
     const int ngrp = pl.var_ngrp[v];
     const int start = pl.start;
@@ -453,12 +458,7 @@ RIP_HD FitResult jump_fast_var(const float (&d)[G], int v, float gain, float rea
             }
         }
     }
-    if (unsure) {
-        Ramp<G> rd;
-#pragma unroll
-        for (int t = 0; t < G; ++t) rd.v[t] = d[t];
-        mask = jump_exact<G>(rd, v, r.slope, dvardt, sig2read, pl, w_all);
-    }
+    if (unsure) mask = jump_exact<G>(rdv, v, r.slope, dvardt, sig2read, pl, w_all);
     r.jump_mask = mask;
     return r;
 }
@@ -499,14 +499,14 @@ inline FastTab make_fast_tab(const RampPlanDev& pl) {
 // one pair of slices: lanes (i0, di), (i0+1, di); V0 / V1 = the lane has a slice (compile time)
 template <bool V0, bool V1>
 RIP_HD void jump_pair(const f2 diff, const f2 inv_dt, const f2 Ac, const f2 Bc, const float nslope, const f2 hd, const f2 hr,
-                      const float ratio, const int i0, uint32_t& mask, bool& unsure) {
+                      const float ratio, const int i0, const bool lane0_live, uint32_t& mask, bool& unsure) {
     // (classification only: rounding is irrelevant here, anything inside the band is re-evaluated exactly)
     const f2 delta = fma2(diff, inv_dt, bc(nslope));
     const f2 hv = fma2(Ac, hd, mul2(Bc, hr));
     const f2 lv = mul2(hv, bc(ratio));
     if (V0) {
         const float l2s = delta.x * abs_f(delta.x);  // signed square: <= 0 is a sure clear (threshold > 0)
-        const bool set = l2s > hv.x, clr = l2s < lv.x;
+        const bool set = lane0_live && (l2s > hv.x), clr = !lane0_live || (l2s < lv.x);
         mask |= set ? (1u << i0) : 0u;
         unsure = unsure || !(set || clr);
     }
@@ -518,12 +518,12 @@ RIP_HD void jump_pair(const f2 diff, const f2 inv_dt, const f2 Ac, const f2 Bc, 
     }
 }
 
-// jump_detect of the whole ramp (plan variant 0) for one active pixel; q[j] = groups (2j, 2j+1).
+// jump_detect of the whole ramp (plan variant 0) for one active pixel; q[j] = groups (2j, 2j+1); start = plan.start (0 / 1).
 // slope / errors: the reference's op order (fitting.py:187-212).  Flags: every slice is classified without branching
 // on packed pairs; pixels with any slice inside the relative band of the threshold (or NaN) redo all slices in the
 // reference's exact f64 op order (cold) => the flags are those of the exact path.
-template <int G, int START>
-RIP_HD FitResult jump_full(const f2 (&q)[G / 2], float gain, float read, const RampPlanDev& pl, const FastTab& ft,
+template <int G>
+RIP_HD FitResult jump_full(const f2 (&q)[G / 2], const int start, float gain, float read, const RampPlanDev& pl, const FastTab& ft,
                            const double* w_all) {
     static_assert(G >= 6 && (G & 1) == 0, "pair indexing of the full-ramp specialisation");
     FitResult r;
@@ -546,27 +546,29 @@ RIP_HD FitResult jump_full(const f2 (&q)[G / 2], float gain, float read, const R
     uint32_t mask = 0u;
     const f2 hd = bc(tb.hi2 * dvardt), hr = bc(tb.hi2 * sig2read);
     const float ns = -r.slope;
+    // start = 1 (EXCLUDE_FIRST) only removes the two slices that begin at group 0: lane x of the pairs k = 0
 #pragma unroll
     for (int k = 0; k < G / 2; ++k) {
+        const bool live0 = (k > 0) || (start == 0);
         // di = 1: (d[2k+1] - d[2k], d[2k+2] - d[2k+1])
         {
-            const bool v0 = full_slice_valid(G, START, 2 * k, 1), v1 = full_slice_valid(G, START, 2 * k + 1, 1);
+            const bool v0 = full_slice_valid(G, 0, 2 * k, 1), v1 = full_slice_valid(G, 0, 2 * k + 1, 1);
             if (v0 || v1) {
                 const f2 up = f2{q[k].y, q[(k + 1 < G / 2) ? k + 1 : k].x};  // (the last lane pair has no second slice)
                 const f2 diff = sub2p(up, q[k]);
-                if (v0 && v1) jump_pair<true, true>(diff, ft.inv_dt[0][k], ft.A[0][k], ft.B[0][k], ns, hd, hr, ft.ratio, 2 * k, mask, unsure);
-                else if (v0) jump_pair<true, false>(diff, ft.inv_dt[0][k], ft.A[0][k], ft.B[0][k], ns, hd, hr, ft.ratio, 2 * k, mask, unsure);
-                else jump_pair<false, true>(diff, ft.inv_dt[0][k], ft.A[0][k], ft.B[0][k], ns, hd, hr, ft.ratio, 2 * k, mask, unsure);
+                if (v0 && v1) jump_pair<true, true>(diff, ft.inv_dt[0][k], ft.A[0][k], ft.B[0][k], ns, hd, hr, ft.ratio, 2 * k, live0, mask, unsure);
+                else if (v0) jump_pair<true, false>(diff, ft.inv_dt[0][k], ft.A[0][k], ft.B[0][k], ns, hd, hr, ft.ratio, 2 * k, live0, mask, unsure);
+                else jump_pair<false, true>(diff, ft.inv_dt[0][k], ft.A[0][k], ft.B[0][k], ns, hd, hr, ft.ratio, 2 * k, live0, mask, unsure);
             }
         }
         // di = 2: (d[2k+2] - d[2k], d[2k+3] - d[2k+1])
         if (k + 1 < G / 2) {
-            const bool v0 = full_slice_valid(G, START, 2 * k, 2), v1 = full_slice_valid(G, START, 2 * k + 1, 2);
+            const bool v0 = full_slice_valid(G, 0, 2 * k, 2), v1 = full_slice_valid(G, 0, 2 * k + 1, 2);
             if (v0 || v1) {
                 const f2 diff = sub2p(q[(k + 1 < G / 2) ? k + 1 : k], q[k]);
-                if (v0 && v1) jump_pair<true, true>(diff, ft.inv_dt[1][k], ft.A[1][k], ft.B[1][k], ns, hd, hr, ft.ratio, 2 * k, mask, unsure);
-                else if (v0) jump_pair<true, false>(diff, ft.inv_dt[1][k], ft.A[1][k], ft.B[1][k], ns, hd, hr, ft.ratio, 2 * k, mask, unsure);
-                else jump_pair<false, true>(diff, ft.inv_dt[1][k], ft.A[1][k], ft.B[1][k], ns, hd, hr, ft.ratio, 2 * k, mask, unsure);
+                if (v0 && v1) jump_pair<true, true>(diff, ft.inv_dt[1][k], ft.A[1][k], ft.B[1][k], ns, hd, hr, ft.ratio, 2 * k, live0, mask, unsure);
+                else if (v0) jump_pair<true, false>(diff, ft.inv_dt[1][k], ft.A[1][k], ft.B[1][k], ns, hd, hr, ft.ratio, 2 * k, live0, mask, unsure);
+                else jump_pair<false, true>(diff, ft.inv_dt[1][k], ft.A[1][k], ft.B[1][k], ns, hd, hr, ft.ratio, 2 * k, live0, mask, unsure);
             }
         }
     }
@@ -583,17 +585,17 @@ RIP_HD FitResult jump_full(const f2 (&q)[G / 2], float gain, float read, const R
 template <int G>
 RIP_HD FitResult ramp_fit_fast(const f2 (&q)[G / 2], GroupFlags& gf, uint32_t& pdq, float gain, float read,
                                const RampPlanDev& pl, const FastTab& ft, const double* w_all) {
-    FitResult r = pl.start ? jump_full<G, 1>(q, gain, read, pl, ft, w_all) : jump_full<G, 0>(q, gain, read, pl, ft, w_all);
+    FitResult r = jump_full<G>(q, pl.start, gain, read, pl, ft, w_all);
     const bool unsat = ((gf.sat >> (G - 1)) & 1u) == 0u;
     if (unsat) gf.jump |= r.jump_mask;
     if (gf.sat) {  // truncated refits only where some group is saturated
-        float d[G];
+        Ramp<G> rd;
 #pragma unroll
-        for (int j = 0; j < G / 2; ++j) { d[2 * j] = q[j].x; d[2 * j + 1] = q[j].y; }
+        for (int j = 0; j < G / 2; ++j) { rd.v[2 * j] = q[j].x; rd.v[2 * j + 1] = q[j].y; }
         for (int iend = G - 1; iend > 2 + pl.start; --iend) {
             const bool layer = ((gf.sat >> iend) & 1u) && !((gf.sat >> (iend - 1)) & 1u);
             if (layer) {
-                FitResult t = jump_fast_var<G>(d, G - iend, gain, read, pl, w_all);
+                FitResult t = jump_fast_var<G>(rd, G - iend, gain, read, pl, w_all);
                 r.slope = t.slope;
                 r.err_read = t.err_read;
                 r.err_poisson = t.err_poisson;
@@ -646,16 +648,16 @@ struct StepCtx {  // what every stage derives from (tile, tid, band, step); all 
 };
 
 // stage a1 : row s-2 (saturation growth, refpix, bias, multilin, D = lin * gain)
-template <int G, int P, bool IN>
+template <int G, int P>
 RIP_HD void stage_a1(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const StepCtx& C) {
     constexpr int H = G / 4, NQ1 = Regs<G, P>::NQ1;
     const int n = C.n, nb = 4, tid = C.tid, col = C.col, x = C.x, r0 = C.r0, r1 = C.r1;
     const unsigned (&o5)[5] = C.o5;
     const uint32_t allg = (1u << G) - 1u;
     const int row = C.s - 2;
-    const bool rowin = IN || (row >= 0 && row < n && row >= r0 - 2 && row < r1 + 2);
+    const bool rowin = in_range(row, imax(r0 - 2, 0), imin(r1 + 2, n));
     f4* dst = sm.D(RIP_O5(-2));
-    if (rowin && (IN || ((tid >= 1 || C.tile == 0) && tid <= TW - 2 && C.xin))) {  // (IN: the two edge columns compute unused values)
+    if (rowin && C.xin) {  // (all columns: the two edge columns of the tile compute values nobody reads)
         uint32_t grown = 0u;
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
@@ -670,7 +672,7 @@ RIP_HD void stage_a1(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const Step
         }
         satm &= allg & ~1u;
         const uint32_t adf = own >> 16;
-        const bool active = IN || (C.xact && (row >= nb && row < n - nb));
+        const bool active = C.xact && in_range(row, nb, n - nb);
         float S[G];
         {
             const uint16_t* rq = sm.raw(RIP_O5(-2)) + tid;
@@ -771,7 +773,7 @@ RIP_HD void stage_a1(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const Step
         } else {
 #pragma unroll
             for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
-            if (A.lincube && row >= r0 && row < r1 && (tid >= 4 || (!IN && C.tile == 0)) && tid < TW - 4) {
+            if (A.lincube && row >= r0 && row < r1 && (tid >= 4 || C.tile == 0) && tid < TW - 4) {
                 const unsigned npl = (unsigned)n * (unsigned)n;
 #pragma unroll
                 for (int g = 0; g < G; ++g)
@@ -780,24 +782,20 @@ RIP_HD void stage_a1(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const Step
         }
         sm.flg(RIP_O5(-2))[tid] = satm | (adf << 16);
         sm.nlc(RIP_O5(-2))[tid] = (uint8_t)(((dq & DQ_NO_LIN_CORR) ? 1u : 0u) | ((aux & 2u) ? 4u : 0u));
-    } else if (!IN && row >= r0 - 2 && row < r1 + 2) {
-#pragma unroll
-        for (int h = 0; h < H; ++h) dst[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
-        sm.flg(RIP_O5(-2))[tid] = 0u;
-        sm.nlc(RIP_O5(-2))[tid] = 0;
     }
+    // (rows of the band range outside the frame, columns beyond the frame: D / flags are never read there)
 }
 
 // stage b : row s-4 (IPC pass 1:  O1 = (D + D) - K (*) D)
-template <int G, int P, bool IN>
+template <int G, int P>
 RIP_HD void stage_b(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const StepCtx& C) {
     constexpr int H = G / 4;
     const int n = C.n, nb = 4, tid = C.tid, col = C.col, r0 = C.r0, r1 = C.r1;
     const unsigned (&o5)[5] = C.o5;
     const int row = C.s - 4;
-    const bool rowok = IN || (row >= nb && row < n - nb && row >= r0 - 1 && row < r1 + 1);
+    const bool rowok = in_range(row, imax(r0 - 1, nb), imin(r1 + 1, n - nb));
     f4* o = sm.O1(row);
-    if (rowok && (IN || (tid >= 2 && tid <= TW - 3 && C.xact))) {  // (IN: edge columns compute unused values)
+    if (rowok) {  // (all columns; the outermost two on each side of the tile compute values nobody reads)
         const float k[9] = {R.kb[0].x, R.kb[0].y, R.kb[0].z, R.kb[0].w, R.kb[1].x, R.kb[1].y, R.kb[1].z, R.kb[1].w, R.kb8};
         const f4* dm = sm.D(RIP_O5(-5));
         const f4* d0 = sm.D(RIP_O5(-4));
@@ -809,16 +807,16 @@ RIP_HD void stage_b(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const StepC
             const f4 dc = d0[h * RW + col];
             const f2 clo{dc.x, dc.y}, chi{dc.z, dc.w};
             const f2 rlo = sub2p(add2p(clo, clo), lo), rhi = sub2p(add2p(chi, chi), hi);  // output + image2 - ipc_fwd(output)
-            o[h * RW + col] = f4{rlo.x, rlo.y, rhi.x, rhi.y};
+            o[h * RW + col] = C.xact ? f4{rlo.x, rlo.y, rhi.x, rhi.y} : f4{0.f, 0.f, 0.f, 0.f};  // reference columns stay 0
         }
-    } else if (!IN && row >= r0 - 1 && row < r1 + 1) {
+    } else if (in_range(row, r0 - 1, r1 + 1)) {  // reference-pixel rows: zeros for the stencil of stage c
 #pragma unroll
         for (int h = 0; h < H; ++h) o[h * RW + col] = f4{0.f, 0.f, 0.f, 0.f};
     }
 }
 
 // stage c : row s-6 (IPC pass 2, /gain; ramp fit, jump flags, DQ propagation; dark, error split, flat/area; stores)
-template <int G, int P, bool IN>
+template <int G, int P>
 RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G>& sm, const Regs<G, P>& R, const StepCtx& C) {
     constexpr int H = G / 4;
     const int n = C.n, nb = 4, na = n - 8, tid = C.tid, col = C.col, x = C.x, r0 = C.r0, r1 = C.r1;
@@ -826,11 +824,11 @@ RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, Sme
     const uint32_t allg = (1u << G) - 1u;
     const unsigned npl = (unsigned)n * (unsigned)n;
     const int row = C.s - 6;
-    const bool out_col = (tid >= 4 || (!IN && C.tile == 0)) && tid < TW - 4 && C.xin;
-    const bool c_on = (IN || (row >= r0 && row < r1)) && out_col;
+    const bool out_col = (tid >= 4 || C.tile == 0) && tid < TW - 4 && C.xin;
+    const bool c_on = in_range(row, r0, r1) && out_col;
     if (!c_on) return;
     const unsigned p = R.orow - 6u * (unsigned)n + (unsigned)x;
-    const bool active = IN || (C.xact && (row >= nb && row < n - nb));
+    const bool active = C.xact && in_range(row, nb, n - nb);
     const uint32_t fl = sm.flg(RIP_O5(-6))[tid];
     const uint32_t nlc = sm.nlc(RIP_O5(-6))[tid];
     const float gval = R.kc[2].y, readv = R.kc[2].z, dsl = R.kc[2].w, flat = R.kc[3].x;
@@ -935,13 +933,13 @@ RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, Sme
 }
 
 // stage a0 : row s (raw -> cumulative saturation / A-D floor bits)
-template <int G, int P, bool IN>
+template <int G, int P>
 RIP_HD void stage_a0(const Args& A, Smem<G>& sm, const StepCtx& C) {
     const int n = C.n, tid = C.tid, col = C.col, r0 = C.r0, r1 = C.r1;
     const unsigned (&o5)[5] = C.o5;
     const int row = C.s;
     uint32_t bits = 0u;
-    const bool rowin = IN || (row >= 0 && row < n && row >= r0 - 3 && row < r1 + 3);
+    const bool rowin = in_range(row, imax(r0 - 3, 0), imin(r1 + 3, n));
     if (rowin && C.xin) {
         const uint16_t* rq = sm.raw(RIP_O5(0)) + tid;
         const float thr = sm.thr(RIP_O5(0))[tid];
@@ -967,28 +965,20 @@ RIP_HD void stage_a0(const Args& A, Smem<G>& sm, const StepCtx& C) {
     sm.sat(row)[col] = bits;
 }
 
-// IN = "interior, steady state": the CTA touches no frame edge (every pixel of the tile is an active pixel, every row
-// it reads exists: interior()) AND the step is one where all four stages have a row of the band to work on
-// (steady()).  All row / frame predicates then compile away and the stages form one straight-line block, which ptxas
-// schedules across stage boundaries; the generic form (IN = false) runs the edge CTAs and the ramp-up / ramp-down
-// steps of every band.  91 % of the CTAs of a 4096^2 frame are interior and 59 of their 73 steps are steady.
-RIP_HD bool interior(int n, int tile, int r0, int r1) { return tile >= 1 && tile * TS + TW <= n - 4 && r0 >= 6 && r1 <= n - 6; }
-RIP_HD bool steady(int s, int r0, int r1) { return s >= r0 + 6 && s <= r1; }
-
 // ---- one march step --------------------------------------------------------------------------------------------
 // Stage rows: a0 row s, a1 row s-2, b row s-4, c row s-6; every stage only reads ring slots written in earlier steps,
 // so one barrier per step suffices and the stages may run in any order.  Order and load placement (see Regs):
 //     [kb <- kbn: the one scoreboard wait]  [cp.async row s+2; Lb(next)]  a1  c  [Lc(next), L1(next)]  b  a0  barrier
 // o5s = (s mod RING) * ROW5, the byte offset of row s's ring5 slot, carried by the caller (next_o5).
-template <int G, int P, bool IN>
+template <int G, int P>
 RIP_HD void step(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G>& sm, Regs<G, P>& R, const int tid,
                  const int tile, const int r0, const int r1, const int s, const unsigned o5s) {
     StepCtx C;
     C.n = A.n; C.tid = tid; C.tile = tile; C.r0 = r0; C.r1 = r1; C.s = s;
     C.x = tile * TS + tid;
     C.col = tid + 1;
-    C.xin = IN || C.x < A.n;
-    C.xact = IN || (C.x >= 4 && C.x < A.n - 4);
+    C.xin = C.x < A.n;
+    C.xact = in_range(C.x, 4, A.n - 4);
     constexpr unsigned RB = Smem<G>::ROW5, RING_B = RING * Smem<G>::ROW5;
     C.o5[0] = o5s; C.o5[1] = wrap5(o5s + RB, RING_B); C.o5[2] = wrap5(o5s + 2 * RB, RING_B);
     C.o5[3] = wrap5(o5s + 3 * RB, RING_B); C.o5[4] = wrap5(o5s + 4 * RB, RING_B);
@@ -998,15 +988,15 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G
     // of load_bn -- and with them everything below -- are ordered after the arrival of all loads in flight.
     const unsigned dep = f_as_u(R.kc[0].x) & (unsigned)A.pad_;
     R.kb[0] = R.kbn[0]; R.kb[1] = R.kbn[1]; R.kb8 = R.kbn8;
-    row_async<G, P, IN>(A, sm, R, s + 2, 2, RIP_O5(2), tile, tid, r0 - 3, r1 + 3);
+    row_async<G, P>(A, sm, R, s + 2, 2, RIP_O5(2), tile, tid, r0 - 3, r1 + 3);
     load_bn<G, P>(A, R, s - 3, tile, tid, dep);
 
-    stage_a1<G, P, IN>(A, sm, R, C);
-    stage_c<G, P, IN>(A, pl, ft, sm, R, C);
+    stage_a1<G, P>(A, sm, R, C);
+    stage_c<G, P>(A, pl, ft, sm, R, C);
     load_c<G, P>(A, R, s - 5, tile, tid, C.x, C.xin);
     load_a1<G, P>(A, R, s - 1, tile, tid);
-    stage_b<G, P, IN>(A, sm, R, C);
-    stage_a0<G, P, IN>(A, sm, C);
+    stage_b<G, P>(A, sm, R, C);
+    stage_a0<G, P>(A, sm, C);
 
     R.orow += (unsigned)A.n;
     cp_async_wait<1>();  // the rows issued in the previous step (row s+1) have landed; the caller's barrier publishes them
@@ -1021,8 +1011,8 @@ RIP_HD void prologue(const Args& A, Smem<G>& sm, Regs<G, P>& R, int tid, int til
     constexpr unsigned RB = Smem<G>::ROW5, RING_B = RING * Smem<G>::ROW5;
     const unsigned o5s = (unsigned)mod_pos(s0, RING) * RB;
     R.orow = (unsigned)(s0 * A.n);  // (mod 2^32 for s0 < 0: only ever used after adding back a non-negative row offset)
-    row_async<G, P, false>(A, sm, R, s0, 0, o5s, tile, tid, r0 - 3, r1 + 3);
-    row_async<G, P, false>(A, sm, R, s0 + 1, 1, wrap5(o5s + RB, RING_B), tile, tid, r0 - 3, r1 + 3);
+    row_async<G, P>(A, sm, R, s0, 0, o5s, tile, tid, r0 - 3, r1 + 3);
+    row_async<G, P>(A, sm, R, s0 + 1, 1, wrap5(o5s + RB, RING_B), tile, tid, r0 - 3, r1 + 3);
     load_c<G, P>(A, R, s0 - 6, tile, tid, x, xin);
     load_a1<G, P>(A, R, s0 - 2, tile, tid);
     load_bn<G, P>(A, R, s0 - 4, tile, tid, 0u);

@@ -112,12 +112,8 @@ static void run_v2_t(rip::v2::Args A, const rip::v2::PackSrc& S, const rip_ramp_
             const int r0 = by * A.band_rows, r1 = (r0 + A.band_rows < n) ? r0 + A.band_rows : n;
             for (int tid = 0; tid < TW; ++tid) prologue<G, P>(A, sm, regs[tid], tid, tile, r0, r1);
             unsigned o5s = first_o5<G>(r0);
-            const bool in = interior(n, tile, r0, r1);  // same dispatch as the kernel (rip_v2.cu)
             for (int s = r0 - 3; s <= r1 + 5; ++s) {
-                for (int tid = 0; tid < TW; ++tid) {
-                    if (in && steady(s, r0, r1)) step<G, P, true>(A, pl, ft, sm, regs[tid], tid, tile, r0, r1, s, o5s);
-                    else step<G, P, false>(A, pl, ft, sm, regs[tid], tid, tile, r0, r1, s, o5s);
-                }
+                for (int tid = 0; tid < TW; ++tid) step<G, P>(A, pl, ft, sm, regs[tid], tid, tile, r0, r1, s, o5s);
                 o5s = next_o5<G>(o5s);
             }
         }
