@@ -458,7 +458,7 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
         v2::Args V;
         memset(&V, 0, sizeof V);
         V.n = n; V.ntile = v2::ntiles(n);
-        V.band_rows = prm->band_rows > 0 ? prm->band_rows : 64;  // measured best on B200 (profiles/r01/tile_sweep_v2.log)
+        V.band_rows = prm->band_rows > 0 ? prm->band_rows : v2_default_band_rows(h->device, n, G);
         V.do_refpix = prm->do_refpix; V.do_not_flag_first = prm->do_not_flag_first; V.exclude_first = prm->exclude_first;
         V.sat_backup = prm->sat_backup; V.area_dtype = prm->area_dtype;
         V.negzero = -0.0f;

@@ -84,6 +84,25 @@ static void launch_t(const Args& A, cudaStream_t st) {
 
 }  // namespace v2
 
+// Band height: about 64 rows (measured best on B200: taller bands lose to the wave tail, shorter ones to the 9 halo
+// steps per band), adjusted so that the CTA count ends just under a whole number of waves of resident CTAs
+// (4096^2, 148 SMs x 4: 67 bands of 62 rows = 2345 CTAs = 3.96 waves instead of 64 x 35 = 3.78; profiles/r02).
+int v2_default_band_rows(int device, int n, int G) {
+    static thread_local int sms_dev = -1, sms = 0;
+    if (sms_dev != device) {
+        RIP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        sms_dev = device;
+    }
+    const int slots = sms * ((G <= 8) ? 4 : 3), ntile = v2::ntiles(n);
+    const int nb0 = (n + 63) / 64;
+    const int waves = (ntile * nb0 + slots - 1) / slots;
+    int nb = waves * slots / ntile;
+    if (nb < nb0) nb = nb0;
+    if (nb > 2 * nb0) nb = 2 * nb0;
+    const int rows = (n + nb - 1) / nb;
+    return rows < 16 ? 16 : rows;
+}
+
 bool v2_supported(int G, int P) {
     return (G == 8 && P == 4) || (G == 8 && P == 11) || (G == 16 && P == 11) || (G == 16 && P == 4);
 }

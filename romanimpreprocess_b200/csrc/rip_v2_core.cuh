@@ -285,7 +285,8 @@ RIP_HD void row_async(const Args& A, Smem<G>& sm, const Regs<G, P>& R, int row, 
     cp_async_commit();
 }
 
-// ---- record loads (registers).  Unconditional: the records are padded with PADR zero rows on both sides, so rows
+// ---- record loads (registers).  Unconditional (measured: predicating them on "the stage has a row next step" makes
+// ptxas spill 176 bytes and scatter scoreboard waits through the step): the records are padded with PADR zero rows on both sides, so rows
 // outside the frame are loaded but never used (a conditional load would keep the old register contents live
 // around the whole loop).
 template <int G, int P>
