@@ -624,3 +624,108 @@ def make_l1_fullcal(counts, cal, read_pattern, rng, read_time=3.04, add_reset_no
     if quantize:
         res = np.round(res)
     return res.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Scene counts (a15) and reference-pixel / 1/f fill (a20): from_sim/sim_to_isim.py:265-402, 615-662
+# ---------------------------------------------------------------------------------------------------------
+G_IDEAL = 1.458  # pars.g_ideal (reference pars.py:21)
+
+
+class NormalStream:
+    """Stand-in for ``galsim.GaussianDeviate(rng).generate(array)``: float64 normals from a NumPy generator, cast to
+    the array's dtype, consumed in call order.  tests/golden/make_golden.py feeds the UNMODIFIED reference functions
+    from an identical stream, which pins the draw order and every deterministic step of the restatements below."""
+
+    def __init__(self, seed):
+        self.rng = np.random.Generator(np.random.PCG64(seed))
+
+    def generate(self, array):
+        array[...] = self.rng.standard_normal(array.size).reshape(array.shape)
+
+
+def noise_1f_frame(stream, nside=4096, channelwidth=128):
+    """One (nside, channelwidth) block of 1/f noise, S(f) = 1/f (sim_to_isim.py:265-303): complex white spectrum of
+    2*nside*channelwidth points scaled by |k|^-1/2 (k = 0 removed), forward FFT, real part of the first half / sqrt 2,
+    mean removed, float32."""
+    m = 2 * nside * channelwidth
+    draws = np.zeros(2 * m)
+    stream.generate(draws)
+    k = np.linspace(0, 1 - 1.0 / m, m)
+    k[m // 2 :] -= 1.0
+    amp = (1.0e-99 + np.abs(k * m)) ** (-0.5)
+    amp[0] = 0.0
+    spec = np.zeros((m,), dtype=np.complex128)
+    spec[:] = draws[:m]
+    spec[:] += 1j * draws[m:]
+    spec *= amp
+    block = np.fft.fft(spec).real[: m // 2] / np.sqrt(2.0)
+    block -= np.mean(block)
+    return block.reshape((nside, channelwidth)).astype(np.float32)
+
+
+def fill_in_refdata_and_1f(im, cal, stream, tij, fill_in_banding=True, amp33=None, nborder=4):
+    """fill_in_refdata_and_1f (sim_to_isim.py:306-402), in place on ``im`` [G,n,n] (and ``amp33`` [G,n,n/32]).
+
+    Reference pixels = N(0,1)*read/sqrt(N_g) + N(0,1)*resetnoise (one layer for all groups) + dark cube (:341-352);
+    active pixels keep ``im`` (:356-358); per group one common and 32 per-channel 1/f frames, odd channels mirrored,
+    added to EVERY pixel as (u_pink*frame + c_pink*common)/sqrt(N_g) (:376-389); reference output = med +
+    (N(0,1)*std + RU_PINK*frame + M_PINK*c_pink*common)/sqrt(N_g) cast to the cube dtype (:392-399); finally
+    clip(round(.), 0, 65535) (:402).  Draw order as in the reference.
+    """
+    G, ny, nx = im.shape
+    cw = nx // 32
+    rd = cal["read"]
+    noise = np.zeros((G + 1, ny, nx), dtype=np.float32)
+    stream.generate(noise)
+    noise[:-1] *= rd["data"][None]
+    noise[-1] *= rd["resetnoise"]
+    for j in range(len(tij)):
+        noise[j] /= len(tij[j]) ** 0.5
+    noise[:-1] += noise[-1][None]
+    dk = cal["dark"]["data"]
+    noise[:-1] += np.copy(dk[dk.shape[0] - G :])
+    nb = nborder
+    noise[:-1, nb : ny - nb, nb : nx - nb] = im[:, nb : ny - nb, nb : nx - nb].astype(noise.dtype)
+    a33 = {"valid": False}
+    if amp33 is not None and "amp33" in rd:
+        a33 = rd["amp33"]
+    if fill_in_banding:
+        u_pink, c_pink = float(rd["anc"]["U_PINK"]), float(rd["anc"]["C_PINK"])
+        for j in range(len(tij)):
+            rn = len(tij[j]) ** 0.5
+            common = noise_1f_frame(stream, ny, cw) * c_pink
+            for ch in range(32):
+                pink = noise_1f_frame(stream, ny, cw) * u_pink + common
+                if ch % 2 == 1:
+                    pink = pink[:, ::-1]
+                noise[j, :, cw * ch : cw * (ch + 1)] += (pink / rn).astype(noise.dtype)
+            if a33["valid"]:
+                white = np.zeros((ny, cw), dtype=np.float32)
+                stream.generate(white)
+                white *= a33["std"]
+                pink = a33["RU_PINK"] * noise_1f_frame(stream, ny, cw) + a33["M_PINK"] * common
+                amp33[j] = (a33["med"] + (white + pink) / rn).astype(amp33.dtype)
+    im[...] = np.clip(np.round(noise[:-1]), 0, 2**16 - 1).astype(im.dtype)
+
+
+def sim_calprep(cal, nborder=4):
+    """Calibration planes of Image2D.simulate (sim_to_isim.py:615-633): dark rate in e/s and flat, both IPC-deconvolved
+    on the active array, with the reference's clips.  Returns (this_dark, this_flat, g)."""
+    nb = nborder
+    this_dark = cal["dark"]["dark_slope"][nb:-nb, nb:-nb]
+    this_flat = cal["flat"]["data"][nb:-nb, nb:-nb]
+    this_dark = this_dark * cal["gain"]["data"][nb:-nb, nb:-nb]
+    g = np.copy(cal["gain"]["data"][nb:-nb, nb:-nb])
+    K = cal["ipc4d"]["data"]
+    this_dark = ipc_rev(this_dark, K)
+    this_flat = ipc_rev(this_flat, K, gain=g)
+    this_flat = np.clip(this_flat, 0.0, 2 - 2**-21)
+    this_dark = np.clip(this_dark, -0.1 * this_flat, None)
+    return this_dark, this_flat, g
+
+
+def scene_rate(image, this_flat, g, area_ratio, t, cnorm=1.0):
+    """Poisson mean of the scene electrons (sim_to_isim.py:636-648): clip(C t g/g_ideal image flat/area, 0)."""
+    flat_witharea = this_flat / area_ratio
+    return np.clip(cnorm * t * g / G_IDEAL * image * flat_witharea, 0, None)

@@ -6,56 +6,9 @@
 #include <memory>
 
 #include "rip_launch.h"
+#include "rip_rng.cuh"
 
 namespace rip {
-
-// ---------------------------------------------------------------------------------------------------------
-// Philox4x32-10 counter-based RNG (Salmon et al. 2011); one stream per (pixel, purpose)
-// ---------------------------------------------------------------------------------------------------------
-struct Philox {
-    uint32_t c[4], k[2];
-    uint32_t out[4];
-    int have;
-    __device__ __forceinline__ void init(uint64_t seed, uint64_t idx, uint32_t stream) {
-        k[0] = (uint32_t)seed; k[1] = (uint32_t)(seed >> 32);
-        c[0] = 0u; c[1] = stream; c[2] = (uint32_t)idx; c[3] = (uint32_t)(idx >> 32);
-        have = 0;
-    }
-    __device__ __forceinline__ void round_(uint32_t (&x)[4], uint32_t k0, uint32_t k1) {
-        const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-        const uint32_t hi0 = __umulhi(M0, x[0]), lo0 = M0 * x[0];
-        const uint32_t hi1 = __umulhi(M1, x[2]), lo1 = M1 * x[2];
-        const uint32_t y0 = hi1 ^ x[1] ^ k0, y1 = lo1, y2 = hi0 ^ x[3] ^ k1, y3 = lo0;
-        x[0] = y0; x[1] = y1; x[2] = y2; x[3] = y3;
-    }
-    __device__ __forceinline__ void gen() {
-        uint32_t x[4] = {c[0], c[1], c[2], c[3]};
-        uint32_t k0 = k[0], k1 = k[1];
-#pragma unroll
-        for (int r = 0; r < 10; ++r) {
-            round_(x, k0, k1);
-            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-        }
-        out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3];
-        ++c[0];
-        have = 4;
-    }
-    __device__ __forceinline__ uint32_t next() {
-        if (have == 0) gen();
-        return out[--have];
-    }
-    // uniform in (0,1), 24-bit
-    __device__ __forceinline__ float uniform() { return ((next() >> 8) + 0.5f) * (1.0f / 16777216.0f); }
-    // uniform in (0,1), 53-bit
-    __device__ __forceinline__ double uniform53() {
-        const uint64_t a = next() >> 5, b = next() >> 6;
-        return ((double)a * 67108864.0 + (double)b + 0.5) * (1.0 / 9007199254740992.0);
-    }
-    __device__ __forceinline__ float normal() {
-        const float u1 = uniform(), u2 = uniform();
-        return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
-    }
-};
 
 // Stirling tail log(k!) - [(k+1/2)log(k+1) - (k+1) + (1/2)log(2pi)]  (Hormann 1993)
 __device__ __forceinline__ double stirling_tail(double k) {

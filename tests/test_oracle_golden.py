@@ -209,3 +209,37 @@ def test_gencal_linearity_sanity(gencal_fixture):
     der = (sp - sm) / 10.0
     assert -1.5 < np.amin(s0) and np.amax(s0) < 1.5
     assert 0.99 < np.amin(der) and np.amax(der) < 1.01
+
+
+def _sim_small_cal(n, G, seed):
+    """Same CALDIR as tests/golden/make_golden_sim.py:small_cal."""
+    from romanimpreprocess_b200 import synth
+
+    pattern = [[0], [1, 2], [3, 4, 5, 6]][:G]
+    cal = synth.make_caldir(n=n, read_pattern=pattern, p_order=3, seed=seed)
+    cal = {k: v["roman"] for k, v in cal.items()}
+    cw = n // 32
+    a33 = cal["read"]["amp33"]
+    a33["med"] = np.ascontiguousarray(a33["med"][:, :cw])
+    a33["std"] = np.ascontiguousarray(a33["std"][:, :cw])
+    return cal, pattern
+
+
+def test_sim_refdata_golden():
+    """a20 / a15: noise_1f_frame, fill_in_refdata_and_1f (3 modes) and the Image2D.simulate calibration planes
+    against the unmodified reference functions (reference from_sim/sim_to_isim.py:265-402, 615-633) fed from the
+    same normal stream (tests/golden/make_golden_sim.py)."""
+    g = load_golden("sim_refdata_n256")
+    n, G, seed = int(g["n"]), int(g["G"]), int(g["seed"])
+    cal, pattern = _sim_small_cal(n, G, seed)
+    tij = orc.read_pattern_to_tij(pattern)
+    assert np.array_equal(orc.noise_1f_frame(orc.NormalStream(11), n, n // 32), g["frame_seed11"])
+    for tag, banding, with33 in (("full", True, True), ("nobanding", False, True), ("no33", True, False)):
+        im = g["im0"].copy()
+        a33 = np.zeros((G, n, n // 32), np.uint16) if with33 else None
+        orc.fill_in_refdata_and_1f(im, cal, orc.NormalStream(77), tij, fill_in_banding=banding, amp33=a33)
+        assert np.array_equal(im, g[f"{tag}_im"]), tag
+        if with33:
+            assert np.array_equal(a33, g[f"{tag}_amp33"]), tag
+    d, fl, _ = orc.sim_calprep(cal)
+    assert np.array_equal(d, g["this_dark"]) and np.array_equal(fl, g["this_flat"])
