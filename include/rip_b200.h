@@ -271,6 +271,55 @@ int rip_make_l1_host(rip_caldir* h, const int32_t* counts, const int32_t* cum_co
 int rip_make_l1_dev(rip_caldir* h, const int32_t* d_counts, const rip_fwd_params* prm, float* d_resultants,
                     void* stream);
 
+/* ---- forward path either side of make_l1_fullcal (a15, a20) ----------------------------------------
+ * Image2D.simulate (from_sim/sim_to_isim.py:615-648).  rip_sim_calprep returns the two calibration planes of the
+ * scene on the active array [na,na]: this_dark = clip(ipc_rev(dark_slope*gain), -0.1*this_flat, .) in e/s and
+ * this_flat = clip(ipc_rev(flat, gain=g), 0, 2-2^-21) (exact against the reference functions for f32 planes).
+ * rip_sim_counts_*: counts (+)= Poisson(clip(cnorm*t_exp*g/g_ideal * image * this_flat/area, 0)) and, when
+ * t_dark > 0, + Poisson(this_dark*t_dark) (romanisim's dark term, restated: SURVEY App. D).  image f32 [na,na]
+ * (e/s per ideal pixel), area [na,na] = pixel area / Omega_ideal (f32|f64) or NULL; counts i32 [na,na];
+ * rate_out f64 [na,na] or NULL receives the Poisson mean (for the statistical tests). */
+int rip_sim_calprep(rip_caldir* h, float* this_dark, float* this_flat);
+int rip_sim_counts_dev(rip_caldir* h, const float* d_image, const void* d_area, int area_dtype, double t_exp,
+                       double cnorm, double g_ideal, double t_dark, uint64_t seed, int32_t* d_counts, int accumulate,
+                       void* stream);
+int rip_sim_counts_host(rip_caldir* h, const float* image, const void* area, int area_dtype, double t_exp, double cnorm,
+                        double g_ideal, double t_dark, uint64_t seed, int32_t* counts, int accumulate, double* rate_out);
+
+/* noise_1f_frame (from_sim/sim_to_isim.py:265-303): nframes blocks [nside, nside/32] f32 of 1/f noise (nside a power
+ * of two, 32..4096).  draws f64 [nframes, 2*m] (m = 2*nside*nside/32): the N(0,1) stream of the reference call (real
+ * parts, then imaginary parts) -- given, the result is deterministic (test path); NULL = Philox(seed, frame). */
+int rip_noise_1f_frames_host(int device, int nside, int nframes, uint64_t seed, const double* draws, float* out);
+
+/* fill_in_refdata_and_1f (from_sim/sim_to_isim.py:306-402), in place on the u16 cube [G,n,n]: reference pixels =
+ * round(N*read/sqrt(N_g) + N*resetnoise + dark cube), active pixels kept, + 1/f banding (one common and 32 channel
+ * frames per group, odd channels mirrored) on every pixel, clip to u16; amp33 u16 [G,n,n/32] (or NULL) = reference
+ * output from the read file's amp33 statistics. */
+int rip_fill_refdata_1f_dev(rip_caldir* h, uint16_t* d_im, uint16_t* d_amp33, int G, const int32_t* reads_per_group,
+                            uint64_t seed, int fill_in_banding, void* stream);
+int rip_fill_refdata_1f_host(rip_caldir* h, uint16_t* im, uint16_t* amp33, int G, const int32_t* reads_per_group,
+                             uint64_t seed, int fill_in_banding);
+
+/* ---- many-realisations bookkeeping (validation_tests/many_realizations.py:58-106; BASELINE configs[4]) ---------
+ * rip_mask_build_host: CombinedMask.build (utils/maskhandling.py:82-117): grow32[b] in {0,1,5,9,25} = pixels affected
+ * by bit b (1 = itself, 5 = cross, 9 = 3x3, 25 = 5x5; zero padding at the edges); mask u8 [ny,nx], 1 = masked.
+ * rip_moments_accumulate_dev: on the active window of full-frame slope f32 / pdq u32 [n,n]:
+ * moments[0] += w, [1] += w*data, [2] += w*data^2 with w = !mask (f32 accumulators [3,na,na], realisation order).
+ * rip_moments_finalize_dev: mean, std, -1000 sentinel (:80-83).  rip_stack_median_dev: np.median over R <= 128 planes. */
+int rip_mask_build_host(int device, const uint32_t* dq, int ny, int nx, const uint8_t* grow32, uint8_t* mask);
+int rip_moments_accumulate_dev(int device, const float* d_slope, const uint32_t* d_pdq, int n, int nb,
+                               const uint8_t* grow32, float* d_moments, void* stream);
+int rip_moments_finalize_dev(int device, float* d_moments, long npix, void* stream);
+int rip_stack_median_dev(int device, const float* d_stack, int R, long npix, float* d_out, void* stream);
+
+/* glue of one realisation: resultants f32 [G,na,na] -> active window of the u16 L1 cube [G,n,n] (romanisim make_asdf
+ * restated: clip to 0..65535, zero border), and the per-realisation planes of many_realizations.py:69-73
+ * (diffs = last - second group, images = slope, err = hypot(err_read, err_poisson); full frames, zero border). */
+int rip_l1_embed_dev(int device, const float* d_resultants, int G, int n, int nb, uint16_t* d_im, void* stream);
+int rip_realization_record_dev(int device, const uint16_t* d_im, int G, int n, int nb, const float* d_slope,
+                               const float* d_err_read, const float* d_err_poisson, float* d_diffs, float* d_images,
+                               float* d_err, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

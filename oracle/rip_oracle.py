@@ -729,3 +729,51 @@ def scene_rate(image, this_flat, g, area_ratio, t, cnorm=1.0):
     """Poisson mean of the scene electrons (sim_to_isim.py:636-648): clip(C t g/g_ideal image flat/area, 0)."""
     flat_witharea = this_flat / area_ratio
     return np.clip(cnorm * t * g / G_IDEAL * image * flat_witharea, 0, None)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Mask growth and the moment sums of the many-realisations protocol
+# (utils/maskhandling.py:82-117, 152-178; validation_tests/many_realizations.py:74-83)
+# ---------------------------------------------------------------------------------------------------------
+PIXELMASK1 = {0: 1, 2: 5, 3: 25, 4: 1, 5: 1, 6: 5, 8: 1, 9: 1, 10: 9, 11: 9, 12: 1, 13: 9, 15: 1, 18: 9, 19: 9, 20: 9,
+              21: 9, 22: 1, 23: 9, 24: 9, 25: 9, 28: 9, 30: 9}  # bit -> pixels affected  # fmt: skip
+
+
+def mask_build(dq, grow=None):
+    """CombinedMask.build (maskhandling.py:82-117): OR over bits of the bit plane dilated by a cross (5), a 3x3 (9)
+    or a 5x5 (25) box, zero padded (scipy.signal.convolve mode='same' of a 0/2 layer with a 0/1 kernel, >= 1)."""
+    grow = PIXELMASK1 if grow is None else grow
+    ny, nx = dq.shape
+    mask = np.zeros((ny, nx), dtype=bool)
+    foot = {
+        5: [(0, 0), (1, 0), (-1, 0), (0, 1), (0, -1)],
+        9: [(a, b) for a in (-1, 0, 1) for b in (-1, 0, 1)],
+        25: [(a, b) for a in range(-2, 3) for b in range(-2, 3)],
+    }
+    for bit, g in grow.items():
+        if g == 0:
+            continue
+        layer = (dq & np.uint32(1 << bit)) != 0
+        if g == 1:
+            mask |= layer
+            continue
+        pad = np.zeros((ny + 4, nx + 4), dtype=bool)
+        pad[2:-2, 2:-2] = layer
+        for a, b in foot[g]:
+            mask |= pad[2 + a : 2 + a + ny, 2 + b : 2 + b + nx]
+    return mask
+
+
+def moments_accumulate(moments, data, dq, grow=None):
+    """many_realizations.py:74-77 on one realisation (float32 accumulators [3,ny,nx], in place)."""
+    w = np.logical_not(mask_build(dq, grow))
+    moments[0] += np.where(w, 1, 0.0)
+    moments[1] += np.where(w, data, 0.0)
+    moments[2] += np.where(w, data**2, 0.0)
+
+
+def moments_finalize(moments):
+    """many_realizations.py:80-83 (in place): mean, std, -1000 where no realisation was unmasked."""
+    moments[1:] /= moments[0] + 1e-25
+    moments[2] = np.sqrt(np.clip(moments[2] - moments[1] ** 2, 0, None))
+    moments[1:] = np.where(moments[0][None] > 0.1, moments[1:], -1000.0)

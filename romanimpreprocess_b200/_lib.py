@@ -132,6 +132,24 @@ _SIGS = {
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "rip_make_l1_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FwdParams), C.c_void_p]),
     "rip_make_l1_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(FwdParams), C.c_void_p, C.c_void_p]),
+    "rip_sim_calprep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rip_sim_counts_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
+                                     C.c_double, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]),
+    "rip_sim_counts_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
+                                      C.c_double, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]),
+    "rip_noise_1f_frames_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "rip_fill_refdata_1f_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int,
+                                          C.c_void_p]),
+    "rip_fill_refdata_1f_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64,
+                                           C.c_int]),
+    "rip_mask_build_host": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "rip_moments_accumulate_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]),
+    "rip_moments_finalize_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_long, C.c_void_p]),
+    "rip_l1_embed_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "rip_realization_record_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rip_stack_median_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p]),
 }  # fmt: skip
 
 EXPORTED_SYMBOLS = sorted(_SIGS)

@@ -364,6 +364,7 @@ extern "C" int rip_caldir_create(int device, const rip_caldir_desc* d, rip_caldi
     h->has_amp33 = d->has_amp33 && d->amp33_med != nullptr;
     if (h->has_amp33) {
         h->amp_med.upload(d->amp33_med, (size_t)n * 128, st);
+        if (d->amp33_std) h->amp_std.upload(d->amp33_std, (size_t)n * 128, st);
         h->refout_slope = (d->refout_slope == d->refout_slope) ? d->refout_slope
                           : (d->amp33_std ? derive_refout_slope(d) : std::numeric_limits<double>::quiet_NaN());
         RIP_REQUIRE(h->refout_slope == h->refout_slope, "rip_caldir_create: cannot derive the reference-output slope (amp33 std missing)");

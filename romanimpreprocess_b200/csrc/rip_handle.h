@@ -38,6 +38,9 @@ struct rip_caldir {
     DevBuf<uint32_t> w_pdq;
     DevBuf<int8_t> w_end;
     DevBuf<uint8_t> w_rdq;
+    // forward path (rip_sim.cu): amp33 noise plane, scene calibration planes (lazy), 1/f frame workspace (lazy)
+    DevBuf<float> amp_std, sim_dark, sim_flat, f_frames, f_work;
+    DevBuf<double> f_sums;
     cudaStream_t stream = nullptr;
     // optional per-launch timing of the fused kernel (rip_profile_enable): event pairs recorded on the launch stream
     bool profile = false;

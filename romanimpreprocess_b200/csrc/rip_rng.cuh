@@ -46,6 +46,15 @@ struct Philox {
         const uint64_t a = next() >> 5, b = next() >> 6;
         return ((double)a * 67108864.0 + (double)b + 0.5) * (1.0 / 9007199254740992.0);
     }
+    // two independent normals from one Box-Muller pair
+    __device__ __forceinline__ void normal2(float& a, float& b) {
+        const float u1 = uniform(), u2 = uniform();
+        const float r = sqrtf(-2.0f * logf(u1));
+        float sn, cs;
+        sincospif(2.0f * u2, &sn, &cs);
+        a = r * cs;
+        b = r * sn;
+    }
     __device__ __forceinline__ float normal() {
         const float u1 = uniform(), u2 = uniform();
         return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);

@@ -1,0 +1,696 @@
+// Forward path, the rows either side of make_l1_fullcal (a15, a20) and the many-realisations
+// bookkeeping (BASELINE configs[4]; reference validation_tests/many_realizations.py:58-106):
+//
+//   sim_calprep / sim_counts   Image2D.simulate (from_sim/sim_to_isim.py:615-648): calibration planes of the scene
+//                              (IPC-deconvolved dark rate and flat, clips) and the Poisson draw of the scene electrons
+//   noise_1f_frames            noise_1f_frame (sim_to_isim.py:265-303): 1/f noise blocks by a length-(n/4)^2 complex FFT
+//                              (four-step, two shared-memory passes) of an on-the-fly Gaussian spectrum
+//   fill_refdata_1f            fill_in_refdata_and_1f (sim_to_isim.py:306-402): reference pixels, banding, amp33
+//   mask_build / moments_*     CombinedMask.build (utils/maskhandling.py:82-117) fused with the moment sums
+//   stack_median               np.median(stack, axis=0) for the realisation stacks
+//
+// Random numbers are counter-based Philox (rip_rng.cuh), not GalSim's Boost-MT: everything stochastic is validated
+// statistically against the oracle (tests/test_gpu_sim.py); every deterministic step is checked exactly.
+#include <math.h>
+#include <stdint.h>
+
+#include "rip_handle.h"
+#include "rip_launch.h"
+#include "rip_math.cuh"
+#include "rip_rng.cuh"
+
+namespace rip {
+
+// ---------------------------------------------------------------------------------------------------------
+// Poisson(lam): multiplication method below 10, Hormann's PTRS transformed rejection above (the algorithm of
+// NumPy's legacy generator).  Result clipped to int32.
+// ---------------------------------------------------------------------------------------------------------
+__device__ long poisson_draw(Philox& rng, double lam) {
+    if (!(lam > 0.0)) return 0;
+    if (lam < 10.0) {
+        const double enlam = exp(-lam);
+        long k = 0;
+        double prod = 1.0;
+        for (;;) {
+            prod *= rng.uniform53();
+            if (prod > enlam) ++k;
+            else return k;
+        }
+    }
+    const double slam = sqrt(lam), loglam = log(lam);
+    const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (;;) {
+        const double U = rng.uniform53() - 0.5, V = rng.uniform53();
+        const double us = 0.5 - fabs(U);
+        const double kf = floor((2.0 * a / us + b) * U + lam + 0.43);
+        if (us >= 0.07 && V <= vr) return kf > 2147483647.0 ? 2147483647L : (long)kf;
+        if (kf < 0.0 || (us < 0.013 && V > us)) continue;
+        if ((log(V) + log(invalpha) - log(a / (us * us) + b)) <= (-lam + kf * loglam - lgamma(kf + 1.0)))
+            return kf > 2147483647.0 ? 2147483647L : (long)kf;
+    }
+}
+
+// this_dark (e/s) input of ipc_rev: dark_slope * gain on the full frame (sim_to_isim.py:624)
+template <typename TG>
+__global__ void dark_e_kernel(const float* __restrict__ dark_slope, const TG* __restrict__ gain, long npix, float* __restrict__ out) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    out[p] = (float)((typename Promote<float, TG>::type)dark_slope[p] * (typename Promote<float, TG>::type)gain[p]);
+}
+
+// clips of sim_to_isim.py:631-633 on the active window of full-frame planes -> dense [na,na] outputs
+__global__ void sim_clip_kernel(const float* __restrict__ dark_full, const float* __restrict__ flat_full, int n, int nb,
+                                float* __restrict__ this_dark, float* __restrict__ this_flat) {
+    const int na = n - 2 * nb;
+    const int xa = blockIdx.x * blockDim.x + threadIdx.x, ya = blockIdx.y;
+    if (xa >= na) return;
+    const long q = (long)(ya + nb) * n + (xa + nb), p = (long)ya * na + xa;
+    const float fl = np_clip<float>(flat_full[q], 0.0f, 1.99999952316284179688f);  // 2 - 2**-21
+    const float lo = -0.1f * fl;  // python float * f32 array -> f32
+    this_flat[p] = fl;
+    this_dark[p] = np_max<float>(dark_full[q], lo);
+}
+
+// counts (+)= Poisson(clip(C t g / g_ideal * image * flat / area, 0)) [+ Poisson(dark * t_dark)]
+template <typename TG, typename TA>
+__global__ void sim_counts_kernel(const float* __restrict__ image, const float* __restrict__ this_flat,
+                                  const float* __restrict__ this_dark, const TG* __restrict__ gain, const TA* __restrict__ area,
+                                  int n, int nb, double ct, double g_ideal, double t_dark, uint64_t seed, int accumulate,
+                                  int32_t* __restrict__ counts, double* __restrict__ rate_out) {
+    const int na = n - 2 * nb;
+    const int xa = blockIdx.x * blockDim.x + threadIdx.x, ya = blockIdx.y;
+    if (xa >= na) return;
+    const long q = (long)(ya + nb) * n + (xa + nb), p = (long)ya * na + xa;
+    const double fa = area ? (double)this_flat[p] / (double)area[p] : (double)this_flat[p];
+    double lam = ct * (double)gain[q] / g_ideal * (double)image[p] * fa;
+    lam = lam > 0.0 ? lam : 0.0;  // np.clip(., 0, None); NaN -> no electrons
+    if (rate_out) rate_out[p] = lam;
+    Philox rng;
+    rng.init(seed, (uint64_t)p, 2u);
+    long c = poisson_draw(rng, lam);
+    if (t_dark > 0.0) {
+        Philox r2;
+        r2.init(seed, (uint64_t)p, 3u);
+        c += poisson_draw(r2, (double)this_dark[p] * t_dark);
+    }
+    if (accumulate) c += counts[p];
+    counts[p] = (int32_t)(c > 2147483647L ? 2147483647L : c);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 1/f frames.  m = 2 * nside * (nside/32) = L^2 with L = nside/4.  Four-step FFT:
+//   X[k1 + L k2] = sum_{n2} W_L^{n2 k2} [ W_m^{n2 k1} sum_{n1} x[L n1 + n2] W_L^{n1 k1} ]
+// pass 1: for 8 values of n2 per CTA, the L-point transforms over n1 and the twiddle -> A[k1][n2]
+// pass 2: for 8 values of k1 per CTA, the L-point transforms over n2 -> real part of X[k] for k < m/2, / sqrt 2
+// ---------------------------------------------------------------------------------------------------------
+constexpr int FCOL = 8;
+
+__device__ __forceinline__ unsigned bitrev(unsigned v, int bits) { return __brev(v) >> (32 - bits); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// in-place decimation-in-time radix-2 transforms of FCOL columns of length L (input already bit-reversed)
+__device__ void cta_fft(float2* s, const float2* tw, int L) {
+    for (int len = 2; len <= L; len <<= 1) {
+        const int half = len >> 1, tstep = L / len;
+        for (int b = threadIdx.x; b < FCOL * (L >> 1); b += blockDim.x) {
+            const int col = b / (L >> 1), i = b - col * (L >> 1);
+            const int grp = i / half, k = i - grp * half;
+            float2* a = s + (long)col * L + grp * len + k;
+            const float2 u = a[0], v = cmul(a[half], tw[k * tstep]);
+            a[0] = make_float2(u.x + v.x, u.y + v.y);
+            a[half] = make_float2(u.x - v.x, u.y - v.y);
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void fill_twiddles(float2* tw, int L) {
+    for (int t = threadIdx.x; t < (L >> 1); t += blockDim.x) {
+        float sn, cs;
+        sincospif(-2.0f * (float)t / (float)L, &sn, &cs);
+        tw[t] = make_float2(cs, sn);
+    }
+}
+
+// amplitude of spectrum element j (sim_to_isim.py:287-292): |k m|^-1/2 with k wrapped to [-1/2, 1/2), 0 at j = 0
+__device__ __forceinline__ float amp_1f(unsigned j, unsigned m) {
+    if (j == 0) return 0.0f;
+    const unsigned d = j < m / 2 ? j : m - j;
+    return rsqrtf((float)d);
+}
+
+__global__ void __launch_bounds__(256) fft1f_pass1_kernel(int L, int logL, uint64_t seed, unsigned frame0,
+                                                          const double* __restrict__ draws, float2* __restrict__ A) {
+    extern __shared__ float2 sm1[];
+    float2* s = sm1;
+    float2* tw = sm1 + (long)FCOL * L;
+    const unsigned m = (unsigned)L * (unsigned)L;
+    const int frame = blockIdx.y, n2_0 = blockIdx.x * FCOL;
+    fill_twiddles(tw, L);
+    for (int idx = threadIdx.x; idx < FCOL * L; idx += blockDim.x) {
+        const int c = idx % FCOL, n1 = idx / FCOL;
+        const unsigned j = (unsigned)L * (unsigned)n1 + (unsigned)(n2_0 + c);
+        float re, im;
+        if (draws) {
+            re = (float)draws[(long)frame * 2 * m + j];
+            im = (float)draws[(long)frame * 2 * m + m + j];
+        } else {
+            Philox rng;
+            rng.init(seed, (uint64_t)j, 1024u + frame0 + (unsigned)frame);
+            rng.normal2(re, im);
+        }
+        const float a = amp_1f(j, m);
+        s[(long)c * L + bitrev((unsigned)n1, logL)] = make_float2(re * a, im * a);
+    }
+    __syncthreads();
+    cta_fft(s, tw, L);
+    for (int idx = threadIdx.x; idx < FCOL * L; idx += blockDim.x) {
+        const int c = idx % FCOL, k1 = idx / FCOL;
+        const unsigned n2 = (unsigned)(n2_0 + c);
+        float sn, cs;
+        sincospif(-2.0f * (float)(n2 * (unsigned)k1) / (float)m, &sn, &cs);  // n2 k1 < 2^20: exact
+        A[((long)frame * L + k1) * L + n2] = cmul(s[(long)c * L + k1], make_float2(cs, sn));
+    }
+}
+
+__global__ void __launch_bounds__(256) fft1f_pass2_kernel(int L, int logL, const float2* __restrict__ A,
+                                                          float* __restrict__ frames, double* __restrict__ sums) {
+    extern __shared__ float2 sm1[];
+    float2* s = sm1;
+    float2* tw = sm1 + (long)FCOL * L;
+    __shared__ double red[256];
+    const long m = (long)L * L;
+    const int frame = blockIdx.y, k1_0 = blockIdx.x * FCOL;
+    fill_twiddles(tw, L);
+    for (int idx = threadIdx.x; idx < FCOL * L; idx += blockDim.x) {
+        const int r = idx / L, n2 = idx - r * L;
+        s[(long)r * L + bitrev((unsigned)n2, logL)] = A[((long)frame * L + (k1_0 + r)) * L + n2];
+    }
+    __syncthreads();
+    cta_fft(s, tw, L);
+    double acc = 0.0;
+    for (int idx = threadIdx.x; idx < FCOL * (L >> 1); idx += blockDim.x) {
+        const int r = idx % FCOL, k2 = idx / FCOL;
+        const float v = s[(long)r * L + k2].x * 0.70710678118654752440f;
+        frames[(long)frame * (m / 2) + (long)(k1_0 + r) + (long)L * k2] = v;
+        acc += (double)v;
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(&sums[frame], red[0]);
+}
+
+__global__ void frame_demean_kernel(float* __restrict__ frames, const double* __restrict__ sums, long half) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int frame = blockIdx.y;
+    if (p >= half) return;
+    frames[(long)frame * half + p] = (float)((double)frames[(long)frame * half + p] - sums[frame] / (double)half);
+}
+
+static int ilog2_exact(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return ((1 << l) == v) ? l : -1;
+}
+
+// nframes blocks [nside, nside/32] f32 into d_frames; d_work >= nframes * (nside/4)^2 float2; d_sums >= nframes doubles
+static void noise_1f_frames_impl(int nside, int nframes, uint64_t seed, unsigned frame0, const double* d_draws,
+                                 float* d_frames, float2* d_work, double* d_sums, cudaStream_t st) {
+    const int L = nside / 4, logL = ilog2_exact(L);
+    RIP_REQUIRE(logL >= 3 && L <= 1024 && nside == 4 * L, "noise_1f_frames: frame side %d must be a power of two in 32..4096", nside);
+    const size_t smem = ((size_t)FCOL * L + L / 2) * sizeof(float2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        RIP_CUDA(cudaFuncSetAttribute(fft1f_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FCOL * 1024 + 512) * 8));
+        RIP_CUDA(cudaFuncSetAttribute(fft1f_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FCOL * 1024 + 512) * 8));
+        attr_done = true;
+    }
+    const long half = (long)L * L / 2;
+    RIP_CUDA(cudaMemsetAsync(d_sums, 0, (size_t)nframes * sizeof(double), st));
+    dim3 grid(L / FCOL, nframes);
+    RIP_LAUNCH(fft1f_pass1_kernel, grid, 256, smem, st, L, logL, seed, frame0, d_draws, d_work);
+    RIP_LAUNCH(fft1f_pass2_kernel, grid, 256, smem, st, L, logL, (const float2*)d_work, d_frames, d_sums);
+    dim3 g2((unsigned)((half + 255) / 256), nframes);
+    RIP_LAUNCH(frame_demean_kernel, g2, 256, 0, st, d_frames, (const double*)d_sums, half);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fill_in_refdata_and_1f: one thread per (group, pixel)
+// ---------------------------------------------------------------------------------------------------------
+struct FillArgs {
+    int n, nb, G, cw, banding;
+    uint64_t seed;
+    float inv_rn[RIP_GMAX];  // sqrt(len(tij[j])) as f32 (python float ** 0.5, weak scalar -> f32)
+    float u_pink, c_pink;
+    const float* read; const float* resetnoise; const float* dark;  // dark: last G groups of the dark cube
+    const float* frames;  // [33][n, cw] of the current group: 0 = common, 1 + ch = channel ch
+    uint16_t* im;
+};
+
+__global__ void fill_refdata_kernel(const FillArgs A, int g) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int n = A.n, nb = A.nb;
+    if (x >= n) return;
+    const long p = (long)y * n + x, npl = (long)n * n;
+    uint16_t* dst = A.im + (long)g * npl + p;
+    float v;
+    if (x >= nb && x < n - nb && y >= nb && y < n - nb) {
+        v = (float)*dst;  // active pixels keep the simulated signal (sim_to_isim.py:356-358)
+    } else {
+        Philox r1, r2;
+        r1.init(A.seed, (uint64_t)p, 32u + (unsigned)g);
+        r2.init(A.seed, (uint64_t)p, 31u);
+        float a = r1.normal() * A.read[p];
+        a = a / A.inv_rn[g];
+        const float b = r2.normal() * A.resetnoise[p];
+        v = (a + b) + A.dark[(long)g * npl + p];
+    }
+    if (A.banding) {
+        const int cw = A.cw, ch = x / cw, xin = x - ch * cw;
+        const int sc = (ch & 1) ? (cw - 1 - xin) : xin;  // odd channels are read out mirrored (:384-385)
+        const long fp = (long)y * cw + sc, fsz = (long)n * cw;
+        const float common = A.frames[fp] * A.c_pink;
+        const float pink = A.frames[(long)(1 + ch) * fsz + fp] * A.u_pink + common;
+        v = v + pink / A.inv_rn[g];
+    }
+    v = rintf(v);
+    v = v < 0.0f ? 0.0f : (v > 65535.0f ? 65535.0f : v);
+    *dst = (uint16_t)v;
+}
+
+// amp33[g] = u16(med + (N std + (RU_PINK frame33 + M_PINK common)) / rn)   (sim_to_isim.py:392-399)
+__global__ void fill_amp33_kernel(int n, int cw, int g, uint64_t seed, float rn, float c_pink, float ru_pink, float m_pink,
+                                  const float* __restrict__ med, const float* __restrict__ stdv, const float* __restrict__ common_f,
+                                  const float* __restrict__ frame33, int banding, uint16_t* __restrict__ amp33) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x, fsz = (long)n * cw;
+    if (p >= fsz) return;
+    Philox r;
+    r.init(seed, (uint64_t)p, 48u + (unsigned)g);
+    const long q = (p / cw) * 128 + (p % cw);  // statistics planes are [n,128]
+    const float white = r.normal() * stdv[q];
+    const float common = common_f[p] * c_pink;
+    const float pink = ru_pink * frame33[p] + m_pink * common;
+    const float v = med[q] + (white + pink) / rn;
+    amp33[(long)g * fsz + p] = (uint16_t)(int)v;  // ndarray.astype(uint16): truncation
+    (void)banding;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CombinedMask.build (maskhandling.py:82-117) on a window, fused with the moment sums of many_realizations.py:74-77
+// ---------------------------------------------------------------------------------------------------------
+struct GrowSets { uint32_t m1, m5, m9, m25; };
+
+__device__ __forceinline__ bool grown_mask(const uint32_t* __restrict__ dq, long pitch, int ny, int nx, int y, int x, const GrowSets S) {
+    const uint32_t any = S.m1 | S.m5 | S.m9 | S.m25;
+    uint32_t hit = dq[(long)y * pitch + x] & any;
+    // scipy.signal.convolve(mode="same") pads with zeros: neighbours outside the window do not contribute
+    for (int dy = -2; dy <= 2; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= ny) continue;
+        for (int dx = -2; dx <= 2; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= nx || (dx == 0 && dy == 0)) continue;
+            const int ady = dy < 0 ? -dy : dy, adx = dx < 0 ? -dx : dx;
+            uint32_t sel = S.m25;
+            if (ady <= 1 && adx <= 1) sel |= S.m9;
+            if (ady + adx == 1) sel |= S.m5;
+            hit |= dq[(long)yy * pitch + xx] & sel;
+        }
+    }
+    return hit != 0u;
+}
+
+__global__ void mask_build_kernel(const uint32_t* __restrict__ dq, long pitch, int ny, int nx, const GrowSets S, uint8_t* __restrict__ mask) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx) return;
+    mask[(long)y * nx + x] = grown_mask(dq, pitch, ny, nx, y, x, S) ? 1 : 0;
+}
+
+// moments[0] += w; moments[1] += w ? data : 0; moments[2] += w ? data**2 : 0      (float32 accumulators)
+__global__ void moments_accumulate_kernel(const float* __restrict__ data, const uint32_t* __restrict__ dq, long pitch, int ny,
+                                          int nx, const GrowSets S, float* __restrict__ mom) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx) return;
+    const bool w = !grown_mask(dq, pitch, ny, nx, y, x, S);
+    const long p = (long)y * nx + x, np_ = (long)ny * nx;
+    const float d = data[(long)y * pitch + x];
+    mom[p] = mom[p] + (w ? 1.0f : 0.0f);
+    mom[np_ + p] = mom[np_ + p] + (w ? d : 0.0f);
+    mom[2 * np_ + p] = mom[2 * np_ + p] + (w ? d * d : 0.0f);
+}
+
+// many_realizations.py:80-83: mean, std, sentinel -1000 where nothing was accumulated
+__global__ void moments_finalize_kernel(float* __restrict__ mom, long npix) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const float m0 = mom[p];
+    const float den = m0 + 1e-25f;
+    float m1 = mom[npix + p] / den, m2 = mom[2 * npix + p] / den;
+    m2 = sqrtf(np_max<float>(m2 - m1 * m1, 0.0f));  // np.clip(., 0, None): NaN propagates
+    const bool ok = m0 > 0.1f;
+    mom[npix + p] = ok ? m1 : -1000.0f;
+    mom[2 * npix + p] = ok ? m2 : -1000.0f;
+}
+
+// np.median over the leading axis of a [R, npix] stack (R <= RP, RP a power of two): bitonic network in registers
+template <int RP>
+__global__ void stack_median_kernel(const float* __restrict__ stack, int R, long npix, float* __restrict__ out) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    float v[RP];
+    bool nan = false;
+#pragma unroll
+    for (int i = 0; i < RP; ++i) {
+        v[i] = (i < R) ? stack[(long)i * npix + p] : INFINITY;
+        nan = nan || (v[i] != v[i]);
+    }
+#pragma unroll
+    for (int k = 2; k <= RP; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < RP; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = ((i & k) == 0);
+                    const float a = v[i], b = v[l];
+                    const bool sw = up ? (a > b) : (a < b);
+                    v[i] = sw ? b : a;
+                    v[l] = sw ? a : b;
+                }
+            }
+        }
+    }
+    // v ascending; padded +inf entries sit at the top.  Dynamic index on a register array would spill: select by scan.
+    const int lo = (R - 1) >> 1, hi = R >> 1;
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < RP; ++i) {
+        a = (i == lo) ? v[i] : a;
+        b = (i == hi) ? v[i] : b;
+    }
+    float med = (lo == hi) ? a : (a + b) / 2.0f;  // np.mean of the two middle values in float32
+    out[p] = nan ? NAN : med;
+}
+
+
+// romanisim.l1.make_asdf restated: resultants f32 [G,na,na] -> active window of the u16 cube [G,n,n]
+__global__ void l1_embed_kernel(const float* __restrict__ res, int G, int n, int nb, uint16_t* __restrict__ im) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, g = blockIdx.z;
+    if (x >= n) return;
+    const int na = n - 2 * nb;
+    uint16_t v = 0;
+    if (x >= nb && x < n - nb && y >= nb && y < n - nb) {
+        float f = res[((long)g * na + (y - nb)) * na + (x - nb)];
+        f = f < 0.0f ? 0.0f : (f > 65535.0f ? 65535.0f : f);  // NaN -> 0
+        v = (uint16_t)(int)f;
+    }
+    im[((long)g * n + y) * n + x] = v;
+}
+
+// one realisation's planes of validation_tests/many_realizations.py:69-73 (full frames, zero border)
+__global__ void realization_record_kernel(const uint16_t* __restrict__ im, int G, int n, int nb, const float* __restrict__ slope,
+                                          const float* __restrict__ er, const float* __restrict__ ep, float* __restrict__ diffs,
+                                          float* __restrict__ images, float* __restrict__ err) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= n) return;
+    const long p = (long)y * n + x, npl = (long)n * n;
+    diffs[p] = (float)im[(long)(G - 1) * npl + p] - (float)im[npl + p];
+    const bool act = x >= nb && x < n - nb && y >= nb && y < n - nb;
+    images[p] = act ? slope[p] : 0.0f;
+    err[p] = act ? sqrtf(er[p] * er[p] + ep[p] * ep[p]) : 0.0f;
+}
+
+static GrowSets grow_sets(const uint8_t* grow32) {
+    GrowSets S{0u, 0u, 0u, 0u};
+    for (int b = 0; b < 32; ++b) {
+        const uint32_t bit = 1u << b;
+        switch (grow32[b]) {
+            case 0: break;
+            case 1: S.m1 |= bit; break;
+            case 5: S.m5 |= bit; break;
+            case 9: S.m9 |= bit; break;
+            case 25: S.m25 |= bit; break;
+            default: RIP_REQUIRE(false, "mask grow code %d for bit %d (expected 0, 1, 5, 9 or 25)", (int)grow32[b], b);
+        }
+    }
+    return S;
+}
+
+static void sim_calprep_impl(rip_caldir* h, float* d_this_dark, float* d_this_flat, cudaStream_t st) {
+    const int n = h->n, nb = h->nb, na = h->na;
+    const long npl = (long)n * n;
+    DevBuf<float> dk(npl), fl(npl);
+    DevRaw tmp;
+    tmp.alloc((size_t)na * na * 8);
+    const unsigned nblk = (unsigned)((npl + 255) / 256);
+    if (h->d.gain_dtype == RIP_F64) RIP_LAUNCH(dark_e_kernel<double>, nblk, 256, 0, st, h->dark_slope.p, (const double*)h->gain.p, npl, dk.p);
+    else RIP_LAUNCH(dark_e_kernel<float>, nblk, 256, 0, st, h->dark_slope.p, (const float*)h->gain.p, npl, dk.p);
+    RIP_CUDA(cudaMemcpyAsync(fl.p, h->flat.p, npl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (h->has_ipc) {
+        launch_ipc_rev_dn(dk.p, n, n, nb, h->ipc.p, h->d.ipc_dtype, nullptr, RIP_F32, false, 0.f, tmp.p, st);
+        launch_ipc_rev_dn(fl.p, n, n, nb, h->ipc.p, h->d.ipc_dtype, h->gain.p, h->d.gain_dtype, false, 0.f, tmp.p, st);
+    }
+    dim3 grid((na + 127) / 128, na);
+    RIP_LAUNCH(sim_clip_kernel, grid, 128, 0, st, (const float*)dk.p, (const float*)fl.p, n, nb, d_this_dark, d_this_flat);
+    RIP_CUDA(cudaStreamSynchronize(st));
+}
+
+static void ensure_sim_planes(rip_caldir* h) {
+    if (h->sim_dark.p) return;
+    const long npa = (long)h->na * h->na;
+    h->sim_dark.alloc(npa);
+    h->sim_flat.alloc(npa);
+    sim_calprep_impl(h, h->sim_dark.p, h->sim_flat.p, h->stream);
+}
+
+static void sim_counts_impl(rip_caldir* h, const float* d_image, const void* d_area, int area_dtype, double t_exp,
+                            double cnorm, double g_ideal, double t_dark, uint64_t seed, int32_t* d_counts, int accumulate,
+                            double* d_rate, cudaStream_t st) {
+    ensure_sim_planes(h);
+    const int n = h->n, nb = h->nb, na = h->na;
+    dim3 grid((na + 127) / 128, na);
+    const double ct = cnorm * t_exp;
+    const bool gd = h->d.gain_dtype == RIP_F64, ad = d_area && area_dtype == RIP_F64;
+#define SC(TG, TA)                                                                                                     \
+    RIP_LAUNCH((sim_counts_kernel<TG, TA>), grid, 128, 0, st, d_image, (const float*)h->sim_flat.p, (const float*)h->sim_dark.p, \
+               (const TG*)h->gain.p, (const TA*)d_area, n, nb, ct, g_ideal, t_dark, seed, accumulate, d_counts, d_rate)
+    if (gd) { if (ad) SC(double, double); else SC(double, float); }
+    else { if (ad) SC(float, double); else SC(float, float); }
+#undef SC
+}
+
+static void fill_refdata_impl(rip_caldir* h, uint16_t* d_im, uint16_t* d_amp33, int G, const int32_t* reads_per_group,
+                              uint64_t seed, int banding, cudaStream_t st) {
+    const int n = h->n, nb = h->nb, cw = n / 32;
+    RIP_REQUIRE(G >= 1 && G <= RIP_GMAX, "rip_fill_refdata_1f: G=%d outside 1..%d", G, RIP_GMAX);
+    RIP_REQUIRE(h->resetnoise.p, "rip_fill_refdata_1f: read file has no resetnoise plane");
+    RIP_REQUIRE(h->d.n_dark >= G && h->dark_cube.p, "rip_fill_refdata_1f: dark cube has %d groups, need %d", h->d.n_dark, G);
+    const bool want33 = d_amp33 && h->has_amp33 && h->amp_std.p;
+    RIP_REQUIRE(!want33 || cw <= 128, "rip_fill_refdata_1f: amp33 statistics are [n,128]; frame side %d has %d-column channels", n, cw);
+    const long npl = (long)n * n, fsz = (long)n * cw;
+    const int nfr = 34;
+    if (banding) {
+        const int L = n / 4;
+        if (h->f_frames.n < (size_t)nfr * fsz) h->f_frames.alloc((size_t)nfr * fsz);
+        if (h->f_work.n < (size_t)nfr * L * L * 2) h->f_work.alloc((size_t)nfr * L * L * 2);
+        if (h->f_sums.n < (size_t)nfr) h->f_sums.alloc(nfr);
+    }
+    FillArgs A;
+    memset(&A, 0, sizeof A);
+    A.n = n; A.nb = nb; A.G = G; A.cw = cw; A.banding = banding; A.seed = seed;
+    for (int g = 0; g < G; ++g) A.inv_rn[g] = (float)sqrt((double)reads_per_group[g]);
+    A.u_pink = (float)h->d.u_pink; A.c_pink = (float)h->d.c_pink;
+    A.read = h->read.p; A.resetnoise = h->resetnoise.p;
+    A.dark = h->dark_cube.p + (size_t)(h->d.n_dark - G) * npl;
+    A.frames = h->f_frames.p; A.im = d_im;
+    dim3 grid((n + 127) / 128, n);
+    for (int g = 0; g < G; ++g) {
+        if (banding)
+            noise_1f_frames_impl(n, want33 ? 34 : 33, seed, (unsigned)(g * 64), nullptr, h->f_frames.p, (float2*)h->f_work.p,
+                                 h->f_sums.p, st);
+        RIP_LAUNCH(fill_refdata_kernel, grid, 128, 0, st, A, g);
+        if (want33 && banding)
+            RIP_LAUNCH(fill_amp33_kernel, (unsigned)((fsz + 255) / 256), 256, 0, st, n, cw, g, seed, A.inv_rn[g], A.c_pink,
+                       (float)h->d.ru_pink, (float)h->d.m_pink, (const float*)h->amp_med.p, (const float*)h->amp_std.p,
+                       (const float*)h->f_frames.p, (const float*)(h->f_frames.p + 33 * fsz), banding, d_amp33);
+    }
+}
+
+template <int RP>
+static void stack_median_t(const float* d_stack, int R, long npix, float* d_out, cudaStream_t st) {
+    RIP_LAUNCH(stack_median_kernel<RP>, (unsigned)((npix + 127) / 128), 128, 0, st, d_stack, R, npix, d_out);
+}
+
+}  // namespace rip
+
+using namespace rip;
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+extern "C" int rip_sim_calprep(rip_caldir* h, float* this_dark, float* this_flat) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && this_dark && this_flat, "rip_sim_calprep: null argument");
+    use_device(h->device);
+    ensure_sim_planes(h);
+    const long npa = (long)h->na * h->na;
+    h->sim_dark.download(this_dark, npa, h->stream);
+    h->sim_flat.download(this_flat, npa, h->stream);
+    RIP_CUDA(cudaStreamSynchronize(h->stream));
+    RIP_API_END
+}
+
+extern "C" int rip_sim_counts_dev(rip_caldir* h, const float* d_image, const void* d_area, int area_dtype, double t_exp,
+                                  double cnorm, double g_ideal, double t_dark, uint64_t seed, int32_t* d_counts,
+                                  int accumulate, void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && d_image && d_counts, "rip_sim_counts_dev: null argument");
+    use_device(h->device);
+    sim_counts_impl(h, d_image, d_area, area_dtype, t_exp, cnorm, g_ideal, t_dark, seed, d_counts, accumulate, nullptr,
+                    (cudaStream_t)stream);
+    RIP_API_END
+}
+
+extern "C" int rip_sim_counts_host(rip_caldir* h, const float* image, const void* area, int area_dtype, double t_exp,
+                                   double cnorm, double g_ideal, double t_dark, uint64_t seed, int32_t* counts,
+                                   int accumulate, double* rate_out) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && image && counts, "rip_sim_counts_host: null argument");
+    use_device(h->device);
+    cudaStream_t st = h->stream;
+    const long npa = (long)h->na * h->na;
+    DevBuf<float> di;
+    DevRaw da;
+    DevBuf<int32_t> dc(npa);
+    DevBuf<double> dr;
+    di.upload(image, npa, st);
+    if (area) da.upload(area, npa * dtype_size(area_dtype), st);
+    if (accumulate) dc.upload(counts, npa, st);
+    if (rate_out) dr.alloc(npa);
+    sim_counts_impl(h, di.p, area ? da.p : nullptr, area_dtype, t_exp, cnorm, g_ideal, t_dark, seed, dc.p, accumulate,
+                    rate_out ? dr.p : nullptr, st);
+    dc.download(counts, npa, st);
+    if (rate_out) dr.download(rate_out, npa, st);
+    RIP_CUDA(cudaStreamSynchronize(st));
+    RIP_API_END
+}
+
+extern "C" int rip_noise_1f_frames_host(int device, int nside, int nframes, uint64_t seed, const double* draws, float* out) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(out && nframes >= 1, "rip_noise_1f_frames_host: null argument");
+    use_device(device);
+    const int L = nside / 4;
+    const long m = (long)L * L, half = m / 2;
+    DevBuf<double> dd, sums(nframes);
+    DevBuf<float> fr((size_t)nframes * half), work((size_t)nframes * m * 2);
+    if (draws) dd.upload(draws, (size_t)nframes * 2 * m, 0);
+    noise_1f_frames_impl(nside, nframes, seed, 0u, draws ? dd.p : nullptr, fr.p, (float2*)work.p, sums.p, 0);
+    fr.download(out, (size_t)nframes * half, 0);
+    RIP_CUDA(cudaDeviceSynchronize());
+    RIP_API_END
+}
+
+extern "C" int rip_fill_refdata_1f_dev(rip_caldir* h, uint16_t* d_im, uint16_t* d_amp33, int G, const int32_t* reads_per_group,
+                                       uint64_t seed, int fill_in_banding, void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && d_im && reads_per_group, "rip_fill_refdata_1f_dev: null argument");
+    use_device(h->device);
+    fill_refdata_impl(h, d_im, d_amp33, G, reads_per_group, seed, fill_in_banding, (cudaStream_t)stream);
+    RIP_API_END
+}
+
+extern "C" int rip_fill_refdata_1f_host(rip_caldir* h, uint16_t* im, uint16_t* amp33, int G, const int32_t* reads_per_group,
+                                        uint64_t seed, int fill_in_banding) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && im && reads_per_group, "rip_fill_refdata_1f_host: null argument");
+    use_device(h->device);
+    cudaStream_t st = h->stream;
+    const long npl = (long)h->n * h->n, a33 = (long)h->n * (h->n / 32);
+    DevBuf<uint16_t> di, da;
+    di.upload(im, (size_t)G * npl, st);
+    if (amp33) { da.alloc((size_t)G * a33); da.zero(st); }
+    fill_refdata_impl(h, di.p, amp33 ? da.p : nullptr, G, reads_per_group, seed, fill_in_banding, st);
+    di.download(im, (size_t)G * npl, st);
+    if (amp33 && h->has_amp33 && h->amp_std.p && fill_in_banding) da.download(amp33, (size_t)G * a33, st);
+    RIP_CUDA(cudaStreamSynchronize(st));
+    RIP_API_END
+}
+
+extern "C" int rip_mask_build_host(int device, const uint32_t* dq, int ny, int nx, const uint8_t* grow32, uint8_t* mask) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(dq && grow32 && mask && ny > 0 && nx > 0, "rip_mask_build_host: null argument");
+    use_device(device);
+    const GrowSets S = grow_sets(grow32);
+    const long npix = (long)ny * nx;
+    DevBuf<uint32_t> d;
+    DevBuf<uint8_t> m(npix);
+    d.upload(dq, npix, 0);
+    dim3 grid((nx + 127) / 128, ny);
+    RIP_LAUNCH(mask_build_kernel, grid, 128, 0, 0, (const uint32_t*)d.p, (long)nx, ny, nx, S, m.p);
+    m.download(mask, npix, 0);
+    RIP_CUDA(cudaDeviceSynchronize());
+    RIP_API_END
+}
+
+extern "C" int rip_moments_accumulate_dev(int device, const float* d_slope, const uint32_t* d_pdq, int n, int nb,
+                                          const uint8_t* grow32, float* d_moments, void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(d_slope && d_pdq && grow32 && d_moments, "rip_moments_accumulate_dev: null argument");
+    use_device(device);
+    const GrowSets S = grow_sets(grow32);
+    const int na = n - 2 * nb;
+    const long off = (long)nb * n + nb;
+    dim3 grid((na + 127) / 128, na);
+    RIP_LAUNCH(moments_accumulate_kernel, grid, 128, 0, (cudaStream_t)stream, d_slope + off, d_pdq + off, (long)n, na, na, S, d_moments);
+    RIP_API_END
+}
+
+extern "C" int rip_moments_finalize_dev(int device, float* d_moments, long npix, void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(d_moments && npix > 0, "rip_moments_finalize_dev: null argument");
+    use_device(device);
+    RIP_LAUNCH(moments_finalize_kernel, (unsigned)((npix + 255) / 256), 256, 0, (cudaStream_t)stream, d_moments, npix);
+    RIP_API_END
+}
+
+extern "C" int rip_stack_median_dev(int device, const float* d_stack, int R, long npix, float* d_out, void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(d_stack && d_out && npix > 0, "rip_stack_median_dev: null argument");
+    RIP_REQUIRE(R >= 1 && R <= 128, "rip_stack_median_dev: R=%d outside 1..128", R);
+    use_device(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (R <= 8) stack_median_t<8>(d_stack, R, npix, d_out, st);
+    else if (R <= 16) stack_median_t<16>(d_stack, R, npix, d_out, st);
+    else if (R <= 32) stack_median_t<32>(d_stack, R, npix, d_out, st);
+    else if (R <= 64) stack_median_t<64>(d_stack, R, npix, d_out, st);
+    else stack_median_t<128>(d_stack, R, npix, d_out, st);
+    RIP_API_END
+}
+
+extern "C" int rip_l1_embed_dev(int device, const float* d_resultants, int G, int n, int nb, uint16_t* d_im, void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(d_resultants && d_im && G >= 1 && n > 2 * nb, "rip_l1_embed_dev: bad argument");
+    use_device(device);
+    dim3 grid((n + 127) / 128, n, G);
+    RIP_LAUNCH(l1_embed_kernel, grid, 128, 0, (cudaStream_t)stream, d_resultants, G, n, nb, d_im);
+    RIP_API_END
+}
+
+extern "C" int rip_realization_record_dev(int device, const uint16_t* d_im, int G, int n, int nb, const float* d_slope,
+                                          const float* d_err_read, const float* d_err_poisson, float* d_diffs,
+                                          float* d_images, float* d_err, void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(d_im && d_slope && d_err_read && d_err_poisson && d_diffs && d_images && d_err && G >= 2,
+                "rip_realization_record_dev: bad argument");
+    use_device(device);
+    dim3 grid((n + 127) / 128, n);
+    RIP_LAUNCH(realization_record_kernel, grid, 128, 0, (cudaStream_t)stream, d_im, G, n, nb, d_slope, d_err_read,
+               d_err_poisson, d_diffs, d_images, d_err);
+    RIP_API_END
+}

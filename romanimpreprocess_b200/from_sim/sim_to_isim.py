@@ -107,4 +107,102 @@ def make_l1_fullcal(counts, read_pattern, caldir, rng=None, persistence=None, ts
     return out, with_dq
 
 
-__all__ = ["make_l1_fullcal", "read_pattern_from_reads", "fwd_params", "pars"]
+def noise_1f_frame(rng, nside=None, seed=None, device=0, nframes=1, draws=None):
+    """
+    1/f noise block(s), S(f) = 1/f, shape (nside, nside/32): reference from_sim/sim_to_isim.py:265-303.
+
+    The reference fills a 2*nside*channelwidth-point complex spectrum from ``galsim.GaussianDeviate`` and takes the
+    real part of the first half of its forward FFT; here the spectrum is generated in the kernel (Philox) and
+    transformed by a four-step shared-memory FFT (``rip_noise_1f_frames_host``).  ``draws`` (float64, [nframes, 2*m])
+    replaces the generator by a given N(0,1) stream (deterministic; tests).
+    """
+    nside = pars.nside if nside is None else int(nside)
+    out = np.empty((nframes, nside, nside // 32), np.float32)
+    d = None if draws is None else np.ascontiguousarray(draws, dtype=np.float64)
+    sd = 0 if draws is not None else _seed_from(rng, seed)
+    _lib.check(_lib.lib().rip_noise_1f_frames_host(device, nside, nframes, sd, _lib.ptr(d), _lib.ptr(out)))
+    return out[0] if nframes == 1 else out
+
+
+def fill_in_refdata_and_1f(im, caldir, rng, tij, fill_in_banding=True, amp33=None, seed=None, device=0):
+    """
+    Fills in reference pixel data and 1/f noise (in place): reference from_sim/sim_to_isim.py:306-402.
+
+    Parameters
+    ----------
+    im : np.ndarray, uint16 (ngroup, n, n)
+        The simulated L1 cube; active pixels are kept, reference pixels are generated, banding is added everywhere.
+    caldir : dict or CalDir
+    rng : int, galsim.BaseDeviate or np.random.Generator (source of the seed)
+    tij : list of list of float
+        Read times per group (only the group lengths matter, as in the reference).
+    amp33 : np.ndarray, uint16 (ngroup, n, n/32), optional
+        Reference output, filled if the read file carries amp33 statistics.
+    """
+    cal = caldir if isinstance(caldir, CalDir) else CalDir(caldir, device)
+    try:
+        G = im.shape[0]
+        if im.dtype != np.uint16 or not im.flags["C_CONTIGUOUS"]:
+            raise TypeError("im must be a C-contiguous uint16 cube")
+        rpg = np.ascontiguousarray([len(t) for t in tij], dtype=np.int32)
+        if len(rpg) != G:
+            raise ValueError("tij must list the reads of every group of im")
+        a33 = None
+        if amp33 is not None:
+            if amp33.dtype != np.uint16 or not amp33.flags["C_CONTIGUOUS"]:
+                raise TypeError("amp33 must be a C-contiguous uint16 cube")
+            a33 = amp33
+        _lib.check(_lib.lib().rip_fill_refdata_1f_host(cal.handle, _lib.ptr(im), _lib.ptr(a33), G, _lib.ptr(rpg),
+                                                       _seed_from(rng, seed), int(bool(fill_in_banding))))  # fmt: skip
+    finally:
+        if cal is not caldir:
+            cal.close()
+
+
+def sim_calprep(caldir, device=0):
+    """The scene's calibration planes of ``Image2D.simulate`` (reference sim_to_isim.py:615-633):
+    (this_dark [e/s], this_flat), both IPC-deconvolved on the active array and clipped."""
+    cal = caldir if isinstance(caldir, CalDir) else CalDir(caldir, device)
+    try:
+        d = np.empty((cal.na, cal.na), np.float32)
+        f = np.empty((cal.na, cal.na), np.float32)
+        _lib.check(_lib.lib().rip_sim_calprep(cal.handle, _lib.ptr(d), _lib.ptr(f)))
+    finally:
+        if cal is not caldir:
+            cal.close()
+    return d, f
+
+
+def simulate_counts(image, caldir, read_pattern, rng=None, seed=None, area_ratio=None, cnorm=1.0, read_time=READ_TIME,
+                    counts=None, dark=False, return_rate=False, device=0):  # fmt: skip
+    """
+    Electrons per pixel of one exposure from a noiseless scene (reference sim_to_isim.py:636-648):
+    ``counts += Poisson(clip(C * t * g / g_ideal * image * this_flat / area_ratio, 0))`` with
+    ``t = read_time * (last read - first read)``.
+
+    image : float32 (na, na), e/s per ideal pixel; area_ratio : pixel area / Omega_ideal (na, na) or None;
+    counts : int32 (na, na) to accumulate into (the reference adds to romanisim's dark/sky counts) or None;
+    dark : also draw the dark electrons Poisson(this_dark * t) (romanisim's term, restated).
+    """
+    cal = caldir if isinstance(caldir, CalDir) else CalDir(caldir, device)
+    try:
+        t = float(read_time) * (read_pattern[-1][-1] - read_pattern[0][0])
+        img = np.ascontiguousarray(image, dtype=np.float32)
+        if img.shape != (cal.na, cal.na):
+            raise ValueError(f"image must cover the active array ({cal.na},{cal.na}), got {img.shape}")
+        ar = None if area_ratio is None else _lib.as_float_plane(area_ratio)
+        acc = counts is not None
+        out = np.ascontiguousarray(counts, dtype=np.int32).copy() if acc else np.empty((cal.na, cal.na), np.int32)
+        rate = np.empty((cal.na, cal.na), np.float64) if return_rate else None
+        _lib.check(_lib.lib().rip_sim_counts_host(cal.handle, _lib.ptr(img), _lib.ptr(ar),
+                                                  _lib.float_tag(ar) if ar is not None else _lib.RIP_F32, t, float(cnorm),
+                                                  float(pars.g_ideal), t if dark else 0.0, _seed_from(rng, seed),
+                                                  _lib.ptr(out), int(acc), _lib.ptr(rate)))  # fmt: skip
+    finally:
+        if cal is not caldir:
+            cal.close()
+    return (out, rate) if return_rate else out
+
+
+__all__ = ["make_l1_fullcal", "read_pattern_from_reads", "fwd_params", "noise_1f_frame", "fill_in_refdata_and_1f",
+           "sim_calprep", "simulate_counts", "pars"]  # fmt: skip

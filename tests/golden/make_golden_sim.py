@@ -98,11 +98,60 @@ def main():
     d = np.clip(d, -0.1 * fl, None)
     od, ofl, og = O.sim_calprep(cal)
     assert np.array_equal(od, d) and np.array_equal(ofl, fl)
+    # CombinedMask.build / PixelMask1 of the unmodified reference (needs an astropy.io.fits stub to import) and the
+    # moment sums of validation_tests/many_realizations.py:74-83 executed line by line
+    ast_mod, ast_io, ast_fits = types.ModuleType("astropy"), types.ModuleType("astropy.io"), types.ModuleType("astropy.io.fits")
+    ast_mod.io, ast_io.fits = ast_io, ast_fits
+    sys.modules.update({"astropy": ast_mod, "astropy.io": ast_io, "astropy.io.fits": ast_fits})
+    from romanimpreprocess.utils import maskhandling as ref_mh
+
+    mrng = np.random.RandomState(99)
+    nm = 96
+    dq = np.zeros((nm, nm), np.uint32)
+    for bit in range(32):
+        hits = mrng.rand(nm, nm) < (0.004 if bit not in (0, 12) else 0.02)
+        dq |= np.where(hits, np.uint32(1 << bit), np.uint32(0)).astype(np.uint32)
+    dq[0, :7] |= np.uint32(1 << 3)  # a 5x5 grower on the edge
+    dq[-1, -1] |= np.uint32(1 << 10)
+    ref_mask = ref_mh.PixelMask1.build(dq)
+    assert np.array_equal(ref_mask, O.mask_build(dq))
+    custom = ref_mh.CombinedMask({"jump_det": 25, "hot": 5, 7: 9, "saturated": 1})
+    ref_mask_c = custom.build(dq)
+    assert np.array_equal(ref_mask_c, O.mask_build(dq, {2: 25, 11: 5, 7: 9, 1: 1}))
+    mom_ref = np.zeros((3, nm, nm), dtype=np.float32)
+    mom_ora = np.zeros((3, nm, nm), dtype=np.float32)
+    mdata, mdq = [], []
+    for j in range(5):
+        dat = (mrng.randn(nm, nm) * 3 + 1.5).astype(np.float32)
+        dqj = np.where(mrng.rand(nm, nm) < 0.3, dq, np.uint32(0)).astype(np.uint32)
+        if j == 0:
+            dqj[5:9, 5:9] |= np.uint32(1)  # masked in every realisation -> sentinel
+        else:
+            dqj[5:9, 5:9] = dqj[5:9, 5:9] | np.uint32(1)
+        w = np.logical_not(ref_mh.PixelMask1.build(dqj))
+        mom_ref[0, :, :] += np.where(w, 1, 0.0)
+        mom_ref[1, :, :] += np.where(w, dat, 0.0)
+        mom_ref[2, :, :] += np.where(w, dat**2, 0.0)
+        O.moments_accumulate(mom_ora, dat, dqj)
+        mdata.append(dat)
+        mdq.append(dqj)
+    mom_sum = mom_ref.copy()
+    mom_ref[1:, :, :] /= mom_ref[0, :, :] + 1e-25
+    mom_ref[2, :, :] = np.sqrt(np.clip(mom_ref[2, :, :] - mom_ref[1, :, :] ** 2, 0, None))
+    mom_ref[1:, :, :] = np.where(mom_ref[0, :, :][None, :, :] > 0.1, mom_ref[1:, :, :], -1000.0)
+    assert np.array_equal(mom_sum, mom_ora)
+    O.moments_finalize(mom_ora)
+    assert np.array_equal(mom_ref, mom_ora)
+    np.savez_compressed(
+        os.path.join(HERE, "mask_moments.npz"), dq=dq, mask_pixelmask1=ref_mask, mask_custom=ref_mask_c,
+        data=np.array(mdata), dqs=np.array(mdq), moments_sum=mom_sum, moments_final=mom_ref,
+    )
     np.savez_compressed(
         os.path.join(HERE, "sim_refdata_n256.npz"), im0=im0, frame_seed11=f_ref, this_dark=d, this_flat=fl,
         n=N, G=G, seed=SEED, **out,
     )
-    print("oracle == reference for noise_1f_frame, fill_in_refdata_and_1f (3 modes), sim_calprep; golden written")
+    print("oracle == reference for noise_1f_frame, fill_in_refdata_and_1f (3 modes), sim_calprep, CombinedMask.build, "
+          "moment sums; golden written")
 
 
 if __name__ == "__main__":

@@ -1,0 +1,312 @@
+"""GPU: the forward-path rows either side of make_l1_fullcal (a15, a20) and the many-realisations
+bookkeeping (BASELINE configs[4]).
+
+Deterministic steps are checked EXACTLY (golden vectors made by the unmodified reference functions, or the oracle
+on the same inputs); everything driven by random numbers is validated statistically against the oracle's ensembles
+(the kernels use Philox, the reference GalSim deviates)."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+from conftest import load_golden
+
+from oracle import rip_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_cal(n, G, seed):
+    from romanimpreprocess_b200 import synth
+
+    pattern = [[0], [1, 2], [3, 4, 5, 6]][:G]
+    return synth.make_caldir(n=n, read_pattern=pattern, p_order=3, seed=seed), pattern
+
+
+def _trees(cal):
+    return {k: v["roman"] for k, v in cal.items()}
+
+
+def test_sim_calprep_exact():
+    """this_dark / this_flat of Image2D.simulate (sim_to_isim.py:615-633) == the reference's own ipc_rev + clips."""
+    from romanimpreprocess_b200.from_sim import sim_to_isim as s2i
+
+    g = load_golden("sim_refdata_n256")
+    cal, _ = _small_cal(int(g["n"]), int(g["G"]), int(g["seed"]))
+    d, f = s2i.sim_calprep(cal)
+    # the fixture's gain plane is float64, so the reference's planes are float64; the library returns float32
+    assert np.array_equal(f, g["this_flat"].astype(np.float32))
+    assert np.allclose(d, g["this_dark"], rtol=1e-5, atol=1e-7)  # (the float64 product dark*gain is rounded to float32 first)
+    # all-float32 CALDIR: identical to the oracle (itself pinned to the reference on the float64 fixture)
+    from romanimpreprocess_b200 import synth
+
+    cal32 = synth.make_caldir(n=128, read_pattern=[[0], [1, 2]], p_order=3, seed=5, gain_dtype=np.float32)
+    d32, f32 = s2i.sim_calprep(cal32)
+    od, of, _ = orc.sim_calprep(_trees(cal32))
+    assert od.dtype == np.float32 and np.array_equal(f32, of) and np.array_equal(d32, od)
+
+
+@pytest.mark.parametrize("n", [256, 4096])
+def test_noise_1f_frame_from_draws(n):
+    """Same N(0,1) stream as the reference call -> same block up to the float32 FFT rounding (the reference
+    transforms in complex128 and casts the block to float32)."""
+    from romanimpreprocess_b200.from_sim import sim_to_isim as s2i
+
+    cw = n // 32
+    m = 2 * n * cw
+    draws = np.zeros(2 * m)
+    orc.NormalStream(11).generate(draws)
+    ref = orc.noise_1f_frame(orc.NormalStream(11), n, cw)
+    if n == 256:
+        assert np.array_equal(ref, load_golden("sim_refdata_n256")["frame_seed11"])
+    out = s2i.noise_1f_frame(None, nside=n, draws=draws[None])
+    assert out.shape == ref.shape and out.dtype == np.float32
+    assert np.abs(out - ref).max() < 2e-5 * ref.std() * np.log2(m)
+
+
+def test_noise_1f_frame_statistics():
+    """Philox-driven blocks: zero mean per block, the variance and the 1/f spectrum of the oracle's ensemble."""
+    from romanimpreprocess_b200.from_sim import sim_to_isim as s2i
+
+    n, nf = 256, 48
+    out = s2i.noise_1f_frame(None, nside=n, seed=5, nframes=nf)
+    ref = np.array([orc.noise_1f_frame(orc.NormalStream(100 + i), n, n // 32) for i in range(nf)])
+    assert np.all(np.abs(out.reshape(nf, -1).mean(axis=1)) < 1e-5)
+    assert abs(out.std() / ref.std() - 1.0) < 0.08  # (the lowest modes dominate the variance: large sample scatter)
+    assert not np.allclose(out[0], out[1])
+
+    def spectrum(fr):
+        p = (np.abs(np.fft.rfft(fr.reshape(nf, -1).astype(np.float64), axis=1)) ** 2).mean(axis=0)[1:]
+        edges = np.unique(np.round(np.logspace(0, np.log10(p.size), 14)).astype(int))
+        return np.array([p[a:b].mean() for a, b in zip(edges[:-1], edges[1:])])
+
+    ps, pr = spectrum(out), spectrum(ref)
+    assert np.all(np.abs(ps / pr - 1.0) < 0.25), ps / pr
+    assert ps[0] / ps[-1] > 50  # red spectrum
+
+
+def test_fill_refdata_deterministic_part_exact():
+    """With the white-noise planes set to zero and no banding, reference pixels = round(dark cube) and active pixels
+    are untouched: identical to the oracle (and to the reference, via the golden pinning of the oracle)."""
+    from romanimpreprocess_b200.from_sim import sim_to_isim as s2i
+
+    n, G = 256, 3
+    cal, pattern = _small_cal(n, G, 4242)
+    cal["read"]["roman"]["data"] = np.zeros_like(cal["read"]["roman"]["data"])
+    cal["read"]["roman"]["resetnoise"] = np.zeros_like(cal["read"]["roman"]["resetnoise"])
+    tij = orc.read_pattern_to_tij(pattern)
+    im0 = np.random.RandomState(1).randint(0, 60000, size=(G, n, n)).astype(np.uint16)
+    im_o, im_g = im0.copy(), im0.copy()
+    orc.fill_in_refdata_and_1f(im_o, _trees(cal), orc.NormalStream(3), tij, fill_in_banding=False)
+    s2i.fill_in_refdata_and_1f(im_g, cal, 7, tij, fill_in_banding=False)
+    assert np.array_equal(im_g, im_o)
+    assert np.array_equal(im_g[:, 4:-4, 4:-4], im0[:, 4:-4, 4:-4])
+
+
+def test_fill_refdata_statistics():
+    """Reference-pixel white noise, banding amplitude / common mode / mirroring, and the reference output, against
+    the oracle's ensemble statistics."""
+    from romanimpreprocess_b200.from_sim import sim_to_isim as s2i
+
+    n, G = 256, 3
+    cal, pattern = _small_cal(n, G, 4242)
+    c = _trees(cal)
+    cw = n // 32
+    tij = orc.read_pattern_to_tij(pattern)
+    base = np.full((G, n, n), 30000, np.uint16)
+    # (1) white part of the reference pixels: z = (value - dark) / sigma ~ N(0, 1 + 1/12 rounding)
+    im = base.copy()
+    s2i.fill_in_refdata_and_1f(im, cal, 11, tij, fill_in_banding=False)
+    border = np.ones((n, n), bool)
+    border[4:-4, 4:-4] = False
+    dk = c["dark"]["data"][-G:]
+    for g in range(G):
+        sig = np.sqrt(c["read"]["data"] ** 2 / len(pattern[g]) + c["read"]["resetnoise"] ** 2)
+        z = ((im[g].astype(np.float64) - dk[g]) / sig)[border]
+        assert abs(z.mean()) < 4 / np.sqrt(z.size) + 0.01
+        assert abs(z.var() - 1.0) < 0.05
+    # the reset layer is common to all groups: differences of groups lose it
+    d01 = (im[0].astype(np.float64) - dk[0]) - (im[1].astype(np.float64) - dk[1])
+    expect = c["read"]["data"] ** 2 * (1.0 / len(pattern[0]) + 1.0 / len(pattern[1]))
+    assert abs((d01[border] ** 2 / expect[border]).mean() - 1.0) < 0.08
+    # (2) banding on a constant cube: compare with the oracle ensemble
+    nr = 6
+    gb, ob = [], []
+    for r in range(nr):
+        a = base.copy()
+        a33 = np.zeros((G, n, cw), np.uint16)
+        s2i.fill_in_refdata_and_1f(a, cal, 100 + r, tij, fill_in_banding=True, amp33=a33)
+        gb.append(a[:, 4:-4, 4:-4].astype(np.float64) - 30000)
+        b = base.copy()
+        orc.fill_in_refdata_and_1f(b, c, orc.NormalStream(500 + r), tij, fill_in_banding=True)
+        ob.append(b[:, 4:-4, 4:-4].astype(np.float64) - 30000)
+    gb, ob = np.array(gb), np.array(ob)
+    for g in range(G):
+        assert abs(gb[:, g].std() / ob[:, g].std() - 1.0) < 0.15, (g, gb[:, g].std(), ob[:, g].std())
+
+    def chan(a, ch):  # active rows of channel ch (interior channels only: no border columns)
+        return a[..., :, cw * ch - 4 : cw * (ch + 1) - 4]
+
+    def corr(x, y):
+        x, y = x - x.mean(), y - y.mean()
+        return (x * y).mean() / np.sqrt((x * x).mean() * (y * y).mean())
+
+    u, cc = float(c["read"]["anc"]["U_PINK"]), float(c["read"]["anc"]["C_PINK"])
+    rho = cc**2 / (cc**2 + u**2)
+    same = corr(chan(gb, 2), chan(gb, 4))
+    mirrored = corr(chan(gb, 2), chan(gb, 3)[..., ::-1])
+    unmirrored = corr(chan(gb, 2), chan(gb, 3))
+    assert abs(same - rho) < 0.08 and abs(mirrored - rho) < 0.08, (same, mirrored, rho)
+    assert unmirrored < mirrored - 0.05
+
+
+def test_fill_refdata_amp33_full_frame():
+    """4096^2 (128-column channels): the reference output follows med + noise with the oracle's scatter."""
+    from romanimpreprocess_b200 import synth
+    from romanimpreprocess_b200.from_sim import sim_to_isim as s2i
+
+    n, G = 4096, 2
+    pattern = [[0], [1, 2]]
+    cal = synth.make_caldir(n=n, read_pattern=pattern, p_order=3, seed=9)
+    c = _trees(cal)
+    tij = orc.read_pattern_to_tij(pattern)
+    im = np.full((G, n, n), 20000, np.uint16)
+    a33 = np.zeros((G, n, 128), np.uint16)
+    s2i.fill_in_refdata_and_1f(im, cal, 21, tij, fill_in_banding=True, amp33=a33)
+    imo = np.full((G, n, n), 20000, np.uint16)
+    a33o = np.zeros((G, n, 128), np.uint16)
+    orc.fill_in_refdata_and_1f(imo, c, orc.NormalStream(8), tij, fill_in_banding=True, amp33=a33o)
+    med = c["read"]["amp33"]["med"]
+    for g in range(G):
+        rg, ro = a33[g].astype(np.float64) - med, a33o[g].astype(np.float64) - med
+        assert abs(rg.mean() - ro.mean()) < 0.3  # truncation bias -0.5 in both
+        assert abs(rg.std() / ro.std() - 1.0) < 0.1, (rg.std(), ro.std())
+        bg, bo = im[g, 4:-4, 4:-4].astype(np.float64) - 20000, imo[g, 4:-4, 4:-4].astype(np.float64) - 20000
+        assert abs(bg.std() / bo.std() - 1.0) < 0.2, (bg.std(), bo.std())
+    # reference output and science channels share the common mode (M_PINK * C_PINK * common)
+    row_sci = (im[1, 4:-4, 4:-4].astype(np.float64) - 20000).mean(axis=1)
+    row_ref = (a33[1, 4:-4].astype(np.float64) - med[4:-4]).mean(axis=1)
+    row_sci_o = (imo[1, 4:-4, 4:-4].astype(np.float64) - 20000).mean(axis=1)
+    row_ref_o = (a33o[1, 4:-4].astype(np.float64) - med[4:-4]).mean(axis=1)
+    cg, co = np.corrcoef(row_sci, row_ref)[0, 1], np.corrcoef(row_sci_o, row_ref_o)[0, 1]
+    assert cg > 0.3 and abs(cg - co) < 0.25, (cg, co)
+
+
+def test_sim_counts_statistics():
+    """Poisson mean == the oracle's scene_rate; counts are Poisson with that mean (both samplers: lam < 10 and PTRS)."""
+    from romanimpreprocess_b200.from_sim import sim_to_isim as s2i
+
+    n, G = 256, 3
+    cal, pattern = _small_cal(n, G, 4242)
+    c = _trees(cal)
+    na = n - 8
+    yy, xx = np.mgrid[0:na, 0:na]
+    image = (0.01 + 0.02 * (xx % 7) + 40.0 * np.exp(-0.5 * ((xx - 120) ** 2 + (yy - 90) ** 2) / 30.0**2)).astype(np.float32)
+    image[:3] = -1.0  # negative scene values clip to zero electrons
+    area = (1.0 + 0.01 * np.sin(xx / 40.0)).astype(np.float64)
+    counts, rate = s2i.simulate_counts(image, cal, pattern, seed=3, area_ratio=area, cnorm=0.9, return_rate=True)
+    this_dark, this_flat, g = orc.sim_calprep(c)
+    t = 3.04 * (pattern[-1][-1] - pattern[0][0])
+    ref_rate = orc.scene_rate(image, this_flat, g, area, t, cnorm=0.9)
+    assert np.allclose(rate, ref_rate, rtol=2e-6, atol=1e-9)
+    assert counts.dtype == np.int32 and np.all(counts >= 0) and np.all(counts[:3] == 0)
+    for lo, hi in ((0.05, 10.0), (10.0, 1e9)):
+        w = (rate > lo) & (rate < hi)
+        assert w.sum() > 5000
+        z = (counts[w] - rate[w]) / np.sqrt(rate[w])
+        assert abs(z.mean()) < 5 / np.sqrt(w.sum()), (lo, z.mean())
+        assert abs(z.var() - 1.0) < 0.05, (lo, z.var())
+    # dark term + accumulation
+    c2 = s2i.simulate_counts(np.zeros_like(image), cal, pattern, seed=4, counts=counts, dark=True)
+    d = (c2 - counts).astype(np.float64)
+    lam = np.clip(this_dark, 0, None) * t
+    assert np.all(d >= 0) and abs(d.mean() - lam.mean()) < 5 * np.sqrt(lam.mean() / d.size) + 1e-3
+
+
+def test_mask_build_exact():
+    from romanimpreprocess_b200.utils import maskhandling
+
+    g = load_golden("mask_moments")
+    assert np.array_equal(maskhandling.PixelMask1.build(g["dq"]), g["mask_pixelmask1"])
+    custom = maskhandling.CombinedMask({"jump_det": 25, "hot": 5, 7: 9, "saturated": 1})
+    assert np.array_equal(custom.build(g["dq"]), g["mask_custom"])
+    big = np.random.RandomState(5).randint(0, 2**32, size=(300, 517), dtype=np.uint64).astype(np.uint32)
+    big &= np.random.RandomState(6).randint(0, 2**32, size=big.shape, dtype=np.uint64).astype(np.uint32)
+    big &= np.random.RandomState(7).randint(0, 2**32, size=big.shape, dtype=np.uint64).astype(np.uint32)
+    big &= np.random.RandomState(8).randint(0, 2**32, size=big.shape, dtype=np.uint64).astype(np.uint32)
+    assert np.array_equal(maskhandling.PixelMask1.build(big), orc.mask_build(big))
+
+
+def test_moments_and_median_exact():
+    """Moment sums / finalisation bit-exact against the reference's lines; stack median == np.median."""
+    import torch
+
+    from romanimpreprocess_b200 import _lib
+    from romanimpreprocess_b200.utils import maskhandling
+
+    g = load_golden("mask_moments")
+    nm = g["dq"].shape[0]
+    n, nb = nm + 8, 4
+    lib = _lib.lib()
+    dev = torch.device("cuda", 0)
+    mom = torch.zeros((3, nm, nm), dtype=torch.float32, device=dev)
+    grow = np.ascontiguousarray(maskhandling.PixelMask1.array)
+    for dat, dq in zip(g["data"], g["dqs"]):
+        full = np.full((n, n), np.nan, np.float32)
+        full[nb:-nb, nb:-nb] = dat
+        fdq = np.full((n, n), 0xFFFFFFFF, np.uint32)  # border flags must not leak into the window
+        fdq[nb:-nb, nb:-nb] = dq
+        ds = torch.from_numpy(full).to(dev)
+        dd = torch.from_numpy(fdq.view(np.int32)).to(dev)
+        _lib.check(lib.rip_moments_accumulate_dev(0, C.c_void_p(ds.data_ptr()), C.c_void_p(dd.data_ptr()), n, nb,
+                                                  _lib.ptr(grow), C.c_void_p(mom.data_ptr()), None))  # fmt: skip
+    torch.cuda.synchronize()
+    assert np.array_equal(mom.cpu().numpy(), g["moments_sum"])
+    _lib.check(lib.rip_moments_finalize_dev(0, C.c_void_p(mom.data_ptr()), nm * nm, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(mom.cpu().numpy(), g["moments_final"])
+    rng = np.random.RandomState(3)
+    for R in (1, 2, 5, 8, 9, 33, 64, 100):
+        st = rng.randn(R, 5000).astype(np.float32)
+        st[:, 7] = 1.0
+        if R > 2:
+            st[1, 11] = np.nan
+            st[2, 13] = np.inf
+        d = torch.from_numpy(st).to(dev)
+        o = torch.empty(5000, dtype=torch.float32, device=dev)
+        _lib.check(lib.rip_stack_median_dev(0, C.c_void_p(d.data_ptr()), R, 5000, C.c_void_p(o.data_ptr()), None))
+        torch.cuda.synchronize()
+        with np.errstate(all="ignore"):
+            ref = np.median(st, axis=0)
+        assert np.array_equal(o.cpu().numpy(), ref, equal_nan=True), R
+
+
+def test_many_realizations_small():
+    """The whole protocol at 256^2: scene -> counts -> ramp -> reference pixels + 1/f -> L1->L2 -> moments.
+    The mean slope recovers the scene (in DN/s) and the realisation scatter matches the reported error."""
+    from romanimpreprocess_b200 import pars, synth
+    from romanimpreprocess_b200.validation_tests import many_realizations as mr
+
+    n, R = 256, 12
+    rp = synth.README_PATTERN
+    cal = synth.make_caldir(n=n, read_pattern=rp, p_order=10, seed=77)
+    c = _trees(cal)
+    na = n - 8
+    yy, xx = np.mgrid[0:na, 0:na]
+    image = (20.0 + 0.1 * xx).astype(np.float32)  # e/s
+    slope_ideal = np.zeros((n, n), np.float32)
+    slope_ideal[4:-4, 4:-4] = image / pars.g_ideal
+    out = mr.run(image, cal, rp, R, seed=100, slope_ideal=slope_ideal)
+    assert out.shape == (8, n, n)
+    cnt, mean, std, bias, mederr = out[3], out[4], out[5], out[6], out[7]
+    act = np.zeros((n, n), bool)
+    act[8:-8, 8:-8] = True
+    good = act & (cnt >= R - 1)
+    assert good.mean() > 0.5 * act.mean()
+    # dark electrons are drawn by the forward model and the dark slope is subtracted by the calibration
+    rel = bias[good] / slope_ideal[good]
+    assert abs(np.median(rel)) < 0.02, np.median(rel)
+    ratio = np.median(std[good] / mederr[good])
+    assert 0.8 < ratio < 1.25, ratio
+    assert np.all(out[1][act] > 0)  # median group difference: the signal accumulates
+    del c

@@ -243,3 +243,18 @@ def test_sim_refdata_golden():
             assert np.array_equal(a33, g[f"{tag}_amp33"]), tag
     d, fl, _ = orc.sim_calprep(cal)
     assert np.array_equal(d, g["this_dark"]) and np.array_equal(fl, g["this_flat"])
+
+
+def test_mask_and_moments_golden():
+    """CombinedMask.build / PixelMask1 (reference utils/maskhandling.py:82-117,152-178) and the moment sums of
+    validation_tests/many_realizations.py:74-83 against the unmodified reference (tests/golden/make_golden_sim.py)."""
+    g = load_golden("mask_moments")
+    assert np.array_equal(orc.mask_build(g["dq"]), g["mask_pixelmask1"])
+    assert np.array_equal(orc.mask_build(g["dq"], {2: 25, 11: 5, 7: 9, 1: 1}), g["mask_custom"])
+    mom = np.zeros_like(g["moments_sum"])
+    for dat, dq in zip(g["data"], g["dqs"]):
+        orc.moments_accumulate(mom, dat, dq)
+    assert np.array_equal(mom, g["moments_sum"])
+    orc.moments_finalize(mom)
+    assert np.array_equal(mom, g["moments_final"])
+    assert np.any(mom[1] == -1000.0)
