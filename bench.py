@@ -491,6 +491,73 @@ def run_forward(args):
     cd.close()
 
 
+def run_realizations(args):
+    """Secondary workload (BASELINE configs[4], not the headline line): validation_tests/many_realizations protocol,
+    `--realizations` noise realisations of one 4096^2 SCA (scene electrons -> forward ramp -> reference pixels + 1/f +
+    amp33 -> fused L1->L2 -> grown mask + moment sums), device resident.  Realisations are split over the ranks; the
+    three moment planes are summed with one NCCL all-reduce inside the timed region (the only exchange step)."""
+    import torch
+    import torch.distributed as dist
+
+    from romanimpreprocess_b200 import pars, synth
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+    from romanimpreprocess_b200.validation_tests import many_realizations as mr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rp = synth.README_PATTERN
+    n = args.n
+    cal, _, area = make_inputs(n, rp, 2, seed=1000)  # the same SCA on every rank
+    cd = gci.CalDir(cal, device=local)
+    na = n - 8
+    yy, xx = np.mgrid[0:na, 0:na].astype(np.float32)
+    image = (3.0 + 0.002 * xx + 400.0 * np.exp(-0.5 * (((xx % 512) - 256) ** 2 + ((yy % 512) - 256) ** 2) / 9.0)).astype(np.float32)
+    R = args.realizations
+    mine = [j for j in range(R) if j % world == rank]
+    rz = mr.Realizations(image, cd, rp, area_ratio=area, config2={"SLICEOUT": True}, device=local, keep_stacks=0)
+    for w in range(max(args.warmup, 1)):
+        rz.step(7 + w)
+    rz.d_moments.zero_()
+    rz.done = 0
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for j in mine:
+        rz.step(100 + 10 * (j + 1))
+    if world > 1:
+        dist.all_reduce(rz.d_moments)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    out = rz.finalize(slope_ideal=None)
+    if rank == 0:
+        good = out[3, 8:-8, 8:-8] >= R - 1
+        ideal = np.zeros((n, n), np.float32)
+        ideal[4:-4, 4:-4] = image / pars.g_ideal
+        bias = np.median((out[4] - ideal)[8:-8, 8:-8][good] / ideal[8:-8, 8:-8][good])
+        print(json.dumps({"metric": "many-realisations SCA realisations/s (scene -> L1 -> L2 -> moments, 4096^2 x 8 resultants)",
+                          "value": R / (float(ms.item()) * 1e-3), "unit": "realisations/s", "n_gpus": world,
+                          "realizations": R, "ms_per_realization_per_gpu": float(ms.item()) / max(len(mine), 1),
+                          "scaling": "strong", "dtype": "f64+f32", "data": "synthetic", "secondary_workload": True,
+                          "exchange": "one NCCL all-reduce of the 3 moment planes (200 MB)" if world > 1 else "none",
+                          "check": {"unmasked_in_all_fraction": float(good.mean()), "median_relative_bias": float(bias)}}),
+              flush=True)  # fmt: skip
+    rz.close()
+    cd.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -505,7 +572,8 @@ def main():
     ap.add_argument("--cpu-tile", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (for ncu captures)")
-    ap.add_argument("--workload", default="l1l2", choices=["l1l2", "forward"],
+    ap.add_argument("--realizations", type=int, default=64, help="noise realisations (workload realizations)")
+    ap.add_argument("--workload", default="l1l2", choices=["l1l2", "forward", "realizations"],
                     help="l1l2 = the headline metric; forward = secondary line for the forward ramp generator")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -513,6 +581,8 @@ def main():
         run_reference(args)
     elif args.workload == "forward":
         run_forward(args)
+    elif args.workload == "realizations":
+        run_realizations(args)
     else:
         run_ours(args)
 

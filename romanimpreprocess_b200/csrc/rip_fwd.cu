@@ -20,13 +20,53 @@ __device__ __forceinline__ double stirling_tail(double k) {
     return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / kp1sq) / kp1sq) / (k + 1.0);
 }
 
-// Binomial(n, p) sampler: inversion for n*min(p,1-p) < 10, Hormann's BTRS transformed rejection otherwise.
+// Binomial(n, p) sampler: sequential inversion of the CDF (BINV) for n*min(p,1-p) < 10, Hormann's BTRS transformed
+// rejection otherwise.  For n < 2^22 (every realistic well) the set-up, the inversion recurrence and the BTRS squeeze
+// run in float32 (integers up to n are exact; the relative error 1e-7 of the probabilities is far below anything a
+// realisation ensemble can resolve); the rarely reached exact acceptance test of BTRS and larger n use float64.
 __device__ long binomial_draw(Philox& rng, long n, double p) {
     if (n <= 0 || p <= 0.0) return 0;
     if (p >= 1.0) return n;
     const bool flip = p > 0.5;
     const double q = flip ? 1.0 - p : p;
     long k;
+    if (n < (1L << 22)) {
+        const float nf = (float)n, qf = (float)q, omq = 1.0f - qf;
+        const float npq = nf * qf;
+        if (npq < 10.0f) {
+            const float f0 = expf(nf * log1pf(-qf)), s = qf / omq;
+            const float bound = fminf(nf, npq + 10.0f * sqrtf(npq * omq + 1.0f));
+            float x = 0.0f, f = f0, u = rng.uniform();
+            while (u > f) {
+                x += 1.0f;
+                if (x > bound) { x = 0.0f; f = f0; u = rng.uniform(); }
+                else { u -= f; f = ((nf - x + 1.0f) * s * f) / x; }
+            }
+            k = (long)x;
+        } else {
+            const float spq = sqrtf(npq * omq);
+            const float b = 1.15f + 2.53f * spq, a = -0.0873f + 0.0248f * b + 0.01f * qf, c = npq + 0.5f;
+            const float vr = 0.92f - 4.2f / b;
+            for (;;) {
+                const float u = rng.uniform() - 0.5f;
+                const float v = rng.uniform();
+                const float us = 0.5f - fabsf(u);
+                const float kk = floorf((2.0f * a / us + b) * u + c);
+                if (kk < 0.0f || kk > nf) continue;
+                if (us >= 0.07f && v <= vr) { k = (long)kk; break; }
+                const double nd = (double)n, kd = (double)kk, usd = (double)us;
+                const double r = q / (1.0 - q), alpha = (2.83 + 5.1 / (double)b) * (double)spq;
+                const double m = floor((nd + 1.0) * q);
+                const double lv = log((double)v * alpha / ((double)a / (usd * usd) + (double)b));
+                const double ub = (m + 0.5) * log((m + 1.0) / (r * (nd - m + 1.0))) +
+                                  (nd + 1.0) * log((nd - m + 1.0) / (nd - kd + 1.0)) +
+                                  (kd + 0.5) * log(r * (nd - kd + 1.0) / (kd + 1.0)) + stirling_tail(m) +
+                                  stirling_tail(nd - m) - stirling_tail(kd) - stirling_tail(nd - kd);
+                if (lv <= ub) { k = (long)kk; break; }
+            }
+        }
+        return flip ? n - k : k;
+    }
     if ((double)n * q < 10.0) {
         // sequential inversion via geometric waiting times
         const double lq = log1p(-q);
@@ -173,7 +213,15 @@ static int il_apply_device(const void* d_counts, int c_dtype, const void* d_star
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K3: forward ramp.  One CTA = TX x TY active pixels (+1 halo for the IPC stencil); loop over reads.
+// K3: forward ramp, two kernels.
+//   fwd_apportion_kernel  one thread per active pixel: reset-noise electrons (start_e) and the cumulative electrons
+//                         at every read (binomial apportioning of the exposure's total) -> HBM (4 B per pixel and read;
+//                         140 MB per read plane set at 4096^2 -- the divergent, log-heavy sampler stays out of the
+//                         arithmetic kernel and no halo pixel is ever drawn twice)
+//   fwd_ramp_kernel       one CTA = 32 x 8 active pixels, all threads owners; per read: (32+2) x (8+2) halo tile of
+//                         electrons in shared memory, IPC 3x3, /gain, certified fast inverse (rip_math.cuh
+//                         invlin_fast_z: the z of the reference's 24-step float64 search with ~2-3 Newton
+//                         evaluations + the last few exact ones instead of 24), group mean, read noise, biascorr
 // ---------------------------------------------------------------------------------------------------------
 struct FwdArgs {
     int n, nb, na, G, P, n_reads;
@@ -185,7 +233,11 @@ struct FwdArgs {
     double biascorr_t0;
     int has_bias;
     const int32_t* counts;      // [na,na] total electrons of the exposure (already Poisson)
-    const int32_t* cum_counts;  // [n_reads,na,na] optional externally apportioned cumulative counts (tests)
+    int32_t* cum;               // [n_reads,na,na] cumulative electrons per read (written by the apportioning kernel
+                                //  unless supplied by the caller: tests)
+    int cum_given;
+    float* start;               // [na,na] electrons in the well at the reset
+    const float* linA; const float* linm;  // [n,n] certificate planes of the fast inverse
     const float* coefs; const float* Smin; const float* Smax;  // full-frame planes
     const void* gain; const void* ipc; const float* read; const float* resetnoise; const float* dark_slope;
     const float* bias;          // [G,na,na] or null (offset applied)
@@ -194,56 +246,103 @@ struct FwdArgs {
 
 constexpr int FTX = 32, FTY = 8;
 
-template <int PMAX, typename TG, typename TK>
-__global__ void __launch_bounds__((FTX + 2) * (FTY + 2)) fwd_ramp_kernel(const FwdArgs A) {
-    __shared__ double se[FTY + 2][FTX + 2];  // electrons in the well at this read (counts so far + start_e)
-    const int tx = threadIdx.x % (FTX + 2), ty = threadIdx.x / (FTX + 2);
-    const int xa = blockIdx.x * FTX + tx - 1, ya = blockIdx.y * FTY + ty - 1;  // active coords incl. halo
+__global__ void invlin_certify_kernel(const float* __restrict__ coefs, int P, long npl, float* __restrict__ linA,
+                                      float* __restrict__ linm) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npl) return;
+    float c[RIP_PMAX];
+#pragma unroll
+    for (int L = 0; L < RIP_PMAX; ++L) c[L] = (L < P) ? coefs[(long)L * npl + p] : 0.0f;
+    float A, m;
+    invlin_certify<RIP_PMAX>(c, P, A, m);
+    linA[p] = A;
+    linm[p] = m;
+}
+
+template <typename TG>
+__global__ void __launch_bounds__(128) fwd_apportion_kernel(const FwdArgs A) {
+    const int xa = blockIdx.x * blockDim.x + threadIdx.x, ya = blockIdx.y;
     const int na = A.na, n = A.n, nb = A.nb;
-    const bool inside = (xa >= 0 && xa < na && ya >= 0 && ya < na);
-    const bool owner = inside && tx >= 1 && tx <= FTX && ty >= 1 && ty <= FTY;
+    if (xa >= na) return;
+    const long pa = (long)ya * na + xa, pf = (long)(ya + nb) * n + (xa + nb), npa = (long)na * na;
+    Philox rng;
+    rng.init(A.seed, (uint64_t)pa, 1u);
+    // reset noise in electrons (sim_to_isim.py:195-215): N(0,1)*resetnoise*gain - t0*dark_slope/gain, float32
+    const TG g = ((const TG*)A.gain)[pf];
+    float start_e = 0.0f;
+    if (A.add_reset_noise) {
+        float rn = rng.normal();
+        rn = rn * A.resetnoise[pf];
+        rn = (float)((typename Promote<float, TG>::type)rn * (typename Promote<float, TG>::type)g);
+        start_e = rn;
+    }
+    if (A.has_bias) {
+        typedef typename Promote<float, TG>::type TP;
+        // tbias * dark_slope / gain : python float * f32 array -> f32, / gain -> TP
+        const float td = (float)A.biascorr_t0 * A.dark_slope[pf];
+        start_e = (float)((TP)start_e - (TP)td / (TP)g);
+    }
+    A.start[pa] = start_e;
+    if (A.cum_given) return;
+    long remaining = 0;
+    if (A.counts) {
+        const long c = A.counts[pa];
+        remaining = c < 0 ? 0 : (c > 2000000000L ? 2000000000L : c);
+    }
+    const double t_last = A.read_time * (double)A.read_index[A.n_reads - 1];
+    double t_prev = 0.0;  // romanisim starts the clock at the reset
+    long cum = 0;
+    for (int k = 0; k < A.n_reads; ++k) {
+        const double t = A.read_time * (double)A.read_index[k];
+        if (remaining > 0 && t > t_prev) {
+            const double p = (t_last > t_prev) ? (t - t_prev) / (t_last - t_prev) : 1.0;
+            const long d = binomial_draw(rng, remaining, p >= 1.0 ? 1.0 : p);
+            cum += d;
+            remaining -= d;
+        }
+        t_prev = t;
+        A.cum[(long)k * npa + pa] = (int32_t)cum;
+    }
+}
+
+template <int P, typename TG, typename TK>
+__global__ void __launch_bounds__(FTX * FTY, 3) fwd_ramp_kernel(const FwdArgs A) {
+    __shared__ double se[FTY + 2][FTX + 2];  // electrons in the well at this read (counts so far + start_e)
+    __shared__ float ss[FTY + 2][FTX + 2];   // start_e of the tile + halo
+    const int tid = threadIdx.x, tx = tid % FTX, ty = tid / FTX;
+    const int x0 = blockIdx.x * FTX, y0 = blockIdx.y * FTY;
+    const int xa = x0 + tx, ya = y0 + ty;
+    const int na = A.na, n = A.n, nb = A.nb;
+    const bool owner = xa < na && ya < na;
     const long pa = (long)ya * na + xa;
     const long pf = (long)(ya + nb) * n + (xa + nb);
     const long npa = (long)na * na, npl = (long)n * n;
-    const TG* gainp = (const TG*)A.gain;
-    const TK* K = (const TK*)A.ipc;
-
-    Philox rng;
-    rng.init(A.seed, inside ? (uint64_t)pa : 0ull, 1u);
-    // reset noise in electrons (sim_to_isim.py:195-215): N(0,1)*resetnoise*gain - t0*dark_slope/gain, float32
-    float start_e = 0.0f;
-    long remaining = 0;
-    TG g = (TG)1;
-    if (inside) {
-        g = gainp[pf];
-        if (A.add_reset_noise) {
-            float rn = rng.normal();
-            rn = rn * A.resetnoise[pf];
-            rn = (float)((typename Promote<float, TG>::type)rn * (typename Promote<float, TG>::type)g);
-            start_e = rn;
-        }
-        if (A.has_bias) {
-            typedef typename Promote<float, TG>::type TP;
-            // tbias * dark_slope / gain : python float * f32 array -> f32, / gain -> TP
-            const float td = (float)A.biascorr_t0 * A.dark_slope[pf];
-            start_e = (float)((TP)start_e - (TP)td / (TP)g);
-        }
-        if (A.counts) {
-            long c = A.counts[pa];
-            remaining = c < 0 ? 0 : (c > 2000000000L ? 2000000000L : c);
-        }
-    }
-    float c[PMAX];
-    float smin = 0.f, smax = 1.f;
-    if (owner) {
+    constexpr int HALO = (FTX + 2) * (FTY + 2);
+    // the (at most two) halo-tile entries this thread stages per read
+    long hsrc[2];
+    int hpos[2];
 #pragma unroll
-        for (int L = 0; L < PMAX; ++L) c[L] = (L < A.P) ? A.coefs[(long)L * npl + pf] : 0.0f;
-        smin = A.Smin[pf];
-        smax = A.Smax[pf];
+    for (int q = 0; q < 2; ++q) {
+        const int e = tid + q * FTX * FTY;
+        hpos[q] = -1;
+        hsrc[q] = -1;
+        if (e < HALO) {
+            const int hy = e / (FTX + 2), hx = e - hy * (FTX + 2);
+            const int gx = x0 + hx - 1, gy = y0 + hy - 1;
+            hpos[q] = e;
+            if (gx >= 0 && gx < na && gy >= 0 && gy < na) hsrc[q] = (long)gy * na + gx;
+        }
     }
-    // IPC taps for the owner pixel (source-indexed kernel)
-    double kt[9];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+        if (hpos[q] >= 0) (&ss[0][0])[hpos[q]] = hsrc[q] >= 0 ? A.start[hsrc[q]] : 0.0f;
+
+    double cd[P];
+    float smin = 0.f, smax = 1.f, linA = 0.f, linm = 0.f;
+    TG g = (TG)1;
+    TK kt[9];
     bool kok[9];
+    const TK* K = (const TK*)A.ipc;
     {
         const int DY[9] = {0, 1, -1, 0, 0, 1, 1, -1, -1};
         const int DX[9] = {0, 0, 0, 1, -1, 1, -1, 1, -1};
@@ -251,48 +350,68 @@ __global__ void __launch_bounds__((FTX + 2) * (FTY + 2)) fwd_ramp_kernel(const F
         for (int q = 0; q < 9; ++q) {
             const int ys = ya - DY[q], xs = xa - DX[q];
             kok[q] = owner && K && ys >= 0 && ys < na && xs >= 0 && xs < na;
-            kt[q] = kok[q] ? (double)K[(long)((1 + DY[q]) * 3 + (1 + DX[q])) * npa + (long)ys * na + xs] : 0.0;
+            kt[q] = kok[q] ? K[(long)((1 + DY[q]) * 3 + (1 + DX[q])) * npa + (long)ys * na + xs] : (TK)0;
         }
     }
-    const double t_last = A.read_time * (double)A.read_index[A.n_reads - 1];
-    double t_prev = 0.0;  // romanisim starts the clock at the reset
-    long cum = 0;
+    if (owner) {
+#pragma unroll
+        for (int L = 0; L < P; ++L) cd[L] = (L < A.P) ? (double)A.coefs[(long)L * npl + pf] : 0.0;
+        smin = A.Smin[pf];
+        smax = A.Smax[pf];
+        linA = A.linA[pf];
+        linm = A.linm[pf];
+        g = ((const TG*)A.gain)[pf];
+    } else {
+#pragma unroll
+        for (int L = 0; L < P; ++L) cd[L] = 0.0;
+    }
+    const float half = (smax - smin) / 2.0f;  // f32 expression in the reference (ipc_linearity.py:390)
+    double root = 0.0;
+    bool have_root = false;
     int k = 0;
     for (int grp = 0; grp < A.G; ++grp) {
         double acc = 0.0;
         for (int r = 0; r < A.reads_per_group[grp]; ++r, ++k) {
-            const double t = A.read_time * (double)A.read_index[k];
-            if (inside) {
-                if (A.cum_counts) {
-                    cum = A.cum_counts[(long)k * npa + pa];
-                } else if (remaining > 0 && t > t_prev) {
-                    const double p = (t_last > t_prev) ? (t - t_prev) / (t_last - t_prev) : 1.0;
-                    const long d = binomial_draw(rng, remaining, p >= 1.0 ? 1.0 : p);
-                    cum += d;
-                    remaining -= d;
-                }
-            }
-            t_prev = t;
             __syncthreads();
-            se[ty][tx] = inside ? (double)(int32_t)cum + (double)start_e : 0.0;
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if (hpos[q] >= 0)
+                    (&se[0][0])[hpos[q]] = hsrc[q] >= 0 ? (double)A.cum[(long)k * npa + hsrc[q]] + (double)(&ss[0][0])[hpos[q]] : 0.0;
             __syncthreads();
             if (owner) {
+                const int sy = ty + 1, sx = tx + 1;
                 double conv;
                 if (K) {
-                    conv = se[ty][tx] * kt[0];
-                    if (kok[1]) conv = conv + se[ty - 1][tx] * kt[1];
-                    if (kok[2]) conv = conv + se[ty + 1][tx] * kt[2];
-                    if (kok[3]) conv = conv + se[ty][tx - 1] * kt[3];
-                    if (kok[4]) conv = conv + se[ty][tx + 1] * kt[4];
-                    if (kok[5]) conv = conv + se[ty - 1][tx - 1] * kt[5];
-                    if (kok[6]) conv = conv + se[ty - 1][tx + 1] * kt[6];
-                    if (kok[7]) conv = conv + se[ty + 1][tx - 1] * kt[7];
-                    if (kok[8]) conv = conv + se[ty + 1][tx + 1] * kt[8];
+                    conv = se[sy][sx] * (double)kt[0];
+                    if (kok[1]) conv = conv + se[sy - 1][sx] * (double)kt[1];
+                    if (kok[2]) conv = conv + se[sy + 1][sx] * (double)kt[2];
+                    if (kok[3]) conv = conv + se[sy][sx - 1] * (double)kt[3];
+                    if (kok[4]) conv = conv + se[sy][sx + 1] * (double)kt[4];
+                    if (kok[5]) conv = conv + se[sy - 1][sx - 1] * (double)kt[5];
+                    if (kok[6]) conv = conv + se[sy - 1][sx + 1] * (double)kt[6];
+                    if (kok[7]) conv = conv + se[sy + 1][sx - 1] * (double)kt[7];
+                    if (kok[8]) conv = conv + se[sy + 1][sx + 1] * (double)kt[8];
                 } else {
-                    conv = se[ty][tx];
+                    conv = se[sy][sx];
                 }
-                bool ex;
-                const double S = invlin_pixel<double, PMAX>(conv / (double)g, c, A.P, smin, smax, ex);
+                const double slin = conv / (double)g;
+                double z;
+                if (linm > 0.0f) {
+                    if (!have_root) {
+                        root = cd[1] != 0.0 ? (slin - cd[0]) / cd[1] : 0.0;
+                        have_root = true;
+                    }
+                    z = invlin_fast_z<P>(slin, cd, linA, linm, root, nullptr);
+                } else {  // no monotonicity certificate for this pixel: the plain search
+                    z = 0.0;
+                    double step = 1.0;
+                    for (int j = 1; j < 25; ++j) {
+                        step = step * 0.5;
+                        const float phi = legendre_eval_cd<P>(z, cd);
+                        z = z + (((double)phi < slin) ? step : -step);
+                    }
+                }
+                const double S = (double)smin + (double)half * (1.0 + z);
                 acc = acc + S;
             }
         }
@@ -396,16 +515,33 @@ static void make_l1_impl(rip_caldir* h, const int32_t* d_counts, const int32_t* 
     A.add_read_noise = prm->add_read_noise; A.add_reset_noise = prm->add_reset_noise;
     A.add_biascorr = prm->add_biascorr; A.quantize = prm->quantize;
     A.biascorr_t0 = h->d.biascorr_t0; A.has_bias = h->has_bias ? 1 : 0;
-    A.counts = d_counts; A.cum_counts = d_cum;
+    const size_t npa = (size_t)h->na * h->na, npl = (size_t)h->n * h->n;
+    // per-CALDIR certificate of the fast inverse (once) and the per-call workspace
+    if (!h->lin_A.p) {
+        h->lin_A.alloc(npl);
+        h->lin_m.alloc(npl);
+        RIP_LAUNCH(invlin_certify_kernel, (unsigned)((npl + 127) / 128), 128, 0, st, (const float*)h->coefs.p, h->P, (long)npl,
+                   h->lin_A.p, h->lin_m.p);
+    }
+    if (h->f_start.n < npa) h->f_start.alloc(npa);
+    if (!d_cum && h->f_cum.n < npa * prm->n_reads) h->f_cum.alloc(npa * prm->n_reads);
+    A.counts = d_counts;
+    A.cum = d_cum ? const_cast<int32_t*>(d_cum) : h->f_cum.p;
+    A.cum_given = d_cum ? 1 : 0;
+    A.start = h->f_start.p;
+    A.linA = h->lin_A.p; A.linm = h->lin_m.p;
     A.coefs = h->coefs.p; A.Smin = h->Smin.p; A.Smax = h->Smax.p;
     A.gain = h->gain.p; A.ipc = h->has_ipc ? h->ipc.p : nullptr; A.read = h->read.p; A.resetnoise = h->resetnoise.p;
     A.dark_slope = h->dark_slope.p;
     // sim_to_isim.py:256-258 adds the whole biascorr cube (same number of groups as the pattern)
     A.bias = h->has_bias ? h->biascorr.p + (size_t)(h->d.n_bias - prm->G) * h->na * h->na : nullptr;
     A.out = d_out;
-    dim3 grid((h->na + FTX - 1) / FTX, (h->na + FTY - 1) / FTY);
-    const int threads = (FTX + 2) * (FTY + 2);
     const bool gd = h->d.gain_dtype == RIP_F64, kd = h->has_ipc && h->d.ipc_dtype == RIP_F64;
+    dim3 ga((h->na + 127) / 128, h->na);
+    if (gd) RIP_LAUNCH(fwd_apportion_kernel<double>, ga, 128, 0, st, A);
+    else RIP_LAUNCH(fwd_apportion_kernel<float>, ga, 128, 0, st, A);
+    dim3 grid((h->na + FTX - 1) / FTX, (h->na + FTY - 1) / FTY);
+    const int threads = FTX * FTY;
 #define FW(PM)                                                                                   \
     do {                                                                                         \
         if (!gd && !kd) RIP_LAUNCH((fwd_ramp_kernel<PM, float, float>), grid, threads, 0, st, A);  \

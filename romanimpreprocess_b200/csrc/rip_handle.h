@@ -41,6 +41,9 @@ struct rip_caldir {
     // forward path (rip_sim.cu): amp33 noise plane, scene calibration planes (lazy), 1/f frame workspace (lazy)
     DevBuf<float> amp_std, sim_dark, sim_flat, f_frames, f_work;
     DevBuf<double> f_sums;
+    // forward ramp (rip_fwd.cu): certificate planes of the fast inverse (lazy, once per CALDIR), per-call workspace
+    DevBuf<float> lin_A, lin_m, f_start;
+    DevBuf<int32_t> f_cum;
     cudaStream_t stream = nullptr;
     // optional per-launch timing of the fused kernel (rip_profile_enable): event pairs recorded on the launch stream
     bool profile = false;

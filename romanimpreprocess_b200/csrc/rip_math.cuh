@@ -116,6 +116,143 @@ RIP_HD TZ invlin_pixel(TZ Slin, const float (&c)[PMAX], int P, float Smin, float
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// The same 24-step inverse, float64, WITHOUT evaluating the polynomial at every step (forward model hot loop).
+//
+// The reference's comparison at step j is  phi_fp(z_j) < Slin  with phi_fp the float32-accumulated evaluation above.
+// Let phi be the exact polynomial and r a point where phi(r) - Slin = rho is known.  If phi' >= m > 0 on [-1,1]
+// (certified once per pixel by invlin_certify) then for s = z - r:   s > 0: phi(z) - Slin >= m s + rho,
+// s < 0: phi(z) - Slin <= m s + rho.  phi_fp differs from phi by at most delta (sum of the float32 roundings of the
+// accumulator: each <= 2^-24 |partial sum|), so the comparison is DECIDED without evaluation whenever
+// |m s + rho| > delta on the right side; only the last few steps (z_j within the rounding noise of the root) run the
+// exact evaluation.  r comes from a few float64 Newton steps started at the previous read's root; Newton need not
+// converge for correctness (rho carries whatever residual is left).  delta: global bound (P-1) 2^-24 sum|c_L| far
+// from r, the measured partial sums at r (plus their Lipschitz drift) within 2^-16 of r.  The result is the
+// reference's z bit for bit (tests/test_hostcheck.py: exhaustive random + adversarial comparison on the host;
+// tests/test_gpu_forward.py: exact DN parity with the oracle).
+// ---------------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define RIP_FMA(a, b, c) __fma_rn((a), (b), (c))
+#else
+#define RIP_FMA(a, b, c) fma((a), (b), (c))
+#endif
+
+// sum |c_L| and a certified lower bound of phi'(z) on [-1,1] (0 = not certified -> plain bisection)
+template <int PMAX>
+RIP_HD void invlin_certify(const float (&c)[PMAX], int P, float& A_out, float& m_out) {
+    double A = 0.0, B2 = 0.0;
+    for (int L = 0; L < P; ++L) {
+        const double ac = fabs((double)c[L]);
+        A += ac;
+        B2 += ac * ((double)(L - 1) * L * (L + 1) * (L + 2) / 8.0);  // max |P_L''| on [-1,1] = P_L''(1)
+    }
+    constexpr int K = 32;
+    const double h = 2.0 / K;
+    double lo = 1.0e300;
+    for (int i = 0; i <= K; ++i) {
+        const double z = -1.0 + h * i;
+        double p0 = 1.0, p1 = z, d0 = 0.0, d1 = 1.0, dphi = 0.0;
+        for (int L = 1; L < P; ++L) {
+            dphi += (double)c[L] * d1;
+            const double pn = ((2 * L + 1) * z * p1 - L * p0) / (L + 1);
+            const double dn = d0 + (2 * L + 1) * p1;
+            p0 = p1; p1 = pn; d0 = d1; d1 = dn;
+        }
+        lo = dphi < lo ? dphi : lo;
+    }
+    lo = lo - 0.5 * h * B2 * (1.0 + 1e-9) - 1e-9 * A * P * P;
+    const bool ok = (A == A) && (A < 1.0e30) && (lo > 1.0e-6 * A) && (lo == lo);
+    float af = (float)A;
+    if ((double)af < A) af = nextafterf(af, INFINITY);
+    float mf = ok ? (float)lo : 0.0f;
+    if (ok && (double)mf > lo) mf = nextafterf(mf, -INFINITY);
+    A_out = af;
+    m_out = (ok && mf > 0.0f) ? mf : 0.0f;
+}
+
+// exact evaluation (== legendre_eval<double, PMAX, false>) with the coefficients already promoted to float64
+template <int P>
+RIP_HD float legendre_eval_cd(double z, const double (&cd)[P]) {
+    float phi = (float)cd[0];
+    double prev = 1.0, cur = z;
+#pragma unroll
+    for (int L = 1; L < P; ++L) {
+        phi = (float)((double)phi + cd[L] * cur);
+        const double a = (2 * L + 1) / (double)(L + 1), b = L / (double)(L + 1);
+        const double nxt = (a * z) * cur - b * prev;
+        prev = cur;
+        cur = nxt;
+    }
+    return phi;
+}
+
+// phi, phi' and sum_L |partial sum_L| (L >= 1) of the exact polynomial, float64 with fused multiply-adds
+template <int P>
+RIP_HD void legendre_newton_eval(double z, const double (&cd)[P], double& phi, double& dphi, double& sabs) {
+    double p0 = 1.0, p1 = z, d0 = 0.0, d1 = 1.0;
+    phi = cd[0];
+    dphi = 0.0;
+    sabs = 0.0;
+#pragma unroll
+    for (int L = 1; L < P; ++L) {
+        phi = RIP_FMA(cd[L], p1, phi);
+        dphi = RIP_FMA(cd[L], d1, dphi);
+        sabs += fabs(phi);
+        const double a = (2 * L + 1) / (double)(L + 1), b = L / (double)(L + 1);
+        const double pn = RIP_FMA(a * z, p1, -(b * p0));
+        const double dn = RIP_FMA((double)(2 * L + 1), p1, d0);
+        p0 = p1; p1 = pn; d0 = d1; d1 = dn;
+    }
+}
+
+RIP_HD double clamp_pm1(double v) { return v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v); }
+
+// Returns the z of the reference's 24-step search.  r: in = starting guess of the root, out = last Newton iterate
+// (feed it to the next read of the same pixel).  n_exact (optional) counts exact evaluations.
+template <int P>
+RIP_HD double invlin_fast_z(double Slin, const double (&cd)[P], float A, float m, double& r, int* n_exact) {
+    const double u = 5.9604644775390625e-08;  // 2^-24
+    const double slack = 1.0 + 1.0 / 1024.0;
+    const double eps = (double)A * 9.094947017729282e-13;  // 2^-40 sum|c|: float64 evaluation errors, generously
+    const double dglob = (double)(P - 1) * u * (double)A * slack + eps;
+    const double D1 = (double)A * (double)(P * (P - 1) / 2) * (double)(P - 1);  // drift of sum_L |S_L| per unit z
+    double rr = clamp_pm1(r), phi, dphi, sabs, rho;
+    if (!(rr == rr)) rr = 0.0;
+    legendre_newton_eval<P>(rr, cd, phi, dphi, sabs);
+    rho = phi - Slin;
+    for (int it = 0; it < 8; ++it) {
+        if (fabs(rho) <= 0.5 * u * sabs) break;
+        const double den = dphi > (double)m ? dphi : (double)m;
+        const double rn = clamp_pm1(rr - rho / den);
+        if (!(rn != rr)) break;  // converged to the grid of doubles, pinned at +-1, or NaN
+        rr = rn;
+        legendre_newton_eval<P>(rr, cd, phi, dphi, sabs);
+        rho = phi - Slin;
+    }
+    r = rr;
+    double z = 0.0, step = 1.0;
+    for (int j = 1; j < 25; ++j) {
+        step = step * 0.5;
+        const double s = z - rr, as = fabs(s);
+        double dl = dglob;
+        if (as <= 1.52587890625e-05) {  // 2^-16: partial sums are those at r up to their drift
+            const double dloc = u * (sabs + as * D1) * slack + eps;
+            dl = dloc < dglob ? dloc : dglob;
+        }
+        const double g = RIP_FMA((double)m, s, rho);
+        bool lt;
+        if (s > 0.0 && g > dl) lt = false;
+        else if (s < 0.0 && g < -dl) lt = true;
+        else if (s == 0.0 && fabs(rho) > dl) lt = rho < 0.0;
+        else {
+            lt = (double)legendre_eval_cd<P>(z, cd) < Slin;
+            if (n_exact) ++*n_exact;
+        }
+        z = z + (lt ? step : -step);
+    }
+    return z;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Ramp-fit plan (built on the host with NumPy so that every scalar has the reference's rounding; see
 // romanimpreprocess_b200/utils/fitting.py:build_plan).  Variant 0 is the full ramp, variant v>=1 is the ramp
 // truncated at iend = G - v (reference utils/fitting.py:165-169,326).

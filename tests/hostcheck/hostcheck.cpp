@@ -153,3 +153,78 @@ extern "C" long hostcheck_shared_div(long count, unsigned seed, float dlo, float
     }
     return bad;
 }
+
+// Certified fast inverse (rip::invlin_fast_z) against the plain 24-step search, on pseudo-random pixels with
+// realistic and with hostile coefficient sets, for ramps of increasing signal (root carried from read to read) and
+// for adversarial signals placed exactly on / one ulp off the float32 values the search compares against.
+// Returns the number of mismatching z.  stats[0] = calls, [1] = exact evaluations, [2] = uncertified pixels.
+template <int P>
+static long invlin_check_t(long npix, unsigned seed, double hostile, double* stats) {
+    unsigned long long st = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+    auto rnd = [&]() { st = st * 6364136223846793005ULL + 1442695040888963407ULL; return (double)(st >> 11) / 9007199254740992.0; };
+    auto slow_z = [&](double Slin, const float (&c)[P]) {
+        double z = 0.0, step = 1.0;
+        bool ex;
+        for (int j = 1; j < 25; ++j) {
+            step *= 0.5;
+            const float phi = legendre_eval<double, P, false>(z, c, P, ex);
+            z = z + (((double)phi < Slin) ? step : -step);
+        }
+        return z;
+    };
+    long bad = 0;
+    for (long px = 0; px < npix; ++px) {
+        float c[P];
+        double cd[P];
+        const double c1 = 20000.0 + 12000.0 * rnd();
+        c[1] = (float)c1;
+        c[0] = (float)(c1 * (0.9 + 0.2 * rnd()) + 3000.0 * rnd());
+        const double c2 = (rnd() < 0.5 ? -1.0 : 1.0) * (20.0 + 180.0 * rnd());
+        if (P > 2) c[2] = (float)c2;
+        for (int L = 3; L < P; ++L) c[L] = (float)((rnd() - 0.5) * 0.04 * c2 * (1.0 + hostile * 30.0 * rnd()));
+        for (int L = 0; L < P; ++L) cd[L] = (double)c[L];
+        float A, m;
+        invlin_certify<P>(c, P, A, m);
+        if (!(m > 0.0f)) { stats[2] += 1; continue; }
+        bool ex;
+        const double lo = legendre_eval<double, P, false>(-1.0, c, P, ex), hi = legendre_eval<double, P, false>(1.0, c, P, ex);
+        double r = 0.0;
+        auto check = [&](double Slin) {
+            int ne = 0;
+            const double zf = invlin_fast_z<P>(Slin, cd, A, m, r, &ne);
+            const double zs = slow_z(Slin, c);
+            stats[0] += 1; stats[1] += ne;
+            if (!(zf == zs)) ++bad;
+        };
+        // a ramp of reads (faint or bright pixel)
+        const double rate = (rnd() < 0.7 ? 40.0 : 1800.0) * rnd();
+        double sig = lo + 200.0 + 3000.0 * rnd();
+        for (int k = 0; k < 12; ++k) { check(sig); sig += rate * (1.0 + rnd()); }
+        // adversarial: exactly the float32 value the search sees at a point of its grid, and its neighbours
+        for (int k = 0; k < 10; ++k) {
+            const int bits = 8 + (int)(rnd() * 17.0);  // grid of step 2^-bits
+            const double zt = clamp_pm1((floor(rnd() * ldexp(2.0, bits)) - ldexp(1.0, bits)) * ldexp(1.0, -bits));
+            const float pf = legendre_eval<double, P, false>(zt, c, P, ex);
+            check((double)pf);
+            check((double)nextafterf(pf, INFINITY));
+            check((double)nextafterf(pf, -INFINITY));
+            check(nextafter((double)pf, INFINITY));
+            check(nextafter((double)pf, -INFINITY));
+            check((double)pf + (rnd() - 0.5) * 0.02);
+        }
+        // edges of the range and beyond, non-finite signals
+        check(lo); check(hi); check(lo - 1e-3); check(hi + 1e-3); check(lo - 5000.0); check(hi + 5000.0);
+        check(nextafter(hi, INFINITY)); check(nextafter(lo, -INFINITY));
+        check(0.0); check(NAN); check(INFINITY); check(-INFINITY);
+        check(0.5 * (lo + hi));
+    }
+    return bad;
+}
+
+extern "C" long hostcheck_invlin_fast(long npix, unsigned seed, int P, double hostile, double* stats) {
+    stats[0] = stats[1] = stats[2] = 0.0;
+    if (P == 4) return invlin_check_t<4>(npix, seed, hostile, stats);
+    if (P == 11) return invlin_check_t<11>(npix, seed, hostile, stats);
+    if (P == 16) return invlin_check_t<16>(npix, seed, hostile, stats);
+    return -1;
+}

@@ -116,3 +116,28 @@ def test_shared_reciprocal_division_is_ieee_division():
     h = harness.lib()
     assert h.hostcheck_shared_div(10000000, 7, 1e-3, 1e6, 3e5) == 0
     assert h.hostcheck_shared_div(10000000, 9, 0.5, 3.0, 1e7) == 0
+
+
+@pytest.mark.parametrize("P,hostile", [(11, 0.0), (4, 0.0), (11, 6.0), (16, 0.3)])
+def test_fast_inverse_equals_24_step_search(P, hostile):
+    """csrc/rip_math.cuh invlin_fast_z (the forward model's certified shortcut) returns the z of the reference's
+    24-step search (utils/ipc_linearity.py:381-387) for every signal: ramps, adversarial values sitting exactly on
+    the float32 numbers the search compares with, range edges, NaN/inf.  `hostile` inflates the high-order
+    coefficients until many pixels lose the monotonicity certificate (those must take the plain search)."""
+    import ctypes as C
+
+    h = harness.lib()
+    h.hostcheck_invlin_fast.restype = C.c_long
+    h.hostcheck_invlin_fast.argtypes = [C.c_long, C.c_uint, C.c_int, C.c_double, C.POINTER(C.c_double)]
+    stats = (C.c_double * 3)()
+    bad = h.hostcheck_invlin_fast(4000, 1234 + P, P, hostile, stats)
+    calls, exact, uncert = stats[0], stats[1], stats[2]
+    assert bad == 0, f"{bad} of {calls:.0f} inversions differ"
+    assert calls > 1000
+    if hostile > 0.0:
+        assert uncert > 0
+    if hostile == 0.0:
+        assert uncert == 0
+        assert exact / calls < 8.0, exact / calls  # the point of it: far fewer than 24 evaluations
+    print(f"P={P} hostile={hostile}: {calls:.0f} calls, {exact / max(calls, 1):.2f} exact evaluations per call, "
+          f"{uncert:.0f} uncertified pixels")
