@@ -11,13 +11,67 @@
 namespace rip {
 
 // Stirling tail log(k!) - [(k+1/2)log(k+1) - (k+1) + (1/2)log(2pi)]  (Hormann 1993)
+__constant__ double c_stirling[10] = {0.0810614667953272, 0.0413406959554092, 0.0276779256849983, 0.02079067210376509,
+                                      0.0166446911898211, 0.0138761288230707, 0.0118967099458917, 0.0104112652619720,
+                                      0.00925546218271273, 0.00833056343336287};
 __device__ __forceinline__ double stirling_tail(double k) {
-    const double t[10] = {0.0810614667953272, 0.0413406959554092, 0.0276779256849983, 0.02079067210376509,
-                          0.0166446911898211, 0.0138761288230707, 0.0118967099458917, 0.0104112652619720,
-                          0.00925546218271273, 0.00833056343336287};
-    if (k <= 9.0) return t[(int)k];
+    if (k <= 9.0) return c_stirling[(int)k];
     const double kp1sq = (k + 1.0) * (k + 1.0);
     return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / kp1sq) / kp1sq) / (k + 1.0);
+}
+
+// Per-read constants of the apportioning (pixel independent): the binomial probability of read k given the reads
+// before it, folded to q = min(p, 1-p), and what the float32 sampler derives from q alone.
+struct ReadTab {
+    double p;
+    float q, omq, l1mq, s;  // q, 1-q, log1p(-q), q/(1-q)
+    int flip, draw;         // p > 1/2; this read draws at all (t > t_prev)
+};
+
+__device__ long binomial_draw(Philox& rng, long n, double p);
+
+// Binomial(n, p_k) for n < 2^22 with the per-read constants (same algorithm as binomial_draw's float32 branch)
+__device__ __forceinline__ int binomial_draw_tab(Philox& rng, int n, const ReadTab& T) {
+    if (n <= 0 || T.p <= 0.0) return 0;
+    if (T.p >= 1.0) return n;
+    const float nf = (float)n, qf = T.q, omq = T.omq;
+    const float npq = nf * qf;
+    int k;
+    // (inversion up to n q = 30 as in NumPy: for small means BTRS's squeeze accepts under half of the candidates and
+    //  every other one pays four float64 logarithms; measured 54 -> see profiles/r01)
+    if (npq < 30.0f) {
+        const float f0 = __expf(nf * T.l1mq), s = T.s;
+        const float bound = fminf(nf, npq + 10.0f * sqrtf(npq * omq + 1.0f));
+        float x = 0.0f, f = f0, u = rng.uniform();
+        while (u > f) {
+            x += 1.0f;
+            if (x > bound) { x = 0.0f; f = f0; u = rng.uniform(); }
+            else { u -= f; f = __fdividef((nf - x + 1.0f) * s * f, x); }
+        }
+        k = (int)x;
+    } else {
+        const float spq = sqrtf(npq * omq);
+        const float b = 1.15f + 2.53f * spq, a = -0.0873f + 0.0248f * b + 0.01f * qf, c = npq + 0.5f;
+        const float vr = 0.92f - __fdividef(4.2f, b);
+        for (;;) {
+            const float u = rng.uniform() - 0.5f;
+            const float v = rng.uniform();
+            const float us = 0.5f - fabsf(u);
+            const float kk = floorf((__fdividef(2.0f * a, us) + b) * u + c);
+            if (kk < 0.0f || kk > nf) continue;
+            if (us >= 0.07f && v <= vr) { k = (int)kk; break; }
+            const double nd = (double)n, kd = (double)kk, usd = (double)us, q = (double)qf;
+            const double r = q / (1.0 - q), alpha = (2.83 + 5.1 / (double)b) * (double)spq;
+            const double m = floor((nd + 1.0) * q);
+            const double lv = log((double)v * alpha / ((double)a / (usd * usd) + (double)b));
+            const double ub = (m + 0.5) * log((m + 1.0) / (r * (nd - m + 1.0))) +
+                              (nd + 1.0) * log((nd - m + 1.0) / (nd - kd + 1.0)) +
+                              (kd + 0.5) * log(r * (nd - kd + 1.0) / (kd + 1.0)) + stirling_tail(m) +
+                              stirling_tail(nd - m) - stirling_tail(kd) - stirling_tail(nd - kd);
+            if (lv <= ub) { k = (int)kk; break; }
+        }
+    }
+    return T.flip ? n - k : k;
 }
 
 // Binomial(n, p) sampler: sequential inversion of the CDF (BINV) for n*min(p,1-p) < 10, Hormann's BTRS transformed
@@ -232,6 +286,7 @@ struct FwdArgs {
     int add_read_noise, add_reset_noise, add_biascorr, quantize;
     double biascorr_t0;
     int has_bias;
+    ReadTab rtab[64];           // per-read apportioning constants (by value: kernel parameters live in constant memory)
     const int32_t* counts;      // [na,na] total electrons of the exposure (already Poisson)
     int32_t* cum;               // [n_reads,na,na] cumulative electrons per read (written by the apportioning kernel
                                 //  unless supplied by the caller: tests)
@@ -284,24 +339,20 @@ __global__ void __launch_bounds__(128) fwd_apportion_kernel(const FwdArgs A) {
     }
     A.start[pa] = start_e;
     if (A.cum_given) return;
-    long remaining = 0;
+    int remaining = 0;
     if (A.counts) {
-        const long c = A.counts[pa];
-        remaining = c < 0 ? 0 : (c > 2000000000L ? 2000000000L : c);
+        const int c = A.counts[pa];
+        remaining = c < 0 ? 0 : (c > 2000000000 ? 2000000000 : c);
     }
-    const double t_last = A.read_time * (double)A.read_index[A.n_reads - 1];
-    double t_prev = 0.0;  // romanisim starts the clock at the reset
-    long cum = 0;
+    int cum = 0;
     for (int k = 0; k < A.n_reads; ++k) {
-        const double t = A.read_time * (double)A.read_index[k];
-        if (remaining > 0 && t > t_prev) {
-            const double p = (t_last > t_prev) ? (t - t_prev) / (t_last - t_prev) : 1.0;
-            const long d = binomial_draw(rng, remaining, p >= 1.0 ? 1.0 : p);
+        const ReadTab& T = A.rtab[k];
+        if (remaining > 0 && T.draw) {
+            const int d = remaining < (1 << 22) ? binomial_draw_tab(rng, remaining, T) : (int)binomial_draw(rng, (long)remaining, T.p);
             cum += d;
             remaining -= d;
         }
-        t_prev = t;
-        A.cum[(long)k * npa + pa] = (int32_t)cum;
+        A.cum[(long)k * npa + pa] = cum;
     }
 }
 
@@ -525,6 +576,22 @@ static void make_l1_impl(rip_caldir* h, const int32_t* d_counts, const int32_t* 
     }
     if (h->f_start.n < npa) h->f_start.alloc(npa);
     if (!d_cum && h->f_cum.n < npa * prm->n_reads) h->f_cum.alloc(npa * prm->n_reads);
+    {   // romanisim starts the clock at the reset: read k draws Binomial(remaining, (t_k - t_prev)/(t_last - t_prev))
+        const double t_last = prm->read_time * (double)prm->read_index[prm->n_reads - 1];
+        double t_prev = 0.0;
+        for (int k = 0; k < prm->n_reads; ++k) {
+            const double t = prm->read_time * (double)prm->read_index[k];
+            ReadTab& T = A.rtab[k];
+            T.draw = t > t_prev ? 1 : 0;
+            double p = (t_last > t_prev) ? (t - t_prev) / (t_last - t_prev) : 1.0;
+            p = p >= 1.0 ? 1.0 : p;
+            T.p = p;
+            T.flip = p > 0.5 ? 1 : 0;
+            const double q = T.flip ? 1.0 - p : p;
+            T.q = (float)q; T.omq = 1.0f - T.q; T.l1mq = log1pf(-T.q); T.s = T.q / T.omq;
+            t_prev = t;
+        }
+    }
     A.counts = d_counts;
     A.cum = d_cum ? const_cast<int32_t*>(d_cum) : h->f_cum.p;
     A.cum_given = d_cum ? 1 : 0;

@@ -519,34 +519,19 @@ RIP_HD void jump_pair(const f2 diff, const f2 inv_dt, const f2 Ac, const f2 Bc, 
     }
 }
 
-// jump_detect of the whole ramp (plan variant 0) for one active pixel; q[j] = groups (2j, 2j+1); start = plan.start (0 / 1).
-// slope / errors: the reference's op order (fitting.py:187-212).  Flags: every slice is classified without branching
-// on packed pairs; pixels with any slice inside the relative band of the threshold (or NaN) redo all slices in the
-// reference's exact f64 op order (cold) => the flags are those of the exact path.
-template <int G>
-RIP_HD FitResult jump_full(const f2 (&q)[G / 2], const int start, float gain, float read, const RampPlanDev& pl, const FastTab& ft,
-                           const double* w_all) {
-    static_assert(G >= 6 && (G & 1) == 0, "pair indexing of the full-ramp specialisation");
-    FitResult r;
-    const float d1 = q[0].y;
-    float acc = 0.0f;
+// The pair-wise classification of the full ramp (sure set / sure clear / unsure -> exact), out of line: only pixels
+// that fail the all-clear test of jump_full come here (cosmic-ray hits, bright sources, NaNs).
+// (TAG = the kernel's P: one copy per kernel instantiation, so that `make check-sass` can compare PTX and SASS counts)
+template <int G, int TAG>
+RIP_HD_COLD uint32_t jump_classify(const Ramp<G> rd, const int start, const float slope, const float dvardt, const float sig2read,
+                                   const ThrBand tb, const RampPlanDev& pl, const FastTab& ft, const double* w_all) {
+    f2 q[G / 2];
 #pragma unroll
-    for (int j = 0; j < G / 2; ++j) {
-        const f2 pr = mul2(ft.K[j], sub2p(q[j], bc(d1)));  // K_t * (d_t - d_1); the sum stays sequential
-        acc = acc + pr.x;
-        acc = acc + pr.y;
-    }
-    r.slope = acc;
-    const float gc = clip_nan(gain, 1e-4f, 1e4f);
-    const float dvardt = max_nan(r.slope / gc, 0.0f);
-    r.err_poisson = sqrtf(max_nan(pl.var_coef[0] * dvardt, 0.0f));
-    r.err_read = read * pl.var_rfac[0];
-    const float sig2read = read * read;
-    const ThrBand tb = thr_band(r.slope, pl);
+    for (int j = 0; j < G / 2; ++j) q[j] = f2{rd.v[2 * j], rd.v[2 * j + 1]};
     bool unsure = !tb.ok;
     uint32_t mask = 0u;
     const f2 hd = bc(tb.hi2 * dvardt), hr = bc(tb.hi2 * sig2read);
-    const float ns = -r.slope;
+    const float ns = -slope;
     // start = 1 (EXCLUDE_FIRST) only removes the two slices that begin at group 0: lane x of the pairs k = 0
 #pragma unroll
     for (int k = 0; k < G / 2; ++k) {
@@ -573,20 +558,93 @@ RIP_HD FitResult jump_full(const f2 (&q)[G / 2], const int start, float gain, fl
             }
         }
     }
-    if (unsure) {
+    if (unsure) mask = jump_exact<G>(rd, 0, slope, dvardt, sig2read, pl, w_all);
+    return mask;
+}
+
+// all-clear test of one slice pair: folds  (clear bound) - delta^2  of the live lanes into a running NaN-propagating
+// minimum.  The bound is the lower edge of the significance band (times var), so a positive minimum means every slice
+// is a sure clear.
+template <bool V0, bool V1>
+RIP_HD void clear_pair(const f2 diff, const f2 inv_dt, const f2 Ac, const f2 Bc, const float nslope, const f2 ld, const f2 lr,
+                       const bool lane0_live, float& tmin) {
+    const f2 delta = fma2(diff, inv_dt, bc(nslope));
+    const f2 lv = fma2(Ac, ld, mul2(Bc, lr));
+    // lo^2 var - delta^2 (classification only: any rounding will do).  A strongly NEGATIVE delta also fails this test
+    // although it is a sure clear; that only sends the pixel to jump_classify, which knows (such pixels are almost
+    // always neighbours of a jump in the same ramp anyway).
+    const f2 t = fma2(f2{-delta.x, -delta.y}, delta, lv);
+    if (V0) tmin = min_nan(tmin, lane0_live ? t.x : tmin);
+    if (V1) tmin = min_nan(tmin, t.y);
+}
+
+// jump_detect of the whole ramp (plan variant 0) for one active pixel; q[j] = groups (2j, 2j+1); start = plan.start (0 / 1).
+// slope / errors: the reference's op order (fitting.py:187-212).  Flags: one branch-free pass proves "no slice is
+// significant" for almost every pixel (minimum over the slices of  lo^2 var - delta^2  > 0); the rest are
+// classified pair-wise out of line and pixels with any slice inside the relative band of the threshold (or NaN)
+// redo all slices in the reference's exact f64 op order => the flags are those of the exact path.
+template <int G, int TAG>
+RIP_HD FitResult jump_full(const f2 (&q)[G / 2], const int start, float gain, float read, const RampPlanDev& pl, const FastTab& ft,
+                           const double* w_all) {
+    static_assert(G >= 6 && (G & 1) == 0, "pair indexing of the full-ramp specialisation");
+    FitResult r;
+    const float d1 = q[0].y;
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < G / 2; ++j) {
+        const f2 pr = mul2(ft.K[j], sub2p(q[j], bc(d1)));  // K_t * (d_t - d_1); the sum stays sequential
+        acc = acc + pr.x;
+        acc = acc + pr.y;
+    }
+    r.slope = acc;
+    const float gc = clip_nan(gain, 1e-4f, 1e4f);
+    const float dvardt = max_nan(r.slope / gc, 0.0f);
+    r.err_poisson = sqrtf(max_nan(pl.var_coef[0] * dvardt, 0.0f));
+    r.err_read = read * pl.var_rfac[0];
+    const float sig2read = read * read;
+    const ThrBand tb = thr_band(r.slope, pl);
+    const float lo2c = tb.lo2 * (1.0f - 2.0e-6f);  // (absorbs the roundings of the products below)
+    const f2 ld = bc(lo2c * dvardt), lr = bc(lo2c * sig2read);
+    const float ns = -r.slope;
+    float tmin = 3.0e38f;
+#pragma unroll
+    for (int k = 0; k < G / 2; ++k) {
+        const bool live0 = (k > 0) || (start == 0);
+        {
+            const bool v0 = full_slice_valid(G, 0, 2 * k, 1), v1 = full_slice_valid(G, 0, 2 * k + 1, 1);
+            if (v0 || v1) {
+                const f2 up = f2{q[k].y, q[(k + 1 < G / 2) ? k + 1 : k].x};
+                const f2 diff = sub2p(up, q[k]);
+                if (v0 && v1) clear_pair<true, true>(diff, ft.inv_dt[0][k], ft.A[0][k], ft.B[0][k], ns, ld, lr, live0, tmin);
+                else if (v0) clear_pair<true, false>(diff, ft.inv_dt[0][k], ft.A[0][k], ft.B[0][k], ns, ld, lr, live0, tmin);
+                else clear_pair<false, true>(diff, ft.inv_dt[0][k], ft.A[0][k], ft.B[0][k], ns, ld, lr, live0, tmin);
+            }
+        }
+        if (k + 1 < G / 2) {
+            const bool v0 = full_slice_valid(G, 0, 2 * k, 2), v1 = full_slice_valid(G, 0, 2 * k + 1, 2);
+            if (v0 || v1) {
+                const f2 diff = sub2p(q[(k + 1 < G / 2) ? k + 1 : k], q[k]);
+                if (v0 && v1) clear_pair<true, true>(diff, ft.inv_dt[1][k], ft.A[1][k], ft.B[1][k], ns, ld, lr, live0, tmin);
+                else if (v0) clear_pair<true, false>(diff, ft.inv_dt[1][k], ft.A[1][k], ft.B[1][k], ns, ld, lr, live0, tmin);
+                else clear_pair<false, true>(diff, ft.inv_dt[1][k], ft.A[1][k], ft.B[1][k], ns, ld, lr, live0, tmin);
+            }
+        }
+    }
+    uint32_t mask = 0u;
+    if (!(tb.ok && tmin > 0.0f)) {  // (NaN anywhere -> tmin is NaN -> not clear)
         Ramp<G> rd;
 #pragma unroll
         for (int j = 0; j < G / 2; ++j) { rd.v[2 * j] = q[j].x; rd.v[2 * j + 1] = q[j].y; }
-        mask = jump_exact<G>(rd, 0, r.slope, dvardt, sig2read, pl, w_all);
+        mask = jump_classify<G, TAG>(rd, start, r.slope, dvardt, sig2read, tb, pl, ft, w_all);
     }
     r.jump_mask = mask;
     return r;
 }
 
-template <int G>
+template <int G, int TAG>
 RIP_HD FitResult ramp_fit_fast(const f2 (&q)[G / 2], GroupFlags& gf, uint32_t& pdq, float gain, float read,
                                const RampPlanDev& pl, const FastTab& ft, const double* w_all) {
-    FitResult r = jump_full<G>(q, pl.start, gain, read, pl, ft, w_all);
+    FitResult r = jump_full<G, TAG>(q, pl.start, gain, read, pl, ft, w_all);
     const bool unsat = ((gf.sat >> (G - 1)) & 1u) == 0u;
     if (unsat) gf.jump |= r.jump_mask;
     if (gf.sat) {  // truncated refits only where some group is saturated
@@ -881,7 +939,7 @@ RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, Sme
     uint32_t pd = (nlc & 4u) ? DQ_REFERENCE_PIXEL : 0u;
     FitResult r;
     if (active) {
-        r = ramp_fit_fast<G>(q, gf, pd, gval, readv, pl, ft, A.w_exact);
+        r = ramp_fit_fast<G, P>(q, gf, pd, gval, readv, pl, ft, A.w_exact);
     } else {
         // reference pixels / phantom border: the fit result is zeroed by the packaging step
         // (gen_cal_image.py:470-472); only the flag propagation of ramp_fit matters (fitting.py:340-353)
