@@ -56,7 +56,10 @@ class Realizations:
         self.t_exp = self.read_time * (read_pattern[-1][-1] - read_pattern[0][0])
         self.rpg = np.ascontiguousarray([len(g) for g in read_pattern], dtype=np.int32)
         self.grow = np.ascontiguousarray(maskhandling.PixelMask1.array)
-        self.dplan = gci.DevicePlan(cal, read_pattern, self.read_time, config2 or {}, do_refpix=cal.has_amp33,
+        # the reference output is 128 columns wide whatever the frame side (gen_cal_image.py:531-556 and the library's
+        # reference-pixel statistics assume it); debugging frames with n/32 != 128 run without that correction
+        self.refpix = bool(cal.has_amp33 and n // 32 == 128)
+        self.dplan = gci.DevicePlan(cal, read_pattern, self.read_time, config2 or {}, do_refpix=self.refpix,
                                     area_dtype=np.float32)  # fmt: skip
         z = dict(device=self.dev)
         self.d_image = torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).to(self.dev)
@@ -98,7 +101,7 @@ class Realizations:
         _lib.check(lib.rip_l1_embed_dev(self.device, _p(self.d_res), self.G, self.n, cal.nb, _p(self.d_im), st))
         _lib.check(lib.rip_fill_refdata_1f_dev(cal.handle, _p(self.d_im), _p(self.d_amp33), self.G, _lib.ptr(self.rpg),
                                                seed, int(self.banding), st))  # fmt: skip
-        gci.calibrate_device(cal, self.dplan, self.d_im.data_ptr(), self.d_amp33.data_ptr() if cal.has_amp33 else 0,
+        gci.calibrate_device(cal, self.dplan, self.d_im.data_ptr(), self.d_amp33.data_ptr() if self.refpix else 0,
                              self.d_area_full.data_ptr(), self.d_slope.data_ptr(), self.d_er.data_ptr(),
                              self.d_ep.data_ptr(), self.d_pdq.data_ptr(), stream=st.value or 0)  # fmt: skip
         _lib.check(lib.rip_moments_accumulate_dev(self.device, _p(self.d_slope), _p(self.d_pdq), self.n, cal.nb,
