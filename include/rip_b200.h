@@ -320,6 +320,20 @@ int rip_realization_record_dev(int device, const uint16_t* d_im, int G, int n, i
                                const float* d_err_read, const float* d_err_poisson, float* d_diffs, float* d_images,
                                float* d_err, void* stream);
 
+/* ---- sky model (utils/sky.py:98-190 medfit; called at gen_cal_image.py:645-647 and by every
+ * production noise layer) ---------------------------------------------------------------------------------------
+ * rip_block_nanmedian_dev / rip_medfit_host: np.nanmedian of the N x N regions of ky x kx = (ny/N) x (nx/N) pixels
+ * starting at ((ny%N)/2, (nx%N)/2) -> meds f32 [N,N] (exact order statistics by radix select; float32 mean of the
+ * two middle values for even counts; NaN for an all-NaN region).  The (order+1)(order+2)/2-coefficient normal
+ * equations are solved by the caller in float64 (Python mirror: the reference's own NumPy lines).
+ * rip_medfit_eval_dev: model[y,x] = float32(sum_k coef[k] * (LPY[j,y] * LPX[i,x])) in the reference's term order
+ * (coef, LPX [order+1,nx], LPY [order+1,ny]: host float64); written to d_model (or NULL) and/or subtracted in place
+ * from d_arr (row pitch in elements; or NULL). */
+int rip_block_nanmedian_dev(int device, const float* d_arr, long pitch, int ny, int nx, int N, float* d_meds, void* stream);
+int rip_medfit_host(int device, const float* arr, int ny, int nx, int N, float* meds);
+int rip_medfit_eval_dev(int device, int ny, int nx, int order, const double* coef, const double* LPX, const double* LPY,
+                        float* d_model, float* d_arr, long pitch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

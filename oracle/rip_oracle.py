@@ -777,3 +777,44 @@ def moments_finalize(moments):
     moments[1:] /= moments[0] + 1e-25
     moments[2] = np.sqrt(np.clip(moments[2] - moments[1] ** 2, 0, None))
     moments[1:] = np.where(moments[0][None] > 0.1, moments[1:], -1000.0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Sky model: utils/sky.py:98-190 (medfit)
+# ---------------------------------------------------------------------------------------------------------
+def medfit(arr, N=8, order=2):
+    """Low-order 2D Legendre fit to the nan-medians of N x N regions; returns (coef, model as arr.dtype)."""
+    from scipy.special import legendre_p
+
+    (ny, nx) = np.shape(arr)
+    kx, ky = nx // N, ny // N
+    px, py = (nx % N) // 2, (ny % N) // 2
+    u_ = 2 * (px - 0.5 + kx * np.linspace(0.5, N - 0.5, N)) / nx - 1
+    v_ = 2 * (py - 0.5 + ky * np.linspace(0.5, N - 0.5, N)) / ny - 1
+    u, v = np.meshgrid(u_, v_)
+    meds = np.nanmedian(arr[py : py + N * ky, px : px + N * kx].reshape((N, ky, N, kx)), axis=(1, 3))
+    nc = (order + 1) * (order + 2) // 2
+    basis = np.zeros((nc, N, N))
+    k = 0
+    for i in range(order + 1):
+        temp = legendre_p(i, u)
+        for j in range(order + 1 - i):
+            basis[k] = temp * legendre_p(j, v)
+            k += 1
+    A = np.zeros((nc, nc))
+    b = np.zeros(nc)
+    for ipix in range(N):
+        for jpix in range(N):
+            if not np.isnan(meds[jpix, ipix]):
+                A += np.outer(basis[:, jpix, ipix], basis[:, jpix, ipix])
+                b += meds[jpix, ipix] * basis[:, jpix, ipix]
+    x = np.linalg.solve(A, b)
+    LPX = np.array([legendre_p(i, np.linspace(-1, 1 - 2 / nx, nx)) for i in range(order + 1)])
+    LPY = np.array([legendre_p(j, np.linspace(-1, 1 - 2 / ny, ny)) for j in range(order + 1)])
+    arrmed = np.zeros((ny, nx))
+    k = 0
+    for i in range(order + 1):
+        for j in range(order + 1 - i):
+            arrmed += x[k] * np.outer(LPY[j], LPX[i])
+            k += 1
+    return x, arrmed.astype(arr.dtype), meds

@@ -694,3 +694,134 @@ extern "C" int rip_realization_record_dev(int device, const uint16_t* d_im, int 
                d_err_poisson, d_diffs, d_images, d_err);
     RIP_API_END
 }
+
+// =========================================================================================================
+// Sky model (utils/sky.py:98-190 medfit): medians of N x N regions by radix select, polynomial evaluation
+// =========================================================================================================
+namespace rip {
+
+__device__ __forceinline__ uint32_t f2key_sky(float v) {  // order-preserving key; NaNs are filtered before
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f_sky(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// np.nanmedian of one ky x kx region per CTA: four 8-bit radix passes over order-preserving keys, tracking the two
+// middle ranks at once; float32 mean of the two middle values for even counts (np.median), NaN when nothing is finite.
+__global__ void __launch_bounds__(1024) block_nanmedian_kernel(const float* __restrict__ arr, long pitch, int py, int px, int ky,
+                                                               int kx, int N, float* __restrict__ meds) {
+    __shared__ uint32_t hist[2][256];
+    __shared__ uint32_t prefix[2], rank[2], mask_s, cnt_s;
+    const int ry = blockIdx.y, rx = blockIdx.x;
+    const float* base = arr + (long)(py + ry * ky) * pitch + (px + rx * kx);
+    const long total = (long)ky * kx;
+    if (threadIdx.x == 0) { prefix[0] = prefix[1] = 0u; rank[0] = rank[1] = 0u; mask_s = 0u; cnt_s = 0u; }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) (&hist[0][0])[i] = 0u;
+        __syncthreads();
+        const uint32_t m = mask_s, p0 = prefix[0], p1 = prefix[1];
+        for (long e = threadIdx.x; e < total; e += blockDim.x) {
+            const float v = base[(e / kx) * pitch + (e % kx)];
+            if (v != v) continue;
+            const uint32_t k = f2key_sky(v), b = (k >> shift) & 255u;
+            if ((k & m) == p0) atomicAdd(&hist[0][b], 1u);
+            if (pass > 0 && (k & m) == p1) atomicAdd(&hist[1][b], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (pass == 0) {
+                uint32_t c = 0;
+                for (int b = 0; b < 256; ++b) c += hist[0][b];
+                cnt_s = c;
+                rank[0] = c ? (c - 1) / 2 : 0u;
+                rank[1] = c / 2;
+                for (int b = 0; b < 256; ++b) hist[1][b] = hist[0][b];
+            }
+            for (int s = 0; s < 2; ++s) {
+                uint32_t r = rank[s], acc = 0;
+                int b = 0;
+                for (; b < 255; ++b) {
+                    if (acc + hist[s][b] > r) break;
+                    acc += hist[s][b];
+                }
+                rank[s] = r - acc;
+                prefix[s] |= (uint32_t)b << shift;
+            }
+            mask_s |= 255u << shift;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        float out = NAN;
+        if (cnt_s) {
+            const float a = key2f_sky(prefix[0]), b = key2f_sky(prefix[1]);
+            out = (cnt_s & 1u) ? a : (a + b) / 2.0f;
+        }
+        meds[ry * N + rx] = out;
+    }
+}
+
+// arrmed = sum_k x[k] * outer(LPY[j], LPX[i]) in float64, terms in the reference's order, cast to float32; optionally
+// subtracted from `arr` in place (float32 subtraction of the float32 model, as `slope -= skymodel` does)
+__global__ void medfit_eval_kernel(int ny, int nx, int order, const double* __restrict__ coef, const double* __restrict__ LPX,
+                                   const double* __restrict__ LPY, float* __restrict__ model, float* __restrict__ arr, long pitch) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nx) return;
+    double acc = 0.0;
+    int k = 0;
+    for (int i = 0; i <= order; ++i)
+        for (int j = 0; j <= order - i; ++j) {
+            acc = acc + coef[k] * (LPY[(long)j * ny + y] * LPX[(long)i * nx + x]);
+            ++k;
+        }
+    const float mval = (float)acc;
+    if (model) model[(long)y * nx + x] = mval;
+    if (arr) arr[(long)y * pitch + x] = arr[(long)y * pitch + x] - mval;
+}
+
+}  // namespace rip
+
+extern "C" int rip_block_nanmedian_dev(int device, const float* d_arr, long pitch, int ny, int nx, int N, float* d_meds,
+                                       void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(d_arr && d_meds && N >= 1 && ny >= N && nx >= N, "rip_block_nanmedian_dev: bad argument");
+    use_device(device);
+    const int kx = nx / N, ky = ny / N, px = (nx % N) / 2, py = (ny % N) / 2;
+    RIP_LAUNCH(block_nanmedian_kernel, dim3(N, N), 1024, 0, (cudaStream_t)stream, d_arr, pitch, py, px, ky, kx, N, d_meds);
+    RIP_API_END
+}
+
+extern "C" int rip_medfit_eval_dev(int device, int ny, int nx, int order, const double* coef, const double* LPX,
+                                   const double* LPY, float* d_model, float* d_arr, long pitch, void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(coef && LPX && LPY && (d_model || d_arr) && order >= 0 && order <= 8, "rip_medfit_eval_dev: bad argument");
+    use_device(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nc = (order + 1) * (order + 2) / 2;
+    DevBuf<double> dc, dx, dy;
+    dc.upload(coef, nc, st);
+    dx.upload(LPX, (size_t)(order + 1) * nx, st);
+    dy.upload(LPY, (size_t)(order + 1) * ny, st);
+    dim3 grid((nx + 127) / 128, ny);
+    RIP_LAUNCH(medfit_eval_kernel, grid, 128, 0, st, ny, nx, order, (const double*)dc.p, (const double*)dx.p,
+               (const double*)dy.p, d_model, d_arr, pitch);
+    RIP_CUDA(cudaStreamSynchronize(st));  // the coefficient tables are freed on return
+    RIP_API_END
+}
+
+extern "C" int rip_medfit_host(int device, const float* arr, int ny, int nx, int N, float* meds) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(arr && meds, "rip_medfit_host: null argument");
+    use_device(device);
+    DevBuf<float> d, m((size_t)N * N);
+    d.upload(arr, (size_t)ny * nx, 0);
+    const int kx = nx / N, ky = ny / N, px = (nx % N) / 2, py = (ny % N) / 2;
+    RIP_REQUIRE(N >= 1 && kx >= 1 && ky >= 1, "rip_medfit_host: %d regions do not fit a %d x %d array", N, ny, nx);
+    RIP_LAUNCH(block_nanmedian_kernel, dim3(N, N), 1024, 0, 0, (const float*)d.p, (long)nx, py, px, ky, kx, N, m.p);
+    m.download(meds, (size_t)N * N, 0);
+    RIP_CUDA(cudaDeviceSynchronize());
+    RIP_API_END
+}

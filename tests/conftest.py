@@ -48,3 +48,17 @@ def build_small_case(tag):
 @pytest.fixture(scope="session")
 def kats():
     return load_golden("kats")
+
+
+def synth_sky_image(ny, nx, seed):
+    """Same seeded image as tests/golden/make_golden_sim.py:synth_sky_image (medfit goldens)."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:ny, 0:nx]
+    img = (0.7 + 0.3 * xx / nx - 0.2 * (yy / ny) ** 2 + 0.05 * rng.randn(ny, nx)).astype(np.float32)
+    img[rng.rand(ny, nx) < 0.02] += 30.0
+    img[rng.rand(ny, nx) < 0.05] = np.nan
+    img[: ny // 8, : nx // 8] = np.nan
+    return img
+
+
+SKY_CASES = {"a": (509, 1022, 2, 8), "b": (300, 257, 0, 8), "c": (412, 412, 3, 4)}

@@ -61,6 +61,17 @@ def small_cal(n, G):
     return cal, pattern
 
 
+def synth_sky_image(ny, nx, seed):
+    """Seeded float32 test image for medfit: smooth gradient + noise + sources + NaN patches (one region all NaN)."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:ny, 0:nx]
+    img = (0.7 + 0.3 * xx / nx - 0.2 * (yy / ny) ** 2 + 0.05 * rng.randn(ny, nx)).astype(np.float32)
+    img[rng.rand(ny, nx) < 0.02] += 30.0
+    img[rng.rand(ny, nx) < 0.05] = np.nan
+    img[: ny // 8, : nx // 8] = np.nan
+    return img
+
+
 def main():
     MG.install_stubs()
     ref_frame, ref_fill = reference_functions(N, N // 32)
@@ -142,6 +153,19 @@ def main():
     assert np.array_equal(mom_sum, mom_ora)
     O.moments_finalize(mom_ora)
     assert np.array_equal(mom_ref, mom_ora)
+    # sky.medfit of the unmodified reference (numpy + scipy only) on a seeded image with NaNs and odd sizes
+    from romanimpreprocess.utils import sky as ref_sky
+
+    sky_out = {}
+    for tag, (sy, sx, order, nreg) in {"a": (509, 1022, 2, 8), "b": (300, 257, 0, 8), "c": (412, 412, 3, 4)}.items():
+        img = synth_sky_image(sy, sx, 40 + ord(tag))
+        coef, model = ref_sky.medfit(img, N=nreg, order=order)
+        ocoef, omodel, omeds = O.medfit(img, N=nreg, order=order)
+        assert np.array_equal(coef, ocoef) and np.array_equal(model, omodel) and model.dtype == np.float32
+        sky_out[f"{tag}_coef"], sky_out[f"{tag}_meds"] = coef, omeds
+        sky_out[f"{tag}_model_sub"] = model[::7, ::5].copy()
+        sky_out[f"{tag}_model_sum"] = np.float64(model.astype(np.float64).sum())
+    np.savez_compressed(os.path.join(HERE, "sky_medfit.npz"), **sky_out)
     np.savez_compressed(
         os.path.join(HERE, "mask_moments.npz"), dq=dq, mask_pixelmask1=ref_mask, mask_custom=ref_mask_c,
         data=np.array(mdata), dqs=np.array(mdq), moments_sum=mom_sum, moments_final=mom_ref,

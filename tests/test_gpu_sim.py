@@ -332,3 +332,32 @@ def test_many_realizations_small():
     assert 0.8 < ratio < 1.25, ratio
     assert np.all(out[1][act] > 0)  # median group difference: the signal accumulates
     del c
+
+
+def test_sky_medfit_exact():
+    """GPU medfit == the reference's medfit bit for bit: region nan-medians by radix select (incl. an all-NaN region and
+    odd sizes), the reference's own normal equations, float64 model evaluation in the reference's term order."""
+    import torch
+
+    from conftest import SKY_CASES, synth_sky_image
+    from romanimpreprocess_b200.utils import sky
+
+    g = load_golden("sky_medfit")
+    for tag, (ny, nx, order, nreg) in SKY_CASES.items():
+        img = synth_sky_image(ny, nx, 40 + ord(tag))
+        coef, model = sky.medfit(img, N=nreg, order=order)
+        assert model.dtype == np.float32 and model.shape == img.shape
+        assert np.array_equal(coef, g[f"{tag}_coef"]), tag
+        assert np.array_equal(model[::7, ::5], g[f"{tag}_model_sub"]), tag
+        assert model.astype(np.float64).sum() == float(g[f"{tag}_model_sum"]), tag
+        # device-resident form on a window of a larger plane, subtracting in place (gen_cal_image.py:645-647)
+        big = np.full((ny + 8, nx + 8), 7.0, np.float32)
+        big[4:-4, 4:-4] = img
+        d = torch.from_numpy(big).cuda()
+        win = d[4:-4, 4:-4]
+        c2 = sky.medfit_device(win.data_ptr(), nx + 8, ny, nx, N=nreg, order=order)
+        torch.cuda.synchronize()
+        out = d.cpu().numpy()
+        assert np.array_equal(c2, coef)
+        assert np.array_equal(out[4:-4, 4:-4], img - model, equal_nan=True)
+        assert np.all(out[:4] == 7.0) and np.all(out[:, :4] == 7.0)

@@ -258,3 +258,21 @@ def test_mask_and_moments_golden():
     orc.moments_finalize(mom)
     assert np.array_equal(mom, g["moments_final"])
     assert np.any(mom[1] == -1000.0)
+
+
+def test_sky_medfit_golden():
+    """sky.medfit (reference utils/sky.py:98-190) against the unmodified reference function."""
+    import warnings
+
+    from conftest import SKY_CASES, synth_sky_image
+
+    g = load_golden("sky_medfit")
+    for tag, (ny, nx, order, nreg) in SKY_CASES.items():
+        img = synth_sky_image(ny, nx, 40 + ord(tag))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            coef, model, meds = orc.medfit(img, N=nreg, order=order)
+        assert np.array_equal(coef, g[f"{tag}_coef"])
+        assert np.array_equal(meds, g[f"{tag}_meds"], equal_nan=True)
+        assert np.array_equal(model[::7, ::5], g[f"{tag}_model_sub"])
+        assert model.astype(np.float64).sum() == float(g[f"{tag}_model_sum"])
