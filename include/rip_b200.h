@@ -334,6 +334,16 @@ int rip_medfit_host(int device, const float* arr, int ny, int nx, int N, float* 
 int rip_medfit_eval_dev(int device, int ny, int nx, int order, const double* coef, const double* LPX, const double* LPY,
                         float* d_model, float* d_arr, long pitch, void* stream);
 
+/* ---- noise layers (L1_to_L2/gen_noise_image.py:60-331 make_noise_cube, directive "R") --------
+ * rip_dark_as_l1_dev: the dark cube's last G groups cast to the u16 L1 cube (:101-109, the "not adding" branch).
+ * rip_add_read_noise_dev: white read noise N(0,1)*read/sqrt(N_k) on the active pixels, round(clip(.,0,65535)) (:121-135).
+ * (the correlated part is rip_fill_refdata_1f_dev, the calibration rip_l1_to_l2_dev, the sky mode removal
+ *  rip_block_nanmedian_dev + rip_medfit_eval_dev.)  rip_active_diff_dev: layer = L2(noisy) - L2(reference) on the
+ * active window of two full-frame float32 planes -> dense [na,na] (:157-163). */
+int rip_dark_as_l1_dev(rip_caldir* h, int G, uint16_t* d_data, void* stream);
+int rip_add_read_noise_dev(rip_caldir* h, uint16_t* d_data, int G, const int32_t* reads_per_group, uint64_t seed, void* stream);
+int rip_active_diff_dev(int device, const float* d_a, const float* d_b, int n, int nb, float* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

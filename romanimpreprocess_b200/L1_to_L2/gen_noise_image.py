@@ -1,0 +1,161 @@
+"""Noise realisations ("noise layers") on the GPU: the read-noise directive of
+``romanimpreprocess.L1_to_L2.gen_noise_image.make_noise_cube`` (reference L1_to_L2/gen_noise_image.py:60-331).
+
+For a layer command such as ``"Rz4S2C1"`` the reference (i) takes the L1 cube (flag ``a``) or the dark cube cast to the
+cube's integer type, (ii) adds white read noise per group and the correlated part (reference pixels, 1/f banding,
+reference output: ``fill_in_refdata_and_1f``), (iii) runs the whole L1->L2 calibration on it through temporary ASDF files,
+(iv) differences the result with the L2 image of the noiseless cube, (v) optionally clips at ``z`` Gaussian-equivalent
+sigmas of the inter-quartile range and (vi) removes the sky modes (``S<order>``: ``sky.medfit``).  Production runs do this
+8 times per exposure (runs/summer2025run/OpenUniverse_to_L1L2.py:124-133), i.e. 9+ calibrations per SCA.
+
+Here every step stays in HBM and shares one resident CALDIR:
+
+    rip_dark_as_l1_dev -> rip_add_read_noise_dev -> rip_fill_refdata_1f_dev -> rip_l1_to_l2_dev
+    [-> medfit (SKYORDER)] -> rip_active_diff_dev [-> z clip (host percentiles)] [-> medfit (S)]
+
+Supported directives: ``R`` (flags ``a``, ``z<number>``), ``S<order>``, ``C<tag>`` (a label: ignored, as in the
+reference).  ``O`` (Pearson pseudo-Poisson draws) and ``P`` (Poisson resampling) are not on the GPU path and raise
+``NotImplementedError``.  Random numbers are Philox (the reference: GalSim): layers are validated statistically.
+"""
+
+import re
+
+import numpy as np
+
+from .. import _lib
+from ..utils import sky
+from . import gen_cal_image as gci
+
+
+def _get_subscript(arr, ch):
+    """Text after the last ``ch`` in ``arr`` up to (not including) the next capital letter:
+    ``_get_subscript('RS2Pg4', 'S') -> '2'`` (reference gen_noise_image.py:33-57)."""
+    return re.split(r"(?=[A-Z])", arr.split(ch)[-1])[0]
+
+
+def _ptr(t):
+    import ctypes as C
+
+    return C.c_void_p(t.data_ptr())
+
+
+class NoiseLayers:
+    """Device-resident noise-layer generator for the exposures of one SCA (one process / GPU)."""
+
+    def __init__(self, caldir, read_pattern, frame_time, config=None, device=0):
+        import torch  # noqa: PLC0415  (device memory only)
+
+        self.torch = torch
+        self.device = device
+        self.dev = torch.device("cuda", device)
+        self.cal = caldir if isinstance(caldir, gci.CalDir) else gci.CalDir(caldir, device)
+        self.owns_cal = self.cal is not caldir
+        self.config = dict(config or {})
+        self.read_pattern = read_pattern
+        cal = self.cal
+        n, G = cal.n, len(read_pattern)
+        self.n, self.na, self.G = n, cal.na, G
+        self.refpix = bool(cal.has_amp33 and n // 32 == 128)  # the reference output is 128 columns wide
+        self.dplan = gci.DevicePlan(cal, read_pattern, frame_time, self.config, do_refpix=self.refpix, area_dtype=np.float32)
+        self.rpg = np.ascontiguousarray([len(g) for g in read_pattern], dtype=np.int32)
+        z = dict(device=self.dev)
+        self.d_work = torch.empty((G, n, n), dtype=torch.uint16, **z)
+        self.d_amp33 = torch.zeros((G, n, 128 if self.refpix else max(n // 32, 1)), dtype=torch.uint16, **z)
+        self.l2 = {k: [torch.empty((n, n), dtype=torch.float32, **z) for _ in range(3)] for k in ("orig", "ref", "noisy")}
+        self.d_pdq = torch.empty((n, n), dtype=torch.int32, **z)
+        self.d_diff = torch.empty((self.na, self.na), dtype=torch.float32, **z)
+        self.have = set()
+
+    def _stream(self):
+        import ctypes as C
+
+        return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _calibrate(self, d_cube, d_amp33, d_area, which):
+        """L1->L2 of a device cube into slot ``which``; the L2 ``data`` plane is sky-subtracted when SKYORDER is set
+        (gen_cal_image.py:643-647), exactly what the reference differences."""
+        st = self._stream()
+        s, er, ep = self.l2[which]
+        gci.calibrate_device(self.cal, self.dplan, d_cube.data_ptr(), d_amp33.data_ptr() if self.refpix else 0,
+                             d_area.data_ptr() if d_area is not None else 0, s.data_ptr(), er.data_ptr(), ep.data_ptr(),
+                             self.d_pdq.data_ptr(), stream=st.value or 0)  # fmt: skip
+        if "SKYORDER" in self.config:
+            nb, n = self.cal.nb, self.n
+            sky.medfit_device(s[nb : n - nb, nb : n - nb].data_ptr(), n, self.na, self.na, order=int(self.config["SKYORDER"]),
+                              device=self.device, stream=st.value or 0, subtract=True)  # fmt: skip
+        self.have.add(which)
+
+    def set_exposure(self, d_data, d_amp33, d_area=None):
+        """The exposure the layers belong to: device tensors u16 [G,n,n], u16 [G,n,128], f32 [n,n] (or None)."""
+        self.d_data, self.d_amp33_in, self.d_area = d_data, d_amp33, d_area
+        self.have.discard("orig")
+        self.have.discard("ref")
+
+    def layer(self, cmd, seed):
+        """One noise layer [na,na] float32 (host) for the directive string ``cmd``."""
+        lib, cal, st = _lib.lib(), self.cal, self._stream()
+        if "O" in cmd or "P" in cmd:
+            raise NotImplementedError(f"noise directive {cmd!r}: only R / S / C are generated on the GPU")
+        self.d_diff.zero_()
+        flags = ""
+        if "R" in cmd:
+            flags = _get_subscript(cmd, "R")
+            if "a" in flags:
+                if "orig" not in self.have:
+                    self._calibrate(self.d_data, self.d_amp33_in, self.d_area, "orig")
+                self.d_work.copy_(self.d_data)
+                if self.refpix:
+                    self.d_amp33.copy_(self.d_amp33_in)
+                base = "orig"
+            else:
+                _lib.check(lib.rip_dark_as_l1_dev(cal.handle, self.G, _ptr(self.d_work), st))
+                if self.refpix:
+                    self.d_amp33.copy_(self.d_amp33_in)
+                if "ref" not in self.have:
+                    self._calibrate(self.d_work, self.d_amp33, self.d_area, "ref")
+                base = "ref"
+            seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+            _lib.check(lib.rip_add_read_noise_dev(cal.handle, _ptr(self.d_work), self.G, _lib.ptr(self.rpg), seed, st))
+            _lib.check(lib.rip_fill_refdata_1f_dev(cal.handle, _ptr(self.d_work), _ptr(self.d_amp33), self.G,
+                                                   _lib.ptr(self.rpg), seed, 1, st))  # fmt: skip
+            self._calibrate(self.d_work, self.d_amp33, self.d_area, "noisy")
+            _lib.check(lib.rip_active_diff_dev(self.device, _ptr(self.l2["noisy"][0]), _ptr(self.l2[base][0]), self.n,
+                                               cal.nb, _ptr(self.d_diff), st))  # fmt: skip
+            if "z" in flags:
+                zclip = float(_get_subscript(flags.upper(), "Z"))
+                diff = self.d_diff.cpu().numpy()
+                iqr = np.percentile(diff, 75) - np.percentile(diff, 25)
+                med = np.percentile(diff, 50)
+                diff = np.clip(diff, med - zclip * iqr / 1.34896, med + zclip * iqr / 1.34896)
+                self.d_diff.copy_(self.torch.from_numpy(np.ascontiguousarray(diff, dtype=np.float32)))
+        if "S" in cmd:
+            sky_order = int("0" + _get_subscript(cmd, "S"))
+            sky.medfit_device(self.d_diff.data_ptr(), self.na, self.na, self.na, order=sky_order, device=self.device,
+                              stream=st.value or 0, subtract=True)  # fmt: skip
+        return self.d_diff.cpu().numpy()
+
+    def close(self):
+        if self.owns_cal:
+            self.cal.close()
+
+
+def make_noise_cube_arrays(data, amp33, caldir, read_pattern, frame_time, layers, seed, area_factor=None, config=None, device=0):
+    """
+    Array-level ``make_noise_cube``: L1 cube u16 [G,n,n] + reference output u16 [G,n,128] -> noise realisations
+    float32 [len(layers), n-8, n-8] for the directive strings in ``layers`` (``config["NOISE"]["LAYER"]``).
+    """
+    import torch  # noqa: PLC0415
+
+    nl = NoiseLayers(caldir, read_pattern, frame_time, config, device)
+    try:
+        dev = nl.dev
+        d_data = torch.from_numpy(np.ascontiguousarray(data).view(np.int16)).to(dev).view(torch.uint16)
+        d_amp = torch.from_numpy(np.ascontiguousarray(amp33).view(np.int16)).to(dev).view(torch.uint16)
+        d_area = None if area_factor is None else torch.from_numpy(np.ascontiguousarray(area_factor, dtype=np.float32)).to(dev)
+        nl.set_exposure(d_data, d_amp, d_area)
+        out = np.zeros((len(layers), nl.na, nl.na), np.float32)
+        for i, cmd in enumerate(layers):
+            out[i] = nl.layer(cmd, int(seed) + 1000 * (i + 1))
+        return out
+    finally:
+        nl.close()

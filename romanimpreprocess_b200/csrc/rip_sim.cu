@@ -825,3 +825,83 @@ extern "C" int rip_medfit_host(int device, const float* arr, int ny, int nx, int
     RIP_CUDA(cudaDeviceSynchronize());
     RIP_API_END
 }
+
+// =========================================================================================================
+// Noise layers (L1_to_L2/gen_noise_image.py:60-331 make_noise_cube), the device-side pieces of directive "R"
+// =========================================================================================================
+namespace rip {
+
+// white read noise on the active pixels of a u16 cube (gen_noise_image.py:121-135):
+//   im = N(0,1);  im *= read / sqrt(N_k)  (float32 array times a float64 quotient, stored float32);
+//   resultants = float32(data) + im;  data = round(clip(resultants, 0, 65535))
+__global__ void add_read_noise_kernel(uint16_t* __restrict__ data, int G, int n, int nb, const float* __restrict__ read,
+                                      const double* __restrict__ sqrt_n, uint64_t seed) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x + nb, y = blockIdx.y + nb, k = blockIdx.z;
+    if (x >= n - nb) return;
+    const long p = (long)y * n + x;
+    Philox r;
+    r.init(seed, (uint64_t)p, 96u + (unsigned)k);
+    float im = r.normal();
+    im = (float)((double)im * ((double)read[p] / sqrt_n[k]));
+    float res = (float)data[(long)k * n * n + p] + im;
+    res = res < 0.0f ? 0.0f : (res > 65535.0f ? 65535.0f : res);
+    data[(long)k * n * n + p] = (uint16_t)rintf(res);
+}
+
+// dark cube (last G groups) cast to the cube's integer type: gen_noise_image.py:101-109 (astype truncates)
+__global__ void dark_to_u16_kernel(const float* __restrict__ dark, long count, uint16_t* __restrict__ out) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= count) return;
+    const float v = dark[p];
+    out[p] = (uint16_t)(int)(v < 0.0f ? 0.0f : (v > 65535.0f ? 65535.0f : v));
+}
+
+// diff = a - b on the active window of two full-frame float32 planes -> dense [na,na]
+__global__ void active_diff_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, int nb, float* __restrict__ out) {
+    const int na = n - 2 * nb;
+    const int xa = blockIdx.x * blockDim.x + threadIdx.x, ya = blockIdx.y;
+    if (xa >= na) return;
+    const long q = (long)(ya + nb) * n + (xa + nb);
+    out[(long)ya * na + xa] = a[q] - b[q];
+}
+
+}  // namespace rip
+
+extern "C" int rip_add_read_noise_dev(rip_caldir* h, uint16_t* d_data, int G, const int32_t* reads_per_group, uint64_t seed,
+                                      void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && d_data && reads_per_group && G >= 1 && G <= RIP_GMAX, "rip_add_read_noise_dev: bad argument");
+    use_device(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    double sq[RIP_GMAX];
+    for (int g = 0; g < G; ++g) sq[g] = sqrt((double)reads_per_group[g]);
+    if (h->f_sums.n < 64) h->f_sums.alloc(64);
+    RIP_CUDA(cudaMemcpyAsync(h->f_sums.p + 40, sq, G * sizeof(double), cudaMemcpyHostToDevice, st));
+    RIP_CUDA(cudaStreamSynchronize(st));  // (sq lives on this stack frame)
+    const int na = h->na;
+    dim3 grid((na + 127) / 128, na, G);
+    RIP_LAUNCH(add_read_noise_kernel, grid, 128, 0, st, d_data, G, h->n, h->nb, (const float*)h->read.p,
+               (const double*)(h->f_sums.p + 40), seed);
+    RIP_API_END
+}
+
+extern "C" int rip_dark_as_l1_dev(rip_caldir* h, int G, uint16_t* d_data, void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && d_data, "rip_dark_as_l1_dev: null argument");
+    RIP_REQUIRE(h->d.n_dark - G == 0 || h->d.n_dark - G == 1, "Dark date cube has the wrong shape.");  // (the reference's message)
+    use_device(h->device);
+    const long npl = (long)h->n * h->n, count = (long)G * npl;
+    RIP_LAUNCH(dark_to_u16_kernel, (unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream,
+               (const float*)(h->dark_cube.p + (size_t)(h->d.n_dark - G) * npl), count, d_data);
+    RIP_API_END
+}
+
+extern "C" int rip_active_diff_dev(int device, const float* d_a, const float* d_b, int n, int nb, float* d_out, void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(d_a && d_b && d_out && n > 2 * nb, "rip_active_diff_dev: bad argument");
+    use_device(device);
+    const int na = n - 2 * nb;
+    dim3 grid((na + 127) / 128, na);
+    RIP_LAUNCH(active_diff_kernel, grid, 128, 0, (cudaStream_t)stream, d_a, d_b, n, nb, d_out);
+    RIP_API_END
+}

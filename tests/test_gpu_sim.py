@@ -361,3 +361,64 @@ def test_sky_medfit_exact():
         assert np.array_equal(c2, coef)
         assert np.array_equal(out[4:-4, 4:-4], img - model, equal_nan=True)
         assert np.all(out[:4] == 7.0) and np.all(out[:, :4] == 7.0)
+
+
+def test_noise_layers_against_oracle_composition():
+    """gen_noise_image 'R' layers (reference L1_to_L2/gen_noise_image.py:60-163, 322-326) at 256^2: the layer built on
+    the GPU has the statistics of the same composition done with the oracle (dark cube -> white noise ->
+    fill_in_refdata_and_1f -> L1->L2 -> difference); 'z' clips, 'S' removes the sky modes, 'a' starts from the exposure."""
+    from romanimpreprocess_b200 import synth
+    from romanimpreprocess_b200.L1_to_L2 import gen_noise_image as gni
+    from romanimpreprocess_b200.utils import sky
+
+    n = 256
+    rp = synth.README_PATTERN
+    G = len(rp)
+    cal = synth.make_caldir(n=n, read_pattern=rp, p_order=10, seed=31, gain_dtype=np.float32, ipc_dtype=np.float32)
+    c = _trees(cal)
+    data, amp33, _ = synth.make_l1(cal, rp, seed=32, n_sources=4, cr_frac=0.0, bright=0.5)
+    cfg = {}
+    layers = gni.make_noise_cube_arrays(data, amp33, cal, rp, synth.FRAME_TIME, ["R", "Rz3", "RaS2", "RS1C7"], seed=5, config=cfg)
+    assert layers.shape == (4, n - 8, n - 8) and layers.dtype == np.float32
+    # oracle composition of the plain 'R' layer
+    tij = orc.read_pattern_to_tij(rp)
+    dk = c["dark"]["data"]
+    base = dk[dk.shape[0] - G :].astype(np.uint16)
+    one = np.ones((n, n), np.float32)
+    ref = orc.l1_to_l2(base, None, c, rp, synth.FRAME_TIME, one, cfg, do_refpix=False)
+    rng = np.random.default_rng(3)
+    noisy = base.copy()
+    for k in range(G):
+        res = noisy[k, 4:-4, 4:-4].astype(np.float32)
+        im = rng.standard_normal(res.shape).astype(np.float32)
+        im *= c["read"]["data"][4:-4, 4:-4] / np.sqrt(len(rp[k]))
+        noisy[k, 4:-4, 4:-4] = np.round(np.clip(res + im, 0, 2**16 - 1)).astype(np.uint16)
+    orc.fill_in_refdata_and_1f(noisy, c, orc.NormalStream(4), tij, fill_in_banding=True)
+    out = orc.l1_to_l2(noisy, None, c, rp, synth.FRAME_TIME, one, cfg, do_refpix=False)
+    odiff = (out["slope"] - ref["slope"])[4:-4, 4:-4]
+    inner = (slice(8, -8), slice(8, -8))
+    g0 = layers[0]
+    okpix = np.isfinite(odiff) & np.isfinite(g0)
+    assert okpix.mean() > 0.99
+
+    def robust_sigma(a):
+        q = np.percentile(a, [25, 75])
+        return (q[1] - q[0]) / 1.34896
+
+    so, sg = robust_sigma(odiff[okpix]), robust_sigma(g0[okpix])
+    assert abs(sg / so - 1.0) < 0.08, (sg, so)
+    assert abs(np.median(g0[okpix])) < 0.2 * sg
+    # the white part dominates and matches the reported read-noise error of the fit
+    assert 0.7 < sg / np.median(out["err_read"][4:-4, 4:-4][okpix]) < 1.6
+    # z clip: nothing beyond 3 "sigma" of the inter-quartile range
+    z = layers[1]
+    iqr = np.percentile(z, 75) - np.percentile(z, 25)
+    assert np.all(np.abs(z - np.percentile(z, 50)) <= 3 * iqr / 1.34896 * (1 + 1e-5))
+    # S: the fitted low-order model of the result is (numerically) gone
+    for lay, order in ((layers[2], 2), (layers[3], 1)):
+        coef, model = sky.medfit(np.ascontiguousarray(lay), order=order)
+        assert np.abs(model).max() < 0.02 * robust_sigma(lay[inner])
+    # 'a': built on the exposure itself -> same noise level
+    assert abs(robust_sigma(layers[2][inner]) / sg - 1.0) < 0.25
+    with pytest.raises(NotImplementedError):
+        gni.make_noise_cube_arrays(data, amp33, cal, rp, synth.FRAME_TIME, ["Rz4PbrS2C1"], seed=5, config=cfg)
