@@ -558,6 +558,53 @@ def run_realizations(args):
         dist.destroy_process_group()
 
 
+def run_noiselayers(args):
+    """Secondary workload (the production call pattern of runs/summer2025run/OpenUniverse_to_L1L2.py:
+    124-133): per exposure `--layers` noise layers "Rz4S2C<i>" with SKYORDER 2 = (1 + layers) full L1->L2 calibrations,
+    white + correlated noise generation (34 x 8 FFTs of 2^20 points per layer), sky-mode fits, differences; device
+    resident except the z-clip percentiles and the returned layers (host)."""
+    import torch
+
+    from romanimpreprocess_b200 import synth
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+    from romanimpreprocess_b200.L1_to_L2 import gen_noise_image as gni
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    rp = synth.README_PATTERN
+    n = args.n
+    cal, exposures, area = make_inputs(n, rp, 2, seed=1000)
+    cd = gci.CalDir(cal, device=local)
+    cfg = {"SKYORDER": 2}
+    nl = gni.NoiseLayers(cd, rp, synth.FRAME_TIME, cfg, device=local)
+    d_data = torch.from_numpy(exposures[0][0].view(np.int16)).to(dev).view(torch.uint16)
+    d_amp = torch.from_numpy(exposures[0][1].view(np.int16)).to(dev).view(torch.uint16)
+    d_area = torch.from_numpy(area).to(dev)
+    layers = [f"Rz4S2C{i + 1}" for i in range(args.layers)]
+    nl.set_exposure(d_data, d_amp, d_area)
+    nl.layer(layers[0], 1)  # warm-up: workspaces, FFT attributes, the reference calibration of the dark cube
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    kept = []
+    for e in range(args.steps):
+        nl.set_exposure(d_data, d_amp, d_area)
+        kept = [nl.layer(cmd, 1000 * e + i + 2) for i, cmd in enumerate(layers)]
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    sig = []
+    for lay in kept:  # (outside the timed region) robust scatter of each layer of the last exposure
+        q = np.percentile(lay[8:-8, 8:-8], [25, 75])
+        sig.append(float((q[1] - q[0]) / 1.34896))
+    print(json.dumps({"metric": "noise-layer exposures/s (gen_noise_image, 4096^2 x 8 resultants, layers Rz4S2C*, SKYORDER 2)",
+                      "value": 1.0 / dt, "unit": "exposures/s", "layers_per_exposure": len(layers),
+                      "ms_per_layer": 1e3 * dt / len(layers), "n_gpus": 1, "steps": args.steps, "dtype": "f32", "data": "synthetic",
+                      "secondary_workload": True, "timing": "wall clock incl. the D2H of every layer (pageable) and the host-side normal equations of the sky fits",
+                      "layer_sigma_DN_per_s": sig}), flush=True)  # fmt: skip
+    nl.close()
+    cd.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -573,7 +620,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (for ncu captures)")
     ap.add_argument("--realizations", type=int, default=64, help="noise realisations (workload realizations)")
-    ap.add_argument("--workload", default="l1l2", choices=["l1l2", "forward", "realizations"],
+    ap.add_argument("--layers", type=int, default=8, help="noise layers per exposure (workload noiselayers)")
+    ap.add_argument("--workload", default="l1l2", choices=["l1l2", "forward", "realizations", "noiselayers"],
                     help="l1l2 = the headline metric; forward = secondary line for the forward ramp generator")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -583,6 +631,8 @@ def main():
         run_forward(args)
     elif args.workload == "realizations":
         run_realizations(args)
+    elif args.workload == "noiselayers":
+        run_noiselayers(args)
     else:
         run_ours(args)
 

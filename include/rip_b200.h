@@ -344,6 +344,13 @@ int rip_dark_as_l1_dev(rip_caldir* h, int G, uint16_t* d_data, void* stream);
 int rip_add_read_noise_dev(rip_caldir* h, uint16_t* d_data, int G, const int32_t* reads_per_group, uint64_t seed, void* stream);
 int rip_active_diff_dev(int device, const float* d_a, const float* d_b, int n, int nb, float* d_out, void* stream);
 
+/* order statistics (0-based ranks, ascending, NaNs excluded; K <= 16 ranks, one CTA each) of a flat float32 device array
+ * -> host; n_valid = number of non-NaN elements.  With rip_clip_dev (np.clip, NaN bounds propagate) this is the z clip of
+ * the noise layers (gen_noise_image.py:165-171: np.percentile's linear interpolation is done by the caller). */
+int rip_order_stats_dev(int device, const float* d_arr, long count, int K, const long* ranks, float* out, long* n_valid,
+                        void* stream);
+int rip_clip_dev(int device, float* d_arr, long count, float lo, float hi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

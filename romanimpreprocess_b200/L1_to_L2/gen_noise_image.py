@@ -11,7 +11,7 @@ sigmas of the inter-quartile range and (vi) removes the sky modes (``S<order>``:
 Here every step stays in HBM and shares one resident CALDIR:
 
     rip_dark_as_l1_dev -> rip_add_read_noise_dev -> rip_fill_refdata_1f_dev -> rip_l1_to_l2_dev
-    [-> medfit (SKYORDER)] -> rip_active_diff_dev [-> z clip (host percentiles)] [-> medfit (S)]
+    [-> medfit (SKYORDER)] -> rip_active_diff_dev [-> z clip: rip_order_stats_dev + rip_clip_dev] [-> medfit (S)]
 
 Supported directives: ``R`` (flags ``a``, ``z<number>``), ``S<order>``, ``C<tag>`` (a label: ignored, as in the
 reference).  ``O`` (Pearson pseudo-Poisson draws) and ``P`` (Poisson resampling) are not on the GPU path and raise
@@ -123,11 +123,11 @@ class NoiseLayers:
                                                cal.nb, _ptr(self.d_diff), st))  # fmt: skip
             if "z" in flags:
                 zclip = float(_get_subscript(flags.upper(), "Z"))
-                diff = self.d_diff.cpu().numpy()
-                iqr = np.percentile(diff, 75) - np.percentile(diff, 25)
-                med = np.percentile(diff, 50)
-                diff = np.clip(diff, med - zclip * iqr / 1.34896, med + zclip * iqr / 1.34896)
-                self.d_diff.copy_(self.torch.from_numpy(np.ascontiguousarray(diff, dtype=np.float32)))
+                p25, p50, p75 = sky.percentiles_device(self.d_diff.data_ptr(), self.na * self.na, (25, 50, 75),
+                                                       device=self.device, stream=st.value or 0)  # fmt: skip
+                iqr, med = p75 - p25, p50
+                _lib.check(lib.rip_clip_dev(self.device, _ptr(self.d_diff), self.na * self.na,
+                                            float(med - zclip * iqr / 1.34896), float(med + zclip * iqr / 1.34896), st))
         if "S" in cmd:
             sky_order = int("0" + _get_subscript(cmd, "S"))
             sky.medfit_device(self.d_diff.data_ptr(), self.na, self.na, self.na, order=sky_order, device=self.device,

@@ -156,6 +156,9 @@ _SIGS = {
     "rip_dark_as_l1_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "rip_add_read_noise_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]),
     "rip_active_diff_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "rip_order_stats_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_long),
+                                      C.c_void_p]),
+    "rip_clip_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_long, C.c_float, C.c_float, C.c_void_p]),
     "rip_stack_median_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p]),
 }  # fmt: skip
 

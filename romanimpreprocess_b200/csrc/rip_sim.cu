@@ -905,3 +905,87 @@ extern "C" int rip_active_diff_dev(int device, const float* d_a, const float* d_
     RIP_LAUNCH(active_diff_kernel, grid, 128, 0, (cudaStream_t)stream, d_a, d_b, n, nb, d_out);
     RIP_API_END
 }
+
+// =========================================================================================================
+// Order statistics of a flat float32 array (np.percentile's inputs for the z clip of the noise layers,
+// gen_noise_image.py:165-171) and the clip itself
+// =========================================================================================================
+namespace rip {
+
+// one CTA per requested rank: value of rank r (0-based, ascending, NaNs excluded) by four 8-bit radix passes
+__global__ void __launch_bounds__(1024) order_stat_kernel(const float* __restrict__ arr, long count, const long* __restrict__ ranks,
+                                                          float* __restrict__ out, long* __restrict__ n_valid) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t prefix, mask_s;
+    __shared__ unsigned long long rank_s, cnt_s;
+    if (threadIdx.x == 0) { prefix = 0u; mask_s = 0u; rank_s = (unsigned long long)ranks[blockIdx.x]; cnt_s = 0ull; }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+        __syncthreads();
+        const uint32_t m = mask_s, p0 = prefix;
+        for (long e = threadIdx.x; e < count; e += blockDim.x) {
+            const float v = arr[e];
+            if (v != v) continue;
+            const uint32_t k = f2key_sky(v);
+            if ((k & m) == p0) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (pass == 0) {
+                unsigned long long c = 0;
+                for (int b = 0; b < 256; ++b) c += hist[b];
+                cnt_s = c;
+                if (rank_s >= c) rank_s = c ? c - 1 : 0;
+            }
+            unsigned long long r = rank_s, acc = 0;
+            int b = 0;
+            for (; b < 255; ++b) {
+                if (acc + hist[b] > r) break;
+                acc += hist[b];
+            }
+            rank_s = r - acc;
+            prefix |= (uint32_t)b << shift;
+            mask_s |= 255u << shift;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[blockIdx.x] = cnt_s ? key2f_sky(prefix) : NAN;
+        if (blockIdx.x == 0) n_valid[0] = (long)cnt_s;
+    }
+}
+
+__global__ void clip_kernel(float* __restrict__ a, long count, float lo, float hi) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= count) return;
+    a[p] = np_clip<float>(a[p], lo, hi);
+}
+
+}  // namespace rip
+
+extern "C" int rip_order_stats_dev(int device, const float* d_arr, long count, int K, const long* ranks, float* out,
+                                   long* n_valid, void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(d_arr && ranks && out && K >= 1 && K <= 16 && count >= 1, "rip_order_stats_dev: bad argument");
+    use_device(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf<long> dr(K + 1);
+    DevBuf<float> dout(K);
+    dr.upload(ranks, K, st);
+    RIP_LAUNCH(order_stat_kernel, K, 1024, 0, st, d_arr, count, (const long*)dr.p, dout.p, dr.p + K);
+    dout.download(out, K, st);
+    long nv = 0;
+    RIP_CUDA(cudaMemcpyAsync(&nv, dr.p + K, sizeof(long), cudaMemcpyDeviceToHost, st));
+    RIP_CUDA(cudaStreamSynchronize(st));
+    if (n_valid) *n_valid = nv;
+    RIP_API_END
+}
+
+extern "C" int rip_clip_dev(int device, float* d_arr, long count, float lo, float hi, void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(d_arr && count >= 1, "rip_clip_dev: bad argument");
+    use_device(device);
+    RIP_LAUNCH(clip_kernel, (unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream, d_arr, count, lo, hi);
+    RIP_API_END
+}

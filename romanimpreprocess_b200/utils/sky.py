@@ -106,3 +106,28 @@ def medfit_device(d_arr, pitch, ny, nx, N=8, order=2, device=0, stream=None, sub
                                        C.c_void_p(d_model or None), C.c_void_p(d_arr if subtract else None), pitch,
                                        C.c_void_p(stream or None)))  # fmt: skip
     return x
+
+
+def percentiles_device(d_arr, count, qs, device=0, stream=None):
+    """``np.percentile(arr, q)`` (linear interpolation) for a flat device-resident float32 array: the two bracketing
+    order statistics of every q come from ``rip_order_stats_dev``; NaN anywhere gives NaN, as in NumPy."""
+    lib = _lib.lib()
+    ranks, fr = [], []
+    for q in qs:
+        vi = (count - 1) * (float(q) / 100.0)
+        lo = int(np.floor(vi))
+        ranks += [lo, min(lo + 1, count - 1)]
+        fr.append(vi - lo)
+    r = np.ascontiguousarray(ranks, dtype=np.int64)
+    out = np.empty(len(ranks), np.float32)
+    nv = C.c_long(0)
+    _lib.check(lib.rip_order_stats_dev(device, C.c_void_p(d_arr), count, len(ranks), _lib.ptr(r), _lib.ptr(out), C.byref(nv),
+                                       C.c_void_p(stream or None)))  # fmt: skip
+    if nv.value != count:
+        return [np.float32(np.nan)] * len(qs)
+    res = []
+    for i, t in enumerate(fr):
+        a, b = np.float64(out[2 * i]), np.float64(out[2 * i + 1])
+        v = a + (b - a) * t if t < 0.5 else b - (b - a) * (1 - t)  # numpy's _lerp
+        res.append(np.float32(v))
+    return res

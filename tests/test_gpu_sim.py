@@ -422,3 +422,24 @@ def test_noise_layers_against_oracle_composition():
     assert abs(robust_sigma(layers[2][inner]) / sg - 1.0) < 0.25
     with pytest.raises(NotImplementedError):
         gni.make_noise_cube_arrays(data, amp33, cal, rp, synth.FRAME_TIME, ["Rz4PbrS2C1"], seed=5, config=cfg)
+
+
+def test_percentiles_device():
+    """Order statistics by radix select + NumPy's linear interpolation == np.percentile (float32 rounding)."""
+    import torch
+
+    from romanimpreprocess_b200.utils import sky
+
+    rng = np.random.RandomState(8)
+    for count in (1, 2, 1001, 300000):
+        a = (rng.randn(count) * 3 - 1).astype(np.float32)
+        if count > 10:
+            a[5] = -0.0
+            a[7] = 1.0e30
+        d = torch.from_numpy(a).cuda()
+        got = sky.percentiles_device(d.data_ptr(), count, (0, 25, 50, 75, 100))
+        ref = np.percentile(a.astype(np.float64), [0, 25, 50, 75, 100])
+        assert np.allclose(np.array(got, np.float64), ref, rtol=2e-7, atol=0), (count, got, ref)
+    a[3] = np.nan
+    d = torch.from_numpy(a).cuda()
+    assert all(np.isnan(v) for v in sky.percentiles_device(d.data_ptr(), a.size, (25, 75)))
