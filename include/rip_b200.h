@@ -351,6 +351,14 @@ int rip_order_stats_dev(int device, const float* d_arr, long count, int K, const
                         void* stream);
 int rip_clip_dev(int device, float* d_arr, long count, float lo, float hi, void* stream);
 
+/* noise directive "P" with flag r (gen_noise_image.py:258-321): per active pixel, n_samp Poisson draws with mean
+ * e = clip(skylevel*gain*frame_time, 0), (draw - e)/gain accumulated sample by sample, averaged into the resultants
+ * (group_of_read[i] = group containing sample i or -1) and contracted with the ramp-fit weights of the pixel's ramp end
+ * (weights f32 [G,G]: row es, w_defined[es] = row exists; es = endslice > 0 ? endslice : G-1): d_diff [na,na] += . */
+int rip_poisson_resample_dev(rip_caldir* h, const float* d_skylevel, const int8_t* d_endslice, int G, int n_samp,
+                             const int32_t* group_of_read, const float* weights, const uint8_t* w_defined, double frame_time,
+                             uint64_t seed, float* d_diff, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

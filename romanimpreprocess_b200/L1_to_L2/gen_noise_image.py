@@ -13,9 +13,10 @@ Here every step stays in HBM and shares one resident CALDIR:
     rip_dark_as_l1_dev -> rip_add_read_noise_dev -> rip_fill_refdata_1f_dev -> rip_l1_to_l2_dev
     [-> medfit (SKYORDER)] -> rip_active_diff_dev [-> z clip: rip_order_stats_dev + rip_clip_dev] [-> medfit (S)]
 
-Supported directives: ``R`` (flags ``a``, ``z<number>``), ``S<order>``, ``C<tag>`` (a label: ignored, as in the
-reference).  ``O`` (Pearson pseudo-Poisson draws) and ``P`` (Poisson resampling) are not on the GPU path and raise
-``NotImplementedError``.  Random numbers are Philox (the reference: GalSim): layers are validated statistically.
+Supported directives: ``R`` (flags ``a``, ``z<number>``), ``P`` (flags ``b<order>``, ``r``: re-sampled Poisson noise of
+the sky level propagated through the ramp-fit weights of each pixel's ramp end, ``rip_poisson_resample_dev``),
+``S<order>``, ``C<tag>`` (a label: ignored, as in the reference) -- i.e. the production layers ``Rz4PbrS2C*``.
+``O`` (Pearson pseudo-Poisson draws) is not on the GPU path and raises ``NotImplementedError``.  Random numbers are Philox (the reference: GalSim): layers are validated statistically.
 """
 
 import re
@@ -64,6 +65,10 @@ class NoiseLayers:
         self.l2 = {k: [torch.empty((n, n), dtype=torch.float32, **z) for _ in range(3)] for k in ("orig", "ref", "noisy")}
         self.d_pdq = torch.empty((n, n), dtype=torch.int32, **z)
         self.d_diff = torch.empty((self.na, self.na), dtype=torch.float32, **z)
+        self.d_withsky = torch.empty((self.na, self.na), dtype=torch.float32, **z)  # data_withsky of the exposure's L2
+        self.d_skylevel = torch.empty((self.na, self.na), dtype=torch.float32, **z)
+        self.d_endslice = torch.empty((self.na, self.na), dtype=torch.int8, **z)
+        self.frame_time = float(frame_time)
         self.have = set()
 
     def _stream(self):
@@ -78,7 +83,10 @@ class NoiseLayers:
         s, er, ep = self.l2[which]
         gci.calibrate_device(self.cal, self.dplan, d_cube.data_ptr(), d_amp33.data_ptr() if self.refpix else 0,
                              d_area.data_ptr() if d_area is not None else 0, s.data_ptr(), er.data_ptr(), ep.data_ptr(),
-                             self.d_pdq.data_ptr(), stream=st.value or 0)  # fmt: skip
+                             self.d_pdq.data_ptr(), d_endslice=self.d_endslice.data_ptr() if which == "orig" else 0,
+                             stream=st.value or 0)  # fmt: skip
+        if which == "orig":  # slope_withsky (gen_cal_image.py:640), active window
+            self.d_withsky.copy_(s[self.cal.nb : self.n - self.cal.nb, self.cal.nb : self.n - self.cal.nb])
         if "SKYORDER" in self.config:
             nb, n = self.cal.nb, self.n
             sky.medfit_device(s[nb : n - nb, nb : n - nb].data_ptr(), n, self.na, self.na, order=int(self.config["SKYORDER"]),
@@ -94,8 +102,8 @@ class NoiseLayers:
     def layer(self, cmd, seed):
         """One noise layer [na,na] float32 (host) for the directive string ``cmd``."""
         lib, cal, st = _lib.lib(), self.cal, self._stream()
-        if "O" in cmd or "P" in cmd:
-            raise NotImplementedError(f"noise directive {cmd!r}: only R / S / C are generated on the GPU")
+        if "O" in cmd:
+            raise NotImplementedError(f"noise directive {cmd!r}: the Pearson draws of 'O' are not generated on the GPU")
         self.d_diff.zero_()
         flags = ""
         if "R" in cmd:
@@ -128,6 +136,38 @@ class NoiseLayers:
                 iqr, med = p75 - p25, p50
                 _lib.check(lib.rip_clip_dev(self.device, _ptr(self.d_diff), self.na * self.na,
                                             float(med - zclip * iqr / 1.34896), float(med + zclip * iqr / 1.34896), st))
+        if "P" in cmd:
+            pflags = _get_subscript(cmd, "P")
+            if "orig" not in self.have:
+                self._calibrate(self.d_data, self.d_amp33_in, self.d_area, "orig")
+            if "b" in pflags:  # background only: the sky model of the given order (reference :191-195)
+                b_order = int("0" + _get_subscript(pflags.upper(), "B"))
+                sky.medfit_device(self.d_withsky.data_ptr(), self.na, self.na, self.na, order=b_order, device=self.device,
+                                  stream=st.value or 0, subtract=False, d_model=self.d_skylevel.data_ptr())  # fmt: skip
+            else:
+                self.d_skylevel.copy_(self.d_withsky)
+            if "r" in pflags:
+                G, meta = self.G, self.dplan.meta
+                start = 1 if self.config.get("EXCLUDE_FIRST", True) else 0
+                w = np.zeros((G, G), np.float32)
+                wdef = np.zeros(G, np.uint8)
+                w[G - 1] = np.array([self.dplan.plan.var_K[0][j] for j in range(G)], np.float32)  # processinfo weights
+                wdef[G - 1] = 1
+                for iend in range(start + 2, G):  # two-point weights of the truncated ramps (reference :204-208)
+                    kt = np.zeros(G, dtype=np.float32)
+                    kt[iend - 1] = 1.0 / (meta["tbar"][iend - 1] - meta["tbar"][start])
+                    kt[start] = -kt[iend - 1]
+                    w[iend - 1], wdef[iend - 1] = kt, 1
+                lastsamp = self.read_pattern[-1][-1]
+                gor = np.full(lastsamp + 1, -1, np.int32)
+                for j, grp in enumerate(self.read_pattern):
+                    for r in grp:
+                        if 0 <= r <= lastsamp:
+                            gor[r] = j
+                _lib.check(lib.rip_poisson_resample_dev(cal.handle, _ptr(self.d_skylevel), _ptr(self.d_endslice), G,
+                                                        lastsamp + 1, _lib.ptr(gor), _lib.ptr(w), _lib.ptr(wdef),
+                                                        self.frame_time, (int(seed) + 7) & 0xFFFFFFFFFFFFFFFF,
+                                                        _ptr(self.d_diff), st))  # fmt: skip
         if "S" in cmd:
             sky_order = int("0" + _get_subscript(cmd, "S"))
             sky.medfit_device(self.d_diff.data_ptr(), self.na, self.na, self.na, order=sky_order, device=self.device,

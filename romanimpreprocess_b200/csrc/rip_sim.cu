@@ -989,3 +989,87 @@ extern "C" int rip_clip_dev(int device, float* d_arr, long count, float lo, floa
     RIP_LAUNCH(clip_kernel, (unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream, d_arr, count, lo, hi);
     RIP_API_END
 }
+
+// =========================================================================================================
+// Noise directive "P" with flag r: re-sampled Poisson noise propagated through the ramp-fit weights
+// (L1_to_L2/gen_noise_image.py:258-321)
+// =========================================================================================================
+namespace rip {
+
+struct PoisArgs {
+    int n, nb, G, n_samp;
+    float frame_time;
+    int group_of_read[64];            // group whose read list contains sample i, or -1
+    float n_in_group[RIP_GMAX];       // len(read_pattern[j])
+    float w[RIP_GMAX][RIP_GMAX];      // w[es][j]: weight of resultant j for pixels whose ramp ends at es (0 where undefined)
+    uint8_t w_defined[RIP_GMAX];
+    uint64_t seed;
+};
+
+template <typename TG>
+__global__ void poisson_resample_kernel(const PoisArgs A, const float* __restrict__ skylevel, const TG* __restrict__ gain,
+                                        const int8_t* __restrict__ endslice, float* __restrict__ diff) {
+    const int na = A.n - 2 * A.nb;
+    const int xa = blockIdx.x * blockDim.x + threadIdx.x, ya = blockIdx.y;
+    if (xa >= na) return;
+    const long p = (long)ya * na + xa, q = (long)(ya + A.nb) * A.n + (xa + A.nb);
+    typedef typename Promote<float, TG>::type TP;
+    const TG g = np_clip<TG>(gain[q], (TG)1e-4, (TG)1e4);
+    // e_per_slice = skylevel * gain * frame_time, clipped at 0 (:283, 289)
+    TP e = (TP)skylevel[p] * (TP)g * (TP)A.frame_time;
+    e = np_max<TP>(e, (TP)0);
+    const int es_raw = endslice ? (int)endslice[p] : -1;
+    const int es = es_raw > 0 ? es_raw : A.G - 1;
+    Philox rng;
+    rng.init(A.seed, (uint64_t)p, 128u);
+    float cur = 0.0f;
+    float delta[RIP_GMAX];
+#pragma unroll
+    for (int j = 0; j < RIP_GMAX; ++j) delta[j] = 0.0f;
+    const double ed = (double)e;
+    for (int i = 0; i < A.n_samp; ++i) {
+        double s = (double)poisson_draw(rng, ed);  // NaN expectation -> 0 draws; the difference below is NaN as in NumPy
+        s = s - ed;
+        s = s / (double)g;
+        cur = (float)((double)cur + s);
+        const int j = A.group_of_read[i];
+#pragma unroll
+        for (int t = 0; t < RIP_GMAX; ++t)
+            if (t == j) delta[t] = delta[t] + cur / A.n_in_group[t];
+    }
+    float d = diff[p];
+    if (es < RIP_GMAX && A.w_defined[es]) {
+#pragma unroll
+        for (int j = 0; j < RIP_GMAX; ++j)
+            if (j < A.G) d = d + A.w[es][j] * delta[j];
+    }
+    diff[p] = d;
+}
+
+}  // namespace rip
+
+extern "C" int rip_poisson_resample_dev(rip_caldir* h, const float* d_skylevel, const int8_t* d_endslice, int G, int n_samp,
+                                        const int32_t* group_of_read, const float* weights /*[G][G] row es*/,
+                                        const uint8_t* w_defined, double frame_time, uint64_t seed, float* d_diff, void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && d_skylevel && group_of_read && weights && w_defined && d_diff, "rip_poisson_resample_dev: null argument");
+    RIP_REQUIRE(G >= 1 && G <= RIP_GMAX && n_samp >= 1 && n_samp <= 64, "rip_poisson_resample_dev: G=%d / n_samp=%d out of range", G, n_samp);
+    use_device(h->device);
+    PoisArgs A;
+    memset(&A, 0, sizeof A);
+    A.n = h->n; A.nb = h->nb; A.G = G; A.n_samp = n_samp; A.frame_time = (float)frame_time; A.seed = seed;
+    for (int i = 0; i < 64; ++i) A.group_of_read[i] = i < n_samp ? group_of_read[i] : -1;
+    for (int j = 0; j < G; ++j) {
+        int c = 0;
+        for (int i = 0; i < n_samp; ++i) c += group_of_read[i] == j;
+        A.n_in_group[j] = (float)(c > 0 ? c : 1);
+        A.w_defined[j] = w_defined[j];
+        for (int t = 0; t < G; ++t) A.w[j][t] = weights[j * G + t];
+    }
+    dim3 grid((h->na + 127) / 128, h->na);
+    if (h->d.gain_dtype == RIP_F64)
+        RIP_LAUNCH(poisson_resample_kernel<double>, grid, 128, 0, (cudaStream_t)stream, A, d_skylevel, (const double*)h->gain.p, d_endslice, d_diff);
+    else
+        RIP_LAUNCH(poisson_resample_kernel<float>, grid, 128, 0, (cudaStream_t)stream, A, d_skylevel, (const float*)h->gain.p, d_endslice, d_diff);
+    RIP_API_END
+}

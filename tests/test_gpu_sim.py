@@ -421,7 +421,43 @@ def test_noise_layers_against_oracle_composition():
     # 'a': built on the exposure itself -> same noise level
     assert abs(robust_sigma(layers[2][inner]) / sg - 1.0) < 0.25
     with pytest.raises(NotImplementedError):
-        gni.make_noise_cube_arrays(data, amp33, cal, rp, synth.FRAME_TIME, ["Rz4PbrS2C1"], seed=5, config=cfg)
+        gni.make_noise_cube_arrays(data, amp33, cal, rp, synth.FRAME_TIME, ["Rz4OS2C5"], seed=5, config=cfg)
+
+
+def test_noise_layer_poisson_resampling():
+    """Directive 'Pbr' (reference gen_noise_image.py:187-321): re-sampled Poisson noise of the sky level through the
+    ramp-fit weights.  For a full ramp the layer is sum_i' A_i' x_i' with x = (Poisson(e) - e)/gain i.i.d. per sample and
+    A_i' = sum_j w_j/N_j #{i in group j, i >= i'}: zero mean and variance e/gain^2 sum A^2, pixel by pixel."""
+    from romanimpreprocess_b200 import synth
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+    from romanimpreprocess_b200.L1_to_L2 import gen_noise_image as gni
+    from romanimpreprocess_b200.utils import sky
+
+    n = 256
+    rp = synth.README_PATTERN
+    G = len(rp)
+    cal = synth.make_caldir(n=n, read_pattern=rp, p_order=10, seed=31, gain_dtype=np.float32, ipc_dtype=np.float32)
+    c = _trees(cal)
+    data, amp33, _ = synth.make_l1(cal, rp, seed=32, n_sources=0, cr_frac=0.0, bright=0.5, sky=2.0)
+    cfg = {}
+    lay = gni.make_noise_cube_arrays(data, amp33, cal, rp, synth.FRAME_TIME, ["Pbr", "Pbr"], seed=9, config=cfg)
+    assert not np.array_equal(lay[0], lay[1])
+    with gci.CalDir(cal) as cd:
+        out = gci.calibrate_arrays(cd, data, None, rp, synth.FRAME_TIME, None, {"SLICEOUT": True}, do_refpix=False)
+        K = np.asarray(out["meta"]["K"], np.float64)
+    skylevel = sky.medfit(np.ascontiguousarray(out["slope"][4:-4, 4:-4]), order=0)[1]
+    gain = np.clip(c["gain"]["data"][4:-4, 4:-4], 1e-4, 1e4).astype(np.float64)
+    nsamp = rp[-1][-1] + 1
+    A = np.zeros(nsamp)
+    for j, grp in enumerate(rp):
+        for i in grp:
+            A[: i + 1] += K[j] / len(grp)
+    var = np.clip(skylevel.astype(np.float64) * gain * synth.FRAME_TIME, 0, None) / gain**2 * np.sum(A**2)
+    full = out["endslice"] <= 0
+    assert full.mean() > 0.9 and var[full].min() > 0
+    z = np.concatenate([(lay[k] / np.sqrt(var))[full] for k in range(2)])
+    assert abs(z.mean()) < 5 / np.sqrt(z.size) + 0.01, z.mean()
+    assert abs(z.var() - 1.0) < 0.05, z.var()
 
 
 def test_percentiles_device():
