@@ -99,8 +99,9 @@ class NoiseLayers:
         self.have.discard("orig")
         self.have.discard("ref")
 
-    def layer(self, cmd, seed):
-        """One noise layer [na,na] float32 (host) for the directive string ``cmd``."""
+    def layer(self, cmd, seed, out=None):
+        """One noise layer [na,na] float32 (host) for the directive string ``cmd``.  ``out``: a float32 [na,na] host array
+        to receive it (page-locked memory from ``_lib.pinned_empty`` makes the copy run at PCIe speed)."""
         lib, cal, st = _lib.lib(), self.cal, self._stream()
         if "O" in cmd:
             raise NotImplementedError(f"noise directive {cmd!r}: the Pearson draws of 'O' are not generated on the GPU")
@@ -172,6 +173,10 @@ class NoiseLayers:
             sky_order = int("0" + _get_subscript(cmd, "S"))
             sky.medfit_device(self.d_diff.data_ptr(), self.na, self.na, self.na, order=sky_order, device=self.device,
                               stream=st.value or 0, subtract=True)  # fmt: skip
+        if out is not None:
+            self.torch.from_numpy(out).copy_(self.d_diff)
+            self.torch.cuda.synchronize(self.dev)
+            return out
         return self.d_diff.cpu().numpy()
 
     def close(self):

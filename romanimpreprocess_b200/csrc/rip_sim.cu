@@ -12,6 +12,7 @@
 // Random numbers are counter-based Philox (rip_rng.cuh), not GalSim's Boost-MT: everything stochastic is validated
 // statistically against the oracle (tests/test_gpu_sim.py); every deterministic step is checked exactly.
 #include <math.h>
+#include <algorithm>
 #include <stdint.h>
 
 #include "rip_handle.h"
@@ -912,48 +913,81 @@ extern "C" int rip_active_diff_dev(int device, const float* d_a, const float* d_
 // =========================================================================================================
 namespace rip {
 
-// one CTA per requested rank: value of rank r (0-based, ascending, NaNs excluded) by four 8-bit radix passes
-__global__ void __launch_bounds__(1024) order_stat_kernel(const float* __restrict__ arr, long count, const long* __restrict__ ranks,
-                                                          float* __restrict__ out, long* __restrict__ n_valid) {
-    __shared__ uint32_t hist[256];
-    __shared__ uint32_t prefix, mask_s;
-    __shared__ unsigned long long rank_s, cnt_s;
-    if (threadIdx.x == 0) { prefix = 0u; mask_s = 0u; rank_s = (unsigned long long)ranks[blockIdx.x]; cnt_s = 0ull; }
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
-        __syncthreads();
-        const uint32_t m = mask_s, p0 = prefix;
-        for (long e = threadIdx.x; e < count; e += blockDim.x) {
-            const float v = arr[e];
-            if (v != v) continue;
-            const uint32_t k = f2key_sky(v);
-            if ((k & m) == p0) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+// K ranks at once (0-based, ascending, NaNs excluded): four 8-bit radix passes; each pass = one grid-wide histogram
+// kernel (per-CTA shared-memory histograms of the elements matching each rank's prefix, flushed with atomics) and one
+// single-CTA scan that narrows every rank's prefix.  state: [K] prefix, [K] remaining rank (u64 as 2 x u32), count.
+constexpr int OS_KMAX = 16;
+struct OsState {
+    uint32_t prefix[OS_KMAX];
+    unsigned long long rank[OS_KMAX];
+    unsigned long long count;
+    uint32_t mask;
+};
+
+__global__ void __launch_bounds__(256) order_hist_kernel(const float* __restrict__ arr, long count, int K, int pass,
+                                                         const OsState* __restrict__ st, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[OS_KMAX][256];
+    for (int i = threadIdx.x; i < K * 256; i += blockDim.x) (&sh[0][0])[i] = 0u;
+    __syncthreads();
+    const int shift = 24 - 8 * pass;
+    const uint32_t m = st->mask;
+    // identical prefixes share a histogram row (the first of them): fewer atomics when ranks are neighbours
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long)gridDim.x * blockDim.x) {
+        const float v = arr[e];
+        if (v != v) continue;
+        const uint32_t k = f2key_sky(v), bin = (k >> shift) & 255u, kp = k & m;
+        for (int r = 0; r < K; ++r) {
+            const uint32_t pr = st->prefix[r];
+            if (kp != pr) continue;
+            bool dup = false;
+            for (int q = 0; q < r; ++q) dup = dup || (st->prefix[q] == pr);
+            if (!dup) atomicAdd(&sh[r][bin], 1u);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (pass == 0) {
-                unsigned long long c = 0;
-                for (int b = 0; b < 256; ++b) c += hist[b];
-                cnt_s = c;
-                if (rank_s >= c) rank_s = c ? c - 1 : 0;
-            }
-            unsigned long long r = rank_s, acc = 0;
-            int b = 0;
-            for (; b < 255; ++b) {
-                if (acc + hist[b] > r) break;
-                acc += hist[b];
-            }
-            rank_s = r - acc;
-            prefix |= (uint32_t)b << shift;
-            mask_s |= 255u << shift;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * 256; i += blockDim.x) {
+        const uint32_t c = (&sh[0][0])[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+__global__ void order_scan_kernel(int K, int pass, OsState* __restrict__ st, uint32_t* __restrict__ hist, float* __restrict__ out) {
+    const int r = threadIdx.x;
+    __shared__ unsigned long long cnt;
+    const int shift = 24 - 8 * pass;
+    if (pass == 0 && r == 0) {
+        unsigned long long c = 0;
+        for (int b = 0; b < 256; ++b) c += hist[b];
+        cnt = c;
+        st->count = c;
+    }
+    __syncthreads();
+    unsigned long long new_rank = 0;
+    uint32_t new_prefix = 0;
+    if (r < K) {
+        int row = r;  // the histogram row of this rank: the first rank with the same prefix
+        for (int q = r - 1; q >= 0; --q)
+            if (st->prefix[q] == st->prefix[r]) row = q;
+        unsigned long long rk = st->rank[r];
+        if (pass == 0 && rk >= cnt) rk = cnt ? cnt - 1 : 0;
+        unsigned long long acc = 0;
+        int b = 0;
+        for (; b < 255; ++b) {
+            const uint32_t h = hist[row * 256 + b];
+            if (acc + h > rk) break;
+            acc += h;
         }
-        __syncthreads();
+        new_rank = rk - acc;
+        new_prefix = st->prefix[r] | ((uint32_t)b << shift);
     }
-    if (threadIdx.x == 0) {
-        out[blockIdx.x] = cnt_s ? key2f_sky(prefix) : NAN;
-        if (blockIdx.x == 0) n_valid[0] = (long)cnt_s;
+    __syncthreads();  // every thread has read the prefixes / histograms of this pass
+    if (r < K) {
+        st->rank[r] = new_rank;
+        st->prefix[r] = new_prefix;
+        if (pass == 3) out[r] = st->count ? key2f_sky(new_prefix) : NAN;
     }
+    for (int i = threadIdx.x; i < K * 256; i += blockDim.x) hist[i] = 0u;
+    if (r == 0) st->mask |= 255u << shift;
 }
 
 __global__ void clip_kernel(float* __restrict__ a, long count, float lo, float hi) {
@@ -967,18 +1001,28 @@ __global__ void clip_kernel(float* __restrict__ a, long count, float lo, float h
 extern "C" int rip_order_stats_dev(int device, const float* d_arr, long count, int K, const long* ranks, float* out,
                                    long* n_valid, void* stream) {
     RIP_API_BEGIN
-    RIP_REQUIRE(d_arr && ranks && out && K >= 1 && K <= 16 && count >= 1, "rip_order_stats_dev: bad argument");
+    RIP_REQUIRE(d_arr && ranks && out && K >= 1 && K <= OS_KMAX && count >= 1, "rip_order_stats_dev: bad argument");
     use_device(device);
     cudaStream_t st = (cudaStream_t)stream;
-    DevBuf<long> dr(K + 1);
+    OsState hs;
+    memset(&hs, 0, sizeof hs);
+    for (int r = 0; r < K; ++r) hs.rank[r] = (unsigned long long)(ranks[r] < 0 ? 0 : ranks[r]);
+    DevRaw dst;
+    DevBuf<uint32_t> hist((size_t)OS_KMAX * 256);
     DevBuf<float> dout(K);
-    dr.upload(ranks, K, st);
-    RIP_LAUNCH(order_stat_kernel, K, 1024, 0, st, d_arr, count, (const long*)dr.p, dout.p, dr.p + K);
+    dst.upload(&hs, sizeof hs, st);
+    hist.zero(st);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const unsigned nblk = (unsigned)std::min<long>((count + 255) / 256, (long)sms * 8);
+    for (int pass = 0; pass < 4; ++pass) {
+        RIP_LAUNCH(order_hist_kernel, nblk, 256, 0, st, d_arr, count, K, pass, (const OsState*)dst.p, hist.p);
+        RIP_LAUNCH(order_scan_kernel, 1, 32, 0, st, K, pass, (OsState*)dst.p, hist.p, dout.p);
+    }
     dout.download(out, K, st);
-    long nv = 0;
-    RIP_CUDA(cudaMemcpyAsync(&nv, dr.p + K, sizeof(long), cudaMemcpyDeviceToHost, st));
+    RIP_CUDA(cudaMemcpyAsync(&hs, dst.p, sizeof hs, cudaMemcpyDeviceToHost, st));
     RIP_CUDA(cudaStreamSynchronize(st));
-    if (n_valid) *n_valid = nv;
+    if (n_valid) *n_valid = (long)hs.count;
     RIP_API_END
 }
 
