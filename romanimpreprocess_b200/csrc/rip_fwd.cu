@@ -287,6 +287,7 @@ struct FwdArgs {
     double biascorr_t0;
     int has_bias;
     ReadTab rtab[64];           // per-read apportioning constants (by value: kernel parameters live in constant memory)
+    float extrap[64];           // (t_k - t_{k-1}) / (t_{k-1} - t_{k-2}): linear extrapolation of the root from read to read
     const int32_t* counts;      // [na,na] total electrons of the exposure (already Poisson)
     int32_t* cum;               // [n_reads,na,na] cumulative electrons per read (written by the apportioning kernel
                                 //  unless supplied by the caller: tests)
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(FTX * FTY, 3) fwd_ramp_kernel(const FwdArgs A)
         for (int L = 0; L < P; ++L) cd[L] = 0.0;
     }
     const float half = (smax - smin) / 2.0f;  // f32 expression in the reference (ipc_linearity.py:390)
-    double root = 0.0;
+    double root = 0.0, root_pp = 0.0;
     bool have_root = false;
     int k = 0;
     for (int grp = 0; grp < A.G; ++grp) {
@@ -450,8 +451,15 @@ __global__ void __launch_bounds__(FTX * FTY, 3) fwd_ramp_kernel(const FwdArgs A)
                 if (linm > 0.0f) {
                     if (!have_root) {
                         root = cd[1] != 0.0 ? (slin - cd[0]) / cd[1] : 0.0;
+                        root_pp = root;
                         have_root = true;
                     }
+                    // starting guess: the root moves almost linearly in time (constant flux, mild non-linearity), so the
+                    // extrapolation from the last two reads lands within the Poisson noise of the increment and one
+                    // Newton step suffices even for bright pixels
+                    const double guess = root + (root - root_pp) * (double)A.extrap[k];
+                    root_pp = root;
+                    root = guess;
                     z = invlin_fast_z<P>(slin, cd, linA, linm, root, nullptr);
                 } else {  // no monotonicity certificate for this pixel: the plain search
                     z = 0.0;
@@ -590,6 +598,11 @@ static void make_l1_impl(rip_caldir* h, const int32_t* d_counts, const int32_t* 
             const double q = T.flip ? 1.0 - p : p;
             T.q = (float)q; T.omq = 1.0f - T.q; T.l1mq = log1pf(-T.q); T.s = T.q / T.omq;
             t_prev = t;
+            A.extrap[k] = 0.0f;
+            if (k >= 2) {
+                const double t1 = prm->read_time * (double)prm->read_index[k - 1], t2 = prm->read_time * (double)prm->read_index[k - 2];
+                if (t1 > t2 && t > t1) A.extrap[k] = (float)((t - t1) / (t1 - t2));
+            }
         }
     }
     A.counts = d_counts;
