@@ -207,7 +207,7 @@ def _params(cal, meta, config, do_refpix, threads=0, band_rows=0, area=None):
 
 def calibrate_arrays(cal, data, amp33, read_pattern, frame_time, area_factor=None, config=None, do_refpix=True,
                      want_rdq=False, want_lin_cube=False, want_endslice=None, threads=0, band_rows=0, out=None,
-                     dplan=None):  # fmt: skip
+                     dplan=None, sky_step=False):  # fmt: skip
     """
     The numerics of ``calibrateimage`` from L1 arrays to L2 arrays (reference gen_cal_image.py:503-629, 697-709).
 
@@ -232,6 +232,10 @@ def calibrate_arrays(cal, data, amp33, read_pattern, frame_time, area_factor=Non
         device-to-host copies run at full PCIe speed); missing entries are allocated.
     dplan : DevicePlan, optional
         Reuse the pixel-independent plan of a previous call with the same read pattern and configuration.
+    sky_step : bool
+        Also do the step that follows the hot path in ``calibrateimage`` (reference gen_cal_image.py:639-651): keep
+        ``slope_withsky``, and with ``SKYORDER`` in ``config`` fit and subtract the sky model on the active array
+        (``utils.sky.medfit`` on the GPU) -> ``skycoefs``, ``skyorder``.
 
     Returns
     -------
@@ -290,6 +294,18 @@ def calibrate_arrays(cal, data, amp33, read_pattern, frame_time, area_factor=Non
                                      C.byref(plan), _lib.ptr(w_exact), C.byref(o))
     )  # fmt: skip
     out["meta"] = meta
+    if sky_step:
+        from ..utils import sky  # noqa: PLC0415
+
+        nb = cal.nb
+        out["slope_withsky"] = np.copy(out["slope"])  # version before sky subtraction (gen_cal_image.py:640)
+        if "SKYORDER" in config:
+            out["skyorder"] = int(config["SKYORDER"])
+            act = np.ascontiguousarray(out["slope"][nb:-nb, nb:-nb])
+            out["skycoefs"], skymodel = sky.medfit(act, order=out["skyorder"], device=cal.device)
+            out["slope"][nb:-nb, nb:-nb] -= skymodel
+        else:
+            out["skycoefs"], out["skyorder"] = np.array([]).astype(np.float32), -1
     return out
 
 

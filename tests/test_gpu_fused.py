@@ -195,3 +195,31 @@ def test_pipeline_matches_synchronous_path():
         for k in ("pdq", "rdq", "endslice"):
             assert np.array_equal(o[k], r[k]), k
     assert not np.array_equal(outs[0]["slope"], outs[1]["slope"])
+
+
+def test_sky_step_after_the_hot_path():
+    """calibrate_arrays(sky_step=True): slope_withsky + SKYORDER medfit subtraction (reference gen_cal_image.py:639-651)
+    == the oracle's medfit (pinned to the reference's) applied to the oracle's slope, bit for bit."""
+    import warnings
+
+    from romanimpreprocess_b200 import synth
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+
+    n, rp = 256, synth.README_PATTERN
+    cal = synth.make_caldir(n=n, seed=61, read_pattern=rp, p_order=10, gain_dtype=np.float32, ipc_dtype=np.float32,
+                            sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
+    data, amp33, _ = synth.make_l1(cal, rp, seed=62, n_sources=9, cr_frac=0.01)
+    area = synth.make_area_factor(n, np.float32)
+    cfg = {"SKYORDER": 2}
+    with gci.CalDir(cal) as cd:
+        out = gci.calibrate_arrays(cd, data, amp33, rp, synth.FRAME_TIME, area, cfg, do_refpix=True, sky_step=True)
+    c = {k: v["roman"] for k, v in cal.items()}
+    ref = orc.l1_to_l2(data, amp33, c, rp, synth.FRAME_TIME, area, cfg, do_refpix=True)
+    assert np.array_equal(out["slope_withsky"], ref["slope"], equal_nan=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        coef, model, _ = orc.medfit(np.ascontiguousarray(ref["slope"][4:-4, 4:-4]), order=2)
+    expect = ref["slope"].copy()
+    expect[4:-4, 4:-4] -= model
+    assert np.array_equal(out["skycoefs"], coef) and out["skyorder"] == 2
+    assert np.array_equal(out["slope"], expect, equal_nan=True)

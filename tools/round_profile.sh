@@ -9,6 +9,8 @@ python bench.py --groups 16 --no-cpu-baseline > $O/bench_g16_$T.json 2>> $O/benc
 python bench.py --workload forward --steps 5 > $O/bench_forward_$T.json 2>> $O/bench_$T.err; cut -c1-300 $O/bench_forward_$T.json
 python bench.py --workload realizations --realizations 64 > $O/bench_realizations_$T.json 2>> $O/bench_$T.err; cat $O/bench_realizations_$T.json
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference_$T.json 2>> $O/bench_$T.err; cut -c1-300 $O/bench_reference_$T.json
+python bench.py --workload noiselayers --steps 3 > $O/bench_noiselayers_$T.json 2>> $O/bench_$T.err; cut -c1-400 $O/bench_noiselayers_$T.json
+python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_$T.log 2>&1; tail -1 $O/smoke_$T.log
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e"
 $CMD > $O/plain_$T.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$T.csv $CMD > $O/ncu1_$T.log 2>&1
