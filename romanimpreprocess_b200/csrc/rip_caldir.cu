@@ -139,14 +139,19 @@ __global__ void __launch_bounds__(256) k0_hist_kernel(const uint16_t* __restrict
 
 // One warp per row of the reference output: bitonic sort of its 128 values e = f32(amp33) - med (4 per lane, element
 // index i = 32 k + lane) -> the two middle order statistics (ranks 63, 64); plus pass 0 of the global radix select.
+constexpr int K0_ROWS = 32;
 __global__ void __launch_bounds__(256) k0_rows_kernel(const uint16_t* __restrict__ amp33, const float* __restrict__ med, int n,
                                                       float* __restrict__ rowA, float* __restrict__ rowB, SelState* __restrict__ st,
                                                       uint32_t* __restrict__ hist, uint32_t* __restrict__ ticket) {
     __shared__ uint32_t sh[2048];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + w, g = blockIdx.y;
+    const int g = blockIdx.y;
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh[i] = 0u;
     __syncthreads();
+    // K0_ROWS rows per CTA, 8 at a time (one per warp): 4x fewer histogram flushes (2048 global atomics each) than one
+    // pass of 8 rows per CTA
+    for (int it = 0; it < K0_ROWS / 8; ++it) {
+    const int row = blockIdx.x * K0_ROWS + it * 8 + w;
     if (row < n) {
         const uint16_t* a = amp33 + ((long)g * n + row) * 128;
         const float* m = med + (long)row * 128;
@@ -185,6 +190,7 @@ __global__ void __launch_bounds__(256) k0_rows_kernel(const uint16_t* __restrict
         if (lane == 31) rowA[(long)g * n + row] = v[1];  // rank 63 = 32*1 + 31
         if (lane == 0) rowB[(long)g * n + row] = v[2];   // rank 64 = 32*2 + 0
     }
+    }
     k0_flush_and_scan(sh, 1, hist + (long)g * 4096, st + g, ticket + g, gridDim.x, 0, (uint32_t)n * 128u);
 }
 
@@ -204,12 +210,75 @@ __device__ __forceinline__ void bitonic_sort_block(float* v, int npow2) {
     }
 }
 
+// np.median of v[0..count) (shared memory) without sorting: four 8-bit radix passes over order-preserving keys,
+// both middle ranks tracked at once (warp 0 / warp 1 scan their 256-bin histogram with a shuffle prefix sum).
+// Every thread of the CTA calls it (blockDim >= 64); NaN anywhere gives NaN, as NumPy does.  ws: shared uint32[520].
+__device__ float block_median_radix(const float* v, int count, uint32_t* ws) {
+    uint32_t* hist = ws;          // [2][256]
+    uint32_t* st = ws + 512;      // prefix[2], rank[2], mask, nan
+    if (threadIdx.x == 0) {
+        st[0] = st[1] = 0u;
+        st[2] = (uint32_t)((count - 1) / 2);
+        st[3] = (uint32_t)(count / 2);
+        st[4] = 0u;
+        st[5] = 0u;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) hist[i] = 0u;
+        __syncthreads();
+        const uint32_t m = st[4], p0 = st[0], p1 = st[1];
+        for (int i = threadIdx.x; i < count; i += blockDim.x) {
+            const float x = v[i];
+            if (x != x) { st[5] = 1u; continue; }
+            const uint32_t k = f2key(x), b = (k >> shift) & 255u;
+            if ((k & m) == p0) atomicAdd(&hist[b], 1u);
+            if ((k & m) == p1) atomicAdd(&hist[256 + b], 1u);
+        }
+        __syncthreads();
+        if (warp < 2) {
+            const uint32_t* h = hist + 256 * warp;
+            uint32_t c[8], tot = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { c[q] = h[lane * 8 + q]; tot += c[q]; }
+            uint32_t incl = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const uint32_t excl = incl - tot, r = st[2 + warp];
+            const bool mine = (r >= excl) && (r < incl);
+            if (mine) {
+                uint32_t acc = excl;
+                int q = 0;
+                for (; q < 7; ++q) {
+                    if (acc + c[q] > r) break;
+                    acc += c[q];
+                }
+                st[2 + warp] = r - acc;
+                st[warp] |= (uint32_t)(lane * 8 + q) << shift;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) st[4] |= 255u << shift;
+        __syncthreads();
+    }
+    const float a = key2f(st[0]), b = key2f(st[1]);
+    float med = (count & 1) ? a : (a + b) / 2.0f;
+    if (st[5]) med = __int_as_float(0x7fc00000);
+    __syncthreads();  // ws may be reused
+    return med;
+}
+
 // global median, per-row reference medians, their median, and the f64 row correction
 __global__ void k0_final_kernel(const SelState* __restrict__ st, const float* __restrict__ rowA,
                                 const float* __restrict__ rowB, int n, int npow2, double slope,
                                 double* __restrict__ rowcorr, float* __restrict__ gmed_out) {
     extern __shared__ float sv[];
     float* refm = sv + npow2;
+    __shared__ uint32_t ws[520];
     const int g = blockIdx.x;
     const float kA = key2f(st[g].prefix[0]), kB = key2f(st[g].prefix[1]);
     const float gmed = (kA + kB) / 2.0f;
@@ -224,8 +293,7 @@ __global__ void k0_final_kernel(const SelState* __restrict__ st, const float* __
         sv[i] = v;
     }
     __syncthreads();
-    bitonic_sort_block(sv, npow2);
-    const float ctr = (n & 1) ? sv[n / 2] : (sv[n / 2 - 1] + sv[n / 2]) / 2.0f;
+    const float ctr = block_median_radix(refm, n, ws);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float dm = refm[i] - ctr;
         rowcorr[(long)g * n + i] = slope * (double)dm;
@@ -240,6 +308,7 @@ __global__ void k0_chan_kernel(const uint16_t* __restrict__ raw, const float* __
     __shared__ float sv[2][512];
     __shared__ float meds[2];
     __shared__ double line_mc[2];
+    __shared__ uint32_t ws[520];
     const int ch = blockIdx.x, g = blockIdx.y;
     const long npl = (long)n * n;
     for (int side = 0; side < 2; ++side) {
@@ -254,8 +323,8 @@ __global__ void k0_chan_kernel(const uint16_t* __restrict__ raw, const float* __
     }
     __syncthreads();
     for (int side = 0; side < 2; ++side) {
-        bitonic_sort_block(sv[side], 512);
-        if (threadIdx.x == 0) meds[side] = (sv[side][255] + sv[side][256]) / 2.0f;
+        const float md = block_median_radix(sv[side], 512, ws);
+        if (threadIdx.x == 0) meds[side] = md;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -301,7 +370,7 @@ static void run_k0(rip_caldir* h, const uint16_t* d_raw, const uint16_t* d_amp33
         h->chan_c.alloc((size_t)RIP_GMAX * 32);
         h->chan_line.alloc((size_t)RIP_GMAX * 32 * n);
     }
-    RIP_LAUNCH(k0_rows_kernel, dim3((n + 7) / 8, G), 256, 0, st, d_amp33, h->amp_med.p, n, h->rowA.p, h->rowB.p, h->sel.p,
+    RIP_LAUNCH(k0_rows_kernel, dim3((n + K0_ROWS - 1) / K0_ROWS, G), 256, 0, st, d_amp33, h->amp_med.p, n, h->rowA.p, h->rowB.p, h->sel.p,
                h->hist.p, h->k0_ticket.p);
     const int nblk = (int)std::min<long>(64, (M + 4095) / 4096);
     for (int pass = 1; pass < 3; ++pass)
