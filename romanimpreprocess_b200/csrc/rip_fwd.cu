@@ -37,16 +37,23 @@ __device__ __forceinline__ int binomial_draw_tab(Philox& rng, int n, const ReadT
     const float nf = (float)n, qf = T.q, omq = T.omq;
     const float npq = nf * qf;
     int k;
-    // (inversion up to n q = 30 as in NumPy: for small means BTRS's squeeze accepts under half of the candidates and
-    //  every other one pays four float64 logarithms; measured 54 -> see profiles/r01)
-    if (npq < 30.0f) {
-        const float f0 = __expf(nf * T.l1mq), s = T.s;
+    // (inversion up to n q = 64 -- NumPy switches at 30: for small means BTRS's squeeze accepts about half of the candidates
+    //  and every other one pays four float64 logarithms, while an inversion step is 8 float32 instructions; measured on
+    //  B200: threshold 10 -> 54 ms, 30 -> 9.9 ms per 4096^2 x 35 reads on a 300-electron scene)
+    const float lf0 = nf * T.l1mq;  // log of P(X = 0) = (1-q)^n
+    // the float32 recurrence needs P(X = 0) well inside the normal range (__expf flushes denormals to zero, and a zero
+    // start would never terminate): e^-60 = 9e-27
+    if (npq < 64.0f && lf0 > -60.0f) {
+        const float f0 = __expf(lf0), s = T.s;
         const float bound = fminf(nf, npq + 10.0f * sqrtf(npq * omq + 1.0f));
         float x = 0.0f, f = f0, u = rng.uniform();
+        int guard = 0;
         while (u > f) {
             x += 1.0f;
-            if (x > bound) { x = 0.0f; f = f0; u = rng.uniform(); }
-            else { u -= f; f = __fdividef((nf - x + 1.0f) * s * f, x); }
+            if (x > bound) {
+                if (++guard > 64) { x = rintf(npq); break; }  // (unreachable for f0 >= e^-60; a bound on the loop all the same)
+                x = 0.0f; f = f0; u = rng.uniform();
+            } else { u -= f; f = __fdividef((nf - x + 1.0f) * s * f, x); }
         }
         k = (int)x;
     } else {

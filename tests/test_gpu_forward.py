@@ -92,3 +92,27 @@ def test_statistics_against_oracle_ensemble():
     assert abs(lr.std() - np.sqrt(4.0 / (R - 1))) < 0.05, lr.std()
     # analytic check of the first difference in the faint region: Var[R1-R0] ~ read^2 (1/N1 + 1/N0) + shot
     assert vg[0].mean() > 0
+
+
+@pytest.mark.timeout(120)
+def test_apportioning_terminates_in_every_regime():
+    """The float32 inversion sampler must hand over to BTRS before P(X = 0) = (1-q)^n leaves the float32 range (a zero
+    start value never terminates; seen once at n q = 128): sweep the electrons per pixel over five decades so that every
+    read meets n (1-q)^n from 1 down to far below 1e-38, and check the apportioned ramp against its expectation."""
+    from romanimpreprocess_b200 import synth
+    from romanimpreprocess_b200.from_sim import sim_to_isim as s2i
+
+    n, rp = 128, synth.README_PATTERN
+    cal = synth.make_caldir(n=n, seed=3, read_pattern=rp, p_order=10, gain_dtype=np.float32, ipc_dtype=np.float32)
+    na = n - 8
+    counts = np.round(np.logspace(0, 5.3, na * na)).astype(np.int32).reshape(na, na)
+    out, _ = s2i.make_l1_fullcal(counts, rp, cal, seed=11, add_reset_noise=False, add_read_noise=False, add_biascorr=False)
+    assert np.all(np.isfinite(out))
+    # the last group's single read holds all electrons: the signal above the first group grows with the counts
+    gain = cal["gain"]["roman"]["data"][4:-4, 4:-4]
+    lin = (out[-1] - out[0]) * gain
+    big = counts > 2000
+    ratio = lin[big] / counts[big]
+    assert 0.6 < np.median(ratio) < 1.2, np.median(ratio)
+    # intermediate groups sit between the first and the last (cumulative counts are monotone)
+    assert np.all(out[3][big] <= out[-1][big] + 1) and np.all(out[3][big] >= out[0][big] - 1)
