@@ -110,17 +110,39 @@ constexpr int FCOL = 8;
 __device__ __forceinline__ unsigned bitrev(unsigned v, int bits) { return __brev(v) >> (32 - bits); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
-// in-place decimation-in-time radix-2 transforms of FCOL columns of length L (input already bit-reversed)
+// in-place decimation-in-time transforms of FCOL columns of length L (input already bit-reversed).  Two radix-2 stages
+// are done per pass on four elements held in registers (half the shared-memory traffic and barriers of stage-by-stage
+// radix 2); an odd number of stages starts with one plain radix-2 pass.  tw[t] = exp(-2 pi i t / L).
 __device__ void cta_fft(float2* s, const float2* tw, int L) {
-    for (int len = 2; len <= L; len <<= 1) {
-        const int half = len >> 1, tstep = L / len;
+    int len = 2;
+    int logL = 0;
+    while ((1 << logL) < L) ++logL;
+    if (logL & 1) {  // stage len = 2: twiddle 1
         for (int b = threadIdx.x; b < FCOL * (L >> 1); b += blockDim.x) {
             const int col = b / (L >> 1), i = b - col * (L >> 1);
-            const int grp = i / half, k = i - grp * half;
-            float2* a = s + (long)col * L + grp * len + k;
-            const float2 u = a[0], v = cmul(a[half], tw[k * tstep]);
+            float2* a = s + (long)col * L + 2 * i;
+            const float2 u = a[0], v = a[1];
             a[0] = make_float2(u.x + v.x, u.y + v.y);
-            a[half] = make_float2(u.x - v.x, u.y - v.y);
+            a[1] = make_float2(u.x - v.x, u.y - v.y);
+        }
+        __syncthreads();
+        len = 4;
+    }
+    for (; len <= (L >> 1); len <<= 2) {  // stages len and 2 len together
+        const int h = len >> 1, t1 = L / len, t2 = L / (2 * len);
+        for (int b = threadIdx.x; b < FCOL * (L >> 2); b += blockDim.x) {
+            const int col = b / (L >> 2), i = b - col * (L >> 2);
+            const int grp = i / h, k = i - grp * h;
+            float2* a = s + (long)col * L + grp * (2 * len) + k;
+            const float2 w1 = tw[k * t1];
+            float2 a0 = a[0], a1 = cmul(a[h], w1), a2 = a[2 * h], a3 = cmul(a[3 * h], w1);
+            const float2 b0 = make_float2(a0.x + a1.x, a0.y + a1.y), b1 = make_float2(a0.x - a1.x, a0.y - a1.y);
+            const float2 b2 = make_float2(a2.x + a3.x, a2.y + a3.y), b3 = make_float2(a2.x - a3.x, a2.y - a3.y);
+            const float2 c2 = cmul(b2, tw[k * t2]), c3 = cmul(b3, tw[(k + h) * t2]);
+            a[0] = make_float2(b0.x + c2.x, b0.y + c2.y);
+            a[2 * h] = make_float2(b0.x - c2.x, b0.y - c2.y);
+            a[h] = make_float2(b1.x + c3.x, b1.y + c3.y);
+            a[3 * h] = make_float2(b1.x - c3.x, b1.y - c3.y);
         }
         __syncthreads();
     }
