@@ -621,7 +621,7 @@ def main():
     ap.add_argument("--exposures", type=int, default=3, help="distinct resident exposures rotated through the steps")
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--band-rows", type=int, default=0)
-    ap.add_argument("--cpu-tile", type=int, default=1024)
+    ap.add_argument("--cpu-tile", type=int, default=2048, help="side of the sub-frame the cpu_baseline times (2048: about 12 s of oracle work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (for ncu captures)")
     ap.add_argument("--realizations", type=int, default=64, help="noise realisations (workload realizations)")
