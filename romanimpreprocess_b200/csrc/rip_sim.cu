@@ -1093,18 +1093,27 @@ __global__ void poisson_resample_kernel(const PoisArgs A, const float* __restric
 #pragma unroll
     for (int j = 0; j < RIP_GMAX; ++j) delta[j] = 0.0f;
     const double ed = (double)e;
-    // sky-level expectations are a few electrons per sample: multiplication method in float32 with exp(-e) hoisted out of
-    // the sample loop (25 -> 17 ms per layer at 4096^2 against the float64 sampler called per draw); PTRS above 10 electrons
+    // sky-level expectations are a few electrons per sample: float32 inversion with exp(-e) hoisted out of
+    // the sample loop (the float64 sampler called per draw took 25 ms per layer at 4096^2, the multiplication method 17 ms); PTRS above 10 electrons
     const bool small = ed < 10.0;
     const double inv_g = 1.0 / (double)g;
-    const float enlam = small ? __expf(-(float)ed) : 0.0f;
+    const float lamf = (float)ed;
+    const float enlam = small ? __expf(-lamf) : 0.0f;
     for (int i = 0; i < A.n_samp; ++i) {
         double s;
         if (small) {
+            // inversion by sequential search with ONE uniform per draw (the multiplication method spent k+1 Philox
+            // outputs per draw: 12 of 32 lanes active and the ALU pipe 51 % busy in profiles/r01/poisson_resample_*);
+            // the search stops in the far tail once the float32 CDF no longer grows (term < 2^-25, beyond the mode)
             int k = 0;
-            if (ed > 0.0) {
-                float prod = rng.uniform();
-                while (prod > enlam) { ++k; prod *= rng.uniform(); }
+            const float u = rng.uniform();
+            float term = enlam, cdf = enlam;
+            while (u > cdf) {
+                ++k;
+                term *= __fdividef(lamf, (float)k);
+                const float nxt = cdf + term;
+                if (nxt == cdf) break;
+                cdf = nxt;
             }
             s = (double)k;
         } else {
