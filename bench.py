@@ -18,6 +18,7 @@ Multi-GPU: one process per GPU (torchrun), SCAs are independent -> no collective
 """
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -246,6 +247,46 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------------------------
+def copy_ceiling(torch, dist, lib, _lib, local, world, dev, h_in, h_area, h_out, d_raw, d_amp, d_area, d_outs, steps):
+    """Copy-only microbenchmark on the e2e leg's own buffers: per step one exposure's inputs host->device on one stream
+    and one exposure's outputs device->host on another, nothing else; all ranks run it at the same time (barrier before),
+    time = max over ranks.  Returns aggregate GB/s (both directions summed) and the SCA/s it would allow."""
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    o_slope, o_er, o_ep, o_pdq, o_end = d_outs
+    pairs_out = [(h_out["slope"], o_slope), (h_out["err_read"], o_er), (h_out["err_poisson"], o_ep), (h_out["pdq"], o_pdq),
+                 (h_out["endslice"], o_end)]  # fmt: skip
+
+    def one(i):
+        d, a = h_in[i % len(h_in)]
+        for host, devt in ((d, d_raw), (a, d_amp), (h_area, d_area)):
+            _lib.check(lib.rip_copy_h2d(local, C.c_void_p(devt.data_ptr()), _lib.ptr(host), C.c_size_t(host.nbytes),
+                                        C.c_void_p(s_in.cuda_stream)))  # fmt: skip
+        for host, devt in pairs_out:
+            _lib.check(lib.rip_copy_d2h(local, _lib.ptr(host), C.c_void_p(devt.data_ptr()), C.c_size_t(host.nbytes),
+                                        C.c_void_p(s_out.cuda_stream)))  # fmt: skip
+
+    h2d = sum(x.nbytes for x in (h_in[0][0], h_in[0][1], h_area))
+    d2h = sum(h.nbytes for h, _ in pairs_out)
+    for i in range(2):
+        one(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(i)
+    s_in.synchronize()
+    t_in = time.perf_counter() - t0
+    s_out.synchronize()
+    t = time.perf_counter() - t0
+    tt = torch.tensor([t, t_in], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t, t_in = float(tt[0].item()), float(tt[1].item())
+    return {"sca_per_s": world * steps / t, "gbs": world * steps * (h2d + d2h) / t / 1e9,
+            "h2d_gbs": world * steps * h2d / t_in / 1e9, "d2h_gbs": world * steps * d2h / t / 1e9}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -351,6 +392,11 @@ def run_ours(args):
              "err_poisson": _lib.pinned_empty((n, n), np.float32), "pdq": _lib.pinned_empty((n, n), np.uint32),
              "endslice": _lib.pinned_empty((na, na), np.int8)}  # fmt: skip
 
+    # copy-only ceiling of this box for exactly these buffers: the step's H2D bytes on one stream and its D2H bytes on
+    # another, concurrently, no kernels -- what a perfect pipeline could reach (all ranks at once; max over ranks)
+    ceil = copy_ceiling(torch, dist, lib, _lib, local, world, dev, h_in, h_area, h_out, d_raw[0], d_amp[0], d_area,
+                        (o_slope, o_er, o_ep, o_pdq, o_end), steps=max(6, min(args.steps, 20)))
+
     # one set of pinned output buffers per slot in flight
     depth = 3
     h_outs = [h_out] + [{k: _lib.pinned_empty(v.shape, v.dtype) for k, v in h_out.items()} for _ in range(depth - 1)]
@@ -425,6 +471,10 @@ def run_ours(args):
                     "api": f"gen_cal_image.Pipeline.submit/result -> rip_pipeline_* (pinned host buffers, {depth} exposures in "
                            "flight: H2D | kernels | D2H on three streams)",
                     "sync_api_value": e2e_sync,
+                    "ceiling_value": ceil["sca_per_s"], "ceiling_gbs": ceil["gbs"], "ceiling_h2d_gbs": ceil["h2d_gbs"],
+                    "ceiling_d2h_gbs": ceil["d2h_gbs"], "frac_of_ceiling": e2e_value / ceil["sca_per_s"],
+                    "ceiling": "copy-only: the same pinned buffers, H2D and D2H of one step on two streams, all ranks "
+                               "concurrently, no kernels (max over ranks)",
                     "pdq_checksum": checksum},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -225,6 +225,10 @@ int rip_pipeline_submit(rip_pipeline* p, const uint16_t* raw, const uint16_t* am
                         const rip_l1l2_params* prm, const rip_ramp_plan* plan, const double* w_exact,
                         const rip_l2_out* out, long* ticket);
 int rip_pipeline_wait(rip_pipeline* p, long ticket);
+/* Keep one AreaFactor plane (gen_cal_image.py:618-622) resident on the device: exposures submitted with area = NULL
+ * use it instead of "no area division", so a stream of exposures that share the plane uploads it once instead of
+ * 67 MB per exposure.  area = NULL drops the resident plane.  Waits for the exposures in flight. */
+int rip_pipeline_set_area(rip_pipeline* p, const void* area, int area_dtype);
 
 /* Per-launch device timing of the fused kernel (bench.py's roofline): while enabled, every rip_l1_to_l2_* call on
  * this handle brackets the fused kernel with CUDA events on its launch stream; rip_profile_fetch waits for them,

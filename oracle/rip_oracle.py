@@ -24,6 +24,7 @@ DO_NOT_USE = np.uint32(1)
 SATURATED = np.uint32(2)
 JUMP_DET = np.uint32(4)
 AD_FLOOR = np.uint32(64)
+GW_AFFECTED_DATA = np.uint32(16)
 NO_FLAT_FIELD = np.uint32(2**18)
 NO_GAIN_VALUE = np.uint32(2**19)
 NO_LIN_CORR = np.uint32(2**20)
@@ -372,10 +373,27 @@ def get_flat(flat_full, gain_full, ipc_kernel, nborder, pdq, ipc_deconvolve=True
 # ---------------------------------------------------------------------------------------------------------
 
 
-def dq_init(data_u16, mask_dq, exclude_first=True):
-    """romancal do_dqinit as used at gen_cal_image.py:117-143: f32 data, pixeldq = mask dq, groupdq u8."""
+def expand_gw(mask_dq, iterations=1):
+    """do_dqinit(..., expand_gw_flagging=1) (gen_cal_image.py:118): GW_AFFECTED_DATA grown by ``iterations`` pixels
+    (binary dilation with the 4-connected structure).  Restated from upstream, parity unpinned."""
+    out = mask_dq.astype(np.uint32).copy()
+    gw = (out & np.uint32(GW_AFFECTED_DATA)) != 0
+    for _ in range(iterations):
+        g = gw.copy()
+        g[1:, :] |= gw[:-1, :]
+        g[:-1, :] |= gw[1:, :]
+        g[:, 1:] |= gw[:, :-1]
+        g[:, :-1] |= gw[:, 1:]
+        gw = g
+    out[gw] |= np.uint32(GW_AFFECTED_DATA)
+    return out
+
+
+def dq_init(data_u16, mask_dq, exclude_first=True, expand_gw_flagging=1):
+    """romancal do_dqinit as used at gen_cal_image.py:117-143: f32 data, pixeldq = mask dq (GW_AFFECTED_DATA grown by
+    one pixel), groupdq u8."""
     data = data_u16.astype(np.float32)
-    pdq = np.zeros(data.shape[1:], dtype=np.uint32) if mask_dq is None else mask_dq.astype(np.uint32).copy()
+    pdq = np.zeros(data.shape[1:], dtype=np.uint32) if mask_dq is None else expand_gw(mask_dq, expand_gw_flagging)
     rdq = np.zeros(data.shape, dtype=np.uint8)
     if exclude_first:
         rdq[0] |= np.uint8(DO_NOT_USE)
@@ -452,13 +470,35 @@ def make_meta(read_pattern, frame_time):
     return meta
 
 
+def apply_refpix_corrections(data, dark_cube, rowcorr, chan_m, chan_c, row0=0):
+    """The subtractions of the reference-pixel loop (gen_cal_image.py:534-556) with the statistics GIVEN: per group
+    ``image = data - dark``; ``image[i,:] -= rowcorr[i]`` (reference_subtraction.py:122-123, float64 then float32 store);
+    ``image[j, channel] -= m*j + c`` (:64-68, same); ``data = image + dark``.  ``row0`` = detector row of ``data[:, 0]``
+    (lets a row band of the frame be corrected with the statistics of the whole frame)."""
+    G, ny, nx = data.shape
+    jj = np.arange(row0, row0 + ny, dtype=np.float64)
+    nch = nx // CHANNELWIDTH
+    for g in range(G):
+        v = data[g] - dark_cube[g]
+        v = (v - rowcorr[g][:, None]).astype(np.float32)
+        line = chan_m[g, :nch][:, None] * jj[None, :] + chan_c[g, :nch][:, None]  # [nch, rows]
+        v = (v - np.repeat(line.T, CHANNELWIDTH, axis=1)).astype(np.float32)
+        data[g] = v + dark_cube[g]
+    return data
+
+
 def l1_to_l2(data_u16, amp33_u16, cal, read_pattern, frame_time, area_factor, config=None, do_refpix=True,
-             return_intermediates=False):  # fmt: skip
+             return_intermediates=False, refpix_corr=None):  # fmt: skip
     """calibrateimage numerics from L1 arrays to L2 arrays (gen_cal_image.py:503-629,697-709).
 
     ``cal`` maps CALDIR keys to the ``roman`` branches.  Returns a dict with slope, err_read, err_poisson, pdq
     (all full frame [n,n]), rdq [G,n,n] u8, endslice i8 [n-8,n-8], K, and optionally the intermediate cubes.
     ``do_refpix=False`` skips the 4096-only reference-pixel loop (small-frame tests).
+    ``refpix_corr = (rowcorr [G,rows], chan_m [G,32], chan_c [G,32], row0)``: apply these reference-pixel corrections
+    instead of deriving them from the frame -- the frame may then be a ROW BAND (all planes of ``cal`` cut to the same
+    rows, ipc4d / biascorr to the matching active rows): the outer 4 rows act as a fake border whose influence ends 6
+    rows in (saturation growth 1 + IPC order 2), so the interior of a band with a 6-row halo equals the whole-frame
+    result.  tests/fullframe.py tiles a 4096^2 frame this way over a process pool.
     """
     config = config or {}
     nb = 4
@@ -470,7 +510,10 @@ def l1_to_l2(data_u16, amp33_u16, cal, read_pattern, frame_time, area_factor, co
     flag_saturation(data, rdq, pdq, cal["saturation"]["data"], cal["saturation"]["dq"], backup=backup)
     ngrp = data.shape[0]
     inter = {}
-    if do_refpix:
+    if refpix_corr is not None:
+        rowcorr, chan_m, chan_c, row0 = refpix_corr
+        apply_refpix_corrections(data, cal["dark"]["data"], rowcorr, chan_m, chan_c, row0)
+    elif do_refpix:
         refpix_loop(data, amp33_u16, cal["dark"]["data"], cal["read"])
     if return_intermediates:
         inter["refcorr"] = data.copy()
@@ -524,8 +567,7 @@ def l1_to_l2(data_u16, amp33_u16, cal, read_pattern, frame_time, area_factor, co
     err_r /= flat
     err_p /= flat
     # endslice (gen_cal_image.py:697-709)
-    n = slope.shape[0]
-    endslice = np.zeros((n - 2 * nb, n - 2 * nb), dtype=np.int8) - 1
+    endslice = np.zeros(rdq[0, nb:-nb, nb:-nb].shape, dtype=np.int8) - 1
     for iend in range(1, ngrp):
         endslice = np.where(
             rdq[iend, nb:-nb, nb:-nb] & ~rdq[iend - 1, nb:-nb, nb:-nb] & SATURATED != 0, iend - 1, endslice

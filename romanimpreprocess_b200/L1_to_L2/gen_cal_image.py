@@ -367,6 +367,19 @@ class Pipeline:
                                                   int(self.want_rdq), C.byref(self._p)))  # fmt: skip
         self._pending = {}
 
+    def set_area(self, area_factor):
+        """Keep ``area_factor`` (float32 / float64 (n, n), or ``None`` to drop it) resident on the device: exposures
+        submitted with ``area_factor=None`` are divided by it.  For streams of exposures that share the plane (the pixel
+        area in detector coordinates is set by the optical distortion of the SCA): one 67 MB upload instead of one per
+        exposure."""
+        if area_factor is None:
+            _lib.check(_lib.lib().rip_pipeline_set_area(self._p, None, _lib.RIP_F32))
+            return
+        area = _lib.as_float_plane(area_factor)
+        if area.shape != (self.cal.n, self.cal.n):
+            raise ValueError(f"area plane must be ({self.cal.n},{self.cal.n})")
+        _lib.check(_lib.lib().rip_pipeline_set_area(self._p, _lib.ptr(area), _lib.float_tag(area)))
+
     def submit(self, data, amp33, area_factor=None, out=None):
         """Queue one exposure; returns a ticket.  ``out``: optional dict of preallocated (pinned) output arrays."""
         cal, n, G = self.cal, self.cal.n, self.G

@@ -26,7 +26,18 @@ __global__ void static_planes_kernel(int n, int nb, const float* __restrict__ sa
     const uint32_t sd = sat_dq[p];
     if ((sd & DQ_NO_SAT_CHECK) || t != t) t = INFINITY;
     thr_eff[p] = t;
-    const uint32_t ld = lin_dq[p], md = mask_dq ? mask_dq[p] : 0u;
+    const uint32_t ld = lin_dq[p];
+    uint32_t md = mask_dq ? mask_dq[p] : 0u;
+    if (mask_dq) {
+        // do_dqinit(..., expand_gw_flagging=1) (gen_cal_image.py:118): GW_AFFECTED_DATA grown by one pixel before it
+        // enters pixeldq.  Restated from upstream (binary dilation, one iteration, 4-connected structure).
+        uint32_t nbq = 0u;
+        if (y > 0) nbq |= mask_dq[p - n];
+        if (y < n - 1) nbq |= mask_dq[p + n];
+        if (x > 0) nbq |= mask_dq[p - 1];
+        if (x < n - 1) nbq |= mask_dq[p + 1];
+        md |= nbq & DQ_GW_AFFECTED_DATA;
+    }
     uint8_t a = 0;
     if (ld & (DQ_NO_LIN_CORR | DQ_REFERENCE_PIXEL)) a |= 1;
     if ((ld | md) & DQ_REFERENCE_PIXEL) a |= 2;
@@ -491,6 +502,15 @@ extern "C" int rip_caldir_get_static(rip_caldir* h, float* dark_slope_ipc, float
 // =========================================================================================================
 // fused L1 -> L2
 // =========================================================================================================
+// default organisation of the fused kernel (RIP_FUSED_VARIANT overrides, for A/B measurements): see rip_v2.cu
+static int fused_default_variant() {
+    static const int v = [] {
+        const char* e = getenv("RIP_FUSED_VARIANT");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
+
 static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16_t* d_amp33, const void* d_area,
                               const rip_l1l2_params* prm, const rip_ramp_plan* plan, const double* w_exact,
                               const rip_l2_out* o, cudaStream_t st) {
@@ -506,7 +526,9 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
     const double* dw = plan_to_device(h->device, plan, w_exact, st);
     if (prm->do_refpix) run_k0(h, d_raw, d_amp33, G, st);
     // v2 (rip_v2_core.cuh) for the common all-f32 configuration; params.threads > 0 selects the generic v1 tile kernel
-    const bool use_v2 = prm->threads == 0 && h->has_ipc && h->d.gain_dtype == RIP_F32 && h->d.ipc_dtype == RIP_F32 &&
+    // (threads < 0: development selector of the fused-kernel variant, -1 = v2, -2 / -3 = v3 without / with stage b in role X)
+    const int variant = prm->threads < 0 ? -prm->threads - 1 : fused_default_variant();
+    const bool use_v2 = prm->threads <= 0 && h->has_ipc && h->d.gain_dtype == RIP_F32 && h->d.ipc_dtype == RIP_F32 &&
                         h->nb == 4 && n % 8 == 0 && n >= 16 && v2_supported(G, h->P) &&
                         (prm->area_dtype == RIP_F32 || prm->area_dtype == RIP_F64);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -528,7 +550,7 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
         v2::Args V;
         memset(&V, 0, sizeof V);
         V.n = n; V.ntile = v2::ntiles(n);
-        V.band_rows = prm->band_rows > 0 ? prm->band_rows : v2_default_band_rows(h->device, n, G);
+        V.band_rows = prm->band_rows > 0 ? prm->band_rows : v2_default_band_rows(h->device, n, G, (variant == 1 || variant == 2) ? ((G <= 8) ? 3 : 2) : 0);
         V.do_refpix = prm->do_refpix; V.do_not_flag_first = prm->do_not_flag_first; V.exclude_first = prm->exclude_first;
         V.sat_backup = prm->sat_backup; V.area_dtype = prm->area_dtype;
         V.negzero = -0.0f;
@@ -540,7 +562,9 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
         V.slope = o->slope; V.err_read = o->err_read; V.err_poisson = o->err_poisson; V.pdq = o->pdq;
         V.endslice = o->endslice; V.rdq = o->rdq; V.lincube = o->lin_cube;
         if (e0) RIP_CUDA(cudaEventRecord(e0, st));
-        launch_cal_fused_v2(V, G, h->P, st);
+        RIP_REQUIRE(((uintptr_t)d_raw & 15) == 0, "rip_l1_to_l2: the raw cube must be 16-byte aligned");
+        if (variant) launch_cal_fused_v3(V, G, h->P, variant, st);
+        else launch_cal_fused_v2(V, G, h->P, st);
         if (e1) RIP_CUDA(cudaEventRecord(e1, st));
         return;
     }
@@ -678,6 +702,10 @@ struct rip_pipeline {
     };
     std::unique_ptr<Slot[]> slots;
     long next_ticket = 0;
+    // AreaFactor plane kept on the device across exposures (rip_pipeline_set_area): submit(area = NULL) then uses it
+    DevRaw area_res;
+    int area_res_dtype = 0;
+    bool area_res_set = false;
 };
 
 extern "C" int rip_pipeline_create(rip_caldir* h, int G, int depth, int want_endslice, int want_rdq, rip_pipeline** out) {
@@ -727,6 +755,26 @@ extern "C" void rip_pipeline_destroy(rip_pipeline* p) {
     delete p;
 }
 
+extern "C" int rip_pipeline_set_area(rip_pipeline* p, const void* area, int area_dtype) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(p, "rip_pipeline_set_area: null pipeline");
+    rip_caldir* h = p->h;
+    use_device(h->device);
+    // exposures in flight may still read the old plane
+    RIP_CUDA(cudaStreamSynchronize(p->s_run));
+    if (!area) {
+        p->area_res_set = false;
+    } else {
+        RIP_REQUIRE(area_dtype == RIP_F32 || area_dtype == RIP_F64, "rip_pipeline_set_area: area dtype must be f32 or f64");
+        const size_t bytes = (size_t)h->n * h->n * dtype_size(area_dtype);
+        p->area_res.upload(area, bytes, p->s_in);
+        RIP_CUDA(cudaStreamSynchronize(p->s_in));
+        p->area_res_dtype = area_dtype;
+        p->area_res_set = true;
+    }
+    RIP_API_END
+}
+
 extern "C" int rip_pipeline_submit(rip_pipeline* p, const uint16_t* raw, const uint16_t* amp33, const void* area,
                                    const rip_l1l2_params* prm, const rip_ramp_plan* plan, const double* w_exact,
                                    const rip_l2_out* out, long* ticket) {
@@ -750,6 +798,12 @@ extern "C" int rip_pipeline_submit(rip_pipeline* p, const uint16_t* raw, const u
         RIP_CUDA(cudaMemcpyAsync(s.amp.p, amp33, (size_t)G * h->n * 128 * 2, cudaMemcpyHostToDevice, p->s_in));
     }
     if (area) RIP_CUDA(cudaMemcpyAsync(s.area.p, area, npl * dtype_size(prm->area_dtype), cudaMemcpyHostToDevice, p->s_in));
+    const void* d_area = area ? s.area.p : nullptr;
+    rip_l1l2_params prm_local = *prm;
+    if (!area && p->area_res_set) {  // resident plane (rip_pipeline_set_area)
+        d_area = p->area_res.p;
+        prm_local.area_dtype = p->area_res_dtype;
+    }
     RIP_CUDA(cudaEventRecord(s.in_done, p->s_in));
     // compute (one stream: the K0 workspace of the handle is shared by all slots)
     RIP_CUDA(cudaStreamWaitEvent(p->s_run, s.in_done, 0));
@@ -757,7 +811,7 @@ extern "C" int rip_pipeline_submit(rip_pipeline* p, const uint16_t* raw, const u
     o.slope = s.slope.p; o.err_read = s.er.p; o.err_poisson = s.ep.p; o.pdq = s.pdq.p;
     if (out->endslice) o.endslice = s.end.p;
     if (out->rdq) o.rdq = s.rdq.p;
-    l1_to_l2_dev_impl(h, s.raw.p, prm->do_refpix ? s.amp.p : nullptr, area ? s.area.p : nullptr, prm, plan, w_exact, &o, p->s_run);
+    l1_to_l2_dev_impl(h, s.raw.p, prm->do_refpix ? s.amp.p : nullptr, d_area, &prm_local, plan, w_exact, &o, p->s_run);
     RIP_CUDA(cudaEventRecord(s.run_done, p->s_run));
     // D2H
     RIP_CUDA(cudaStreamWaitEvent(p->s_out, s.run_done, 0));

@@ -25,6 +25,7 @@ constexpr uint32_t DQ_DO_NOT_USE = 1u;
 constexpr uint32_t DQ_SATURATED = 2u;
 constexpr uint32_t DQ_JUMP_DET = 4u;
 constexpr uint32_t DQ_AD_FLOOR = 64u;
+constexpr uint32_t DQ_GW_AFFECTED_DATA = 16u;
 constexpr uint32_t DQ_NO_FLAT_FIELD = 1u << 18;
 constexpr uint32_t DQ_NO_GAIN_VALUE = 1u << 19;
 constexpr uint32_t DQ_NO_LIN_CORR = 1u << 20;

@@ -287,7 +287,7 @@ __global__ void fill_refdata_kernel(const FillArgs A, int g) {
     } else {
         Philox r1, r2;
         r1.init(A.seed, (uint64_t)p, 32u + (unsigned)g);
-        r2.init(A.seed, (uint64_t)p, 31u);
+        r2.init(A.seed, (uint64_t)p, 8u);
         float a = r1.normal() * A.read[p];
         a = a / A.inv_rn[g];
         const float b = r2.normal() * A.resetnoise[p];

@@ -4,6 +4,9 @@
 #include "rip_v2_core.cuh"
 
 #include <algorithm>
+#include <mutex>
+#include <set>
+#include <utility>
 
 namespace rip {
 
@@ -62,16 +65,59 @@ __global__ void __launch_bounds__(TW, MINB) cal_fused_v2_kernel(const Args A) {
     }
 }
 
+// v3: role-split CTA (rip_v2_core.cuh, "v3"): 256 threads, X = warps 0-3, Y = warps 4-7, TMA-fed raw ring
+template <int G, int P, bool BX, int MINB, int XR, int YR>
+__global__ void __launch_bounds__(2 * TW, MINB) cal_fused_v3_kernel(const Args A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    v3_body<G, P, BX, XR, YR>(A, c_plan_v2, c_fast_v2, smem_raw);
+}
+
+template <int G, int P, int MINB>
+__global__ void __launch_bounds__(TW, MINB) cal_fused_v2t_kernel(const Args A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    v2t_body<G, P>(A, c_plan_v2, c_fast_v2, smem_raw);
+}
+
+// cudaFuncSetAttribute is per (device, function): remember what has been configured where
+static void configure_once(const void* fn, size_t smem) {
+    static std::mutex mu;
+    static std::set<std::pair<int, const void*>> done;
+    int dev = 0;
+    RIP_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count({dev, fn})) return;
+    RIP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RIP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    done.insert({dev, fn});
+}
+
+template <int G, int P, bool BX>
+static void launch_v3(const Args& A, cudaStream_t st) {
+    constexpr int MINB = (G <= 8) ? 3 : 2;
+    const size_t smem = v3_smem_bytes<G>(BX);
+    // launch allocation 80 (G <= 8: 3 CTAs/SM) or 128 (2 CTAs/SM) registers per thread, re-split between the roles
+    constexpr int XR = BX ? ((G <= 8) ? 72 : 112) : ((G <= 8) ? 64 : 96);
+    constexpr int YR = BX ? ((G <= 8) ? 88 : 144) : ((G <= 8) ? 96 : 160);
+    auto kern = cal_fused_v3_kernel<G, P, BX, MINB, XR, YR>;
+    configure_once((const void*)kern, smem);
+    dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
+    RIP_LAUNCH(kern, grid, 2 * TW, smem, st, A);
+}
+
+template <int G, int P>
+static void launch_v2t(const Args& A, cudaStream_t st) {
+    const size_t smem = Smem<G>::bytes();
+    auto kern = cal_fused_v2t_kernel<G, P, (G <= 8) ? 4 : 2>;
+    configure_once((const void*)kern, smem);
+    dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
+    RIP_LAUNCH(kern, grid, TW, smem, st, A);
+}
+
 template <int G, int P, int MINB>
 static void launch_tb(const Args& A, cudaStream_t st) {
     const size_t smem = Smem<G>::bytes();
     auto kern = cal_fused_v2_kernel<G, P, MINB>;
-    static thread_local bool configured = false;
-    if (!configured) {
-        RIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = true;
-    }
+    configure_once((const void*)kern, smem);
     dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
     RIP_LAUNCH(kern, grid, TW, smem, st, A);
 }
@@ -87,13 +133,13 @@ static void launch_t(const Args& A, cudaStream_t st) {
 // Band height: about 64 rows (measured best on B200: taller bands lose to the wave tail, shorter ones to the 9 halo
 // steps per band), adjusted so that the CTA count ends just under a whole number of waves of resident CTAs
 // (4096^2, 148 SMs x 4: 67 bands of 62 rows = 2345 CTAs = 3.96 waves instead of 64 x 35 = 3.78; profiles/r02).
-int v2_default_band_rows(int device, int n, int G) {
+int v2_default_band_rows(int device, int n, int G, int ctas_per_sm) {
     static thread_local int sms_dev = -1, sms = 0;
     if (sms_dev != device) {
         RIP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
         sms_dev = device;
     }
-    const int slots = sms * ((G <= 8) ? 4 : 3), ntile = v2::ntiles(n);
+    const int slots = sms * (ctas_per_sm > 0 ? ctas_per_sm : ((G <= 8) ? 4 : 3)), ntile = v2::ntiles(n);
     const int nb0 = (n + 63) / 64;
     const int waves = (ntile * nb0 + slots - 1) / slots;
     int nb = waves * slots / ntile;
@@ -105,6 +151,16 @@ int v2_default_band_rows(int device, int n, int G) {
 
 bool v2_supported(int G, int P) {
     return (G == 8 && P == 4) || (G == 8 && P == 11) || (G == 16 && P == 11) || (G == 16 && P == 4);
+}
+
+// variant: 0 = v2 (one role, 128 threads), 1 = v3 (X: a0 a1 | Y: b c), 2 = v3 (X: a0 a1 b | Y: c)
+void launch_cal_fused_v3(const v2::Args& A, int G, int P, int variant, cudaStream_t st) {
+    const bool bx = variant == 2;
+#define RIP_V3(GG, PP) \
+    if (G == GG && P == PP) { if (variant == 3) v2::launch_v2t<GG, PP>(A, st); else if (bx) v2::launch_v3<GG, PP, true>(A, st); else v2::launch_v3<GG, PP, false>(A, st); return; }
+    RIP_V3(8, 11) RIP_V3(8, 4) RIP_V3(16, 11) RIP_V3(16, 4)
+#undef RIP_V3
+    throw Error("cal_fused v3: unsupported (G, P)");
 }
 
 void launch_cal_fused_v2(const v2::Args& A, int G, int P, cudaStream_t st) {

@@ -875,8 +875,15 @@ RIP_HD void stage_b(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const StepC
 }
 
 // stage c : row s-6 (IPC pass 2, /gain; ramp fit, jump flags, DQ propagation; dark, error split, flat/area; stores)
-template <int G, int P>
-RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G>& sm, const Regs<G, P>& R, const StepCtx& C) {
+struct NoHook {
+    RIP_HD void operator()() const {}
+};
+// `reload` runs once per call, after the ramp fit (the register peak of the stage), when the staged record R.kc /
+// R.area* lives on only in a few locals: role Y of v3 issues the loads of the NEXT row there, so that they fly during
+// the epilogue and the wait at the step barrier instead of being consumed right after their issue.
+template <int G, int P, typename Hook = NoHook>
+RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G>& sm, const Regs<G, P>& R, const StepCtx& C,
+                    Hook reload = Hook()) {
     constexpr int H = G / 4;
     const int n = C.n, nb = 4, na = n - 8, tid = C.tid, col = C.col, x = C.x, r0 = C.r0, r1 = C.r1;
     const unsigned (&o5)[5] = C.o5;
@@ -885,13 +892,18 @@ RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, Sme
     const int row = C.s - 6;
     const bool out_col = (tid >= 4 || C.tile == 0) && tid < TW - 4 && C.xin;
     const bool c_on = in_range(row, r0, r1) && out_col;
-    if (!c_on) return;
+    if (!c_on) {
+        reload();
+        return;
+    }
     const unsigned p = R.orow - 6u * (unsigned)n + (unsigned)x;
     const bool active = C.xact && in_range(row, nb, n - nb);
     const uint32_t fl = sm.flg(RIP_O5(-6))[tid];
     const uint32_t nlc = sm.nlc(RIP_O5(-6))[tid];
     const float gval = R.kc[2].y, readv = R.kc[2].z, dsl = R.kc[2].w, flat = R.kc[3].x;
     const uint32_t sdq = f_as_u(R.kc[3].y);
+    const float area32 = R.area32;
+    const double area64 = R.area64;
     f2 q[G / 2];
     if (active) {
         const float k[9] = {R.kc[0].x, R.kc[0].y, R.kc[0].z, R.kc[0].w, R.kc[1].x, R.kc[1].y, R.kc[1].z, R.kc[1].w, R.kc[2].x};
@@ -952,11 +964,12 @@ RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, Sme
         if (gf.sat & allg) pdq2 |= DQ_SATURATED;
         if ((pd & DQ_REFERENCE_PIXEL) == 0u) pd |= pdq2;
     }
+    reload();  // (after the ramp fit, the register peak of the stage; before the epilogue)
     const uint32_t pdq = sdq | ((nlc & 1u) ? DQ_NO_LIN_CORR : 0u) | (pd & ~DQ_REFERENCE_PIXEL);
     float fa = flat;
     if (A.area) {
-        if (A.area_dtype == RIP_F64) fa = (float)((double)fa / R.area64);
-        else fa = fa / R.area32;
+        if (A.area_dtype == RIP_F64) fa = (float)((double)fa / area64);
+        else fa = fa / area32;
     }
     l2_epilogue(r, active, dsl, fa);
     A.slope[p] = r.slope;
@@ -1088,6 +1101,324 @@ template <int G>
 RIP_HD unsigned next_o5(unsigned o5s) { return (o5s == (RING - 1) * Smem<G>::ROW5) ? 0u : o5s + Smem<G>::ROW5; }
 template <int G>
 RIP_HD unsigned first_o5(int r0) { return (unsigned)mod_pos(r0 - 3, RING) * Smem<G>::ROW5; }
+
+// =================================================================================================================
+// v3: the same four stages, ROLE-SPLIT over two warp groups of one CTA and fed by the TMA engine.
+//
+//   * CTA = 256 threads on one 128-column tile.  Warps 0-3 (role X) run a0 + a1 (+ b when BX), warps 4-7 (role Y) run
+//     (b +) c on the SAME columns; the shared-memory rings are the hand-off, one __syncthreads() per march step as in
+//     v2 (every stage still reads only ring slots written in earlier steps).  Each role carries only its own staged
+//     records (X: rec1, Y: recK), so both fit in 80 registers -> 3 CTAs x 8 warps = 24 warps/SM instead of 16, and
+//     each warp's instruction footprint halves.
+//   * The raw resultant rows and the saturation thresholds arrive by 1-D bulk copies (cp.async.bulk = UBLKCP, the TMA
+//     engine) issued by ONE elected thread two rows ahead, completion through an mbarrier per ring slot
+//     (expect_tx / try_wait.parity); the 128 LDGSTS per row of v2 and their address arithmetic are gone.
+//   * Row / channel corrections (24 doubles per row) keep riding a per-thread cp.async group.
+// Device only (the host check walks the v2 `step`, which calls the identical stage functions).
+// =================================================================================================================
+#if defined(__CUDACC__)
+namespace tma {
+__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void expect_tx(uint64_t* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (bytes and both addresses multiples of 16), completion counted on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)),
+                 "l"(src), "r"(bytes), "r"(s32(b))
+                 : "memory");
+}
+__device__ __forceinline__ bool try_wait(uint64_t* b, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(s32(b)), "r"(parity)
+        : "memory");
+    return ok != 0u;
+}
+// (try_wait suspends the thread in hardware for a bounded time; the spin count only guards against a lost copy:
+// a trap is an error the host sees, a silent hang is not)
+__device__ __forceinline__ void wait_parity(uint64_t* b, unsigned parity) {
+    unsigned spins = 0;
+    while (!try_wait(b, parity)) {
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+}  // namespace tma
+
+// shared memory of v3 = the v2 rings | 2 slots of IPC taps for stage b (words 0..2 of recK: 3 x TW float4) |
+// RING + 2 mbarriers ("raw row landed", "taps landed")
+constexpr int TAPS_BYTES = 3 * TW * 16;
+template <int G>
+RIP_HD constexpr size_t v3_off_taps() { return (Smem<G>::bytes() + 127) / 128 * 128; }
+template <int G>
+RIP_HD constexpr size_t v3_off_mbar() { return v3_off_taps<G>() + 2 * TAPS_BYTES; }
+// (with BX only the first tap slot is used: the mbarriers then sit behind it)
+template <int G>
+RIP_HD constexpr size_t v3_smem_bytes(bool bx) { return v3_off_mbar<G>() - (bx ? TAPS_BYTES : 0) + 8 * (RING + 2); }
+template <int G>
+__device__ __forceinline__ uint64_t* v3_mbar(unsigned char* base, bool bx) { return (uint64_t*)(base + v3_off_mbar<G>() - (bx ? TAPS_BYTES : 0)); }
+template <int G>
+__device__ __forceinline__ f4* v3_taps(unsigned char* base, int slot) { return (f4*)(base + v3_off_taps<G>() + (size_t)slot * TAPS_BYTES); }
+
+// Bulk copies of detector row `row` into ring slot (index k5, byte offset slot_o5), issued by the first warp of role X:
+// lane 0 arms the mbarrier, lanes 0 .. G-1 copy one resultant each, lane G the thresholds (one instruction sequence
+// for the warp instead of G + 1 in a single lane).  complete_tx before expect_tx is harmless: the phase cannot
+// complete before the one pending arrival, which carries the expected byte count.
+template <int G>
+__device__ __forceinline__ void tma_row(const Args& A, Smem<G>& sm, uint64_t* mbar, int row, int k5, unsigned slot_o5, int tile, int lo,
+                                        int hi, int lane) {
+    if (!in_range(row, imax(lo, 0), imin(hi, A.n))) return;
+    const int x0 = tile * TS;
+    const unsigned ncol = (unsigned)imin(TW, A.n - x0);  // multiple of 8 (n % 8 == 0, TS % 8 == 0)
+    const size_t npl = (size_t)A.n * (size_t)A.n, o = (size_t)row * (size_t)A.n + (size_t)x0;
+    uint64_t* b = mbar + k5;
+    if (lane == 0) tma::expect_tx(b, (unsigned)G * ncol * 2u + ncol * 4u);
+    if (lane < G) tma::bulk_g2s(sm.raw(slot_o5) + lane * TW, A.raw + (size_t)lane * npl + o, ncol * 2u, b);
+    else if (lane == G) tma::bulk_g2s(sm.thr(slot_o5), A.thr + o, ncol * 4u, b);
+}
+
+// row / channel corrections of `row` (threads 0 .. 3G-1 of role X, 8 bytes each), one cp.async group per step
+template <int G>
+__device__ __forceinline__ void corr_async(const Args& A, Smem<G>& sm, int row, unsigned slot_o5, int tile, int tid, int lo, int hi) {
+    if (A.do_refpix && tid < 3 * G && in_range(row, imax(lo, 0), imin(hi, A.n))) {
+        const int g = tid % G, which = tid / G;
+        if (which == 0) {
+            cp_async<8>(sm.rc(slot_o5) + g, A.rowcorr + ((unsigned)(g * A.n) + (unsigned)row));
+        } else {
+            int ch = ((tile * TS) >> 7) + (which - 1);
+            if (ch > 31) ch = 31;
+            cp_async<8>(sm.ln(slot_o5) + (which - 1) * G + g, A.chan_line + ((unsigned)((g * 32 + ch) * A.n) + (unsigned)row));
+        }
+    }
+    cp_async_commit();
+}
+
+__device__ __forceinline__ void make_ctx(StepCtx& C, const Args& A, int tid, int tile, int r0, int r1, int s, unsigned o5s, unsigned RB,
+                                         unsigned RING_B) {
+    C.n = A.n; C.tid = tid; C.tile = tile; C.r0 = r0; C.r1 = r1; C.s = s;
+    C.x = tile * TS + tid;
+    C.col = tid + 1;
+    C.xin = C.x < A.n;
+    C.xact = in_range(C.x, 4, A.n - 4);
+    C.o5[0] = o5s; C.o5[1] = wrap5(o5s + RB, RING_B); C.o5[2] = wrap5(o5s + 2 * RB, RING_B);
+    C.o5[3] = wrap5(o5s + 3 * RB, RING_B); C.o5[4] = wrap5(o5s + 4 * RB, RING_B);
+}
+
+// rows for which stage b runs (IPC pass 1): the taps of exactly these rows are copied
+template <int G>
+__device__ __forceinline__ bool v3_b_row(int row, int r0, int r1, int n) { return in_range(row, imax(r0 - 1, 4), imin(r1 + 1, n - 4)); }
+// taps of stage b (words 0..2 of the recK record of `row`) -> tap slot `slot`, by one thread
+template <int G>
+__device__ __forceinline__ void tma_taps(const Args& A, unsigned char* smem_raw, uint64_t* mbar, int row, int slot, int tile, int r0, int r1) {
+    if (!v3_b_row<G>(row, r0, r1, A.n)) return;
+    uint64_t* b = mbar + RING + slot;
+    tma::expect_tx(b, (unsigned)TAPS_BYTES);
+    tma::bulk_g2s(v3_taps<G>(smem_raw, slot), A.recK + ((long)row * A.ntile + tile) * (KQ * TW), (unsigned)TAPS_BYTES, b);
+}
+
+// v2 with the TMA-fed raw ring ("v2t"): one role, 128 threads, the march step of v2 -- only the raw rows and thresholds
+// arrive by bulk copies (lanes of warp 0) instead of one LDGSTS pair per thread.
+template <int G, int P>
+__device__ __forceinline__ void v2t_body(const Args& A, const RampPlanDev& pl, const FastTab& ft, unsigned char* smem_raw) {
+    constexpr unsigned RB = Smem<G>::ROW5, RING_B = RING * Smem<G>::ROW5;
+    Smem<G> sm;
+    sm.carve(smem_raw);
+    uint64_t* mbar = (uint64_t*)(smem_raw + (size_t)RING * Smem<G>::ROW5 + (size_t)O_DEPTH * Smem<G>::ROW4);  // the 64 spare bytes of Smem::bytes()
+    static_assert(8 * RING <= 64, "mbarriers must fit behind the rings");
+    Regs<G, P> R;
+    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int r0 = blockIdx.y * A.band_rows;
+    const int r1 = imin(r0 + A.band_rows, A.n);
+    const int x = tile * TS + tid;
+    const bool xin = x < A.n;
+    const int s0 = r0 - 3;
+    unsigned o5s = first_o5<G>(r0);
+    int k5 = mod_pos(s0, RING);
+    unsigned nwait = 0;
+    R.orow = (unsigned)(s0 * A.n);
+    if (tid == 0) {
+        for (int k = 0; k < RING; ++k) tma::mbar_init(mbar + k, 1u);
+        tma::fence_mbar_init();
+    }
+    for (int k = 0; k < RING; ++k)
+        for (int i = tid; i < Smem<G>::H * RW; i += TW) sm.D((unsigned)k * RB)[i] = f4{0.f, 0.f, 0.f, 0.f};
+    for (int i = tid; i < O_DEPTH * Smem<G>::ROW4 / 16; i += TW) ((f4*)sm.r4)[i] = f4{0.f, 0.f, 0.f, 0.f};
+    __syncthreads();
+    if (tid < 32) {
+        tma_row<G>(A, sm, mbar, s0, k5, o5s, tile, r0 - 3, r1 + 3, tid);
+        tma_row<G>(A, sm, mbar, s0 + 1, (k5 + 1) % RING, wrap5(o5s + RB, RING_B), tile, r0 - 3, r1 + 3, tid);
+    }
+    corr_async<G>(A, sm, s0, o5s, tile, tid, r0 - 3, r1 + 3);
+    corr_async<G>(A, sm, s0 + 1, wrap5(o5s + RB, RING_B), tile, tid, r0 - 3, r1 + 3);
+    load_c<G, P>(A, R, s0 - 6, tile, tid, x, xin);
+    load_a1<G, P>(A, R, s0 - 2, tile, tid);
+    load_bn<G, P>(A, R, s0 - 4, tile, tid, 0u);
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int s = s0; s <= r1 + 5; ++s) {
+        StepCtx C;
+        make_ctx(C, A, tid, tile, r0, r1, s, o5s, RB, RING_B);
+        const unsigned (&o5)[5] = C.o5;
+        const unsigned dep = f_as_u(R.kc[0].x) & (unsigned)A.pad_;
+        R.kb[0] = R.kbn[0]; R.kb[1] = R.kbn[1]; R.kb8 = R.kbn8;
+        if (tid < 32) tma_row<G>(A, sm, mbar, s + 2, (k5 + 2) % RING, RIP_O5(2), tile, r0 - 3, r1 + 3, tid);
+        corr_async<G>(A, sm, s + 2, RIP_O5(2), tile, tid, r0 - 3, r1 + 3);
+        load_bn<G, P>(A, R, s - 3, tile, tid, dep);
+        stage_a1<G, P>(A, sm, R, C);
+        stage_c<G, P>(A, pl, ft, sm, R, C);
+        load_c<G, P>(A, R, s - 5, tile, tid, C.x, C.xin);
+        load_a1<G, P>(A, R, s - 1, tile, tid);
+        stage_b<G, P>(A, sm, R, C);
+        if (in_range(s, imax(r0 - 3, 0), imin(r1 + 3, A.n))) {
+            tma::wait_parity(mbar + k5, (nwait / RING) & 1u);
+            ++nwait;
+        }
+        stage_a0<G, P>(A, sm, C);
+        R.orow += (unsigned)A.n;
+        cp_async_wait<1>();
+        o5s = next_o5<G>(o5s);
+        k5 = (k5 == RING - 1) ? 0 : k5 + 1;
+        __syncthreads();
+    }
+}
+
+// role X: a0 (row s), a1 (row s-2) and, with BX, b (row s-4).  With BX the taps of stage b arrive in ONE slot, copied
+// at the top of the step that uses them (stage a1 runs in between: about a third of a step).
+template <int G, int P, bool BX>
+__device__ __forceinline__ void v3_role_x(const Args& A, Smem<G>& sm, unsigned char* smem_raw, uint64_t* mbar, const int tid, const int tile,
+                                          const int r0, const int r1) {
+    constexpr unsigned RB = Smem<G>::ROW5, RING_B = RING * Smem<G>::ROW5;
+    Regs<G, P> R;
+    const int s0 = r0 - 3;
+    unsigned o5s = first_o5<G>(r0);
+    int k5 = mod_pos(s0, RING);  // ring slot index of row s
+    unsigned nwait = 0;          // rows of this band waited for so far (they arrive in row order, slot after slot)
+    unsigned nb_wait = 0;        // stage-b rows waited for so far
+    load_a1<G, P>(A, R, s0 - 2, tile, tid);
+    if (tid < 32) {
+        tma_row<G>(A, sm, mbar, s0, k5, o5s, tile, r0 - 3, r1 + 3, tid);
+        tma_row<G>(A, sm, mbar, s0 + 1, (k5 + 1) % RING, wrap5(o5s + RB, RING_B), tile, r0 - 3, r1 + 3, tid);
+    }
+    corr_async<G>(A, sm, s0, o5s, tile, tid, r0 - 3, r1 + 3);
+    corr_async<G>(A, sm, s0 + 1, wrap5(o5s + RB, RING_B), tile, tid, r0 - 3, r1 + 3);
+    cp_async_wait<0>();
+    __syncthreads();  // (pairs with the prologue barrier of role Y)
+    for (int s = s0; s <= r1 + 5; ++s) {
+        StepCtx C;
+        make_ctx(C, A, tid, tile, r0, r1, s, o5s, RB, RING_B);
+        const unsigned (&o5)[5] = C.o5;
+        if (tid < 32) {
+            tma_row<G>(A, sm, mbar, s + 2, (k5 + 2) % RING, RIP_O5(2), tile, r0 - 3, r1 + 3, tid);
+            if (BX && tid == G + 1) tma_taps<G>(A, smem_raw, mbar, s - 4, 0, tile, r0, r1);
+        }
+        corr_async<G>(A, sm, s + 2, RIP_O5(2), tile, tid, r0 - 3, r1 + 3);
+        stage_a1<G, P>(A, sm, R, C);
+        load_a1<G, P>(A, R, s - 1, tile, tid);
+        if (BX) {
+            if (v3_b_row<G>(s - 4, r0, r1, A.n)) {
+                tma::wait_parity(mbar + RING, nb_wait & 1u);
+                ++nb_wait;
+                const f4* kt = v3_taps<G>(smem_raw, 0);
+                R.kb[0] = kt[tid]; R.kb[1] = kt[TW + tid]; R.kb8 = ((const float*)(kt + 2 * TW))[4 * tid];
+            }
+            stage_b<G, P>(A, sm, R, C);
+        }
+        if (in_range(s, imax(r0 - 3, 0), imin(r1 + 3, A.n))) {  // row s has a copy in flight (or landed): same predicate as tma_row
+            tma::wait_parity(mbar + k5, (nwait / RING) & 1u);
+            ++nwait;
+        }
+        stage_a0<G, P>(A, sm, C);
+        cp_async_wait<1>();
+        o5s = next_o5<G>(o5s);
+        k5 = (k5 == RING - 1) ? 0 : k5 + 1;
+        __syncthreads();
+    }
+}
+
+// role Y: c (row s-6) and, without BX, b (row s-4; taps double-buffered in shared memory, copied one step ahead by the
+// role's first thread).  The record of stage c is re-loaded for the next row from INSIDE stage c, right after its last
+// use (see stage_c): the loads have two thirds of a step to land instead of the few instructions before the barrier.
+template <int G, int P>
+struct ReloadC {
+    const Args& A;
+    Regs<G, P>& R;
+    int row, tile, tid, x;
+    bool xin;
+    __device__ __forceinline__ void operator()() const { load_c<G, P>(A, R, row, tile, tid, x, xin); }
+};
+template <int G, int P, bool BX>
+__device__ __forceinline__ void v3_role_y(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G>& sm, unsigned char* smem_raw,
+                                          uint64_t* mbar, const int tid, const int tile, const int r0, const int r1) {
+    constexpr unsigned RB = Smem<G>::ROW5, RING_B = RING * Smem<G>::ROW5;
+    Regs<G, P> R;
+    const int s0 = r0 - 3;
+    const int x = tile * TS + tid;
+    const bool xin = x < A.n;
+    unsigned o5s = first_o5<G>(r0);
+    unsigned nb_wait = 0;  // stage-b rows waited for so far (consecutive rows alternate between the two tap slots)
+    R.orow = (unsigned)(s0 * A.n);
+    load_c<G, P>(A, R, s0 - 6, tile, tid, x, xin);
+    if (!BX && tid == 0) tma_taps<G>(A, smem_raw, mbar, s0 - 4, (s0 - 4) & 1, tile, r0, r1);
+    __syncthreads();
+    for (int s = s0; s <= r1 + 5; ++s) {
+        StepCtx C;
+        make_ctx(C, A, tid, tile, r0, r1, s, o5s, RB, RING_B);
+        if (!BX && tid == 0) tma_taps<G>(A, smem_raw, mbar, s - 3, (s - 3) & 1, tile, r0, r1);  // next step's row
+        stage_c<G, P>(A, pl, ft, sm, R, C, ReloadC<G, P>{A, R, s - 5, tile, tid, C.x, C.xin});
+        if (!BX) {
+            if (v3_b_row<G>(s - 4, r0, r1, A.n)) {
+                tma::wait_parity(mbar + RING + ((s - 4) & 1), (nb_wait >> 1) & 1u);
+                ++nb_wait;
+                const f4* kt = v3_taps<G>(smem_raw, (s - 4) & 1);
+                R.kb[0] = kt[tid]; R.kb[1] = kt[TW + tid]; R.kb8 = ((const float*)(kt + 2 * TW))[4 * tid];
+            }
+            stage_b<G, P>(A, sm, R, C);
+        }
+        R.orow += (unsigned)A.n;
+        o5s = next_o5<G>(o5s);
+        __syncthreads();
+    }
+}
+
+// XR / YR: register budgets of the two roles (setmaxnreg; XR + YR <= 2 x the launch allocation), 0 = leave alone
+template <int G, int P, bool BX, int XR, int YR>
+__device__ __forceinline__ void v3_body(const Args& A, const RampPlanDev& pl, const FastTab& ft, unsigned char* smem_raw) {
+    Smem<G> sm;
+    sm.carve(smem_raw);
+    uint64_t* mbar = v3_mbar<G>(smem_raw, BX);
+    const int t = threadIdx.x, tile = blockIdx.x;
+    const int r0 = blockIdx.y * A.band_rows;
+    const int r1 = imin(r0 + A.band_rows, A.n);
+    constexpr unsigned RB = Smem<G>::ROW5;
+    // ring pads and the slots stage a1 / b read before anything was written there (never the bulk-copy targets)
+    for (int k = 0; k < RING; ++k)
+        for (int i = t; i < Smem<G>::H * RW; i += 2 * TW) sm.D((unsigned)k * RB)[i] = f4{0.f, 0.f, 0.f, 0.f};
+    for (int i = t; i < O_DEPTH * Smem<G>::ROW4 / 16; i += 2 * TW) ((f4*)sm.r4)[i] = f4{0.f, 0.f, 0.f, 0.f};
+    if (t == 0) {
+        for (int k = 0; k < RING + 2; ++k) tma::mbar_init(mbar + k, 1u);
+        tma::fence_mbar_init();
+    }
+    __syncthreads();
+    if (t < TW) {
+        if (XR > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(XR));
+        v3_role_x<G, P, BX>(A, sm, smem_raw, mbar, t, tile, r0, r1);
+    } else {
+        if (YR > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(YR));
+        v3_role_y<G, P, BX>(A, pl, ft, sm, smem_raw, mbar, t - TW, tile, r0, r1);
+    }
+}
+#endif  // __CUDACC__
 
 // ---- packed calibration records (built once per CALDIR and group count) -------------------------------------
 struct PackSrc {

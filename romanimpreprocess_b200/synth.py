@@ -193,6 +193,14 @@ def make_caldir(
         gain[yy[5 * k : 6 * k], xx[5 * k : 6 * k]] = 0.05
         dark_dq[yy[6 * k : 7 * k], xx[6 * k : 7 * k]] |= pixel.UNRELIABLE_DARK
         lin_dq[yy[7 * k :], xx[7 * k :]] |= pixel.NONLINEAR
+        # guide-window pixels in the mask (do_dqinit grows them by one pixel): a block, scattered pixels, frame corners
+        grng = np.random.RandomState(seed=seed + 7919)
+        mdq = cal["mask"]["roman"]["dq"]
+        gy, gx = grng.randint(0, n, size=max(n * n // 2000, 4)), grng.randint(0, n, size=max(n * n // 2000, 4))
+        mdq[gy, gx] |= pixel.GW_AFFECTED_DATA
+        mdq[n // 3 : n // 3 + 5, n // 2 : n // 2 + 7] |= pixel.GW_AFFECTED_DATA
+        mdq[0, 0] |= pixel.GW_AFFECTED_DATA
+        mdq[n - 1, n - 1] |= pixel.GW_AFFECTED_DATA
 
     return cal
 

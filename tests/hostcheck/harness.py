@@ -84,7 +84,7 @@ def static_products(c, nb=4):
     thr = c["saturation"]["data"].astype(np.float32).copy()
     thr[((sat_dq & orc.NO_SAT_CHECK) != 0) | np.isnan(thr)] = np.inf
     ld = lin["dq"]
-    md = c["mask"]["dq"] if "mask" in c else np.zeros((n, n), np.uint32)
+    md = orc.expand_gw(c["mask"]["dq"]) if "mask" in c else np.zeros((n, n), np.uint32)  # (do_dqinit, expand_gw_flagging=1)
     aux = np.zeros((n, n), np.uint8)
     aux |= np.where(ld & (orc.NO_LIN_CORR | orc.REFERENCE_PIXEL) != 0, 1, 0).astype(np.uint8)
     aux |= np.where((ld | md) & orc.REFERENCE_PIXEL != 0, 2, 0).astype(np.uint8)

@@ -164,6 +164,66 @@ def test_full_size_band_and_tiling_invariance(full_case):
     band_check(out, cal, data_u16, amp33_u16, rp, area, sp["flat"], sp["dark_slope_ipc"])
 
 
+def _compare_full(out, ref, tag):
+    stats = {}
+    for k in ("slope", "err_read", "err_poisson"):
+        stats[k] = assert_float_close(out[k], ref[k], f"{tag} {k}")
+    for k in ("pdq", "rdq", "endslice"):
+        assert_bits_equal(out[k], ref[k], f"{tag} {k}")
+    return stats
+
+
+def test_full_frame_every_pixel(full_case):
+    """BASELINE metric configuration (4096^2 x 8 resultants, P = 11, reference-pixel correction on): EVERY pixel of the
+    CUDA result against ``oracle.l1_to_l2`` of the whole frame (row bands in a process pool with the global K0
+    statistics: tests/fullframe.py).  DQ / rdq / endslice bit-exact, floats rtol 1e-5 (the reference's own "same answer"
+    bar is <= 2 differing pixels, tests/romanimpreprocess/test_workflow.py:870-874; ours must be 0)."""
+    import fullframe
+
+    cal, data_u16, amp33_u16, rp, area = full_case
+    cfg = dict(CFG7)
+    ref = fullframe.oracle_full_frame(cal, data_u16, amp33_u16, rp, area, cfg)
+    out = _run(cal, data_u16, amp33_u16, rp, area, cfg, True)
+    stats = _compare_full(out, ref, "4096^2 x 8")
+    print("4096^2 x 8, values not bit-identical:", stats)
+    assert np.count_nonzero(ref["pdq"] & orc.SATURATED) > 1000 and np.count_nonzero(ref["pdq"] & orc.JUMP_DET) > 5000
+    assert np.count_nonzero(ref["pdq"] & orc.GW_AFFECTED_DATA) > np.count_nonzero(cal["mask"]["roman"]["dq"] & orc.GW_AFFECTED_DATA)
+
+
+def test_full_frame_dummy_caldir_dtypes():
+    """The dtypes of the production DUMMY CALDIR (reference runs/summer2025run/make_gain_file.py:88,138,194): gain
+    float32, ipc4d FLOAT64 (the reference then runs its IPC stage in float64), at 4096^2 x 8, every pixel."""
+    import fullframe
+    from romanimpreprocess_b200 import synth
+
+    rp = synth.README_PATTERN
+    cal = synth.make_caldir(n=4096, seed=1010, read_pattern=rp, p_order=10, gain_dtype=np.float32,
+                            ipc_dtype=np.float64, sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
+    data_u16, amp33_u16, _ = synth.make_l1(cal, rp, seed=210, n_sources=25, cr_frac=1e-3, bright=3.0)
+    area = synth.make_area_factor(4096, np.float64)
+    cfg = dict(CFG7)
+    ref = fullframe.oracle_full_frame(cal, data_u16, amp33_u16, rp, area, cfg)
+    out = _run(cal, data_u16, amp33_u16, rp, area, cfg, True)
+    print("4096^2 x 8 (ipc4d f64), values not bit-identical:", _compare_full(out, ref, "ipc4d f64"))
+
+
+def test_long_table_1024_with_refpix():
+    """BASELINE configs[2]: the 16-resultant table, reference-pixel correction on, at 1024^2 (whole-frame oracle)."""
+    import fullframe
+    from romanimpreprocess_b200 import synth
+
+    rp = synth.LONG16_PATTERN
+    cal = synth.make_caldir(n=1024, seed=1020, read_pattern=rp, p_order=10, gain_dtype=np.float32,
+                            ipc_dtype=np.float32, sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
+    data_u16, amp33_u16, _ = synth.make_l1(cal, rp, seed=220, n_sources=25, cr_frac=2e-3, bright=4.0)
+    area = synth.make_area_factor(1024, np.float32)
+    cfg = {"SLICEOUT": True, "SATURATION_BACKUP": 2}
+    ref = fullframe.oracle_full_frame(cal, data_u16, amp33_u16, rp, area, cfg, band=128)
+    out = _run(cal, data_u16, amp33_u16, rp, area, cfg, True)
+    print("1024^2 x 16, values not bit-identical:", _compare_full(out, ref, "long table"))
+    assert len(np.unique(ref["endslice"])) >= 6
+
+
 def test_pipeline_matches_synchronous_path():
     """rip_pipeline_* (three streams, exposures in flight) gives the same arrays as rip_l1_to_l2_host, in order, also
     when more exposures are queued than there are slots."""

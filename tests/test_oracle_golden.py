@@ -276,3 +276,25 @@ def test_sky_medfit_golden():
         assert np.array_equal(meds, g[f"{tag}_meds"], equal_nan=True)
         assert np.array_equal(model[::7, ::5], g[f"{tag}_model_sub"])
         assert model.astype(np.float64).sum() == float(g[f"{tag}_model_sum"])
+
+
+def test_band_tiled_oracle_equals_whole_frame():
+    """tests/fullframe.py (the whole-frame checker of the 4096^2 GPU parity tests): oracle.l1_to_l2 run band by band
+    with the global reference-pixel statistics == oracle.l1_to_l2 of the whole frame, bit for bit (256^2, all flag
+    branches, guide-window growth across band edges)."""
+    import fullframe
+    from romanimpreprocess_b200 import synth
+
+    rp = synth.README_PATTERN
+    n = 256
+    cal = synth.make_caldir(n=n, seed=5, read_pattern=rp, p_order=10, gain_dtype=np.float32, ipc_dtype=np.float32,
+                            sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
+    data, amp33, _ = synth.make_l1(cal, rp, seed=6, n_sources=25, cr_frac=0.01, bright=3.0)
+    area = synth.make_area_factor(n, np.float64)
+    cfg = {"RAMP_OPT_PARS": {"slope": 0.4, "gain": 1.8, "sigma_read": 7.0}, "SLICEOUT": True}
+    c = {k: v["roman"] for k, v in cal.items()}
+    ref = orc.l1_to_l2(data, amp33, c, rp, 3.04, area, cfg, do_refpix=True)
+    tiled = fullframe.oracle_full_frame(cal, data, amp33, rp, area, cfg, band=48, workers=2)
+    for k in ("slope", "err_read", "err_poisson", "pdq", "rdq", "endslice"):
+        assert np.array_equal(ref[k], tiled[k], equal_nan=True), k
+    assert np.count_nonzero(ref["pdq"] & orc.GW_AFFECTED_DATA) > np.count_nonzero(c["mask"]["dq"] & orc.GW_AFFECTED_DATA)
