@@ -334,6 +334,18 @@ int rip_realization_record_dev(int device, const uint16_t* d_im, int G, int n, i
  * (coef, LPX [order+1,nx], LPY [order+1,ny]: host float64); written to d_model (or NULL) and/or subtracted in place
  * from d_arr (row pitch in elements; or NULL). */
 int rip_block_nanmedian_dev(int device, const float* d_arr, long pitch, int ny, int nx, int N, float* d_meds, void* stream);
+/* The pixel-independent part of medfit (utils/sky.py:137-175), host float64: from meds f32 [N,N] (NaN = region without
+ * a finite median) the (order+1)(order+2)/2 coefficients in the reference's ordering, and (if not NULL) the Legendre
+ * polynomials on the pixel grid LPX [order+1,nx], LPY [order+1,ny] for rip_medfit_eval_dev.  Legendre values follow
+ * scipy.special.legendre_p bit for bit; the normal equations are accumulated in the reference's order and solved by LU
+ * with partial pivoting (LAPACK's result agrees to a few ulp of float64: the order of its updates is not defined). */
+int rip_medfit_solve(int ny, int nx, int N, int order, const float* meds, double* coef, double* LPX, double* LPY);
+/* smooth_mode (utils/sky.py:46-93) as called at gen_cal_image.py:641: rip_bin_masked_dev = binkxk(where(~mask, arr,
+ * nan), k) on device planes (mask u8 [ny,nx] or NULL; out f32 [ny/k, nx/k]); rip_gauss_hist_dev = the smoothed
+ * histogram sums[j] = sum_i exp(-0.5 ((z[j] - a_i) / width)^2) over the non-NaN elements, float64, nz <= 32. */
+int rip_bin_masked_dev(int device, const float* d_arr, const uint8_t* d_mask, int ny, int nx, int k, float* d_out, void* stream);
+int rip_gauss_hist_dev(int device, const float* d_arr, long count, const double* z, int nz, double width, double* sums,
+                       void* stream);
 int rip_medfit_host(int device, const float* arr, int ny, int nx, int N, float* meds);
 int rip_medfit_eval_dev(int device, int ny, int nx, int order, const double* coef, const double* LPX, const double* LPY,
                         float* d_model, float* d_arr, long pitch, void* stream);
@@ -362,6 +374,18 @@ int rip_clip_dev(int device, float* d_arr, long count, float lo, float hi, void*
 int rip_poisson_resample_dev(rip_caldir* h, const float* d_skylevel, const int8_t* d_endslice, int G, int n_samp,
                              const int32_t* group_of_read, const float* weights, const uint8_t* w_defined, double frame_time,
                              uint64_t seed, float* d_diff, void* stream);
+
+/* ---- pixel area from the WCS (utils/coordutils.py:17-82 pixelarea, used at L1_to_L2/gen_cal_image.py:618-622 with the
+ * FITSWCS header of :82-83).  wcs = 211 doubles describing a zenithal FITS WCS with SIP:
+ * CRPIX1,2 CRVAL1,2 CD1_1 CD1_2 CD2_1 CD2_2 LONPOLE proj(0 TAN, 1 STG) sip_order, A[p][q] (10x10), B[p][q] (10x10)
+ * (romanimpreprocess_b200.utils.coordutils.FitsWCS.pack).  out [N,N] f32|f64 = pixel solid angle [sr] * inv_omega
+ * (inv_omega = 1/pars.Omega_ideal gives AreaFactor).  Same construction as the reference, float64. */
+int rip_pixel_area_dev(int device, const double* wcs, int nwcs, int N, double inv_omega, void* d_out, int out_dtype,
+                       void* stream);
+int rip_pixel_area_host(int device, const double* wcs, int nwcs, int N, double inv_omega, void* out, int out_dtype);
+/* The same plane computed straight into the pipeline's resident AreaFactor buffer (see rip_pipeline_set_area): the
+ * per-exposure AreaFactor then costs a 1.7 kB upload and a 0.3 ms kernel instead of a 67 MB copy. */
+int rip_pipeline_set_area_wcs(rip_pipeline* p, const double* wcs, int nwcs, double inv_omega, int area_dtype);
 
 #ifdef __cplusplus
 }

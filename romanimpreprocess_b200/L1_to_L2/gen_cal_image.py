@@ -380,6 +380,18 @@ class Pipeline:
             raise ValueError(f"area plane must be ({self.cal.n},{self.cal.n})")
         _lib.check(_lib.lib().rip_pipeline_set_area(self._p, _lib.ptr(area), _lib.float_tag(area)))
 
+    def set_area_wcs(self, wcs, dtype=np.float32):
+        """Compute the AreaFactor plane of the next exposures ON THE DEVICE from their WCS (``utils.coordutils.FitsWCS``,
+        header text or dict; reference gen_cal_image.py:618-621): pixel solid angle / ``pars.Omega_ideal`` at the n x n
+        pixel positions of the full frame, written into the pipeline's resident area buffer (``rip_pipeline_set_area_wcs``).
+        Asynchronous on the compute stream: exposures already submitted keep their plane."""
+        from ..utils import coordutils  # noqa: PLC0415
+
+        w = wcs if isinstance(wcs, coordutils.FitsWCS) else coordutils.FitsWCS(wcs)
+        v = w.pack()
+        tag = _lib.RIP_F64 if np.dtype(dtype) == np.float64 else _lib.RIP_F32
+        _lib.check(_lib.lib().rip_pipeline_set_area_wcs(self._p, _lib.ptr(v), int(v.size), 1.0 / pars.Omega_ideal, tag))
+
     def submit(self, data, amp33, area_factor=None, out=None):
         """Queue one exposure; returns a ticket.  ``out``: optional dict of preallocated (pinned) output arrays."""
         cal, n, G = self.cal, self.cal.n, self.G
@@ -448,50 +460,182 @@ _CAL_CACHE = {}
 
 
 def _cached_caldir(caldir, device):
+    """One resident CalDir (and one pipeline per group count) per (device, CALDIR file set): the reference re-opens the
+    calibration files for every exposure (gen_cal_image.py:112,172,213,531,536,560,632); here they are uploaded once."""
     key = (device, tuple(sorted((k, v if isinstance(v, str) else id(v)) for k, v in caldir.items())))
     if key not in _CAL_CACHE:
-        _CAL_CACHE[key] = CalDir(caldir, device)
+        _CAL_CACHE[key] = {"cal": CalDir(caldir, device), "pipes": {}}
     return _CAL_CACHE[key]
+
+
+def clear_caldir_cache():
+    """Release the resident CALDIRs of ``calibrateimage`` (device memory)."""
+    for ent in _CAL_CACHE.values():
+        for pipe in ent["pipes"].values():
+            pipe.close()
+        ent["cal"].close()
+    _CAL_CACHE.clear()
+
+
+class ProcessLog:
+    """String log of the processing steps (reference utils/processlog.py:12-56; stored as ``processinfo["log"]``)."""
+
+    def __init__(self):
+        self.output = ""
+        self.reffiles = {}
+
+    def append(self, newoutput):
+        self.output += newoutput
+
+
+def read_l1(path_or_tree):
+    """The L1 inputs of ``initializationstep`` (gen_cal_image.py:116-126): data u16 [G,n,n], amp33 u16 [G,n,128] or None,
+    read pattern, frame time and the ``meta`` branch; ``reference_read`` + ``data_encoding_offset`` are folded back into
+    the data as ``do_dqinit`` does for EXTRACT_REF files (from_sim/sim_to_isim.py:711-730; restated)."""
+    with open_tree(path_or_tree) as f:
+        r = f["roman"]
+        data = np.ascontiguousarray(np.asarray(r["data"]), dtype=np.uint16)
+        amp33 = np.ascontiguousarray(np.asarray(r["amp33"]), dtype=np.uint16) if "amp33" in r else None
+        meta = r["meta"]
+        read_pattern = [[int(x) for x in g] for g in meta["exposure"]["read_pattern"]]
+        frame_time = float(meta["exposure"]["frame_time"])
+        if "reference_read" in r:
+            inst = meta["instrument"] if "instrument" in meta else {}
+            off = int(inst["data_encoding_offset"]) if "data_encoding_offset" in inst else 0
+            data = (data.astype(np.int32) + np.asarray(r["reference_read"]).astype(np.int32) - off).astype(np.uint16)
+        border = {
+            "amp33": None if amp33 is None else np.copy(amp33),
+            "border_ref_pix_left": data[:, :, :4].astype(np.float32),
+            "border_ref_pix_right": data[:, :, -4:].astype(np.float32),
+            "border_ref_pix_top": data[:, -4:, :].astype(np.float32),
+            "border_ref_pix_bottom": data[:, :4, :].astype(np.float32),
+        }  # oututils.add_in_ref_data (L1_to_L2/oututils.py:43-49)
+        meta_copy = _plain_copy(meta)
+    return data, amp33, read_pattern, frame_time, meta_copy, border
+
+
+def _plain_copy(node):
+    """Deep copy of a metadata branch that outlives its file (arrays materialised, tagged nodes kept)."""
+    if isinstance(node, dict) or hasattr(node, "items"):
+        out = type(node)() if isinstance(node, dict) else {}
+        if hasattr(node, "tag") and hasattr(out, "tag"):
+            out.tag = node.tag
+        for k, v in node.items():
+            out[k] = _plain_copy(v)
+        return out
+    if isinstance(node, (list, tuple)):
+        out = type(node)(_plain_copy(v) for v in node) if isinstance(node, list) else [_plain_copy(v) for v in node]
+        if hasattr(node, "tag") and hasattr(out, "tag"):
+            out.tag = node.tag
+        return out
+    if hasattr(node, "__array__") and not isinstance(node, (str, bytes)):
+        return np.array(node)
+    return node
 
 
 def calibrateimage(config, verbose=True, device=0):
     """
-    Main routine to run the specified calibrations from a config file (same contract as the reference's
-    ``calibrateimage``: reads ``config["IN"]`` (L1 ASDF), writes ``config["OUT"]`` (L2 ASDF)).
+    Main routine to run the specified calibrations from a config file: the reference's entry point
+    (L1_to_L2/gen_cal_image.py:480-739) with the same configuration keys.  Reads ``config["IN"]`` (L1 ASDF), writes
+    ``config["OUT"]`` (L2 ASDF: ``roman`` + ``processinfo`` trees, arrays as the reference packs them at :653-723).
 
-    The per-pixel numerics run on the GPU; reading/writing the data models, the WCS-derived pixel area, sky
-    statistics and packaging are the reference's host code and need its I/O stack (``asdf``, ``roman_datamodels``,
-    ``romanisim``, ``astropy``, ``gwcs``) -- they are imported from the installed ``romanimpreprocess`` package, which
-    this module does not replace.
+    What runs where: the per-pixel chain (dq-init ... endslice, :503-629, 697-709) is the fused CUDA path; the pixel
+    area comes from the ``FITSWCS`` header on the device (``utils.coordutils``); mask growth, binning, sky mode and the
+    ``SKYORDER`` fit (:639-651) are device kernels; reading, packaging and writing are host code here
+    (``asdf`` if installed, else ``io.asdf_lite``).
+
+    Not implemented (raise ``NotImplementedError`` instead of silently differing from the reference): ``dark_decay`` in
+    CALDIR (:567-570), ``correct_wfi18_transient`` (:572-575), ``romancal_ramp_fit`` (:415-432), ``FITSOUT`` (:725-736).
+    Metadata of the L1 file is passed through; romanisim's ``make_asdf`` bookkeeping (photometry, cal_step, WCS object)
+    is not reproduced: the FITS header text is stored under ``processinfo["fitswcs"]`` instead.
     """
-    try:
-        import asdf  # noqa: PLC0415
-        from romanimpreprocess.L1_to_L2 import gen_cal_image as _ref  # noqa: PLC0415
-    except ImportError as e:
-        raise ImportError(
-            "calibrateimage() reads and writes ASDF data models through the reference's I/O layer "
-            "(asdf, roman_datamodels, romanisim, romanimpreprocess); install them, or call calibrate_arrays() "
-            "with in-memory arrays"
-        ) from e
-    caldir = config["CALDIR"]
-    cal = _cached_caldir(caldir, device)
-    with asdf.open(config["IN"]) as f:
-        r = f["roman"]
-        data = np.asarray(r["data"])
-        amp33 = np.asarray(r["amp33"]) if "amp33" in r else None
-        read_pattern = [list(g) for g in r["meta"]["exposure"]["read_pattern"]]
-        frame_time = float(r["meta"]["exposure"]["frame_time"])
-        if "reference_read" in r:  # EXTRACT_REF round trip (reference sim_to_isim.py:711-730)
-            off = int(r["meta"]["instrument"].get("data_encoding_offset", 0)) if "instrument" in r["meta"] else 0
-            data = (data.astype(np.int32) + np.asarray(r["reference_read"]).astype(np.int32) - off).astype(np.uint16)
-    thewcs = _ref.wcs_from_config(config)
-    from romanisim import wcs as riwcs  # noqa: PLC0415
-    from romanimpreprocess.utils import coordutils  # noqa: PLC0415
+    from ..caltree import write_tree  # noqa: PLC0415
+    from ..utils import coordutils, maskhandling, sky  # noqa: PLC0415
 
-    area = coordutils.pixelarea(riwcs.convert_wcs_to_gwcs(_ref.repackage_wcs(thewcs)), N=data.shape[-1]) / pars.Omega_ideal
-    out = calibrate_arrays(cal, data, amp33, read_pattern, frame_time, area, config, do_refpix=cal.has_amp33,
-                           want_rdq=True, want_endslice=bool(config.get("SLICEOUT", False)))  # fmt: skip
-    return _ref._package_l2(config, out, thewcs) if hasattr(_ref, "_package_l2") else out
+    caldir = config["CALDIR"]
+    if "dark_decay" in caldir:
+        raise NotImplementedError("CALDIR['dark_decay'] (romancal dark-decay step, gen_cal_image.py:567-570) is not implemented on the GPU path")
+    for key in ("correct_wfi18_transient", "romancal_ramp_fit", "FITSOUT"):
+        if config.get(key, False):
+            raise NotImplementedError(f"config['{key}'] is not implemented on the GPU path (reference gen_cal_image.py)")
+    mylog = ProcessLog()
+    wcs = coordutils.wcs_from_config(config)
+    if wcs is None:
+        raise ValueError("Unrecognized WCS")  # (the reference cannot package an exposure without FITSWCS either)
+    ent = _cached_caldir(caldir, device)
+    cal = ent["cal"]
+    data, amp33, read_pattern, frame_time, l1meta, border = read_l1(config["IN"])
+    mylog.append("Initialized data\n")
+    G, n, nb = data.shape[0], data.shape[1], cal.nb
+    do_refpix = cal.has_amp33 and amp33 is not None
+    pkey = (G, tuple(tuple(g) for g in read_pattern), frame_time, repr(sorted((k, repr(v)) for k, v in config.items() if k in
+            ("EXCLUDE_FIRST", "SATURATION_BACKUP", "RAMP_OPT_PARS", "JUMP_DETECT_PARS", "SLICEOUT"))), do_refpix)  # fmt: skip
+    if pkey not in ent["pipes"]:
+        ent["pipes"][pkey] = Pipeline(cal, read_pattern, frame_time, config, do_refpix=do_refpix, depth=1, want_rdq=True,
+                                      area_dtype=np.float64)  # fmt: skip
+    pipe = ent["pipes"][pkey]
+    # AreaFactor = pixel area / Omega_ideal at the n x n pixel positions (gen_cal_image.py:618-621), float64 on the device
+    pipe.set_area_wcs(wcs, dtype=np.float64)
+    out = pipe.result(pipe.submit(data, amp33 if do_refpix else None, None))
+    meta = out["meta"]
+    mylog.append("Saturation check complete\n" + ("Reference pixel correction complete\n" if do_refpix else "") +
+                 "Linearity correction complete\nRamp fitting complete\nDark current subtracted\nacquired flat field\n")  # fmt: skip
+    slope, pdq, rdq = out["slope"], out["pdq"], out["rdq"]
+    medgain = cal.medgain
+    mylog.append(f"median gain = {medgain:8.5f} e/DN\n")
+    # sky information (gen_cal_image.py:639-651)
+    slope_withsky = np.copy(slope)
+    m = maskhandling.PixelMask1.build(pdq, device=device)
+    medsky, _ = sky.smooth_mode(sky.binkxk(slope, 4, mask=m, device=device), device=device)
+    if "SKYORDER" in config:
+        skyorder = int(config["SKYORDER"])
+        skycoefs, skymodel = sky.medfit(np.ascontiguousarray(slope[nb:-nb, nb:-nb]), order=skyorder, device=device)
+        slope[nb:-nb, nb:-nb] -= skymodel
+    else:
+        skycoefs, skyorder = np.array([]).astype(np.float32), -1
+    # packaging (rimage.make_asdf arrays :653-666, oututils.add_in_ref_data :674, typefix dummy fields)
+    act = np.s_[nb:-nb, nb:-nb]
+    var_r = out["err_read"][act] ** 2
+    var_p = out["err_poisson"][act] ** 2
+    im2 = {
+        "meta": l1meta,
+        "data": np.ascontiguousarray(slope[act]),
+        "dq": np.ascontiguousarray(pdq[act]),
+        "var_poisson": var_p,
+        "var_rnoise": var_r,
+        "var_flat": np.zeros_like(var_r),
+        "err": np.sqrt(var_r + var_p),
+        "dq_border_ref_pix_left": np.copy(pdq[:, :4]), "dq_border_ref_pix_right": np.copy(pdq[:, -4:]),
+        "dq_border_ref_pix_top": np.copy(pdq[-4:, :]), "dq_border_ref_pix_bottom": np.copy(pdq[:4, :]),
+        "data_withsky": np.ascontiguousarray(slope_withsky[act]),
+    }  # fmt: skip
+    for k, v in border.items():
+        if v is not None:
+            im2[k] = v
+    for fld in ("chisq", "dumo"):  # utils/typefix.py:22-29
+        im2[fld] = np.zeros(im2["data"].shape, dtype=np.float16)
+    im2["meta"].setdefault("dummyfields", [])
+    im2["meta"]["dummyfields"] = list(im2["meta"]["dummyfields"]) + ["roman.chisq", "roman.dumo"]
+    im2["meta"]["calibration_software_name"] = "gen_cal_image / HLWAS PIT (romanimpreprocess_b200)"  # oututils.py:102-106
+    from .. import __version__ as _ver  # noqa: PLC0415
+
+    im2["meta"]["calibration_software_version"] = str(_ver)
+    if "exposure" in im2["meta"]:
+        im2["meta"]["exposure"]["read_pattern"] = [list(g) for g in read_pattern]
+    processinfo = {
+        "medsky": float(medsky), "medgain": float(medgain), "skyorder": skyorder, "skycoefs": np.asarray(skycoefs),
+        "ramp_opt_pars": {k: float(v) for k, v in meta["ramp_opt_pars"].items()},
+        "meta": {"frame_time": float(frame_time), "read_pattern": [list(g) for g in read_pattern], "ngrp": int(G),
+                 "tbar": meta["tbar"], "tau": meta["tau"], "N": meta["N"], "nborder": int(nb), "K": meta["K"]},
+        "weights": meta["K"], "config": _plain_copy(config), "log": mylog.output,
+        "exclude_first": bool(config.get("EXCLUDE_FIRST", True)),
+        "fitswcs": open(config["FITSWCS"]).read(),
+    }  # fmt: skip
+    if config.get("SLICEOUT", False):
+        processinfo["endslice"] = out["endslice"]
+    write_tree(config["OUT"], {"roman": im2, "processinfo": processinfo})
+    if verbose:
+        print(mylog.output)
 
 
 __all__ = ["CalDir", "DevicePlan", "Pipeline", "calibrate_arrays", "calibrate_device", "calibrateimage", "exposure_meta",

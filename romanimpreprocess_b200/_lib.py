@@ -122,7 +122,13 @@ _SIGS = {
     "rip_pipeline_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(L1L2Params),
                                       C.POINTER(RampPlan), C.c_void_p, C.POINTER(L2Out), C.POINTER(C.c_long)]),
     "rip_pipeline_wait": (C.c_int, [C.c_void_p, C.c_long]),
+    "rip_medfit_solve": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rip_bin_masked_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "rip_gauss_hist_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "rip_pipeline_set_area": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "rip_pipeline_set_area_wcs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int]),
+    "rip_pixel_area_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p]),
+    "rip_pixel_area_host": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int]),
     "rip_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "rip_profile_fetch": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "rip_refpix_stats_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,

@@ -775,6 +775,24 @@ extern "C" int rip_pipeline_set_area(rip_pipeline* p, const void* area, int area
     RIP_API_END
 }
 
+extern "C" int rip_pipeline_set_area_wcs(rip_pipeline* p, const double* wcs, int nwcs, double inv_omega, int area_dtype) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(p && wcs, "rip_pipeline_set_area_wcs: null argument");
+    rip_caldir* h = p->h;
+    use_device(h->device);
+    RIP_REQUIRE(area_dtype == RIP_F32 || area_dtype == RIP_F64, "rip_pipeline_set_area_wcs: area dtype must be f32 or f64");
+    const size_t bytes = (size_t)h->n * h->n * dtype_size(area_dtype);
+    if (p->area_res.bytes < bytes) {
+        RIP_CUDA(cudaStreamSynchronize(p->s_run));
+        p->area_res.alloc(bytes);
+    }
+    // on the compute stream: ordered after the exposures already queued (they read the old plane), before the next ones
+    launch_pixel_area(wcs, nwcs, h->n, inv_omega, p->area_res.p, area_dtype, p->s_run);
+    p->area_res_dtype = area_dtype;
+    p->area_res_set = true;
+    RIP_API_END
+}
+
 extern "C" int rip_pipeline_submit(rip_pipeline* p, const uint16_t* raw, const uint16_t* amp33, const void* area,
                                    const rip_l1l2_params* prm, const rip_ramp_plan* plan, const double* w_exact,
                                    const rip_l2_out* out, long* ticket) {

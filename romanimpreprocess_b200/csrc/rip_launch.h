@@ -33,4 +33,7 @@ void v2_pack(rip_caldir* h, int G, cudaStream_t st);
 v2::f4* v2_rec1_row0(rip_caldir* h, int G);  // record of detector row 0 inside the padded allocations
 v2::f4* v2_recK_row0(rip_caldir* h);
 
+// rip_area.cu ----------------------------------------------------------------------------------------------
+void launch_pixel_area(const double* wcs, int nwcs, int N, double inv_omega, void* d_out, int out_dtype, cudaStream_t st);
+
 }  // namespace rip

@@ -143,7 +143,8 @@ class BlockArray:
             if got != item * count:
                 raise AsdfLiteError("read_into: short read")
         else:
-            src = np.ascontiguousarray(self._array()[first : first + count])
+            part = self._array()[first : first + count]
+            src = np.ascontiguousarray(part, dtype=part.dtype.newbyteorder("="))  # (big-endian blocks: swapped here)
             mv[: item * count] = memoryview(src).cast("B")
         return item * count
 

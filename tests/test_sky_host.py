@@ -1,0 +1,50 @@
+"""CPU: the host part of the sky fit that lives in the library (rip_medfit_solve, csrc/rip_sky.cu) against the reference's
+NumPy / SciPy lines (utils/sky.py:137-175, restated in oracle.medfit and pinned by tests/golden/sky_medfit.npz)."""
+
+import numpy as np
+from scipy.special import legendre_p
+from scipy.stats import norm
+
+from romanimpreprocess_b200.utils import sky
+
+
+def _reference_solve(meds, N, nx, ny, order):
+    kx, ky = nx // N, ny // N
+    px, py = (nx % N) // 2, (ny % N) // 2
+    u_ = 2 * (px - 0.5 + kx * np.linspace(0.5, N - 0.5, N)) / nx - 1
+    v_ = 2 * (py - 0.5 + ky * np.linspace(0.5, N - 0.5, N)) / ny - 1
+    u, v = np.meshgrid(u_, v_)
+    nc = (order + 1) * (order + 2) // 2
+    basis = np.zeros((nc, N, N))
+    k = 0
+    for i in range(order + 1):
+        t = legendre_p(i, u)
+        for j in range(order + 1 - i):
+            basis[k] = t * legendre_p(j, v)
+            k += 1
+    A, b = np.zeros((nc, nc)), np.zeros(nc)
+    for ip in range(N):
+        for jp in range(N):
+            if not np.isnan(meds[jp, ip]):
+                A += np.outer(basis[:, jp, ip], basis[:, jp, ip])
+                b += meds[jp, ip] * basis[:, jp, ip]
+    return np.linalg.solve(A, b)
+
+
+def test_medfit_solve_against_numpy():
+    rng = np.random.default_rng(1)
+    for ny, nx, N, order in [(4088, 4088, 8, 2), (248, 248, 8, 2), (500, 377, 8, 3), (4088, 4088, 8, 0), (4088, 4088, 6, 4)]:
+        meds = rng.normal(1.0, 0.1, (N, N)).astype(np.float32)
+        meds[1, 2] = np.nan
+        coef, LPX, LPY = sky._solve(meds, N, nx, ny, order)
+        x = _reference_solve(meds, N, nx, ny, order)
+        assert np.max(np.abs(coef - x)) <= 1e-14 * np.abs(x).max()
+        # grid polynomials: bit-identical to scipy.special.legendre_p on np.linspace (utils/sky.py:167-175)
+        for i in range(order + 1):
+            assert np.array_equal(LPX[i], np.ravel(legendre_p(i, np.linspace(-1, 1 - 2 / nx, nx)))), (nx, i)
+            assert np.array_equal(LPY[i], np.ravel(legendre_p(i, np.linspace(-1, 1 - 2 / ny, ny)))), (ny, i)
+
+
+def test_norm_ppf():
+    for p in (0.75, 0.9, 0.6, 0.01, 0.999, 0.5):
+        assert abs(sky._norm_ppf(p) - norm.ppf(p)) < 1e-14 * max(1.0, abs(norm.ppf(p)))
