@@ -528,8 +528,9 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
     // v2 (rip_v2_core.cuh) for the common all-f32 configuration; params.threads > 0 selects the generic v1 tile kernel
     // (threads < 0: development selector of the fused-kernel variant, -1 = v2, -2 / -3 = v3 without / with stage b in role X)
     const int variant = prm->threads < 0 ? -prm->threads - 1 : fused_default_variant();
-    const bool use_v2 = prm->threads <= 0 && h->has_ipc && h->d.gain_dtype == RIP_F32 && h->d.ipc_dtype == RIP_F32 &&
-                        h->nb == 4 && n % 8 == 0 && n >= 16 && v2_supported(G, h->P) &&
+    const bool k64 = h->has_ipc && h->d.ipc_dtype == RIP_F64;
+    const bool use_v2 = prm->threads <= 0 && h->has_ipc && h->d.gain_dtype == RIP_F32 &&
+                        h->nb == 4 && n % 8 == 0 && n >= 16 && v2_supported(G, h->P, k64) &&
                         (prm->area_dtype == RIP_F32 || prm->area_dtype == RIP_F64);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {
@@ -550,7 +551,7 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
         v2::Args V;
         memset(&V, 0, sizeof V);
         V.n = n; V.ntile = v2::ntiles(n);
-        V.band_rows = prm->band_rows > 0 ? prm->band_rows : v2_default_band_rows(h->device, n, G, (variant == 1 || variant == 2) ? ((G <= 8) ? 3 : 2) : 0);
+        V.band_rows = prm->band_rows > 0 ? prm->band_rows : v2_default_band_rows(h->device, n, G, (k64 || variant == 1 || variant == 2) ? ((G <= 8) ? 3 : 2) : 0);
         V.do_refpix = prm->do_refpix; V.do_not_flag_first = prm->do_not_flag_first; V.exclude_first = prm->exclude_first;
         V.sat_backup = prm->sat_backup; V.area_dtype = prm->area_dtype;
         V.negzero = -0.0f;
@@ -563,7 +564,8 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
         V.endslice = o->endslice; V.rdq = o->rdq; V.lincube = o->lin_cube;
         if (e0) RIP_CUDA(cudaEventRecord(e0, st));
         RIP_REQUIRE(((uintptr_t)d_raw & 15) == 0, "rip_l1_to_l2: the raw cube must be 16-byte aligned");
-        if (variant) launch_cal_fused_v3(V, G, h->P, variant, st);
+        if (k64) launch_cal_fused_v2k64(V, G, h->P, st);
+        else if (variant) launch_cal_fused_v3(V, G, h->P, variant, st);
         else launch_cal_fused_v2(V, G, h->P, st);
         if (e1) RIP_CUDA(cudaEventRecord(e1, st));
         return;

@@ -24,7 +24,8 @@ size_t cal_fused_smem_bytes(int G, int g_dtype, int k_dtype, int threads);
 
 // rip_v2.cu ------------------------------------------------------------------------------------------------
 namespace v2 { struct Args; struct f4; }
-bool v2_supported(int G, int P);
+bool v2_supported(int G, int P, bool k64 = false);
+void launch_cal_fused_v2k64(const v2::Args& A, int G, int P, cudaStream_t st);
 int v2_default_band_rows(int device, int n, int G, int ctas_per_sm = 0);
 void launch_cal_fused_v3(const v2::Args& A, int G, int P, int variant, cudaStream_t st);
 void v2_plan_to_device(const rip_ramp_plan* plan, cudaStream_t st);

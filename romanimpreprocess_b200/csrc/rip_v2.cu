@@ -43,6 +43,20 @@ __global__ void pack_recK_kernel(const PackSrc S, int ntile, f4* __restrict__ ou
     }
 }
 
+__global__ void pack_recK64_kernel(const PackSrc S, int ntile, f4* __restrict__ out) {
+    const int c = threadIdx.x, tile = blockIdx.x, row = (int)blockIdx.y - PADR;
+    const int x = tile * TS + c;
+    f4* o = out + ((long)row * ntile + tile) * ((long)KQ64 * TW) + c;
+    for (int q = 0; q < KQ64; ++q) {
+        f4 v;
+        v.x = recK64_word(S, row, x, 4 * q);
+        v.y = recK64_word(S, row, x, 4 * q + 1);
+        v.z = recK64_word(S, row, x, 4 * q + 2);
+        v.w = recK64_word(S, row, x, 4 * q + 3);
+        o[q * TW] = v;
+    }
+}
+
 // One CTA per (column tile, row band).  (A persistent-CTA variant pulling work items from an atomic counter was
 // measured on B200: no gain -- 1120 items on 592 resident slots already overlap well -- and its outer loop cost
 // registers, i.e. spills at the 128-register budget; dropped.)
@@ -70,6 +84,26 @@ template <int G, int P, bool BX, int MINB, int XR, int YR>
 __global__ void __launch_bounds__(2 * TW, MINB) cal_fused_v3_kernel(const Args A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     v3_body<G, P, BX, XR, YR>(A, c_plan_v2, c_fast_v2, smem_raw);
+}
+
+// float64 ipc4d (K64): same march, IPC stages in float64 (3 CTAs/SM: the O1 ring holds doubles)
+template <int G, int P, int MINB>
+__global__ void __launch_bounds__(TW, MINB) cal_fused_v2k64_kernel(const Args A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<G, true> sm;
+    sm.carve(smem_raw);
+    Regs<G, P> R;
+    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int r0 = blockIdx.y * A.band_rows;
+    const int r1 = min(r0 + A.band_rows, A.n);
+    prologue<G, P, true>(A, sm, R, tid, tile, r0, r1);
+    __syncthreads();
+    unsigned o5s = first_o5<G>(r0);
+    for (int s = r0 - 3; s <= r1 + 5; ++s) {
+        step<G, P, true>(A, c_plan_v2, c_fast_v2, sm, R, tid, tile, r0, r1, s, o5s);
+        o5s = next_o5<G>(o5s);
+        __syncthreads();
+    }
 }
 
 template <int G, int P, int MINB>
@@ -102,6 +136,15 @@ static void launch_v3(const Args& A, cudaStream_t st) {
     configure_once((const void*)kern, smem);
     dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
     RIP_LAUNCH(kern, grid, 2 * TW, smem, st, A);
+}
+
+template <int G, int P>
+static void launch_k64(const Args& A, cudaStream_t st) {
+    const size_t smem = Smem<G, true>::bytes();
+    auto kern = cal_fused_v2k64_kernel<G, P, 3>;
+    configure_once((const void*)kern, smem);
+    dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
+    RIP_LAUNCH(kern, grid, TW, smem, st, A);
 }
 
 template <int G, int P>
@@ -149,8 +192,15 @@ int v2_default_band_rows(int device, int n, int G, int ctas_per_sm) {
     return rows < 16 ? 16 : rows;
 }
 
-bool v2_supported(int G, int P) {
+bool v2_supported(int G, int P, bool k64) {
+    if (k64) return G == 8 && (P == 4 || P == 11);  // (G = 16 with float64 taps would leave one CTA per SM: generic kernel)
     return (G == 8 && P == 4) || (G == 8 && P == 11) || (G == 16 && P == 11) || (G == 16 && P == 4);
+}
+
+void launch_cal_fused_v2k64(const v2::Args& A, int G, int P, cudaStream_t st) {
+    if (G == 8 && P == 4) v2::launch_k64<8, 4>(A, st);
+    else if (G == 8 && P == 11) v2::launch_k64<8, 11>(A, st);
+    else throw Error("cal_fused v2 (float64 ipc4d): unsupported (G, P)");
 }
 
 // variant: 0 = v2 (one role, 128 threads), 1 = v3 (X: a0 a1 | Y: b c), 2 = v3 (X: a0 a1 b | Y: c)
@@ -182,15 +232,19 @@ void v2_plan_to_device(const rip_ramp_plan* plan, cudaStream_t st) {
 v2::f4* v2_rec1_row0(rip_caldir* h, int G) {
     return (v2::f4*)h->v2_rec1.p + (size_t)v2::PADR * v2::ntiles(h->n) * v2::nq1(G, h->P) * v2::TW;
 }
-v2::f4* v2_recK_row0(rip_caldir* h) { return (v2::f4*)h->v2_recK.p + (size_t)v2::PADR * v2::ntiles(h->n) * v2::KQ * v2::TW; }
+v2::f4* v2_recK_row0(rip_caldir* h) {
+    return (v2::f4*)h->v2_recK.p + (size_t)v2::PADR * v2::ntiles(h->n) * v2::kq_of(h->d.ipc_dtype == RIP_F64) * v2::TW;
+}
 
 // (re)build the packed records of a handle for G groups
 void v2_pack(rip_caldir* h, int G, cudaStream_t st) {
     if (h->v2_G == G) return;
+    const bool k64 = h->d.ipc_dtype == RIP_F64;
+    const int kq = v2::kq_of(k64);
     const int n = h->n, ntile = v2::ntiles(n), nq = v2::nq1(G, h->P);
     const int nrow = n + 2 * v2::PADR;  // zero rows on both sides: the kernel's loaders never clamp
     h->v2_rec1.alloc((size_t)nrow * ntile * nq * v2::TW * 4);
-    h->v2_recK.alloc((size_t)nrow * ntile * v2::KQ * v2::TW * 4);
+    h->v2_recK.alloc((size_t)nrow * ntile * kq * v2::TW * 4);
     v2::PackSrc S;
     S.n = n; S.nb = h->nb; S.G = G; S.P = h->P;
     S.dark = h->dark_cube.p;
@@ -200,7 +254,8 @@ void v2_pack(rip_caldir* h, int G, cudaStream_t st) {
     S.read = h->read.p; S.dslope = h->dslope_ipc.p; S.flat = h->flat_ipc.p; S.sdq = h->sdq.p;
     dim3 grid(ntile, nrow);
     RIP_LAUNCH(v2::pack_rec1_kernel, grid, v2::TW, 0, st, S, ntile, nq, v2_rec1_row0(h, G));
-    RIP_LAUNCH(v2::pack_recK_kernel, grid, v2::TW, 0, st, S, ntile, v2_recK_row0(h));
+    if (k64) RIP_LAUNCH(v2::pack_recK64_kernel, grid, v2::TW, 0, st, S, ntile, v2_recK_row0(h));
+    else RIP_LAUNCH(v2::pack_recK_kernel, grid, v2::TW, 0, st, S, ntile, v2_recK_row0(h));
     h->v2_G = G;
 }
 

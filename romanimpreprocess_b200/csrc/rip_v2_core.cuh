@@ -36,6 +36,8 @@ constexpr int TW = 128;   // columns per tile (= compute threads per CTA)
 constexpr int TS = 120;   // tile stride: outputs are tile columns 4..123 (tile 0 also 0..3)
 constexpr int RW = TW + 2;  // ring width: 1 pad column on each side
 constexpr int KQ = 4;     // float4 words per pixel in recK
+constexpr int KQ64 = 6;   // ... when the taps are float64 (K64)
+RIP_HD constexpr int kq_of(bool k64) { return k64 ? KQ64 : KQ; }
 constexpr int RING = 5;   // depth of the rings addressed with the shared modulo-5 slot (D, raw, thresholds, flags, corrections)
 constexpr int O_DEPTH = 4, S_DEPTH = 4;
 constexpr int PADR = 10;  // zero rows above and below the packed records: the loaders never clamp (rows -9 .. n+4 are touched)
@@ -166,7 +168,13 @@ struct Args {
 //   ring4 (depth 4, slot = row & 3):      O1 f4[G/4][RW] | sat u32[RW]
 // raw / thr / rc / ln are filled by cp.async two steps ahead (rows s-2 .. s+2 live); flg (satm | adf<<16) and nlc
 // (bit0 dynamic NO_LIN_CORR, bit2 reference pixel) are thread-private delay lines a1 -> c.
-template <int G>
+struct alignas(16) d2 {
+    double x, y;
+};
+// K64: ipc4d is float64 (the dtype the DUMMY CALDIR builder writes, runs/summer2025run/make_gain_file.py:138,194): the
+// reference then runs both IPC passes in float64, so the O1 ring holds doubles -- G/2 planes of
+// (two groups of one pixel) = conflict-free LDS.128 -- and the taps are doubles; D stays float32 (data * gain is f32).
+template <int G, bool K64 = false>
 struct Smem {
     static constexpr int H = G / 4;
     static constexpr int OFF_D = 0;
@@ -178,7 +186,7 @@ struct Smem {
     static constexpr int OFF_NLC = OFF_LN + 16 * G;
     static constexpr int ROW5 = (OFF_NLC + TW + 15) / 16 * 16;
     static constexpr int OFF_O1 = 0;
-    static constexpr int OFF_SAT = 16 * H * RW;
+    static constexpr int OFF_SAT = (K64 ? 32 : 16) * H * RW;
     static constexpr int ROW4 = (OFF_SAT + 4 * RW + 15) / 16 * 16;
     unsigned char* r5;
     unsigned char* r4;
@@ -196,6 +204,7 @@ struct Smem {
     RIP_HD double* ln(unsigned o5) const { return (double*)(r5 + o5 + OFF_LN); }
     RIP_HD uint8_t* nlc(unsigned o5) const { return (uint8_t*)(r5 + o5 + OFF_NLC); }
     RIP_HD f4* O1(int row) const { return (f4*)(r4 + (unsigned)(row & (O_DEPTH - 1)) * ROW4 + OFF_O1); }
+    RIP_HD d2* O1d(int row) const { return (d2*)(r4 + (unsigned)(row & (O_DEPTH - 1)) * ROW4 + OFF_O1); }  // [G/2][RW]
     RIP_HD uint32_t* sat(int row) const { return (uint32_t*)(r4 + (unsigned)(row & (S_DEPTH - 1)) * ROW4 + OFF_SAT); }
 };
 
@@ -212,6 +221,9 @@ struct Regs {
     f4 kbn[2];         // the same for the NEXT step, in flight during this one
     float kbn8;
     f4 kc[KQ];         // stage c,  row s-6
+    // K64 (float64 taps): recK has KQ64 words per pixel: 9 taps as doubles (18 words), gain read dslope flat sdq pad
+    double kbd[9], kbnd[9];  // stage b taps (this step / next step)
+    f4 kc64[6];              // stage c record
     float area32;
     double area64;
     unsigned orow;     // s * n (pixel offset of detector row s): CTA-uniform, advanced by n per step
@@ -256,8 +268,8 @@ RIP_HD void cp_async_wait() {
 //   the saturation threshold of the thread's own column (4 bytes);
 //   row correction [G] and the two channel lines [2][G] of the row (threads 0 .. 3G-1, 8 bytes each).
 // Every thread commits one group per step (possibly empty) so that wait_group counts steps.
-template <int G, int P>
-RIP_HD void row_async(const Args& A, Smem<G>& sm, const Regs<G, P>& R, int row, int row_off, unsigned slot_o5, int tile, int tid,
+template <int G, int P, class SM>
+RIP_HD void row_async(const Args& A, SM& sm, const Regs<G, P>& R, int row, int row_off, unsigned slot_o5, int tile, int tid,
                       int lo, int hi) {  // row_off: rows relative to row s (R.orow)
     if (in_range(row, imax(lo, 0), imin(hi, A.n))) {
         const unsigned npl = (unsigned)A.n * (unsigned)A.n;
@@ -304,6 +316,39 @@ RIP_HD void load_bn(const Args& A, Regs<G, P>& R, int row, int tile, int tid, un
     R.kbn[1] = p[TW + tid];
     R.kbn8 = ((const float*)(p + 2 * TW))[4 * tid];  // .x of the third word
 }
+RIP_HD double f2_as_double(float lo, float hi) {
+    double d;
+    float w[2] = {lo, hi};
+    memcpy(&d, w, 8);
+    return d;
+}
+// K64 forms of the two recK loaders: taps of stage b as doubles (words 0..17), whole record of stage c (6 words of 4)
+template <int G, int P>
+RIP_HD void load_bn64(const Args& A, Regs<G, P>& R, int row, int tile, int tid, unsigned dep) {
+    const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ64 * TW) + dep;
+    f4 w[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) w[q] = p[q * TW + tid];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        R.kbnd[2 * q] = f2_as_double(w[q].x, w[q].y);
+        R.kbnd[2 * q + 1] = f2_as_double(w[q].z, w[q].w);
+    }
+    R.kbnd[8] = f2_as_double(w[4].x, w[4].y);
+}
+template <int G, int P>
+RIP_HD void load_c64(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int x, bool xin) {
+    const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ64 * TW);
+#pragma unroll
+    for (int q = 0; q < KQ64; ++q) R.kc64[q] = p[q * TW + tid];
+    if (A.area) {
+        const int rr = row < 0 ? 0 : (row >= A.n ? A.n - 1 : row);
+        const unsigned o = (unsigned)rr * (unsigned)A.n + (unsigned)(xin ? x : 0);
+        if (A.area_dtype == RIP_F64) R.area64 = ((const double*)A.area)[o];
+        else R.area32 = ((const float*)A.area)[o];
+    }
+}
+
 template <int G, int P>
 RIP_HD void load_c(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int x, bool xin) {
     const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW);
@@ -707,8 +752,8 @@ struct StepCtx {  // what every stage derives from (tile, tid, band, step); all 
 };
 
 // stage a1 : row s-2 (saturation growth, refpix, bias, multilin, D = lin * gain)
-template <int G, int P>
-RIP_HD void stage_a1(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const StepCtx& C) {
+template <int G, int P, class SM>
+RIP_HD void stage_a1(const Args& A, SM& sm, const Regs<G, P>& R, const StepCtx& C) {
     constexpr int H = G / 4, NQ1 = Regs<G, P>::NQ1;
     const int n = C.n, nb = 4, tid = C.tid, col = C.col, x = C.x, r0 = C.r0, r1 = C.r1;
     const unsigned (&o5)[5] = C.o5;
@@ -846,8 +891,8 @@ RIP_HD void stage_a1(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const Step
 }
 
 // stage b : row s-4 (IPC pass 1:  O1 = (D + D) - K (*) D)
-template <int G, int P>
-RIP_HD void stage_b(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const StepCtx& C) {
+template <int G, int P, class SM>
+RIP_HD void stage_b(const Args& A, SM& sm, const Regs<G, P>& R, const StepCtx& C) {
     constexpr int H = G / 4;
     const int n = C.n, nb = 4, tid = C.tid, col = C.col, r0 = C.r0, r1 = C.r1;
     const unsigned (&o5)[5] = C.o5;
@@ -874,6 +919,56 @@ RIP_HD void stage_b(const Args& A, Smem<G>& sm, const Regs<G, P>& R, const StepC
     }
 }
 
+// stage b, float64 taps (K64): O1 = f64(f32(D + D)) - K (*) D with every product and sum a separate float64 operation in
+// the reference's accumulation order (utils/ipc_linearity.py:69-94; the image is float32, the kernel float64 -> NumPy
+// promotes the products).  D is read as float4 (4 groups) and converted on the fly.
+#define RIP_TAP64(V, Q)                  \
+    {                                    \
+        const f4 t = (V);                \
+        const double kq = k[Q];          \
+        a0 = a0 + (double)t.x * kq;      \
+        a1 = a1 + (double)t.y * kq;      \
+        a2 = a2 + (double)t.z * kq;      \
+        a3 = a3 + (double)t.w * kq;      \
+    }
+template <int G, int P, class SM>
+RIP_HD void stage_b64(const Args& A, SM& sm, const Regs<G, P>& R, const StepCtx& C) {
+    constexpr int H = G / 4;
+    const int n = C.n, nb = 4, col = C.col, r0 = C.r0, r1 = C.r1;
+    const unsigned (&o5)[5] = C.o5;
+    const int row = C.s - 4;
+    const bool rowok = in_range(row, imax(r0 - 1, nb), imin(r1 + 1, n - nb));
+    d2* o = sm.O1d(row);
+    if (rowok) {
+        const double (&k)[9] = R.kbd;
+        const f4* dm = sm.D(RIP_O5(-5));
+        const f4* d0 = sm.D(RIP_O5(-4));
+        const f4* dp = sm.D(RIP_O5(-3));
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const f4 c = d0[h * RW + col];
+            double a0 = (double)c.x * k[0], a1 = (double)c.y * k[0], a2 = (double)c.z * k[0], a3 = (double)c.w * k[0];
+            RIP_TAP64(dm[h * RW + col], 1)
+            RIP_TAP64(dp[h * RW + col], 2)
+            RIP_TAP64(d0[h * RW + col - 1], 3)
+            RIP_TAP64(d0[h * RW + col + 1], 4)
+            RIP_TAP64(dm[h * RW + col - 1], 5)
+            RIP_TAP64(dm[h * RW + col + 1], 6)
+            RIP_TAP64(dp[h * RW + col - 1], 7)
+            RIP_TAP64(dp[h * RW + col + 1], 8)
+            // output + image2 (both float32 arrays: float32 sum) - ipc_fwd(output) (float64)
+            const double r0_ = (double)(c.x + c.x) - a0, r1_ = (double)(c.y + c.y) - a1;
+            const double r2_ = (double)(c.z + c.z) - a2, r3_ = (double)(c.w + c.w) - a3;
+            o[(2 * h) * RW + col] = C.xact ? d2{r0_, r1_} : d2{0.0, 0.0};
+            o[(2 * h + 1) * RW + col] = C.xact ? d2{r2_, r3_} : d2{0.0, 0.0};
+        }
+    } else if (in_range(row, r0 - 1, r1 + 1)) {
+#pragma unroll
+        for (int j = 0; j < G / 2; ++j) o[j * RW + col] = d2{0.0, 0.0};
+    }
+}
+#undef RIP_TAP64
+
 // stage c : row s-6 (IPC pass 2, /gain; ramp fit, jump flags, DQ propagation; dark, error split, flat/area; stores)
 struct NoHook {
     RIP_HD void operator()() const {}
@@ -881,67 +976,15 @@ struct NoHook {
 // `reload` runs once per call, after the ramp fit (the register peak of the stage), when the staged record R.kc /
 // R.area* lives on only in a few locals: role Y of v3 issues the loads of the NEXT row there, so that they fly during
 // the epilogue and the wait at the step barrier instead of being consumed right after their issue.
-template <int G, int P, typename Hook = NoHook>
-RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G>& sm, const Regs<G, P>& R, const StepCtx& C,
-                    Hook reload = Hook()) {
-    constexpr int H = G / 4;
-    const int n = C.n, nb = 4, na = n - 8, tid = C.tid, col = C.col, x = C.x, r0 = C.r0, r1 = C.r1;
-    const unsigned (&o5)[5] = C.o5;
+// everything of stage c behind the IPC correction: ramp fit, flags, dark / error split / flat, stores
+template <int G, int P, class SM, typename Hook>
+RIP_HD void stage_c_tail(const Args& A, const RampPlanDev& pl, const FastTab& ft, SM& sm, const StepCtx& C, const f2 (&q)[G / 2],
+                         const uint32_t fl, const uint32_t nlc, const float gval, const float readv, const float dsl, const float flat,
+                         const uint32_t sdq, const float area32, const double area64, const unsigned p, const bool active, Hook reload) {
+    const int n = C.n, nb = 4, na = n - 8, x = C.x;
     const uint32_t allg = (1u << G) - 1u;
     const unsigned npl = (unsigned)n * (unsigned)n;
     const int row = C.s - 6;
-    const bool out_col = (tid >= 4 || C.tile == 0) && tid < TW - 4 && C.xin;
-    const bool c_on = in_range(row, r0, r1) && out_col;
-    if (!c_on) {
-        reload();
-        return;
-    }
-    const unsigned p = R.orow - 6u * (unsigned)n + (unsigned)x;
-    const bool active = C.xact && in_range(row, nb, n - nb);
-    const uint32_t fl = sm.flg(RIP_O5(-6))[tid];
-    const uint32_t nlc = sm.nlc(RIP_O5(-6))[tid];
-    const float gval = R.kc[2].y, readv = R.kc[2].z, dsl = R.kc[2].w, flat = R.kc[3].x;
-    const uint32_t sdq = f_as_u(R.kc[3].y);
-    const float area32 = R.area32;
-    const double area64 = R.area64;
-    f2 q[G / 2];
-    if (active) {
-        const float k[9] = {R.kc[0].x, R.kc[0].y, R.kc[0].z, R.kc[0].w, R.kc[1].x, R.kc[1].y, R.kc[1].z, R.kc[1].w, R.kc[2].x};
-        SharedDiv sd;
-        sd.init(gval);
-        const f4* om = sm.O1(row - 1);
-        const f4* o0 = sm.O1(row);
-        const f4* op = sm.O1(row + 1);
-        const f4* dd = sm.D(RIP_O5(-6));
-        f2 t[G / 2];
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
-            f2 lo, hi;
-            stencil9(om + h * RW, o0 + h * RW, op + h * RW, col, k, A.negzero, lo, hi);
-            const f4 oc = o0[h * RW + col], dc = dd[h * RW + col];
-            t[2 * h] = sub2p(add2p(f2{oc.x, oc.y}, f2{dc.x, dc.y}), lo);  // (output + image2) - ipc_fwd(output)
-            t[2 * h + 1] = sub2p(add2p(f2{oc.z, oc.w}, f2{dc.z, dc.w}), hi);
-        }
-        bool slow = !sd.ok;
-        if (!slow) {
-            f2 chk = f2{0.f, 0.f};
-#pragma unroll
-            for (int j = 0; j < G / 2; ++j) { q[j] = sd.div2(t[j]); chk = add2p(chk, q[j]); }
-            const float tt = chk.x + chk.y;
-            slow = !(tt == tt);  // a NaN from the correction steps (infinite numerator) -> true division
-        }
-        if (slow) {
-#pragma unroll
-            for (int j = 0; j < G / 2; ++j) q[j] = f2{t[j].x / gval, t[j].y / gval};
-        }
-        if (A.lincube) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) A.lincube[(unsigned)g * npl + p] = (g & 1) ? q[g >> 1].y : q[g >> 1].x;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < G / 2; ++j) q[j] = f2{0.f, 0.f};  // unused: every output of a non-active pixel is flag-only
-    }
     GroupFlags gf;
     gf.sat = fl & 0xffffu;
     gf.adf = fl >> 16;
@@ -1004,9 +1047,149 @@ RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, Sme
     }
 }
 
+
+template <int G, int P, class SM, typename Hook = NoHook>
+RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, SM& sm, const Regs<G, P>& R, const StepCtx& C,
+                    Hook reload = Hook()) {
+    constexpr int H = G / 4;
+    const int n = C.n, nb = 4, na = n - 8, tid = C.tid, col = C.col, x = C.x, r0 = C.r0, r1 = C.r1;
+    const unsigned (&o5)[5] = C.o5;
+    const uint32_t allg = (1u << G) - 1u;
+    const unsigned npl = (unsigned)n * (unsigned)n;
+    const int row = C.s - 6;
+    const bool out_col = (tid >= 4 || C.tile == 0) && tid < TW - 4 && C.xin;
+    const bool c_on = in_range(row, r0, r1) && out_col;
+    if (!c_on) {
+        reload();
+        return;
+    }
+    const unsigned p = R.orow - 6u * (unsigned)n + (unsigned)x;
+    const bool active = C.xact && in_range(row, nb, n - nb);
+    const uint32_t fl = sm.flg(RIP_O5(-6))[tid];
+    const uint32_t nlc = sm.nlc(RIP_O5(-6))[tid];
+    const float gval = R.kc[2].y, readv = R.kc[2].z, dsl = R.kc[2].w, flat = R.kc[3].x;
+    const uint32_t sdq = f_as_u(R.kc[3].y);
+    const float area32 = R.area32;
+    const double area64 = R.area64;
+    f2 q[G / 2];
+    if (active) {
+        const float k[9] = {R.kc[0].x, R.kc[0].y, R.kc[0].z, R.kc[0].w, R.kc[1].x, R.kc[1].y, R.kc[1].z, R.kc[1].w, R.kc[2].x};
+        SharedDiv sd;
+        sd.init(gval);
+        const f4* om = sm.O1(row - 1);
+        const f4* o0 = sm.O1(row);
+        const f4* op = sm.O1(row + 1);
+        const f4* dd = sm.D(RIP_O5(-6));
+        f2 t[G / 2];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            f2 lo, hi;
+            stencil9(om + h * RW, o0 + h * RW, op + h * RW, col, k, A.negzero, lo, hi);
+            const f4 oc = o0[h * RW + col], dc = dd[h * RW + col];
+            t[2 * h] = sub2p(add2p(f2{oc.x, oc.y}, f2{dc.x, dc.y}), lo);  // (output + image2) - ipc_fwd(output)
+            t[2 * h + 1] = sub2p(add2p(f2{oc.z, oc.w}, f2{dc.z, dc.w}), hi);
+        }
+        bool slow = !sd.ok;
+        if (!slow) {
+            f2 chk = f2{0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < G / 2; ++j) { q[j] = sd.div2(t[j]); chk = add2p(chk, q[j]); }
+            const float tt = chk.x + chk.y;
+            slow = !(tt == tt);  // a NaN from the correction steps (infinite numerator) -> true division
+        }
+        if (slow) {
+#pragma unroll
+            for (int j = 0; j < G / 2; ++j) q[j] = f2{t[j].x / gval, t[j].y / gval};
+        }
+        if (A.lincube) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) A.lincube[(unsigned)g * npl + p] = (g & 1) ? q[g >> 1].y : q[g >> 1].x;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < G / 2; ++j) q[j] = f2{0.f, 0.f};  // unused: every output of a non-active pixel is flag-only
+    }
+    stage_c_tail<G, P>(A, pl, ft, sm, C, q, fl, nlc, gval, readv, dsl, flat, sdq, area32, area64, p, active, reload);
+}
+
+// stage c with float64 taps (K64): IPC pass 2 and the division by the gain in float64, the float32 store of the
+// reference's `data[j] = ...` (utils/ipc_linearity.py:185-186), then the common tail.
+template <int G, int P, class SM, typename Hook = NoHook>
+RIP_HD void stage_c64(const Args& A, const RampPlanDev& pl, const FastTab& ft, SM& sm, const Regs<G, P>& R, const StepCtx& C,
+                      Hook reload = Hook()) {
+    constexpr int H = G / 4;
+    const int n = C.n, nb = 4, tid = C.tid, col = C.col, x = C.x, r0 = C.r0, r1 = C.r1;
+    const unsigned (&o5)[5] = C.o5;
+    const unsigned npl = (unsigned)n * (unsigned)n;
+    const int row = C.s - 6;
+    const bool out_col = (tid >= 4 || C.tile == 0) && tid < TW - 4 && C.xin;
+    const bool c_on = in_range(row, r0, r1) && out_col;
+    if (!c_on) {
+        reload();
+        return;
+    }
+    const unsigned p = R.orow - 6u * (unsigned)n + (unsigned)x;
+    const bool active = C.xact && in_range(row, nb, n - nb);
+    const uint32_t fl = sm.flg(RIP_O5(-6))[tid];
+    const uint32_t nlc = sm.nlc(RIP_O5(-6))[tid];
+    // record: words 0..17 taps (doubles), 18 gain, 19 read, 20 dark slope, 21 flat, 22 static dq
+    const float gval = R.kc64[4].z, readv = R.kc64[4].w, dsl = R.kc64[5].x, flat = R.kc64[5].y;
+    const uint32_t sdq = f_as_u(R.kc64[5].z);
+    const float area32 = R.area32;
+    const double area64 = R.area64;
+    f2 q[G / 2];
+    if (active) {
+        double k[9];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            k[2 * t] = f2_as_double(R.kc64[t].x, R.kc64[t].y);
+            k[2 * t + 1] = f2_as_double(R.kc64[t].z, R.kc64[t].w);
+        }
+        k[8] = f2_as_double(R.kc64[4].x, R.kc64[4].y);
+        const d2* om = sm.O1d(row - 1);
+        const d2* o0 = sm.O1d(row);
+        const d2* op = sm.O1d(row + 1);
+        const f4* dd = sm.D(RIP_O5(-6));
+        const double gd = (double)gval;
+#pragma unroll
+        for (int j = 0; j < G / 2; ++j) {
+            const d2 c = o0[j * RW + col];
+            double a0 = c.x * k[0], a1 = c.y * k[0];
+#define RIP_TAPD(V, Q)              \
+    {                               \
+        const d2 t = (V);           \
+        a0 = a0 + t.x * k[Q];       \
+        a1 = a1 + t.y * k[Q];       \
+    }
+            RIP_TAPD(om[j * RW + col], 1)
+            RIP_TAPD(op[j * RW + col], 2)
+            RIP_TAPD(o0[j * RW + col - 1], 3)
+            RIP_TAPD(o0[j * RW + col + 1], 4)
+            RIP_TAPD(om[j * RW + col - 1], 5)
+            RIP_TAPD(om[j * RW + col + 1], 6)
+            RIP_TAPD(op[j * RW + col - 1], 7)
+            RIP_TAPD(op[j * RW + col + 1], 8)
+#undef RIP_TAPD
+            const f4 dc = dd[(j >> 1) * RW + col];
+            const double dx = (double)((j & 1) ? dc.z : dc.x), dy = (double)((j & 1) ? dc.w : dc.y);
+            const double o2x = (c.x + dx) - a0, o2y = (c.y + dy) - a1;  // (output + image2) - ipc_fwd(output)
+            q[j] = f2{(float)(o2x / gd), (float)(o2y / gd)};
+        }
+        if (A.lincube) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) A.lincube[(unsigned)g * npl + p] = (g & 1) ? q[g >> 1].y : q[g >> 1].x;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < G / 2; ++j) q[j] = f2{0.f, 0.f};
+    }
+    (void)H;
+    stage_c_tail<G, P>(A, pl, ft, sm, C, q, fl, nlc, gval, readv, dsl, flat, sdq, area32, area64, p, active, reload);
+}
+
 // stage a0 : row s (raw -> cumulative saturation / A-D floor bits)
-template <int G, int P>
-RIP_HD void stage_a0(const Args& A, Smem<G>& sm, const StepCtx& C) {
+template <int G, int P, class SM>
+RIP_HD void stage_a0(const Args& A, SM& sm, const StepCtx& C) {
     const int n = C.n, tid = C.tid, col = C.col, r0 = C.r0, r1 = C.r1;
     const unsigned (&o5)[5] = C.o5;
     const int row = C.s;
@@ -1042,8 +1225,8 @@ RIP_HD void stage_a0(const Args& A, Smem<G>& sm, const StepCtx& C) {
 // so one barrier per step suffices and the stages may run in any order.  Order and load placement (see Regs):
 //     [kb <- kbn: the one scoreboard wait]  [cp.async row s+2; Lb(next)]  a1  c  [Lc(next), L1(next)]  b  a0  barrier
 // o5s = (s mod RING) * ROW5, the byte offset of row s's ring5 slot, carried by the caller (next_o5).
-template <int G, int P>
-RIP_HD void step(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G>& sm, Regs<G, P>& R, const int tid,
+template <int G, int P, bool K64 = false>
+RIP_HD void step(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G, K64>& sm, Regs<G, P>& R, const int tid,
                  const int tile, const int r0, const int r1, const int s, const unsigned o5s) {
     StepCtx C;
     C.n = A.n; C.tid = tid; C.tile = tile; C.r0 = r0; C.r1 = r1; C.s = s;
@@ -1058,6 +1241,22 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G
 
     // The one scoreboard wait of the step: `dep` is zero at run time (Args::pad_), but ptxas cannot know, so the loads
     // of load_bn -- and with them everything below -- are ordered after the arrival of all loads in flight.
+    if (K64) {
+        const unsigned dep = f_as_u(R.kc64[0].x) & (unsigned)A.pad_;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) R.kbd[t] = R.kbnd[t];
+        row_async<G, P>(A, sm, R, s + 2, 2, RIP_O5(2), tile, tid, r0 - 3, r1 + 3);
+        load_bn64<G, P>(A, R, s - 3, tile, tid, dep);
+        stage_a1<G, P>(A, sm, R, C);
+        stage_c64<G, P>(A, pl, ft, sm, R, C);
+        load_c64<G, P>(A, R, s - 5, tile, tid, C.x, C.xin);
+        load_a1<G, P>(A, R, s - 1, tile, tid);
+        stage_b64<G, P>(A, sm, R, C);
+        stage_a0<G, P>(A, sm, C);
+        R.orow += (unsigned)A.n;
+        cp_async_wait<1>();
+        return;
+    }
     const unsigned dep = f_as_u(R.kc[0].x) & (unsigned)A.pad_;
     R.kb[0] = R.kbn[0]; R.kb[1] = R.kbn[1]; R.kb8 = R.kbn8;
     row_async<G, P>(A, sm, R, s + 2, 2, RIP_O5(2), tile, tid, r0 - 3, r1 + 3);
@@ -1075,8 +1274,8 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G
 }
 
 // prologue: offsets, the cp.async rows of the first two steps, the records the first step consumes, ring pads
-template <int G, int P>
-RIP_HD void prologue(const Args& A, Smem<G>& sm, Regs<G, P>& R, int tid, int tile, int r0, int r1) {
+template <int G, int P, bool K64 = false>
+RIP_HD void prologue(const Args& A, Smem<G, K64>& sm, Regs<G, P>& R, int tid, int tile, int r0, int r1) {
     const int x = tile * TS + tid;
     const bool xin = x < A.n;
     const int s0 = r0 - 3;
@@ -1085,14 +1284,19 @@ RIP_HD void prologue(const Args& A, Smem<G>& sm, Regs<G, P>& R, int tid, int til
     R.orow = (unsigned)(s0 * A.n);  // (mod 2^32 for s0 < 0: only ever used after adding back a non-negative row offset)
     row_async<G, P>(A, sm, R, s0, 0, o5s, tile, tid, r0 - 3, r1 + 3);
     row_async<G, P>(A, sm, R, s0 + 1, 1, wrap5(o5s + RB, RING_B), tile, tid, r0 - 3, r1 + 3);
-    load_c<G, P>(A, R, s0 - 6, tile, tid, x, xin);
+    if (K64) {
+        load_c64<G, P>(A, R, s0 - 6, tile, tid, x, xin);
+        load_bn64<G, P>(A, R, s0 - 4, tile, tid, 0u);
+    } else {
+        load_c<G, P>(A, R, s0 - 6, tile, tid, x, xin);
+        load_bn<G, P>(A, R, s0 - 4, tile, tid, 0u);
+    }
     load_a1<G, P>(A, R, s0 - 2, tile, tid);
-    load_bn<G, P>(A, R, s0 - 4, tile, tid, 0u);
     // ring pads and the slots stage a1 / b read before anything was written there
     // (D of every ring5 slot and the whole ring4; never the cp.async targets)
     for (int k = 0; k < RING; ++k)
         for (int i = tid; i < Smem<G>::H * RW; i += TW) sm.D((unsigned)k * RB)[i] = f4{0.f, 0.f, 0.f, 0.f};
-    for (int i = tid; i < O_DEPTH * Smem<G>::ROW4 / 16; i += TW) ((f4*)sm.r4)[i] = f4{0.f, 0.f, 0.f, 0.f};
+    for (int i = tid; i < O_DEPTH * Smem<G, K64>::ROW4 / 16; i += TW) ((f4*)sm.r4)[i] = f4{0.f, 0.f, 0.f, 0.f};
     cp_async_wait<0>();
 }
 
@@ -1489,6 +1693,35 @@ RIP_HD float recK_word(const PackSrc& S, int row, int x, int w) {
     if (w == 11) return S.dslope[p];
     if (w == 12) return S.flat[p];
     if (w == 13) return u_as_f(S.sdq[p]);
+    return 0.0f;
+}
+
+// word w of the float64-tap record (K64): 0..17 the 9 gathered taps as doubles (low word first), 18 gain, 19 read,
+// 20 dark slope (IPC corrected), 21 flat, 22 static dq bits, 23 zero.  S.ipc then points at float64 data.
+RIP_HD float recK64_word(const PackSrc& S, int row, int x, int w) {
+    if (x >= S.n || row < 0 || row >= S.n) return 0.0f;
+    const long p = (long)row * S.n + x;
+    const int na = S.n - 2 * S.nb;
+    if (w < 18) {
+        const int t = w >> 1;
+        const int DY[9] = {0, 1, -1, 0, 0, 1, 1, -1, -1};
+        const int DX[9] = {0, 0, 0, 1, -1, 1, -1, 1, -1};
+        const int ya = row - S.nb, xa = x - S.nb;
+        double v = 0.0;
+        if (ya >= 0 && ya < na && xa >= 0 && xa < na) {
+            const int ys = ya - DY[t], xs = xa - DX[t];
+            if (ys >= 0 && ys < na && xs >= 0 && xs < na)
+                v = ((const double*)S.ipc)[((long)((1 + DY[t]) * 3 + (1 + DX[t])) * na + ys) * na + xs];
+        }
+        float parts[2];
+        memcpy(parts, &v, 8);
+        return parts[w & 1];
+    }
+    if (w == 18) return S.gain[p];
+    if (w == 19) return S.read[p];
+    if (w == 20) return S.dslope[p];
+    if (w == 21) return S.flat[p];
+    if (w == 22) return u_as_f(S.sdq[p]);
     return 0.0f;
 }
 

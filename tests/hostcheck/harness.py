@@ -69,6 +69,8 @@ def lib():
         assert _h.hostcheck_sizeof_calargs() == C.sizeof(CalArgs)
         _h.hostcheck_cal_fused_v2.restype = C.c_int
         _h.hostcheck_cal_fused_v2.argtypes = [C.POINTER(V2Args), C.POINTER(PackSrc), C.POINTER(_lib.RampPlan)]
+        _h.hostcheck_cal_fused_v2k64.restype = C.c_int
+        _h.hostcheck_cal_fused_v2k64.argtypes = [C.POINTER(V2Args), C.POINTER(PackSrc), C.POINTER(_lib.RampPlan)]
         assert _h.hostcheck_sizeof_v2args() == C.sizeof(V2Args)
         assert _h.hostcheck_sizeof_packsrc() == C.sizeof(PackSrc)
         _h.hostcheck_shared_div.restype = C.c_long
@@ -216,7 +218,8 @@ def _run_v2(c, data_u16, amp33_u16, read_pattern, area, config, do_refpix, band_
     G, n, _ = data_u16.shape
     na = n - 8
     P = c["linearitylegendre"]["data"].shape[0]
-    assert c["gain"]["data"].dtype == np.float32 and c["ipc4d"]["data"].dtype == np.float32
+    k64 = c["ipc4d"]["data"].dtype == np.float64
+    assert c["gain"]["data"].dtype == np.float32
     S = PackSrc()
     S.n, S.nb, S.G, S.P = n, 4, G, P
     S.dark = p(c["dark"]["data"], np.float32)
@@ -229,7 +232,7 @@ def _run_v2(c, data_u16, amp33_u16, read_pattern, area, config, do_refpix, band_
     S.Sref = p(c["linearitylegendre"]["Sref"], np.float32)
     S.gain = p(c["gain"]["data"], np.float32)
     S.aux, S.sdq = p(aux), p(sdq)
-    S.ipc = p(c["ipc4d"]["data"], np.float32)
+    S.ipc = p(c["ipc4d"]["data"], np.float64 if k64 else np.float32)
     S.read = p(c["read"]["data"], np.float32)
     S.dslope, S.flat = p(dslope, np.float32), p(flat, np.float32)
     A = V2Args()
@@ -263,7 +266,7 @@ def _run_v2(c, data_u16, amp33_u16, read_pattern, area, config, do_refpix, band_
     if want_lin:
         out["ipc"] = np.full((G, n, n), np.nan, np.float32)
         A.lincube = p(out["ipc"])
-    rc = lib().hostcheck_cal_fused_v2(C.byref(A), C.byref(S), C.byref(plan))
+    rc = (lib().hostcheck_cal_fused_v2k64 if k64 else lib().hostcheck_cal_fused_v2)(C.byref(A), C.byref(S), C.byref(plan))
     assert rc == 0, "v2 host check: unsupported (G, P)"
     out["K"] = meta["K"]
     return out

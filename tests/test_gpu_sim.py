@@ -388,7 +388,7 @@ def test_smooth_mode_and_binning():
     b = sky.binkxk(img, 4, mask=mask)
     bref = np.mean(np.where(~mask, img, np.nan)[:1020, :1028].reshape(255, 4, 257, 4), axis=(1, 3))
     assert b.shape == bref.shape and np.array_equal(np.isnan(b), np.isnan(bref))
-    np.testing.assert_allclose(b, bref, rtol=3e-7, equal_nan=True)
+    np.testing.assert_allclose(b, bref, rtol=1e-6, equal_nan=True)
     arr = bref.astype(np.float32)
 
     def ref_smooth_mode(arr, pc=25.0, pksmooth=0.5, niter=3):

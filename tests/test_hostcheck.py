@@ -81,8 +81,11 @@ def test_band_check_helper_on_host():
 
 
 V2_CASES = [
-    # n, pattern, order, seed, config, band_rows, bright, refpix
+    # n, pattern, order, seed, config, band_rows, bright, refpix[, ipc4d dtype]
     (40, "README_PATTERN", 10, 12, {}, 16, 1.0, False),
+    (56, "README_PATTERN", 10, 16, {}, 7, 12.0, False, np.float64),   # float64 ipc4d: the K64 form of the kernel
+    (256, "README_PATTERN", 10, 28, {"SATURATION_BACKUP": 0}, 100, 8.0, True, np.float64),
+    (128, "README_PATTERN", 3, 29, {"EXCLUDE_FIRST": False}, 50, 4.0, True, np.float64),
     (56, "README_PATTERN", 10, 15, {}, 7, 12.0, False),
     (256, "README_PATTERN", 10, 21, {}, 32, 1.0, True),
     (256, "LONG16_PATTERN", 10, 22, {"EXCLUDE_FIRST": False, "SATURATION_BACKUP": 2}, 100, 4.0, True),
@@ -91,13 +94,14 @@ V2_CASES = [
 ]  # fmt: skip
 
 
-@pytest.mark.parametrize("case", V2_CASES, ids=[f"n{c[0]}_{c[1]}_s{c[3]}" for c in V2_CASES])
+@pytest.mark.parametrize("case", V2_CASES, ids=[f"n{c[0]}_{c[1]}_s{c[3]}" + ("_k64" if len(c) > 8 else "") for c in V2_CASES])
 def test_v2_kernel_source(case):
     """The throughput kernel (csrc/rip_v2_core.cuh: packed records, float4 rings, packed-pair arithmetic, shared
     reciprocal division, squared jump test) must reproduce the oracle bit for bit, like v1."""
-    n, rpname, po, seed, cfg, band, bright, refpix = case
+    n, rpname, po, seed, cfg, band, bright, refpix = case[:8]
+    kdt = case[8] if len(case) > 8 else np.float32
     rp = getattr(synth, rpname)
-    cal = synth.make_caldir(n=n, seed=seed, read_pattern=rp, p_order=po, gain_dtype=np.float32, ipc_dtype=np.float32,
+    cal = synth.make_caldir(n=n, seed=seed, read_pattern=rp, p_order=po, gain_dtype=np.float32, ipc_dtype=kdt,
                             sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
     data_u16, amp33_u16, _ = synth.make_l1(cal, rp, seed=seed + 1, n_sources=25 if n > 100 else 9, cr_frac=0.01,
                                            bright=bright)  # fmt: skip
