@@ -39,9 +39,10 @@ N_SIDE = 4096
 P_ORDER = 10
 
 
-def bytes_per_pixel(G, P):
-    """Algorithmic HBM bytes per pixel of the fused L1->L2 pass: B(G,P) = 10.0625 G + 4 P + 105."""
-    return 10.0625 * G + 4.0 * P + 105.0
+def bytes_per_pixel(G, P, k64=False):
+    """Algorithmic HBM bytes per pixel of the fused L1->L2 pass: B(G,P) = 10.0625 G + 4 P + 105; a float64
+    ipc4d (the dtype the DUMMY CALDIR builder writes) doubles the 36 B/px of the nine taps."""
+    return 10.0625 * G + 4.0 * P + 105.0 + (36.0 if k64 else 0.0)
 
 
 def measured_peak_gbs():
@@ -139,21 +140,22 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(inside), "source": self.mode}  # fmt: skip
 
 
-def make_inputs(n, read_pattern, n_exposures, seed=1000):
+def make_inputs(n, read_pattern, n_exposures, seed=1000, ipc_dtype=np.float32):
     """Synthetic CALDIR + exposures; cached under the temp dir so that repeated invocations on one box (plain run, ncu
     launch list, ncu full capture) do not regenerate them (~1 min of NumPy RNG at 4096^2)."""
     import pickle
 
     from romanimpreprocess_b200 import synth
 
-    cache = os.path.join(tempfile.gettempdir(), f"rip_bench_inputs_n{n}_G{len(read_pattern)}_e{n_exposures}_s{seed}.pkl")
+    cache = os.path.join(tempfile.gettempdir(), f"rip_bench_inputs_n{n}_G{len(read_pattern)}_e{n_exposures}_s{seed}"
+                         f"{'_k64' if ipc_dtype == np.float64 else ''}.pkl")
     if os.path.exists(cache):
         try:
             with open(cache, "rb") as f:
                 return pickle.load(f)
         except Exception:  # noqa: BLE001
             pass
-    res = _make_inputs(n, read_pattern, n_exposures, seed)
+    res = _make_inputs(n, read_pattern, n_exposures, seed, ipc_dtype)
     try:
         with open(cache + ".tmp", "wb") as f:
             pickle.dump(res, f, protocol=4)
@@ -163,11 +165,11 @@ def make_inputs(n, read_pattern, n_exposures, seed=1000):
     return res
 
 
-def _make_inputs(n, read_pattern, n_exposures, seed):
+def _make_inputs(n, read_pattern, n_exposures, seed, ipc_dtype=np.float32):
     from romanimpreprocess_b200 import synth
 
     cal = synth.make_caldir(n=n, seed=seed, read_pattern=read_pattern, p_order=P_ORDER, gain_dtype=np.float32,
-                            ipc_dtype=np.float32, sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
+                            ipc_dtype=ipc_dtype, sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
     data, amp33, _ = synth.make_l1(cal, read_pattern, seed=200, n_sources=25, cr_frac=1e-3, bright=3.0)
     rng = np.random.default_rng(seed + 1)
     exposures = [(data, amp33)]
@@ -308,7 +310,8 @@ def run_ours(args):
     rp = synth.README_PATTERN if args.groups == 8 else synth.LONG16_PATTERN
     G, n = len(rp), args.n
     n_exp = max(2, args.exposures)
-    cal, exposures, area = make_inputs(n, rp, n_exp, seed=1000 + rank)
+    k64 = args.ipc_dtype == "f64"
+    cal, exposures, area = make_inputs(n, rp, n_exp, seed=1000 + rank, ipc_dtype=np.float64 if k64 else np.float32)
     cfg = {"SLICEOUT": True}
     cd = gci.CalDir(cal, device=local)
     dplan = gci.DevicePlan(cd, rp, synth.FRAME_TIME, cfg, do_refpix=True, area_dtype=np.float32,
@@ -439,7 +442,7 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        algo_bytes = bytes_per_pixel(G, P_ORDER + 1) * n * n
+        algo_bytes = bytes_per_pixel(G, P_ORDER + 1, k64) * n * n
         fused_avg_ms = fused_ms.value / max(fused_n.value, 1)
         achieved = algo_bytes / (fused_avg_ms * 1e-3) / 1e9
         traffic = None
@@ -447,7 +450,7 @@ def run_ours(args):
         if os.path.exists(tpath):
             try:
                 with open(tpath) as f:
-                    traffic = json.load(f).get(f"G{G}_P{P_ORDER + 1}_n{n}")
+                    traffic = json.load(f).get(f"G{G}_P{P_ORDER + 1}_n{n}" + ("_k64" if k64 else ""))
             except Exception:  # noqa: BLE001
                 traffic = None
         line = {
@@ -456,14 +459,14 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": f"fused L1->L2 (gen_cal_image chain), one {n}^2 x {G}-resultant SCA per GPU per step, "
-                            f"Legendre order {P_ORDER} (P={P_ORDER + 1}), f32 CALDIR planes, refpix + IPC + ramp fit + "
+                            f"Legendre order {P_ORDER} (P={P_ORDER + 1}), {'f32 CALDIR planes with float64 ipc4d (IPC stage in float64)' if k64 else 'f32 CALDIR planes'}, refpix + IPC + ramp fit + "
                             "jump/saturation flags + dark + flat/area + endslice (BASELINE metric config)",
                 "l2_policy": f"inputs larger than L2: each step streams {algo_bytes / 1e9:.2f} GB (126 MB L2) and "
                              f"{n_exp} distinct exposures are rotated",
                 "threads": args.threads or 128, "band_rows": args.band_rows or "auto (62 rows at 4096^2 on 148 SMs: 3.96 waves of 592 resident CTAs)", "parallelism": f"sca-sharded x{world}",
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "cal_fused_v2_kernel<8,11>" if args.groups == 8 else "cal_fused_v2_kernel<16,11>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": ("cal_fused_v2k64_kernel<8,11>" if k64 else "cal_fused_v2_kernel<8,11>") if args.groups == 8 else "cal_fused_v2_kernel<16,11>",
                          "kernel_ms": fused_avg_ms, "algorithmic_bytes": algo_bytes,
                          "step_share": fused_ms.value / ms_total},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -668,6 +671,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_SIDE, help="frame side (default 4096; smaller only for debugging)")
     ap.add_argument("--groups", type=int, default=8, choices=[8, 16])
+    ap.add_argument("--ipc-dtype", default="f32", choices=["f32", "f64"], help="dtype of the CALDIR's ipc4d (f64: the DUMMY builder's)")
     ap.add_argument("--exposures", type=int, default=3, help="distinct resident exposures rotated through the steps")
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--band-rows", type=int, default=0)

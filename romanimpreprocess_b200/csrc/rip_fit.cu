@@ -141,11 +141,7 @@ static void launch_cal_t(const CalArgs& A, int threads, cudaStream_t st) {
     typedef typename Promote<TIM, TK>::type TI;
     const size_t smem = CalSmem<GMAX, TIM, TI>::bytes(threads);
     auto kern = cal_fused_kernel<GMAX, PMAX, TG, TK>;
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        RIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (smem > 48 * 1024) configure_smem_once((const void*)kern, smem);
     const int tw = threads - 6;
     dim3 grid((A.n + tw - 1) / tw, (A.n + A.band_rows - 1) / A.band_rows);
     RIP_LAUNCH(kern, grid, threads, smem, st, A);

@@ -29,6 +29,7 @@ void launch_cal_fused_v2k64(const v2::Args& A, int G, int P, cudaStream_t st);
 int v2_default_band_rows(int device, int n, int G, int ctas_per_sm = 0);
 void launch_cal_fused_v3(const v2::Args& A, int G, int P, int variant, cudaStream_t st);
 void v2_plan_to_device(const rip_ramp_plan* plan, cudaStream_t st);
+void v3_plan_to_device(const rip_ramp_plan* plan, const void* fast_tab, cudaStream_t st);  // rip_v3.cu
 void launch_cal_fused_v2(const v2::Args& A, int G, int P, cudaStream_t st);
 void v2_pack(rip_caldir* h, int G, cudaStream_t st);
 v2::f4* v2_rec1_row0(rip_caldir* h, int G);  // record of detector row 0 inside the padded allocations

@@ -1,6 +1,9 @@
 // Runtime: error slot, launch counter, memory helpers of the C ABI (include/rip_b200.h).
 #include "rip_rt.h"
 
+#include <map>
+#include <mutex>
+
 namespace rip {
 static thread_local char g_err[1024] = "";
 std::atomic<long long> g_launches{0};
@@ -10,6 +13,19 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
+}
+
+void configure_smem_once(const void* fn, size_t smem, bool prefer_smem_carveout) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> done;  // largest size configured so far
+    int dev = 0;
+    RIP_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = done.find({dev, fn});
+    if (it != done.end() && it->second >= smem) return;
+    RIP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (prefer_smem_carveout) RIP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    done[{dev, fn}] = smem;
 }
 }  // namespace rip
 

@@ -137,4 +137,7 @@ struct DevRaw {
 // device plan cache (ramp plan in __constant__ memory + exact weights in global memory); defined in rip_fit.cu
 const double* plan_to_device(int device, const rip_ramp_plan* plan, const double* w_exact, cudaStream_t st);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (device, function): configure each pair once (rip_rt.cu)
+void configure_smem_once(const void* fn, size_t smem, bool prefer_smem_carveout = false);
+
 }  // namespace rip

@@ -247,12 +247,8 @@ static void noise_1f_frames_impl(int nside, int nframes, uint64_t seed, unsigned
     const int L = nside / 4, logL = ilog2_exact(L);
     RIP_REQUIRE(logL >= 3 && L <= 1024 && nside == 4 * L, "noise_1f_frames: frame side %d must be a power of two in 32..4096", nside);
     const size_t smem = ((size_t)FCOL * L + L / 2) * sizeof(float2);
-    static bool attr_done = false;
-    if (!attr_done) {
-        RIP_CUDA(cudaFuncSetAttribute(fft1f_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FCOL * 1024 + 512) * 8));
-        RIP_CUDA(cudaFuncSetAttribute(fft1f_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FCOL * 1024 + 512) * 8));
-        attr_done = true;
-    }
+    configure_smem_once((const void*)fft1f_pass1_kernel, (FCOL * 1024 + 512) * 8);
+    configure_smem_once((const void*)fft1f_pass2_kernel, (FCOL * 1024 + 512) * 8);
     const long half = (long)L * L / 2;
     RIP_CUDA(cudaMemsetAsync(d_sums, 0, (size_t)nframes * sizeof(double), st));
     dim3 grid(L / FCOL, nframes);

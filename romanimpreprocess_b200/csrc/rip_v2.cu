@@ -79,13 +79,6 @@ __global__ void __launch_bounds__(TW, MINB) cal_fused_v2_kernel(const Args A) {
     }
 }
 
-// v3: role-split CTA (rip_v2_core.cuh, "v3"): 256 threads, X = warps 0-3, Y = warps 4-7, TMA-fed raw ring
-template <int G, int P, bool BX, int MINB, int XR, int YR>
-__global__ void __launch_bounds__(2 * TW, MINB) cal_fused_v3_kernel(const Args A) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    v3_body<G, P, BX, XR, YR>(A, c_plan_v2, c_fast_v2, smem_raw);
-}
-
 // float64 ipc4d (K64): same march, IPC stages in float64 (3 CTAs/SM: the O1 ring holds doubles)
 template <int G, int P, int MINB>
 __global__ void __launch_bounds__(TW, MINB) cal_fused_v2k64_kernel(const Args A) {
@@ -106,51 +99,12 @@ __global__ void __launch_bounds__(TW, MINB) cal_fused_v2k64_kernel(const Args A)
     }
 }
 
-template <int G, int P, int MINB>
-__global__ void __launch_bounds__(TW, MINB) cal_fused_v2t_kernel(const Args A) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    v2t_body<G, P>(A, c_plan_v2, c_fast_v2, smem_raw);
-}
-
-// cudaFuncSetAttribute is per (device, function): remember what has been configured where
-static void configure_once(const void* fn, size_t smem) {
-    static std::mutex mu;
-    static std::set<std::pair<int, const void*>> done;
-    int dev = 0;
-    RIP_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lk(mu);
-    if (done.count({dev, fn})) return;
-    RIP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RIP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    done.insert({dev, fn});
-}
-
-template <int G, int P, bool BX>
-static void launch_v3(const Args& A, cudaStream_t st) {
-    constexpr int MINB = (G <= 8) ? 3 : 2;
-    const size_t smem = v3_smem_bytes<G>(BX);
-    // launch allocation 80 (G <= 8: 3 CTAs/SM) or 128 (2 CTAs/SM) registers per thread, re-split between the roles
-    constexpr int XR = BX ? ((G <= 8) ? 72 : 112) : ((G <= 8) ? 64 : 96);
-    constexpr int YR = BX ? ((G <= 8) ? 88 : 144) : ((G <= 8) ? 96 : 160);
-    auto kern = cal_fused_v3_kernel<G, P, BX, MINB, XR, YR>;
-    configure_once((const void*)kern, smem);
-    dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
-    RIP_LAUNCH(kern, grid, 2 * TW, smem, st, A);
-}
+static void configure_once(const void* fn, size_t smem) { configure_smem_once(fn, smem, true); }
 
 template <int G, int P>
 static void launch_k64(const Args& A, cudaStream_t st) {
     const size_t smem = Smem<G, true>::bytes();
     auto kern = cal_fused_v2k64_kernel<G, P, 3>;
-    configure_once((const void*)kern, smem);
-    dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
-    RIP_LAUNCH(kern, grid, TW, smem, st, A);
-}
-
-template <int G, int P>
-static void launch_v2t(const Args& A, cudaStream_t st) {
-    const size_t smem = Smem<G>::bytes();
-    auto kern = cal_fused_v2t_kernel<G, P, (G <= 8) ? 4 : 2>;
     configure_once((const void*)kern, smem);
     dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
     RIP_LAUNCH(kern, grid, TW, smem, st, A);
@@ -203,16 +157,6 @@ void launch_cal_fused_v2k64(const v2::Args& A, int G, int P, cudaStream_t st) {
     else throw Error("cal_fused v2 (float64 ipc4d): unsupported (G, P)");
 }
 
-// variant: 0 = v2 (one role, 128 threads), 1 = v3 (X: a0 a1 | Y: b c), 2 = v3 (X: a0 a1 b | Y: c)
-void launch_cal_fused_v3(const v2::Args& A, int G, int P, int variant, cudaStream_t st) {
-    const bool bx = variant == 2;
-#define RIP_V3(GG, PP) \
-    if (G == GG && P == PP) { if (variant == 3) v2::launch_v2t<GG, PP>(A, st); else if (bx) v2::launch_v3<GG, PP, true>(A, st); else v2::launch_v3<GG, PP, false>(A, st); return; }
-    RIP_V3(8, 11) RIP_V3(8, 4) RIP_V3(16, 11) RIP_V3(16, 4)
-#undef RIP_V3
-    throw Error("cal_fused v3: unsupported (G, P)");
-}
-
 void launch_cal_fused_v2(const v2::Args& A, int G, int P, cudaStream_t st) {
     if (G == 16 && P == 4) v2::launch_t<16, 4>(A, st);
     else if (G == 8 && P == 4) v2::launch_t<8, 4>(A, st);
@@ -226,6 +170,7 @@ void v2_plan_to_device(const rip_ramp_plan* plan, cudaStream_t st) {
     // (the copy is taken from pageable memory at enqueue time, so the temporary may die here)
     const v2::FastTab ft = v2::make_fast_tab(*plan);
     RIP_CUDA(cudaMemcpyToSymbolAsync(c_fast_v2, &ft, sizeof ft, 0, cudaMemcpyHostToDevice, st));
+    v3_plan_to_device(plan, &ft, st);  // (the role-split variants live in their own translation unit: rip_v3.cu)
 }
 
 // record of detector row 0 inside the padded allocations

@@ -234,6 +234,9 @@ RIP_HD int mod_pos(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 RIP_HD bool in_range(int v, int lo, int hi) { return (unsigned)(v - lo) < (unsigned)(hi - lo); }
 RIP_HD int imax(int a, int b) { return a > b ? a : b; }
 RIP_HD int imin(int a, int b) { return a < b ? a : b; }
+// a record row the loaders may touch instead of `row`: rows outside [lo, hi) are loaded (unconditional loaders, see
+// below) but never used, so they are folded onto the nearest used row -- an L2 hit instead of HBM traffic
+RIP_HD int fold_row(int row, int lo, int hi) { return imin(imax(row, lo), hi - 1); }
 // byte offset of ring5 slot (f + k) mod 5 given o = f * ROW5: one add + one unsigned min (x - 5 ROW5 wraps above x when x < 5 ROW5)
 RIP_HD unsigned wrap5(unsigned x, unsigned ring_bytes) { const unsigned y = x - ring_bytes; return x < y ? x : y; }
 // byte offset of the ring5 slot of row s+DK, given o5[k] = offset of row s+k (DK is a compile-time constant)
@@ -261,6 +264,31 @@ RIP_HD void cp_async_wait() {
 #if defined(__CUDA_ARCH__)
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 #endif
+}
+
+// L2 prefetch of one contiguous block by the TMA engine (cp.async.bulk.prefetch.L2 = UBLKPF: one instruction, no
+// registers, no completion tracking).  The packed records of a (row, tile) are contiguous 16 KB (rec1) / 8 KB (recK)
+// blocks: one elected thread asks for the block about one march step before the loaders read it, so the loads that
+// follow hit L2 (~300 cycles) instead of waiting for HBM (measured before: 7 % of the warp samples on the step's one
+// scoreboard wait).  addr and bytes are multiples of 16.  The host build does nothing.
+RIP_HD void l2_prefetch_block(const void* addr, unsigned bytes) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(addr), "r"(bytes) : "memory");
+#else
+    (void)addr; (void)bytes;
+#endif
+}
+// records the loaders of step s+1 will read: rec1 of row s (load_a1 at the end of step s+1), recK of row s-2 (load_bn at
+// the top of step s+1; load_c re-reads that row two steps later, from L2).  KQW = float4 words per pixel of recK.
+template <int G, int P, int KQW>
+RIP_HD void prefetch_records(const Args& A, int s, int tile, int tid, int r0, int r1) {
+    if (tid == 0) {
+        constexpr int NQ1 = nq1(G, P);
+        if (in_range(s, r0 - 2, imin(r1 + 2, A.n)))
+            l2_prefetch_block(A.rec1 + ((long)s * A.ntile + tile) * (NQ1 * TW), (unsigned)(NQ1 * TW * 16));
+        if (in_range(s - 2, r0 - 1, imin(r1 + 1, A.n)))
+            l2_prefetch_block(A.recK + ((long)(s - 2) * A.ntile + tile) * (KQW * TW), (unsigned)(KQW * TW * 16));
+    }
 }
 
 // Everything stage a0 / a1 need of detector row `row` that is not a packed record -> ring slot `slot`:
@@ -1246,11 +1274,12 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G
 #pragma unroll
         for (int t = 0; t < 9; ++t) R.kbd[t] = R.kbnd[t];
         row_async<G, P>(A, sm, R, s + 2, 2, RIP_O5(2), tile, tid, r0 - 3, r1 + 3);
-        load_bn64<G, P>(A, R, s - 3, tile, tid, dep);
+        prefetch_records<G, P, KQ64>(A, s, tile, tid, r0, r1);
+        load_bn64<G, P>(A, R, fold_row(s - 3, r0 - 1, r1 + 1), tile, tid, dep);
         stage_a1<G, P>(A, sm, R, C);
         stage_c64<G, P>(A, pl, ft, sm, R, C);
-        load_c64<G, P>(A, R, s - 5, tile, tid, C.x, C.xin);
-        load_a1<G, P>(A, R, s - 1, tile, tid);
+        load_c64<G, P>(A, R, fold_row(s - 5, r0 - 1, r1 + 1), tile, tid, C.x, C.xin);
+        load_a1<G, P>(A, R, fold_row(s - 1, r0 - 2, r1 + 2), tile, tid);
         stage_b64<G, P>(A, sm, R, C);
         stage_a0<G, P>(A, sm, C);
         R.orow += (unsigned)A.n;
@@ -1260,12 +1289,13 @@ RIP_HD void step(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem<G
     const unsigned dep = f_as_u(R.kc[0].x) & (unsigned)A.pad_;
     R.kb[0] = R.kbn[0]; R.kb[1] = R.kbn[1]; R.kb8 = R.kbn8;
     row_async<G, P>(A, sm, R, s + 2, 2, RIP_O5(2), tile, tid, r0 - 3, r1 + 3);
-    load_bn<G, P>(A, R, s - 3, tile, tid, dep);
+    prefetch_records<G, P, KQ>(A, s, tile, tid, r0, r1);
+    load_bn<G, P>(A, R, fold_row(s - 3, r0 - 1, r1 + 1), tile, tid, dep);
 
     stage_a1<G, P>(A, sm, R, C);
     stage_c<G, P>(A, pl, ft, sm, R, C);
-    load_c<G, P>(A, R, s - 5, tile, tid, C.x, C.xin);
-    load_a1<G, P>(A, R, s - 1, tile, tid);
+    load_c<G, P>(A, R, fold_row(s - 5, r0 - 1, r1 + 1), tile, tid, C.x, C.xin);
+    load_a1<G, P>(A, R, fold_row(s - 1, r0 - 2, r1 + 2), tile, tid);
     stage_b<G, P>(A, sm, R, C);
     stage_a0<G, P>(A, sm, C);
 
@@ -1285,13 +1315,13 @@ RIP_HD void prologue(const Args& A, Smem<G, K64>& sm, Regs<G, P>& R, int tid, in
     row_async<G, P>(A, sm, R, s0, 0, o5s, tile, tid, r0 - 3, r1 + 3);
     row_async<G, P>(A, sm, R, s0 + 1, 1, wrap5(o5s + RB, RING_B), tile, tid, r0 - 3, r1 + 3);
     if (K64) {
-        load_c64<G, P>(A, R, s0 - 6, tile, tid, x, xin);
-        load_bn64<G, P>(A, R, s0 - 4, tile, tid, 0u);
+        load_c64<G, P>(A, R, fold_row(s0 - 6, r0 - 1, r1 + 1), tile, tid, x, xin);
+        load_bn64<G, P>(A, R, fold_row(s0 - 4, r0 - 1, r1 + 1), tile, tid, 0u);
     } else {
-        load_c<G, P>(A, R, s0 - 6, tile, tid, x, xin);
-        load_bn<G, P>(A, R, s0 - 4, tile, tid, 0u);
+        load_c<G, P>(A, R, fold_row(s0 - 6, r0 - 1, r1 + 1), tile, tid, x, xin);
+        load_bn<G, P>(A, R, fold_row(s0 - 4, r0 - 1, r1 + 1), tile, tid, 0u);
     }
-    load_a1<G, P>(A, R, s0 - 2, tile, tid);
+    load_a1<G, P>(A, R, fold_row(s0 - 2, r0 - 2, r1 + 2), tile, tid);
     // ring pads and the slots stage a1 / b read before anything was written there
     // (D of every ring5 slot and the whole ring4; never the cp.async targets)
     for (int k = 0; k < RING; ++k)
