@@ -249,6 +249,17 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------------------------
+def bench_wcs(n_active, k):
+    """A TAN-SIP WCS like the reference's test scene (tests/romanimpreprocess/test_workflow.py:62-83), dithered per exposure."""
+    from romanimpreprocess_b200.utils import coordutils
+
+    hdr = {"CTYPE1": "RA---TAN-SIP", "CTYPE2": "DEC--TAN-SIP", "CRPIX1": (n_active + 1) / 2.0, "CRPIX2": (n_active + 1) / 2.0,
+           "CD1_1": 3.0555555555555554e-05, "CD1_2": 0.0, "CD2_1": 0.0, "CD2_2": 3.0555555555555554e-05,
+           "CRVAL1": 37.0 + 0.01 * k, "CRVAL2": -20.0 + 0.005 * k, "LONPOLE": 215.0, "A_ORDER": 2, "A_0_2": 2.0e-6,
+           "A_1_1": -1.0e-6, "A_2_0": 3.0e-6, "B_ORDER": 2, "B_0_2": 1.4e-5, "B_1_1": -1.0e-5, "B_2_0": 3.0e-7}  # fmt: skip
+    return coordutils.FitsWCS(hdr)
+
+
 def copy_ceiling(torch, dist, lib, _lib, local, world, dev, h_in, h_area, h_out, d_raw, d_amp, d_area, d_outs, steps):
     """Copy-only microbenchmark on the e2e leg's own buffers: per step one exposure's inputs host->device on one stream
     and one exposure's outputs device->host on another, nothing else; all ranks run it at the same time (barrier before),
@@ -260,14 +271,14 @@ def copy_ceiling(torch, dist, lib, _lib, local, world, dev, h_in, h_area, h_out,
 
     def one(i):
         d, a = h_in[i % len(h_in)]
-        for host, devt in ((d, d_raw), (a, d_amp), (h_area, d_area)):
+        for host, devt in ((d, d_raw), (a, d_amp)) + (((h_area, d_area),) if h_area is not None else ()):
             _lib.check(lib.rip_copy_h2d(local, C.c_void_p(devt.data_ptr()), _lib.ptr(host), C.c_size_t(host.nbytes),
                                         C.c_void_p(s_in.cuda_stream)))  # fmt: skip
         for host, devt in pairs_out:
             _lib.check(lib.rip_copy_d2h(local, _lib.ptr(host), C.c_void_p(devt.data_ptr()), C.c_size_t(host.nbytes),
                                         C.c_void_p(s_out.cuda_stream)))  # fmt: skip
 
-    h2d = sum(x.nbytes for x in (h_in[0][0], h_in[0][1], h_area))
+    h2d = sum(x.nbytes for x in (h_in[0][0], h_in[0][1])) + (h_area.nbytes if h_area is not None else 0)
     d2h = sum(h.nbytes for h, _ in pairs_out)
     for i in range(2):
         one(i)
@@ -397,7 +408,12 @@ def run_ours(args):
 
     # copy-only ceiling of this box for exactly these buffers: the step's H2D bytes on one stream and its D2H bytes on
     # another, concurrently, no kernels -- what a perfect pipeline could reach (all ranks at once; max over ranks)
-    ceil = copy_ceiling(torch, dist, lib, _lib, local, world, dev, h_in, h_area, h_out, d_raw[0], d_amp[0], d_area,
+    # The pixel-area plane of an exposure is a function of its WCS (reference gen_cal_image.py:618-621): the end-to-end
+    # path uploads the ~1.7 kB of WCS coefficients and evaluates the plane on the device (rip_pipeline_set_area_wcs), as
+    # calibrateimage(config) does; --e2e-area-upload restores the 67 MB host plane per step of the earlier rounds.
+    up_area = args.e2e_area_upload
+    wcs_list = [bench_wcs(n - 8, k) for k in range(n_exp)]
+    ceil = copy_ceiling(torch, dist, lib, _lib, local, world, dev, h_in, h_area if up_area else None, h_out, d_raw[0], d_amp[0], d_area,
                         (o_slope, o_er, o_ep, o_pdq, o_end), steps=max(6, min(args.steps, 20)))
 
     # one set of pinned output buffers per slot in flight
@@ -412,7 +428,9 @@ def run_ours(args):
             if len(tickets) >= depth:
                 pipe.result(tickets.pop(0))  # the slot's host buffers are about to be reused
             d, a = h_in[(first + i) % n_exp]
-            tickets.append(pipe.submit(d, a, h_area, out=h_outs[(first + i) % depth]))
+            if not up_area:
+                pipe.set_area_wcs(wcs_list[(first + i) % n_exp], dtype=np.float32)
+            tickets.append(pipe.submit(d, a, h_area if up_area else None, out=h_outs[(first + i) % depth]))
         for t in tickets:
             pipe.result(t)
 
@@ -436,7 +454,7 @@ def run_ours(args):
                              dplan=dplan)  # fmt: skip
     e2e_sync = world * 3 / (time.perf_counter() - ts0)
     pipe.close()
-    h2d = int(exposures[0][0].nbytes + exposures[0][1].nbytes + area.nbytes)
+    h2d = int(exposures[0][0].nbytes + exposures[0][1].nbytes + (area.nbytes if up_area else wcs_list[0].pack().nbytes))
     d2h = int(sum(v.nbytes for v in h_out.values() if isinstance(v, np.ndarray)))
     checksum = int(h_out["pdq"].astype(np.uint64).sum() % (1 << 32))
 
@@ -472,7 +490,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps,
                     "api": f"gen_cal_image.Pipeline.submit/result -> rip_pipeline_* (pinned host buffers, {depth} exposures in "
-                           "flight: H2D | kernels | D2H on three streams)",
+                           "flight: H2D | kernels | D2H on three streams); "
+                           + ("AreaFactor plane uploaded per exposure" if up_area else
+                              "AreaFactor plane evaluated on the device from each exposure's FITS WCS (TAN-SIP), inside the timed region"),
                     "sync_api_value": e2e_sync,
                     "ceiling_value": ceil["sca_per_s"], "ceiling_gbs": ceil["gbs"], "ceiling_h2d_gbs": ceil["h2d_gbs"],
                     "ceiling_d2h_gbs": ceil["d2h_gbs"], "frac_of_ceiling": e2e_value / ceil["sca_per_s"],
@@ -678,6 +698,7 @@ def main():
     ap.add_argument("--cpu-tile", type=int, default=2048, help="side of the sub-frame the cpu_baseline times (2048: about 12 s of oracle work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (for ncu captures)")
+    ap.add_argument("--e2e-area-upload", action="store_true", help="e2e leg: upload the AreaFactor plane per exposure instead of evaluating it on the device from the WCS")
     ap.add_argument("--realizations", type=int, default=64, help="noise realisations (workload realizations)")
     ap.add_argument("--layers", type=int, default=8, help="noise layers per exposure (workload noiselayers)")
     ap.add_argument("--workload", default="l1l2", choices=["l1l2", "forward", "realizations", "noiselayers"],

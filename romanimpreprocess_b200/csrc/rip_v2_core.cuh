@@ -1508,11 +1508,12 @@ __device__ __forceinline__ void v2t_body(const Args& A, const RampPlanDev& pl, c
         R.kb[0] = R.kbn[0]; R.kb[1] = R.kbn[1]; R.kb8 = R.kbn8;
         if (tid < 32) tma_row<G>(A, sm, mbar, s + 2, (k5 + 2) % RING, RIP_O5(2), tile, r0 - 3, r1 + 3, tid);
         corr_async<G>(A, sm, s + 2, RIP_O5(2), tile, tid, r0 - 3, r1 + 3);
-        load_bn<G, P>(A, R, s - 3, tile, tid, dep);
+        prefetch_records<G, P, KQ>(A, s, tile, tid, r0, r1);
+        load_bn<G, P>(A, R, fold_row(s - 3, r0 - 1, r1 + 1), tile, tid, dep);
         stage_a1<G, P>(A, sm, R, C);
         stage_c<G, P>(A, pl, ft, sm, R, C);
-        load_c<G, P>(A, R, s - 5, tile, tid, C.x, C.xin);
-        load_a1<G, P>(A, R, s - 1, tile, tid);
+        load_c<G, P>(A, R, fold_row(s - 5, r0 - 1, r1 + 1), tile, tid, C.x, C.xin);
+        load_a1<G, P>(A, R, fold_row(s - 1, r0 - 2, r1 + 2), tile, tid);
         stage_b<G, P>(A, sm, R, C);
         if (in_range(s, imax(r0 - 3, 0), imin(r1 + 3, A.n))) {
             tma::wait_parity(mbar + k5, (nwait / RING) & 1u);
@@ -1557,8 +1558,9 @@ __device__ __forceinline__ void v3_role_x(const Args& A, Smem<G>& sm, unsigned c
             if (BX && tid == G + 1) tma_taps<G>(A, smem_raw, mbar, s - 4, 0, tile, r0, r1);
         }
         corr_async<G>(A, sm, s + 2, RIP_O5(2), tile, tid, r0 - 3, r1 + 3);
+        prefetch_records<G, P, KQ>(A, s, tile, tid, r0, r1);
         stage_a1<G, P>(A, sm, R, C);
-        load_a1<G, P>(A, R, s - 1, tile, tid);
+        load_a1<G, P>(A, R, fold_row(s - 1, r0 - 2, r1 + 2), tile, tid);
         if (BX) {
             if (v3_b_row<G>(s - 4, r0, r1, A.n)) {
                 tma::wait_parity(mbar + RING, nb_wait & 1u);
@@ -1609,7 +1611,7 @@ __device__ __forceinline__ void v3_role_y(const Args& A, const RampPlanDev& pl, 
         StepCtx C;
         make_ctx(C, A, tid, tile, r0, r1, s, o5s, RB, RING_B);
         if (!BX && tid == 0) tma_taps<G>(A, smem_raw, mbar, s - 3, (s - 3) & 1, tile, r0, r1);  // next step's row
-        stage_c<G, P>(A, pl, ft, sm, R, C, ReloadC<G, P>{A, R, s - 5, tile, tid, C.x, C.xin});
+        stage_c<G, P>(A, pl, ft, sm, R, C, ReloadC<G, P>{A, R, fold_row(s - 5, r0 - 1, r1 + 1), tile, tid, C.x, C.xin});
         if (!BX) {
             if (v3_b_row<G>(s - 4, r0, r1, A.n)) {
                 tma::wait_parity(mbar + RING + ((s - 4) & 1), (nb_wait >> 1) & 1u);
