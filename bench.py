@@ -196,24 +196,49 @@ def _oracle_tile(args):
     data, amp33, _ = synth.make_l1(cal, rp, seed=seed + 1, n_sources=25, cr_frac=1e-3, bright=3.0)
     area = synth.make_area_factor(m, np.float32)
     c = {k: v["roman"] for k, v in cal.items()}
+    chain = orc.l1_to_l2
+    if _ref_available():  # the reference's own unmodified functions (oracle/_ref, see oracle/ref_chain.py)
+        from oracle import ref_chain
+
+        chain = ref_chain.l1_to_l2
     t = time.perf_counter()
-    orc.l1_to_l2(data, amp33, c, rp, synth.FRAME_TIME, area, {"SLICEOUT": True}, do_refpix=True)
+    chain(data, amp33, c, rp, synth.FRAME_TIME, area, {"SLICEOUT": True}, do_refpix=True)
     return time.perf_counter() - t
+
+
+def _ref_available():
+    try:
+        from oracle import ref_chain
+
+        return ref_chain.available()
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def _cpu_kind():
+    """(kind, description) of what the CPU legs execute."""
+    if _ref_available():
+        return "reference", ("the reference's own unmodified functions from oracle/_ref (ref_chain.l1_to_l2: multilin, correct_cube, "
+                             "construct_weights, ramp_fit + jump_detect, get_flat; the romancal/stcal steps and -- on sub-frames, whose "
+                             "size the reference's row/channel subtraction cannot take -- the reference-pixel loop from the oracle port)")
+    return "port", "oracle/rip_oracle.py l1_to_l2 (NumPy port of the reference chain)"
 
 
 def cpu_baseline_single(m=1024):
     """Oracle on one core on an m^2 sub-frame; returns the cpu_baseline object."""
     dt = _oracle_tile((m, 77))
     frac = (m * m) / float(N_SIDE * N_SIDE)
-    return {"value": frac / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"oracle/rip_oracle.py l1_to_l2 (NumPy port of the reference chain) on one {m}x{m} sub-frame "
+    kind, what = _cpu_kind()
+    return {"value": frac / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"{what} on one {m}x{m} sub-frame "
                       f"(1/{int(round(1 / frac))} of an SCA, same G=8, P=11, refpix+IPC+jump flags), {dt:.1f} s, "
                       "scaled by pixel count"}  # fmt: skip
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm (oracle port; the Python reference cannot travel to the GPU box and
-    needs asdf/romancal) on all host cores, one independent sub-frame per process per step."""
+    """--impl reference: the reference's own functions (oracle/_ref; the oracle port if that directory is absent -- the
+    reference's calibrateimage itself needs asdf/romancal/stcal, which this image lacks) on all host cores, one
+    independent sub-frame per process per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -237,8 +262,8 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "gen_cal_image L1->L2, one 4096^2 x 8-resultant SCA, P=11, CPU reference path "
                                "(BASELINE configs[0])", "step": f"{cores} independent {m}x{m} sub-frames"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"per step: {cores} processes x one {m}x{m} sub-frame through oracle.l1_to_l2, "
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": _cpu_kind()[0],
+                         "sample": f"per step: {cores} processes x one {m}x{m} sub-frame through {_cpu_kind()[1]}, "
                                    "scaled by pixel count"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -631,6 +656,140 @@ def run_realizations(args):
         dist.destroy_process_group()
 
 
+def run_exposure18(args):
+    """Secondary workload (BASELINE configs[3]): whole 18-SCA WFI exposures through L1->L2, the (exposure, SCA) items
+    dealt to the ranks by sharding.assign_items_balanced (reference: one Slurm task per SCA,
+    runs/summer2025run/OpenUniverse_to_L1L2.job:4), every rank holding only its own SCAs' CALDIRs (all 18 on one GPU,
+    2-4 per GPU on eight).  `--exposures18` exposures in total: strong scaling.  No collective on the data path."""
+    import torch
+    import torch.distributed as dist
+
+    from romanimpreprocess_b200 import _lib, sharding, synth
+    from romanimpreprocess_b200.L1_to_L2 import exposure_driver as xd
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    rp = synth.README_PATTERN
+    n, G, NSCA, E = args.n, len(synth.README_PATTERN), 18, args.exposures18
+    cal, exposures, area = make_inputs(n, rp, 2, seed=1000)  # one synthetic CALDIR content, uploaded once per SCA
+    cfg = {"SLICEOUT": True}
+    items = [(e, sca) for e in range(E) for sca in range(1, NSCA + 1)]
+    t_setup = time.perf_counter()
+    drv = xd.ExposureCalibrator({sca: cal for sca in range(1, NSCA + 1)}, items, rp, synth.FRAME_TIME, cfg, rank=rank,
+                                world=world, device=local, depth=2)  # fmt: skip
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    na = n - 8
+    free_b, total_b = torch.cuda.mem_get_info(local)
+
+    # ---- device-resident leg: this rank's items, inputs in HBM ----------------------------------------------
+    d_raw = [torch.from_numpy(d.view(np.int16)).to(dev) for d, _ in exposures]
+    d_amp = [torch.from_numpy(a.view(np.int16)).to(dev) for _, a in exposures]
+    d_area = torch.from_numpy(area).to(dev)
+    o_slope = torch.empty((n, n), dtype=torch.float32, device=dev)
+    o_er, o_ep = torch.empty_like(o_slope), torch.empty_like(o_slope)
+    o_pdq = torch.empty((n, n), dtype=torch.int32, device=dev)
+    o_end = torch.empty((na, na), dtype=torch.int8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def resident_pass():
+        for k, (e, sca) in enumerate(drv.items):
+            gci.calibrate_device(drv.cals[sca], drv.pipes[sca].dplan, d_raw[k % 2].data_ptr(), d_amp[k % 2].data_ptr(),
+                                 d_area.data_ptr(), o_slope.data_ptr(), o_er.data_ptr(), o_ep.data_ptr(), o_pdq.data_ptr(),
+                                 d_endslice=o_end.data_ptr(), stream=stream)  # fmt: skip
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, args.warmup // 3)):
+        resident_pass()
+    barrier()
+    l0 = lib.rip_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        resident_pass()
+    ev1.record()
+    barrier()
+    launches = lib.rip_launch_count() - l0
+    tmax = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_pass = float(tmax.item()) / args.steps  # one pass = all E exposures of the job
+    value = E / (ms_pass * 1e-3)
+
+    # ---- end-to-end leg: pinned host cubes in, pinned host arrays out, WCS -> area on the device --------------
+    h_in = []
+    for d, a in exposures:
+        pd, pa = _lib.pinned_empty(d.shape, np.uint16), _lib.pinned_empty(a.shape, np.uint16)
+        pd[...] = d
+        pa[...] = a
+        h_in.append((pd, pa))
+    outs = [{"slope": _lib.pinned_empty((n, n), np.float32), "err_read": _lib.pinned_empty((n, n), np.float32),
+             "err_poisson": _lib.pinned_empty((n, n), np.float32), "pdq": _lib.pinned_empty((n, n), np.uint32),
+             "endslice": _lib.pinned_empty((na, na), np.int8)} for _ in range(6)]  # fmt: skip
+    wcs = {it: bench_wcs(na, it[0] * NSCA + it[1]) for it in drv.items}
+    sums = []
+
+    def fetch(e, sca):
+        d, a = h_in[(e + sca) % 2]
+        return d, a, wcs[(e, sca)]
+
+    def sink(e, sca, out):
+        sums.append(int(out["pdq"][n // 2, ::64].astype(np.uint64).sum()))  # the result is read on the host
+
+    drv.run(fetch, sink, list(outs))  # warm-up pass (allocates nothing afterwards)
+    barrier()
+    te0 = time.perf_counter()
+    ndone = drv.run(fetch, sink, list(outs))
+    torch.cuda.synchronize()
+    te = time.perf_counter() - te0
+    rate_items, total_items, te_max = sharding.job_throughput(ndone, te)
+    e2e_value = rate_items / NSCA
+    counts = torch.zeros(world, dtype=torch.float64, device=dev)
+    counts[rank] = len(drv.items)
+    nres = torch.zeros(world, dtype=torch.float64, device=dev)
+    nres[rank] = len(drv.scas)
+    if world > 1:
+        dist.all_reduce(counts)
+        dist.all_reduce(nres)
+    if rank == 0:
+        h2d = int(exposures[0][0].nbytes + exposures[0][1].nbytes + 8 * 211)
+        d2h = int(sum(v.nbytes for v in outs[0].values()))
+        print(json.dumps({
+            "metric": "18-SCA WFI exposures/sec through L1->L2 (4096^2 x 8 resultants per SCA)", "value": value,
+            "unit": "exposures/s", "sca_per_s": value * NSCA, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_pass, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (one CALDIR content uploaded as 18 separate resident handles; 2 exposure cubes rotated)",
+            "secondary_workload": True,
+            "config": {"workload": f"exposure18: {E} exposures x 18 SCAs = {len(items)} (exposure, SCA) items per pass, dealt by "
+                                   "sharding.assign_items_balanced; one resident CALDIR handle + pipeline per SCA of a rank",
+                       "items_per_rank": [int(c) for c in counts.tolist()], "resident_caldirs_per_rank": [int(c) for c in nres.tolist()],
+                       "imbalance_max_over_mean": float(counts.max().item() / counts.mean().item()),
+                       "sca_major_imbalance": sharding.imbalance(items, world, sharding.assign_items),
+                       "hbm_used_gb_rank0": (total_b - free_b) / 1e9, "caldir_setup_s_rank0": t_setup,
+                       "parallelism": f"sca-sharded x{world}"},
+            "e2e": {"value": e2e_value, "unit": "exposures/s", "sca_per_s": rate_items, "h2d_bytes_per_step": h2d * len(items),
+                    "d2h_bytes_per_step": d2h * len(items), "items": int(total_items), "seconds_max_over_ranks": te_max,
+                    "api": "exposure_driver.ExposureCalibrator.run -> one gen_cal_image.Pipeline per resident SCA (pinned host "
+                           "buffers, AreaFactor from each item's WCS on the device)", "checksum": int(sum(sums) % (1 << 32))},
+            "gpu_launches": int(launches)}), flush=True)  # fmt: skip
+    drv.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_noiselayers(args):
     """Secondary workload (the production call pattern of runs/summer2025run/OpenUniverse_to_L1L2.py:
     124-133): per exposure `--layers` noise layers (half "Rz4PbrS2C<i>", half "Rz4S2C<i>") with SKYORDER 2 = (2 + layers) full L1->L2 calibrations,
@@ -700,8 +859,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (for ncu captures)")
     ap.add_argument("--e2e-area-upload", action="store_true", help="e2e leg: upload the AreaFactor plane per exposure instead of evaluating it on the device from the WCS")
     ap.add_argument("--realizations", type=int, default=64, help="noise realisations (workload realizations)")
+    ap.add_argument("--exposures18", type=int, default=4, help="exposures of 18 SCAs each (workload exposure18)")
     ap.add_argument("--layers", type=int, default=8, help="noise layers per exposure (workload noiselayers)")
-    ap.add_argument("--workload", default="l1l2", choices=["l1l2", "forward", "realizations", "noiselayers"],
+    ap.add_argument("--workload", default="l1l2", choices=["l1l2", "forward", "realizations", "noiselayers", "exposure18"],
                     help="l1l2 = the headline metric; forward = secondary line for the forward ramp generator")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -713,6 +873,8 @@ def main():
         run_realizations(args)
     elif args.workload == "noiselayers":
         run_noiselayers(args)
+    elif args.workload == "exposure18":
+        run_exposure18(args)
     else:
         run_ours(args)
 

@@ -262,6 +262,15 @@ typedef struct rip_fwd_params {
     double read_time;
     uint64_t seed;
     int32_t add_read_noise, add_reset_noise, add_biascorr, quantize;
+    /* cosmic rays (romanisim.cr.simulate_crs, run per read by romanisim's apportioning when crparam is not None; the
+     * reference passes crparam={} = these defaults, from_sim/sim_to_isim.py:233-242).  0 = off. */
+    int32_t cr_enable;
+    int32_t pad_;
+    double cr_flux;                    /* events / cm^2 / s                                  (8)      */
+    double cr_area;                    /* detector area [cm^2]                               (16.8)   */
+    double cr_conversion_factor;       /* eV per electron                                    (0.5)    */
+    double cr_pixel_size;              /* [um]                                               (10)     */
+    double cr_pixel_depth;             /* [um]                                               (5)      */
 } rip_fwd_params;
 
 /* make_l1_fullcal (from_sim/sim_to_isim.py:163-262) with romanisim's apportioning / read noise restated
@@ -274,6 +283,14 @@ int rip_make_l1_host(rip_caldir* h, const int32_t* counts, const int32_t* cum_co
                      float* resultants);
 int rip_make_l1_dev(rip_caldir* h, const int32_t* d_counts, const rip_fwd_params* prm, float* d_resultants,
                     void* stream);
+/* Cosmic-ray group bits of the last rip_make_l1_* call of the handle that ran with cr_enable: u32 [na,na], bit g set
+ * = a cosmic ray deposited electrons during group g (the per-group JUMP_DET flags of romanisim's dq cube, which
+ * make_l1_fullcal returns at from_sim/sim_to_isim.py:262).  _dev returns the handle's own device buffer. */
+int rip_fwd_cr_groups_host(rip_caldir* h, uint32_t* groups);
+int rip_fwd_cr_groups_dev(rip_caldir* h, const uint32_t** d_groups);
+/* Cumulative electrons per read i32 [n_reads,na,na] of the handle's last forward ramp (apportioning + cosmic rays), for
+ * the statistical tests of the samplers (only when the ramp drew them itself or ran with cr_enable). */
+int rip_fwd_cum_counts_host(rip_caldir* h, int n_reads, int32_t* cum);
 
 /* ---- forward path either side of make_l1_fullcal (a15, a20) ----------------------------------------
  * Image2D.simulate (from_sim/sim_to_isim.py:615-648).  rip_sim_calprep returns the two calibration planes of the

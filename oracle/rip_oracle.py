@@ -488,7 +488,7 @@ def apply_refpix_corrections(data, dark_cube, rowcorr, chan_m, chan_c, row0=0):
 
 
 def l1_to_l2(data_u16, amp33_u16, cal, read_pattern, frame_time, area_factor, config=None, do_refpix=True,
-             return_intermediates=False, refpix_corr=None):  # fmt: skip
+             return_intermediates=False, refpix_corr=None, fns=None):  # fmt: skip
     """calibrateimage numerics from L1 arrays to L2 arrays (gen_cal_image.py:503-629,697-709).
 
     ``cal`` maps CALDIR keys to the ``roman`` branches.  Returns a dict with slope, err_read, err_poisson, pdq
@@ -499,8 +499,17 @@ def l1_to_l2(data_u16, amp33_u16, cal, read_pattern, frame_time, area_factor, co
     rows, ipc4d / biascorr to the matching active rows): the outer 4 rows act as a fake border whose influence ends 6
     rows in (saturation growth 1 + IPC order 2), so the interior of a band with a 6-row halo equals the whole-frame
     result.  tests/fullframe.py tiles a 4096^2 frame this way over a process pool.
+    ``fns``: replacements for the reference-owned steps (refpix_loop, multilin, correct_cube, construct_weights, ramp_fit,
+    get_flat) -- oracle/ref_chain.py passes the reference's own unmodified functions here.
     """
     config = config or {}
+    fns = fns or {}
+    _refpix_loop = fns.get("refpix_loop", refpix_loop)
+    _multilin = fns.get("multilin", multilin)
+    _correct_cube = fns.get("correct_cube", correct_cube)
+    _construct_weights = fns.get("construct_weights", construct_weights)
+    _ramp_fit = fns.get("ramp_fit", ramp_fit)
+    _get_flat = fns.get("get_flat", get_flat)
     nb = 4
     exclude_first = config.get("EXCLUDE_FIRST", True)
     backup = config.get("SATURATION_BACKUP", 1)
@@ -514,14 +523,14 @@ def l1_to_l2(data_u16, amp33_u16, cal, read_pattern, frame_time, area_factor, co
         rowcorr, chan_m, chan_c, row0 = refpix_corr
         apply_refpix_corrections(data, cal["dark"]["data"], rowcorr, chan_m, chan_c, row0)
     elif do_refpix:
-        refpix_loop(data, amp33_u16, cal["dark"]["data"], cal["read"])
+        _refpix_loop(data, amp33_u16, cal["dark"]["data"], cal["read"])
     if return_intermediates:
         inter["refcorr"] = data.copy()
     if "biascorr" in cal:
         bc = cal["biascorr"]["data"]
         de = bc.shape[0] - ngrp
         data[:, nb:-nb, nb:-nb] -= bc[de:]
-    data, dq_lin = multilin(
+    data, dq_lin = _multilin(
         data,
         cal["linearitylegendre"],
         do_not_flag_first=(list(read_pattern[0]) == [0]),
@@ -531,15 +540,15 @@ def l1_to_l2(data_u16, amp33_u16, cal, read_pattern, frame_time, area_factor, co
     if return_intermediates:
         inter["lin"] = data.copy()
     if "ipc4d" in cal:
-        correct_cube(data, cal["ipc4d"]["data"], cal["gain"]["data"])
+        _correct_cube(data, cal["ipc4d"]["data"], cal["gain"]["data"])
     if return_intermediates:
         inter["ipc"] = data.copy()
     uopt = config.get("RAMP_OPT_PARS", {"slope": 0.4, "gain": 1.8, "sigma_read": 6.5})
     u_ = float(uopt["slope"]) / float(uopt["gain"]) / float(uopt["sigma_read"]) ** 2
-    meta["K"] = construct_weights(u_, meta, exclude_first=exclude_first)
+    meta["K"] = _construct_weights(u_, meta, exclude_first=exclude_first)
     if "JUMP_DETECT_PARS" in config:
         meta["jump_detect_pars"] = config["JUMP_DETECT_PARS"]
-    slope, err_r, err_p = ramp_fit(data, rdq, pdq, meta, cal["gain"]["data"], cal["read"]["data"], exclude_first)
+    slope, err_r, err_p = _ramp_fit(data, rdq, pdq, meta, cal["gain"]["data"], cal["read"]["data"], exclude_first)
     # do_ramp_fit packaging (gen_cal_image.py:458-475): err, var_poisson, border zeroed
     err = np.hypot(err_r, err_p)
     varp = err_p**2
@@ -555,13 +564,13 @@ def l1_to_l2(data_u16, amp33_u16, cal, read_pattern, frame_time, area_factor, co
     # dark current (gen_cal_image.py:212-229)
     dslope = np.array(cal["dark"]["dark_slope"], dtype=np.float32)[None]
     if "ipc4d" in cal:
-        correct_cube(dslope, cal["ipc4d"]["data"], cal["gain"]["data"])
+        _correct_cube(dslope, cal["ipc4d"]["data"], cal["gain"]["data"])
     subtract_dark_current(slope, pdq, dslope[0], cal["dark"]["dq"], nb)
     # unpack + error split (gen_cal_image.py:607-613)
     err_p = np.sqrt(varp)
     err_r = np.sqrt(np.clip(err**2 - err_p**2, 0.0, None))
     # flat + area (gen_cal_image.py:616-629)
-    flat = get_flat(cal["flat"]["data"], cal["gain"]["data"], cal["ipc4d"]["data"], nb, pdq)
+    flat = _get_flat(cal["flat"]["data"], cal["gain"]["data"], cal["ipc4d"]["data"], nb, pdq)
     flat = (flat / area_factor).astype(np.float32)
     slope /= flat
     err_r /= flat
@@ -609,7 +618,7 @@ def forward_deterministic(mean_counts_per_read, cal, read_pattern, start_e):
 
 
 def make_l1_fullcal(counts, cal, read_pattern, rng, read_time=3.04, add_reset_noise=True, add_read_noise=True,
-                    quantize=True, cum_counts_out=None):  # fmt: skip
+                    quantize=True, cum_counts_out=None, crparam=None, cr_groups_out=None):  # fmt: skip
     """make_l1_fullcal (from_sim/sim_to_isim.py:195-260) with romanisim's apportioning and read noise RESTATED
     (parity unpinned): NumPy ``rng`` (a ``np.random.Generator``) instead of GalSim deviates.
 
@@ -646,6 +655,11 @@ def make_l1_fullcal(counts, cal, read_pattern, rng, read_time=3.04, add_reset_no
                 d = rng.binomial(remaining, min(p, 1.0))
                 cum += d
                 remaining -= d
+                if crparam is not None:  # (restated romanisim: cosmic rays of the interval since the previous read)
+                    before = cum.copy()
+                    simulate_crs(cum, t - t_prev, rng, **crparam)
+                    if cr_groups_out is not None:
+                        cr_groups_out[len(res)] |= cum != before
             t_prev = t
             if cum_counts_out is not None:
                 cum_counts_out[k] = cum
@@ -666,6 +680,73 @@ def make_l1_fullcal(counts, cal, read_pattern, rng, read_time=3.04, add_reset_no
     if quantize:
         res = np.round(res)
     return res.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Cosmic rays: romanisim.cr (romanisim 0.x; third-party, absent from /root/reference) RESTATED from its published
+# algorithm -- parity unpinned.  The reference switches it on with crparam={} (from_sim/sim_to_isim.py:233-242):
+# romanisim.l1.apportion_counts_to_resultants calls cr.simulate_crs(electrons_so_far, read_time, **crparam) once per
+# read and flags the pixels it changed with JUMP_DET in that resultant's dq.
+# ---------------------------------------------------------------------------------------------------------
+def _cr_sampler(pdf, x):
+    """romanisim.cr.create_sampler: inverse-transform sampler of a tabulated pdf (linear interpolation)."""
+    y = pdf(x)
+    cdf = np.cumsum(y) - y[0]
+    cdf /= cdf.max()
+    return lambda u: np.interp(u, cdf, x)
+
+
+def cr_sample_params(n_samples, n_i, n_j, rng, min_dedx=10, max_dedx=10000, min_cr_len=10, max_cr_len=2000, grid_size=10000):
+    """romanisim.cr.sample_cr_params: positions [pix], direction [rad], projected length [um], dE/dx [eV/um]."""
+    cr_i, cr_j = (rng.random(size=(n_samples, 2)) * (n_i, n_j)).transpose()
+    cr_phi = rng.random(n_samples) * 2 * np.pi
+    len_grid = np.linspace(min_cr_len, max_cr_len, grid_size)
+    cr_length = _cr_sampler(lambda x: np.power(x, -4.33), len_grid)(rng.random(n_samples))
+    dedx_grid = np.linspace(min_dedx, max_dedx, grid_size)
+
+    def moyal(x, location=120, scale=50):
+        xs = (x - location) / scale
+        return np.exp(-(xs + np.exp(-xs)) / 2)
+
+    cr_dedx = _cr_sampler(moyal, dedx_grid)(rng.random(n_samples))
+    return cr_i, cr_j, cr_phi, cr_length, cr_dedx
+
+
+def cr_traverse(start, end, n_i, n_j):
+    """romanisim.cr.traverse: pixels crossed by the segment start -> end (pixel centres at integers, borders at
+    half-integers) and the path length inside each [pixels]; pixels outside the array are dropped."""
+    (i0, j0), (i1, j1) = start, end
+    di, dj = i1 - i0, j1 - j0
+    ts = [0.0, 1.0]
+    for a0, d in ((i0, di), (j0, dj)):
+        if d != 0:
+            lo, hi = min(a0, a0 + d), max(a0, a0 + d)
+            b = np.arange(np.ceil(lo - 0.5) + 0.5, hi, 1.0)
+            tt = (b - a0) / d
+            ts.extend(tt[(tt > 0) & (tt < 1)].tolist())
+    ts = np.unique(np.array(ts))
+    tm = 0.5 * (ts[1:] + ts[:-1])
+    ii = np.rint(i0 + tm * di).astype(int)
+    jj = np.rint(j0 + tm * dj).astype(int)
+    length = (ts[1:] - ts[:-1]) * np.hypot(di, dj)
+    ok = (ii >= 0) & (ii < n_i) & (jj >= 0) & (jj < n_j) & (length > 0)
+    return ii[ok], jj[ok], length[ok]
+
+
+def simulate_crs(image, time, rng, flux=8, area=16.8, conversion_factor=0.5, pixel_size=10, pixel_depth=5):
+    """romanisim.cr.simulate_crs: adds cosmic-ray electrons to ``image`` in place; returns (image, number of events)."""
+    n_i, n_j = image.shape
+    n_samples = rng.poisson(flux * area * time)
+    ci, cj, phi, length, dedx = cr_sample_params(n_samples, n_i, n_j, rng)
+    length = length / pixel_size
+    i1 = (ci + length * np.cos(phi)).clip(-0.5, n_i + 0.5)
+    j1 = (cj + length * np.sin(phi)).clip(-0.5, n_j + 0.5)
+    counts_per_pix = dedx * pixel_size / conversion_factor
+    for a0, b0, a1, b1, cpp in zip(ci, cj, i1, j1, counts_per_pix):
+        ii, jj, l2 = cr_traverse((a0, b0), (a1, b1), n_i, n_j)
+        l3 = ((pixel_depth / pixel_size) ** 2 + l2**2) ** 0.5
+        image[ii, jj] += rng.poisson(cpp * l3).astype(image.dtype)
+    return image, n_samples
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -82,6 +82,7 @@ class CalDir:
 
     def __init__(self, caldir, device=0):
         self.device = device
+        self.source = caldir  # the CALDIR it was built from (file names or in-memory trees), for late host-side reads
         self._h = C.c_void_p()
         d = _lib.CaldirDesc()
         keep = []

@@ -68,7 +68,9 @@ class FwdParams(C.Structure):
     _fields_ = [("G", C.c_int32), ("n_reads", C.c_int32), ("reads_per_group", C.c_int32 * RIP_GMAX),
                 ("read_index", C.c_int32 * 64), ("read_time", C.c_double), ("seed", C.c_uint64),
                 ("add_read_noise", C.c_int32), ("add_reset_noise", C.c_int32), ("add_biascorr", C.c_int32),
-                ("quantize", C.c_int32)]  # fmt: skip
+                ("quantize", C.c_int32), ("cr_enable", C.c_int32), ("pad_", C.c_int32), ("cr_flux", C.c_double),
+                ("cr_area", C.c_double), ("cr_conversion_factor", C.c_double), ("cr_pixel_size", C.c_double),
+                ("cr_pixel_depth", C.c_double)]  # fmt: skip
 
 
 _SIGS = {
@@ -139,6 +141,9 @@ _SIGS = {
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "rip_make_l1_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FwdParams), C.c_void_p]),
     "rip_make_l1_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(FwdParams), C.c_void_p, C.c_void_p]),
+    "rip_fwd_cr_groups_host": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rip_fwd_cr_groups_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "rip_fwd_cum_counts_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "rip_sim_calprep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rip_sim_counts_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
                                      C.c_double, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]),

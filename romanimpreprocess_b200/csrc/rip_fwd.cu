@@ -4,6 +4,7 @@
 //
 // ALU-bound (24 bisection steps x Legendre order x n_reads in float64), not HBM-bound.
 #include <memory>
+#include <vector>
 
 #include "rip_launch.h"
 #include "rip_rng.cuh"
@@ -364,6 +365,128 @@ __global__ void __launch_bounds__(128) fwd_apportion_kernel(const FwdArgs A) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Cosmic rays: romanisim.cr.simulate_crs (romanisim 0.x, called per read by l1.apportion_counts_to_resultants when
+// crparam is not None -- the reference passes crparam={} = the defaults, from_sim/sim_to_isim.py:233-242), restated
+// from the published algorithm (third-party source absent: parity unpinned, validated statistically):
+//   N ~ Poisson(flux * area * dt) events per read; position uniform on the array, direction phi uniform in [0, 2 pi),
+//   projected path length [um] from a power law x^-4.33 on [10, 2000], energy loss dE/dx [eV/um] from a Moyal
+//   distribution (location 120, scale 50) on [10, 10000], both by inverse-transform sampling of the pdf tabulated on
+//   10000 grid points (cumulative sum, linear interpolation of the inverse); the end point is clipped to
+//   [-0.5, N + 0.5] per axis; every pixel the segment crosses receives Poisson(dE/dx * pixel_size / conversion_factor
+//   * sqrt((depth / pixel_size)^2 + l2d^2)) electrons, l2d = path length inside the pixel [pixels].
+// The electrons stay in the well: they are added to the cumulative counts of the read and of every later read.
+// One CTA per read; one thread per event (a few hundred events per read at the default flux).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CR_GRID = 10000;
+struct CrArgs {
+    int na, n_reads;
+    uint64_t seed;
+    double lam[64];             // expected events per read: flux * area * (t_k - t_{k-1})
+    int group_of_read[64];
+    double counts_per_pix;      // pixel_size / conversion_factor  (times dE/dx)
+    double depth_ratio;         // pixel_depth / pixel_size
+    double inv_pixel_size;      // 1 / pixel_size [1/um]
+    const float* len_cdf;       // [CR_GRID] cumulative distributions of the two samplers
+    const float* dedx_cdf;
+    int32_t* cum;               // [n_reads, na, na]
+    uint32_t* groups;           // [na, na] bit g = a cosmic ray deposited electrons during group g
+};
+
+// inverse-transform sample: x(u) with cdf tabulated on linspace(lo, hi, CR_GRID)
+__device__ inline double cr_sample(const float* __restrict__ cdf, double lo, double hi, float u) {
+    int a = 0, b = CR_GRID - 1;  // cdf[a] <= u <= cdf[b]
+    while (b - a > 1) {
+        const int m = (a + b) >> 1;
+        if (cdf[m] <= u) a = m; else b = m;
+    }
+    const float ca = cdf[a], cb = cdf[b];
+    const double f = cb > ca ? (double)(u - ca) / (double)(cb - ca) : 0.0;
+    return lo + (hi - lo) * ((double)a + f) / (double)(CR_GRID - 1);
+}
+
+__global__ void __launch_bounds__(128) fwd_cr_kernel(const CrArgs A) {
+    const int k = blockIdx.x;
+    __shared__ int n_ev;
+    if (threadIdx.x == 0) {
+        Philox r;
+        r.init(A.seed, (uint64_t)k, 200u);
+        long nn = poisson_draw(r, A.lam[k]);
+        n_ev = nn > (1 << 20) ? (1 << 20) : (int)nn;
+    }
+    __syncthreads();
+    const int na = A.na;
+    const long npa = (long)na * na;
+    const uint32_t gbit = 1u << A.group_of_read[k];
+    for (int ev = threadIdx.x; ev < n_ev; ev += blockDim.x) {
+        Philox r;
+        r.init(A.seed, ((uint64_t)k << 32) | (uint64_t)ev, 201u);
+        const double i0 = (double)r.uniform() * na, j0 = (double)r.uniform() * na;
+        const double phi = 6.283185307179586 * (double)r.uniform();
+        const double len = cr_sample(A.len_cdf, 10.0, 2000.0, r.uniform()) * A.inv_pixel_size;
+        const double dedx = cr_sample(A.dedx_cdf, 10.0, 10000.0, r.uniform());
+        double sn, cs;
+        sincos(phi, &sn, &cs);
+        const double i1 = fmin(fmax(i0 + len * cs, -0.5), na + 0.5), j1 = fmin(fmax(j0 + len * sn, -0.5), na + 0.5);
+        const double di = i1 - i0, dj = j1 - j0;
+        const double L = sqrt(di * di + dj * dj);
+        const double cpp = dedx * A.counts_per_pix;
+        // walk the pixel-border crossings (borders at half-integers, pixel centres at integers) in order of t in [0, 1]
+        const double inv_di = di != 0.0 ? 1.0 / di : 0.0, inv_dj = dj != 0.0 ? 1.0 / dj : 0.0;
+        double bi = di > 0.0 ? floor(i0 + 0.5) + 0.5 : ceil(i0 - 0.5) - 0.5;   // next border along i
+        double bj = dj > 0.0 ? floor(j0 + 0.5) + 0.5 : ceil(j0 - 0.5) - 0.5;
+        const double si = di > 0.0 ? 1.0 : -1.0, sj = dj > 0.0 ? 1.0 : -1.0;
+        double t = 0.0;
+        for (int guard = 0; guard < 1024 && t < 1.0; ++guard) {
+            double ti = di != 0.0 ? (bi - i0) * inv_di : 2.0, tj = dj != 0.0 ? (bj - j0) * inv_dj : 2.0;
+            if (ti <= t) { bi += si; continue; }   // (a start exactly on a border)
+            if (tj <= t) { bj += sj; continue; }
+            double tn = fmin(fmin(ti, tj), 1.0);
+            const double tm = 0.5 * (t + tn);
+            const long ii = llrint(i0 + tm * di), jj = llrint(j0 + tm * dj);   // pixel of the segment's midpoint
+            const double l2 = (tn - t) * L;
+            if (ii >= 0 && ii < na && jj >= 0 && jj < na && l2 > 0.0) {
+                const double l3 = sqrt(A.depth_ratio * A.depth_ratio + l2 * l2);
+                const long d = poisson_draw(r, cpp * l3);
+                if (d > 0) {
+                    const long pa = ii * na + jj;
+                    const int dd = d > 1000000000L ? 1000000000 : (int)d;
+                    for (int kk = k; kk < A.n_reads; ++kk) atomicAdd(&A.cum[(long)kk * npa + pa], dd);
+                    atomicOr(&A.groups[pa], gbit);
+                }
+            }
+            if (tn == ti) bi += si;
+            if (tn == tj) bj += sj;
+            t = tn;
+        }
+    }
+}
+
+// the two cumulative tables of romanisim.cr.create_sampler: cumsum(pdf) - pdf[0], normalised to its maximum
+static void cr_tables(std::vector<float>& len_cdf, std::vector<float>& dedx_cdf) {
+    len_cdf.resize(CR_GRID);
+    dedx_cdf.resize(CR_GRID);
+    std::vector<double> y(CR_GRID);
+    auto build = [&](std::vector<float>& out) {
+        double acc = 0.0;
+        std::vector<double> c(CR_GRID);
+        for (int i = 0; i < CR_GRID; ++i) { acc += y[i]; c[i] = acc - y[0]; }
+        const double mx = c[CR_GRID - 1];
+        for (int i = 0; i < CR_GRID; ++i) out[i] = (float)(c[i] / mx);
+    };
+    for (int i = 0; i < CR_GRID; ++i) {
+        const double x = 10.0 + (2000.0 - 10.0) * i / (CR_GRID - 1);
+        y[i] = pow(x, -4.33);
+    }
+    build(len_cdf);
+    for (int i = 0; i < CR_GRID; ++i) {
+        const double x = 10.0 + (10000.0 - 10.0) * i / (CR_GRID - 1);
+        const double xs = (x - 120.0) / 50.0;
+        y[i] = exp(-(xs + exp(-xs)) / 2.0);
+    }
+    build(dedx_cdf);
+}
+
 template <int P, typename TG, typename TK>
 __global__ void __launch_bounds__(FTX * FTY, 3) fwd_ramp_kernel(const FwdArgs A) {
     __shared__ double se[FTY + 2][FTX + 2];  // electrons in the well at this read (counts so far + start_e)
@@ -613,6 +736,11 @@ static void make_l1_impl(rip_caldir* h, const int32_t* d_counts, const int32_t* 
         }
     }
     A.counts = d_counts;
+    if (d_cum && prm->cr_enable) {  // cosmic rays add to the cumulative counts: work on a copy of the caller's cube
+        if (h->f_cum.n < npa * prm->n_reads) h->f_cum.alloc(npa * prm->n_reads);
+        RIP_CUDA(cudaMemcpyAsync(h->f_cum.p, d_cum, npa * prm->n_reads * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        d_cum = h->f_cum.p;
+    }
     A.cum = d_cum ? const_cast<int32_t*>(d_cum) : h->f_cum.p;
     A.cum_given = d_cum ? 1 : 0;
     A.start = h->f_start.p;
@@ -627,6 +755,40 @@ static void make_l1_impl(rip_caldir* h, const int32_t* d_counts, const int32_t* 
     dim3 ga((h->na + 127) / 128, h->na);
     if (gd) RIP_LAUNCH(fwd_apportion_kernel<double>, ga, 128, 0, st, A);
     else RIP_LAUNCH(fwd_apportion_kernel<float>, ga, 128, 0, st, A);
+    if (prm->cr_enable) {  // cosmic rays on top of the apportioned (or supplied) cumulative counts
+        RIP_REQUIRE(prm->cr_flux >= 0.0 && prm->cr_area >= 0.0 && prm->cr_conversion_factor > 0.0 && prm->cr_pixel_size > 0.0 &&
+                    prm->cr_pixel_depth >= 0.0, "rip_make_l1: bad cosmic-ray parameters");
+        if (!h->cr_len_cdf.p) {
+            std::vector<float> a, b;
+            cr_tables(a, b);
+            h->cr_len_cdf.upload(a.data(), a.size(), st);
+            h->cr_dedx_cdf.upload(b.data(), b.size(), st);
+            RIP_CUDA(cudaStreamSynchronize(st));  // (the host vectors die here)
+        }
+        if (h->f_crg.n < npa) h->f_crg.alloc(npa);
+        RIP_CUDA(cudaMemsetAsync(h->f_crg.p, 0, npa * sizeof(uint32_t), st));
+        CrArgs Cr;
+        memset(&Cr, 0, sizeof Cr);
+        Cr.na = h->na; Cr.n_reads = prm->n_reads; Cr.seed = prm->seed;
+        double t_prev = 0.0;
+        int k = 0;
+        for (int g = 0; g < prm->G; ++g)
+            for (int r = 0; r < prm->reads_per_group[g]; ++r, ++k) {
+                const double t = prm->read_time * (double)prm->read_index[k];
+                Cr.lam[k] = t > t_prev ? prm->cr_flux * prm->cr_area * (t - t_prev) : 0.0;
+                Cr.group_of_read[k] = g;
+                t_prev = t;
+            }
+        Cr.counts_per_pix = prm->cr_pixel_size / prm->cr_conversion_factor;
+        Cr.depth_ratio = prm->cr_pixel_depth / prm->cr_pixel_size;
+        Cr.inv_pixel_size = 1.0 / prm->cr_pixel_size;
+        Cr.len_cdf = h->cr_len_cdf.p; Cr.dedx_cdf = h->cr_dedx_cdf.p;
+        Cr.cum = A.cum; Cr.groups = h->f_crg.p;
+        RIP_LAUNCH(fwd_cr_kernel, prm->n_reads, 128, 0, st, Cr);
+        h->f_crg_valid = true;
+    } else {
+        h->f_crg_valid = false;
+    }
     dim3 grid((h->na + FTX - 1) / FTX, (h->na + FTY - 1) / FTY);
     const int threads = FTX * FTY;
 #define FW(PM)                                                                                   \
@@ -665,5 +827,38 @@ extern "C" int rip_make_l1_host(rip_caldir* h, const int32_t* counts, const int3
     make_l1_impl(h, counts ? dc.p : nullptr, cum_counts ? dcum.p : nullptr, prm, dout.p, st);
     dout.download(resultants, npa * prm->G, st);
     RIP_CUDA(cudaStreamSynchronize(st));
+    RIP_API_END
+}
+
+// bit g of plane [na,na] = a cosmic ray deposited electrons during group g of the LAST rip_make_l1_* call with
+// cr_enable (the per-group JUMP_DET flag romanisim's apportioning returns in its dq cube)
+extern "C" int rip_fwd_cr_groups_host(rip_caldir* h, uint32_t* groups) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && groups, "rip_fwd_cr_groups_host: null argument");
+    RIP_REQUIRE(h->f_crg_valid, "rip_fwd_cr_groups_host: the last forward ramp of this handle ran without cosmic rays");
+    use_device(h->device);
+    h->f_crg.download(groups, (size_t)h->na * h->na, h->stream);
+    RIP_CUDA(cudaStreamSynchronize(h->stream));
+    RIP_API_END
+}
+
+extern "C" int rip_fwd_cr_groups_dev(rip_caldir* h, const uint32_t** d_groups) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && d_groups, "rip_fwd_cr_groups_dev: null argument");
+    RIP_REQUIRE(h->f_crg_valid, "rip_fwd_cr_groups_dev: the last forward ramp of this handle ran without cosmic rays");
+    *d_groups = h->f_crg.p;
+    RIP_API_END
+}
+
+// cumulative electrons per read [n_reads,na,na] of the LAST forward ramp of the handle (binomial apportioning + cosmic
+// rays): for the statistical tests of the samplers
+extern "C" int rip_fwd_cum_counts_host(rip_caldir* h, int n_reads, int32_t* cum) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && cum && n_reads >= 1, "rip_fwd_cum_counts_host: bad argument");
+    const size_t npa = (size_t)h->na * h->na;
+    RIP_REQUIRE(h->f_cum.n >= npa * (size_t)n_reads, "rip_fwd_cum_counts_host: no forward ramp with %d reads has run on this handle", n_reads);
+    use_device(h->device);
+    h->f_cum.download(cum, npa * (size_t)n_reads, h->stream);
+    RIP_CUDA(cudaStreamSynchronize(h->stream));
     RIP_API_END
 }

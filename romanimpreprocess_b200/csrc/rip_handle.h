@@ -44,6 +44,9 @@ struct rip_caldir {
     // forward ramp (rip_fwd.cu): certificate planes of the fast inverse (lazy, once per CALDIR), per-call workspace
     DevBuf<float> lin_A, lin_m, f_start;
     DevBuf<int32_t> f_cum;
+    DevBuf<uint32_t> f_crg;              // cosmic-ray group bits of the last forward ramp
+    DevBuf<float> cr_len_cdf, cr_dedx_cdf;  // samplers of romanisim.cr (built on first use)
+    bool f_crg_valid = false;
     cudaStream_t stream = nullptr;
     // optional per-launch timing of the fused kernel (rip_profile_enable): event pairs recorded on the launch stream
     bool profile = false;

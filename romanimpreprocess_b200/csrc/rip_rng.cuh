@@ -1,5 +1,6 @@
 // Counter-based random numbers shared by the forward-model kernels (rip_fwd.cu, rip_sim.cu).
 #pragma once
+#include <math.h>
 #include <stdint.h>
 
 namespace rip {
@@ -43,7 +44,7 @@ struct Philox {
     // in [2^-24, 1 - 2^-24]; the earlier 24-bit form rounded its top value to exactly 1.0f.
     // Stream ids in use (one purpose each, disjoint): 1 apportioning, 2/3 scene Poisson, 8 reset noise of the reference
     // pixels, 16+g forward read noise, 32+g / 48+g reference-pixel and white noise per group, 96+k noise-layer draws,
-    // 128 Poisson re-sampling, 1024+ 1/f frames.
+    // 128 Poisson re-sampling, 200 / 201 cosmic-ray counts / events, 1024+ 1/f frames.
     __device__ __forceinline__ float uniform() { return ((float)(next() >> 9) + 0.5f) * (1.0f / 8388608.0f); }
     // uniform in (0,1), 53-bit
     __device__ __forceinline__ double uniform53() {
@@ -64,5 +65,35 @@ struct Philox {
         return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
     }
 };
+
+// ---------------------------------------------------------------------------------------------------------
+// Poisson(lam): multiplication method below 10, Hormann's PTRS transformed rejection above (the algorithm of
+// NumPy's legacy generator).  Result clipped to int32.
+// ---------------------------------------------------------------------------------------------------------
+__device__ inline long poisson_draw(Philox& rng, double lam) {
+    if (!(lam > 0.0)) return 0;
+    if (lam < 10.0) {
+        const double enlam = exp(-lam);
+        long k = 0;
+        double prod = 1.0;
+        for (;;) {
+            prod *= rng.uniform53();
+            if (prod > enlam) ++k;
+            else return k;
+        }
+    }
+    const double slam = sqrt(lam), loglam = log(lam);
+    const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (;;) {
+        const double U = rng.uniform53() - 0.5, V = rng.uniform53();
+        const double us = 0.5 - fabs(U);
+        const double kf = floor((2.0 * a / us + b) * U + lam + 0.43);
+        if (us >= 0.07 && V <= vr) return kf > 2147483647.0 ? 2147483647L : (long)kf;
+        if (kf < 0.0 || (us < 0.013 && V > us)) continue;
+        if ((log(V) + log(invalpha) - log(a / (us * us) + b)) <= (-lam + kf * loglam - lgamma(kf + 1.0)))
+            return kf > 2147483647.0 ? 2147483647L : (long)kf;
+    }
+}
 
 }  // namespace rip

@@ -22,36 +22,6 @@
 
 namespace rip {
 
-// ---------------------------------------------------------------------------------------------------------
-// Poisson(lam): multiplication method below 10, Hormann's PTRS transformed rejection above (the algorithm of
-// NumPy's legacy generator).  Result clipped to int32.
-// ---------------------------------------------------------------------------------------------------------
-__device__ long poisson_draw(Philox& rng, double lam) {
-    if (!(lam > 0.0)) return 0;
-    if (lam < 10.0) {
-        const double enlam = exp(-lam);
-        long k = 0;
-        double prod = 1.0;
-        for (;;) {
-            prod *= rng.uniform53();
-            if (prod > enlam) ++k;
-            else return k;
-        }
-    }
-    const double slam = sqrt(lam), loglam = log(lam);
-    const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
-    const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
-    for (;;) {
-        const double U = rng.uniform53() - 0.5, V = rng.uniform53();
-        const double us = 0.5 - fabs(U);
-        const double kf = floor((2.0 * a / us + b) * U + lam + 0.43);
-        if (us >= 0.07 && V <= vr) return kf > 2147483647.0 ? 2147483647L : (long)kf;
-        if (kf < 0.0 || (us < 0.013 && V > us)) continue;
-        if ((log(V) + log(invalpha) - log(a / (us * us) + b)) <= (-lam + kf * loglam - lgamma(kf + 1.0)))
-            return kf > 2147483647.0 ? 2147483647L : (long)kf;
-    }
-}
-
 // this_dark (e/s) input of ipc_rev: dark_slope * gain on the full frame (sim_to_isim.py:624)
 template <typename TG>
 __global__ void dark_e_kernel(const float* __restrict__ dark_slope, const TG* __restrict__ gain, long npix, float* __restrict__ out) {

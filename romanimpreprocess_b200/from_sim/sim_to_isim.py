@@ -12,8 +12,10 @@ read_pattern_from_reads
 The reference delegates the apportioning and the read noise to ``romanisim.l1`` (whose source is not part of the
 reference) and draws from GalSim deviates.  The kernel restates them with a counter-based Philox
 generator, so individual realisations differ from the reference's while their statistics agree (validated as in
-the reference's ``validation_tests/many_realizations.py``).  Cosmic-ray injection (``romanisim.cr``, switched on by
-``crparam={}`` at sim_to_isim.py:238) is not restated: the returned ``dq`` carries the linearity file's flags only.
+the reference's ``validation_tests/many_realizations.py``).  Cosmic-ray injection (``romanisim.cr.simulate_crs``,
+switched on by ``crparam={}`` at sim_to_isim.py:238) is restated from its published algorithm in the kernel
+``fwd_cr_kernel`` (``crparam`` argument of ``make_l1_fullcal``; the reference's behaviour is ``crparam={}``): the
+returned ``dq`` then carries JUMP_DET in the groups a cosmic ray hit, as romanisim's does.
 """
 
 import ctypes as C
@@ -24,6 +26,8 @@ from .. import _lib, pars
 from ..L1_to_L2.gen_cal_image import CalDir
 
 READ_TIME = 3.04  # romanisim.parameters.read_time [s]
+# defaults of romanisim.cr.simulate_crs (what crparam={} selects)
+CR_DEFAULTS = {"flux": 8.0, "area": 16.8, "conversion_factor": 0.5, "pixel_size": 10.0, "pixel_depth": 5.0}
 
 
 def read_pattern_from_reads(reads):
@@ -46,7 +50,7 @@ def _seed_from(rng, seed):
 
 
 def fwd_params(read_pattern, seed, read_time=READ_TIME, add_read_noise=True, add_reset_noise=True, add_biascorr=True,
-               quantize=True):  # fmt: skip
+               quantize=True, crparam=None):  # fmt: skip
     G = len(read_pattern)
     if G > _lib.RIP_GMAX:
         raise ValueError(f"the GPU forward model supports up to {_lib.RIP_GMAX} resultants")
@@ -63,6 +67,15 @@ def fwd_params(read_pattern, seed, read_time=READ_TIME, add_read_noise=True, add
     prm.seed = int(seed)
     prm.add_read_noise, prm.add_reset_noise = int(bool(add_read_noise)), int(bool(add_reset_noise))
     prm.add_biascorr, prm.quantize = int(bool(add_biascorr)), int(bool(quantize))
+    if crparam is not None:  # romanisim: `if crparam is not None: cr.simulate_crs(..., **crparam)`
+        unknown = set(crparam) - set(CR_DEFAULTS)
+        if unknown:
+            raise TypeError(f"simulate_crs() got unexpected keyword arguments {sorted(unknown)}")
+        cr = {**CR_DEFAULTS, **crparam}
+        prm.cr_enable = 1
+        prm.cr_flux, prm.cr_area = float(cr["flux"]), float(cr["area"])
+        prm.cr_conversion_factor = float(cr["conversion_factor"])
+        prm.cr_pixel_size, prm.cr_pixel_depth = float(cr["pixel_size"]), float(cr["pixel_depth"])
     return prm
 
 
@@ -83,6 +96,9 @@ def make_l1_fullcal(counts, read_pattern, caldir, rng=None, persistence=None, ts
         Source of the seed of the counter-based generator of the kernel.
     persistence, tstart
         Accepted for signature compatibility; not used (as in the reference: "not used yet").
+    crparam : dict or None (keyword)
+        ``None`` (default here): no cosmic rays.  A dict -- ``{}`` is what the reference passes -- switches on
+        ``romanisim.cr.simulate_crs`` per read with these overrides of its defaults (``CR_DEFAULTS``).
 
     Returns
     -------
@@ -101,6 +117,13 @@ def make_l1_fullcal(counts, read_pattern, caldir, rng=None, persistence=None, ts
         _lib.check(_lib.lib().rip_make_l1_host(cal.handle, _lib.ptr(c), _lib.ptr(cc), C.byref(prm), _lib.ptr(out)))
         with_dq = np.empty((prm.G, cal.na, cal.na), np.uint32)
         with_dq[...] = cal.lin_dq_active[None]
+        if prm.cr_enable:  # romanisim: dq[group, crhits] |= JUMP_DET
+            from ..dqflags import pixel  # noqa: PLC0415
+
+            crg = np.empty((cal.na, cal.na), np.uint32)
+            _lib.check(_lib.lib().rip_fwd_cr_groups_host(cal.handle, _lib.ptr(crg)))
+            for g in range(prm.G):
+                with_dq[g] |= np.where((crg >> g) & 1, np.uint32(pixel.JUMP_DET), np.uint32(0))
     finally:
         if cal is not caldir:
             cal.close()
@@ -174,7 +197,7 @@ def sim_calprep(caldir, device=0):
 
 
 def simulate_counts(image, caldir, read_pattern, rng=None, seed=None, area_ratio=None, cnorm=1.0, read_time=READ_TIME,
-                    counts=None, dark=False, return_rate=False, device=0):  # fmt: skip
+                    counts=None, dark=False, return_rate=False, device=0, sky=None):  # fmt: skip
     """
     Electrons per pixel of one exposure from a noiseless scene (reference sim_to_isim.py:636-648):
     ``counts += Poisson(clip(C * t * g / g_ideal * image * this_flat / area_ratio, 0))`` with
@@ -183,6 +206,10 @@ def simulate_counts(image, caldir, read_pattern, rng=None, seed=None, area_ratio
     image : float32 (na, na), e/s per ideal pixel; area_ratio : pixel area / Omega_ideal (na, na) or None;
     counts : int32 (na, na) to accumulate into (the reference adds to romanisim's dark/sky counts) or None;
     dark : also draw the dark electrons Poisson(this_dark * t) (romanisim's term, restated).
+    sky : sky background level in e/s/pixel (scalar or (na, na) plane) or None: adds Poisson(sky * this_flat * t), the
+        background term of romanisim's ``simulate_counts`` (restated; the LEVEL comes from ``galsim.roman.getSkyLevel``
+        -- zodiacal-light tables that ship with GalSim, absent here -- plus stray light and thermal background, so the
+        caller supplies it).
     """
     cal = caldir if isinstance(caldir, CalDir) else CalDir(caldir, device)
     try:
@@ -198,6 +225,21 @@ def simulate_counts(image, caldir, read_pattern, rng=None, seed=None, area_ratio
                                                   _lib.float_tag(ar) if ar is not None else _lib.RIP_F32, t, float(cnorm),
                                                   float(pars.g_ideal), t if dark else 0.0, _seed_from(rng, seed),
                                                   _lib.ptr(out), int(acc), _lib.ptr(rate)))  # fmt: skip
+        if sky is not None:
+            # Poisson(sky * this_flat * t) through the same kernel: its mean is C t g/g_ideal * image * flat / area, so
+            # the "image" of the sky term is sky * g_ideal / g * area (C = 1); own random stream (seed + 1)
+            from ..caltree import open_tree  # noqa: PLC0415
+
+            with open_tree(cal.source["gain"]) as f:
+                g_act = np.asarray(f["roman"]["data"])[cal.nb : cal.n - cal.nb, cal.nb : cal.n - cal.nb].astype(np.float64)
+            sk = np.broadcast_to(np.asarray(sky, dtype=np.float64), (cal.na, cal.na)) * float(pars.g_ideal) / g_act
+            if ar is not None:
+                sk = sk * ar
+            sk = np.ascontiguousarray(sk, dtype=np.float32)
+            _lib.check(_lib.lib().rip_sim_counts_host(cal.handle, _lib.ptr(sk), _lib.ptr(ar),
+                                                      _lib.float_tag(ar) if ar is not None else _lib.RIP_F32, t, 1.0,
+                                                      float(pars.g_ideal), 0.0, (_seed_from(rng, seed) + 1) & 0xFFFFFFFFFFFFFFFF,
+                                                      _lib.ptr(out), 1, None))  # fmt: skip
     finally:
         if cal is not caldir:
             cal.close()

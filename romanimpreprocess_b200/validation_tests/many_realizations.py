@@ -15,6 +15,10 @@ difference, the slope and its error.  Here every realisation stays in HBM:
 (one process per GPU); the three moment planes are then summed over ranks by the caller (``torch.distributed``
 all-reduce, the only exchange step of this workload).
 
+Cosmic rays: the reference's forward model injects them (``crparam={}`` at from_sim/sim_to_isim.py:238 = romanisim's
+defaults); so does this one by default (``crparam={}``; the detector area scales with the frame for small test frames),
+``crparam=None`` switches them off.
+
 Deviations from the reference script, stated: sky subtraction and WCS are outside the hot path (``images`` are the
 flat-fielded slopes; the caller supplies the area plane); ``err`` is ``hypot(err_read, err_poisson)``; the reference
 maps ``images`` and ``err`` onto the SAME memmap file (lines 55-56), so its planes 2 and 7 are both medians of the
@@ -39,7 +43,7 @@ class Realizations:
     """Device-resident state of a many-realisations run of one SCA (one process / GPU)."""
 
     def __init__(self, image, caldir, read_pattern, area_ratio=None, config2=None, cnorm=1.0, device=0,
-                 keep_stacks=0, dark=True, fill_in_banding=True, read_time=s2i.READ_TIME):  # fmt: skip
+                 keep_stacks=0, dark=True, fill_in_banding=True, read_time=s2i.READ_TIME, crparam={}):  # fmt: skip  # noqa: B006
         import torch  # noqa: PLC0415  (device memory only)
 
         self.torch = torch
@@ -55,6 +59,8 @@ class Realizations:
         self.cnorm, self.dark, self.banding = float(cnorm), bool(dark), bool(fill_in_banding)
         self.t_exp = self.read_time * (read_pattern[-1][-1] - read_pattern[0][0])
         self.rpg = np.ascontiguousarray([len(g) for g in read_pattern], dtype=np.int32)
+        # cosmic rays as in the reference (romanisim defaults; 16.8 cm^2 is the area of the full 4088^2 array)
+        self.crparam = None if crparam is None else {"area": s2i.CR_DEFAULTS["area"] * (na / 4088.0) ** 2, **crparam}
         self.grow = np.ascontiguousarray(maskhandling.PixelMask1.array)
         # the reference output is 128 columns wide whatever the frame side (gen_cal_image.py:531-556 and the library's
         # reference-pixel statistics assume it); debugging frames with n/32 != 128 run without that correction
@@ -96,7 +102,7 @@ class Realizations:
         _lib.check(lib.rip_sim_counts_dev(cal.handle, _p(self.d_image), _p(self.d_area_act), _lib.RIP_F32, self.t_exp,
                                           self.cnorm, float(pars.g_ideal), self.t_exp if self.dark else 0.0, seed,
                                           _p(self.d_counts), 0, st))  # fmt: skip
-        prm = s2i.fwd_params(self.read_pattern, seed, read_time=self.read_time)
+        prm = s2i.fwd_params(self.read_pattern, seed, read_time=self.read_time, crparam=self.crparam)
         _lib.check(lib.rip_make_l1_dev(cal.handle, _p(self.d_counts), C.byref(prm), _p(self.d_res), st))
         _lib.check(lib.rip_l1_embed_dev(self.device, _p(self.d_res), self.G, self.n, cal.nb, _p(self.d_im), st))
         _lib.check(lib.rip_fill_refdata_1f_dev(cal.handle, _p(self.d_im), _p(self.d_amp33), self.G, _lib.ptr(self.rpg),
@@ -138,16 +144,53 @@ class Realizations:
             self.cal.close()
 
 
-def run(image, caldir, read_pattern, Nrun, seed=100, slope_ideal=None, rank=0, ranks=1, **kw):
-    """Run ``Nrun`` realisations (this rank's share when ``ranks`` > 1) and return the reference's 8-plane stack.
-    Seeds follow the reference: realisation j uses ``seed + 10 (j + 1)``."""
+def run(image, caldir, read_pattern, Nrun, seed=100, slope_ideal=None, rank=0, ranks=1, group=None, **kw):
+    """Run ``Nrun`` realisations and return the reference's 8-plane stack.  Seeds follow the reference: realisation j
+    uses ``seed + 10 (j + 1)``.
+
+    ``ranks`` > 1: this process runs the realisations ``j % ranks == rank`` (one process per GPU) and the partial results
+    are combined over ``group`` (an initialised ``torch.distributed`` NCCL group; default: the world) BEFORE they are
+    finalised -- the three moment sums by an all-reduce, the per-realisation stacks of the medians by an all-gather --
+    so every rank returns the statistics of all ``Nrun`` realisations."""
     mine = [j for j in range(Nrun) if j % ranks == rank]
     emulate_alias = kw.pop("emulate_alias", False)
+    if ranks > 1:
+        import torch.distributed as dist  # noqa: PLC0415
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("many_realizations.run(ranks > 1) needs an initialised torch.distributed process group: "
+                               "moment sums and stacks of the ranks are combined before finalisation")  # fmt: skip
     R = Realizations(image, caldir, read_pattern, keep_stacks=len(mine), **kw)
     try:
         for j in mine:
             R.step(seed + 10 * (j + 1))
         R.torch.cuda.synchronize(R.dev)
+        if ranks > 1:
+            combine_ranks(R, Nrun, ranks, group)
         return R.finalize(slope_ideal=slope_ideal, emulate_alias=emulate_alias)
     finally:
         R.close()
+
+
+def combine_ranks(R, Nrun, ranks, group=None):
+    """Sum the raw moment planes of all ranks and gather their stacks (the one exchange step of this workload)."""
+    import torch.distributed as dist  # noqa: PLC0415
+
+    torch = R.torch
+    dist.all_reduce(R.d_moments, group=group)
+    kmax = (Nrun + ranks - 1) // ranks
+    if not kmax:
+        return
+    n = R.n
+    gathered = []
+    for name in ("d_diffs", "d_images", "d_err"):
+        mine = getattr(R, name, None)
+        pad = torch.zeros((kmax, n, n), dtype=torch.float32, device=R.dev)
+        if mine is not None and R.done:
+            pad[: R.done] = mine[: R.done]
+        parts = [torch.empty_like(pad) for _ in range(ranks)]
+        dist.all_gather(parts, pad, group=group)
+        # rank r holds the realisations j = r, r + ranks, ...: its first len(range(r, Nrun, ranks)) slices are valid
+        gathered.append(torch.cat([parts[r][: len(range(r, Nrun, ranks))] for r in range(ranks)]))
+    R.d_diffs, R.d_images, R.d_err = gathered
+    R.keep = R.done = Nrun

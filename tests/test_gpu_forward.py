@@ -116,3 +116,103 @@ def test_apportioning_terminates_in_every_regime():
     assert 0.6 < np.median(ratio) < 1.2, np.median(ratio)
     # intermediate groups sit between the first and the last (cumulative counts are monotone)
     assert np.all(out[3][big] <= out[-1][big] + 1) and np.all(out[3][big] >= out[0][big] - 1)
+
+
+def test_cosmic_rays_statistics_against_oracle():
+    """Cosmic-ray injection (fwd_cr_kernel, restating romanisim.cr.simulate_crs: parity unpinned) against ensembles of
+    the oracle's NumPy restatement: number of events (Poisson), pixels per event, electrons per event, distribution
+    over the groups, persistence of the deposit through the later reads, JUMP_DET in the returned dq."""
+    import ctypes as C
+
+    from romanimpreprocess_b200 import _lib, synth
+    from romanimpreprocess_b200.dqflags import pixel
+    from romanimpreprocess_b200.from_sim import sim_to_isim as s2i
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+
+    n, rp = 512, synth.README_PATTERN
+    na, nreads = n - 8, sum(len(g) for g in rp)
+    cal = synth.make_caldir(n=n, seed=61, read_pattern=rp, p_order=3, gain_dtype=np.float32, ipc_dtype=np.float32,
+                            biascorr_amp=3.0)  # fmt: skip
+    counts = np.zeros((na, na), np.int32)  # no scene: every electron of the cumulative cube is a cosmic-ray electron
+    area = 4.0  # cm^2: 8 * 4 * 3.04 = 97 events per read on 504^2 pixels (a few % of the pixels are hit in total)
+    lam_total = 8.0 * area * s2i.READ_TIME * (rp[-1][-1] - 0)  # reads at t = 3.04 k, k = 0..34: the first has dt = 0
+    stats = []
+    with gci.CalDir(cal) as cd:
+        for seed in (7, 8, 9):
+            out, dq = s2i.make_l1_fullcal(counts, rp, cd, seed=seed, add_reset_noise=False, add_read_noise=False,
+                                          crparam={"area": area})  # fmt: skip
+            cum = np.empty((nreads, na, na), np.int32)
+            _lib.check(_lib.lib().rip_fwd_cum_counts_host(cd.handle, nreads, _lib.ptr(cum)))
+            crg = np.empty((na, na), np.uint32)
+            _lib.check(_lib.lib().rip_fwd_cr_groups_host(cd.handle, _lib.ptr(crg)))
+            assert np.all(np.diff(cum.astype(np.int64), axis=0) >= 0)  # the deposit stays in the well
+            assert np.array_equal(crg != 0, cum[-1] > 0)
+            k = 0
+            for g, grp in enumerate(rp):  # bit g <=> the cumulative count rose during a read of group g
+                rose = np.zeros((na, na), bool)
+                for _ in grp:
+                    rose |= (cum[k] - (cum[k - 1] if k else 0)) > 0
+                    k += 1
+                assert np.array_equal(((crg >> g) & 1).astype(bool), rose)
+                assert np.array_equal((dq[g] & pixel.JUMP_DET) != 0, rose)
+            # a hit pixel's resultants rise with the deposit: the last resultant exceeds the first where electrons landed
+            hit = cum[-1] > 2000
+            assert np.mean((out[-1] - out[0])[hit]) > 50.0 * np.mean(np.abs((out[-1] - out[0])[~(cum[-1] > 0)]) + 1e-3)
+            per_group = np.array([np.count_nonzero((crg >> g) & 1) for g in range(len(rp))], float)
+            stats.append((np.count_nonzero(cum[-1] > 0), float(cum[-1].astype(np.int64).sum()), per_group))
+    # oracle ensemble with the same parameters (reads 1..34 have dt = read_time)
+    ref = []
+    for seed in (1, 2, 3):
+        rng = np.random.default_rng(seed)
+        img = np.zeros((na, na), np.int64)
+        nev = 0
+        for _ in range(rp[-1][-1]):
+            _, m = orc.simulate_crs(img, s2i.READ_TIME, rng, area=area)
+            nev += m
+        ref.append((np.count_nonzero(img), float(img.sum()), nev))
+    npx, ne = np.mean([s[0] for s in stats]), np.mean([s[1] for s in stats])
+    rpx, re_, rev = np.mean([r[0] for r in ref]), np.mean([r[1] for r in ref]), np.mean([r[2] for r in ref])
+    assert abs(rev - lam_total) < 5 * np.sqrt(lam_total / 3)  # the oracle draws Poisson(lam) events
+    # ~3300 events per run, ~2.8 pixels each: 3 runs against 3 runs -> a few % statistical error on the pixel count; the
+    # electrons per event are heavy-tailed (Moyal dE/dx x power-law length): wider tolerance
+    assert abs(npx - rpx) < 0.06 * rpx, (npx, rpx)
+    assert abs(ne - re_) < 0.15 * re_, (ne, re_)
+    # hits per group follow the group durations (group 0 is the read at t = 0: no cosmic rays)
+    per_group = np.sum([s[2] for s in stats], axis=0)
+    dur = np.array([len(g) for g in rp], float)
+    dur[0] -= 1.0
+    expect = per_group.sum() * dur / dur.sum()
+    assert per_group[0] == 0
+    assert np.all(np.abs(per_group[1:] - expect[1:]) < 6 * np.sqrt(expect[1:]) + 0.03 * expect[1:])
+    (C, pixel)
+
+
+def test_cosmic_ray_jump_count_like_the_reference_workflow():
+    """Port of the reference's end-to-end bound (tests/romanimpreprocess/test_workflow.py:623-627): a simulated
+    4088^2 exposure with romanisim's default cosmic rays (crparam={}, from_sim/sim_to_isim.py:238), its 14-read test
+    pattern, calibrated through L1->L2, shows between 10 000 and 30 000 JUMP_DET pixels."""
+    import torch
+
+    from romanimpreprocess_b200 import synth
+    from romanimpreprocess_b200.dqflags import pixel
+    from romanimpreprocess_b200.validation_tests import many_realizations as mr
+
+    n, rp = 4096, synth.TEST_READ_PATTERN
+    cal = synth.make_caldir(n=n, seed=71, read_pattern=rp, p_order=3, gain_dtype=np.float32, ipc_dtype=np.float32,
+                            biascorr_amp=3.0)  # fmt: skip
+    na = n - 8
+    image = np.full((na, na), 1.0, np.float32)  # flat 1 e/s/pixel sky, as the reference's blank test scene
+    z = mr.Realizations(image, cal, rp, keep_stacks=0, crparam={})
+    try:
+        z.step(200)
+        torch.cuda.synchronize()
+        pdq = z.d_pdq.cpu().numpy().view(np.uint32)
+        count = int(np.count_nonzero(pdq & np.uint32(pixel.JUMP_DET)))
+        z0 = mr.Realizations(image, z.cal, rp, keep_stacks=0, crparam=None)
+        z0.step(200)
+        torch.cuda.synchronize()
+        count0 = int(np.count_nonzero(z0.d_pdq.cpu().numpy().view(np.uint32) & np.uint32(pixel.JUMP_DET)))
+    finally:
+        z.close()
+    assert 10000 < count < 30000, (count, count0)
+    assert count0 < 2000, count0  # without cosmic rays only the false-positive tail of the jump test remains

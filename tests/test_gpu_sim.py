@@ -221,6 +221,11 @@ def test_sim_counts_statistics():
     d = (c2 - counts).astype(np.float64)
     lam = np.clip(this_dark, 0, None) * t
     assert np.all(d >= 0) and abs(d.mean() - lam.mean()) < 5 * np.sqrt(lam.mean() / d.size) + 1e-3
+    # sky background term of romanisim's simulate_counts (restated): Poisson(sky * this_flat * t) on top
+    c3 = s2i.simulate_counts(np.zeros_like(image), cal, pattern, seed=5, area_ratio=area, sky=1.5)
+    lam3 = 1.5 * this_flat.astype(np.float64) * t
+    z3 = (c3 - lam3) / np.sqrt(lam3)
+    assert abs(z3.mean()) < 5 / np.sqrt(z3.size) and abs(z3.var() - 1.0) < 0.05, (z3.mean(), z3.var())
 
 
 def test_mask_build_exact():

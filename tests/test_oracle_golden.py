@@ -298,3 +298,25 @@ def test_band_tiled_oracle_equals_whole_frame():
     for k in ("slope", "err_read", "err_poisson", "pdq", "rdq", "endslice"):
         assert np.array_equal(ref[k], tiled[k], equal_nan=True), k
     assert np.count_nonzero(ref["pdq"] & orc.GW_AFFECTED_DATA) > np.count_nonzero(c["mask"]["dq"] & orc.GW_AFFECTED_DATA)
+
+
+def test_reference_function_chain_equals_the_oracle_port():
+    """oracle/ref_chain.py (the reference's own unmodified functions from oracle/_ref, the CPU baseline of bench.py) and the
+    oracle port give identical L2 arrays: pins the port's glue against the reference functions on whole chains."""
+    from oracle import ref_chain
+    from romanimpreprocess_b200 import synth
+
+    if not ref_chain.available():
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py needs /root/reference)")
+    for n, rp, po, gdt, kdt, cfg in ((72, synth.README_PATTERN, 10, np.float32, np.float32, {"SLICEOUT": True}),
+                                     (64, synth.TEST_READ_PATTERN, 3, np.float64, np.float64, {"EXCLUDE_FIRST": False}),
+                                     (64, synth.LONG16_PATTERN, 10, np.float32, np.float64, {"SATURATION_BACKUP": 2})):  # fmt: skip
+        cal = synth.make_caldir(n=n, seed=5, read_pattern=rp, p_order=po, gain_dtype=gdt, ipc_dtype=kdt, sprinkle_flags=True,
+                                biascorr_amp=3.0)  # fmt: skip
+        data, amp33, _ = synth.make_l1(cal, rp, seed=6, n_sources=9, cr_frac=0.01, bright=6.0)
+        c = {k: v["roman"] for k, v in cal.items()}
+        area = synth.make_area_factor(n, np.float64)
+        a = orc.l1_to_l2(data, amp33, c, rp, synth.FRAME_TIME, area, cfg, do_refpix=False)
+        b = ref_chain.l1_to_l2(data, amp33, c, rp, synth.FRAME_TIME, area, cfg, do_refpix=False)
+        for k in ("slope", "err_read", "err_poisson", "pdq", "rdq", "endslice"):
+            assert np.array_equal(a[k], b[k], equal_nan=a[k].dtype.kind == "f"), (n, k)

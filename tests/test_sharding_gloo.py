@@ -67,3 +67,19 @@ def test_single_process_needs_no_group():
     assert sorted(sum(parts, [])) == items
     assert max(map(len, parts)) - min(map(len, parts)) <= 1
     assert sharding.resident_scas(parts[0]) == [1, 9, 17]
+
+
+def test_balanced_assignment_18_scas_on_8_ranks():
+    sys.path.insert(0, ROOT)
+    from romanimpreprocess_b200 import sharding
+
+    items = [(e, s) for e in range(4) for s in range(1, 19)]  # 4 exposures x 18 SCAs = 72 items
+    parts = [sharding.assign_items_balanced(items, r, 8) for r in range(8)]
+    assert sorted(sum(parts, [])) == sorted(items)  # disjoint cover
+    assert {len(p) for p in parts} == {9}  # 72 / 8, where SCA-major dealing gives 12/12/8/8/...
+    assert sharding.imbalance(items, 8) == 1.0
+    assert sharding.imbalance(items, 8, sharding.assign_items) == pytest.approx(12 / 9.0)
+    assert max(len(sharding.resident_scas(p)) for p in parts) <= 4  # 2 own SCAs + at most the 2 leftover ones
+    for w in (1, 2, 4):
+        ps = [sharding.assign_items_balanced(items, r, w) for r in range(w)]
+        assert sorted(sum(ps, [])) == sorted(items) and max(map(len, ps)) - min(map(len, ps)) <= 1
