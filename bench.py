@@ -765,7 +765,7 @@ def run_exposure18(args):
         dist.all_reduce(nres)
     if rank == 0:
         h2d = int(exposures[0][0].nbytes + exposures[0][1].nbytes + 8 * 211)
-        d2h = int(sum(v.nbytes for v in outs[0].values()))
+        d2h = int(sum(v.nbytes for v in outs[0].values() if isinstance(v, np.ndarray)))
         print(json.dumps({
             "metric": "18-SCA WFI exposures/sec through L1->L2 (4096^2 x 8 resultants per SCA)", "value": value,
             "unit": "exposures/s", "sca_per_s": value * NSCA, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
