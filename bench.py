@@ -792,7 +792,7 @@ def run_exposure18(args):
 
 def run_noiselayers(args):
     """Secondary workload (the production call pattern of runs/summer2025run/OpenUniverse_to_L1L2.py:
-    124-133): per exposure `--layers` noise layers (half "Rz4PbrS2C<i>", half "Rz4S2C<i>") with SKYORDER 2 = (2 + layers) full L1->L2 calibrations,
+    124-133): per exposure `--layers` noise layers (half "Rz4PbrS2C<i>", half "Rz4OS2C<i>": the production list) with SKYORDER 2 = (2 + layers) full L1->L2 calibrations,
     white + correlated noise generation (34 x 8 FFTs of 2^20 points per layer), sky-mode fits, differences; device
     resident except the z-clip percentiles and the returned layers (host)."""
     import torch
@@ -813,9 +813,8 @@ def run_noiselayers(args):
     d_data = torch.from_numpy(exposures[0][0].view(np.int16)).to(dev).view(torch.uint16)
     d_amp = torch.from_numpy(exposures[0][1].view(np.int16)).to(dev).view(torch.uint16)
     d_area = torch.from_numpy(area).to(dev)
-    # the production list is 4 x "Rz4PbrS2C*" + 4 x "Rz4OS2C*"; the Pearson draws of "O" are not on the GPU path, those
-    # layers run here without them
-    layers = [f"Rz4PbrS2C{i + 1}" if i < args.layers // 2 else f"Rz4S2C{i + 1}" for i in range(args.layers)]
+    # the production list: 4 x "Rz4PbrS2C*" + 4 x "Rz4OS2C*" (runs/summer2025run/OpenUniverse_to_L1L2.py:124-133)
+    layers = [f"Rz4PbrS2C{i + 1}" if i < args.layers // 2 else f"Rz4OS2C{i + 1}" for i in range(args.layers)]
     nl.set_exposure(d_data, d_amp, d_area)
     nl.layer(layers[0], 1)  # warm-up: workspaces, FFT attributes, the reference calibration of the dark cube
     torch.cuda.synchronize()
@@ -833,7 +832,7 @@ def run_noiselayers(args):
     for lay in kept:  # (outside the timed region) robust scatter of each layer of the last exposure
         q = np.percentile(lay[8:-8, 8:-8], [25, 75])
         sig.append(float((q[1] - q[0]) / 1.34896))
-    print(json.dumps({"metric": "noise-layer exposures/s (gen_noise_image, 4096^2 x 8 resultants, layers Rz4PbrS2C* / Rz4S2C*, SKYORDER 2)",
+    print(json.dumps({"metric": "noise-layer exposures/s (gen_noise_image, 4096^2 x 8 resultants, layers Rz4PbrS2C* / Rz4OS2C*, SKYORDER 2)",
                       "value": 1.0 / dt, "unit": "exposures/s", "layers_per_exposure": len(layers),
                       "ms_per_layer": 1e3 * dt / len(layers), "n_gpus": 1, "steps": args.steps, "dtype": "f32", "data": "synthetic",
                       "secondary_workload": True, "timing": "wall clock incl. the D2H of every layer (pinned buffers) and the host-side normal equations of the sky fits",

@@ -391,6 +391,14 @@ int rip_clip_dev(int device, float* d_arr, long count, float lo, float hi, void*
 int rip_poisson_resample_dev(rip_caldir* h, const float* d_skylevel, const int8_t* d_endslice, int G, int n_samp,
                              const int32_t* group_of_read, const float* weights, const uint8_t* w_defined, double frame_time,
                              uint64_t seed, float* d_diff, void* stream);
+/* Noise directive "O" (L1_to_L2/gen_noise_image.py:173-227 -> GalPoisson/draw_with_tilnus.py:12, find_tilnus.py:46):
+ * d_diff f32 [na,na] += Pearson draw / clip(gain, 1e-4, 1e4) with I = max(gain * d_withsky, 0.01) and the moments
+ * tilnu[i] = (nu21, nu31, nu41) [e/s units] of the ramp ending at group i = (endslice > 0 ? endslice : G-1); rows with
+ * defined[i] == 0 and i <= start draw nothing.  Pearson Type I (Beta) is generated on the device; pixels that fall into
+ * Types III-VI are counted in *d_unsupported (device int32, zeroed by the caller) and draw 0. */
+int rip_pearson_noise_dev(rip_caldir* h, const float* d_withsky, const int8_t* d_endslice, int G, int start,
+                          const double* tilnu, const uint8_t* defined, uint64_t seed, float* d_diff,
+                          int32_t* d_unsupported, void* stream);
 
 /* ---- pixel area from the WCS (utils/coordutils.py:17-82 pixelarea, used at L1_to_L2/gen_cal_image.py:618-622 with the
  * FITSWCS header of :82-83).  wcs = 211 doubles describing a zenithal FITS WCS with SIP:

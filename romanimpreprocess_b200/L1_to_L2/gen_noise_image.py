@@ -15,8 +15,15 @@ Here every step stays in HBM and shares one resident CALDIR:
 
 Supported directives: ``R`` (flags ``a``, ``z<number>``), ``P`` (flags ``b<order>``, ``r``: re-sampled Poisson noise of
 the sky level propagated through the ramp-fit weights of each pixel's ramp end, ``rip_poisson_resample_dev``),
-``S<order>``, ``C<tag>`` (a label: ignored, as in the reference) -- i.e. the production layers ``Rz4PbrS2C*``.
-``O`` (Pearson pseudo-Poisson draws) is not on the GPU path and raises ``NotImplementedError``.  Random numbers are Philox (the reference: GalSim): layers are validated statistically.
+``O`` (pseudo-Poisson draws from the Pearson family with the moments of the ramp-fitted Poisson noise, reference
+:173-227 -> ``GalPoisson``; ``rip_pearson_noise_dev``), ``S<order>``, ``C<tag>`` (a label: ignored, as in the reference)
+-- i.e. both production layer families ``Rz4PbrS2C*`` and ``Rz4OS2C*`` (runs/summer2025run/OpenUniverse_to_L1L2.py:124-133).
+``O`` generates Pearson Type I (Beta) deviates, the type every Roman read pattern tried here selects (their nu_41 is
+negative); a pixel that falls into Types III-VI raises ``NotImplementedError`` instead of silently drawing nothing.
+Random numbers are Philox (the reference: GalSim / NumPy): layers are validated statistically.
+
+``generate_all_noise(config)`` is the reference's driver (:334-391): layers of ``config["NOISE"]["LAYER"]`` for the exposure
+``config["IN"]``, written to ``config["NOISE"]["OUT"]`` (ASDF tree ``{"config", "noise"}``).
 """
 
 import re
@@ -32,6 +39,22 @@ def _get_subscript(arr, ch):
     """Text after the last ``ch`` in ``arr`` up to (not including) the next capital letter:
     ``_get_subscript('RS2Pg4', 'S') -> '2'`` (reference gen_noise_image.py:33-57)."""
     return re.split(r"(?=[A-Z])", arr.split(ch)[-1])[0]
+
+
+def tilde_nus(read_pattern, weights):
+    """(nu~21, nu~31, nu~41) per frame of the weighted MultiAccum combination ``sum_k weights[k] * resultant_k`` of a unit
+    Poisson rate (GalPoisson/find_tilnus.py:46-78): with L[k, r] = 1/N_k on the reads of group k, T = the reversed
+    cumulative sum of L along the reads (the weight of each read's increment in each resultant) and w = weights . T[:, 1:],
+    nu_p1 = sum(w^p), then nu~21 = nu21, nu~31 = nu31 - 3 nu21^2, nu~41 = nu41 - 10 nu21 nu31 - nu21 * 3 nu21^2 + 18 nu21^3."""
+    nread = max(g[0] + len(g) for g in read_pattern)
+    L = np.zeros((len(read_pattern), nread))
+    for k, g in enumerate(read_pattern):
+        L[k, g[0] : g[0] + len(g)] = 1.0 / len(g)
+    T = np.cumsum(L[:, ::-1], axis=1)[:, ::-1]
+    w = np.dot(np.asarray(weights), T[:, 1:])
+    nu21, nu31, nu41 = np.sum(w**2), np.sum(w**3), np.sum(w**4)
+    nu42 = 3 * nu21**2
+    return nu21, nu31 - 3 * nu21**2, nu41 - 10 * nu21 * nu31 - nu21 * nu42 + 18 * nu21**3
 
 
 def _ptr(t):
@@ -103,8 +126,6 @@ class NoiseLayers:
         """One noise layer [na,na] float32 (host) for the directive string ``cmd``.  ``out``: a float32 [na,na] host array
         to receive it (page-locked memory from ``_lib.pinned_empty`` makes the copy run at PCIe speed)."""
         lib, cal, st = _lib.lib(), self.cal, self._stream()
-        if "O" in cmd:
-            raise NotImplementedError(f"noise directive {cmd!r}: the Pearson draws of 'O' are not generated on the GPU")
         self.d_diff.zero_()
         flags = ""
         if "R" in cmd:
@@ -137,6 +158,31 @@ class NoiseLayers:
                 iqr, med = p75 - p25, p50
                 _lib.check(lib.rip_clip_dev(self.device, _ptr(self.d_diff), self.na * self.na,
                                             float(med - zclip * iqr / 1.34896), float(med + zclip * iqr / 1.34896), st))
+        if "O" in cmd:  # pseudo-Poisson draws from the Pearson family (reference :173-227)
+            if "orig" not in self.have:
+                self._calibrate(self.d_data, self.d_amp33_in, self.d_area, "orig")
+            G, meta = self.G, self.dplan.meta
+            start = 1 if self.config.get("EXCLUDE_FIRST", True) else 0
+            wv = {G - 1: np.array([self.dplan.plan.var_K[0][j] for j in range(G)], np.float32)}  # processinfo weights
+            for iend in range(start + 2, G):
+                kt = np.zeros(G, dtype=np.float32)
+                kt[iend - 1] = 1.0 / (meta["tbar"][iend - 1] - meta["tbar"][start])
+                kt[start] = -kt[iend - 1]
+                wv[iend - 1] = kt
+            tab, defined = np.zeros((G, 3), np.float64), np.zeros(G, np.uint8)
+            t_fr = self.frame_time
+            for i in range(start + 1, G):
+                n21, n31, n41 = tilde_nus(self.read_pattern, wv[i])
+                tab[i] = (n21 * t_fr, n31 * t_fr**2, n41 * t_fr**3)  # e/frame -> e/s (reference :212-216)
+                defined[i] = 1
+            bad = self.torch.zeros(1, dtype=self.torch.int32, device=self.dev)
+            _lib.check(lib.rip_pearson_noise_dev(cal.handle, _ptr(self.d_withsky), _ptr(self.d_endslice), G, start,
+                                                 _lib.ptr(tab), _lib.ptr(defined), (int(seed) + 13) & 0xFFFFFFFFFFFFFFFF,
+                                                 _ptr(self.d_diff), _ptr(bad), st))  # fmt: skip
+            nbad = int(bad.item())
+            if nbad:
+                raise NotImplementedError(f"noise directive {cmd!r}: {nbad} pixels need Pearson Types III-VI, which are not "
+                                          "generated on the GPU (only Type I, the one Roman read patterns select)")  # fmt: skip
         if "P" in cmd:
             pflags = _get_subscript(cmd, "P")
             if "orig" not in self.have:
@@ -204,3 +250,62 @@ def make_noise_cube_arrays(data, amp33, caldir, read_pattern, frame_time, layers
         return out
     finally:
         nl.close()
+
+
+def _fits_cube(path, cube):
+    """Minimal FITS primary HDU for a float32 cube (the reference's FITSOUT side product, :386-390)."""
+    a = np.ascontiguousarray(cube, dtype=">f4")
+    cards = [f"{'SIMPLE':<8}= {'T':>20}", f"{'BITPIX':<8}= {-32:>20}", f"{'NAXIS':<8}= {a.ndim:>20}"]
+    cards += [f"{'NAXIS' + str(i + 1):<8}= {d:>20}" for i, d in enumerate(a.shape[::-1])]
+    cards.append("END")
+    hdr = "".join(c.ljust(80) for c in cards)
+    hdr += " " * (-len(hdr) % 2880)
+    with open(path, "wb") as f:
+        f.write(hdr.encode("ascii"))
+        f.write(a.tobytes())
+        f.write(b"\0" * (-a.nbytes % 2880))
+
+
+def generate_all_noise(config, device=0):
+    """
+    Driver for noise generation: the reference's ``generate_all_noise`` (L1_to_L2/gen_noise_image.py:334-391) with the
+    same configuration keys -- ``config["NOISE"]`` holds ``LAYER`` (list of directive strings), ``SEED``, ``OUT`` (``TEMP`` is
+    accepted and unused: nothing goes through temporary files here).  Reads the L1 exposure ``config["IN"]``; the L2
+    quantities the reference takes from ``config["OUT"]`` (``data``, ``data_withsky``, weights, endslice) are recomputed on
+    the device from the same inputs.  Writes ``{"config", "noise"}`` (float32, or float16 with ``NOISE_PRECISION: 16``).
+    """
+    import torch  # noqa: PLC0415
+
+    from ..caltree import write_tree  # noqa: PLC0415
+    from ..utils import coordutils  # noqa: PLC0415
+
+    noise = config["NOISE"]
+    if config.get("NOISE_PRECISION", 32) not in (16, 32):
+        raise ValueError("Unsupported noise precision.")
+    data, amp33, read_pattern, frame_time, _, _ = gci.read_l1(config["IN"])
+    ent = gci._cached_caldir(config["CALDIR"], device)
+    cal = ent["cal"]
+    nl = NoiseLayers(cal, read_pattern, frame_time, {**config, "SLICEOUT": True}, device)
+    dev = nl.dev
+    d_data = torch.from_numpy(np.array(data, dtype=np.uint16).view(np.int16)).to(dev).view(torch.uint16)
+    a33 = np.array(amp33, dtype=np.uint16) if amp33 is not None else np.zeros((data.shape[0], cal.n, 128), np.uint16)
+    d_amp = torch.from_numpy(np.ascontiguousarray(a33).view(np.int16)).to(dev).view(torch.uint16)
+    d_area = None
+    wcs = coordutils.wcs_from_config(config)
+    if wcs is not None:  # AreaFactor of the exposure (gen_cal_image.py:618-621), as calibrateimage used it
+        area = coordutils.pixelarea_device(wcs, N=cal.n, inv_omega=1.0 / gci.pars.Omega_ideal, dtype=np.float32, device=device)
+        d_area = torch.from_numpy(np.ascontiguousarray(area, dtype=np.float32)).to(dev)
+    nl.set_exposure(d_data, d_amp, d_area)
+    layers = list(noise["LAYER"])
+    noiseimage = np.zeros((len(layers), nl.na, nl.na), np.float32)
+    for i, cmd in enumerate(layers):
+        noiseimage[i] = nl.layer(cmd, int(noise["SEED"]) + 1000 * (i + 1))
+    print(noiseimage.shape)
+    print("percentiles:")
+    for q in (5, 25, 50, 75, 95):
+        print(q, np.percentile(noiseimage, q, axis=(1, 2)))
+    if config.get("NOISE_PRECISION", 32) == 16:
+        noiseimage = noiseimage.astype(np.float16)
+    write_tree(noise["OUT"], {"config": gci._plain_copy(config), "noise": noiseimage})
+    if config.get("FITSOUT", False):
+        _fits_cube(noise["OUT"][:-5] + "_asdf_to.fits", noiseimage.astype(np.float32))

@@ -171,6 +171,8 @@ _SIGS = {
     "rip_order_stats_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_long),
                                       C.c_void_p]),
     "rip_clip_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_long, C.c_float, C.c_float, C.c_void_p]),
+    "rip_pearson_noise_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rip_poisson_resample_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_double, C.c_uint64, C.c_void_p, C.c_void_p]),
     "rip_stack_median_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p]),

@@ -44,7 +44,7 @@ struct Philox {
     // in [2^-24, 1 - 2^-24]; the earlier 24-bit form rounded its top value to exactly 1.0f.
     // Stream ids in use (one purpose each, disjoint): 1 apportioning, 2/3 scene Poisson, 8 reset noise of the reference
     // pixels, 16+g forward read noise, 32+g / 48+g reference-pixel and white noise per group, 96+k noise-layer draws,
-    // 128 Poisson re-sampling, 200 / 201 cosmic-ray counts / events, 1024+ 1/f frames.
+    // 128 Poisson re-sampling, 160 Pearson draws, 200 / 201 cosmic-ray counts / events, 1024+ 1/f frames.
     __device__ __forceinline__ float uniform() { return ((float)(next() >> 9) + 0.5f) * (1.0f / 8388608.0f); }
     // uniform in (0,1), 53-bit
     __device__ __forceinline__ double uniform53() {

@@ -1108,6 +1108,113 @@ __global__ void poisson_resample_kernel(const PoisArgs A, const float* __restric
 
 }  // namespace rip
 
+namespace rip {
+
+// ---------------------------------------------------------------------------------------------------------
+// Noise directive "O" (reference L1_to_L2/gen_noise_image.py:173-227): pseudo-Poisson draws from the Pearson family with
+// the 2nd-4th moments of the ramp-fitted Poisson noise, diff += draw / gain.  Per active pixel: I = max(gain *
+// data_withsky, 0.01), the (tilde nu_21, nu_31, nu_41) of the pixel's ramp end, beta_1 = nu31^2 / (nu21^3 I),
+// beta_2 = (3 nu21^2 I + nu41) / (nu21^2 I); outside the admissible region the draw is 0
+// (GalPoisson/draw_with_tilnus.py:42-60); below the Type III line (beta_2 < 1.5 beta_1 + 3) the Pearson Type I = a
+// shifted and scaled Beta(a, b) with (a, b) from the closed form of :160-198 -- the only type the production read
+// patterns reach (their nu_41 is negative).  Types III-VI are counted in *unsupported and draw 0: the host raises.
+// Beta(a, b) = X / (X + Y) with Gamma variates by Marsaglia & Tsang (2000).
+// ---------------------------------------------------------------------------------------------------------
+__device__ inline double gamma_draw(Philox& rng, double a) {
+    double boost = 1.0;
+    if (a < 1.0) {  // Gamma(a) = Gamma(a + 1) U^(1/a)
+        boost = pow(rng.uniform53(), 1.0 / a);
+        a += 1.0;
+    }
+    const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (int it = 0; it < 64; ++it) {
+        float xa, xb;
+        rng.normal2(xa, xb);
+        const double x = (double)xa;
+        const double t = 1.0 + c * x;
+        if (t <= 0.0) continue;
+        const double v = t * t * t;
+        const double u = rng.uniform53();
+        if (u < 1.0 - 0.0331 * (x * x) * (x * x) || log(u) < 0.5 * x * x + d * (1.0 - v + log(v))) return boost * d * v;
+    }
+    return boost * d;  // (never reached in practice: acceptance > 95 % per trial)
+}
+
+struct PearsonArgs {
+    int n, nb, G, start;
+    double nu21[RIP_GMAX], nu31[RIP_GMAX], nu41[RIP_GMAX];
+    unsigned char defined[RIP_GMAX];
+    uint64_t seed;
+};
+
+template <typename TG>
+__global__ void pearson_noise_kernel(const PearsonArgs A, const float* __restrict__ withsky, const TG* __restrict__ gain,
+                                     const int8_t* __restrict__ endslice, float* __restrict__ diff, int* __restrict__ unsupported) {
+    const int na = A.n - 2 * A.nb;
+    const int xa = blockIdx.x * blockDim.x + threadIdx.x, ya = blockIdx.y;
+    if (xa >= na) return;
+    const long p = (long)ya * na + xa, q = (long)(ya + A.nb) * A.n + (xa + A.nb);
+    const int es0 = endslice ? (int)endslice[p] : 0;
+    const int es = es0 > 0 ? es0 : A.G - 1;  // np.where(endslice > 0, endslice, ngrp - 1)
+    if (es < A.start + 1 || es >= A.G || !A.defined[es]) return;
+    typedef typename Promote<float, TG>::type TP;
+    const TP g = np_clip<TP>((TP)gain[q], (TP)1e-4, (TP)1e4);
+    const double gI = (double)(g * (TP)withsky[p]);
+    const double I = gI < 0.01 ? 0.01 : gI;  // np.clip(., 0.01, None): NaN stays NaN -> every test below is false
+    const double n21 = A.nu21[es], n31 = A.nu31[es], n41 = A.nu41[es];
+    const double b1 = n31 * n31 / (n21 * n21 * n21 * I);
+    const double b2 = (3.0 * n21 * n21 * I + n41) / (n21 * n21 * I);
+    const bool base = (b2 > 0.0) && (b1 >= 0.0) && (b2 > b1 + 1.0) && (b2 > 0.75 * b1);
+    if (!base) return;
+    const double rhs1 = 1.5 * b1 + 3.0;
+    if (!(b2 < rhs1)) {  // Types III (==), VI, V, IV
+        const double rhs2 = (48.0 + 39.0 * b1 + 6.0 * pow(4.0 + b1, 1.5)) / (32.0 - b1);
+        if (b2 == rhs1 || b2 == rhs2 || (b2 > rhs1 && b2 < rhs2) || (b2 > rhs2 && b1 < 32.0)) atomicAdd(unsupported, 1);
+        return;
+    }
+    // Type I: u = a + b, v = (a - b)^2 / (a b)
+    const double u = 3.0 * (b1 - b2 + 1.0) / ((b2 - 3.0) - 1.5 * b1);
+    const double v = b1 * (u + 2.0) * (u + 2.0) / (4.0 * (u + 1.0));
+    const double sq = sqrt(v / (v + 4.0));
+    const double ap = 0.5 * u * (1.0 + sq), bp = 0.5 * u * (1.0 - sq);
+    const bool cond = (n31 < 0.0) ? (ap > bp) : (ap < bp);  // sign of the skew picks the branch
+    const double a = cond ? ap : bp, b = cond ? bp : ap;
+    const double mean = a / (a + b), var = a * b / ((a + b) * (a + b) * (a + b + 1.0));
+    const double scale = sqrt(n21 * I / var);
+    if (!(a > 0.0) || !(b > 0.0) || !(scale == scale)) return;
+    Philox rng;
+    rng.init(A.seed, (uint64_t)p, 160u);
+    const double X = gamma_draw(rng, a), Y = gamma_draw(rng, b);
+    const double y = X / (X + Y);
+    diff[p] = (float)((TP)diff[p] + (TP)(float)(scale * (y - mean)) / g);
+}
+
+}  // namespace rip
+
+// tilnu: [G][3] = (nu21, nu31, nu41) in e/s units of the ramp ending at group i (rows with defined[i] == 0 are skipped);
+// d_unsupported: device int counter of pixels whose Pearson type is not I (the caller zeroes it and reads it back)
+extern "C" int rip_pearson_noise_dev(rip_caldir* h, const float* d_withsky, const int8_t* d_endslice, int G, int start,
+                                     const double* tilnu, const uint8_t* defined, uint64_t seed, float* d_diff,
+                                     int32_t* d_unsupported, void* stream) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && d_withsky && tilnu && defined && d_diff && d_unsupported, "rip_pearson_noise_dev: null argument");
+    RIP_REQUIRE(G >= 1 && G <= RIP_GMAX && start >= 0, "rip_pearson_noise_dev: G=%d / start=%d out of range", G, start);
+    use_device(h->device);
+    PearsonArgs A;
+    memset(&A, 0, sizeof A);
+    A.n = h->n; A.nb = h->nb; A.G = G; A.start = start; A.seed = seed;
+    for (int i = 0; i < G; ++i) {
+        A.nu21[i] = tilnu[3 * i]; A.nu31[i] = tilnu[3 * i + 1]; A.nu41[i] = tilnu[3 * i + 2];
+        A.defined[i] = defined[i];
+    }
+    dim3 grid((h->na + 127) / 128, h->na);
+    if (h->d.gain_dtype == RIP_F64)
+        RIP_LAUNCH(pearson_noise_kernel<double>, grid, 128, 0, (cudaStream_t)stream, A, d_withsky, (const double*)h->gain.p, d_endslice, d_diff, (int*)d_unsupported);
+    else
+        RIP_LAUNCH(pearson_noise_kernel<float>, grid, 128, 0, (cudaStream_t)stream, A, d_withsky, (const float*)h->gain.p, d_endslice, d_diff, (int*)d_unsupported);
+    RIP_API_END
+}
+
 extern "C" int rip_poisson_resample_dev(rip_caldir* h, const float* d_skylevel, const int8_t* d_endslice, int G, int n_samp,
                                         const int32_t* group_of_read, const float* weights /*[G][G] row es*/,
                                         const uint8_t* w_defined, double frame_time, uint64_t seed, float* d_diff, void* stream) {

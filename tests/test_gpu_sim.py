@@ -475,8 +475,9 @@ def test_noise_layers_against_oracle_composition():
         assert np.abs(model).max() < 0.02 * robust_sigma(lay[inner])
     # 'a': built on the exposure itself -> same noise level
     assert abs(robust_sigma(layers[2][inner]) / sg - 1.0) < 0.25
-    with pytest.raises(NotImplementedError):
-        gni.make_noise_cube_arrays(data, amp33, cal, rp, synth.FRAME_TIME, ["Rz4OS2C5"], seed=5, config=cfg)
+    # the second production family runs too (directive 'O': test_noise_layer_pearson_directive_moments)
+    lo = gni.make_noise_cube_arrays(data, amp33, cal, rp, synth.FRAME_TIME, ["Rz4OS2C5"], seed=5, config=cfg)
+    assert lo.shape == (1, n - 8, n - 8) and np.all(np.isfinite(lo)) and 0.8 < robust_sigma(lo[0][inner]) / sg < 2.0
 
 
 def test_noise_layer_poisson_resampling():
@@ -534,3 +535,100 @@ def test_percentiles_device():
     a[3] = np.nan
     d = torch.from_numpy(a).cuda()
     assert all(np.isnan(v) for v in sky.percentiles_device(d.data_ptr(), a.size, (25, 75)))
+
+
+def test_noise_layer_pearson_directive_moments():
+    """Directive 'O' (reference gen_noise_image.py:173-227, GalPoisson/draw_with_tilnus.py): the draws have the moments
+    the Pearson family is solved for -- variance nu21 I, third central moment nu31 I, fourth 3 nu21^2 I^2 + nu41 I (in
+    electrons; the layer is draw / gain) -- for ramps ending at two different groups, and 0 where the admissibility test
+    of the reference fails; a pattern / weight combination that needs another Pearson type raises."""
+    import torch
+
+    from romanimpreprocess_b200 import _lib, synth
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+    from romanimpreprocess_b200.L1_to_L2 import gen_noise_image as gni
+
+    n, rp = 520, synth.README_PATTERN
+    G, na = len(rp), n - 8
+    cal = synth.make_caldir(n=n, read_pattern=rp, p_order=3, seed=33, gain_dtype=np.float32, ipc_dtype=np.float32)
+    gain = np.clip(_trees(cal)["gain"]["data"][4:-4, 4:-4], 1e-4, 1e4).astype(np.float64)
+    levels = [1e-4, 0.5, 5.0, 50.0, 5000.0]  # electrons/s of gain * data_withsky, one band of rows each
+    band = na // len(levels)
+    I = np.zeros((na, na))
+    for k, v in enumerate(levels):
+        I[k * band : (k + 1) * band if k < len(levels) - 1 else na] = v
+    withsky = (I / gain).astype(np.float32)
+    ends = np.full((na, na), -1, np.int8)  # -1 / 0: the full ramp (row G-1 of the table)
+    ends[:, na // 2 :] = 2  # right half: ramps truncated after group 2 (two-point weights)
+    meta = gci.exposure_meta(rp, synth.FRAME_TIME)
+    plan, _ = gci.ramp_setup(meta, {})
+    K = np.array([plan.var_K[0][j] for j in range(G)], np.float32)
+    kt = np.zeros(G, np.float32)
+    kt[2] = 1.0 / (meta["tbar"][2] - meta["tbar"][1])
+    kt[1] = -kt[2]
+    tab, defined = np.zeros((G, 3)), np.zeros(G, np.uint8)
+    for i, w in ((G - 1, K), (2, kt)):
+        t = gni.tilde_nus(rp, w)
+        tab[i] = (t[0] * synth.FRAME_TIME, t[1] * synth.FRAME_TIME**2, t[2] * synth.FRAME_TIME**3)
+        defined[i] = 1
+    dev = torch.device("cuda", 0)
+    with gci.CalDir(cal) as cd:
+        def run(seed, tab=tab):
+            d_ws, d_es = torch.from_numpy(withsky).to(dev), torch.from_numpy(ends).to(dev)
+            d_diff = torch.zeros((na, na), dtype=torch.float32, device=dev)
+            bad = torch.zeros(1, dtype=torch.int32, device=dev)
+            _lib.check(_lib.lib().rip_pearson_noise_dev(cd.handle, d_ws.data_ptr(), d_es.data_ptr(), G, 1, _lib.ptr(tab),
+                                                        _lib.ptr(defined), seed, d_diff.data_ptr(), bad.data_ptr(), None))
+            torch.cuda.synchronize()
+            return d_diff.cpu().numpy().astype(np.float64) * gain, int(bad.item())
+
+        e, nbad = run(5)
+        e2, _ = run(6)
+        assert nbad == 0 and not np.array_equal(e, e2)
+        for half, row in ((np.s_[:, : na // 2], G - 1), (np.s_[:, na // 2 :], 2)):
+            n21, n31, n41 = tab[row]
+            for k, v in enumerate(levels):
+                x = e[half][k * band + 1 : (k + 1) * band - 1].ravel()
+                b1, b2 = n31**2 / (n21**3 * max(v, 0.01)), (3 * n21**2 * max(v, 0.01) + n41) / (n21**2 * max(v, 0.01))
+                if not ((b2 > 0) and (b2 > b1 + 1) and (b2 > 0.75 * b1)):
+                    assert np.all(x == 0.0), (row, v)  # inadmissible: the reference leaves these pixels at zero
+                    continue
+                Iv, N = max(v, 0.01), x.size
+                m2, m3, m4 = n21 * Iv, n31 * Iv, 3 * n21**2 * Iv**2 + n41 * Iv
+                assert abs(x.mean()) < 5 * np.sqrt(m2 / N), (row, v, x.mean())
+                assert abs(x.var() / m2 - 1) < 6 * np.sqrt((m4 / m2**2 - 1) / N) + 1e-3, (row, v, x.var(), m2)
+                skew, sk_hat = m3 / m2**1.5, np.mean((x - x.mean()) ** 3) / x.var() ** 1.5
+                assert abs(sk_hat - skew) < 6 * np.sqrt(6.0 / N) + 0.05 * abs(skew), (row, v, sk_hat, skew)
+                kurt, ku_hat = m4 / m2**2, np.mean((x - x.mean()) ** 4) / x.var() ** 2
+                assert abs(ku_hat - kurt) < 6 * np.sqrt(24.0 / N) + 0.1 * abs(kurt - 3), (row, v, ku_hat, kurt)
+        # a positive nu41 large enough to leave the Type I region is reported, not silently zeroed
+        tab_bad = tab.copy()
+        tab_bad[:, 2] = np.abs(tab_bad[:, 2]) * 50.0
+        _, nbad = run(7, tab_bad)
+        assert nbad > 0
+
+
+def test_generate_all_noise_driver(tmp_path):
+    """generate_all_noise(config) (reference gen_noise_image.py:334-391) on fixture files: one layer of each production
+    family, written to config['NOISE']['OUT']; the 'O' layer has the variance of the ramp-fitted Poisson noise."""
+    from fixture_files import write_exposure
+
+    from romanimpreprocess_b200.caltree import open_tree
+    from romanimpreprocess_b200.L1_to_L2 import gen_noise_image as gni
+
+    config, cal, data, amp33, rp = write_exposure(str(tmp_path), n=256, ipc_dtype=np.float32)
+    config["SKYORDER"] = 2
+    config["NOISE"] = {"LAYER": ["Rz4PbrS2C1", "Rz4OS2C5", "O"], "TEMP": str(tmp_path / "temp.asdf"), "SEED": 77,
+                       "OUT": str(tmp_path / "noise.asdf")}  # fmt: skip
+    config["NOISE_PRECISION"] = 32
+    gni.generate_all_noise(config)
+    with open_tree(config["NOISE"]["OUT"]) as f:
+        noise = np.asarray(f["noise"])
+        assert list(f["config"]["NOISE"]["LAYER"]) == config["NOISE"]["LAYER"]
+    assert noise.shape == (3, 248, 248) and noise.dtype == np.float32 and np.all(np.isfinite(noise))
+
+    def mad(a):
+        return np.median(np.abs(a - np.median(a)))
+
+    assert 0.5 < mad(noise[0]) / mad(noise[1]) < 2.0  # both families: read noise + a Poisson-like term of the same sky
+    assert 0 < mad(noise[2]) < mad(noise[1])  # the Pearson term alone is the smaller part of the layer

@@ -48,3 +48,16 @@ def test_medfit_solve_against_numpy():
 def test_norm_ppf():
     for p in (0.75, 0.9, 0.6, 0.01, 0.999, 0.5):
         assert abs(sky._norm_ppf(p) - norm.ppf(p)) < 1e-14 * max(1.0, abs(norm.ppf(p)))
+
+
+def test_tilde_nus_against_the_reference_golden():
+    """gen_noise_image.tilde_nus == the reference's GalPoisson/find_tilnus.get_tilde_nus (golden: make_golden_tilnus.py)."""
+    from conftest import load_golden
+    from romanimpreprocess_b200 import synth
+    from romanimpreprocess_b200.L1_to_L2 import gen_noise_image as gni
+
+    g = load_golden("tilnus")
+    for name in ("README_PATTERN", "TEST_READ_PATTERN", "LONG16_PATTERN"):
+        for j in range(3):
+            t = gni.tilde_nus(getattr(synth, name), g[f"{name}_w{j}"])
+            np.testing.assert_allclose(t, g[f"{name}_t{j}"][:3], rtol=1e-13, atol=0)
