@@ -129,6 +129,14 @@ struct SharedDiv {
     }
 };
 
+// two u16 -> f32 exactly with one packed subtraction: (0x4B000000 | v) is 2^23 + v
+RIP_HD f2 u16_pair_to_f32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return sub2p(f2{__uint_as_float(0x4B000000u | a), __uint_as_float(0x4B000000u | b)}, bc(8388608.0f));
+#else
+    return f2{(float)a, (float)b};
+#endif
+}
 // u16 -> f32 exactly, on the full-rate pipes: (0x4B000000 | v) is 2^23 + v
 RIP_HD float u16_to_f32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
@@ -805,30 +813,33 @@ RIP_HD void stage_a1(const Args& A, SM& sm, const Regs<G, P>& R, const StepCtx& 
         satm &= allg & ~1u;
         const uint32_t adf = own >> 16;
         const bool active = C.xact && in_range(row, nb, n - nb);
-        float S[G];
+        // raw u16 -> f32 as group pairs: (2^23 | v) - 2^23 is exact, so the packed subtraction equals the conversion
+        f2 Sp[G / 2];
         {
             const uint16_t* rq = sm.raw(RIP_O5(-2)) + tid;
 #pragma unroll
-            for (int g = 0; g < G; ++g) S[g] = u16_to_f32(rq[g * TW]);
+            for (int j = 0; j < G / 2; ++j) Sp[j] = u16_pair_to_f32((uint32_t)rq[(2 * j) * TW], (uint32_t)rq[(2 * j + 1) * TW]);
         }
         if (A.do_refpix) {  // gen_cal_image.py:535-556: f64 subtractions, f32 stores
             const int chsel = ((x >> 7) != ((C.tile * TS) >> 7)) ? 1 : 0;
-            const double* rc = sm.rc(RIP_O5(-2));
-            const double* ln = sm.ln(RIP_O5(-2)) + chsel * G;
+            const d2* rc = (const d2*)sm.rc(RIP_O5(-2));               // one LDS.128 per group pair
+            const d2* ln = (const d2*)(sm.ln(RIP_O5(-2)) + chsel * G);
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const float dk = r1w<NQ1>(R.r1, g);
-                float v = S[g] - dk;
-                v = (float)((double)v - rc[g]);
-                v = (float)((double)v - ln[g]);
-                S[g] = v + dk;
+            for (int j = 0; j < G / 2; ++j) {
+                const f2 dk = f2{r1w<NQ1>(R.r1, 2 * j), r1w<NQ1>(R.r1, 2 * j + 1)};
+                const f2 v0 = sub2p(Sp[j], dk);  // (no product feeds these packed additions)
+                const d2 rcv = rc[j], lnv = ln[j];
+                float vx = (float)((double)v0.x - rcv.x), vy = (float)((double)v0.y - rcv.y);
+                vx = (float)((double)vx - lnv.x);
+                vy = (float)((double)vy - lnv.y);
+                Sp[j] = add2p(f2{vx, vy}, dk);
             }
         }
         // biascorr (embedded with zeros outside the active region: v - 0 == v)
         f2 S2[G / 2];
 #pragma unroll
         for (int j = 0; j < G / 2; ++j)
-            S2[j] = sub2p(f2{S[2 * j], S[2 * j + 1]}, f2{r1w<NQ1>(R.r1, G + 2 * j), r1w<NQ1>(R.r1, G + 2 * j + 1)});
+            S2[j] = sub2p(Sp[j], f2{r1w<NQ1>(R.r1, G + 2 * j), r1w<NQ1>(R.r1, G + 2 * j + 1)});
         const float Smin = r1w<NQ1>(R.r1, 2 * G), Smax = r1w<NQ1>(R.r1, 2 * G + 1), Sref = r1w<NQ1>(R.r1, 2 * G + 2);
         const float gain = r1w<NQ1>(R.r1, 2 * G + 3);
         const uint32_t aux = f_as_u(r1w<NQ1>(R.r1, 2 * G + 4));
