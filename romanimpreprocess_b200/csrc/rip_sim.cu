@@ -1140,6 +1140,30 @@ __device__ inline double gamma_draw(Philox& rng, double a) {
     return boost * d;  // (never reached in practice: acceptance > 95 % per trial)
 }
 
+// Beta(a, b): Joehnk's algorithm when both shapes are <= 1 (with its log-space branch for draws that underflow -- near
+// the admissibility boundary beta_2 -> beta_1 + 1 the shapes tend to 0 and the distribution to two points), two Gamma
+// variates otherwise: the selection NumPy's generator makes.
+__device__ inline double beta_draw(Philox& rng, double a, double b) {
+    if (a <= 1.0 && b <= 1.0) {
+        for (int it = 0; it < 4096; ++it) {
+            const double U = rng.uniform53(), V = rng.uniform53();
+            const double X = pow(U, 1.0 / a), Y = pow(V, 1.0 / b);
+            const double XpY = X + Y;
+            if (XpY <= 1.0) {
+                if (XpY > 0.0) return X / XpY;
+                double lx = log(U) / a, ly = log(V) / b;
+                const double lm = lx > ly ? lx : ly;
+                lx -= lm;
+                ly -= lm;
+                return exp(lx - log(exp(lx) + exp(ly)));
+            }
+        }
+        return a / (a + b);
+    }
+    const double X = gamma_draw(rng, a), Y = gamma_draw(rng, b);
+    return X / (X + Y);
+}
+
 struct PearsonArgs {
     int n, nb, G, start;
     double nu21[RIP_GMAX], nu31[RIP_GMAX], nu41[RIP_GMAX];
@@ -1184,8 +1208,7 @@ __global__ void pearson_noise_kernel(const PearsonArgs A, const float* __restric
     if (!(a > 0.0) || !(b > 0.0) || !(scale == scale)) return;
     Philox rng;
     rng.init(A.seed, (uint64_t)p, 160u);
-    const double X = gamma_draw(rng, a), Y = gamma_draw(rng, b);
-    const double y = X / (X + Y);
+    const double y = beta_draw(rng, a, b);
     diff[p] = (float)((TP)diff[p] + (TP)(float)(scale * (y - mean)) / g);
 }
 

@@ -601,6 +601,11 @@ def test_noise_layer_pearson_directive_moments():
                 assert abs(sk_hat - skew) < 6 * np.sqrt(6.0 / N) + 0.05 * abs(skew), (row, v, sk_hat, skew)
                 kurt, ku_hat = m4 / m2**2, np.mean((x - x.mean()) ** 4) / x.var() ** 2
                 assert abs(ku_hat - kurt) < 6 * np.sqrt(24.0 / N) + 0.1 * abs(kurt - 3), (row, v, ku_hat, kurt)
+        # every intensity from far below the admissibility boundary (shapes -> 0: two-point limit of the Beta) to bright
+        # stars draws a finite value
+        withsky[...] = (np.logspace(-3, 6, na * na).reshape(na, na) / gain).astype(np.float32)
+        e3, nbad = run(8)
+        assert nbad == 0 and np.all(np.isfinite(e3)) and np.count_nonzero(e3) > 0.5 * e3.size
         # a positive nu41 large enough to leave the Type I region is reported, not silently zeroed
         tab_bad = tab.copy()
         tab_bad[:, 2] = np.abs(tab_bad[:, 2]) * 50.0
