@@ -3,6 +3,8 @@
 #include "rip_launch.h"
 #include "rip_v2_core.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <mutex>
 #include <set>
@@ -160,7 +162,11 @@ void launch_cal_fused_v2k64(const v2::Args& A, int G, int P, cudaStream_t st) {
 void launch_cal_fused_v2(const v2::Args& A, int G, int P, cudaStream_t st) {
     if (G == 16 && P == 4) v2::launch_t<16, 4>(A, st);
     else if (G == 8 && P == 4) v2::launch_t<8, 4>(A, st);
-    else if (G == 8 && P == 11) v2::launch_t<8, 11>(A, st);
+    else if (G == 8 && P == 11) {
+        static const int minb = [] { const char* e = getenv("RIP_FUSED_MINB"); return e ? atoi(e) : 4; }();  // (development: register budget A/B)
+        if (minb == 5) v2::launch_tb<8, 11, 5>(A, st);
+        else v2::launch_t<8, 11>(A, st);
+    }
     else if (G == 16 && P == 11) v2::launch_t<16, 11>(A, st);
     else throw Error("cal_fused v2: unsupported (G, P)");
 }
