@@ -532,6 +532,12 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
     const bool use_v2 = prm->threads <= 0 && h->has_ipc && h->d.gain_dtype == RIP_F32 &&
                         h->nb == 4 && n % 8 == 0 && n >= 16 && v2_supported(G, h->P, k64) &&
                         (prm->area_dtype == RIP_F32 || prm->area_dtype == RIP_F64);
+    if (!use_v2 && prm->threads <= 0 && !h->warned_generic) {  // say so once per handle: the generic kernel is ~5x slower
+        h->warned_generic = true;
+        fprintf(stderr, "librip_b200: this configuration (G=%d, P=%d, gain %s, ipc4d %s, n=%d) runs the generic fused kernel, about 5x "
+                        "slower than the throughput kernel (float32 gain; G = 8 or 16; P <= 11; float64 ipc4d only with G = 8)\n",
+                G, h->P, h->d.gain_dtype == RIP_F64 ? "float64" : "float32", !h->has_ipc ? "absent" : (k64 ? "float64" : "float32"), n);
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {
         if (h->prof_used + 2 > h->prof_ev.size()) {

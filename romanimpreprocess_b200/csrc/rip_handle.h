@@ -47,6 +47,7 @@ struct rip_caldir {
     DevBuf<uint32_t> f_crg;              // cosmic-ray group bits of the last forward ramp
     DevBuf<float> cr_len_cdf, cr_dedx_cdf;  // samplers of romanisim.cr (built on first use)
     bool f_crg_valid = false;
+    bool warned_generic = false;          // the "generic kernel" notice was printed for this handle
     cudaStream_t stream = nullptr;
     // optional per-launch timing of the fused kernel (rip_profile_enable): event pairs recorded on the launch stream
     bool profile = false;

@@ -25,6 +25,10 @@ size_t cal_fused_smem_bytes(int G, int g_dtype, int k_dtype, int threads);
 // rip_v2.cu ------------------------------------------------------------------------------------------------
 namespace v2 { struct Args; struct f4; }
 bool v2_supported(int G, int P, bool k64 = false);
+// The throughput kernel is instantiated for P = 4 and P = 11 Legendre coefficients; a CALDIR with fewer runs the next
+// larger instantiation on records padded with zero coefficients (phi + 0 * P_L(z) == phi for |z| <= 1; the extrapolating
+// evaluation for |z| > 1 sums the same zeros): same values as the exact-P evaluation.
+inline int v2_pad_P(int P) { return P <= 4 ? 4 : (P <= 11 ? 11 : P); }
 void launch_cal_fused_v2k64(const v2::Args& A, int G, int P, cudaStream_t st);
 int v2_default_band_rows(int device, int n, int G, int ctas_per_sm = 0);
 void launch_cal_fused_v3(const v2::Args& A, int G, int P, int variant, cudaStream_t st);

@@ -149,17 +149,20 @@ int v2_default_band_rows(int device, int n, int G, int ctas_per_sm) {
 }
 
 bool v2_supported(int G, int P, bool k64) {
+    P = v2_pad_P(P);
     if (k64) return G == 8 && (P == 4 || P == 11);  // (G = 16 with float64 taps would leave one CTA per SM: generic kernel)
     return (G == 8 && P == 4) || (G == 8 && P == 11) || (G == 16 && P == 11) || (G == 16 && P == 4);
 }
 
 void launch_cal_fused_v2k64(const v2::Args& A, int G, int P, cudaStream_t st) {
+    P = v2_pad_P(P);
     if (G == 8 && P == 4) v2::launch_k64<8, 4>(A, st);
     else if (G == 8 && P == 11) v2::launch_k64<8, 11>(A, st);
     else throw Error("cal_fused v2 (float64 ipc4d): unsupported (G, P)");
 }
 
 void launch_cal_fused_v2(const v2::Args& A, int G, int P, cudaStream_t st) {
+    P = v2_pad_P(P);
     if (G == 16 && P == 4) v2::launch_t<16, 4>(A, st);
     else if (G == 8 && P == 4) v2::launch_t<8, 4>(A, st);
     else if (G == 8 && P == 11) {
@@ -181,7 +184,7 @@ void v2_plan_to_device(const rip_ramp_plan* plan, cudaStream_t st) {
 
 // record of detector row 0 inside the padded allocations
 v2::f4* v2_rec1_row0(rip_caldir* h, int G) {
-    return (v2::f4*)h->v2_rec1.p + (size_t)v2::PADR * v2::ntiles(h->n) * v2::nq1(G, h->P) * v2::TW;
+    return (v2::f4*)h->v2_rec1.p + (size_t)v2::PADR * v2::ntiles(h->n) * v2::nq1(G, v2_pad_P(h->P)) * v2::TW;
 }
 v2::f4* v2_recK_row0(rip_caldir* h) {
     return (v2::f4*)h->v2_recK.p + (size_t)v2::PADR * v2::ntiles(h->n) * v2::kq_of(h->d.ipc_dtype == RIP_F64) * v2::TW;
@@ -192,7 +195,7 @@ void v2_pack(rip_caldir* h, int G, cudaStream_t st) {
     if (h->v2_G == G) return;
     const bool k64 = h->d.ipc_dtype == RIP_F64;
     const int kq = v2::kq_of(k64);
-    const int n = h->n, ntile = v2::ntiles(n), nq = v2::nq1(G, h->P);
+    const int n = h->n, ntile = v2::ntiles(n), nq = v2::nq1(G, v2_pad_P(h->P));
     const int nrow = n + 2 * v2::PADR;  // zero rows on both sides: the kernel's loaders never clamp
     h->v2_rec1.alloc((size_t)nrow * ntile * nq * v2::TW * 4);
     h->v2_recK.alloc((size_t)nrow * ntile * kq * v2::TW * 4);

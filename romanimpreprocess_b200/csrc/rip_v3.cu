@@ -53,6 +53,7 @@ static void launch_v2t(const Args& A, cudaStream_t st) {
 
 // variant: 0 = v2 (one role, 128 threads), 1 = v3 (X: a0 a1 | Y: b c), 2 = v3 (X: a0 a1 b | Y: c)
 void launch_cal_fused_v3(const v2::Args& A, int G, int P, int variant, cudaStream_t st) {
+    P = v2_pad_P(P);
     const bool bx = variant == 2;
 #define RIP_V3(GG, PP) \
     if (G == GG && P == PP) { if (variant == 3) v2::launch_v2t<GG, PP>(A, st); else if (bx) v2::launch_v3<GG, PP, true>(A, st); else v2::launch_v3<GG, PP, false>(A, st); return; }

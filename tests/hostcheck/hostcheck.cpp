@@ -123,7 +123,7 @@ static void run_v2_t(rip::v2::Args A, const rip::v2::PackSrc& S, const rip_ramp_
 
 // S->ipc points at float64 taps (the v2 kernel for float64 ipc4d: G = 8 only)
 extern "C" int hostcheck_cal_fused_v2k64(const rip::v2::Args* A, const rip::v2::PackSrc* S, const rip_ramp_plan* plan) {
-    const int G = S->G, P = S->P;
+    const int G = S->G, P = S->P <= 4 ? 4 : (S->P <= 11 ? 11 : S->P);  // (v2_pad_P: records padded with zero coefficients)
     if (G == 8 && P == 4) run_v2_t<8, 4, true>(*A, *S, *plan);
     else if (G == 8 && P == 11) run_v2_t<8, 11, true>(*A, *S, *plan);
     else return 1;
@@ -131,7 +131,7 @@ extern "C" int hostcheck_cal_fused_v2k64(const rip::v2::Args* A, const rip::v2::
 }
 
 extern "C" int hostcheck_cal_fused_v2(const rip::v2::Args* A, const rip::v2::PackSrc* S, const rip_ramp_plan* plan) {
-    const int G = S->G, P = S->P;
+    const int G = S->G, P = S->P <= 4 ? 4 : (S->P <= 11 ? 11 : S->P);
     if (G == 8 && P == 4) run_v2_t<8, 4>(*A, *S, *plan);
     else if (G == 8 && P == 11) run_v2_t<8, 11>(*A, *S, *plan);
     else if (G == 16 && P == 11) run_v2_t<16, 11>(*A, *S, *plan);

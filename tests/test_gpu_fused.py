@@ -54,6 +54,8 @@ MEDIUM = [
     (384, "README_PATTERN", 3, np.float32, np.float32, 26,
      {"SATURATION_BACKUP": 0, "JUMP_DETECT_PARS": {"SthreshA": 4.0, "SthreshB": 3.5}}, 8.0, np.float32),
     (128, "LONG16_PATTERN", 3, np.float32, np.float32, 27, {}, 6.0, np.float64),
+    (256, "README_PATTERN", 6, np.float32, np.float32, 28, {}, 4.0, np.float32),   # P = 7: the P = 11 kernel on zero-padded records
+    (256, "README_PATTERN", 7, np.float32, np.float64, 29, {}, 4.0, np.float64),   # P = 8 with float64 ipc4d
 ]  # fmt: skip
 
 

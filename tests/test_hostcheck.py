@@ -87,6 +87,8 @@ V2_CASES = [
     (256, "README_PATTERN", 10, 28, {"SATURATION_BACKUP": 0}, 100, 8.0, True, np.float64),
     (128, "README_PATTERN", 3, 29, {"EXCLUDE_FIRST": False}, 50, 4.0, True, np.float64),
     (56, "README_PATTERN", 10, 15, {}, 7, 12.0, False),
+    (64, "README_PATTERN", 6, 31, {}, 20, 6.0, False),      # P = 7: runs the P = 11 kernel on zero-padded records
+    (64, "LONG16_PATTERN", 2, 32, {}, 20, 6.0, False),      # P = 3 -> 4
     (256, "README_PATTERN", 10, 21, {}, 32, 1.0, True),
     (256, "LONG16_PATTERN", 10, 22, {"EXCLUDE_FIRST": False, "SATURATION_BACKUP": 2}, 100, 4.0, True),
     (384, "README_PATTERN", 3, 26, {"SATURATION_BACKUP": 0, "JUMP_DETECT_PARS": {"SthreshA": 4.0, "SthreshB": 3.5}}, 128, 8.0, True),
