@@ -233,14 +233,27 @@ RIP_HD double invlin_fast_z(double Slin, const double (&cd)[P], float A, float m
     // |s| > mu_far  =>  |m s| > dglob + |rho|  =>  m s + rho has the sign of s and clears the global bound: decided.
     // (true for all lanes of a warp during the first ~17 steps: one subtraction and one comparison per step)
     const double mu_far = (dglob + fabs(rho)) / (double)m * (1.0 + 1.0 / 1024.0);
-    double z = 0.0, step = 1.0;
+    // The search runs on the grid z = Z 2^-24 (24 halvings of a unit step starting at 0), so the far test is done in
+    // integers: Z < Zlo  =>  z < r - mu_far, Z > Zhi  =>  z > r + mu_far, with one grid unit of margin for the roundings of
+    // the scaling (the far test is only a SUFFICIENT condition: a step it misses is decided by the tests below, with the
+    // same outcome).  Two integer comparisons and an integer add per far step instead of five float64 operations.
+    const double SC = 16777216.0, lim = 1073741824.0;
+    double dlo = floor(rr * SC - mu_far * SC) - 1.0, dhi = ceil(rr * SC + mu_far * SC) + 1.0;
+    if (!(dlo > -lim)) dlo = -lim;  // (also catches NaN: then nothing is "far")
+    if (!(dhi < lim)) dhi = lim;
+    if (!(mu_far == mu_far) || !(rr == rr)) { dlo = -lim; dhi = lim; }
+    const int Zlo = (int)dlo, Zhi = (int)dhi;
+    int Z = 0, istep = 1 << 24;
     for (int j = 1; j < 25; ++j) {
-        step = step * 0.5;
-        const double s = z - rr, as = fabs(s);
+        istep >>= 1;
         bool lt;
-        if (as > mu_far) {
-            lt = s < 0.0;
+        if (Z < Zlo) {
+            lt = true;
+        } else if (Z > Zhi) {
+            lt = false;
         } else {
+            const double z = (double)Z * (1.0 / 16777216.0);
+            const double s = z - rr, as = fabs(s);
             double dl = dglob;
             if (as <= 1.52587890625e-05) {  // 2^-16: partial sums are those at r up to their drift
                 const double dloc = u * (sabs + as * D1) * slack + eps;
@@ -255,9 +268,9 @@ RIP_HD double invlin_fast_z(double Slin, const double (&cd)[P], float A, float m
                 if (n_exact) ++*n_exact;
             }
         }
-        z = z + (lt ? step : -step);
+        Z += lt ? istep : -istep;
     }
-    return z;
+    return (double)Z * (1.0 / 16777216.0);
 }
 
 // ---------------------------------------------------------------------------------------------------------
