@@ -790,6 +790,50 @@ def run_exposure18(args):
         dist.destroy_process_group()
 
 
+def run_files(args):
+    """Secondary workload: the file-level drop-in at full size.  CALDIR files, L1 exposures and FITSWCS
+    headers are written once to tmpfs (layouts of SURVEY App. B, tests/fixture_files.py); each step is one
+    gen_cal_image.calibrateimage(config): read the L1 ASDF file, L1->L2 on the GPU (resident CALDIR, area from the WCS,
+    sky mode + SKYORDER fit), write the L2 ASDF file.  Wall clock, one GPU."""
+    import shutil
+
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fixture_files import write_exposure
+
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    tmp = tempfile.mkdtemp(prefix="rip_files_", dir=base)
+    try:
+        t0 = time.perf_counter()
+        config, cal, data, amp33, rp = write_exposure(tmp, n=args.n, seed=41, p_order=P_ORDER, ipc_dtype=np.float64)
+        t_write = time.perf_counter() - t0
+        in_bytes = os.path.getsize(config["IN"])
+        gci.calibrateimage(config, verbose=False)  # first exposure: opens the CALDIR files, builds the resident handle
+        torch.cuda.synchronize()
+        ts = []
+        for i in range(max(args.steps, 2)):
+            cfg = dict(config, OUT=os.path.join(tmp, f"sim_L2_F184_1_1_{i}.asdf"))
+            t = time.perf_counter()
+            gci.calibrateimage(cfg, verbose=False)
+            ts.append(time.perf_counter() - t)
+            out_bytes = os.path.getsize(cfg["OUT"])
+            os.remove(cfg["OUT"])
+        dt = float(np.median(ts))
+        print(json.dumps({"metric": "calibrateimage(config) exposures/s from / to ASDF files on tmpfs (4096^2 x 8 resultants)",
+                          "value": 1.0 / dt, "unit": "SCA/s", "s_per_exposure": dt, "n_gpus": 1, "steps": len(ts),
+                          "dtype": "f32 (float64 ipc4d: the DUMMY CALDIR dtype)", "data": "synthetic", "secondary_workload": True,
+                          "l1_file_bytes": int(in_bytes), "l2_file_bytes": int(out_bytes), "fixture_write_s": t_write,
+                          "io": "asdf" if __import__("romanimpreprocess_b200.caltree", fromlist=["have_asdf"]).have_asdf() else "io/asdf_lite.py",
+                          "timing": "wall clock per call, median; includes reading the L1 file, packaging and writing the L2 file"}),
+              flush=True)  # fmt: skip
+        gci.clear_caldir_cache()
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_noiselayers(args):
     """Secondary workload (the production call pattern of runs/summer2025run/OpenUniverse_to_L1L2.py:
     124-133): per exposure `--layers` noise layers (half "Rz4PbrS2C<i>", half "Rz4OS2C<i>": the production list) with SKYORDER 2 = (2 + layers) full L1->L2 calibrations,
@@ -860,7 +904,7 @@ def main():
     ap.add_argument("--realizations", type=int, default=64, help="noise realisations (workload realizations)")
     ap.add_argument("--exposures18", type=int, default=4, help="exposures of 18 SCAs each (workload exposure18)")
     ap.add_argument("--layers", type=int, default=8, help="noise layers per exposure (workload noiselayers)")
-    ap.add_argument("--workload", default="l1l2", choices=["l1l2", "forward", "realizations", "noiselayers", "exposure18"],
+    ap.add_argument("--workload", default="l1l2", choices=["l1l2", "forward", "realizations", "noiselayers", "exposure18", "files"],
                     help="l1l2 = the headline metric; forward = secondary line for the forward ramp generator")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -874,6 +918,8 @@ def main():
         run_noiselayers(args)
     elif args.workload == "exposure18":
         run_exposure18(args)
+    elif args.workload == "files":
+        run_files(args)
     else:
         run_ours(args)
 
