@@ -81,6 +81,27 @@ __global__ void __launch_bounds__(TW, MINB) cal_fused_v2_kernel(const Args A) {
     }
 }
 
+// v6 (rip_v2_core.cuh, "v6"): five resident CTAs per SM -- 96 registers, depth-4 record ring, stage c one row behind
+// stage b with a barrier in between
+template <int G, int P>
+__global__ void __launch_bounds__(TW, 5) cal_fused_v6_kernel(const Args A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem6<G> sm;
+    sm.carve(smem_raw);
+    Regs<G, P> R;
+    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int r0 = blockIdx.y * A.band_rows;
+    const int r1 = min(r0 + A.band_rows, A.n);
+    prologue6<G, P>(A, sm, R, tid, tile, r0, r1);
+    __syncthreads();
+    for (int s = r0 - 3; s <= r1 + 4; ++s) {
+        step6a<G, P>(A, sm, R, tid, tile, r0, r1, s);
+        __syncthreads();
+        step6b<G, P>(A, c_plan_v2, c_fast_v2, sm, R, tid, tile, r0, r1, s);
+        __syncthreads();
+    }
+}
+
 // float64 ipc4d (K64): same march, IPC stages in float64 (3 CTAs/SM: the O1 ring holds doubles)
 template <int G, int P, int MINB>
 __global__ void __launch_bounds__(TW, MINB) cal_fused_v2k64_kernel(const Args A) {
@@ -102,6 +123,15 @@ __global__ void __launch_bounds__(TW, MINB) cal_fused_v2k64_kernel(const Args A)
 }
 
 static void configure_once(const void* fn, size_t smem) { configure_smem_once(fn, smem, true); }
+
+template <int G, int P>
+static void launch_v6(const Args& A, cudaStream_t st) {
+    const size_t smem = Smem6<G>::bytes();
+    auto kern = cal_fused_v6_kernel<G, P>;
+    configure_once((const void*)kern, smem);
+    dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
+    RIP_LAUNCH(kern, grid, TW, smem, st, A);
+}
 
 template <int G, int P>
 static void launch_k64(const Args& A, cudaStream_t st) {
@@ -152,6 +182,14 @@ bool v2_supported(int G, int P, bool k64) {
     P = v2_pad_P(P);
     if (k64) return G == 8 && (P == 4 || P == 11);  // (G = 16 with float64 taps would leave one CTA per SM: generic kernel)
     return (G == 8 && P == 4) || (G == 8 && P == 11) || (G == 16 && P == 11) || (G == 16 && P == 4);
+}
+
+bool v6_supported(int G, int P) { return G == 8 && (v2_pad_P(P) == 4 || v2_pad_P(P) == 11); }
+void launch_cal_fused_v6(const v2::Args& A, int G, int P, cudaStream_t st) {
+    P = v2_pad_P(P);
+    if (G == 8 && P == 4) v2::launch_v6<8, 4>(A, st);
+    else if (G == 8 && P == 11) v2::launch_v6<8, 11>(A, st);
+    else throw Error("cal_fused v6: unsupported (G, P)");
 }
 
 void launch_cal_fused_v2k64(const v2::Args& A, int G, int P, cudaStream_t st) {

@@ -185,6 +185,8 @@ struct alignas(16) d2 {
 template <int G, bool K64 = false>
 struct Smem {
     static constexpr int H = G / 4;
+    static constexpr int DEPTH = RING;  // slots of the row-record ring
+    static constexpr int C_LAG = 6;     // stage c runs on row s - C_LAG
     static constexpr int OFF_D = 0;
     static constexpr int OFF_RAW = OFF_D + 16 * H * RW;
     static constexpr int OFF_THR = OFF_RAW + 2 * G * TW;
@@ -249,6 +251,8 @@ RIP_HD int fold_row(int row, int lo, int hi) { return imin(imax(row, lo), hi - 1
 RIP_HD unsigned wrap5(unsigned x, unsigned ring_bytes) { const unsigned y = x - ring_bytes; return x < y ? x : y; }
 // byte offset of the ring5 slot of row s+DK, given o5[k] = offset of row s+k (DK is a compile-time constant)
 #define RIP_O5(DK) o5[(((DK) % 5) + 5) % 5]
+// the same inside the stage functions, for the ring depth of the shared-memory layout they are instantiated with
+#define RIP_OS(DK) o5[(((DK) % SM::DEPTH) + SM::DEPTH) % SM::DEPTH]
 
 // ---- asynchronous global -> shared copies (LDGSTS); the host build copies at once ---------------------------
 template <int BYTES>
@@ -796,7 +800,7 @@ RIP_HD void stage_a1(const Args& A, SM& sm, const Regs<G, P>& R, const StepCtx& 
     const uint32_t allg = (1u << G) - 1u;
     const int row = C.s - 2;
     const bool rowin = in_range(row, imax(r0 - 2, 0), imin(r1 + 2, n));
-    f4* dst = sm.D(RIP_O5(-2));
+    f4* dst = sm.D(RIP_OS(-2));
     if (rowin && C.xin) {  // (all columns: the two edge columns of the tile compute values nobody reads)
         uint32_t grown = 0u;
 #pragma unroll
@@ -816,14 +820,14 @@ RIP_HD void stage_a1(const Args& A, SM& sm, const Regs<G, P>& R, const StepCtx& 
         // raw u16 -> f32 as group pairs: (2^23 | v) - 2^23 is exact, so the packed subtraction equals the conversion
         f2 Sp[G / 2];
         {
-            const uint16_t* rq = sm.raw(RIP_O5(-2)) + tid;
+            const uint16_t* rq = sm.raw(RIP_OS(-2)) + tid;
 #pragma unroll
             for (int j = 0; j < G / 2; ++j) Sp[j] = u16_pair_to_f32((uint32_t)rq[(2 * j) * TW], (uint32_t)rq[(2 * j + 1) * TW]);
         }
         if (A.do_refpix) {  // gen_cal_image.py:535-556: f64 subtractions, f32 stores
             const int chsel = ((x >> 7) != ((C.tile * TS) >> 7)) ? 1 : 0;
-            const d2* rc = (const d2*)sm.rc(RIP_O5(-2));               // one LDS.128 per group pair
-            const d2* ln = (const d2*)(sm.ln(RIP_O5(-2)) + chsel * G);
+            const d2* rc = (const d2*)sm.rc(RIP_OS(-2));               // one LDS.128 per group pair
+            const d2* ln = (const d2*)(sm.ln(RIP_OS(-2)) + chsel * G);
 #pragma unroll
             for (int j = 0; j < G / 2; ++j) {
                 const f2 dk = f2{r1w<NQ1>(R.r1, 2 * j), r1w<NQ1>(R.r1, 2 * j + 1)};
@@ -923,8 +927,8 @@ RIP_HD void stage_a1(const Args& A, SM& sm, const Regs<G, P>& R, const StepCtx& 
                     A.lincube[(unsigned)g * npl + (unsigned)row * (unsigned)n + (unsigned)x] = (g & 1) ? phi2[g >> 1].y : phi2[g >> 1].x;
             }
         }
-        sm.flg(RIP_O5(-2))[tid] = satm | (adf << 16);
-        sm.nlc(RIP_O5(-2))[tid] = (uint8_t)(((dq & DQ_NO_LIN_CORR) ? 1u : 0u) | ((aux & 2u) ? 4u : 0u));
+        sm.flg(RIP_OS(-2))[tid] = satm | (adf << 16);
+        sm.nlc(RIP_OS(-2))[tid] = (uint8_t)(((dq & DQ_NO_LIN_CORR) ? 1u : 0u) | ((aux & 2u) ? 4u : 0u));
     }
     // (rows of the band range outside the frame, columns beyond the frame: D / flags are never read there)
 }
@@ -940,9 +944,9 @@ RIP_HD void stage_b(const Args& A, SM& sm, const Regs<G, P>& R, const StepCtx& C
     f4* o = sm.O1(row);
     if (rowok) {  // (all columns; the outermost two on each side of the tile compute values nobody reads)
         const float k[9] = {R.kb[0].x, R.kb[0].y, R.kb[0].z, R.kb[0].w, R.kb[1].x, R.kb[1].y, R.kb[1].z, R.kb[1].w, R.kb8};
-        const f4* dm = sm.D(RIP_O5(-5));
-        const f4* d0 = sm.D(RIP_O5(-4));
-        const f4* dp = sm.D(RIP_O5(-3));
+        const f4* dm = sm.D(RIP_OS(-5));
+        const f4* d0 = sm.D(RIP_OS(-4));
+        const f4* dp = sm.D(RIP_OS(-3));
 #pragma unroll
         for (int h = 0; h < H; ++h) {
             f2 lo, hi;
@@ -980,9 +984,9 @@ RIP_HD void stage_b64(const Args& A, SM& sm, const Regs<G, P>& R, const StepCtx&
     d2* o = sm.O1d(row);
     if (rowok) {
         const double (&k)[9] = R.kbd;
-        const f4* dm = sm.D(RIP_O5(-5));
-        const f4* d0 = sm.D(RIP_O5(-4));
-        const f4* dp = sm.D(RIP_O5(-3));
+        const f4* dm = sm.D(RIP_OS(-5));
+        const f4* d0 = sm.D(RIP_OS(-4));
+        const f4* dp = sm.D(RIP_OS(-3));
 #pragma unroll
         for (int h = 0; h < H; ++h) {
             const f4 c = d0[h * RW + col];
@@ -1023,7 +1027,7 @@ RIP_HD void stage_c_tail(const Args& A, const RampPlanDev& pl, const FastTab& ft
     const int n = C.n, nb = 4, na = n - 8, x = C.x;
     const uint32_t allg = (1u << G) - 1u;
     const unsigned npl = (unsigned)n * (unsigned)n;
-    const int row = C.s - 6;
+    const int row = C.s - SM::C_LAG;
     GroupFlags gf;
     gf.sat = fl & 0xffffu;
     gf.adf = fl >> 16;
@@ -1095,17 +1099,17 @@ RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, SM&
     const unsigned (&o5)[5] = C.o5;
     const uint32_t allg = (1u << G) - 1u;
     const unsigned npl = (unsigned)n * (unsigned)n;
-    const int row = C.s - 6;
+    const int row = C.s - SM::C_LAG;
     const bool out_col = (tid >= 4 || C.tile == 0) && tid < TW - 4 && C.xin;
     const bool c_on = in_range(row, r0, r1) && out_col;
     if (!c_on) {
         reload();
         return;
     }
-    const unsigned p = R.orow - 6u * (unsigned)n + (unsigned)x;
+    const unsigned p = R.orow - (unsigned)SM::C_LAG * (unsigned)n + (unsigned)x;
     const bool active = C.xact && in_range(row, nb, n - nb);
-    const uint32_t fl = sm.flg(RIP_O5(-6))[tid];
-    const uint32_t nlc = sm.nlc(RIP_O5(-6))[tid];
+    const uint32_t fl = sm.flg(RIP_OS(-SM::C_LAG))[tid];
+    const uint32_t nlc = sm.nlc(RIP_OS(-SM::C_LAG))[tid];
     const float gval = R.kc[2].y, readv = R.kc[2].z, dsl = R.kc[2].w, flat = R.kc[3].x;
     const uint32_t sdq = f_as_u(R.kc[3].y);
     const float area32 = R.area32;
@@ -1118,7 +1122,7 @@ RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, SM&
         const f4* om = sm.O1(row - 1);
         const f4* o0 = sm.O1(row);
         const f4* op = sm.O1(row + 1);
-        const f4* dd = sm.D(RIP_O5(-6));
+        const f4* dd = sm.D(RIP_OS(-SM::C_LAG));
         f2 t[G / 2];
 #pragma unroll
         for (int h = 0; h < H; ++h) {
@@ -1160,17 +1164,17 @@ RIP_HD void stage_c64(const Args& A, const RampPlanDev& pl, const FastTab& ft, S
     const int n = C.n, nb = 4, tid = C.tid, col = C.col, x = C.x, r0 = C.r0, r1 = C.r1;
     const unsigned (&o5)[5] = C.o5;
     const unsigned npl = (unsigned)n * (unsigned)n;
-    const int row = C.s - 6;
+    const int row = C.s - SM::C_LAG;
     const bool out_col = (tid >= 4 || C.tile == 0) && tid < TW - 4 && C.xin;
     const bool c_on = in_range(row, r0, r1) && out_col;
     if (!c_on) {
         reload();
         return;
     }
-    const unsigned p = R.orow - 6u * (unsigned)n + (unsigned)x;
+    const unsigned p = R.orow - (unsigned)SM::C_LAG * (unsigned)n + (unsigned)x;
     const bool active = C.xact && in_range(row, nb, n - nb);
-    const uint32_t fl = sm.flg(RIP_O5(-6))[tid];
-    const uint32_t nlc = sm.nlc(RIP_O5(-6))[tid];
+    const uint32_t fl = sm.flg(RIP_OS(-SM::C_LAG))[tid];
+    const uint32_t nlc = sm.nlc(RIP_OS(-SM::C_LAG))[tid];
     // record: words 0..17 taps (doubles), 18 gain, 19 read, 20 dark slope, 21 flat, 22 static dq
     const float gval = R.kc64[4].z, readv = R.kc64[4].w, dsl = R.kc64[5].x, flat = R.kc64[5].y;
     const uint32_t sdq = f_as_u(R.kc64[5].z);
@@ -1188,7 +1192,7 @@ RIP_HD void stage_c64(const Args& A, const RampPlanDev& pl, const FastTab& ft, S
         const d2* om = sm.O1d(row - 1);
         const d2* o0 = sm.O1d(row);
         const d2* op = sm.O1d(row + 1);
-        const f4* dd = sm.D(RIP_O5(-6));
+        const f4* dd = sm.D(RIP_OS(-SM::C_LAG));
         const double gd = (double)gval;
 #pragma unroll
         for (int j = 0; j < G / 2; ++j) {
@@ -1235,8 +1239,8 @@ RIP_HD void stage_a0(const Args& A, SM& sm, const StepCtx& C) {
     uint32_t bits = 0u;
     const bool rowin = in_range(row, imax(r0 - 3, 0), imin(r1 + 3, n));
     if (rowin && C.xin) {
-        const uint16_t* rq = sm.raw(RIP_O5(0)) + tid;
-        const float thr = sm.thr(RIP_O5(0))[tid];
+        const uint16_t* rq = sm.raw(RIP_OS(0)) + tid;
+        const float thr = sm.thr(RIP_OS(0))[tid];
         uint32_t rv[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) rv[g] = rq[g * TW];
@@ -1346,6 +1350,135 @@ template <int G>
 RIP_HD unsigned next_o5(unsigned o5s) { return (o5s == (RING - 1) * Smem<G>::ROW5) ? 0u : o5s + Smem<G>::ROW5; }
 template <int G>
 RIP_HD unsigned first_o5(int r0) { return (unsigned)mod_pos(r0 - 3, RING) * Smem<G>::ROW5; }
+
+// =================================================================================================================
+// v6: the v2 stages re-scheduled for FIVE resident CTAs per SM (96 registers, 43.8 KB of rings at G = 8).
+//
+//   * stage c follows stage b within the step (row s-5 instead of s-6) behind a SECOND barrier: the D ring shrinks from 5
+//     to 4 rows and the O1 ring from 4 to 3; raw rows are copied ONE row ahead (they are L2-prefetched two ahead), so every
+//     per-row record (D | raw | thr | flg | rc | ln | nlc | sat) lives in one depth-4 ring addressed by (row & 3);
+//   * the records are no longer staged a whole step ahead in registers (66 of v2's 128): the IPC taps of stage b are
+//     loaded at the top of the step, the record of stage c right before stage b (it flies during b and the barrier), the
+//     record of a1 after stage c as before -- every load hits L2 thanks to prefetch_records (which runs one step ahead
+//     of the loads: rec1 of row s, recK of row s-2 at step s).
+//   step order:  [async row s+1; prefetch]  a1  b  [Lc]  | barrier |  c  [L1(next) Lb(next)]  a0  | barrier |
+// =================================================================================================================
+RIP_HD int mod3_pos(int a) { int r = a % 3; return r < 0 ? r + 3 : r; }
+
+template <int G>
+struct Smem6 {
+    static constexpr int H = G / 4;
+    static constexpr int DEPTH = 4;
+    static constexpr int C_LAG = 5;
+    static constexpr int OFF_D = 0;
+    static constexpr int OFF_RAW = OFF_D + 16 * H * RW;
+    static constexpr int OFF_THR = OFF_RAW + 2 * G * TW;
+    static constexpr int OFF_FLG = OFF_THR + 4 * TW;
+    static constexpr int OFF_RC = OFF_FLG + 4 * TW;
+    static constexpr int OFF_LN = OFF_RC + 8 * G;
+    static constexpr int OFF_NLC = OFF_LN + 16 * G;
+    static constexpr int OFF_SAT = (OFF_NLC + TW + 15) / 16 * 16;
+    static constexpr int ROW5 = (OFF_SAT + 4 * RW + 15) / 16 * 16;  // bytes of one row record
+    static constexpr int ROWO = 16 * H * RW;                        // bytes of one O1 row
+    unsigned char* r5;
+    unsigned char* ro;
+    RIP_HD static size_t bytes() { return (size_t)DEPTH * ROW5 + (size_t)3 * ROWO + 64; }
+    RIP_HD void carve(unsigned char* base) {
+        r5 = base;
+        ro = base + (size_t)DEPTH * ROW5;
+    }
+    RIP_HD f4* D(unsigned o5) const { return (f4*)(r5 + o5 + OFF_D); }
+    RIP_HD uint16_t* raw(unsigned o5) const { return (uint16_t*)(r5 + o5 + OFF_RAW); }
+    RIP_HD float* thr(unsigned o5) const { return (float*)(r5 + o5 + OFF_THR); }
+    RIP_HD uint32_t* flg(unsigned o5) const { return (uint32_t*)(r5 + o5 + OFF_FLG); }
+    RIP_HD double* rc(unsigned o5) const { return (double*)(r5 + o5 + OFF_RC); }
+    RIP_HD double* ln(unsigned o5) const { return (double*)(r5 + o5 + OFF_LN); }
+    RIP_HD uint8_t* nlc(unsigned o5) const { return (uint8_t*)(r5 + o5 + OFF_NLC); }
+    RIP_HD uint32_t* sat(int row) const { return (uint32_t*)(r5 + (unsigned)(row & 3) * ROW5 + OFF_SAT); }
+    RIP_HD f4* O1(int row) const { return (f4*)(ro + (unsigned)mod3_pos(row) * ROWO); }
+};
+
+template <int G>
+RIP_HD void make_ctx6(StepCtx& C, const Args& A, int tid, int tile, int r0, int r1, int s) {
+    C.n = A.n; C.tid = tid; C.tile = tile; C.r0 = r0; C.r1 = r1; C.s = s;
+    C.x = tile * TS + tid;
+    C.col = tid + 1;
+    C.xin = C.x < A.n;
+    C.xact = in_range(C.x, 4, A.n - 4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) C.o5[k] = (unsigned)((s + k) & 3) * (unsigned)Smem6<G>::ROW5;
+    C.o5[4] = 0u;
+}
+
+// L2 prefetch of the raw rows / thresholds the NEXT step copies (row s+2): G segments of 2 TW bytes + 4 TW bytes
+template <int G>
+RIP_HD void prefetch_raw(const Args& A, int row, int tile, int tid, int lo, int hi) {
+    if (tid <= G && in_range(row, imax(lo, 0), imin(hi, A.n))) {
+        const int x0 = tile * TS;
+        const unsigned ncol = (unsigned)imin(TW, A.n - x0);
+        const size_t npl = (size_t)A.n * (size_t)A.n, o = (size_t)row * (size_t)A.n + (size_t)x0;
+        if (tid < G) l2_prefetch_block(A.raw + (size_t)tid * npl + o, ncol * 2u);
+        else l2_prefetch_block(A.thr + o, ncol * 4u);
+    }
+}
+
+// IPC taps of stage b straight into R.kb (single buffer: b consumes them before the next load is issued)
+template <int G, int P>
+RIP_HD void load_b6(const Args& A, Regs<G, P>& R, int row, int tile, int tid) {
+    const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW);
+    R.kb[0] = p[tid];
+    R.kb[1] = p[TW + tid];
+    R.kb8 = ((const float*)(p + 2 * TW))[4 * tid];
+}
+
+// first half of a march step (before the mid-step barrier): a1 (row s-2) and b (row s-4)
+template <int G, int P>
+RIP_HD void step6a(const Args& A, Smem6<G>& sm, Regs<G, P>& R, const int tid, const int tile, const int r0, const int r1, const int s) {
+    using SM = Smem6<G>;
+    StepCtx C;
+    make_ctx6<G>(C, A, tid, tile, r0, r1, s);
+    const unsigned (&o5)[5] = C.o5;
+    row_async<G, P>(A, sm, R, s + 1, 1, RIP_OS(1), tile, tid, r0 - 3, r1 + 3);
+    prefetch_records<G, P, KQ>(A, s, tile, tid, r0, r1);
+    prefetch_raw<G>(A, s + 2, tile, tid, r0 - 3, r1 + 3);
+    stage_a1<G, P>(A, sm, R, C);
+    stage_b<G, P>(A, sm, R, C);
+    // record of stage c: issued only now (ptxas puts every global load of the loop on one scoreboard, so an earlier issue
+    // would make stage b's first use of its taps wait for it); it flies while the warps gather at the barrier
+    load_c<G, P>(A, R, fold_row(s - 5, r0 - 1, r1 + 1), tile, tid, C.x, C.xin);
+}
+
+// second half (after the barrier that publishes O1 of row s-4): c (row s-5), the record of the next a1, a0 (row s)
+template <int G, int P>
+RIP_HD void step6b(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem6<G>& sm, Regs<G, P>& R, const int tid, const int tile,
+                   const int r0, const int r1, const int s) {
+    StepCtx C;
+    make_ctx6<G>(C, A, tid, tile, r0, r1, s);
+    stage_c<G, P>(A, pl, ft, sm, R, C);
+    // records of the next step's a1 (row s-1) and b (row s-3): in flight during a0 and the barrier
+    load_a1<G, P>(A, R, fold_row(s - 1, r0 - 2, r1 + 2), tile, tid);
+    load_b6<G, P>(A, R, fold_row(s - 3, r0 - 1, r1 + 1), tile, tid);
+    stage_a0<G, P>(A, sm, C);
+    R.orow += (unsigned)A.n;
+    cp_async_wait<0>();  // row s+1 has landed; the caller's barrier publishes it
+}
+
+template <int G, int P>
+RIP_HD void prologue6(const Args& A, Smem6<G>& sm, Regs<G, P>& R, int tid, int tile, int r0, int r1) {
+    using SM = Smem6<G>;
+    const int s0 = r0 - 3;
+    R.orow = (unsigned)(s0 * A.n);
+    row_async<G, P>(A, sm, R, s0, 0, (unsigned)(s0 & 3) * (unsigned)SM::ROW5, tile, tid, r0 - 3, r1 + 3);
+    load_a1<G, P>(A, R, fold_row(s0 - 2, r0 - 2, r1 + 2), tile, tid);
+    load_b6<G, P>(A, R, fold_row(s0 - 4, r0 - 1, r1 + 1), tile, tid);
+    // ring pads and the slots the stages read before anything was written there (never the cp.async targets)
+    for (int k = 0; k < SM::DEPTH; ++k) {
+        for (int i = tid; i < SM::H * RW; i += TW) sm.D((unsigned)k * SM::ROW5)[i] = f4{0.f, 0.f, 0.f, 0.f};
+        for (int i = tid; i < RW; i += TW) sm.sat(k)[i] = 0u;
+    }
+    for (int i = tid; i < 3 * SM::ROWO / 16; i += TW) ((f4*)sm.ro)[i] = f4{0.f, 0.f, 0.f, 0.f};
+    cp_async_wait<0>();
+}
 
 // =================================================================================================================
 // v3: the same four stages, ROLE-SPLIT over two warp groups of one CTA and fed by the TMA engine.

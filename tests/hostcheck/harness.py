@@ -69,6 +69,8 @@ def lib():
         assert _h.hostcheck_sizeof_calargs() == C.sizeof(CalArgs)
         _h.hostcheck_cal_fused_v2.restype = C.c_int
         _h.hostcheck_cal_fused_v2.argtypes = [C.POINTER(V2Args), C.POINTER(PackSrc), C.POINTER(_lib.RampPlan)]
+        _h.hostcheck_cal_fused_v6.restype = C.c_int
+        _h.hostcheck_cal_fused_v6.argtypes = [C.POINTER(V2Args), C.POINTER(PackSrc), C.POINTER(_lib.RampPlan)]
         _h.hostcheck_cal_fused_v2k64.restype = C.c_int
         _h.hostcheck_cal_fused_v2k64.argtypes = [C.POINTER(V2Args), C.POINTER(PackSrc), C.POINTER(_lib.RampPlan)]
         assert _h.hostcheck_sizeof_v2args() == C.sizeof(V2Args)
@@ -130,7 +132,7 @@ def refpix_stats(data_u16, amp33_u16, c):
 
 
 def run_fused(cal, data_u16, amp33_u16, read_pattern, frame_time, area, config=None, do_refpix=False, threads=64,
-              band_rows=16, want_rdq=True, want_lin=True, v2=False):  # fmt: skip
+              band_rows=16, want_rdq=True, want_lin=True, v2=False, v6=False):  # fmt: skip
     """Host emulation of rip_l1_to_l2 (same argument meaning as the oracle's l1_to_l2); ``v2`` selects the v2 kernel
     source (rip_v2_core.cuh: all-f32 planes, G in {8,16}, P in {4,11})."""
     config = config or {}
@@ -156,9 +158,9 @@ def run_fused(cal, data_u16, amp33_u16, read_pattern, frame_time, area, config=N
         keep.append(a)
         return a.ctypes.data_as(C.c_void_p)
 
-    if v2:
+    if v2 or v6:
         return _run_v2(c, data_u16, amp33_u16, read_pattern, area, config, do_refpix, band_rows, want_rdq, want_lin,
-                       plan, w_exact, (thr, aux, sdq, dslope, flat), meta, p)
+                       plan, w_exact, (thr, aux, sdq, dslope, flat), meta, p, v6=v6)
     A = CalArgs()
     A.n, A.nb, A.G, A.P = n, nb, G, c["linearitylegendre"]["data"].shape[0]
     A.band_rows = band_rows
@@ -212,8 +214,8 @@ def run_fused(cal, data_u16, amp33_u16, read_pattern, frame_time, area, config=N
     return out
 
 
-def _run_v2(c, data_u16, amp33_u16, read_pattern, area, config, do_refpix, band_rows, want_rdq, want_lin, plan, w_exact,
-            static, meta, p):  # fmt: skip
+def _run_v2(c, data_u16, amp33_u16, read_pattern, area, config, do_refpix, band_rows, want_rdq, want_lin, plan, w_exact,  # noqa: PLR0913
+            static, meta, p, v6=False):  # fmt: skip
     thr, aux, sdq, dslope, flat = static
     G, n, _ = data_u16.shape
     na = n - 8
@@ -266,7 +268,8 @@ def _run_v2(c, data_u16, amp33_u16, read_pattern, area, config, do_refpix, band_
     if want_lin:
         out["ipc"] = np.full((G, n, n), np.nan, np.float32)
         A.lincube = p(out["ipc"])
-    rc = (lib().hostcheck_cal_fused_v2k64 if k64 else lib().hostcheck_cal_fused_v2)(C.byref(A), C.byref(S), C.byref(plan))
+    fn = lib().hostcheck_cal_fused_v6 if v6 else (lib().hostcheck_cal_fused_v2k64 if k64 else lib().hostcheck_cal_fused_v2)
+    rc = fn(C.byref(A), C.byref(S), C.byref(plan))
     assert rc == 0, "v2 host check: unsupported (G, P)"
     out["K"] = meta["K"]
     return out

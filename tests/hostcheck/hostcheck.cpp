@@ -121,6 +121,65 @@ static void run_v2_t(rip::v2::Args A, const rip::v2::PackSrc& S, const rip_ramp_
         }
 }
 
+// ---- v6: depth-4 record ring, two barriers per step (all threads walk the first half of a step, then the second) --------
+template <int G, int P>
+static void run_v6_t(rip::v2::Args A, const rip::v2::PackSrc& S, const rip_ramp_plan& pl) {
+    using namespace rip::v2;
+    const int n = A.n, ntile = ntiles(n), nq = nq1(G, P);
+    const int nrow = n + 2 * PADR;
+    std::vector<f4> rec1((size_t)nrow * ntile * nq * TW), recK((size_t)nrow * ntile * KQ * TW);
+    for (int prow = 0; prow < nrow; ++prow)
+        for (int tile = 0; tile < ntile; ++tile)
+            for (int c = 0; c < TW; ++c) {
+                const int x = tile * TS + c, row = prow - PADR;
+                for (int q = 0; q < nq; ++q)
+                    rec1[((size_t)(prow * ntile + tile) * nq + q) * TW + c] =
+                        f4{rec1_word(S, row, x, 4 * q), rec1_word(S, row, x, 4 * q + 1), rec1_word(S, row, x, 4 * q + 2), rec1_word(S, row, x, 4 * q + 3)};
+                for (int q = 0; q < KQ; ++q)
+                    recK[((size_t)(prow * ntile + tile) * KQ + q) * TW + c] =
+                        f4{recK_word(S, row, x, 4 * q), recK_word(S, row, x, 4 * q + 1), recK_word(S, row, x, 4 * q + 2), recK_word(S, row, x, 4 * q + 3)};
+            }
+    A.ntile = ntile;
+    A.rec1 = rec1.data() + (size_t)PADR * ntile * nq * TW;
+    A.recK = recK.data() + (size_t)PADR * ntile * KQ * TW;
+    std::vector<double> line;
+    if (A.do_refpix && A.chan_m && A.chan_c) {
+        line.resize((size_t)G * 32 * n);
+        for (int g = 0; g < G; ++g)
+            for (int ch = 0; ch < 32; ++ch)
+                for (int j = 0; j < n; ++j) line[((size_t)g * 32 + ch) * n + j] = A.chan_m[g * 32 + ch] * (double)j + A.chan_c[g * 32 + ch];
+        A.chan_line = line.data();
+    }
+    const FastTab ft = make_fast_tab(pl);
+    const size_t smem = Smem6<G>::bytes();
+    std::vector<unsigned char> buf(smem + 64);
+    std::vector<Regs<G, P>> regs(TW);
+    const int gy = (n + A.band_rows - 1) / A.band_rows;
+    for (int by = 0; by < gy; ++by)
+        for (int tile = 0; tile < ntile; ++tile) {
+            memset(buf.data(), 0xA5, buf.size());
+            memset((void*)regs.data(), 0xA5, sizeof(Regs<G, P>) * TW);
+            unsigned char* base = buf.data();
+            base += (16 - ((size_t)base & 15)) & 15;
+            Smem6<G> sm;
+            sm.carve(base);
+            const int r0 = by * A.band_rows, r1 = (r0 + A.band_rows < n) ? r0 + A.band_rows : n;
+            for (int tid = 0; tid < TW; ++tid) prologue6<G, P>(A, sm, regs[tid], tid, tile, r0, r1);
+            for (int s = r0 - 3; s <= r1 + 4; ++s) {
+                for (int tid = 0; tid < TW; ++tid) step6a<G, P>(A, sm, regs[tid], tid, tile, r0, r1, s);
+                for (int tid = 0; tid < TW; ++tid) step6b<G, P>(A, pl, ft, sm, regs[tid], tid, tile, r0, r1, s);
+            }
+        }
+}
+
+extern "C" int hostcheck_cal_fused_v6(const rip::v2::Args* A, const rip::v2::PackSrc* S, const rip_ramp_plan* plan) {
+    const int G = S->G, P = S->P <= 4 ? 4 : (S->P <= 11 ? 11 : S->P);
+    if (G == 8 && P == 4) run_v6_t<8, 4>(*A, *S, *plan);
+    else if (G == 8 && P == 11) run_v6_t<8, 11>(*A, *S, *plan);
+    else return 1;
+    return 0;
+}
+
 // S->ipc points at float64 taps (the v2 kernel for float64 ipc4d: G = 8 only)
 extern "C" int hostcheck_cal_fused_v2k64(const rip::v2::Args* A, const rip::v2::PackSrc* S, const rip_ramp_plan* plan) {
     const int G = S->G, P = S->P <= 4 ? 4 : (S->P <= 11 ? 11 : S->P);  // (v2_pad_P: records padded with zero coefficients)

@@ -115,6 +115,27 @@ def test_v2_kernel_source(case):
     assert all(v == 0 for v in stats.values()), stats
 
 
+V6_CASES = [c for c in V2_CASES if c[1] == "README_PATTERN" and len(c) == 8]
+
+
+@pytest.mark.parametrize("case", V6_CASES, ids=[f"n{c[0]}_{c[1]}_s{c[3]}" for c in V6_CASES])
+def test_v6_kernel_source(case):
+    """The five-CTAs-per-SM schedule of the throughput kernel (rip_v2_core.cuh "v6": depth-4 record ring, stage c one row
+    behind stage b behind a second barrier, records loaded from L2 just in time) walks to the same result."""
+    n, rpname, po, seed, cfg, band, bright, refpix = case[:8]
+    rp = getattr(synth, rpname)
+    cal = synth.make_caldir(n=n, seed=seed, read_pattern=rp, p_order=po, gain_dtype=np.float32, ipc_dtype=np.float32,
+                            sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
+    data_u16, amp33_u16, _ = synth.make_l1(cal, rp, seed=seed + 1, n_sources=25 if n > 100 else 9, cr_frac=0.01,
+                                           bright=bright)  # fmt: skip
+    area = synth.make_area_factor(n)
+    c = {k: v["roman"] for k, v in cal.items()}
+    ref = orc.l1_to_l2(data_u16, amp33_u16, c, rp, 3.04, area, cfg, do_refpix=refpix, return_intermediates=True)
+    out = harness.run_fused(cal, data_u16, amp33_u16, rp, 3.04, area, cfg, do_refpix=refpix, band_rows=band, v6=True)
+    stats = compare_l2(out, ref, lin_key="ipc")
+    assert all(v == 0 for v in stats.values()), stats
+
+
 def test_shared_reciprocal_division_is_ieee_division():
     """rip::v2::SharedDiv (one refined reciprocal + two FMA-residual corrections per numerator) == x / d bit for bit,
     with the hardware reciprocal emulated as a +-1 ulp perturbed 1/d: 2 x 10^7 random pairs in the ranges the kernel
