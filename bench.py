@@ -496,6 +496,11 @@ def run_ours(args):
                     traffic = json.load(f).get(f"G{G}_P{P_ORDER + 1}_n{n}" + ("_k64" if k64 else ""))
             except Exception:  # noqa: BLE001
                 traffic = None
+        v6 = args.groups == 8 and not k64 and os.environ.get("RIP_FUSED_VARIANT", "4") == "4" and args.threads == 0
+        kernel_name = ("cal_fused_v2k64_kernel<8,11>" if k64 else ("cal_fused_v6_kernel<8,11>" if v6 else "cal_fused_v2_kernel<8,11>")) \
+            if args.groups == 8 else "cal_fused_v2_kernel<16,11>"
+        band_txt = ("auto (49 rows at 4096^2 on 148 SMs: 3.97 waves of 740 resident CTAs)" if v6 else
+                    "auto (62 rows at 4096^2 on 148 SMs: 3.96 waves of 592 resident CTAs)")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -506,10 +511,10 @@ def run_ours(args):
                             "jump/saturation flags + dark + flat/area + endslice (BASELINE metric config)",
                 "l2_policy": f"inputs larger than L2: each step streams {algo_bytes / 1e9:.2f} GB (126 MB L2) and "
                              f"{n_exp} distinct exposures are rotated",
-                "threads": args.threads or 128, "band_rows": args.band_rows or "auto (62 rows at 4096^2 on 148 SMs: 3.96 waves of 592 resident CTAs)", "parallelism": f"sca-sharded x{world}",
+                "threads": args.threads or 128, "band_rows": args.band_rows or band_txt, "parallelism": f"sca-sharded x{world}",
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": ("cal_fused_v2k64_kernel<8,11>" if k64 else "cal_fused_v2_kernel<8,11>") if args.groups == 8 else "cal_fused_v2_kernel<16,11>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name,
                          "kernel_ms": fused_avg_ms, "algorithmic_bytes": algo_bytes,
                          "step_share": fused_ms.value / ms_total},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -506,7 +506,7 @@ extern "C" int rip_caldir_get_static(rip_caldir* h, float* dark_slope_ipc, float
 static int fused_default_variant() {
     static const int v = [] {
         const char* e = getenv("RIP_FUSED_VARIANT");
-        return e ? atoi(e) : 0;
+        return e ? atoi(e) : 4;  // 4 = v6 (five CTAs per SM) where it is instantiated, else v2; 0 forces v2
     }();
     return v;
 }
@@ -526,7 +526,8 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
     const double* dw = plan_to_device(h->device, plan, w_exact, st);
     if (prm->do_refpix) run_k0(h, d_raw, d_amp33, G, st);
     // v2 (rip_v2_core.cuh) for the common all-f32 configuration; params.threads > 0 selects the generic v1 tile kernel
-    // (threads < 0: development selector of the fused-kernel variant, -1 = v2, -2 / -3 = v3 without / with stage b in role X)
+    // (threads < 0: development selector of the fused-kernel variant, -1 = v2, -2 / -3 = v3 without / with stage b in role X,
+    //  -4 = v2t, -5 = v6; default: v6 where supported (G = 8, float32 ipc4d), else v2)
     const int variant = prm->threads < 0 ? -prm->threads - 1 : fused_default_variant();
     const bool k64 = h->has_ipc && h->d.ipc_dtype == RIP_F64;
     const bool use_v2 = prm->threads <= 0 && h->has_ipc && h->d.gain_dtype == RIP_F32 &&

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(TW, MINB) cal_fused_v2_kernel(const Args A) {
 
 // v6 (rip_v2_core.cuh, "v6"): five resident CTAs per SM -- 96 registers, depth-4 record ring, stage c one row behind
 // stage b with a barrier in between
-template <int G, int P>
+template <int G, int P, int SCHED = 0>
 __global__ void __launch_bounds__(TW, 5) cal_fused_v6_kernel(const Args A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem6<G> sm;
@@ -95,10 +95,54 @@ __global__ void __launch_bounds__(TW, 5) cal_fused_v6_kernel(const Args A) {
     prologue6<G, P>(A, sm, R, tid, tile, r0, r1);
     __syncthreads();
     for (int s = r0 - 3; s <= r1 + 4; ++s) {
-        step6a<G, P>(A, sm, R, tid, tile, r0, r1, s);
+        step6a<G, P, SCHED>(A, sm, R, tid, tile, r0, r1, s);
         __syncthreads();
-        step6b<G, P>(A, c_plan_v2, c_fast_v2, sm, R, tid, tile, r0, r1, s);
+        step6b<G, P, SCHED>(A, c_plan_v2, c_fast_v2, sm, R, tid, tile, r0, r1, s);
         __syncthreads();
+    }
+}
+
+// v6 with split-phase barriers (rip_v2_core.cuh, SCHED 3): the two CTA barriers of a v6 step become mbarrier
+// arrive / wait pairs with independent work in between (stage a0 behind the mid-step arrival, the ramp fit and epilogue of
+// stage c behind the end-of-step arrival), so a warp rarely blocks on its slowest sibling.
+//     wait-end(prev)  a1  [Lc]  b  arrive-mid  a0  wait-mid  c: stencil, arrive-end, ramp fit ...  [L1 Lb]
+template <int G, int P>
+__global__ void __launch_bounds__(TW, 5) cal_fused_v6s_kernel(const Args A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using SM = Smem6<G>;
+    SM sm;
+    sm.carve(smem_raw);
+    uint64_t* mbar = (uint64_t*)(smem_raw + (size_t)SM::DEPTH * SM::ROW5 + (size_t)3 * SM::ROWO);  // the 64 spare bytes
+    Regs<G, P> R;
+    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int r0 = blockIdx.y * A.band_rows;
+    const int r1 = min(r0 + A.band_rows, A.n);
+    if (tid == 0) {
+        tma::mbar_init(mbar, TW);
+        tma::mbar_init(mbar + 1, TW);
+        tma::fence_mbar_init();
+    }
+    prologue6<G, P>(A, sm, R, tid, tile, r0, r1);
+    __syncthreads();
+    unsigned it = 0;
+    for (int s = r0 - 3; s <= r1 + 4; ++s, ++it) {
+        StepCtx C;
+        make_ctx6<G>(C, A, tid, tile, r0, r1, s);
+        const unsigned (&o5)[5] = C.o5;
+        if (it) sp_wait(mbar + 1, (it - 1u) & 1u);  // everything the previous step published (and released) is visible
+        row_async<G, P>(A, sm, R, s + 1, 1, RIP_OS(1), tile, tid, r0 - 3, r1 + 3);
+        prefetch_records<G, P, KQ>(A, s, tile, tid, r0, r1);
+        prefetch_raw<G>(A, s + 2, tile, tid, r0 - 3, r1 + 3);
+        stage_a1<G, P>(A, sm, R, C);
+        load_c<G, P>(A, R, fold_row(s - 5, r0 - 1, r1 + 1), tile, tid, C.x, C.xin);
+        stage_b<G, P>(A, sm, R, C);
+        sp_arrive(mbar);       // O1 of row s-4 and D of row s-2 are written
+        stage_a0<G, P>(A, sm, C);
+        sp_wait(mbar, it & 1u);
+        stage_c<G, P>(A, c_plan_v2, c_fast_v2, sm, R, C, NoHook(), ArriveHook{mbar + 1});
+        load_a1<G, P>(A, R, fold_row(s - 1, r0 - 2, r1 + 2), tile, tid);
+        load_b6<G, P>(A, R, fold_row(s - 3, r0 - 1, r1 + 1), tile, tid);
+        R.orow += (unsigned)A.n;
     }
 }
 
@@ -124,10 +168,19 @@ __global__ void __launch_bounds__(TW, MINB) cal_fused_v2k64_kernel(const Args A)
 
 static void configure_once(const void* fn, size_t smem) { configure_smem_once(fn, smem, true); }
 
-template <int G, int P>
+template <int G, int P, int SCHED = 0>
 static void launch_v6(const Args& A, cudaStream_t st) {
     const size_t smem = Smem6<G>::bytes();
-    auto kern = cal_fused_v6_kernel<G, P>;
+    auto kern = cal_fused_v6_kernel<G, P, SCHED>;
+    configure_once((const void*)kern, smem);
+    dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
+    RIP_LAUNCH(kern, grid, TW, smem, st, A);
+}
+
+template <int G, int P>
+static void launch_v6s(const Args& A, cudaStream_t st) {
+    const size_t smem = Smem6<G>::bytes();
+    auto kern = cal_fused_v6s_kernel<G, P>;
     configure_once((const void*)kern, smem);
     dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
     RIP_LAUNCH(kern, grid, TW, smem, st, A);
@@ -187,8 +240,14 @@ bool v2_supported(int G, int P, bool k64) {
 bool v6_supported(int G, int P) { return G == 8 && (v2_pad_P(P) == 4 || v2_pad_P(P) == 11); }
 void launch_cal_fused_v6(const v2::Args& A, int G, int P, cudaStream_t st) {
     P = v2_pad_P(P);
-    if (G == 8 && P == 4) v2::launch_v6<8, 4>(A, st);
-    else if (G == 8 && P == 11) v2::launch_v6<8, 11>(A, st);
+    if (G == 8 && P == 4) v2::launch_v6<8, 4, 2>(A, st);
+    else if (G == 8 && P == 11) {
+        // measured (profiles/r02/ab_v6_sched.log): record of stage c issued before stage b (SCHED 2) 1.3245 ms, after it
+        // 1.328 ms, stage a0 in the first half 1.342 ms
+        static const int split = [] { const char* e = getenv("RIP_V6_SPLIT"); return e ? atoi(e) : 0; }();  // (development A/B)
+        if (split) v2::launch_v6s<8, 11>(A, st);
+        else v2::launch_v6<8, 11, 2>(A, st);
+    }
     else throw Error("cal_fused v6: unsupported (G, P)");
 }
 

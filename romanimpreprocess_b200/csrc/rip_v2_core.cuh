@@ -1091,9 +1091,11 @@ RIP_HD void stage_c_tail(const Args& A, const RampPlanDev& pl, const FastTab& ft
 }
 
 
-template <int G, int P, class SM, typename Hook = NoHook>
+// `reads_done` runs exactly once per call, after the stage's last read of the shared-memory rows other threads will
+// overwrite (O1 rows and D of the stage's row): v6 arrives at its split end-of-step barrier there.
+template <int G, int P, class SM, typename Hook = NoHook, typename Hook2 = NoHook>
 RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, SM& sm, const Regs<G, P>& R, const StepCtx& C,
-                    Hook reload = Hook()) {
+                    Hook reload = Hook(), Hook2 reads_done = Hook2()) {
     constexpr int H = G / 4;
     const int n = C.n, nb = 4, na = n - 8, tid = C.tid, col = C.col, x = C.x, r0 = C.r0, r1 = C.r1;
     const unsigned (&o5)[5] = C.o5;
@@ -1103,6 +1105,7 @@ RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, SM&
     const bool out_col = (tid >= 4 || C.tile == 0) && tid < TW - 4 && C.xin;
     const bool c_on = in_range(row, r0, r1) && out_col;
     if (!c_on) {
+        reads_done();
         reload();
         return;
     }
@@ -1152,6 +1155,7 @@ RIP_HD void stage_c(const Args& A, const RampPlanDev& pl, const FastTab& ft, SM&
 #pragma unroll
         for (int j = 0; j < G / 2; ++j) q[j] = f2{0.f, 0.f};  // unused: every output of a non-active pixel is flag-only
     }
+    reads_done();
     stage_c_tail<G, P>(A, pl, ft, sm, C, q, fl, nlc, gval, readv, dsl, flat, sdq, area32, area64, p, active, reload);
 }
 
@@ -1431,8 +1435,48 @@ RIP_HD void load_b6(const Args& A, Regs<G, P>& R, int row, int tile, int tid) {
     R.kb8 = ((const float*)(p + 2 * TW))[4 * tid];
 }
 
+// Split-phase CTA barrier on an mbarrier (count = TW): arrive where the thread's contribution is published, wait where
+// the others' is needed, independent work in between (v6 SCHED 3).  The host walk needs neither.
+RIP_HD void sp_arrive(uint64_t* b) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+#else
+    (void)b;
+#endif
+}
+RIP_HD void sp_wait(uint64_t* b, unsigned parity) {
+#if defined(__CUDA_ARCH__)
+    unsigned ok = 0, spins = 0;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(b);
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > (1u << 24)) __trap();  // (a lost arrival must be an error the host sees, not a hang)
+    } while (!ok);
+#else
+    (void)b; (void)parity;
+#endif
+}
+struct ArriveHook {
+    uint64_t* b;
+    RIP_HD void operator()() const {
+        cp_async_wait<0>();  // this thread's part of row s+1 has landed: published by the arrival
+        sp_arrive(b);
+    }
+};
+
 // first half of a march step (before the mid-step barrier): a1 (row s-2) and b (row s-4)
-template <int G, int P>
+// SCHED (development A/B): 0 = a1 b [Lc] | c [L1 Lb] a0 ;  1 = a0 moved into the first half ;  2 = Lc issued before b ;
+// 3 = 2 with SPLIT-PHASE barriers (mbar[0] mid-step, mbar[1] end of step; `it` = steps done, gives the wait parity):
+//     wait-end(prev)  a1  [Lc]  b  arrive-mid  a0  wait-mid  c: stencil, arrive-end, ramp fit ...  [L1 Lb]
+template <int G, int P, int SCHED = 0>
 RIP_HD void step6a(const Args& A, Smem6<G>& sm, Regs<G, P>& R, const int tid, const int tile, const int r0, const int r1, const int s) {
     using SM = Smem6<G>;
     StepCtx C;
@@ -1442,14 +1486,16 @@ RIP_HD void step6a(const Args& A, Smem6<G>& sm, Regs<G, P>& R, const int tid, co
     prefetch_records<G, P, KQ>(A, s, tile, tid, r0, r1);
     prefetch_raw<G>(A, s + 2, tile, tid, r0 - 3, r1 + 3);
     stage_a1<G, P>(A, sm, R, C);
+    if (SCHED == 2) load_c<G, P>(A, R, fold_row(s - 5, r0 - 1, r1 + 1), tile, tid, C.x, C.xin);
     stage_b<G, P>(A, sm, R, C);
     // record of stage c: issued only now (ptxas puts every global load of the loop on one scoreboard, so an earlier issue
     // would make stage b's first use of its taps wait for it); it flies while the warps gather at the barrier
-    load_c<G, P>(A, R, fold_row(s - 5, r0 - 1, r1 + 1), tile, tid, C.x, C.xin);
+    if (SCHED != 2) load_c<G, P>(A, R, fold_row(s - 5, r0 - 1, r1 + 1), tile, tid, C.x, C.xin);
+    if (SCHED == 1) stage_a0<G, P>(A, sm, C);
 }
 
 // second half (after the barrier that publishes O1 of row s-4): c (row s-5), the record of the next a1, a0 (row s)
-template <int G, int P>
+template <int G, int P, int SCHED = 0>
 RIP_HD void step6b(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem6<G>& sm, Regs<G, P>& R, const int tid, const int tile,
                    const int r0, const int r1, const int s) {
     StepCtx C;
@@ -1458,7 +1504,7 @@ RIP_HD void step6b(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem
     // records of the next step's a1 (row s-1) and b (row s-3): in flight during a0 and the barrier
     load_a1<G, P>(A, R, fold_row(s - 1, r0 - 2, r1 + 2), tile, tid);
     load_b6<G, P>(A, R, fold_row(s - 3, r0 - 1, r1 + 1), tile, tid);
-    stage_a0<G, P>(A, sm, C);
+    if (SCHED != 1) stage_a0<G, P>(A, sm, C);
     R.orow += (unsigned)A.n;
     cp_async_wait<0>();  // row s+1 has landed; the caller's barrier publishes it
 }

@@ -166,8 +166,8 @@ static void run_v6_t(rip::v2::Args A, const rip::v2::PackSrc& S, const rip_ramp_
             const int r0 = by * A.band_rows, r1 = (r0 + A.band_rows < n) ? r0 + A.band_rows : n;
             for (int tid = 0; tid < TW; ++tid) prologue6<G, P>(A, sm, regs[tid], tid, tile, r0, r1);
             for (int s = r0 - 3; s <= r1 + 4; ++s) {
-                for (int tid = 0; tid < TW; ++tid) step6a<G, P>(A, sm, regs[tid], tid, tile, r0, r1, s);
-                for (int tid = 0; tid < TW; ++tid) step6b<G, P>(A, pl, ft, sm, regs[tid], tid, tile, r0, r1, s);
+                for (int tid = 0; tid < TW; ++tid) step6a<G, P, 2>(A, sm, regs[tid], tid, tile, r0, r1, s);
+                for (int tid = 0; tid < TW; ++tid) step6b<G, P, 2>(A, pl, ft, sm, regs[tid], tid, tile, r0, r1, s);
             }
         }
 }
