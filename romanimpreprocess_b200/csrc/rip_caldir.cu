@@ -558,7 +558,7 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
         v2::Args V;
         memset(&V, 0, sizeof V);
         V.n = n; V.ntile = v2::ntiles(n);
-        V.band_rows = prm->band_rows > 0 ? prm->band_rows : v2_default_band_rows(h->device, n, G, (variant == 4 && !k64 && v6_supported(G, h->P)) ? 5 : (k64 || variant == 1 || variant == 2) ? ((G <= 8) ? 3 : 2) : 0);
+        V.band_rows = prm->band_rows > 0 ? prm->band_rows : v2_default_band_rows(h->device, n, G, (variant == 4 && v6_supported(G, h->P)) ? (k64 ? 4 : 5) : (k64 || variant == 1 || variant == 2) ? ((G <= 8) ? 3 : 2) : 0);
         V.do_refpix = prm->do_refpix; V.do_not_flag_first = prm->do_not_flag_first; V.exclude_first = prm->exclude_first;
         V.sat_backup = prm->sat_backup; V.area_dtype = prm->area_dtype;
         V.negzero = -0.0f;
@@ -571,7 +571,8 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
         V.endslice = o->endslice; V.rdq = o->rdq; V.lincube = o->lin_cube;
         if (e0) RIP_CUDA(cudaEventRecord(e0, st));
         RIP_REQUIRE(((uintptr_t)d_raw & 15) == 0, "rip_l1_to_l2: the raw cube must be 16-byte aligned");
-        if (k64) launch_cal_fused_v2k64(V, G, h->P, st);
+        if (k64 && variant == 4 && v6_supported(G, h->P)) launch_cal_fused_v6k64(V, G, h->P, st);
+        else if (k64) launch_cal_fused_v2k64(V, G, h->P, st);
         else if (variant == 4 && v6_supported(G, h->P)) launch_cal_fused_v6(V, G, h->P, st);
         else if (variant && variant != 4) launch_cal_fused_v3(V, G, h->P, variant, st);
         else launch_cal_fused_v2(V, G, h->P, st);

@@ -32,6 +32,7 @@ inline int v2_pad_P(int P) { return P <= 4 ? 4 : (P <= 11 ? 11 : P); }
 void launch_cal_fused_v2k64(const v2::Args& A, int G, int P, cudaStream_t st);
 bool v6_supported(int G, int P);
 void launch_cal_fused_v6(const v2::Args& A, int G, int P, cudaStream_t st);
+void launch_cal_fused_v6k64(const v2::Args& A, int G, int P, cudaStream_t st);
 int v2_default_band_rows(int device, int n, int G, int ctas_per_sm = 0);
 void launch_cal_fused_v3(const v2::Args& A, int G, int P, int variant, cudaStream_t st);
 void v2_plan_to_device(const rip_ramp_plan* plan, cudaStream_t st);

@@ -102,6 +102,27 @@ __global__ void __launch_bounds__(TW, 5) cal_fused_v6_kernel(const Args A) {
     }
 }
 
+// v6 for a float64 ipc4d: the same schedule with the IPC stages in float64 (O1 ring of doubles: 3 x 8320 B): 56.0 KB of rings
+// -> FOUR resident CTAs per SM (4 x (57344 + 1024) B = the SM's 228 KB exactly) where the v2 organisation allows three
+template <int G, int P>
+__global__ void __launch_bounds__(TW, 4) cal_fused_v6k64_kernel(const Args A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem6<G, true> sm;
+    sm.carve(smem_raw);
+    Regs<G, P> R;
+    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int r0 = blockIdx.y * A.band_rows;
+    const int r1 = min(r0 + A.band_rows, A.n);
+    prologue6<G, P, true>(A, sm, R, tid, tile, r0, r1);
+    __syncthreads();
+    for (int s = r0 - 3; s <= r1 + 4; ++s) {
+        step6a<G, P, 2, true>(A, sm, R, tid, tile, r0, r1, s);
+        __syncthreads();
+        step6b<G, P, 2, true>(A, c_plan_v2, c_fast_v2, sm, R, tid, tile, r0, r1, s);
+        __syncthreads();
+    }
+}
+
 // v6 with split-phase barriers (rip_v2_core.cuh, SCHED 3): the two CTA barriers of a v6 step become mbarrier
 // arrive / wait pairs with independent work in between (stage a0 behind the mid-step arrival, the ramp fit and epilogue of
 // stage c behind the end-of-step arrival), so a warp rarely blocks on its slowest sibling.
@@ -172,6 +193,15 @@ template <int G, int P, int SCHED = 0>
 static void launch_v6(const Args& A, cudaStream_t st) {
     const size_t smem = Smem6<G>::bytes();
     auto kern = cal_fused_v6_kernel<G, P, SCHED>;
+    configure_once((const void*)kern, smem);
+    dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
+    RIP_LAUNCH(kern, grid, TW, smem, st, A);
+}
+
+template <int G, int P>
+static void launch_v6k64(const Args& A, cudaStream_t st) {
+    const size_t smem = Smem6<G, true>::bytes();
+    auto kern = cal_fused_v6k64_kernel<G, P>;
     configure_once((const void*)kern, smem);
     dim3 grid(A.ntile, (A.n + A.band_rows - 1) / A.band_rows);
     RIP_LAUNCH(kern, grid, TW, smem, st, A);
@@ -249,6 +279,13 @@ void launch_cal_fused_v6(const v2::Args& A, int G, int P, cudaStream_t st) {
         else v2::launch_v6<8, 11, 2>(A, st);
     }
     else throw Error("cal_fused v6: unsupported (G, P)");
+}
+
+void launch_cal_fused_v6k64(const v2::Args& A, int G, int P, cudaStream_t st) {
+    P = v2_pad_P(P);
+    if (G == 8 && P == 4) v2::launch_v6k64<8, 4>(A, st);
+    else if (G == 8 && P == 11) v2::launch_v6k64<8, 11>(A, st);
+    else throw Error("cal_fused v6 (float64 ipc4d): unsupported (G, P)");
 }
 
 void launch_cal_fused_v2k64(const v2::Args& A, int G, int P, cudaStream_t st) {

@@ -1369,7 +1369,7 @@ RIP_HD unsigned first_o5(int r0) { return (unsigned)mod_pos(r0 - 3, RING) * Smem
 // =================================================================================================================
 RIP_HD int mod3_pos(int a) { int r = a % 3; return r < 0 ? r + 3 : r; }
 
-template <int G>
+template <int G, bool K64 = false>
 struct Smem6 {
     static constexpr int H = G / 4;
     static constexpr int DEPTH = 4;
@@ -1383,7 +1383,7 @@ struct Smem6 {
     static constexpr int OFF_NLC = OFF_LN + 16 * G;
     static constexpr int OFF_SAT = (OFF_NLC + TW + 15) / 16 * 16;
     static constexpr int ROW5 = (OFF_SAT + 4 * RW + 15) / 16 * 16;  // bytes of one row record
-    static constexpr int ROWO = 16 * H * RW;                        // bytes of one O1 row
+    static constexpr int ROWO = (K64 ? 32 : 16) * H * RW;           // bytes of one O1 row (float64 taps: O1 in doubles)
     unsigned char* r5;
     unsigned char* ro;
     RIP_HD static size_t bytes() { return (size_t)DEPTH * ROW5 + (size_t)3 * ROWO + 64; }
@@ -1400,6 +1400,7 @@ struct Smem6 {
     RIP_HD uint8_t* nlc(unsigned o5) const { return (uint8_t*)(r5 + o5 + OFF_NLC); }
     RIP_HD uint32_t* sat(int row) const { return (uint32_t*)(r5 + (unsigned)(row & 3) * ROW5 + OFF_SAT); }
     RIP_HD f4* O1(int row) const { return (f4*)(ro + (unsigned)mod3_pos(row) * ROWO); }
+    RIP_HD d2* O1d(int row) const { return (d2*)(ro + (unsigned)mod3_pos(row) * ROWO); }  // [G/2][RW]
 };
 
 template <int G>
@@ -1472,20 +1473,40 @@ struct ArriveHook {
     }
 };
 
+// the same for float64 taps (words 0..17 of the K64 record) into R.kbd
+template <int G, int P>
+RIP_HD void load_b6_64(const Args& A, Regs<G, P>& R, int row, int tile, int tid) {
+    const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ64 * TW);
+    f4 w[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) w[q] = p[q * TW + tid];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        R.kbd[2 * q] = f2_as_double(w[q].x, w[q].y);
+        R.kbd[2 * q + 1] = f2_as_double(w[q].z, w[q].w);
+    }
+    R.kbd[8] = f2_as_double(w[4].x, w[4].y);
+}
+
 // first half of a march step (before the mid-step barrier): a1 (row s-2) and b (row s-4)
 // SCHED (development A/B): 0 = a1 b [Lc] | c [L1 Lb] a0 ;  1 = a0 moved into the first half ;  2 = Lc issued before b ;
 // 3 = 2 with SPLIT-PHASE barriers (mbar[0] mid-step, mbar[1] end of step; `it` = steps done, gives the wait parity):
 //     wait-end(prev)  a1  [Lc]  b  arrive-mid  a0  wait-mid  c: stencil, arrive-end, ramp fit ...  [L1 Lb]
-template <int G, int P, int SCHED = 0>
-RIP_HD void step6a(const Args& A, Smem6<G>& sm, Regs<G, P>& R, const int tid, const int tile, const int r0, const int r1, const int s) {
-    using SM = Smem6<G>;
+template <int G, int P, int SCHED = 0, bool K64 = false>
+RIP_HD void step6a(const Args& A, Smem6<G, K64>& sm, Regs<G, P>& R, const int tid, const int tile, const int r0, const int r1, const int s) {
+    using SM = Smem6<G, K64>;
     StepCtx C;
     make_ctx6<G>(C, A, tid, tile, r0, r1, s);
     const unsigned (&o5)[5] = C.o5;
     row_async<G, P>(A, sm, R, s + 1, 1, RIP_OS(1), tile, tid, r0 - 3, r1 + 3);
-    prefetch_records<G, P, KQ>(A, s, tile, tid, r0, r1);
+    prefetch_records<G, P, K64 ? KQ64 : KQ>(A, s, tile, tid, r0, r1);
     prefetch_raw<G>(A, s + 2, tile, tid, r0 - 3, r1 + 3);
     stage_a1<G, P>(A, sm, R, C);
+    if (K64) {  // float64 taps: same schedule (record of stage c before stage b)
+        load_c64<G, P>(A, R, fold_row(s - 5, r0 - 1, r1 + 1), tile, tid, C.x, C.xin);
+        stage_b64<G, P>(A, sm, R, C);
+        return;
+    }
     if (SCHED == 2) load_c<G, P>(A, R, fold_row(s - 5, r0 - 1, r1 + 1), tile, tid, C.x, C.xin);
     stage_b<G, P>(A, sm, R, C);
     // record of stage c: issued only now (ptxas puts every global load of the loop on one scoreboard, so an earlier issue
@@ -1495,28 +1516,31 @@ RIP_HD void step6a(const Args& A, Smem6<G>& sm, Regs<G, P>& R, const int tid, co
 }
 
 // second half (after the barrier that publishes O1 of row s-4): c (row s-5), the record of the next a1, a0 (row s)
-template <int G, int P, int SCHED = 0>
-RIP_HD void step6b(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem6<G>& sm, Regs<G, P>& R, const int tid, const int tile,
+template <int G, int P, int SCHED = 0, bool K64 = false>
+RIP_HD void step6b(const Args& A, const RampPlanDev& pl, const FastTab& ft, Smem6<G, K64>& sm, Regs<G, P>& R, const int tid, const int tile,
                    const int r0, const int r1, const int s) {
     StepCtx C;
     make_ctx6<G>(C, A, tid, tile, r0, r1, s);
-    stage_c<G, P>(A, pl, ft, sm, R, C);
+    if (K64) stage_c64<G, P>(A, pl, ft, sm, R, C);
+    else stage_c<G, P>(A, pl, ft, sm, R, C);
     // records of the next step's a1 (row s-1) and b (row s-3): in flight during a0 and the barrier
     load_a1<G, P>(A, R, fold_row(s - 1, r0 - 2, r1 + 2), tile, tid);
-    load_b6<G, P>(A, R, fold_row(s - 3, r0 - 1, r1 + 1), tile, tid);
+    if (K64) load_b6_64<G, P>(A, R, fold_row(s - 3, r0 - 1, r1 + 1), tile, tid);
+    else load_b6<G, P>(A, R, fold_row(s - 3, r0 - 1, r1 + 1), tile, tid);
     if (SCHED != 1) stage_a0<G, P>(A, sm, C);
     R.orow += (unsigned)A.n;
     cp_async_wait<0>();  // row s+1 has landed; the caller's barrier publishes it
 }
 
-template <int G, int P>
-RIP_HD void prologue6(const Args& A, Smem6<G>& sm, Regs<G, P>& R, int tid, int tile, int r0, int r1) {
-    using SM = Smem6<G>;
+template <int G, int P, bool K64 = false>
+RIP_HD void prologue6(const Args& A, Smem6<G, K64>& sm, Regs<G, P>& R, int tid, int tile, int r0, int r1) {
+    using SM = Smem6<G, K64>;
     const int s0 = r0 - 3;
     R.orow = (unsigned)(s0 * A.n);
     row_async<G, P>(A, sm, R, s0, 0, (unsigned)(s0 & 3) * (unsigned)SM::ROW5, tile, tid, r0 - 3, r1 + 3);
     load_a1<G, P>(A, R, fold_row(s0 - 2, r0 - 2, r1 + 2), tile, tid);
-    load_b6<G, P>(A, R, fold_row(s0 - 4, r0 - 1, r1 + 1), tile, tid);
+    if (K64) load_b6_64<G, P>(A, R, fold_row(s0 - 4, r0 - 1, r1 + 1), tile, tid);
+    else load_b6<G, P>(A, R, fold_row(s0 - 4, r0 - 1, r1 + 1), tile, tid);
     // ring pads and the slots the stages read before anything was written there (never the cp.async targets)
     for (int k = 0; k < SM::DEPTH; ++k) {
         for (int i = tid; i < SM::H * RW; i += TW) sm.D((unsigned)k * SM::ROW5)[i] = f4{0.f, 0.f, 0.f, 0.f};

@@ -71,6 +71,8 @@ def lib():
         _h.hostcheck_cal_fused_v2.argtypes = [C.POINTER(V2Args), C.POINTER(PackSrc), C.POINTER(_lib.RampPlan)]
         _h.hostcheck_cal_fused_v6.restype = C.c_int
         _h.hostcheck_cal_fused_v6.argtypes = [C.POINTER(V2Args), C.POINTER(PackSrc), C.POINTER(_lib.RampPlan)]
+        _h.hostcheck_cal_fused_v6k64.restype = C.c_int
+        _h.hostcheck_cal_fused_v6k64.argtypes = [C.POINTER(V2Args), C.POINTER(PackSrc), C.POINTER(_lib.RampPlan)]
         _h.hostcheck_cal_fused_v2k64.restype = C.c_int
         _h.hostcheck_cal_fused_v2k64.argtypes = [C.POINTER(V2Args), C.POINTER(PackSrc), C.POINTER(_lib.RampPlan)]
         assert _h.hostcheck_sizeof_v2args() == C.sizeof(V2Args)
@@ -268,7 +270,10 @@ def _run_v2(c, data_u16, amp33_u16, read_pattern, area, config, do_refpix, band_
     if want_lin:
         out["ipc"] = np.full((G, n, n), np.nan, np.float32)
         A.lincube = p(out["ipc"])
-    fn = lib().hostcheck_cal_fused_v6 if v6 else (lib().hostcheck_cal_fused_v2k64 if k64 else lib().hostcheck_cal_fused_v2)
+    if v6:
+        fn = lib().hostcheck_cal_fused_v6k64 if k64 else lib().hostcheck_cal_fused_v6
+    else:
+        fn = lib().hostcheck_cal_fused_v2k64 if k64 else lib().hostcheck_cal_fused_v2
     rc = fn(C.byref(A), C.byref(S), C.byref(plan))
     assert rc == 0, "v2 host check: unsupported (G, P)"
     out["K"] = meta["K"]

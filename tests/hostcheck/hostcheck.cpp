@@ -122,9 +122,10 @@ static void run_v2_t(rip::v2::Args A, const rip::v2::PackSrc& S, const rip_ramp_
 }
 
 // ---- v6: depth-4 record ring, two barriers per step (all threads walk the first half of a step, then the second) --------
-template <int G, int P>
+template <int G, int P, bool K64 = false>
 static void run_v6_t(rip::v2::Args A, const rip::v2::PackSrc& S, const rip_ramp_plan& pl) {
     using namespace rip::v2;
+    constexpr int KQ = K64 ? rip::v2::KQ64 : rip::v2::KQ;
     const int n = A.n, ntile = ntiles(n), nq = nq1(G, P);
     const int nrow = n + 2 * PADR;
     std::vector<f4> rec1((size_t)nrow * ntile * nq * TW), recK((size_t)nrow * ntile * KQ * TW);
@@ -137,7 +138,8 @@ static void run_v6_t(rip::v2::Args A, const rip::v2::PackSrc& S, const rip_ramp_
                         f4{rec1_word(S, row, x, 4 * q), rec1_word(S, row, x, 4 * q + 1), rec1_word(S, row, x, 4 * q + 2), rec1_word(S, row, x, 4 * q + 3)};
                 for (int q = 0; q < KQ; ++q)
                     recK[((size_t)(prow * ntile + tile) * KQ + q) * TW + c] =
-                        f4{recK_word(S, row, x, 4 * q), recK_word(S, row, x, 4 * q + 1), recK_word(S, row, x, 4 * q + 2), recK_word(S, row, x, 4 * q + 3)};
+                        K64 ? f4{recK64_word(S, row, x, 4 * q), recK64_word(S, row, x, 4 * q + 1), recK64_word(S, row, x, 4 * q + 2), recK64_word(S, row, x, 4 * q + 3)}
+                            : f4{recK_word(S, row, x, 4 * q), recK_word(S, row, x, 4 * q + 1), recK_word(S, row, x, 4 * q + 2), recK_word(S, row, x, 4 * q + 3)};
             }
     A.ntile = ntile;
     A.rec1 = rec1.data() + (size_t)PADR * ntile * nq * TW;
@@ -151,7 +153,7 @@ static void run_v6_t(rip::v2::Args A, const rip::v2::PackSrc& S, const rip_ramp_
         A.chan_line = line.data();
     }
     const FastTab ft = make_fast_tab(pl);
-    const size_t smem = Smem6<G>::bytes();
+    const size_t smem = Smem6<G, K64>::bytes();
     std::vector<unsigned char> buf(smem + 64);
     std::vector<Regs<G, P>> regs(TW);
     const int gy = (n + A.band_rows - 1) / A.band_rows;
@@ -161,13 +163,13 @@ static void run_v6_t(rip::v2::Args A, const rip::v2::PackSrc& S, const rip_ramp_
             memset((void*)regs.data(), 0xA5, sizeof(Regs<G, P>) * TW);
             unsigned char* base = buf.data();
             base += (16 - ((size_t)base & 15)) & 15;
-            Smem6<G> sm;
+            Smem6<G, K64> sm;
             sm.carve(base);
             const int r0 = by * A.band_rows, r1 = (r0 + A.band_rows < n) ? r0 + A.band_rows : n;
-            for (int tid = 0; tid < TW; ++tid) prologue6<G, P>(A, sm, regs[tid], tid, tile, r0, r1);
+            for (int tid = 0; tid < TW; ++tid) prologue6<G, P, K64>(A, sm, regs[tid], tid, tile, r0, r1);
             for (int s = r0 - 3; s <= r1 + 4; ++s) {
-                for (int tid = 0; tid < TW; ++tid) step6a<G, P, 2>(A, sm, regs[tid], tid, tile, r0, r1, s);
-                for (int tid = 0; tid < TW; ++tid) step6b<G, P, 2>(A, pl, ft, sm, regs[tid], tid, tile, r0, r1, s);
+                for (int tid = 0; tid < TW; ++tid) step6a<G, P, 2, K64>(A, sm, regs[tid], tid, tile, r0, r1, s);
+                for (int tid = 0; tid < TW; ++tid) step6b<G, P, 2, K64>(A, pl, ft, sm, regs[tid], tid, tile, r0, r1, s);
             }
         }
 }
@@ -176,6 +178,14 @@ extern "C" int hostcheck_cal_fused_v6(const rip::v2::Args* A, const rip::v2::Pac
     const int G = S->G, P = S->P <= 4 ? 4 : (S->P <= 11 ? 11 : S->P);
     if (G == 8 && P == 4) run_v6_t<8, 4>(*A, *S, *plan);
     else if (G == 8 && P == 11) run_v6_t<8, 11>(*A, *S, *plan);
+    else return 1;
+    return 0;
+}
+
+extern "C" int hostcheck_cal_fused_v6k64(const rip::v2::Args* A, const rip::v2::PackSrc* S, const rip_ramp_plan* plan) {
+    const int G = S->G, P = S->P <= 4 ? 4 : (S->P <= 11 ? 11 : S->P);
+    if (G == 8 && P == 4) run_v6_t<8, 4, true>(*A, *S, *plan);
+    else if (G == 8 && P == 11) run_v6_t<8, 11, true>(*A, *S, *plan);
     else return 1;
     return 0;
 }

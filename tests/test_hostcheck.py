@@ -115,16 +115,17 @@ def test_v2_kernel_source(case):
     assert all(v == 0 for v in stats.values()), stats
 
 
-V6_CASES = [c for c in V2_CASES if c[1] == "README_PATTERN" and len(c) == 8]
+V6_CASES = [c for c in V2_CASES if c[1] == "README_PATTERN"]  # (G = 8; float32 and float64 ipc4d)
 
 
-@pytest.mark.parametrize("case", V6_CASES, ids=[f"n{c[0]}_{c[1]}_s{c[3]}" for c in V6_CASES])
+@pytest.mark.parametrize("case", V6_CASES, ids=[f"n{c[0]}_{c[1]}_s{c[3]}" + ("_k64" if len(c) > 8 else "") for c in V6_CASES])
 def test_v6_kernel_source(case):
     """The five-CTAs-per-SM schedule of the throughput kernel (rip_v2_core.cuh "v6": depth-4 record ring, stage c one row
     behind stage b behind a second barrier, records loaded from L2 just in time) walks to the same result."""
     n, rpname, po, seed, cfg, band, bright, refpix = case[:8]
+    kdt = case[8] if len(case) > 8 else np.float32
     rp = getattr(synth, rpname)
-    cal = synth.make_caldir(n=n, seed=seed, read_pattern=rp, p_order=po, gain_dtype=np.float32, ipc_dtype=np.float32,
+    cal = synth.make_caldir(n=n, seed=seed, read_pattern=rp, p_order=po, gain_dtype=np.float32, ipc_dtype=kdt,
                             sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
     data_u16, amp33_u16, _ = synth.make_l1(cal, rp, seed=seed + 1, n_sources=25 if n > 100 else 9, cr_frac=0.01,
                                            bright=bright)  # fmt: skip
