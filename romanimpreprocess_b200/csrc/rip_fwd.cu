@@ -489,7 +489,7 @@ static void cr_tables(std::vector<float>& len_cdf, std::vector<float>& dedx_cdf)
 
 template <int P, typename TG, typename TK>
 __global__ void __launch_bounds__(FTX * FTY, 3) fwd_ramp_kernel(const FwdArgs A) {
-    __shared__ double se[FTY + 2][FTX + 2];  // electrons in the well at this read (counts so far + start_e)
+    __shared__ double se[2][FTY + 2][FTX + 2];  // electrons in the well at this read (counts so far + start_e), double-buffered
     __shared__ float ss[FTY + 2][FTX + 2];   // start_e of the tile + halo
     const int tid = threadIdx.x, tx = tid % FTX, ty = tid / FTX;
     const int x0 = blockIdx.x * FTX, y0 = blockIdx.y * FTY;
@@ -551,17 +551,30 @@ __global__ void __launch_bounds__(FTX * FTY, 3) fwd_ramp_kernel(const FwdArgs A)
     double root = 0.0, root_pp = 0.0;
     bool have_root = false;
     int k = 0;
+    // cumulative electrons of the NEXT read for this thread's halo entries: loaded one read ahead, so that the global
+    // loads fly during the inversion of the current read (ncu before: 1.1 long-scoreboard stall cycles per issue)
+    int cnext[2] = {0, 0};
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+        if (hsrc[q] >= 0) cnext[q] = A.cum[hsrc[q]];
     for (int grp = 0; grp < A.G; ++grp) {
         double acc = 0.0;
         for (int r = 0; r < A.reads_per_group[grp]; ++r, ++k) {
-            __syncthreads();
+            // one barrier per read: read k stages into buffer k & 1, which was last read during read k-2, i.e. before
+            // every thread arrived at the barrier of read k-1
+            double (*seb)[FTX + 2] = se[k & 1];
 #pragma unroll
             for (int q = 0; q < 2; ++q)
-                if (hpos[q] >= 0)
-                    (&se[0][0])[hpos[q]] = hsrc[q] >= 0 ? (double)A.cum[(long)k * npa + hsrc[q]] + (double)(&ss[0][0])[hpos[q]] : 0.0;
+                if (hpos[q] >= 0) (&seb[0][0])[hpos[q]] = hsrc[q] >= 0 ? (double)cnext[q] + (double)(&ss[0][0])[hpos[q]] : 0.0;
             __syncthreads();
+            if (k + 1 < A.n_reads) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    if (hsrc[q] >= 0) cnext[q] = A.cum[(long)(k + 1) * npa + hsrc[q]];
+            }
             if (owner) {
                 const int sy = ty + 1, sx = tx + 1;
+                double (*se)[FTX + 2] = seb;  // (the names below are those of the single-buffer version)
                 double conv;
                 if (K) {
                     conv = se[sy][sx] * (double)kt[0];

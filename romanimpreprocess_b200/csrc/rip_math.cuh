@@ -243,8 +243,31 @@ RIP_HD double invlin_fast_z(double Slin, const double (&cd)[P], float A, float m
     if (!(dhi < lim)) dhi = lim;
     if (!(mu_far == mu_far) || !(rr == rr)) { dlo = -lim; dhi = lim; }
     const int Zlo = (int)dlo, Zhi = (int)dhi;
-    int Z = 0, istep = 1 << 24;
-    for (int j = 1; j < 25; ++j) {
+    int Z = 0, istep = 1 << 24, j0 = 1;
+    // Closed form for the leading run of far steps.  While every visited Z is far, each decision goes towards r, i.e. the
+    // search walks the midpoints of the dyadic intervals that contain r: after k steps Z + 2^24 is an odd multiple of
+    // 2^(24-k).  Let [t, u] = [Zlo, Zhi] + 2^24 be the not-far window and 2^b the granularity of the COARSEST dyadic point
+    // inside it (highest bit in which t-1 and u differ).  No midpoint of granularity > 2^b lies in the window, so the
+    // first 23-b visited points are far and the (23-b)-th is the odd multiple of 2^(b+1) of the interval of width
+    // 2^(b+2) that contains the window: the loop starts there (about 6 iterations remain instead of 24).
+    {
+        const int t = Zlo + (1 << 24), uu = Zhi + (1 << 24);
+        if (t >= 1 && uu < (1 << 25) && uu >= t) {
+            const unsigned x = (unsigned)(t - 1) ^ (unsigned)uu;
+#if defined(__CUDA_ARCH__)
+            const int b = 31 - __clz((int)x);
+#else
+            const int b = 31 - __builtin_clz(x);
+#endif
+            const int nskip = 23 - b;
+            if (nskip >= 1) {
+                Z = (int)((((unsigned)uu >> (b + 2)) << (b + 2)) + (1u << (b + 1))) - (1 << 24);
+                istep = 1 << (b + 1);
+                j0 = nskip + 1;
+            }
+        }
+    }
+    for (int j = j0; j < 25; ++j) {
         istep >>= 1;
         bool lt;
         if (Z < Zlo) {
