@@ -308,7 +308,7 @@ struct FwdArgs {
     float* out;                 // [G,na,na]
 };
 
-constexpr int FTX = 32, FTY = 8;
+constexpr int FTX = 32, FTY = 4;
 
 __global__ void invlin_certify_kernel(const float* __restrict__ coefs, int P, long npl, float* __restrict__ linA,
                                       float* __restrict__ linm) {
@@ -488,7 +488,7 @@ static void cr_tables(std::vector<float>& len_cdf, std::vector<float>& dedx_cdf)
 }
 
 template <int P, typename TG, typename TK>
-__global__ void __launch_bounds__(FTX * FTY, 3) fwd_ramp_kernel(const FwdArgs A) {
+__global__ void __launch_bounds__(FTX * FTY, 6) fwd_ramp_kernel(const FwdArgs A) {
     __shared__ double se[2][FTY + 2][FTX + 2];  // electrons in the well at this read (counts so far + start_e), double-buffered
     __shared__ float ss[FTY + 2][FTX + 2];   // start_e of the tile + halo
     const int tid = threadIdx.x, tx = tid % FTX, ty = tid / FTX;
