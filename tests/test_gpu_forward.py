@@ -208,6 +208,20 @@ def test_cosmic_ray_jump_count_like_the_reference_workflow():
         torch.cuda.synchronize()
         pdq = z.d_pdq.cpu().numpy().view(np.uint32)
         count = int(np.count_nonzero(pdq & np.uint32(pixel.JUMP_DET)))
+        # quality of the unmasked pixels, as the reference asserts it (test_workflow.py:660-668): calibrated slope minus
+        # the expected signal [DN/s] is beyond 100 (resp. 20 where the signal is below 1 DN/s: everywhere here) in fewer
+        # than 50 pixels of the exposure
+        from romanimpreprocess_b200 import pars
+
+        slope = z.d_slope.cpu().numpy()[4:-4, 4:-4]
+        good = pdq[4:-4, 4:-4] == 0
+        # (the scene enters as C t g/g_ideal * image * flat electrons, sim_to_isim.py:645-647, so the flat-fielded slope
+        #  in DN/s is image / g_ideal; the reference's fixture has gain == g_ideal and divides by its gain map)
+        expected = image / np.float32(pars.g_ideal)
+        x = np.where(good, slope - expected, 0.0)
+        n100, n20 = int(np.count_nonzero(np.abs(x) > 100)), int(np.count_nonzero(np.abs(x) > 20))
+        assert good.mean() > 0.9 and n100 < 50 and n20 < 50, (good.mean(), n100, n20)
+        assert abs(np.median(x[good])) < 0.02 * float(np.median(expected[good])) + 0.01  # unbiased to ~2 %
         z0 = mr.Realizations(image, z.cal, rp, keep_stacks=0, crparam=None)
         z0.step(200)
         torch.cuda.synchronize()
