@@ -19,7 +19,8 @@ the sky level propagated through the ramp-fit weights of each pixel's ramp end, 
 :173-227 -> ``GalPoisson``; ``rip_pearson_noise_dev``), ``S<order>``, ``C<tag>`` (a label: ignored, as in the reference)
 -- i.e. both production layer families ``Rz4PbrS2C*`` and ``Rz4OS2C*`` (runs/summer2025run/OpenUniverse_to_L1L2.py:124-133).
 ``O`` generates Pearson Type I (Beta) deviates, the type every Roman read pattern tried here selects (their nu_41 is
-negative); a pixel that falls into Types III-VI raises ``NotImplementedError`` instead of silently drawing nothing.
+negative), and Type VI (beta prime); a pixel that falls into Type IV (or exactly onto the Type III / V lines) raises
+``NotImplementedError`` instead of silently drawing nothing.
 Random numbers are Philox (the reference: GalSim / NumPy): layers are validated statistically.
 
 ``generate_all_noise(config)`` is the reference's driver (:334-391): layers of ``config["NOISE"]["LAYER"]`` for the exposure
@@ -181,8 +182,8 @@ class NoiseLayers:
                                                  _ptr(self.d_diff), _ptr(bad), st))  # fmt: skip
             nbad = int(bad.item())
             if nbad:
-                raise NotImplementedError(f"noise directive {cmd!r}: {nbad} pixels need Pearson Types III-VI, which are not "
-                                          "generated on the GPU (only Type I, the one Roman read patterns select)")  # fmt: skip
+                raise NotImplementedError(f"noise directive {cmd!r}: {nbad} pixels need Pearson Type IV (or III / V), which are not "
+                                          "generated on the GPU (Types I and VI are; Roman read patterns select Type I)")  # fmt: skip
         if "P" in cmd:
             pflags = _get_subscript(cmd, "P")
             if "orig" not in self.have:

@@ -1117,7 +1117,8 @@ namespace rip {
 // beta_2 = (3 nu21^2 I + nu41) / (nu21^2 I); outside the admissible region the draw is 0
 // (GalPoisson/draw_with_tilnus.py:42-60); below the Type III line (beta_2 < 1.5 beta_1 + 3) the Pearson Type I = a
 // shifted and scaled Beta(a, b) with (a, b) from the closed form of :160-198 -- the only type the production read
-// patterns reach (their nu_41 is negative).  Types III-VI are counted in *unsupported and draw 0: the host raises.
+// patterns reach (their nu_41 is negative); between the Type III and Type V lines the Type VI = beta prime of :670-721.
+// Types III and V (exact equalities), IV (Devroye's sampler) are counted in *unsupported and draw 0: the host raises.
 // Beta(a, b) = X / (X + Y) with Gamma variates by Marsaglia & Tsang (2000).
 // ---------------------------------------------------------------------------------------------------------
 __device__ inline double gamma_draw(Philox& rng, double a) {
@@ -1191,9 +1192,27 @@ __global__ void pearson_noise_kernel(const PearsonArgs A, const float* __restric
     const bool base = (b2 > 0.0) && (b1 >= 0.0) && (b2 > b1 + 1.0) && (b2 > 0.75 * b1);
     if (!base) return;
     const double rhs1 = 1.5 * b1 + 3.0;
-    if (!(b2 < rhs1)) {  // Types III (==), VI, V, IV
+    if (!(b2 < rhs1)) {  // Types III (==), VI, V (==), IV
         const double rhs2 = (48.0 + 39.0 * b1 + 6.0 * pow(4.0 + b1, 1.5)) / (32.0 - b1);
-        if (b2 == rhs1 || b2 == rhs2 || (b2 > rhs1 && b2 < rhs2) || (b2 > rhs2 && b1 < 32.0)) atomicAdd(unsupported, 1);
+        if (b2 > rhs1 && b2 < rhs2) {
+            // Type VI = shifted / scaled beta prime (GalPoisson/draw_with_tilnus.py:670-721): y = X / Y with
+            // X ~ Gamma(alpha), Y ~ Gamma(beta); draw = sign (scale y - shift)
+            const double r = 6.0 * (b2 - b1 - 1.0) / (3.0 * b1 - 2.0 * b2 + 6.0);
+            const double eps = r * r / (4.0 + (b1 / 4.0) * (r + 2.0) * (r + 2.0) / (r + 1.0));
+            const double dd = sqrt(r * r - 4.0 * eps);
+            const double q1 = (2.0 - r + dd) / 2.0, q2 = (r - 2.0 + dd) / 2.0;
+            const double al = q2 + 1.0, be = q1 - q2 - 1.0;
+            const double var1 = al * (al + be - 1.0) / ((be - 2.0) * (be - 1.0) * (be - 1.0));
+            const double sc = sqrt(n21 * I / var1), sh = sc * (al / (be - 1.0));
+            if (!(al > 0.0) || !(be > 2.0) || !(sc == sc)) { atomicAdd(unsupported, 1); return; }
+            Philox rng;
+            rng.init(A.seed, (uint64_t)p, 160u);
+            const double X = gamma_draw(rng, al), Y = gamma_draw(rng, be);
+            const double draw = (n31 >= 0.0 ? 1.0 : -1.0) * (sc * (X / Y) - sh);
+            diff[p] = (float)((TP)diff[p] + (TP)(float)draw / g);
+            return;
+        }
+        if (b2 == rhs1 || b2 == rhs2 || (b2 > rhs2 && b1 < 32.0)) atomicAdd(unsupported, 1);  // III, V, IV
         return;
     }
     // Type I: u = a + b, v = (a - b)^2 / (a b)

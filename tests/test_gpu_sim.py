@@ -606,7 +606,24 @@ def test_noise_layer_pearson_directive_moments():
         withsky[...] = (np.logspace(-3, 6, na * na).reshape(na, na) / gain).astype(np.float32)
         e3, nbad = run(8)
         assert nbad == 0 and np.all(np.isfinite(e3)) and np.count_nonzero(e3) > 0.5 * e3.size
-        # a positive nu41 large enough to leave the Type I region is reported, not silently zeroed
+        # Type VI (beta prime): a moderately positive nu41 puts beta_2 between the Type III and Type V lines; same moment
+        # targets.  nu41 = 1.6 nu31^2 / nu21 gives beta_2 - 3 = 1.6 beta_1 for every intensity.
+        tab6 = tab.copy()
+        tab6[:, 2] = np.where(tab6[:, 0] > 0, 1.6 * tab6[:, 1] ** 2 / np.where(tab6[:, 0] > 0, tab6[:, 0], 1.0), 0.0)
+        withsky[...] = (I / gain).astype(np.float32)
+        e6, nbad = run(9, tab6)
+        assert nbad == 0
+        n21, n31, n41 = tab6[2]
+        for k, v in enumerate(levels[1:4], start=1):
+            x = e6[:, na // 2 :][k * band + 1 : (k + 1) * band - 1].ravel()
+            m2, m3, m4 = n21 * v, n31 * v, 3 * n21**2 * v**2 + n41 * v
+            b1, b2 = m3**2 / m2**3, m4 / m2**2
+            assert 1.5 * b1 + 3 < b2 < (48 + 39 * b1 + 6 * (4 + b1) ** 1.5) / (32 - b1)  # the case is Type VI
+            N = x.size
+            assert abs(x.mean()) < 5 * np.sqrt(m2 / N) and abs(x.var() / m2 - 1) < 6 * np.sqrt((b2 - 1) / N) + 1e-3, (v, x.mean(), x.var(), m2)
+            sk_hat = np.mean((x - x.mean()) ** 3) / x.var() ** 1.5
+            assert abs(sk_hat - m3 / m2**1.5) < 6 * np.sqrt(6.0 / N) + 0.08 * abs(m3 / m2**1.5), (v, sk_hat, m3 / m2**1.5)
+        # a positive nu41 large enough to reach the Type IV region is reported, not silently zeroed
         tab_bad = tab.copy()
         tab_bad[:, 2] = np.abs(tab_bad[:, 2]) * 50.0
         _, nbad = run(7, tab_bad)
