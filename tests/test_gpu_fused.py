@@ -192,6 +192,22 @@ def test_full_frame_every_pixel(full_case):
     assert np.count_nonzero(ref["pdq"] & orc.GW_AFFECTED_DATA) > np.count_nonzero(cal["mask"]["roman"]["dq"] & orc.GW_AFFECTED_DATA)
 
 
+def test_full_frame_kernel_variants_agree_and_repeat(full_case):
+    """The default kernel (v6: five CTAs per SM, two barriers per step, rings reused after 3 / 4 rows) run three times on the
+    whole 4096^2 frame gives bitwise identical arrays each time (a shared-memory race would not) and the same arrays as the
+    v2 kernel (params.threads = -1) and, for the float64-ipc4d path, as its v2 form."""
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+
+    cal, data_u16, amp33_u16, rp, area = full_case
+    keys = ("slope", "err_read", "err_poisson", "pdq", "rdq", "endslice")
+    with gci.CalDir(cal) as cd:
+        runs = [gci.calibrate_arrays(cd, data_u16, amp33_u16, rp, 3.04, area, dict(CFG7), do_refpix=True, want_rdq=True,
+                                     want_endslice=True, threads=t) for t in (0, 0, 0, -1)]  # fmt: skip
+    for r in runs[1:]:
+        for k in keys:
+            assert np.array_equal(runs[0][k], r[k], equal_nan=runs[0][k].dtype.kind == "f"), k
+
+
 def test_full_frame_dummy_caldir_dtypes():
     """The dtypes of the production DUMMY CALDIR (reference runs/summer2025run/make_gain_file.py:88,138,194): gain
     float32, ipc4d FLOAT64 (the reference then runs its IPC stage in float64), at 4096^2 x 8, every pixel."""
