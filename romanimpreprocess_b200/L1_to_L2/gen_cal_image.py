@@ -546,7 +546,8 @@ def calibrateimage(config, verbose=True, device=0):
     (``asdf`` if installed, else ``io.asdf_lite``).
 
     Not implemented (raise ``NotImplementedError`` instead of silently differing from the reference): ``dark_decay`` in
-    CALDIR (:567-570), ``correct_wfi18_transient`` (:572-575), ``romancal_ramp_fit`` (:415-432), ``FITSOUT`` (:725-736).
+    CALDIR (:567-570), ``correct_wfi18_transient`` (:572-575), ``romancal_ramp_fit`` (:415-432).  ``FITSOUT`` (:725-736) is
+    written with ``io/fits_lite.py``.
     Metadata of the L1 file is passed through; romanisim's ``make_asdf`` bookkeeping (photometry, cal_step, WCS object)
     is not reproduced: the FITS header text is stored under ``processinfo["fitswcs"]`` instead.
     """
@@ -556,7 +557,7 @@ def calibrateimage(config, verbose=True, device=0):
     caldir = config["CALDIR"]
     if "dark_decay" in caldir:
         raise NotImplementedError("CALDIR['dark_decay'] (romancal dark-decay step, gen_cal_image.py:567-570) is not implemented on the GPU path")
-    for key in ("correct_wfi18_transient", "romancal_ramp_fit", "FITSOUT"):
+    for key in ("correct_wfi18_transient", "romancal_ramp_fit"):
         if config.get(key, False):
             raise NotImplementedError(f"config['{key}'] is not implemented on the GPU path (reference gen_cal_image.py)")
     mylog = ProcessLog()
@@ -635,6 +636,12 @@ def calibrateimage(config, verbose=True, device=0):
     if config.get("SLICEOUT", False):
         processinfo["endslice"] = out["endslice"]
     write_tree(config["OUT"], {"roman": im2, "processinfo": processinfo})
+    if config.get("FITSOUT", False):  # (gen_cal_image.py:725-736; saturated pixels are accepted in this step, as there)
+        from ..io import fits_lite  # noqa: PLC0415
+
+        good = ~maskhandling.PixelMask1.build(im2["dq"], device=device)
+        fits_lite.write_hdus(config["OUT"][:-5] + "_asdf_to.fits",
+                             [(im2["data"], None), (im2["dq"], None), (np.where(good, im2["data"], -1000).astype(np.float32), None)])  # fmt: skip
     if verbose:
         print(mylog.output)
 

@@ -253,20 +253,6 @@ def make_noise_cube_arrays(data, amp33, caldir, read_pattern, frame_time, layers
         nl.close()
 
 
-def _fits_cube(path, cube):
-    """Minimal FITS primary HDU for a float32 cube (the reference's FITSOUT side product, :386-390)."""
-    a = np.ascontiguousarray(cube, dtype=">f4")
-    cards = [f"{'SIMPLE':<8}= {'T':>20}", f"{'BITPIX':<8}= {-32:>20}", f"{'NAXIS':<8}= {a.ndim:>20}"]
-    cards += [f"{'NAXIS' + str(i + 1):<8}= {d:>20}" for i, d in enumerate(a.shape[::-1])]
-    cards.append("END")
-    hdr = "".join(c.ljust(80) for c in cards)
-    hdr += " " * (-len(hdr) % 2880)
-    with open(path, "wb") as f:
-        f.write(hdr.encode("ascii"))
-        f.write(a.tobytes())
-        f.write(b"\0" * (-a.nbytes % 2880))
-
-
 def generate_all_noise(config, device=0):
     """
     Driver for noise generation: the reference's ``generate_all_noise`` (L1_to_L2/gen_noise_image.py:334-391) with the
@@ -309,4 +295,7 @@ def generate_all_noise(config, device=0):
         noiseimage = noiseimage.astype(np.float16)
     write_tree(noise["OUT"], {"config": gci._plain_copy(config), "noise": noiseimage})
     if config.get("FITSOUT", False):
-        _fits_cube(noise["OUT"][:-5] + "_asdf_to.fits", noiseimage.astype(np.float32))
+        from ..io import fits_lite  # noqa: PLC0415
+
+        # (FITS has no float16: float32 as in the reference, :386-390)
+        fits_lite.write_hdus(noise["OUT"][:-5] + "_asdf_to.fits", [(noiseimage.astype(np.float32), None)])

@@ -38,6 +38,23 @@ class CombinedMask:
         _lib.check(_lib.lib().rip_mask_build_host(device, _lib.ptr(dq), ny, nx, _lib.ptr(self.array), _lib.ptr(out)))
         return out.astype(bool)
 
+    def convert_file(self, file_in, file_mask, device=0):
+        """Stand-alone function to make a mask from an L2 file (reference utils/maskhandling.py:119-149; the third call of
+        the production loop, runs/summer2025run/OpenUniverse_to_L1L2.py:165).  ``.asdf``: the boolean array under ``mask``;
+        ``.fits``: a masked image (HDU0: data with -1000 where masked, for display) and an int8 version (HDU1, ``MASK``)."""
+        from ..caltree import open_tree, write_tree  # noqa: PLC0415
+        from ..io import fits_lite  # noqa: PLC0415
+
+        with open_tree(file_in) as f_in:
+            dq = np.asarray(f_in["roman"]["dq"])
+            data = np.asarray(f_in["roman"]["data"])
+        locmask = self.build(dq, device=device)
+        if file_mask[-5:] == ".asdf":
+            write_tree(file_mask, {"mask": locmask})
+        elif file_mask[-5:] == ".fits":
+            fits_lite.write_hdus(file_mask, [(np.where(locmask, -1000.0, data).astype(np.float32), None),
+                                             (np.where(locmask, 1, 0).astype(np.int8), {"EXTNAME": "MASK"})])  # fmt: skip
+
 
 # reference utils/maskhandling.py:152-178
 PixelMask1 = CombinedMask(

@@ -40,7 +40,7 @@ def test_extract_ref_file_is_reconstituted(tmp_path):
 
 def test_unimplemented_switches_raise(tmp_path):
     config, *_ = write_exposure(str(tmp_path), n=128)
-    for key in ("correct_wfi18_transient", "romancal_ramp_fit", "FITSOUT"):
+    for key in ("correct_wfi18_transient", "romancal_ramp_fit"):
         with pytest.raises(NotImplementedError, match=key):
             gci.calibrateimage(dict(config, **{key: True}))
     bad = dict(config, CALDIR=dict(config["CALDIR"], dark_decay="x.asdf"))
@@ -58,7 +58,12 @@ def test_calibrateimage_writes_the_l2_file(tmp_path, n, ipc_dtype):
 
     config, cal, data, amp33, rp = write_exposure(str(tmp_path), n=n, ipc_dtype=ipc_dtype)
     gci.calibrateimage(config, verbose=False)
-    gci.calibrateimage(config, verbose=False)  # second exposure on the cached CALDIR / pipeline
+    gci.calibrateimage(dict(config, FITSOUT=True), verbose=False)  # second exposure on the cached CALDIR / pipeline
+    from romanimpreprocess_b200.io import fits_lite
+
+    (fd, _), (fq, hq), (fm, _) = fits_lite.read_hdus(config["OUT"][:-5] + "_asdf_to.fits")
+    maskhandling.PixelMask1.convert_file(config["OUT"], config["OUT"][:-5] + "_mask.fits")
+    (md, _), (mm, hm) = fits_lite.read_hdus(config["OUT"][:-5] + "_mask.fits")
     gci.clear_caldir_cache()
     c = {k: v["roman"] for k, v in cal.items()}
     area = coordutils.pixelarea(coordutils.wcs_from_config(config), N=n) / pars.Omega_ideal
@@ -68,6 +73,11 @@ def test_calibrateimage_writes_the_l2_file(tmp_path, n, ipc_dtype):
         act = np.s_[4:-4, 4:-4]
         assert np.array_equal(np.asarray(r["dq"]), ref["pdq"][act])
         assert np.array_equal(np.asarray(pi["endslice"]), ref["endslice"])
+        # FITS side products (gen_cal_image.py:725-736, maskhandling.py:145-149)
+        grown = maskhandling.PixelMask1.build(ref["pdq"][act])
+        assert np.array_equal(fq, ref["pdq"][act]) and fq.dtype == np.uint32 and hq["BZERO"] == 2147483648
+        assert np.array_equal(fd, np.asarray(r["data"])) and np.array_equal(fm, np.where(~grown, fd, -1000).astype(np.float32))
+        assert np.array_equal(mm, grown.astype(np.int8)) and hm["EXTNAME"] == "MASK" and np.array_equal(md, np.where(grown, -1000.0, fd).astype(np.float32))
         np.testing.assert_allclose(np.asarray(r["data_withsky"]), ref["slope"][act], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(np.asarray(r["var_rnoise"]), ref["err_read"][act] ** 2, rtol=2e-5, atol=1e-9)
         np.testing.assert_allclose(np.asarray(r["var_poisson"]), ref["err_poisson"][act] ** 2, rtol=2e-5, atol=1e-9)

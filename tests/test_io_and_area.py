@@ -198,3 +198,25 @@ def test_area_device_matches_numpy():
         af = cu.pixelarea_device(w, N=N, inv_omega=1.0 / pars.Omega_ideal, dtype=np.float32)
         assert af.dtype == np.float32 and np.max(np.abs(af / (ref / pars.Omega_ideal) - 1)) < 2e-7
         assert _lib.lib().rip_launch_count() > 0
+
+
+def test_fits_lite_round_trip(tmp_path):
+    """io/fits_lite.py: the two FITS layouts the reference writes (mask image with an int8 MASK extension,
+    utils/maskhandling.py:145-149; float32 noise cube, gen_noise_image.py:386-390) -- blocks of 2880 bytes, big-endian
+    data, signed bytes as BITPIX 8 + BZERO -128."""
+    from romanimpreprocess_b200.io import fits_lite
+
+    rng = np.random.RandomState(4)
+    img = rng.randn(37, 53).astype(np.float32)
+    msk = (rng.rand(37, 53) < 0.3).astype(np.int8) - (rng.rand(37, 53) < 0.1).astype(np.int8)
+    cube = rng.randn(3, 11, 7).astype(np.float32)
+    p1, p2 = str(tmp_path / "m.fits"), str(tmp_path / "c.fits")
+    fits_lite.write_hdus(p1, [(img, None), (msk, {"EXTNAME": "MASK"})])
+    fits_lite.write_hdus(p2, [(cube, None)])
+    raw = open(p1, "rb").read()
+    assert len(raw) % 2880 == 0 and raw[:30] == b"SIMPLE  =                    T" and b"XTENSION= 'IMAGE   '" in raw
+    (a0, h0), (a1, h1) = fits_lite.read_hdus(p1)
+    assert np.array_equal(a0, img) and h0["BITPIX"] == -32 and h0["NAXIS1"] == 53 and h0["NAXIS2"] == 37
+    assert np.array_equal(a1, msk) and a1.dtype == np.int8 and h1["EXTNAME"] == "MASK" and h1["BZERO"] == -128
+    ((c0, hc),) = fits_lite.read_hdus(p2)
+    assert np.array_equal(c0, cube) and hc["NAXIS"] == 3 and hc["NAXIS3"] == 3
