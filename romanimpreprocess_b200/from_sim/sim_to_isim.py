@@ -246,5 +246,165 @@ def simulate_counts(image, caldir, read_pattern, rng=None, seed=None, area_ratio
     return (out, rate) if return_rate else out
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# File-level driver: run_config / Image2D (reference from_sim/sim_to_isim.py:63-160, 405-520, 612-700, 793-812, 947-997)
+# ---------------------------------------------------------------------------------------------------------------
+L1_TAG = "asdf://stsci.edu/datamodels/roman/tags/wfi_science_raw-1.0.0"
+
+
+def _sip_flip(header, axis):
+    """WCS part of ``hdu_sip_hflip`` (axis 1) / ``hdu_sip_vflip`` (axis 2): reference :63-160, on a header dict in place.
+    ``n`` = image size along the flipped axis comes from NAXIS<axis>."""
+    n = int(header[f"NAXIS{axis}"])
+    header[f"CRPIX{axis}"] = n + 1 - header[f"CRPIX{axis}"]
+    for key in (f"CD1_{axis}", f"CD2_{axis}"):
+        if key in header:
+            header[key] = -header[key]
+    try:
+        a_order, b_order = int(header["A_ORDER"]), int(header["B_ORDER"])
+    except (ValueError, KeyError):
+        return
+    # the powers of the flipped SIP axis: u^p for axis 1, v^q for axis 2.  A (the u distortion) changes sign for even
+    # powers of u / odd powers of v, B (the v distortion) for odd powers of u / even powers of v.
+    for name, order, parity in (("A", a_order, 0 if axis == 1 else 1), ("B", b_order, 1 if axis == 1 else 0)):
+        for p in range(order + 1):
+            for q in range(order + 1 - p):
+                if (p if axis == 1 else q) % 2 == parity:
+                    key = f"{name}_{p:1d}_{q:1d}"
+                    if key in header:
+                        header[key] = -float(header[key])
+
+
+class Image2D:
+    """2D scene with its WCS: the reference's ``Image2D("anlsim", fname=...)`` (an OpenUniverse-2024 style "truth" FITS image
+    in electrons per exposure), ``simulate`` through a CALDIR and ``L1_write_to``.  Scene electrons, ramps, cosmic rays,
+    reference pixels and 1/f noise are generated on the GPU; FITS / ASDF files by ``io/fits_lite.py`` / ``caltree``.
+
+    Not reproduced: romanisim's built-in reference data (``caldir=None``), its metadata bookkeeping (a minimal ``meta`` with
+    exposure / instrument / pointing entries is written), the idealised L2 product (``L2_write_to``), and the zodiacal sky
+    level of ``galsim.roman.getSkyLevel`` (configure ``SKY_E_PER_S`` [e/s/pixel], default 0)."""
+
+    def __init__(self, intype, **kwargs):
+        if intype != "anlsim":
+            raise ValueError(f"Image2D: unknown input type {intype!r}")
+        self.init_anlsim(kwargs["fname"], flip=kwargs.get("flip", True))
+
+    def init_anlsim(self, fname, flip=True):
+        import re  # noqa: PLC0415
+
+        from ..io import fits_lite  # noqa: PLC0415
+
+        m = re.search(r"_(\d+)_(\d+)\.fits", fname)
+        self.idsca = (int(m.group(1)), int(m.group(2)))
+        data, self.header = fits_lite.read_primary(fname)
+        data = np.array(data, dtype=np.float64)
+        if flip:  # SCAs are flipped depending on which row of the focal plane they are in (:489-493)
+            if self.idsca[1] % 3 == 0:
+                data = data[:, ::-1]
+                _sip_flip(self.header, 1)
+            else:
+                data = data[::-1, :]
+                _sip_flip(self.header, 2)
+        self.image = np.ascontiguousarray(data / float(self.header["EXPTIME"]), dtype=np.float32)  # electrons per second
+        self.header["CRPIX1"] -= 1  # offset from FITS -> GWCS convention (:497-498)
+        self.header["CRPIX2"] -= 1
+        date = str(self.header.get("DATE-OBS", "2025-01-01T00:00:00.000000"))
+        self.date = date.replace(" ", "T") + ("Z" if "DATE-OBS" in self.header else "")
+        self.filter = str(self.header.get("FILTER", "F184"))[:4]
+        self.ra_, self.dec_, self.pa_ = (float(self.header.get(k, 0.0)) for k in ("RA_TARG", "DEC_TARG", "PA_OBSY"))
+
+    def simulate(self, use_read_pattern, caldir=None, config=None, seed=43, includewcs=False, device=0):
+        from ..L1_to_L2 import gen_cal_image as gci  # noqa: PLC0415
+        from ..io import asdf_lite  # noqa: PLC0415
+        from ..utils import coordutils  # noqa: PLC0415
+
+        config = config or {}
+        if caldir is None:
+            raise NotImplementedError("Image2D.simulate without CALDIR uses romanisim's built-in reference data: not available here")
+        cal = gci._cached_caldir(caldir, device)["cal"]
+        na, n, nb = cal.na, cal.n, cal.nb
+        if self.image.shape != (na, na):
+            raise ValueError(f"the scene must cover the active array ({na},{na}), got {self.image.shape}")
+        rp = [list(g) for g in use_read_pattern]
+        G = len(rp)
+        # pixel area / Omega_ideal on the active array (:645; the flat already contains the pixel area)
+        wcs_hdr = dict(self.header, CRPIX1=self.header["CRPIX1"] + 1, CRPIX2=self.header["CRPIX2"] + 1)
+        area = coordutils.pixelarea_device(coordutils.FitsWCS(wcs_hdr), N=na, inv_omega=1.0 / pars.Omega_ideal,
+                                           dtype=np.float64, device=device)  # fmt: skip
+        cnorm = float(config.get("CNORM", 1.0))
+        counts = simulate_counts(self.image, cal, rp, seed=seed, area_ratio=area, cnorm=cnorm, dark=True,
+                                 sky=config.get("SKY_E_PER_S"), device=device)  # fmt: skip
+        # cosmic rays as the reference switches them on (crparam={}: romanisim's defaults); the default detector area of
+        # 16.8 cm^2 belongs to the full 4088^2 array and scales with the frame for the small frames of the tests
+        crparam = {"area": CR_DEFAULTS["area"] * (na / 4088.0) ** 2}
+        l1, _ = make_l1_fullcal(counts, rp, cal, seed=(int(seed) + 1) & 0xFFFFFFFFFFFFFFFF, crparam=crparam)
+        data = np.zeros((G, n, n), np.uint16)
+        data[:, nb : n - nb, nb : n - nb] = np.clip(l1, 0, 65535).astype(np.uint16)
+        amp33 = None
+        if cal.has_amp33 and not (isinstance(caldir, dict) and caldir.get("NO_AMP33")):
+            amp33 = np.zeros((G, n, 128), np.uint16)
+        tij = [[READ_TIME * r for r in g] for g in rp]
+        fill_in_refdata_and_1f(data, cal, (int(seed) + 2) & 0xFFFFFFFFFFFFFFFF, tij, fill_in_banding=True, amp33=amp33)
+        sca = self.idsca[1]
+        meta = asdf_lite.TaggedDict({
+            "exposure": {"read_pattern": rp, "frame_time": READ_TIME, "nresultants": G, "ma_table_number": 1000000,
+                         "start_time": self.date},
+            "instrument": {"name": "WFI", "detector": f"WFI{sca:02d}", "optical_element": "F" + self.filter[1:]},
+            "observation": {"visit": int(self.idsca[0])},
+            "pointing": {"ra_v1": self.ra_, "dec_v1": self.dec_, "pa_v3": self.pa_},
+            "model_type": "ScienceRawModel",
+        })  # fmt: skip
+        im = {"meta": meta, "data": data}
+        if amp33 is not None:
+            im["amp33"] = amp33
+        if "EXTRACT_REF" in config:  # reference read moved out of the cube (:711-735)
+            off = int(config["EXTRACT_REF"].get("data_encoding_offset", 0))
+            meta["instrument"]["data_encoding_offset"] = off
+            meta["exposure"]["read_pattern"] = rp[1:]
+            for key, refkey in (("data", "reference_read"), ("amp33", "reference_amp33")):
+                if key not in im:
+                    continue
+                cube = im[key]
+                im[refkey] = np.copy(cube[0])
+                modref = cube[0].astype(np.int32) - off
+                for k in range(1, G):
+                    cube[k] = np.clip(cube[k].astype(np.int32) - modref, 0, 65535).astype(np.uint16)
+                im[key] = cube[1:]
+        self.tree = {"roman": asdf_lite.TaggedDict(im, tag=L1_TAG), "romanisim": {"version": "romanimpreprocess_b200"}}
+
+    def L1_write_to(self, filename):
+        from ..caltree import write_tree  # noqa: PLC0415
+
+        if not hasattr(self, "tree"):
+            return False
+        write_tree(filename, self.tree)
+        return True
+
+
+def run_config(config, device=0):
+    """L1 image construction from a configuration dictionary: the reference's ``run_config`` (from_sim/sim_to_isim.py:947-997)
+    with the same keys (``IN``: truth FITS image, ``OUT``: L1 ASDF file, ``READS``, ``CALDIR``, ``SEED``, ``CNORM``,
+    ``EXTRACT_REF``, ``FITSOUT``).  Also writes the FITS WCS header text ``<OUT>_asdf_wcshead.txt`` that
+    ``calibrateimage`` reads back as ``FITSWCS``."""
+    from ..io import fits_lite  # noqa: PLC0415
+
+    caldir = config.get("CALDIR", None)
+    rp = read_pattern_from_reads(config["READS"])
+    seed = int(config.get("SEED", 43))
+    x = Image2D("anlsim", fname=config["IN"])
+    x.simulate(rp, caldir=caldir, config=config, seed=seed, device=device)
+    x.L1_write_to(config["OUT"])
+    with open(config["OUT"][:-5] + "_asdf_wcshead.txt", "w") as f:
+        f.write(fits_lite.header_text(x.header, comment="truth wcs from sim_to_isim"))
+    if config.get("FITSOUT", False):
+        r = x.tree["roman"]
+        d = np.asarray(r["data"])
+        image_out = np.zeros((d.shape[0], d.shape[1], d.shape[2] + 128), np.uint16)
+        image_out[:, :, : d.shape[2]] = d
+        if "amp33" in r:
+            image_out[:, :, d.shape[2] :] = r["amp33"]
+        fits_lite.write_hdus(config["OUT"][:-5] + "_asdf_to.fits", [(image_out, None)])
+
+
 __all__ = ["make_l1_fullcal", "read_pattern_from_reads", "fwd_params", "noise_1f_frame", "fill_in_refdata_and_1f",
-           "sim_calprep", "simulate_counts", "pars"]  # fmt: skip
+           "sim_calprep", "simulate_counts", "pars", "Image2D", "run_config"]  # fmt: skip

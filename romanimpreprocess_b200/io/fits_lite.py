@@ -103,3 +103,41 @@ def read_hdus(path):
             a = a.astype(np.dtype(dt).newbyteorder("="))
         out.append((a, hdr))
     return out
+
+
+def header_text(header, comment=None):
+    """80-column card stream padded to 2880 bytes, as ``astropy.io.fits.Header.tofile`` writes a header (what the
+    ``FITSWCS`` files of the reference hold, from_sim/sim_to_isim.py:986-987)."""
+    cards = [_card(k, v) for k, v in header.items() if k not in ("COMMENT", "HISTORY", "END", "")]
+    if comment:
+        cards.append(f"COMMENT {comment}".ljust(80)[:80])
+    cards.append("END".ljust(80))
+    text = "".join(cards)
+    return text + " " * (-len(text) % 2880)
+
+
+def read_primary(path):
+    """Primary HDU of any simple FITS image file: ``(array in native byte order, header dict in card order)``."""
+    from ..utils.coordutils import parse_header  # noqa: PLC0415
+
+    raw = open(path, "rb").read()
+    pos, text = 0, ""
+    while True:
+        block = raw[pos : pos + 2880].decode("ascii", errors="replace")
+        pos += 2880
+        text += block
+        if any(block[i : i + 8] == "END     " for i in range(0, 2880, 80)):
+            break
+        if pos >= len(raw):
+            raise ValueError(f"{path}: no END card in the primary header")
+    hdr = parse_header(text)
+    shape = tuple(int(hdr[f"NAXIS{i}"]) for i in range(int(hdr["NAXIS"]), 0, -1))
+    dt = {8: ">u1", 16: ">i2", 32: ">i4", 64: ">i8", -32: ">f4", -64: ">f8"}[int(hdr["BITPIX"])]
+    n = int(np.prod(shape)) if shape else 0
+    a = np.frombuffer(raw, dtype=dt, count=n, offset=pos).reshape(shape)
+    a = a.astype(np.dtype(dt).newbyteorder("="))
+    if "BSCALE" in hdr or "BZERO" in hdr:
+        bs, bz = float(hdr.get("BSCALE", 1.0)), float(hdr.get("BZERO", 0.0))
+        if bs != 1.0 or bz != 0.0:
+            a = a * bs + bz
+    return a, hdr

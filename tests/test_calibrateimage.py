@@ -97,3 +97,53 @@ def test_calibrateimage_writes_the_l2_file(tmp_path, n, ipc_dtype):
         m = maskhandling.PixelMask1.build(ref["pdq"])
         binned = np.mean(np.where(~m, ref["slope"], np.nan)[: n // 4 * 4, : n // 4 * 4].reshape(n // 4, 4, n // 4, 4), axis=(1, 3))
         assert abs(pi["medsky"] - np.nanmedian(binned)) < 0.2 * np.nanstd(binned)
+
+
+@pytest.mark.gpu
+def test_run_config_then_calibrateimage_round_trip(tmp_path):
+    """The production loop on files (reference runs/summer2025run/OpenUniverse_to_L1L2.py:155-165): ``sim_to_isim.run_config``
+    turns a truth FITS image into an L1 ASDF file + FITSWCS header text, ``calibrateimage`` turns that into the L2 file,
+    ``PixelMask1.convert_file`` writes the mask: the calibrated slope recovers the (flipped) truth scene."""
+    from fixture_files import sim_header
+
+    from romanimpreprocess_b200 import synth
+    from romanimpreprocess_b200.from_sim import sim_to_isim as s2i
+    from romanimpreprocess_b200.io import fits_lite
+    from romanimpreprocess_b200.utils import maskhandling
+
+    n = 256
+    na = n - 8
+    config2, cal, _, _, rp = write_exposure(str(tmp_path), n=n, ipc_dtype=np.float32)
+    yy, xx = np.mgrid[0:na, 0:na]
+    exptime = 139.8
+    rate = 40.0 + 0.1 * xx + 0.05 * yy  # e/s per ideal pixel, asymmetric so that a wrong flip shows
+    truth = str(tmp_path / "Roman_Test_truth_F184_7_1.fits")  # (obsid 7, SCA 1: vertical flip)
+    hdr = dict(sim_header(na), EXPTIME=exptime, FILTER="F184", RA_TARG=37.0, DEC_TARG=-20.0, PA_OBSY=35.0)
+    hdr["DATE-OBS"] = "2026-03-01 00:00:00.000"
+    fits_lite.write_hdus(truth, [((rate * exptime).astype(np.float32), hdr)])
+    reads = [v for g in rp for v in (g[0], g[-1] + 1)]
+    config1 = {"IN": truth, "OUT": str(tmp_path / "sim_L1_F184_7_1.asdf"), "READS": reads, "CALDIR": config2["CALDIR"],
+               "CNORM": 1.0, "SEED": 500, "FITSOUT": True}  # fmt: skip
+    s2i.run_config(config1)
+    d, a33, rpat, ft, meta, _ = gci.read_l1(config1["OUT"])
+    assert d.shape == (len(rp), n, n) and d.dtype == np.uint16 and rpat == [list(g) for g in rp] and ft == 3.04
+    assert meta["instrument"]["detector"] == "WFI01" and meta["instrument"]["optical_element"] == "F184"
+    assert a33 is not None and a33.shape == (len(rp), n, 128)
+    ((fimg, _),) = fits_lite.read_hdus(config1["OUT"][:-5] + "_asdf_to.fits")
+    assert fimg.shape == (len(rp), n, n + 128) and np.array_equal(fimg[:, :, :n], d)
+    w = coordutils.FitsWCS(open(config1["OUT"][:-5] + "_asdf_wcshead.txt").read())
+    assert w.crpix[1] == pytest.approx(na + 1 - (na + 1) / 2.0 - 1) and w.cd[1, 1] == pytest.approx(-3.0555555555555554e-05)
+    config2 = dict(config2, IN=config1["OUT"], OUT=str(tmp_path / "sim_L2_F184_7_1.asdf"),
+                   FITSWCS=config1["OUT"][:-5] + "_asdf_wcshead.txt")  # fmt: skip
+    gci.calibrateimage(config2, verbose=False)
+    maskhandling.PixelMask1.convert_file(config2["OUT"], config2["OUT"][:-5] + "_mask.fits")
+    gci.clear_caldir_cache()
+    with open_tree(config2["OUT"]) as f:
+        slope, dq = np.asarray(f["roman"]["data_withsky"]), np.asarray(f["roman"]["dq"])
+    expected = (rate[::-1, :] / pars.g_ideal).astype(np.float32)  # SCA 1 is flipped vertically (sim_to_isim.py:489-493)
+    good = dq == 0
+    ratio = slope[good] / expected[good]
+    assert good.mean() > 0.7 and abs(np.median(ratio) - 1.0) < 0.03, (good.mean(), np.median(ratio))
+    wrong = slope[good] / (rate / pars.g_ideal)[good]
+    assert np.std(wrong) > 2 * np.std(ratio)  # (the unflipped scene does not fit)
+    assert synth.FRAME_TIME == ft
