@@ -364,12 +364,16 @@ def run_ours(args):
     o_pdq = torch.empty((n, n), dtype=torch.int32, device=dev)
     o_end = torch.empty((na, na), dtype=torch.int8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
+    lookahead = not args.no_refpix_lookahead
 
     def step(i):
         k = i % n_exp
         gci.calibrate_device(cd, dplan, d_raw[k].data_ptr(), d_amp[k].data_ptr(), d_area.data_ptr(), o_slope.data_ptr(),
                              o_er.data_ptr(), o_ep.data_ptr(), o_pdq.data_ptr(), d_endslice=o_end.data_ptr(),
                              stream=stream)  # fmt: skip
+        if lookahead:  # reference-pixel statistics of the next resident exposure beside this exposure's fused kernel
+            k1 = (i + 1) % n_exp
+            gci.prefetch_refpix_device(cd, d_raw[k1].data_ptr(), d_amp[k1].data_ptr(), G)
 
     def barrier():
         torch.cuda.synchronize()
@@ -512,6 +516,7 @@ def run_ours(args):
                 "l2_policy": f"inputs larger than L2: each step streams {algo_bytes / 1e9:.2f} GB (126 MB L2) and "
                              f"{n_exp} distinct exposures are rotated",
                 "threads": args.threads or 128, "band_rows": args.band_rows or band_txt, "parallelism": f"sca-sharded x{world}",
+                "refpix_lookahead": bool(lookahead),
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name,
@@ -905,6 +910,8 @@ def main():
     ap.add_argument("--cpu-tile", type=int, default=2048, help="side of the sub-frame the cpu_baseline times (2048: about 12 s of oracle work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (for ncu captures)")
+    ap.add_argument("--no-refpix-lookahead", action="store_true",
+                    help="device-resident leg: reference-pixel statistics in the step's own stream (no look-ahead of the next exposure)")
     ap.add_argument("--e2e-area-upload", action="store_true", help="e2e leg: upload the AreaFactor plane per exposure instead of evaluating it on the device from the WCS")
     ap.add_argument("--realizations", type=int, default=64, help="noise realisations (workload realizations)")
     ap.add_argument("--exposures18", type=int, default=4, help="exposures of 18 SCAs each (workload exposure18)")

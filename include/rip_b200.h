@@ -213,6 +213,15 @@ int rip_l1_to_l2_host(rip_caldir* h, const uint16_t* raw, const uint16_t* amp33,
 int rip_l1_to_l2_dev(rip_caldir* h, const uint16_t* d_raw, const uint16_t* d_amp33, const void* d_area,
                      const rip_l1l2_params* prm, const rip_ramp_plan* plan, const double* w_exact,
                      const rip_l2_out* d_out, void* stream);
+/* Look-ahead of the reference-pixel statistics (the "K0" kernels: utils/reference_subtraction_util.py:14-136 restated)
+ * for the NEXT exposure of a device-resident stream: computed on a high-priority side stream of the handle into the
+ * second of two workspace sets while the fused kernel of the current exposure runs.  If the rip_l1_to_l2_dev call that
+ * FOLLOWS names the same d_raw, it waits for that result instead of running the statistics itself (identical results:
+ * same kernels, same inputs); any other call in between discards the look-ahead.  Call it AFTER the rip_l1_to_l2_dev of
+ * the current exposure.  The cubes must be complete in device memory when this is called (the call is not ordered
+ * against any user stream) and must not change until that rip_l1_to_l2_dev call has been issued.
+ * Optional: without it rip_l1_to_l2_dev computes the statistics in its own stream, as before. */
+int rip_caldir_prefetch_refpix(rip_caldir* h, const uint16_t* d_raw_next, const uint16_t* d_amp33_next, int G);
 /* Pipelined host entry for a stream of exposures of one SCA: `depth` exposures in flight on three CUDA streams
  * (H2D | reference-pixel statistics + fused kernel | D2H), so PCIe copies overlap the kernels.  submit() returns
  * immediately (it blocks only when all slots are busy) and hands back a ticket; the host output buffers named in

@@ -339,6 +339,15 @@ def calibrate_device(cal, dplan, d_raw, d_amp33, d_area, d_slope, d_err_read, d_
     )  # fmt: skip
 
 
+def prefetch_refpix_device(cal, d_raw_next, d_amp33_next, ngrp):
+    """
+    Start the reference-pixel statistics of the NEXT exposure (device pointers; the cubes must already be complete) on
+    the handle's side stream, so that they run beside the fused kernel of the current one; the ``calibrate_device`` call
+    with the same ``d_raw`` then only waits for them (``rip_caldir_prefetch_refpix``).  Same results either way.
+    """
+    _lib.check(_lib.lib().rip_caldir_prefetch_refpix(cal.handle, C.c_void_p(d_raw_next), C.c_void_p(d_amp33_next), int(ngrp)))
+
+
 class Pipeline:
     """
     A stream of exposures of one SCA through the GPU with the PCIe copies overlapped (``rip_pipeline_*``): ``depth``

@@ -117,6 +117,7 @@ _SIGS = {
     "rip_caldir_get_static": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "rip_l1_to_l2_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(L1L2Params),
                                     C.POINTER(RampPlan), C.c_void_p, C.POINTER(L2Out)]),
+    "rip_caldir_prefetch_refpix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "rip_l1_to_l2_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(L1L2Params),
                                    C.POINTER(RampPlan), C.c_void_p, C.POINTER(L2Out), C.c_void_p]),
     "rip_pipeline_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

@@ -360,37 +360,37 @@ using namespace rip;
 // =========================================================================================================
 // the handle
 // =========================================================================================================
-static void run_k0(rip_caldir* h, const uint16_t* d_raw, const uint16_t* d_amp33, int G, cudaStream_t st) {
+static void run_k0(rip_caldir* h, rip_caldir::K0Work& W, const uint16_t* d_raw, const uint16_t* d_amp33, int G, cudaStream_t st) {
     const int n = h->n;
     RIP_REQUIRE(h->has_amp33, "reference-pixel correction needs amp33 statistics in the read file (the reference's np.polyfit fails without them: SURVEY 7)");
     RIP_REQUIRE(n % 128 == 0 && n <= 4096 && n >= 128, "reference-pixel correction needs a frame side that is a multiple of 128 in 128..4096 (got %d)", n);
     RIP_REQUIRE(d_amp33 != nullptr, "reference-pixel correction needs the amp33 cube");
     const long M = (long)n * 128;
     const int nch = n / 128;
-    if (h->hist.n < (size_t)G * 4096) {
-        h->hist.alloc((size_t)RIP_GMAX * 4096);
-        h->sel.alloc(RIP_GMAX);
-        h->k0_ticket.alloc(RIP_GMAX);
-        h->k0_ticket.zero(st);
-        h->hist.zero(st);  // (histograms and tickets are left zeroed by every pass)
-        h->rowA.alloc((size_t)RIP_GMAX * n);
-        h->rowB.alloc((size_t)RIP_GMAX * n);
-        h->gmed.alloc(RIP_GMAX);
-        h->rowcorr.alloc((size_t)RIP_GMAX * n);
-        h->chan_m.alloc((size_t)RIP_GMAX * 32);
-        h->chan_c.alloc((size_t)RIP_GMAX * 32);
-        h->chan_line.alloc((size_t)RIP_GMAX * 32 * n);
+    if (W.hist.n < (size_t)G * 4096) {
+        W.hist.alloc((size_t)RIP_GMAX * 4096);
+        W.sel.alloc(RIP_GMAX);
+        W.k0_ticket.alloc(RIP_GMAX);
+        W.k0_ticket.zero(st);
+        W.hist.zero(st);  // (histograms and tickets are left zeroed by every pass)
+        W.rowA.alloc((size_t)RIP_GMAX * n);
+        W.rowB.alloc((size_t)RIP_GMAX * n);
+        W.gmed.alloc(RIP_GMAX);
+        W.rowcorr.alloc((size_t)RIP_GMAX * n);
+        W.chan_m.alloc((size_t)RIP_GMAX * 32);
+        W.chan_c.alloc((size_t)RIP_GMAX * 32);
+        W.chan_line.alloc((size_t)RIP_GMAX * 32 * n);
     }
-    RIP_LAUNCH(k0_rows_kernel, dim3((n + K0_ROWS - 1) / K0_ROWS, G), 256, 0, st, d_amp33, h->amp_med.p, n, h->rowA.p, h->rowB.p, h->sel.p,
-               h->hist.p, h->k0_ticket.p);
+    RIP_LAUNCH(k0_rows_kernel, dim3((n + K0_ROWS - 1) / K0_ROWS, G), 256, 0, st, d_amp33, h->amp_med.p, n, W.rowA.p, W.rowB.p, W.sel.p,
+               W.hist.p, W.k0_ticket.p);
     const int nblk = (int)std::min<long>(64, (M + 4095) / 4096);
     for (int pass = 1; pass < 3; ++pass)
-        RIP_LAUNCH(k0_hist_kernel, dim3(nblk, G), 256, 0, st, d_amp33, h->amp_med.p, M, pass, h->sel.p, h->hist.p, h->k0_ticket.p);
+        RIP_LAUNCH(k0_hist_kernel, dim3(nblk, G), 256, 0, st, d_amp33, h->amp_med.p, M, pass, W.sel.p, W.hist.p, W.k0_ticket.p);
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
-    RIP_LAUNCH(k0_final_kernel, G, 1024, (size_t)2 * np2 * sizeof(float), st, h->sel.p, h->rowA.p, h->rowB.p, n, np2,
-               h->refout_slope, h->rowcorr.p, h->gmed.p);
-    RIP_LAUNCH(k0_chan_kernel, dim3(nch, G), 256, 0, st, d_raw, h->dark_cube.p, n, h->rowcorr.p, h->chan_m.p, h->chan_c.p, h->chan_line.p);
+    RIP_LAUNCH(k0_final_kernel, G, 1024, (size_t)2 * np2 * sizeof(float), st, W.sel.p, W.rowA.p, W.rowB.p, n, np2,
+               h->refout_slope, W.rowcorr.p, W.gmed.p);
+    RIP_LAUNCH(k0_chan_kernel, dim3(nch, G), 256, 0, st, d_raw, h->dark_cube.p, n, W.rowcorr.p, W.chan_m.p, W.chan_c.p, W.chan_line.p);
 }
 
 static double derive_refout_slope(const rip_caldir_desc* d) {
@@ -424,6 +424,15 @@ extern "C" int rip_caldir_create(int device, const rip_caldir_desc* d, rip_caldi
     h->P = d->P;
     const size_t npl = (size_t)n * n, npa = (size_t)na * na;
     RIP_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {
+        int pr_lo = 0, pr_hi = 0;
+        RIP_CUDA(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
+        RIP_CUDA(cudaStreamCreateWithPriority(&h->s_k0, cudaStreamNonBlocking, pr_hi));
+        for (auto& w : h->k0w) {
+            RIP_CUDA(cudaEventCreateWithFlags(&w.ev_k0, cudaEventDisableTiming));
+            RIP_CUDA(cudaEventCreateWithFlags(&w.ev_used, cudaEventDisableTiming));
+        }
+    }
     cudaStream_t st = h->stream;
     h->coefs.upload(d->lin_coefs, (size_t)d->P * npl, st);
     h->Smin.upload(d->Smin, npl, st);
@@ -481,7 +490,12 @@ extern "C" int rip_caldir_create(int device, const rip_caldir_desc* d, rip_caldi
 extern "C" void rip_caldir_destroy(rip_caldir* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    if (h->s_k0) { cudaStreamSynchronize(h->s_k0); cudaStreamDestroy(h->s_k0); }
     if (h->stream) cudaStreamDestroy(h->stream);
+    for (auto& w : h->k0w) {
+        if (w.ev_k0) cudaEventDestroy(w.ev_k0);
+        if (w.ev_used) cudaEventDestroy(w.ev_used);
+    }
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     delete h;
 }
@@ -524,7 +538,21 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
     RIP_REQUIRE(!h->has_bias || h->d.n_bias >= G, "rip_l1_to_l2: biascorr cube has fewer groups than the exposure");
     RIP_REQUIRE(prm->sat_backup >= 0 && prm->sat_backup < RIP_GMAX, "rip_l1_to_l2: bad SATURATION_BACKUP %d", prm->sat_backup);
     const double* dw = plan_to_device(h->device, plan, w_exact, st);
-    if (prm->do_refpix) run_k0(h, d_raw, d_amp33, G, st);
+    // a look-ahead (rip_caldir_prefetch_refpix) is valid for the call that immediately follows it and names the same cube
+    int pre = -1;
+    for (int k = 0; k < 2; ++k) {
+        if (prm->do_refpix && h->k0w[k].key && h->k0w[k].key == (const void*)d_raw) pre = k;
+        h->k0w[k].key = nullptr;
+    }
+    if (pre >= 0) h->k0_cur = pre;
+    rip_caldir::K0Work* W = &h->k0w[h->k0_cur];
+    if (prm->do_refpix) {
+        if (W->busy) {  // work of the side stream on this set (the awaited statistics, or an unused look-ahead)
+            RIP_CUDA(cudaStreamWaitEvent(st, W->ev_k0, 0));
+            W->busy = false;
+        }
+        if (pre < 0) run_k0(h, *W, d_raw, d_amp33, G, st);
+    }
     // v2 (rip_v2_core.cuh) for the common all-f32 configuration; params.threads > 0 selects the generic v1 tile kernel
     // (threads < 0: development selector of the fused-kernel variant, -1 = v2, -2 / -3 = v3 without / with stage b in role X,
     //  -4 = v2t, -5 = v6; default: v6 where supported (G = 8, float32 ipc4d), else v2)
@@ -558,14 +586,15 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
         v2::Args V;
         memset(&V, 0, sizeof V);
         V.n = n; V.ntile = v2::ntiles(n);
-        V.band_rows = prm->band_rows > 0 ? prm->band_rows : v2_default_band_rows(h->device, n, G, (variant == 4 && v6_supported(G, h->P)) ? (k64 ? 4 : 5) : (k64 || variant == 1 || variant == 2) ? ((G <= 8) ? 3 : 2) : 0);
+        const int cps = (variant == 4 && v6_supported(G, h->P)) ? (k64 ? 4 : 5) : (k64 || variant == 1 || variant == 2) ? ((G <= 8) ? 3 : 2) : 0;
+        V.band_rows = prm->band_rows > 0 ? prm->band_rows : v2_default_band_rows(h->device, n, G, cps);
         V.do_refpix = prm->do_refpix; V.do_not_flag_first = prm->do_not_flag_first; V.exclude_first = prm->exclude_first;
         V.sat_backup = prm->sat_backup; V.area_dtype = prm->area_dtype;
         V.negzero = -0.0f;
         V.raw = d_raw; V.area = d_area;
-        V.rowcorr = h->rowcorr.p; V.chan_m = h->chan_m.p; V.chan_c = h->chan_c.p;
+        V.rowcorr = W->rowcorr.p; V.chan_m = W->chan_m.p; V.chan_c = W->chan_c.p;
         V.rec1 = v2_rec1_row0(h, G); V.recK = v2_recK_row0(h); V.thr = h->thr_eff.p;
-        V.chan_line = h->chan_line.p;
+        V.chan_line = W->chan_line.p;
         V.w_exact = dw;
         V.slope = o->slope; V.err_read = o->err_read; V.err_poisson = o->err_poisson; V.pdq = o->pdq;
         V.endslice = o->endslice; V.rdq = o->rdq; V.lincube = o->lin_cube;
@@ -577,6 +606,7 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
         else if (variant && variant != 4) launch_cal_fused_v3(V, G, h->P, variant, st);
         else launch_cal_fused_v2(V, G, h->P, st);
         if (e1) RIP_CUDA(cudaEventRecord(e1, st));
+        if (prm->do_refpix) { RIP_CUDA(cudaEventRecord(W->ev_used, st)); W->used_recorded = true; }
         return;
     }
     CalArgs A;
@@ -586,7 +616,7 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
     A.do_refpix = prm->do_refpix; A.do_not_flag_first = prm->do_not_flag_first; A.exclude_first = prm->exclude_first;
     A.sat_backup = prm->sat_backup; A.area_dtype = prm->area_dtype;
     A.raw = d_raw; A.area = d_area;
-    A.rowcorr = h->rowcorr.p; A.chan_m = h->chan_m.p; A.chan_c = h->chan_c.p;
+    A.rowcorr = W->rowcorr.p; A.chan_m = W->chan_m.p; A.chan_c = W->chan_c.p;
     A.dark = h->dark_cube.p;
     A.bias = bias_p;
     A.coefs = h->coefs.p; A.Smin = h->Smin.p; A.Smax = h->Smax.p; A.Sref = h->Sref.p;
@@ -599,6 +629,7 @@ static void l1_to_l2_dev_impl(rip_caldir* h, const uint16_t* d_raw, const uint16
     if (e0) RIP_CUDA(cudaEventRecord(e0, st));
     launch_cal_fused(A, h->d.gain_dtype, h->has_ipc ? h->d.ipc_dtype : RIP_F32, threads, st);
     if (e1) RIP_CUDA(cudaEventRecord(e1, st));
+    if (prm->do_refpix) { RIP_CUDA(cudaEventRecord(W->ev_used, st)); W->used_recorded = true; }
 }
 
 extern "C" int rip_profile_enable(rip_caldir* h, int on) {
@@ -633,6 +664,22 @@ extern "C" int rip_l1_to_l2_dev(rip_caldir* h, const uint16_t* d_raw, const uint
     RIP_REQUIRE(h, "rip_l1_to_l2_dev: null handle");
     use_device(h->device);
     l1_to_l2_dev_impl(h, d_raw, d_amp33, d_area, prm, plan, w_exact, d_out, (cudaStream_t)stream);
+    RIP_API_END
+}
+
+extern "C" int rip_caldir_prefetch_refpix(rip_caldir* h, const uint16_t* d_raw_next, const uint16_t* d_amp33_next, int G) {
+    RIP_API_BEGIN
+    RIP_REQUIRE(h && d_raw_next && d_amp33_next, "rip_caldir_prefetch_refpix: null argument");
+    RIP_REQUIRE(G >= 3 && G <= RIP_GMAX, "rip_caldir_prefetch_refpix: G=%d outside 3..%d", G, RIP_GMAX);
+    RIP_REQUIRE((int)(h->dark_cube.n / ((size_t)h->n * h->n)) >= G, "rip_caldir_prefetch_refpix: dark cube has fewer groups than the exposure");
+    use_device(h->device);
+    rip_caldir::K0Work& W = h->k0w[1 - h->k0_cur];  // the set the most recent fused launch does NOT read
+    // the last fused kernel that read this set (two exposures back) must have finished before it is overwritten
+    if (W.used_recorded) RIP_CUDA(cudaStreamWaitEvent(h->s_k0, W.ev_used, 0));
+    run_k0(h, W, d_raw_next, d_amp33_next, G, h->s_k0);
+    RIP_CUDA(cudaEventRecord(W.ev_k0, h->s_k0));
+    W.key = (const void*)d_raw_next;
+    W.busy = true;
     RIP_API_END
 }
 
@@ -680,11 +727,15 @@ extern "C" int rip_refpix_stats_host(rip_caldir* h, const uint16_t* raw, const u
     const int n = h->n;
     h->w_raw.upload(raw, (size_t)G * n * n, st);
     h->w_amp.upload(amp33, (size_t)G * n * 128, st);
-    run_k0(h, h->w_raw.p, h->w_amp.p, G, st);
-    if (rowcorr) h->rowcorr.download(rowcorr, (size_t)G * n, st);
-    if (chan_m) h->chan_m.download(chan_m, (size_t)G * 32, st);
-    if (chan_c) h->chan_c.download(chan_c, (size_t)G * 32, st);
-    if (gmed) h->gmed.download(gmed, G, st);
+    RIP_CUDA(cudaStreamSynchronize(h->s_k0));  // a pending look-ahead may own set 0
+    rip_caldir::K0Work& W0 = h->k0w[0];
+    W0.key = nullptr;
+    W0.busy = false;
+    run_k0(h, W0, h->w_raw.p, h->w_amp.p, G, st);
+    if (rowcorr) W0.rowcorr.download(rowcorr, (size_t)G * n, st);
+    if (chan_m) W0.chan_m.download(chan_m, (size_t)G * 32, st);
+    if (chan_c) W0.chan_c.download(chan_c, (size_t)G * 32, st);
+    if (gmed) W0.gmed.download(gmed, G, st);
     RIP_CUDA(cudaStreamSynchronize(st));
     RIP_API_END
 }

@@ -27,10 +27,22 @@ struct rip_caldir {
     DevBuf<float> v2_rec1, v2_recK;
     int v2_G = 0;
     // K0 workspace
-    DevBuf<uint32_t> hist, k0_ticket;
-    DevBuf<SelState> sel;
-    DevBuf<float> rowA, rowB, gmed;
-    DevBuf<double> rowcorr, chan_m, chan_c, chan_line;
+    // K0 (reference-pixel statistics) workspaces: two sets, so that the statistics of the NEXT exposure can be computed on
+    // the handle's side stream while the fused kernel of the current one runs (rip_caldir_prefetch_refpix)
+    struct K0Work {
+        DevBuf<uint32_t> hist, k0_ticket;
+        DevBuf<SelState> sel;
+        DevBuf<float> rowA, rowB, gmed;
+        DevBuf<double> rowcorr, chan_m, chan_c, chan_line;
+        cudaEvent_t ev_k0 = nullptr;    // statistics complete (recorded on the side stream)
+        cudaEvent_t ev_used = nullptr;  // last fused kernel that read this set has finished
+        bool used_recorded = false;
+        const void* key = nullptr;      // raw cube the set was precomputed for (null: none pending)
+        bool busy = false;              // the side stream has written this set since the user stream last waited for it
+    };
+    K0Work k0w[2];
+    int k0_cur = 0;                     // set read by the most recent fused launch
+    cudaStream_t s_k0 = nullptr;        // high-priority side stream of the look-ahead
     // host-entry workspace
     DevBuf<uint16_t> w_raw, w_amp;
     DevRaw w_area;

@@ -275,6 +275,56 @@ def test_pipeline_matches_synchronous_path():
     assert not np.array_equal(outs[0]["slope"], outs[1]["slope"])
 
 
+def test_refpix_lookahead_matches_in_stream_statistics():
+    """rip_caldir_prefetch_refpix: the reference-pixel statistics of the next device-resident exposure, computed on the
+    handle's side stream beside the current fused kernel, give bitwise the arrays of the in-stream path -- over a rotation
+    of exposures (both workspace sets reused), with a look-ahead that is never consumed, and with one for another cube."""
+    import torch
+
+    from romanimpreprocess_b200 import synth
+    from romanimpreprocess_b200.L1_to_L2 import gen_cal_image as gci
+
+    n, rp = 512, synth.README_PATTERN
+    cal = synth.make_caldir(n=n, seed=52, read_pattern=rp, p_order=10, gain_dtype=np.float32, ipc_dtype=np.float32,
+                            sprinkle_flags=True, biascorr_amp=3.0)  # fmt: skip
+    exposures = [synth.make_l1(cal, rp, seed=80 + k, n_sources=25, cr_frac=0.01, bright=3.0)[:2] for k in range(3)]
+    area = synth.make_area_factor(n, np.float32)
+    cfg = {"SLICEOUT": True}
+    dev = torch.device("cuda", 0)
+    with gci.CalDir(cal) as cd:
+        ref = [gci.calibrate_arrays(cd, d, a, rp, 3.04, area, cfg) for d, a in exposures]
+        dplan = gci.DevicePlan(cd, rp, 3.04, cfg, do_refpix=True, area_dtype=np.float32)
+        d_raw = [torch.from_numpy(d.view(np.int16)).to(dev) for d, _ in exposures]
+        d_amp = [torch.from_numpy(a.view(np.int16)).to(dev) for _, a in exposures]
+        d_area = torch.from_numpy(area).to(dev)
+        outs = [{"slope": torch.empty((n, n), dtype=torch.float32, device=dev),
+                 "err_read": torch.empty((n, n), dtype=torch.float32, device=dev),
+                 "err_poisson": torch.empty((n, n), dtype=torch.float32, device=dev),
+                 "pdq": torch.empty((n, n), dtype=torch.int32, device=dev)} for _ in range(7)]  # fmt: skip
+        torch.cuda.synchronize()
+        stream = torch.cuda.current_stream().cuda_stream
+        order = [0, 1, 2, 0, 1, 2, 0]
+        for i, k in enumerate(order):
+            o = outs[i]
+            gci.calibrate_device(cd, dplan, d_raw[k].data_ptr(), d_amp[k].data_ptr(), d_area.data_ptr(),
+                                 o["slope"].data_ptr(), o["err_read"].data_ptr(), o["err_poisson"].data_ptr(),
+                                 o["pdq"].data_ptr(), stream=stream)  # fmt: skip
+            if i == 3:    # a look-ahead for a cube that is NOT the next one: must be ignored, not used
+                gci.prefetch_refpix_device(cd, d_raw[0].data_ptr(), d_amp[0].data_ptr(), len(rp))
+            elif i == 4:  # two look-aheads in a row, the second one is the right one
+                gci.prefetch_refpix_device(cd, d_raw[1].data_ptr(), d_amp[1].data_ptr(), len(rp))
+                gci.prefetch_refpix_device(cd, d_raw[2].data_ptr(), d_amp[2].data_ptr(), len(rp))
+            elif i + 1 < len(order):
+                k1 = order[i + 1]
+                gci.prefetch_refpix_device(cd, d_raw[k1].data_ptr(), d_amp[k1].data_ptr(), len(rp))
+        torch.cuda.synchronize()
+        for i, k in enumerate(order):
+            for name in ("slope", "err_read", "err_poisson"):
+                assert np.array_equal(outs[i][name].cpu().numpy(), ref[k][name], equal_nan=True), (i, name)
+            assert np.array_equal(outs[i]["pdq"].cpu().numpy().view(np.uint32), ref[k]["pdq"]), i
+    assert not np.array_equal(ref[0]["slope"], ref[1]["slope"], equal_nan=True)
+
+
 def test_sky_step_after_the_hot_path():
     """calibrate_arrays(sky_step=True): slope_withsky + SKYORDER medfit subtraction (reference gen_cal_image.py:639-651)
     == the oracle's medfit (pinned to the reference's) applied to the oracle's slope (model within one float32 ulp: the
