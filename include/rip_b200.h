@@ -403,12 +403,16 @@ int rip_poisson_resample_dev(rip_caldir* h, const float* d_skylevel, const int8_
 /* Noise directive "O" (L1_to_L2/gen_noise_image.py:173-227 -> GalPoisson/draw_with_tilnus.py:12, find_tilnus.py:46):
  * d_diff f32 [na,na] += Pearson draw / clip(gain, 1e-4, 1e4) with I = max(gain * d_withsky, 0.01) and the moments
  * tilnu[i] = (nu21, nu31, nu41) [e/s units] of the ramp ending at group i = (endslice > 0 ? endslice : G-1); rows with
- * defined[i] == 0 and i <= start draw nothing.  Pearson Types I (Beta) and VI (beta prime) are generated on the device;
- * pixels that fall into Type IV or exactly onto the Type III / V lines are counted in *d_unsupported (device int32,
- * zeroed by the caller) and draw 0. */
+ * defined[i] == 0 and i <= start draw nothing.  All types the reference dispatches are generated on the device: I (Beta),
+ * VI (beta prime), IV (Devroye's log-concave rejection in the angle, Heinrich 2004), and on the exact III / V lines the
+ * Gamma / inverse Gamma.  Pixels whose parameters are invalid (where the reference raises ValueError) are counted in
+ * *d_unsupported (device int32, zeroed by the caller) and draw 0. */
 int rip_pearson_noise_dev(rip_caldir* h, const float* d_withsky, const int8_t* d_endslice, int G, int start,
                           const double* tilnu, const uint8_t* defined, uint64_t seed, float* d_diff,
                           int32_t* d_unsupported, void* stream);
+/* log k(m, nu) of the Pearson IV density in the angle (Heinrich 2004; GalPoisson/draw_with_tilnus.py:296-306 with a = 1),
+ * as the Type IV sampler of rip_pearson_noise_dev evaluates it (complex log-gamma by recurrence + Stirling): test hook. */
+double rip_pearson4_logk_host(double m, double nu);
 
 /* ---- pixel area from the WCS (utils/coordutils.py:17-82 pixelarea, used at L1_to_L2/gen_cal_image.py:618-622 with the
  * FITSWCS header of :82-83).  wcs = 211 doubles describing a zenithal FITS WCS with SIP:

@@ -18,9 +18,10 @@ the sky level propagated through the ramp-fit weights of each pixel's ramp end, 
 ``O`` (pseudo-Poisson draws from the Pearson family with the moments of the ramp-fitted Poisson noise, reference
 :173-227 -> ``GalPoisson``; ``rip_pearson_noise_dev``), ``S<order>``, ``C<tag>`` (a label: ignored, as in the reference)
 -- i.e. both production layer families ``Rz4PbrS2C*`` and ``Rz4OS2C*`` (runs/summer2025run/OpenUniverse_to_L1L2.py:124-133).
-``O`` generates Pearson Type I (Beta) deviates, the type every Roman read pattern tried here selects (their nu_41 is
-negative), and Type VI (beta prime); a pixel that falls into Type IV (or exactly onto the Type III / V lines) raises
-``NotImplementedError`` instead of silently drawing nothing.
+``O`` generates every Pearson type the reference dispatches: Type I (Beta; the type every Roman read pattern tried here
+selects, their nu_41 is negative), Type VI (beta prime), Type IV (Devroye's rejection sampler in the angle, exact
+normalisation: one sampler where the reference needs two) and, exactly on their lines, Types III / V; pixels with invalid
+Pearson parameters raise ``ValueError`` as in the reference.
 Random numbers are Philox (the reference: GalSim / NumPy): layers are validated statistically.
 
 ``generate_all_noise(config)`` is the reference's driver (:334-391): layers of ``config["NOISE"]["LAYER"]`` for the exposure
@@ -182,8 +183,8 @@ class NoiseLayers:
                                                  _ptr(self.d_diff), _ptr(bad), st))  # fmt: skip
             nbad = int(bad.item())
             if nbad:
-                raise NotImplementedError(f"noise directive {cmd!r}: {nbad} pixels need Pearson Type IV (or III / V), which are not "
-                                          "generated on the GPU (Types I and VI are; Roman read patterns select Type I)")  # fmt: skip
+                # (reference GalPoisson/draw_with_tilnus.py:565-566: "Some intensities give invalid Pearson-IV parameters.")
+                raise ValueError(f"noise directive {cmd!r}: {nbad} pixels give invalid Pearson parameters")
         if "P" in cmd:
             pflags = _get_subscript(cmd, "P")
             if "orig" not in self.have:

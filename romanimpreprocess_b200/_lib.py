@@ -172,6 +172,7 @@ _SIGS = {
     "rip_order_stats_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_long),
                                       C.c_void_p]),
     "rip_clip_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_long, C.c_float, C.c_float, C.c_void_p]),
+    "rip_pearson4_logk_host": (C.c_double, [C.c_double, C.c_double]),
     "rip_pearson_noise_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rip_poisson_resample_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -1165,6 +1165,52 @@ __device__ inline double beta_draw(Philox& rng, double a, double b) {
     return X / (X + Y);
 }
 
+// Re ln Gamma(x + i y), x > 0: recurrence up to Re z >= 16, then Stirling's series (truncation < 2e-12 there).
+// (GalPoisson/draw_with_tilnus.py:296-306 takes it from scipy.special.loggamma.)
+__host__ __device__ inline double re_lgamma_cplx(double x, double y) {
+    double acc = 0.0;
+    while (x < 16.0) {
+        acc += log(x * x + y * y);  // 2 Re ln z
+        x += 1.0;
+    }
+    const double r2 = x * x + y * y, y2 = y * y, x2 = x * x;
+    const double re1 = x / r2;                                                        // Re z^-1
+    const double re3 = x * (x2 - 3.0 * y2) / (r2 * r2 * r2);                          // Re z^-3
+    const double re5 = x * (x2 * x2 - 10.0 * x2 * y2 + 5.0 * y2 * y2) / (r2 * r2 * r2 * r2 * r2);  // Re z^-5
+    return (x - 0.5) * (0.5 * log(r2)) - y * atan2(y, x) - x + 0.91893853320467274178 + re1 / 12.0 - re3 / 360.0 +
+           re5 / 1260.0 - 0.5 * acc;
+}
+
+// log of the normalisation of the Pearson IV density in the angle t = atan((x - lam) / a):
+// g(t) = k cos(t)^(2m-2) exp(-nu t), k = 2^(2m-2) |Gamma(m + i nu/2)|^2 / (pi Gamma(2m-1))   (Heinrich 2004, eq. 6-8)
+__host__ __device__ inline double pearson4_logk(double m, double nu) {
+    return (2.0 * m - 2.0) * 0.69314718055994530942 + 2.0 * re_lgamma_cplx(m, 0.5 * nu) - 1.14472988584940017414 - lgamma(2.0 * m - 1.0);
+}
+
+// One Pearson IV deviate, f(x) ~ (1 + xi^2)^-m exp(-nu atan xi), xi = (x - lam) / a, m > 1: Devroye's rejection method
+// for log-concave densities applied to the angle (Heinrich 2004, section 7; the sampler of the reference's
+// pt4_rvs_devroye, GalPoisson/draw_with_tilnus.py:444-483).  The hat needs rc = 1 / g(mode); the reference's rc carries a
+// factor `a` on top (its log k is the x-space constant): its hat still dominates for a >= 1 (same distribution, low
+// acceptance -- the reason it switches to a second sampler) and does not for a < 1.  Here rc is the exact one:
+// acceptance >= 1/4 for every (m, nu), one sampler.
+__device__ inline double pearson4_draw(Philox& rng, double m, double nu, double a, double lam) {
+    const double b = 2.0 * m - 2.0;
+    const double M = atan2(-nu, b);
+    const double r_const = b * log(b / hypot(b, nu)) - nu * M;
+    const double rc = exp(-r_const - pearson4_logk(m, nu));
+    for (int it = 0; it < 512; ++it) {
+        double x = 4.0 * rng.uniform53(), z = 0.0;
+        bool right = false;
+        if (x > 2.0) { x -= 2.0; right = true; }
+        if (x > 1.0) { z = log(x - 1.0); x = 1.0 - z; }
+        x = right ? M + rc * x : M - rc * x;
+        if (!(fabs(x) < 1.57079632679489661923)) continue;
+        if (z + log(rng.uniform53()) > b * log(cos(x)) - nu * x - r_const) continue;
+        return a * tan(x) + lam;
+    }
+    return a * tan(M) + lam;  // (not reached: 512 rejections in a row have probability < 1e-60)
+}
+
 struct PearsonArgs {
     int n, nb, G, start;
     double nu21[RIP_GMAX], nu31[RIP_GMAX], nu41[RIP_GMAX];
@@ -1212,7 +1258,39 @@ __global__ void pearson_noise_kernel(const PearsonArgs A, const float* __restric
             diff[p] = (float)((TP)diff[p] + (TP)(float)draw / g);
             return;
         }
-        if (b2 == rhs1 || b2 == rhs2 || (b2 > rhs2 && b1 < 32.0)) atomicAdd(unsupported, 1);  // III, V, IV
+        const double sgn = (n31 >= 0.0) ? 1.0 : -1.0;
+        double draw;
+        if (b2 == rhs1) {
+            // Type III = shifted / scaled Gamma (:256-281; its sign is that of nu31 with 0 counted as negative)
+            const double sc = fabs(n31) / (2.0 * n21), shape = 4.0 * n21 * n21 * n21 * I / (n31 * n31);
+            if (!(shape > 0.0) || !(sc == sc)) { atomicAdd(unsupported, 1); return; }
+            Philox rng;
+            rng.init(A.seed, (uint64_t)p, 160u);
+            draw = ((n31 > 0.0) ? 1.0 : -1.0) * (sc * gamma_draw(rng, shape) - shape * sc);
+        } else if (b2 == rhs2) {
+            // Type V = shifted inverse Gamma (:601-668): y = beta / Gamma(alpha)
+            const double st = sqrt(4.0 + b1);
+            const double pp = 4.0 * (1.0 + 2.0 / b1 + st / b1), pm = 4.0 * (1.0 + 2.0 / b1 - st / b1);
+            const double pq = pp > 4.0 ? pp : pm;
+            const double be = sqrt(n21 * I) * (pq - 2.0) * sqrt(pq - 3.0), al = pq - 1.0;
+            if (!(al > 1.0) || !(be > 0.0)) { atomicAdd(unsupported, 1); return; }
+            Philox rng;
+            rng.init(A.seed, (uint64_t)p, 160u);
+            draw = sgn * (be / gamma_draw(rng, al) - be / (al - 1.0));
+        } else if (b2 > rhs2 && b1 < 32.0) {
+            // Type IV (:535-598)
+            const double r = 6.0 * (b2 - b1 - 1.0) / (2.0 * b2 - 3.0 * b1 - 6.0);
+            const double inner = 16.0 * (r - 1.0) - b1 * (r - 2.0) * (r - 2.0);
+            if (!(r > 1.0) || !(inner > 0.0)) { atomicAdd(unsupported, 1); return; }  // the reference raises ValueError here
+            const double nu = -sgn * (r * (r - 2.0) * sqrt(b1) / sqrt(inner));  // sign(mu_3) = -sign(nu)
+            const double a4 = sqrt(n21 * I * inner) / 4.0, m4 = r / 2.0 + 1.0;
+            Philox rng;
+            rng.init(A.seed, (uint64_t)p, 160u);
+            draw = pearson4_draw(rng, m4, nu, a4, a4 * nu / (2.0 * (m4 - 1.0)));
+        } else {
+            return;  // (beta_1 >= 32 above the Type V line: no type in the reference either, the pixel stays 0)
+        }
+        diff[p] = (float)((TP)diff[p] + (TP)(float)draw / g);
         return;
     }
     // Type I: u = a + b, v = (a - b)^2 / (a b)
@@ -1234,7 +1312,8 @@ __global__ void pearson_noise_kernel(const PearsonArgs A, const float* __restric
 }  // namespace rip
 
 // tilnu: [G][3] = (nu21, nu31, nu41) in e/s units of the ramp ending at group i (rows with defined[i] == 0 are skipped);
-// d_unsupported: device int counter of pixels whose Pearson type is not I (the caller zeroes it and reads it back)
+// d_unsupported: device int counter of pixels whose Pearson parameters are invalid (Type IV with r <= 1 or a non-positive
+// discriminant, where the reference raises ValueError; Type VI / III / V with non-positive shapes); the caller zeroes it
 extern "C" int rip_pearson_noise_dev(rip_caldir* h, const float* d_withsky, const int8_t* d_endslice, int G, int start,
                                      const double* tilnu, const uint8_t* defined, uint64_t seed, float* d_diff,
                                      int32_t* d_unsupported, void* stream) {
@@ -1256,6 +1335,8 @@ extern "C" int rip_pearson_noise_dev(rip_caldir* h, const float* d_withsky, cons
         RIP_LAUNCH(pearson_noise_kernel<float>, grid, 128, 0, (cudaStream_t)stream, A, d_withsky, (const float*)h->gain.p, d_endslice, d_diff, (int*)d_unsupported);
     RIP_API_END
 }
+
+extern "C" double rip_pearson4_logk_host(double m, double nu) { return rip::pearson4_logk(m, nu); }
 
 extern "C" int rip_poisson_resample_dev(rip_caldir* h, const float* d_skylevel, const int8_t* d_endslice, int G, int n_samp,
                                         const int32_t* group_of_read, const float* weights /*[G][G] row es*/,

@@ -541,7 +541,7 @@ def test_noise_layer_pearson_directive_moments():
     """Directive 'O' (reference gen_noise_image.py:173-227, GalPoisson/draw_with_tilnus.py): the draws have the moments
     the Pearson family is solved for -- variance nu21 I, third central moment nu31 I, fourth 3 nu21^2 I^2 + nu41 I (in
     electrons; the layer is draw / gain) -- for ramps ending at two different groups, and 0 where the admissibility test
-    of the reference fails; a pattern / weight combination that needs another Pearson type raises."""
+    of the reference fails; Types VI and IV for positive nu41."""
     import torch
 
     from romanimpreprocess_b200 import _lib, synth
@@ -623,11 +623,38 @@ def test_noise_layer_pearson_directive_moments():
             assert abs(x.mean()) < 5 * np.sqrt(m2 / N) and abs(x.var() / m2 - 1) < 6 * np.sqrt((b2 - 1) / N) + 1e-3, (v, x.mean(), x.var(), m2)
             sk_hat = np.mean((x - x.mean()) ** 3) / x.var() ** 1.5
             assert abs(sk_hat - m3 / m2**1.5) < 6 * np.sqrt(6.0 / N) + 0.08 * abs(m3 / m2**1.5), (v, sk_hat, m3 / m2**1.5)
-        # a positive nu41 large enough to reach the Type IV region is reported, not silently zeroed
-        tab_bad = tab.copy()
-        tab_bad[:, 2] = np.abs(tab_bad[:, 2]) * 50.0
-        _, nbad = run(7, tab_bad)
-        assert nbad > 0
+        # Type IV: a large positive nu41 puts every intensity above the Type V line, with m from 2.5 (fourth moment barely
+        # finite) to 4e4 (nearly Gaussian).  The draws follow the Pearson IV law the reference solves for
+        # (GalPoisson/draw_with_tilnus.py:535-598): Kolmogorov-Smirnov distance to the numerically integrated CDF.
+        tab4 = tab.copy()
+        tab4[:, 2] = np.abs(tab4[:, 2]) * 5.0
+        e4, nbad = run(7, tab4)
+        assert nbad == 0 and np.all(np.isfinite(e4))
+        th = np.linspace(-np.pi / 2, np.pi / 2, 800001)[1:-1]
+        ms = []
+        for half, row in ((np.s_[:, : na // 2], G - 1), (np.s_[:, na // 2 :], 2)):
+            n21, n31, n41 = tab4[row]
+            for k, v in enumerate(levels):
+                Iv = max(v, 0.01)
+                x = np.sort(e4[half][k * band + 1 : (k + 1) * band - 1].ravel())
+                b1, b2 = n31**2 / (n21**3 * Iv), (3 * n21**2 * Iv + n41) / (n21**2 * Iv)
+                assert b2 > (48 + 39 * b1 + 6 * (4 + b1) ** 1.5) / (32 - b1) and b1 < 32  # the case is Type IV
+                r = 6 * (b2 - b1 - 1) / (2 * b2 - 3 * b1 - 6)
+                inner = 16 * (r - 1) - b1 * (r - 2) ** 2
+                nu = (-1.0 if n31 >= 0 else 1.0) * r * (r - 2) * np.sqrt(b1) / np.sqrt(inner)
+                a, m = np.sqrt(n21 * Iv * inner) / 4, r / 2 + 1
+                lam = a * nu / (2 * (m - 1))
+                ms.append(m)
+                logg = (2 * m - 2) * np.log(np.cos(th)) - nu * th
+                c = np.cumsum(np.exp(logg - logg.max()))
+                F = np.interp(np.arctan((x - lam) / a), th, c / c[-1])
+                N = x.size
+                ks = np.max(np.abs(F - (np.arange(N) + 0.5) / N))
+                assert ks < 1.95 / np.sqrt(N) + 2e-3, (row, v, m, nu, ks)  # (float32 layer / gain round trip: 2e-3)
+                if m > 10:  # moments converge: variance nu21 I, and the skew has the sign of nu31
+                    assert abs(x.var() / (n21 * Iv) - 1) < 6 * np.sqrt((b2 - 1) / N) + 1e-3, (row, v, x.var(), n21 * Iv)
+                    assert abs(x.mean()) < 5 * np.sqrt(n21 * Iv / N)
+        assert min(ms) < 2.6 and max(ms) > 1e4
 
 
 def test_generate_all_noise_driver(tmp_path):

@@ -61,3 +61,23 @@ def test_tilde_nus_against_the_reference_golden():
         for j in range(3):
             t = gni.tilde_nus(getattr(synth, name), g[f"{name}_w{j}"])
             np.testing.assert_allclose(t, g[f"{name}_t{j}"][:3], rtol=1e-13, atol=0)
+
+
+def test_pearson4_normalisation_against_scipy():
+    """log k(m, nu) of the Pearson IV density (reference GalPoisson/draw_with_tilnus.py:296-306, there through
+    scipy.special.loggamma of a complex argument) as the library evaluates it for the Type IV sampler (recurrence +
+    Stirling series): 1e-8 relative over m - 1 = 1e-3 .. 1e6, |nu| = 1e-4 .. 1e6."""
+    import math
+
+    from scipy.special import loggamma
+
+    from romanimpreprocess_b200 import _lib
+
+    lib = _lib.lib()
+    rng = np.random.default_rng(1)
+    for _ in range(4000):
+        m = 1.0 + 10 ** rng.uniform(-3, 6)
+        nu = rng.choice([-1.0, 1.0]) * 10 ** rng.uniform(-4, 6)
+        ref = (2 * m - 2) * math.log(2) + 2 * loggamma(m + 0.5j * nu).real - (math.log(math.pi) + loggamma(2 * m - 1).real)
+        got = lib.rip_pearson4_logk_host(m, nu)
+        assert abs(got - ref) <= 1e-8 * max(1.0, abs(ref)), (m, nu, ref, got)
