@@ -214,7 +214,7 @@ int rip_l1_to_l2_dev(rip_caldir* h, const uint16_t* d_raw, const uint16_t* d_amp
                      const rip_l1l2_params* prm, const rip_ramp_plan* plan, const double* w_exact,
                      const rip_l2_out* d_out, void* stream);
 /* Look-ahead of the reference-pixel statistics (the "K0" kernels: utils/reference_subtraction_util.py:14-136 restated)
- * for the NEXT exposure of a device-resident stream: computed on a high-priority side stream of the handle into the
+ * for the NEXT exposure of a device-resident stream: computed on a low-priority side stream of the handle into the
  * second of two workspace sets while the fused kernel of the current exposure runs.  If the rip_l1_to_l2_dev call that
  * FOLLOWS names the same d_raw, it waits for that result instead of running the statistics itself (identical results:
  * same kernels, same inputs); any other call in between discards the look-ahead.  Call it AFTER the rip_l1_to_l2_dev of

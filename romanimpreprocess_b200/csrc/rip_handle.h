@@ -42,7 +42,7 @@ struct rip_caldir {
     };
     K0Work k0w[2];
     int k0_cur = 0;                     // set read by the most recent fused launch
-    cudaStream_t s_k0 = nullptr;        // high-priority side stream of the look-ahead
+    cudaStream_t s_k0 = nullptr;        // low-priority side stream of the look-ahead
     // host-entry workspace
     DevBuf<uint16_t> w_raw, w_amp;
     DevRaw w_area;
