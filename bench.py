@@ -724,11 +724,17 @@ def run_exposure18(args):
     o_end = torch.empty((na, na), dtype=torch.int8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
+    lookahead = not args.no_refpix_lookahead
+
     def resident_pass():
         for k, (e, sca) in enumerate(drv.items):
             gci.calibrate_device(drv.cals[sca], drv.pipes[sca].dplan, d_raw[k % 2].data_ptr(), d_amp[k % 2].data_ptr(),
                                  d_area.data_ptr(), o_slope.data_ptr(), o_er.data_ptr(), o_ep.data_ptr(), o_pdq.data_ptr(),
                                  d_endslice=o_end.data_ptr(), stream=stream)  # fmt: skip
+            if lookahead:  # reference-pixel statistics of the next item (on ITS CalDir handle) beside this fused kernel
+                kn = (k + 1) % len(drv.items)
+                sca1 = drv.items[kn][1]
+                gci.prefetch_refpix_device(drv.cals[sca1], d_raw[kn % 2].data_ptr(), d_amp[kn % 2].data_ptr(), G)
 
     def barrier():
         torch.cuda.synchronize()
@@ -797,7 +803,8 @@ def run_exposure18(args):
             "ms_per_step": ms_pass, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (one CALDIR content uploaded as 18 separate resident handles; 2 exposure cubes rotated)",
             "secondary_workload": True,
-            "config": {"workload": f"exposure18: {E} exposures x 18 SCAs = {len(items)} (exposure, SCA) items per pass, dealt by "
+            "config": {"refpix_lookahead": bool(lookahead),
+                       "workload": f"exposure18: {E} exposures x 18 SCAs = {len(items)} (exposure, SCA) items per pass, dealt by "
                                    "sharding.assign_items_balanced; one resident CALDIR handle + pipeline per SCA of a rank",
                        "items_per_rank": [int(c) for c in counts.tolist()], "resident_caldirs_per_rank": [int(c) for c in nres.tolist()],
                        "imbalance_max_over_mean": float(counts.max().item() / counts.mean().item()),
