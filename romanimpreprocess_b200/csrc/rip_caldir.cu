@@ -735,6 +735,7 @@ extern "C" int rip_refpix_stats_host(rip_caldir* h, const uint16_t* raw, const u
     rip_caldir::K0Work& W0 = h->k0w[0];
     W0.key = nullptr;
     W0.busy = false;
+    if (W0.used_recorded) RIP_CUDA(cudaStreamWaitEvent(st, W0.ev_used, 0));  // a fused kernel on a caller's stream may still read it
     run_k0(h, W0, h->w_raw.p, h->w_amp.p, G, st);
     if (rowcorr) W0.rowcorr.download(rowcorr, (size_t)G * n, st);
     if (chan_m) W0.chan_m.download(chan_m, (size_t)G * 32, st);
