@@ -341,19 +341,56 @@ RIP_HD void row_async(const Args& A, SM& sm, const Regs<G, P>& R, int row, int r
 // ptxas spill 176 bytes and scatter scoreboard waits through the step): the records are padded with PADR zero rows on both sides, so rows
 // outside the frame are loaded but never used (a conditional load would keep the old register contents live
 // around the whole loop).
+// 128-bit load of a record word.  Every word is read once per launch by exactly one thread, so it is loaded without an
+// L1 allocation (SASS LDG.E.NA.128.CONSTANT): with the shared-memory carve-out at its maximum only ~28 KB of L1 remain
+// per SM, which the 24 KB of records per CTA and step would otherwise sweep -- evicting the 32-byte stack frames and
+// the uniform float64 tables of the cold paths.  Measured: 1.329 -> 1.297 ms (profiles/r02/ab_rec_no_l1.log).
+RIP_HD f4 ld_rec(const f4* p) {
+#if defined(__CUDA_ARCH__)
+    f4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+RIP_HD float ld_rec1(const float* p) {
+#if defined(__CUDA_ARCH__)
+    float v;
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+// the L2 planes are written once and never read back by the kernel: streaming stores (evict-first)
+RIP_HD void st_out(float* p, float v) {
+#if defined(__CUDA_ARCH__)
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+RIP_HD void st_out(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 template <int G, int P>
 RIP_HD void load_a1(const Args& A, Regs<G, P>& R, int row, int tile, int tid) {
     const f4* p = A.rec1 + ((long)row * A.ntile + tile) * (Regs<G, P>::NQ1 * TW);
 #pragma unroll
-    for (int q = 0; q < Regs<G, P>::NQ1; ++q) R.r1[q] = p[q * TW + tid];
+    for (int q = 0; q < Regs<G, P>::NQ1; ++q) R.r1[q] = ld_rec(p + q * TW + tid);
 }
 template <int G, int P>
 RIP_HD void load_bn(const Args& A, Regs<G, P>& R, int row, int tile, int tid, unsigned dep) {
     // dep: a run-time zero derived from a register of the loads in flight (see step): the address depends on it, so
     // these loads cannot be issued before the step's single scoreboard wait
     const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW) + dep;
-    R.kbn[0] = p[tid];
-    R.kbn[1] = p[TW + tid];
+    R.kbn[0] = ld_rec(p + tid);
+    R.kbn[1] = ld_rec(p + TW + tid);
     R.kbn8 = ((const float*)(p + 2 * TW))[4 * tid];  // .x of the third word
 }
 RIP_HD double f2_as_double(float lo, float hi) {
@@ -368,7 +405,7 @@ RIP_HD void load_bn64(const Args& A, Regs<G, P>& R, int row, int tile, int tid, 
     const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ64 * TW) + dep;
     f4 w[5];
 #pragma unroll
-    for (int q = 0; q < 5; ++q) w[q] = p[q * TW + tid];
+    for (int q = 0; q < 5; ++q) w[q] = ld_rec(p + q * TW + tid);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         R.kbnd[2 * q] = f2_as_double(w[q].x, w[q].y);
@@ -380,7 +417,7 @@ template <int G, int P>
 RIP_HD void load_c64(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int x, bool xin) {
     const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ64 * TW);
 #pragma unroll
-    for (int q = 0; q < KQ64; ++q) R.kc64[q] = p[q * TW + tid];
+    for (int q = 0; q < KQ64; ++q) R.kc64[q] = ld_rec(p + q * TW + tid);
     if (A.area) {
         const int rr = row < 0 ? 0 : (row >= A.n ? A.n - 1 : row);
         const unsigned o = (unsigned)rr * (unsigned)A.n + (unsigned)(xin ? x : 0);
@@ -393,7 +430,7 @@ template <int G, int P>
 RIP_HD void load_c(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int x, bool xin) {
     const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW);
 #pragma unroll
-    for (int q = 0; q < KQ; ++q) R.kc[q] = p[q * TW + tid];
+    for (int q = 0; q < KQ; ++q) R.kc[q] = ld_rec(p + q * TW + tid);
     if (A.area) {
         const int rr = row < 0 ? 0 : (row >= A.n ? A.n - 1 : row);
         const unsigned o = (unsigned)rr * (unsigned)A.n + (unsigned)(xin ? x : 0);
@@ -1058,10 +1095,10 @@ RIP_HD void stage_c_tail(const Args& A, const RampPlanDev& pl, const FastTab& ft
         else fa = fa / area32;
     }
     l2_epilogue(r, active, dsl, fa);
-    A.slope[p] = r.slope;
-    A.err_read[p] = r.err_read;
-    A.err_poisson[p] = r.err_poisson;
-    A.pdq[p] = pdq;
+    st_out(A.slope + p, r.slope);
+    st_out(A.err_read + p, r.err_read);
+    st_out(A.err_poisson + p, r.err_poisson);
+    st_out(A.pdq + p, pdq);
     if (A.endslice && active) {
         // group where SATURATED first appears, minus one (gen_cal_image.py:703-708: the last 0->1 transition wins)
         const uint32_t tr = gf.sat & ~(gf.sat << 1) & ~1u & allg;
@@ -1431,9 +1468,9 @@ RIP_HD void prefetch_raw(const Args& A, int row, int tile, int tid, int lo, int 
 template <int G, int P>
 RIP_HD void load_b6(const Args& A, Regs<G, P>& R, int row, int tile, int tid) {
     const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW);
-    R.kb[0] = p[tid];
-    R.kb[1] = p[TW + tid];
-    R.kb8 = ((const float*)(p + 2 * TW))[4 * tid];
+    R.kb[0] = ld_rec(p + tid);
+    R.kb[1] = ld_rec(p + TW + tid);
+    R.kb8 = ld_rec1((const float*)(p + 2 * TW) + 4 * tid);
 }
 
 // Split-phase CTA barrier on an mbarrier (count = TW): arrive where the thread's contribution is published, wait where
@@ -1479,7 +1516,7 @@ RIP_HD void load_b6_64(const Args& A, Regs<G, P>& R, int row, int tile, int tid)
     const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ64 * TW);
     f4 w[5];
 #pragma unroll
-    for (int q = 0; q < 5; ++q) w[q] = p[q * TW + tid];
+    for (int q = 0; q < 5; ++q) w[q] = ld_rec(p + q * TW + tid);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         R.kbd[2 * q] = f2_as_double(w[q].x, w[q].y);
