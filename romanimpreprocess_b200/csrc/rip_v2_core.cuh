@@ -345,8 +345,11 @@ RIP_HD void row_async(const Args& A, SM& sm, const Regs<G, P>& R, int row, int r
 // L1 allocation (SASS LDG.E.NA.128.CONSTANT): with the shared-memory carve-out at its maximum only ~28 KB of L1 remain
 // per SM, which the 24 KB of records per CTA and step would otherwise sweep -- evicting the 32-byte stack frames and
 // the uniform float64 tables of the cold paths.  Measured: 1.329 -> 1.297 ms (profiles/r02/ab_rec_no_l1.log).
+// (G = 16: the v2 organisation with its smaller carve-out measured 1.7 % slower with it -- plain loads there.)
+template <int G>
 RIP_HD f4 ld_rec(const f4* p) {
 #if defined(__CUDA_ARCH__)
+    if (G > 8) return *p;
     f4 v;
     asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
@@ -382,15 +385,15 @@ template <int G, int P>
 RIP_HD void load_a1(const Args& A, Regs<G, P>& R, int row, int tile, int tid) {
     const f4* p = A.rec1 + ((long)row * A.ntile + tile) * (Regs<G, P>::NQ1 * TW);
 #pragma unroll
-    for (int q = 0; q < Regs<G, P>::NQ1; ++q) R.r1[q] = ld_rec(p + q * TW + tid);
+    for (int q = 0; q < Regs<G, P>::NQ1; ++q) R.r1[q] = ld_rec<G>(p + q * TW + tid);
 }
 template <int G, int P>
 RIP_HD void load_bn(const Args& A, Regs<G, P>& R, int row, int tile, int tid, unsigned dep) {
     // dep: a run-time zero derived from a register of the loads in flight (see step): the address depends on it, so
     // these loads cannot be issued before the step's single scoreboard wait
     const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW) + dep;
-    R.kbn[0] = ld_rec(p + tid);
-    R.kbn[1] = ld_rec(p + TW + tid);
+    R.kbn[0] = ld_rec<G>(p + tid);
+    R.kbn[1] = ld_rec<G>(p + TW + tid);
     R.kbn8 = ((const float*)(p + 2 * TW))[4 * tid];  // .x of the third word
 }
 RIP_HD double f2_as_double(float lo, float hi) {
@@ -405,7 +408,7 @@ RIP_HD void load_bn64(const Args& A, Regs<G, P>& R, int row, int tile, int tid, 
     const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ64 * TW) + dep;
     f4 w[5];
 #pragma unroll
-    for (int q = 0; q < 5; ++q) w[q] = ld_rec(p + q * TW + tid);
+    for (int q = 0; q < 5; ++q) w[q] = ld_rec<G>(p + q * TW + tid);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         R.kbnd[2 * q] = f2_as_double(w[q].x, w[q].y);
@@ -417,7 +420,7 @@ template <int G, int P>
 RIP_HD void load_c64(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int x, bool xin) {
     const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ64 * TW);
 #pragma unroll
-    for (int q = 0; q < KQ64; ++q) R.kc64[q] = ld_rec(p + q * TW + tid);
+    for (int q = 0; q < KQ64; ++q) R.kc64[q] = ld_rec<G>(p + q * TW + tid);
     if (A.area) {
         const int rr = row < 0 ? 0 : (row >= A.n ? A.n - 1 : row);
         const unsigned o = (unsigned)rr * (unsigned)A.n + (unsigned)(xin ? x : 0);
@@ -430,7 +433,7 @@ template <int G, int P>
 RIP_HD void load_c(const Args& A, Regs<G, P>& R, int row, int tile, int tid, int x, bool xin) {
     const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW);
 #pragma unroll
-    for (int q = 0; q < KQ; ++q) R.kc[q] = ld_rec(p + q * TW + tid);
+    for (int q = 0; q < KQ; ++q) R.kc[q] = ld_rec<G>(p + q * TW + tid);
     if (A.area) {
         const int rr = row < 0 ? 0 : (row >= A.n ? A.n - 1 : row);
         const unsigned o = (unsigned)rr * (unsigned)A.n + (unsigned)(xin ? x : 0);
@@ -1468,8 +1471,8 @@ RIP_HD void prefetch_raw(const Args& A, int row, int tile, int tid, int lo, int 
 template <int G, int P>
 RIP_HD void load_b6(const Args& A, Regs<G, P>& R, int row, int tile, int tid) {
     const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ * TW);
-    R.kb[0] = ld_rec(p + tid);
-    R.kb[1] = ld_rec(p + TW + tid);
+    R.kb[0] = ld_rec<G>(p + tid);
+    R.kb[1] = ld_rec<G>(p + TW + tid);
     R.kb8 = ld_rec1((const float*)(p + 2 * TW) + 4 * tid);
 }
 
@@ -1516,7 +1519,7 @@ RIP_HD void load_b6_64(const Args& A, Regs<G, P>& R, int row, int tile, int tid)
     const f4* p = A.recK + ((long)row * A.ntile + tile) * (KQ64 * TW);
     f4 w[5];
 #pragma unroll
-    for (int q = 0; q < 5; ++q) w[q] = ld_rec(p + q * TW + tid);
+    for (int q = 0; q < 5; ++q) w[q] = ld_rec<G>(p + q * TW + tid);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         R.kbd[2 * q] = f2_as_double(w[q].x, w[q].y);
