@@ -81,3 +81,41 @@ def test_pearson4_normalisation_against_scipy():
         ref = (2 * m - 2) * math.log(2) + 2 * loggamma(m + 0.5j * nu).real - (math.log(math.pi) + loggamma(2 * m - 1).real)
         got = lib.rip_pearson4_logk_host(m, nu)
         assert abs(got - ref) <= 1e-8 * max(1.0, abs(ref)), (m, nu, ref, got)
+
+
+def test_pearson4_devroye_sampler_host_emulation():
+    """The Type IV sampler of rip_pearson_noise_dev (csrc/rip_sim.cu pearson4_draw: Devroye's rejection method for
+    log-concave densities on the angle, Heinrich 2004 section 7, as the reference's pt4_rvs_devroye,
+    GalPoisson/draw_with_tilnus.py:444-483, but with the exact hat constant rc = 1 / g(mode)) restated with NumPy around the
+    library's own log k: the accepted draws follow the Pearson IV law (Kolmogorov-Smirnov against the integrated density)
+    and at least a quarter of the proposals are accepted for every (m, nu) -- the bound of the method when rc is exact."""
+    from romanimpreprocess_b200 import _lib
+
+    lib = _lib.lib()
+    rng = np.random.default_rng(7)
+    th = np.linspace(-np.pi / 2, np.pi / 2, 400001)[1:-1]
+    for m, nu in ((2.51, 0.13), (2.75, -0.14), (6.7, 0.23), (44.4, -1.77), (421.6, 17.1), (41917.0, -1707.0)):
+        b = 2 * m - 2
+        M = np.arctan2(-nu, b)
+        r_const = b * np.log(b / np.hypot(b, nu)) - nu * M
+        rc = np.exp(-r_const - lib.rip_pearson4_logk_host(m, nu))
+        n = 60000
+        x = 4 * rng.random(n)
+        right = x > 2
+        x = np.where(right, x - 2, x)
+        tail = x > 1
+        with np.errstate(divide="ignore"):
+            z = np.where(tail, np.log(np.where(tail, x - 1, 1.0)), 0.0)
+        x = np.where(tail, 1 - z, x)
+        t = np.where(right, M + rc * x, M - rc * x)
+        inside = np.abs(t) < np.pi / 2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ok = inside & ~(z + np.log(rng.random(n)) > b * np.log(np.cos(np.where(inside, t, 0.0))) - nu * t - r_const)
+        acc = ok.mean()
+        assert acc > 0.24, (m, nu, acc)
+        t = np.sort(t[ok])
+        logg = b * np.log(np.cos(th)) - nu * th
+        c = np.cumsum(np.exp(logg - logg.max()))
+        F = np.interp(t, th, c / c[-1])
+        ks = np.max(np.abs(F - (np.arange(t.size) + 0.5) / t.size))
+        assert ks < 1.95 / np.sqrt(t.size), (m, nu, ks, acc)
